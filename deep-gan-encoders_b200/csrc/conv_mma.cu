@@ -1,0 +1,760 @@
+// conv_mma.cu -- im2col-free implicit-GEMM convolution on tcgen05 tensor cores (sm_100a).
+//
+// Replaces the reference's ATen chains around F.conv2d / F.conv_transpose2d:
+//   ModulateConvBlock.forward   model/stylegan2_generator.py:855-922 (plain :897-904, up :879-895)
+//   BEBlock.forward convs       model/E/E.py:59-62, 72-75, 81-84 ; ln.Conv2d.forward model/utils/lreq.py:126-156
+//
+// Formulation: y = d[n,o] * conv(x * s[n,i], W) -- the style scale is folded into the
+// PRODUCER of x (its epilogue multiplies by the next layer's style), so one shared weight tensor serves the
+// whole batch and the conv is a dense GEMM:  D[pixel, cout] = sum_{tap, cin} A[pixel+tap, cin] * B[tap][cout, cin].
+//
+// Data path per CTA (persistent, one output tile = 16x8 pixels x <=256 output columns):
+//   TMA  : one 18x10-pixel halo patch per K-chunk of channels (ACT layout, 16-byte channel groups -> the
+//          smem image IS the canonical no-swizzle K-major UMMA layout, so all 9 taps are just different
+//          descriptor start addresses into the same patch -- no im2col, no 9x re-read);
+//          one weight slab per (tap, K-chunk).
+//   MMA  : tcgen05.mma kind::f16 (bf16 in, fp32 accumulate in TMEM), M=128, N<=128 per instruction.
+//          planes==2 => split precision: x = xh+xl, w = wh+wl, acc += xh*wh + xh*wl + xl*wh  (bf16x3,
+//          ~2^-16 relative operand error -> meets the 1e-3 parity bar that plain bf16 misses).
+//   TMEM : two accumulator stages so the epilogue of tile i overlaps the mainloop of tile i+1.
+//   EPI  : 4 warps, one TMEM lane (= pixel) per thread: demod, noise, bias, lrelu, residual blend, fused
+//          ToRGB partial sums, next-layer style scale, bf16 hi/lo split, 16/32-byte vector stores.
+#include <stdarg.h>
+
+#include "dge_common.cuh"
+
+namespace dge {
+
+constexpr int TH = 16, TW = 8;            // output tile (pixels); TW=8 -> one UMMA core-matrix row group per tile row
+constexpr int PH = TH + 2, PW = TW + 2;   // halo patch
+constexpr int PATCH_BYTES = PH * PW * 16; // one (channel-group, plane) slab of the patch: 2880 B
+constexpr int MAX_B_SLOTS = 8;
+constexpr int NUM_THREADS = 192;          // warp0: TMA, warp1: MMA + TMEM alloc, warps 2..5: epilogue
+
+struct TapEntry {
+  int16_t a_off;  // patch pixel offset dy*PW+dx of this tap
+  int16_t w_tap;  // tap index into WPK
+  int16_t phase;  // output phase (0 for stride-1 convs, 2*py+px for the transposed conv)
+  int16_t pad;
+};
+
+struct ConvKParams {
+  int N, H, W;             // input dims
+  int dom_h, dom_w;        // tile domain (H,W) or (H+1,W+1) for the transposed conv
+  int tiles_x, tiles_y;
+  int Cin, Cout, P;
+  int kc, nchunks;         // channels per A chunk, number of chunks
+  int ntile, cw, nsub;     // CTA columns, columns per phase, columns per MMA
+  int n_ntiles, np;        // N tiles, phases per CTA tile
+  int planes;
+  int total_tiles;
+  int ntaps;
+  TapEntry taps[9];
+  int a_slot_bytes, b_slot_bytes, b_sub_bytes, b_slots;
+  int tmem_cols;
+  // epilogue
+  const float* demod;
+  const float* noise;
+  long long noise_bstride;
+  const float* noise_w;
+  float noise_scalar;
+  const float* bias;
+  float slope, gain;
+  const float* blend_src;
+  int blend_pool;
+  float blend_a, blend_b;
+  void* out_act;
+  int out_planes;
+  const float* out_scale;
+  float* out_f32b;
+  float* out_nchw;
+  const float* rgb_w;
+  float* rgb_out;
+  float* out_raw_up;
+  // checker kernel only
+  const void* x;
+  const void* wpk;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded spin: a protocol bug traps (visible CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!done && spin > (1u << 26)) {
+      printf("dge conv_mma: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, addr,
+             parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, no-swizzle ("interleaved") shared-memory matrix descriptor:
+//   element (row r, 16-byte k-group j) lives at start + (r/8)*SBO + (r%8)*16 + j*LBO.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  return d;                // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n
+__device__ __forceinline__ uint32_t make_idesc_bf16(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+// epilogues (shared by the tcgen05 kernel and the checker kernel)
+// ---------------------------------------------------------------------------------------------
+struct PixelCtx {
+  int n, y, x;
+  bool valid;
+  float nz;
+};
+
+// pointwise epilogue on 16 consecutive output channels c0..c0+15 of one pixel
+__device__ __forceinline__ void epi_pointwise16(const ConvKParams& p, const PixelCtx& px, int c0, float* v,
+                                                float* rgb) {
+  const int H = p.H, W = p.W, C8 = p.Cout >> 3;
+  if (p.demod) {
+    const float4* d = reinterpret_cast<const float4*>(p.demod + (size_t)px.n * p.Cout + c0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 t = __ldg(d + q);
+      v[4 * q] *= t.x; v[4 * q + 1] *= t.y; v[4 * q + 2] *= t.z; v[4 * q + 3] *= t.w;
+    }
+  }
+  if (p.noise) {
+    if (p.noise_w) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaf(px.nz, __ldg(p.noise_w + c0 + j), v[j]);
+    } else {
+      const float t = px.nz * p.noise_scalar;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] += t;
+    }
+  }
+  if (p.bias) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] += __ldg(p.bias + c0 + j);
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = (v[j] < 0.f ? v[j] * p.slope : v[j]) * p.gain;
+  if (!px.valid) return;
+  if (p.blend_src) {
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      float s[8];
+      const int c8 = (c0 >> 3) + g;
+      if (p.blend_pool) {
+        float t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] = 0.f;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx) {
+            load8_f32b(p.blend_src, f32b_idx32(px.n, c8, 2 * px.y + dy, 2 * px.x + dx, C8, 2 * H, 2 * W), t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] += t[j];
+          }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] *= 0.25f;
+      } else {
+        load8_f32b(p.blend_src, f32b_idx32(px.n, c8, px.y, px.x, C8, H, W), s);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[8 * g + j] = p.blend_a * s[j] + p.blend_b * v[8 * g + j];
+    }
+  }
+  if (p.rgb_w) {
+    const float* w = p.rgb_w + (size_t)px.n * 3 * p.Cout + c0;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      float acc = rgb[ch];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc = fmaf(v[j], __ldg(w + ch * p.Cout + j), acc);
+      rgb[ch] = acc;
+    }
+  }
+  if (p.out_f32b) {
+    store8_f32b(p.out_f32b, f32b_idx32(px.n, c0 >> 3, px.y, px.x, C8, H, W), v);
+    store8_f32b(p.out_f32b, f32b_idx32(px.n, (c0 >> 3) + 1, px.y, px.x, C8, H, W), v + 8);
+  }
+  if (p.out_nchw) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) p.out_nchw[(((size_t)px.n * p.Cout + c0 + j) * H + px.y) * W + px.x] = v[j];
+  }
+  if (p.out_act) {
+    float t[16];
+    if (p.out_scale) {
+      const float* s = p.out_scale + (size_t)px.n * p.Cout + c0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) t[j] = v[j] * __ldg(s + j);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) t[j] = v[j];
+    }
+    store8_act(p.out_act, px.n, c0 >> 3, px.y, px.x, C8, p.out_planes, H, W, t);
+    store8_act(p.out_act, px.n, (c0 >> 3) + 1, px.y, px.x, C8, p.out_planes, H, W, t + 8);
+  }
+}
+
+// raw transposed-conv epilogue: pixel (Y,X) of the (H+1)x(W+1) domain, phase (py,px) -> t[2Y+py][2X+px]
+__device__ __forceinline__ void epi_rawup16(const ConvKParams& p, int n, int Y, int X, bool valid, int phase, int c0,
+                                            const float* v) {
+  const int py = phase >> 1, pxs = phase & 1;
+  const int Ho = 2 * p.H + 1, Wo = 2 * p.W + 1;
+  const int oy = 2 * Y + py, ox = 2 * X + pxs;
+  if (!valid || oy >= Ho || ox >= Wo) return;
+  const int C8 = p.Cout >> 3;
+  store8_f32b(p.out_raw_up, f32b_idx32(n, c0 >> 3, oy, ox, C8, Ho, Wo), v);
+  store8_f32b(p.out_raw_up, f32b_idx32(n, (c0 >> 3) + 1, oy, ox, C8, Ho, Wo), v + 8);
+}
+
+struct TileCoord {
+  int n, y0, x0, nt, p0, co0;
+};
+__device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int tile) {
+  TileCoord t;
+  t.nt = tile % p.n_ntiles;
+  int mt = tile / p.n_ntiles;
+  const int per_img = p.tiles_x * p.tiles_y;
+  t.n = mt / per_img;
+  int r = mt - t.n * per_img;
+  int ty = r / p.tiles_x;
+  t.y0 = ty * TH;
+  t.x0 = (r - ty * p.tiles_x) * TW;
+  const int col0 = t.nt * p.ntile;
+  t.p0 = col0 / p.Cout;
+  t.co0 = col0 - t.p0 * p.Cout;
+  return t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the tcgen05 kernel
+// ---------------------------------------------------------------------------------------------
+template <int EPI>  // 0 = pointwise, 1 = raw up
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ ConvKParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* a_smem = smem;
+  uint8_t* b_smem = a_smem + 2 * p.a_slot_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + p.b_slots * p.b_slot_bytes);
+  uint64_t* a_full = bars;            // [2]
+  uint64_t* a_empty = bars + 2;       // [2]
+  uint64_t* tm_full = bars + 4;       // [2]
+  uint64_t* tm_empty = bars + 6;      // [2]
+  uint64_t* b_full = bars + 8;        // [MAX_B_SLOTS]
+  uint64_t* b_empty = bars + 8 + MAX_B_SLOTS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * MAX_B_SLOTS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+      mbar_init(&tm_full[i], 1);
+      mbar_init(&tm_empty[i], 4);
+    }
+    for (int i = 0; i < p.b_slots; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =================================== TMA producer ===================================
+    if (lane == 0) {
+      const int kc8p = (p.kc >> 3) * p.planes;
+      uint32_t a_it = 0, b_it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        for (int ch = 0; ch < p.nchunks; ++ch) {
+          const uint32_t slot = a_it & 1, ph = (a_it >> 1) & 1;
+          mbar_wait(&a_empty[slot], ph ^ 1);
+          mbar_arrive_expect_tx(&a_full[slot], (uint32_t)p.a_slot_bytes);
+          tma_load_4d(a_smem + slot * p.a_slot_bytes, &tmA, &a_full[slot], 2 * (t.x0 - 1), t.y0 - 1, ch * kc8p, t.n);
+          ++a_it;
+          for (int e = 0; e < p.ntaps; ++e) {
+            const int q = p.taps[e].phase - t.p0;
+            if (q < 0 || q >= p.np) continue;
+            const uint32_t bs = b_it % p.b_slots, bph = (b_it / p.b_slots) & 1;
+            mbar_wait(&b_empty[bs], bph ^ 1);
+            mbar_arrive_expect_tx(&b_full[bs], (uint32_t)p.b_slot_bytes);
+            uint8_t* dst = b_smem + bs * p.b_slot_bytes;
+            for (int s = 0; s * p.nsub < p.cw; ++s)
+              tma_load_3d(dst + s * p.b_sub_bytes, &tmB, &b_full[bs], 2 * (t.co0 + s * p.nsub), ch * kc8p,
+                          p.taps[e].w_tap);
+            ++b_it;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =================================== MMA issuer ======================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(p.nsub);
+      const uint32_t a_lbo = p.planes * PATCH_BYTES, a_sbo = PW * 16;
+      const uint32_t nb = p.nsub * 16;  // bytes of one (k-group, plane) slab of a B sub-block
+      const uint32_t b_lbo = p.planes * nb, b_sbo = 128;
+      uint32_t a_it = 0, b_it = 0, acc_it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        const uint32_t acc = acc_it & 1, acc_ph = (acc_it >> 1) & 1;
+        mbar_wait(&tm_empty[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + acc * p.ntile;
+        uint32_t started = 0;
+        for (int ch = 0; ch < p.nchunks; ++ch) {
+          const uint32_t slot = a_it & 1, ph = (a_it >> 1) & 1;
+          mbar_wait(&a_full[slot], ph);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(a_smem + slot * p.a_slot_bytes);
+          for (int e = 0; e < p.ntaps; ++e) {
+            const int q = p.taps[e].phase - t.p0;
+            if (q < 0 || q >= p.np) continue;
+            const uint32_t bs = b_it % p.b_slots, bph = (b_it / p.b_slots) & 1;
+            mbar_wait(&b_full[bs], bph);
+            tc_fence_after();
+            const uint32_t b_base = smem_u32(b_smem + bs * p.b_slot_bytes);
+            const uint32_t a_tap = a_base + (uint32_t)p.taps[e].a_off * 16;
+            for (int s = 0; s * p.nsub < p.cw; ++s) {
+              const uint32_t d = d_base + q * p.cw + s * p.nsub;
+              const uint32_t sbit = 1u << (q * 2 + s);
+              const uint32_t b_sub = b_base + s * p.b_sub_bytes;
+              for (int k = 0; k < (p.kc >> 4); ++k) {
+                const uint32_t a_hi = a_tap + (2 * k) * a_lbo;
+                const uint32_t b_hi = b_sub + (2 * k) * b_lbo;
+                const uint64_t da_hi = make_smem_desc(a_hi, a_lbo, a_sbo);
+                const uint64_t db_hi = make_smem_desc(b_hi, b_lbo, b_sbo);
+                tc_mma_bf16(d, da_hi, db_hi, idesc, ((started & sbit) | k) ? 1u : 0u);
+                if (p.planes == 2) {
+                  const uint64_t da_lo = make_smem_desc(a_hi + PATCH_BYTES, a_lbo, a_sbo);
+                  const uint64_t db_lo = make_smem_desc(b_hi + nb, b_lbo, b_sbo);
+                  tc_mma_bf16(d, da_hi, db_lo, idesc, 1u);
+                  tc_mma_bf16(d, da_lo, db_hi, idesc, 1u);
+                }
+              }
+              started |= sbit;
+            }
+            tc_commit(&b_empty[bs]);
+            ++b_it;
+          }
+          tc_commit(&a_empty[slot]);
+          ++a_it;
+        }
+        tc_commit(&tm_full[acc]);
+        ++acc_it;
+      }
+    }
+  } else {
+    // =================================== epilogue ========================================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int m = quarter * 32 + lane;
+    const int ty = m >> 3, tx = m & 7;
+    uint32_t acc_it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const uint32_t acc = acc_it & 1, acc_ph = (acc_it >> 1) & 1;
+      PixelCtx px;
+      px.n = t.n;
+      px.y = t.y0 + ty;
+      px.x = t.x0 + tx;
+      px.valid = (px.y < p.dom_h) && (px.x < p.dom_w);
+      px.nz = 0.f;
+      if (EPI == 0 && p.noise && px.valid)
+        px.nz = __ldg(p.noise + (size_t)px.n * p.noise_bstride + (size_t)px.y * p.W + px.x);
+      float rgb[3] = {0.f, 0.f, 0.f};
+      mbar_wait(&tm_full[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * p.ntile + ((uint32_t)(quarter * 32) << 16);
+      for (int q = 0; q < p.np; ++q) {
+        for (int c = 0; c < p.cw; c += 16) {
+          float v[16];
+          __syncwarp();  // .sync.aligned TMEM load needs a converged warp (the epilogue body diverges on px.valid)
+          tc_ld16(taddr + q * p.cw + c, v);
+          if (EPI == 0)
+            epi_pointwise16(p, px, t.co0 + c, v, rgb);
+          else
+            epi_rawup16(p, px.n, px.y, px.x, px.valid, t.p0 + q, t.co0 + c, v);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tm_empty[acc]);
+      if (EPI == 0 && p.rgb_w && px.valid) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch)
+          atomicAdd(p.rgb_out + (((size_t)px.n * 3 + ch) * p.H + px.y) * p.W + px.x, rgb[ch]);
+      }
+      ++acc_it;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// checker kernel: same tiling / packing / epilogue, CUDA-core FMAs straight from global memory.
+// Test-only (DGE_CONV_FLAG_CHECKER): isolates TMA/UMMA-descriptor bugs from packing/epilogue bugs.
+// ---------------------------------------------------------------------------------------------
+template <int EPI>
+__global__ void __launch_bounds__(128) conv_checker_kernel(const __grid_constant__ ConvKParams p) {
+  const int m = threadIdx.x, ty = m >> 3, tx = m & 7;
+  const int C8in = p.Cin >> 3;
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const TileCoord t = decode_tile(p, tile);
+    PixelCtx px;
+    px.n = t.n;
+    px.y = t.y0 + ty;
+    px.x = t.x0 + tx;
+    px.valid = (px.y < p.dom_h) && (px.x < p.dom_w);
+    px.nz = 0.f;
+    if (EPI == 0 && p.noise && px.valid)
+      px.nz = __ldg(p.noise + (size_t)px.n * p.noise_bstride + (size_t)px.y * p.W + px.x);
+    float rgb[3] = {0.f, 0.f, 0.f};
+    for (int q = 0; q < p.np; ++q) {
+      for (int c = 0; c < p.cw; c += 16) {
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        for (int e = 0; e < p.ntaps; ++e) {
+          if (p.taps[e].phase != t.p0 + q) continue;
+          const int dy = p.taps[e].a_off / PW, dx = p.taps[e].a_off % PW;
+          const int iy = px.y - 1 + dy, ix = px.x - 1 + dx;
+          if (iy < 0 || iy >= p.H || ix < 0 || ix >= p.W) continue;
+          for (int g = 0; g < C8in; ++g) {
+            float ah[8], al[8];
+            const uint4* xa = reinterpret_cast<const uint4*>(p.x);
+            unpack8(__ldg(xa + act_idx16(px.n, g, 0, iy, ix, C8in, p.planes, p.H, p.W)), ah);
+            if (p.planes == 2) unpack8(__ldg(xa + act_idx16(px.n, g, 1, iy, ix, C8in, p.planes, p.H, p.W)), al);
+            for (int j = 0; j < 16; ++j) {
+              const int co = t.co0 + c + j;
+              const uint4* wb = reinterpret_cast<const uint4*>(p.wpk);
+              // WPK [tap][Cin/8][planes][Cout][8]
+              const size_t wi = (((size_t)p.taps[e].w_tap * C8in + g) * p.planes) * p.Cout + co;
+              float wh[8], wl[8];
+              unpack8(__ldg(wb + wi), wh);
+              float acc = v[j];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) acc = fmaf(ah[k], wh[k], acc);
+              if (p.planes == 2) {
+                unpack8(__ldg(wb + wi + p.Cout), wl);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc = fmaf(ah[k], wl[k], fmaf(al[k], wh[k], acc));
+              }
+              v[j] = acc;
+            }
+          }
+        }
+        if (EPI == 0)
+          epi_pointwise16(p, px, t.co0 + c, v, rgb);
+        else
+          epi_rawup16(p, px.n, px.y, px.x, px.valid, t.p0 + q, t.co0 + c, v);
+      }
+    }
+    if (EPI == 0 && p.rgb_w && px.valid) {
+      for (int ch = 0; ch < 3; ++ch)
+        atomicAdd(p.rgb_out + (((size_t)px.n * 3 + ch) * p.H + px.y) * p.W + px.x, rgb[ch]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !ptr) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// Tensor maps view the 16-byte channel groups as pairs of uint64 so that a whole pixel row of a patch is ONE
+// contiguous inner-dimension run (box inner extent = 2*pixels elements, <= 256).
+static int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return DGE_ERR_CUDA;
+  }
+  cuuint64_t gd[5], gs[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: CUresult %d (rank %d dims %llu %llu %llu box %u %u %u)", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], box[0], box[1],
+              box[2]);
+    return DGE_ERR_CUDA;
+  }
+  return DGE_OK;
+}
+
+static int largest_div(int value, int cap, int step) {
+  for (int c = (cap / step) * step; c >= step; c -= step)
+    if (value % c == 0) return c;
+  return 0;
+}
+
+static int g_num_sms = 0;
+
+int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
+  DGE_REQUIRE(a != nullptr, "conv: null args");
+  DGE_REQUIRE(a->kind >= 0 && a->kind <= 2, "conv: bad kind %d", a->kind);
+  DGE_REQUIRE(a->n > 0 && a->h > 0 && a->w > 0, "conv: bad dims n=%d h=%d w=%d", a->n, a->h, a->w);
+  DGE_REQUIRE(a->cin >= 16 && a->cin % 16 == 0, "conv: cin=%d must be a positive multiple of 16", a->cin);
+  DGE_REQUIRE(a->cout >= 16 && a->cout % 16 == 0, "conv: cout=%d must be a positive multiple of 16", a->cout);
+  DGE_REQUIRE(a->planes == 1 || a->planes == 2, "conv: planes=%d must be 1 or 2", a->planes);
+  DGE_REQUIRE(a->x && a->wpk, "conv: null x / wpk");
+  const bool up = a->kind == DGE_CONV_UP3X3;
+  if (up) {
+    DGE_REQUIRE(a->out_raw_up != nullptr, "conv: UP3X3 needs out_raw_up");
+  } else {
+    DGE_REQUIRE(a->out_act || a->out_f32b || a->out_nchw || a->rgb_out, "conv: no output given");
+    DGE_REQUIRE(!a->out_act || a->out_planes == 1 || a->out_planes == 2, "conv: out_planes=%d", a->out_planes);
+    DGE_REQUIRE(!a->rgb_w == !a->rgb_out, "conv: rgb_w and rgb_out must be given together");
+    DGE_REQUIRE(!a->noise_w || a->noise, "conv: noise_w without noise");
+  }
+
+  ConvKParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = a->n; p.H = a->h; p.W = a->w;
+  p.Cin = a->cin; p.Cout = a->cout;
+  p.planes = a->planes;
+  p.P = up ? 4 : 1;
+  p.dom_h = up ? a->h + 1 : a->h;
+  p.dom_w = up ? a->w + 1 : a->w;
+  p.tiles_x = (p.dom_w + TW - 1) / TW;
+  p.tiles_y = (p.dom_h + TH - 1) / TH;
+  // taps
+  if (a->kind == DGE_CONV_3X3) {
+    p.ntaps = 9;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        TapEntry& t = p.taps[ky * 3 + kx];
+        t.a_off = (int16_t)(ky * PW + kx);
+        t.w_tap = (int16_t)(ky * 3 + kx);
+        t.phase = 0;
+      }
+  } else if (a->kind == DGE_CONV_1X1) {
+    p.ntaps = 1;
+    p.taps[0].a_off = (int16_t)(1 * PW + 1);
+    p.taps[0].w_tap = 0;
+    p.taps[0].phase = 0;
+  } else {
+    // t[2Y+ky'][2X+kx'] += x[Y - a][X - b] * Wf[ky][kx],  ky = ky' + 2a  (ky' = ky%2, a = ky/2)
+    p.ntaps = 9;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        TapEntry& t = p.taps[ky * 3 + kx];
+        const int dy = 1 - ky / 2, dx = 1 - kx / 2;  // patch offset of input pixel (Y - ky/2, X - kx/2)
+        t.a_off = (int16_t)(dy * PW + dx);
+        t.w_tap = (int16_t)(ky * 3 + kx);
+        t.phase = (int16_t)(2 * (ky % 2) + (kx % 2));
+      }
+  }
+  // N tiling
+  const int ntot = p.P * p.Cout;
+  if (up && ntot <= 256) {
+    p.ntile = ntot; p.cw = p.Cout; p.np = 4;
+  } else if (up && 2 * p.Cout <= 256) {
+    p.ntile = 2 * p.Cout; p.cw = p.Cout; p.np = 2;
+  } else {
+    p.cw = largest_div(p.Cout, 256, 16);
+    p.ntile = p.cw; p.np = 1;
+  }
+  p.nsub = largest_div(p.cw, 128, 16);
+  p.n_ntiles = ntot / p.ntile;
+  DGE_REQUIRE(p.cw > 0 && p.nsub > 0 && p.n_ntiles * p.ntile == ntot, "conv: cannot tile cout=%d", p.Cout);
+  DGE_REQUIRE(p.np * (p.cw / p.nsub) <= 8 && p.cw / p.nsub <= 2, "conv: internal sub-tile bookkeeping overflow");
+  // K chunking
+  p.kc = largest_div(p.Cin, p.cw > 128 ? 32 : 64, 16);
+  p.nchunks = p.Cin / p.kc;
+  p.a_slot_bytes = (p.kc / 8) * p.planes * PATCH_BYTES;
+  p.b_sub_bytes = (p.kc / 8) * p.planes * p.nsub * 16;
+  p.b_slot_bytes = (p.cw / p.nsub) * p.b_sub_bytes;
+  const int smem_budget = 200 * 1024;
+  p.b_slots = (smem_budget - 2 * p.a_slot_bytes) / p.b_slot_bytes;
+  if (p.b_slots > MAX_B_SLOTS) p.b_slots = MAX_B_SLOTS;
+  DGE_REQUIRE(p.b_slots >= 2, "conv: smem budget too small for this shape (b_slot=%d)", p.b_slot_bytes);
+  int cols = 32;
+  while (cols < 2 * p.ntile) cols *= 2;
+  DGE_REQUIRE(cols <= 512, "conv: TMEM overflow");
+  p.tmem_cols = cols;
+  p.total_tiles = p.N * p.tiles_x * p.tiles_y * p.n_ntiles;
+
+  p.demod = a->demod; p.noise = a->noise; p.noise_bstride = a->noise_bstride; p.noise_w = a->noise_w;
+  p.noise_scalar = a->noise_scalar; p.bias = a->bias; p.slope = a->slope; p.gain = a->gain;
+  p.blend_src = a->blend_src; p.blend_pool = a->blend_pool; p.blend_a = a->blend_a; p.blend_b = a->blend_b;
+  p.out_act = a->out_act; p.out_planes = a->out_planes; p.out_scale = a->out_scale; p.out_f32b = a->out_f32b;
+  p.out_nchw = a->out_nchw; p.rgb_w = a->rgb_w; p.rgb_out = a->rgb_out; p.out_raw_up = a->out_raw_up;
+  p.x = a->x; p.wpk = a->wpk;
+
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+
+  if (a->flags & DGE_CONV_FLAG_CHECKER) {
+    int grid = p.total_tiles < 8 * g_num_sms ? p.total_tiles : 8 * g_num_sms;
+    if (up)
+      conv_checker_kernel<1><<<grid, 128, 0, stream>>>(p);
+    else
+      conv_checker_kernel<0><<<grid, 128, 0, stream>>>(p);
+    count_launch();
+    return check_launch("conv_checker_kernel");
+  }
+
+  // tensor maps
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t c8p = (uint64_t)(p.Cin / 8) * p.planes;
+    uint64_t dims[4] = {(uint64_t)2 * p.W, (uint64_t)p.H, c8p, (uint64_t)p.N};
+    uint64_t strides[3] = {(uint64_t)p.W * 16, (uint64_t)p.H * p.W * 16, c8p * p.H * p.W * 16};
+    uint32_t box[4] = {2 * PW, PH, (uint32_t)((p.kc / 8) * p.planes), 1};
+    int r = make_tmap(&tmA, a->x, 4, dims, strides, box);
+    if (r) return r;
+  }
+  {
+    const uint64_t c8p = (uint64_t)(p.Cin / 8) * p.planes;
+    const int wtaps = (a->kind == DGE_CONV_1X1) ? 1 : 9;
+    uint64_t dims[3] = {(uint64_t)2 * p.Cout, c8p, (uint64_t)wtaps};
+    uint64_t strides[2] = {(uint64_t)p.Cout * 16, c8p * p.Cout * 16};
+    uint32_t box[3] = {(uint32_t)(2 * p.nsub), (uint32_t)((p.kc / 8) * p.planes), 1};
+    int r = make_tmap(&tmB, a->wpk, 3, dims, strides, box);
+    if (r) return r;
+  }
+
+  size_t smem = (size_t)2 * p.a_slot_bytes + (size_t)p.b_slots * p.b_slot_bytes + (8 + 2 * MAX_B_SLOTS) * 8 + 16;
+  // TMEM is 512 columns per SM: keep co-resident CTAs * tmem_cols <= 512 by padding the smem request.
+  int max_occ = 512 / p.tmem_cols;
+  if (max_occ > 2) max_occ = 2;
+  const size_t min_smem = (227 * 1024) / (max_occ + 1) + 1024;
+  if (smem < min_smem) smem = min_smem;
+  static bool attr_set[2] = {false, false};
+  const int ei = up ? 1 : 0;
+  if (!attr_set[ei]) {
+    cudaError_t e = up ? cudaFuncSetAttribute(conv_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+                       : cudaFuncSetAttribute(conv_mma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(smem) failed: %s", cudaGetErrorString(e));
+      return DGE_ERR_CUDA;
+    }
+    attr_set[ei] = true;
+  }
+  int grid = g_num_sms * max_occ;
+  if (grid > p.total_tiles) grid = p.total_tiles;
+  if (up)
+    conv_mma_kernel<1><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, p);
+  else
+    conv_mma_kernel<0><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, p);
+  count_launch();
+  return check_launch("conv_mma_kernel");
+}
+
+}  // namespace dge
+
+extern "C" int dge_conv_forward(const dge_conv_args* a, void* stream) {
+  return dge::conv_forward(a, static_cast<cudaStream_t>(stream));
+}

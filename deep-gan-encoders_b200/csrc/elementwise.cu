@@ -1,0 +1,639 @@
+// elementwise.cu -- the HBM-bound kernels around the conv: layout changes, weight packing, style/demod GEMVs,
+// FIR up-sampling epilogue, ToRGB skip initialisation, encoder statistics / instance-norm / pooling / blend.
+// Every kernel is one pass over its data with 16/32-byte vector accesses; one thread handles one
+// (pixel, 8-channel group) unless noted.
+#include <stdarg.h>
+#include <string.h>
+
+#include "dge_common.cuh"
+
+namespace dge {
+
+// ---------------------------------------------------------------------------------------------
+// error / bookkeeping
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static thread_local int64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch() { ++g_launches; }
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return DGE_ERR_CUDA;
+  }
+  return DGE_OK;
+}
+
+static inline int grid_for(size_t work, int block) {
+  size_t g = (work + block - 1) / block;
+  if (g > (size_t)148 * 64) g = (size_t)148 * 64;  // grid-stride beyond this
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+#define LAUNCH_1D(kernel, work, stream, ...)                                     \
+  do {                                                                           \
+    kernel<<<grid_for((work), 256), 256, 0, (cudaStream_t)(stream)>>>(__VA_ARGS__); \
+    count_launch();                                                              \
+    return check_launch(#kernel);                                                \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// weight preparation
+// ---------------------------------------------------------------------------------------------
+// WPK [taps][Cin/8][planes][Cout][8]; one thread per (tap, cin-group, cout)
+__global__ void k_pack_conv_weight(const float* __restrict__ w, uint4* __restrict__ out, int cout, int cin, int ks,
+                                   int flip, float scale, int planes) {
+  const int taps = ks * ks, C8 = cin >> 3;
+  const size_t total = (size_t)taps * C8 * cout;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int co = (int)(i % cout);
+    const int g = (int)((i / cout) % C8);
+    const int tap = (int)(i / ((size_t)cout * C8));
+    int ky = tap / ks, kx = tap % ks;
+    if (flip) { ky = ks - 1 - ky; kx = ks - 1 - kx; }
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = w[(((size_t)co * cin + g * 8 + k) * ks + ky) * ks + kx] * scale;
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    const size_t o = (((size_t)tap * C8 + g) * planes) * cout + co;
+    out[o] = hi;
+    if (planes == 2) out[o + cout] = lo;
+  }
+}
+
+__global__ void k_weight_sqsum(const float* __restrict__ w, float* __restrict__ w2, int cout, int cin, int kk,
+                               float scale) {
+  const size_t total = (size_t)cout * cin;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < kk; ++k) {
+      const float t = w[i * kk + k] * scale;
+      s = fmaf(t, t, s);
+    }
+    w2[i] = s;
+  }
+}
+
+// one warp per (n, o)
+__global__ void k_demod(const float* __restrict__ w2, const float* __restrict__ style, float* __restrict__ d, int n,
+                        int cout, int cin, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int idx = gw; idx < n * cout; idx += nw) {
+    const int b = idx / cout, o = idx % cout;
+    float s = 0.f;
+    for (int i = lane; i < cin; i += 32) {
+      const float st = style[(size_t)b * cin + i];
+      s = fmaf(w2[(size_t)o * cin + i], st * st, s);
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) d[idx] = rsqrtf(s + eps);
+  }
+}
+
+__global__ void k_rgb_weights(const float* __restrict__ w, const float* __restrict__ style, float* __restrict__ out,
+                              int n, int nch, int cin, float scale) {
+  const size_t total = (size_t)n * nch * cin;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cin);
+    const int ch = (int)((i / cin) % nch);
+    const int b = (int)(i / ((size_t)cin * nch));
+    out[i] = w[(size_t)ch * cin + c] * scale * style[(size_t)b * cin + c];
+  }
+}
+
+// one warp per (n, m)
+__global__ void k_dense(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                        float* __restrict__ y, int n, int k, int m, float wscale, float bscale, float add_bias,
+                        float slope, float gain) {
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int idx = gw; idx < n * m; idx += nw) {
+    const int r = idx / m, o = idx % m;
+    float s = 0.f;
+    for (int i = lane; i < k; i += 32) s = fmaf(x[(size_t)r * k + i], w[(size_t)o * k + i], s);
+#pragma unroll
+    for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) {
+      float v = s * wscale + (b ? b[o] * bscale : 0.f) + add_bias;
+      v = (v < 0.f ? v * slope : v) * gain;
+      y[idx] = v;
+    }
+  }
+}
+
+// one warp per row
+__global__ void k_pixel_norm(const float* __restrict__ x, float* __restrict__ y, int n, int k, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int r = gw; r < n; r += nw) {
+    float s = 0.f;
+    for (int i = lane; i < k; i += 32) {
+      const float t = x[(size_t)r * k + i];
+      s = fmaf(t, t, s);
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    const float inv = 1.f / sqrtf(s / (float)k + eps);
+    for (int i = lane; i < k; i += 32) y[(size_t)r * k + i] = x[(size_t)r * k + i] * inv;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout conversions.  index space: (n, c8, y, x) with x fastest
+// ---------------------------------------------------------------------------------------------
+struct Idx4 {
+  int n, g, y, x;
+};
+__device__ __forceinline__ Idx4 decode4(size_t i, int C8, int H, int W) {
+  Idx4 r;
+  r.x = (int)(i % W);
+  size_t t = i / W;
+  r.y = (int)(t % H);
+  t /= H;
+  r.g = (int)(t % C8);
+  r.n = (int)(t / C8);
+  return r;
+}
+
+__global__ void k_nchw_to_act(const float* __restrict__ x, long long bstride, const float* __restrict__ scale,
+                              void* __restrict__ act, int n, int c, int h, int w, int planes) {
+  const int C8 = c >> 3;
+  const size_t total = (size_t)n * C8 * h * w;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const Idx4 q = decode4(i, C8, h, w);
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int ch = q.g * 8 + k;
+      float t = x[(size_t)q.n * bstride + ((size_t)ch * h + q.y) * w + q.x];
+      if (scale) t *= scale[(size_t)q.n * c + ch];
+      v[k] = t;
+    }
+    store8_act(act, q.n, q.g, q.y, q.x, C8, planes, h, w, v);
+  }
+}
+
+__global__ void k_nchw_to_f32b(const float* __restrict__ x, float* __restrict__ out, int n, int c, int h, int w) {
+  const int C8 = c >> 3;
+  const size_t total = (size_t)n * C8 * h * w;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const Idx4 q = decode4(i, C8, h, w);
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = x[(((size_t)q.n * c + q.g * 8 + k) * h + q.y) * w + q.x];
+    store8_f32b(out, i, v);
+  }
+}
+
+__global__ void k_f32b_to_nchw(const float* __restrict__ x, float* __restrict__ out, int n, int c, int h, int w) {
+  const int C8 = c >> 3;
+  const size_t total = (size_t)n * C8 * h * w;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const Idx4 q = decode4(i, C8, h, w);
+    float v[8];
+    load8_f32b(x, i, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) out[(((size_t)q.n * c + q.g * 8 + k) * h + q.y) * w + q.x] = v[k];
+  }
+}
+
+__global__ void k_act_to_nchw(const void* __restrict__ act, float* __restrict__ out, int n, int c, int h, int w,
+                              int planes) {
+  const int C8 = c >> 3;
+  const size_t total = (size_t)n * C8 * h * w;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const Idx4 q = decode4(i, C8, h, w);
+    float v[8];
+    load8_act(act, q.n, q.g, q.y, q.x, C8, planes, h, w, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) out[(((size_t)q.n * c + q.g * 8 + k) * h + q.y) * w + q.x] = v[k];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// StyleGAN2 up path: 4x4 FIR over the raw (2H+1)x(2W+1) transposed-conv map, then the layer epilogue.
+//   out[y][x] = sum_{a,b} f[a] f[b] t[y+a-1][x+b-1],  f = [1,3,3,1]/4   (kernel/sum*gain^2 = outer/64*4)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_up_fir_epilogue(const float* __restrict__ t, const float* __restrict__ demod,
+                                  const float* __restrict__ noise, long long noise_bstride, float noise_scalar,
+                                  const float* __restrict__ bias, float slope, float gain,
+                                  const float* __restrict__ out_scale, void* __restrict__ out_act,
+                                  float* __restrict__ out_nchw, int n, int c, int ho, int wo, int planes) {
+  const int C8 = c >> 3, hi = ho + 1, wi = wo + 1;
+  const size_t total = (size_t)n * C8 * ho * wo;
+  const float f[4] = {0.25f, 0.75f, 0.75f, 0.25f};
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const Idx4 q = decode4(i, C8, ho, wo);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int yy = q.y + a - 1;
+      if (yy < 0 || yy >= hi) continue;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int xx = q.x + b - 1;
+        if (xx < 0 || xx >= wi) continue;
+        float v[8];
+        load8_f32b(t, f32b_idx32(q.n, q.g, yy, xx, C8, hi, wi), v);
+        const float wgt = f[a] * f[b];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(wgt, v[k], acc[k]);
+      }
+    }
+    const float nz = noise ? noise[(size_t)q.n * noise_bstride + (size_t)q.y * wo + q.x] * noise_scalar : 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int ch = q.g * 8 + k;
+      float v = acc[k];
+      if (demod) v *= demod[(size_t)q.n * c + ch];
+      v += nz;
+      if (bias) v += bias[ch];
+      v = (v < 0.f ? v * slope : v) * gain;
+      acc[k] = v;
+    }
+    if (out_nchw) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) out_nchw[(((size_t)q.n * c + q.g * 8 + k) * ho + q.y) * wo + q.x] = acc[k];
+    }
+    if (out_act) {
+      if (out_scale) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] *= out_scale[(size_t)q.n * c + q.g * 8 + k];
+      }
+      store8_act(out_act, q.n, q.g, q.y, q.x, C8, planes, ho, wo, acc);
+    }
+  }
+}
+
+// skip-branch RGB upsample: zero-insert x2, pad (2,1), 4x4 FIR (f = [1,3,3,1]/4 per axis after the x4 gain):
+//   out[2m]   = (x[m-1] + 3 x[m]) / 4 ,  out[2m+1] = (3 x[m] + x[m+1]) / 4   per axis
+__global__ void k_rgb_init(const float* __restrict__ in, const float* __restrict__ bias, float* __restrict__ out,
+                           int n, int nch, int ho, int wo) {
+  const size_t total = (size_t)n * nch * ho * wo;
+  const int hin = ho >> 1, win = wo >> 1;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % wo);
+    size_t tt = i / wo;
+    const int y = (int)(tt % ho);
+    tt /= ho;
+    const int ch = (int)(tt % nch);
+    float v = bias ? bias[ch] : 0.f;
+    if (in) {
+      const float* src = in + tt * (size_t)hin * win;
+      const int my = y >> 1, mx = x >> 1;
+      int y0, y1, x0, x1;
+      float wy0, wy1, wx0, wx1;
+      if (y & 1) { y0 = my; y1 = my + 1; wy0 = 0.75f; wy1 = 0.25f; } else { y0 = my - 1; y1 = my; wy0 = 0.25f; wy1 = 0.75f; }
+      if (x & 1) { x0 = mx; x1 = mx + 1; wx0 = 0.75f; wx1 = 0.25f; } else { x0 = mx - 1; x1 = mx; wx0 = 0.25f; wx1 = 0.75f; }
+      float s = 0.f;
+      const bool vy0 = y0 >= 0 && y0 < hin, vy1 = y1 >= 0 && y1 < hin;
+      const bool vx0 = x0 >= 0 && x0 < win, vx1 = x1 >= 0 && x1 < win;
+      if (vy0 && vx0) s = fmaf(wy0 * wx0, src[(size_t)y0 * win + x0], s);
+      if (vy0 && vx1) s = fmaf(wy0 * wx1, src[(size_t)y0 * win + x1], s);
+      if (vy1 && vx0) s = fmaf(wy1 * wx0, src[(size_t)y1 * win + x0], s);
+      if (vy1 && vx1) s = fmaf(wy1 * wx1, src[(size_t)y1 * win + x1], s);
+      v += s;
+    }
+    out[i] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// encoder pieces
+// ---------------------------------------------------------------------------------------------
+__global__ void k_from_rgb(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ b,
+                           float* __restrict__ out, int n, int cimg, int c, int h, int wd, float slope) {
+  const int C8 = c >> 3;
+  const size_t total = (size_t)n * C8 * h * wd;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const Idx4 q = decode4(i, C8, h, wd);
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = b ? b[q.g * 8 + k] : 0.f;
+    for (int ci = 0; ci < cimg; ++ci) {
+      const float px = img[(((size_t)q.n * cimg + ci) * h + q.y) * wd + q.x];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = fmaf(px, w[(size_t)(q.g * 8 + k) * cimg + ci], v[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = v[k] < 0.f ? v[k] * slope : v[k];
+    store8_f32b(out, i, v);
+  }
+}
+
+// grid (splits, n*C8); fp64 accumulation (naive fp32 E[x^2]-E[x]^2 loses the variance when |mean| >> std)
+__global__ void k_instance_stats_partial(const float* __restrict__ x, double* __restrict__ scratch, int c, int hw) {
+  const int C8 = c >> 3;
+  const int ng = blockIdx.y;  // n*C8 + g
+  const int nidx = ng / C8, g = ng % C8;
+  double s1[8], s2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.0;
+  const size_t base = (size_t)ng * hw;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)hw; i += (size_t)gridDim.x * blockDim.x) {
+    float v[8];
+    load8_f32b(x, base + i, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s1[k] += (double)v[k];
+      s2[k] += (double)v[k] * (double)v[k];
+    }
+  }
+  __shared__ double red[8][16];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+      s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], off);
+      s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], off);
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      red[warp][2 * k] = s1[k];
+      red[warp][2 * k + 1] = s2[k];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    double t = 0.0;
+    for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) t += red[wv][threadIdx.x];
+    const int k = threadIdx.x >> 1, which = threadIdx.x & 1;
+    atomicAdd(&scratch[((size_t)nidx * c + g * 8 + k) * 2 + which], t);
+  }
+}
+
+__global__ void k_instance_stats_final(const double* __restrict__ scratch, float* __restrict__ style,
+                                       float* __restrict__ mean_rstd, int n, int c, int hw, float eps) {
+  const int total = n * c;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / c, ch = i % c;
+    const double m = scratch[2 * (size_t)i] / hw;
+    double var = scratch[2 * (size_t)i + 1] / hw - m * m;
+    if (var < 0.0) var = 0.0;
+    if (style) {
+      style[(size_t)b * 2 * c + ch] = (float)m;
+      style[(size_t)b * 2 * c + c + ch] = (float)sqrt(var);
+    }
+    if (mean_rstd) {
+      mean_rstd[2 * (size_t)i] = (float)m;
+      mean_rstd[2 * (size_t)i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+  }
+}
+
+__global__ void k_instance_norm(const float* __restrict__ x, const float* __restrict__ mr, void* __restrict__ out_act,
+                                float* __restrict__ out_f32b, int n, int c, int h, int w, int planes) {
+  const int C8 = c >> 3;
+  const size_t total = (size_t)n * C8 * h * w;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const Idx4 q = decode4(i, C8, h, w);
+    float v[8];
+    load8_f32b(x, i, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const size_t s = ((size_t)q.n * c + q.g * 8 + k) * 2;
+      v[k] = (v[k] - __ldg(mr + s)) * __ldg(mr + s + 1);
+    }
+    if (out_f32b) store8_f32b(out_f32b, i, v);
+    if (out_act) store8_act(out_act, q.n, q.g, q.y, q.x, C8, planes, h, w, v);
+  }
+}
+
+__device__ __forceinline__ void pooled8(const float* src, int n, int g, int y, int x, int C8, int ho, int wo,
+                                        float* s) {
+  float t[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s[k] = 0.f;
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      load8_f32b(src, f32b_idx32(n, g, 2 * y + dy, 2 * x + dx, C8, 2 * ho, 2 * wo), t);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s[k] += t[k];
+    }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s[k] *= 0.25f;
+}
+
+// x: F32B at (2*ho, 2*wo) -> ACT at (ho, wo)
+__global__ void k_avgpool_to_act(const float* __restrict__ x, void* __restrict__ out, int n, int c, int ho, int wo,
+                                 int planes) {
+  const int C8 = c >> 3;
+  const size_t total = (size_t)n * C8 * ho * wo;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const Idx4 q = decode4(i, C8, ho, wo);
+    float s[8];
+    pooled8(x, q.n, q.g, q.y, q.x, C8, ho, wo, s);
+    store8_act(out, q.n, q.g, q.y, q.x, C8, planes, ho, wo, s);
+  }
+}
+
+__global__ void k_blend(const float* __restrict__ a_src, const float* __restrict__ b_src, float* __restrict__ out,
+                        float a, float b, int pool, int n, int c, int ho, int wo) {
+  const int C8 = c >> 3;
+  const size_t total = (size_t)n * C8 * ho * wo;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const Idx4 q = decode4(i, C8, ho, wo);
+    float va[8], vb[8];
+    if (pool) {
+      pooled8(a_src, q.n, q.g, q.y, q.x, C8, ho, wo, va);
+      pooled8(b_src, q.n, q.g, q.y, q.x, C8, ho, wo, vb);
+    } else {
+      load8_f32b(a_src, i, va);
+      load8_f32b(b_src, i, vb);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) va[k] = a * va[k] + b * vb[k];
+    store8_f32b(out, i, va);
+  }
+}
+
+}  // namespace dge
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+using namespace dge;
+
+extern "C" {
+
+const char* dge_last_error(void) { return g_err; }
+int dge_version(void) { return 100; }
+int64_t dge_launch_count(void) { return g_launches; }
+void dge_launch_count_reset(void) { g_launches = 0; }
+
+int dge_device_ok(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    set_error("cudaGetDevice: %s", cudaGetErrorString(e));
+    return DGE_ERR_CUDA;
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) {
+    set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    return DGE_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    set_error("device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
+    return DGE_ERR_UNSUPPORTED;
+  }
+  return DGE_OK;
+}
+
+int dge_pack_conv_weight(const float* w, void* wpk, int cout, int cin, int ksize, int flip, float scale, int planes,
+                         void* stream) {
+  DGE_REQUIRE(w && wpk, "pack_conv_weight: null pointer");
+  DGE_REQUIRE(cin % 16 == 0 && cout % 16 == 0 && cin > 0 && cout > 0, "pack_conv_weight: cin=%d cout=%d must be multiples of 16", cin, cout);
+  DGE_REQUIRE(ksize == 1 || ksize == 3, "pack_conv_weight: ksize=%d", ksize);
+  DGE_REQUIRE(planes == 1 || planes == 2, "pack_conv_weight: planes=%d", planes);
+  LAUNCH_1D(k_pack_conv_weight, (size_t)ksize * ksize * (cin / 8) * cout, stream, w, (uint4*)wpk, cout, cin, ksize,
+            flip, scale, planes);
+}
+
+int dge_weight_sqsum(const float* w, float* w2, int cout, int cin, int ksize, float scale, void* stream) {
+  DGE_REQUIRE(w && w2 && cout > 0 && cin > 0 && ksize > 0, "weight_sqsum: bad args");
+  LAUNCH_1D(k_weight_sqsum, (size_t)cout * cin, stream, w, w2, cout, cin, ksize * ksize, scale);
+}
+
+int dge_demod(const float* w2, const float* style, float* d, int n, int cout, int cin, float eps, void* stream) {
+  DGE_REQUIRE(w2 && style && d && n > 0 && cout > 0 && cin > 0, "demod: bad args");
+  LAUNCH_1D(k_demod, (size_t)n * cout * 32, stream, w2, style, d, n, cout, cin, eps);
+}
+
+int dge_rgb_weights(const float* w, const float* style, float* rgb_w, int n, int nch, int cin, float scale,
+                    void* stream) {
+  DGE_REQUIRE(w && style && rgb_w && n > 0 && nch > 0 && cin > 0, "rgb_weights: bad args");
+  LAUNCH_1D(k_rgb_weights, (size_t)n * nch * cin, stream, w, style, rgb_w, n, nch, cin, scale);
+}
+
+int dge_dense(const float* x, const float* w, const float* b, float* y, int n, int k, int m, float wscale,
+              float bscale, float add_bias, float slope, float gain, void* stream) {
+  DGE_REQUIRE(x && w && y && n > 0 && k > 0 && m > 0, "dense: bad args");
+  LAUNCH_1D(k_dense, (size_t)n * m * 32, stream, x, w, b, y, n, k, m, wscale, bscale, add_bias, slope, gain);
+}
+
+int dge_pixel_norm(const float* x, float* y, int n, int k, float eps, void* stream) {
+  DGE_REQUIRE(x && y && n > 0 && k > 0, "pixel_norm: bad args");
+  LAUNCH_1D(k_pixel_norm, (size_t)n * 32, stream, x, y, n, k, eps);
+}
+
+#define REQ_NCHW(name)                                                                                      \
+  DGE_REQUIRE(n > 0 && c > 0 && c % 8 == 0 && h > 0 && w > 0, name ": bad dims n=%d c=%d h=%d w=%d (c %% 8)", n, c, h, w)
+
+int dge_nchw_to_act(const float* x, int64_t x_bstride, const float* scale, void* act, int n, int c, int h, int w,
+                    int planes, void* stream) {
+  DGE_REQUIRE(x && act, "nchw_to_act: null pointer");
+  REQ_NCHW("nchw_to_act");
+  DGE_REQUIRE(planes == 1 || planes == 2, "nchw_to_act: planes=%d", planes);
+  LAUNCH_1D(k_nchw_to_act, (size_t)n * (c / 8) * h * w, stream, x, (long long)x_bstride, scale, act, n, c, h, w, planes);
+}
+int dge_nchw_to_f32b(const float* x, float* out, int n, int c, int h, int w, void* stream) {
+  DGE_REQUIRE(x && out, "nchw_to_f32b: null pointer");
+  REQ_NCHW("nchw_to_f32b");
+  LAUNCH_1D(k_nchw_to_f32b, (size_t)n * (c / 8) * h * w, stream, x, out, n, c, h, w);
+}
+int dge_f32b_to_nchw(const float* x, float* out, int n, int c, int h, int w, void* stream) {
+  DGE_REQUIRE(x && out, "f32b_to_nchw: null pointer");
+  REQ_NCHW("f32b_to_nchw");
+  LAUNCH_1D(k_f32b_to_nchw, (size_t)n * (c / 8) * h * w, stream, x, out, n, c, h, w);
+}
+int dge_act_to_nchw(const void* act, float* out, int n, int c, int h, int w, int planes, void* stream) {
+  DGE_REQUIRE(act && out, "act_to_nchw: null pointer");
+  REQ_NCHW("act_to_nchw");
+  DGE_REQUIRE(planes == 1 || planes == 2, "act_to_nchw: planes=%d", planes);
+  LAUNCH_1D(k_act_to_nchw, (size_t)n * (c / 8) * h * w, stream, act, out, n, c, h, w, planes);
+}
+
+int dge_up_fir_epilogue(const float* raw_up, const float* demod, const float* noise, int64_t noise_bstride,
+                        float noise_scalar, const float* bias, float slope, float gain, const float* out_scale,
+                        void* out_act, float* out_nchw, int n, int c, int h_out, int w_out, int planes, void* stream) {
+  DGE_REQUIRE(raw_up && (out_act || out_nchw), "up_fir_epilogue: null pointer");
+  DGE_REQUIRE(n > 0 && c > 0 && c % 8 == 0 && h_out > 0 && w_out > 0 && h_out % 2 == 0 && w_out % 2 == 0,
+              "up_fir_epilogue: bad dims n=%d c=%d h=%d w=%d", n, c, h_out, w_out);
+  DGE_REQUIRE(!out_act || planes == 1 || planes == 2, "up_fir_epilogue: planes=%d", planes);
+  LAUNCH_1D(k_up_fir_epilogue, (size_t)n * (c / 8) * h_out * w_out, stream, raw_up, demod, noise,
+            (long long)noise_bstride, noise_scalar, bias, slope, gain, out_scale, out_act, out_nchw, n, c, h_out, w_out,
+            planes);
+}
+
+int dge_rgb_init(const float* img_in, const float* bias, float* img_out, int n, int nch, int h_out, int w_out,
+                 void* stream) {
+  DGE_REQUIRE(img_out && n > 0 && nch > 0 && h_out > 0 && w_out > 0, "rgb_init: bad args");
+  DGE_REQUIRE(!img_in || (h_out % 2 == 0 && w_out % 2 == 0), "rgb_init: odd output size with an input image");
+  LAUNCH_1D(k_rgb_init, (size_t)n * nch * h_out * w_out, stream, img_in, bias, img_out, n, nch, h_out, w_out);
+}
+
+int dge_from_rgb(const float* img, const float* w, const float* b, float* out, int n, int cimg, int c, int h, int wd,
+                 float slope, void* stream) {
+  DGE_REQUIRE(img && w && out, "from_rgb: null pointer");
+  DGE_REQUIRE(n > 0 && cimg > 0 && c > 0 && c % 8 == 0 && h > 0 && wd > 0, "from_rgb: bad dims");
+  LAUNCH_1D(k_from_rgb, (size_t)n * (c / 8) * h * wd, stream, img, w, b, out, n, cimg, c, h, wd, slope);
+}
+
+int dge_instance_stats(const float* x, double* scratch, float* style, float* mean_rstd, int n, int c, int h, int w,
+                       float eps, void* stream) {
+  DGE_REQUIRE(x && scratch && (style || mean_rstd), "instance_stats: null pointer");
+  REQ_NCHW("instance_stats");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * (size_t)n * c, st);
+  if (e != cudaSuccess) {
+    set_error("instance_stats memset: %s", cudaGetErrorString(e));
+    return DGE_ERR_CUDA;
+  }
+  const int hw = h * w;
+  int splits = (hw + 256 * 16 - 1) / (256 * 16);
+  if (splits < 1) splits = 1;
+  if (splits > 256) splits = 256;
+  dim3 grid(splits, n * (c / 8));
+  k_instance_stats_partial<<<grid, 256, 0, st>>>(x, scratch, c, hw);
+  count_launch();
+  int r = check_launch("k_instance_stats_partial");
+  if (r) return r;
+  k_instance_stats_final<<<grid_for((size_t)n * c, 256), 256, 0, st>>>(scratch, style, mean_rstd, n, c, hw, eps);
+  count_launch();
+  return check_launch("k_instance_stats_final");
+}
+
+int dge_instance_norm(const float* x, const float* mean_rstd, void* out_act, float* out_f32b, int n, int c, int h,
+                      int w, int planes, void* stream) {
+  DGE_REQUIRE(x && mean_rstd && (out_act || out_f32b), "instance_norm: null pointer");
+  REQ_NCHW("instance_norm");
+  DGE_REQUIRE(!out_act || planes == 1 || planes == 2, "instance_norm: planes=%d", planes);
+  LAUNCH_1D(k_instance_norm, (size_t)n * (c / 8) * h * w, stream, x, mean_rstd, out_act, out_f32b, n, c, h, w, planes);
+}
+
+int dge_avgpool_to_act(const float* x, void* out_act, int n, int c, int h, int w, int planes, void* stream) {
+  DGE_REQUIRE(x && out_act, "avgpool_to_act: null pointer");
+  REQ_NCHW("avgpool_to_act");
+  DGE_REQUIRE(h % 2 == 0 && w % 2 == 0, "avgpool_to_act: odd input size %dx%d", h, w);
+  DGE_REQUIRE(planes == 1 || planes == 2, "avgpool_to_act: planes=%d", planes);
+  LAUNCH_1D(k_avgpool_to_act, (size_t)n * (c / 8) * (h / 2) * (w / 2), stream, x, out_act, n, c, h / 2, w / 2, planes);
+}
+
+int dge_blend(const float* a_src, const float* b_src, float* out, float a, float b, int pool, int n, int c, int h_out,
+              int w_out, void* stream) {
+  DGE_REQUIRE(a_src && b_src && out, "blend: null pointer");
+  DGE_REQUIRE(n > 0 && c > 0 && c % 8 == 0 && h_out > 0 && w_out > 0, "blend: bad dims");
+  LAUNCH_1D(k_blend, (size_t)n * (c / 8) * h_out * w_out, stream, a_src, b_src, out, a, b, pool, n, c, h_out, w_out);
+}
+
+}  // extern "C"

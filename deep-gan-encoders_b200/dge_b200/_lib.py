@@ -1,0 +1,90 @@
+"""ctypes binding of libdge_b200.so -- the C ABI declared in include/dge_b200.h.
+
+The library is the product path: if it is missing or the device is not a B200 the ops raise
+(there is NO CPU / eager fallback anywhere in this package).
+"""
+import ctypes
+import os
+from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdge_b200.so")
+
+_lib = None
+
+
+class DgeError(RuntimeError):
+    pass
+
+
+class ConvArgs(Structure):
+    """Mirror of `dge_conv_args` (include/dge_b200.h)."""
+    _fields_ = [
+        ("kind", c_int32), ("flags", c_int32),
+        ("n", c_int32), ("h", c_int32), ("w", c_int32),
+        ("cin", c_int32), ("cout", c_int32),
+        ("planes", c_int32),
+        ("x", c_void_p), ("wpk", c_void_p),
+        ("demod", c_void_p), ("noise", c_void_p), ("noise_bstride", c_int64),
+        ("noise_w", c_void_p), ("noise_scalar", c_float),
+        ("bias", c_void_p), ("slope", c_float), ("gain", c_float),
+        ("blend_src", c_void_p), ("blend_pool", c_int32), ("blend_a", c_float), ("blend_b", c_float),
+        ("out_act", c_void_p), ("out_planes", c_int32), ("out_scale", c_void_p),
+        ("out_f32b", c_void_p), ("out_nchw", c_void_p),
+        ("rgb_w", c_void_p), ("rgb_out", c_void_p),
+        ("out_raw_up", c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/dge_b200.h declares
+P = c_void_p
+SIGNATURES = {
+    "dge_last_error": (c_char_p, []),
+    "dge_version": (c_int, []),
+    "dge_device_ok": (c_int, []),
+    "dge_launch_count": (c_int64, []),
+    "dge_launch_count_reset": (None, []),
+    "dge_conv_forward": (c_int, [POINTER(ConvArgs), P]),
+    "dge_pack_conv_weight": (c_int, [P, P, c_int, c_int, c_int, c_int, c_float, c_int, P]),
+    "dge_weight_sqsum": (c_int, [P, P, c_int, c_int, c_int, c_float, P]),
+    "dge_demod": (c_int, [P, P, P, c_int, c_int, c_int, c_float, P]),
+    "dge_rgb_weights": (c_int, [P, P, P, c_int, c_int, c_int, c_float, P]),
+    "dge_dense": (c_int, [P, P, P, P, c_int, c_int, c_int, c_float, c_float, c_float, c_float, c_float, P]),
+    "dge_pixel_norm": (c_int, [P, P, c_int, c_int, c_float, P]),
+    "dge_nchw_to_act": (c_int, [P, c_int64, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "dge_nchw_to_f32b": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
+    "dge_f32b_to_nchw": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
+    "dge_act_to_nchw": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "dge_up_fir_epilogue": (c_int, [P, P, P, c_int64, c_float, P, c_float, c_float, P, P, P,
+                                    c_int, c_int, c_int, c_int, c_int, P]),
+    "dge_rgb_init": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
+    "dge_from_rgb": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P]),
+    "dge_instance_stats": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_float, P]),
+    "dge_instance_norm": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "dge_avgpool_to_act": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "dge_blend": (c_int, [P, P, P, c_float, c_float, c_int, c_int, c_int, c_int, c_int, P]),
+}
+
+
+def load():
+    """Load the shared library (once). Raises DgeError with build instructions if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DgeError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C deep-gan-encoders_b200/csrc`). There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().dge_last_error()
+        raise DgeError(f"dge_b200 call failed (rc={rc}): {msg.decode() if msg else '?'}")

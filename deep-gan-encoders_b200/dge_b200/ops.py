@@ -1,0 +1,293 @@
+"""Tensor-level wrappers over the C ABI (include/dge_b200.h).
+
+PyTorch is used only for device memory and streams; every function launches hand-written sm_100a
+kernels on torch's current CUDA stream and raises if the library / device is unavailable.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ConvArgs, DgeError, check
+
+CONV_3X3, CONV_1X1, CONV_UP3X3 = 0, 1, 2
+FLAG_CHECKER = 1
+
+_device_checked = False
+
+
+def lib():
+    global _device_checked
+    L = _lib.load()
+    if not _device_checked:
+        if not torch.cuda.is_available():
+            raise DgeError("dge_b200 needs a CUDA device (B200, sm_100a); no CPU fallback exists")
+        check(L.dge_device_ok())
+        _device_checked = True
+    return L
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "dge_b200 ops need contiguous CUDA tensors"
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _f32(t):
+    assert t is None or t.dtype == torch.float32
+    return _p(t)
+
+
+# ------------------------------------------------------------------------------------------------
+# layout containers
+# ------------------------------------------------------------------------------------------------
+class Act:
+    """ACT layout: bf16 [N][C/8][planes][H][W][8] (planes=2: x = hi + lo)."""
+
+    def __init__(self, n, c, h, w, planes=2, device="cuda"):
+        assert c % 16 == 0, f"ACT tensors need C % 16 == 0 (got {c})"
+        self.n, self.c, self.h, self.w, self.planes = n, c, h, w, planes
+        self.t = torch.empty((n, c // 8, planes, h, w, 8), dtype=torch.bfloat16, device=device)
+
+    def to_nchw(self):
+        out = torch.empty((self.n, self.c, self.h, self.w), dtype=torch.float32, device=self.t.device)
+        check(lib().dge_act_to_nchw(_p(self.t), _p(out), self.n, self.c, self.h, self.w, self.planes, _stream()))
+        return out
+
+
+class F32B:
+    """F32B layout: fp32 [N][C/8][H][W][8]."""
+
+    def __init__(self, n, c, h, w, device="cuda"):
+        assert c % 8 == 0
+        self.n, self.c, self.h, self.w = n, c, h, w
+        self.t = torch.empty((n, c // 8, h, w, 8), dtype=torch.float32, device=device)
+
+    def to_nchw(self):
+        out = torch.empty((self.n, self.c, self.h, self.w), dtype=torch.float32, device=self.t.device)
+        check(lib().dge_f32b_to_nchw(_p(self.t), _p(out), self.n, self.c, self.h, self.w, _stream()))
+        return out
+
+
+def nchw_to_act(x, scale=None, planes=2, batch=None):
+    """NCHW fp32 -> ACT. `batch` > x.shape[0]==1 broadcasts the single sample (const input)."""
+    x = x.contiguous()
+    n0, c, h, w = x.shape
+    n = batch if batch is not None else n0
+    bstride = 0 if (batch is not None and n0 == 1) else c * h * w
+    out = Act(n, c, h, w, planes, x.device)
+    check(lib().dge_nchw_to_act(_f32(x), bstride, _f32(scale), _p(out.t), n, c, h, w, planes, _stream()))
+    return out
+
+
+def nchw_to_f32b(x):
+    x = x.contiguous()
+    n, c, h, w = x.shape
+    out = F32B(n, c, h, w, x.device)
+    check(lib().dge_nchw_to_f32b(_f32(x), _p(out.t), n, c, h, w, _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# weights
+# ------------------------------------------------------------------------------------------------
+def pack_conv_weight(w, scale=1.0, flip=False, planes=2):
+    """OIHW fp32 -> WPK bf16 [taps][Cin/8][planes][Cout][8]."""
+    w = w.detach().contiguous()
+    cout, cin, k, k2 = w.shape
+    assert k == k2
+    out = torch.empty((k * k, cin // 8, planes, cout, 8), dtype=torch.bfloat16, device=w.device)
+    check(lib().dge_pack_conv_weight(_f32(w), _p(out), cout, cin, k, int(flip), float(scale), planes, _stream()))
+    return out
+
+
+def weight_sqsum(w, scale=1.0):
+    w = w.detach().contiguous()
+    cout, cin, k, _ = w.shape
+    out = torch.empty((cout, cin), dtype=torch.float32, device=w.device)
+    check(lib().dge_weight_sqsum(_f32(w), _p(out), cout, cin, k, float(scale), _stream()))
+    return out
+
+
+def demod(w2, style, eps=1e-8):
+    n, cin = style.shape
+    cout = w2.shape[0]
+    out = torch.empty((n, cout), dtype=torch.float32, device=style.device)
+    check(lib().dge_demod(_f32(w2), _f32(style.contiguous()), _p(out), n, cout, cin, float(eps), _stream()))
+    return out
+
+
+def rgb_weights(w, style, scale):
+    """w [nch][cin] (1x1 ToRGB weight), style [n][cin] -> [n][nch][cin]."""
+    w = w.detach().contiguous().view(w.shape[0], -1)
+    nch, cin = w.shape
+    n = style.shape[0]
+    out = torch.empty((n, nch, cin), dtype=torch.float32, device=style.device)
+    check(lib().dge_rgb_weights(_f32(w), _f32(style.contiguous()), _p(out), n, nch, cin, float(scale), _stream()))
+    return out
+
+
+def dense(x, w, b=None, wscale=1.0, bscale=1.0, add_bias=0.0, slope=1.0, gain=1.0):
+    x = x.contiguous()
+    w = w.detach().contiguous()
+    n, k = x.shape
+    m = w.shape[0]
+    assert w.shape[1] == k
+    y = torch.empty((n, m), dtype=torch.float32, device=x.device)
+    bb = None if b is None else b.detach().contiguous()
+    check(lib().dge_dense(_f32(x), _f32(w), _f32(bb), _p(y), n, k, m, float(wscale), float(bscale), float(add_bias),
+                          float(slope), float(gain), _stream()))
+    return y
+
+
+def pixel_norm(x, eps=1e-8):
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    check(lib().dge_pixel_norm(_f32(x), _p(y), x.shape[0], x.shape[1], float(eps), _stream()))
+    return y
+
+
+# ------------------------------------------------------------------------------------------------
+# conv
+# ------------------------------------------------------------------------------------------------
+def conv(x, wpk, cout, kind=CONV_3X3, *, demod=None, noise=None, noise_batched=False, noise_w=None,
+         noise_scalar=0.0, bias=None, slope=1.0, gain=1.0, blend_src=None, blend_pool=False, blend_a=0.0,
+         blend_b=1.0, out_act=False, out_planes=None, out_scale=None, out_f32b=False, out_nchw=False, rgb_w=None,
+         rgb_out=None, checker=False):
+    """tcgen05 implicit-GEMM conv with fused epilogue (dge_conv_forward). Returns a dict of outputs."""
+    assert isinstance(x, Act)
+    dev = x.t.device
+    a = ConvArgs()
+    a.kind, a.flags = kind, (FLAG_CHECKER if checker else 0)
+    a.n, a.h, a.w, a.cin, a.cout, a.planes = x.n, x.h, x.w, x.c, cout, x.planes
+    a.x, a.wpk = x.t.data_ptr(), wpk.data_ptr()
+    keep = [x.t, wpk]
+    res = {}
+
+    def ptr(t):
+        if t is None:
+            return None
+        assert t.is_cuda and t.is_contiguous()
+        keep.append(t)
+        return t.data_ptr()
+
+    if kind == CONV_UP3X3:
+        raw = torch.empty((x.n, cout // 8, 2 * x.h + 1, 2 * x.w + 1, 8), dtype=torch.float32, device=dev)
+        a.out_raw_up = ptr(raw)
+        res["raw_up"] = raw
+    else:
+        a.demod = ptr(demod)
+        a.noise = ptr(noise)
+        a.noise_bstride = x.h * x.w if (noise is not None and noise_batched) else 0
+        a.noise_w = ptr(noise_w)
+        a.noise_scalar = float(noise_scalar)
+        a.bias = ptr(bias)
+        a.slope, a.gain = float(slope), float(gain)
+        if blend_src is not None:
+            a.blend_src = ptr(blend_src.t if isinstance(blend_src, F32B) else blend_src)
+            a.blend_pool, a.blend_a, a.blend_b = int(blend_pool), float(blend_a), float(blend_b)
+        if out_act:
+            o = Act(x.n, cout, x.h, x.w, out_planes or x.planes, dev)
+            a.out_act, a.out_planes = ptr(o.t), o.planes
+            a.out_scale = ptr(out_scale)
+            res["act"] = o
+        if out_f32b:
+            o = F32B(x.n, cout, x.h, x.w, dev)
+            a.out_f32b = ptr(o.t)
+            res["f32b"] = o
+        if out_nchw:
+            o = torch.empty((x.n, cout, x.h, x.w), dtype=torch.float32, device=dev)
+            a.out_nchw = ptr(o)
+            res["nchw"] = o
+        if rgb_w is not None:
+            a.rgb_w, a.rgb_out = ptr(rgb_w), ptr(rgb_out)
+    check(lib().dge_conv_forward(ctypes.byref(a), _stream()))
+    return res
+
+
+def up_fir_epilogue(raw_up, n, c, h_out, w_out, *, demod=None, noise=None, noise_batched=False, noise_scalar=0.0,
+                    bias=None, slope=1.0, gain=1.0, out_scale=None, planes=2, out_act=True, out_nchw=False):
+    dev = raw_up.device
+    res = {}
+    act = Act(n, c, h_out, w_out, planes, dev) if out_act else None
+    nchw = torch.empty((n, c, h_out, w_out), dtype=torch.float32, device=dev) if out_nchw else None
+    check(lib().dge_up_fir_epilogue(
+        _f32(raw_up), _f32(demod), _f32(noise), (h_out * w_out if noise_batched else 0), float(noise_scalar),
+        _f32(bias), float(slope), float(gain), _f32(out_scale), _p(act.t) if act else None, _p(nchw), n, c, h_out,
+        w_out, planes, _stream()))
+    if act is not None:
+        res["act"] = act
+    if nchw is not None:
+        res["nchw"] = nchw
+    return res
+
+
+def rgb_init(img_in, bias, n, nch, h_out, w_out, device):
+    out = torch.empty((n, nch, h_out, w_out), dtype=torch.float32, device=device)
+    check(lib().dge_rgb_init(_f32(img_in), _f32(bias), _p(out), n, nch, h_out, w_out, _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# encoder pieces
+# ------------------------------------------------------------------------------------------------
+def from_rgb(img, w, b, slope=0.2):
+    img = img.contiguous()
+    n, cimg, h, wd = img.shape
+    w2 = w.detach().contiguous().view(w.shape[0], -1)
+    c = w2.shape[0]
+    out = F32B(n, c, h, wd, img.device)
+    bb = None if b is None else b.detach().contiguous()
+    check(lib().dge_from_rgb(_f32(img), _f32(w2), _f32(bb), _p(out.t), n, cimg, c, h, wd, float(slope), _stream()))
+    return out
+
+
+def instance_stats(x, eps=1e-8):
+    """F32B -> (style [n][2c] = mean||std, mean_rstd [n][c][2])."""
+    assert isinstance(x, F32B)
+    dev = x.t.device
+    scratch = torch.empty((2 * x.n * x.c,), dtype=torch.float64, device=dev)
+    style = torch.empty((x.n, 2 * x.c), dtype=torch.float32, device=dev)
+    mr = torch.empty((x.n, x.c, 2), dtype=torch.float32, device=dev)
+    check(lib().dge_instance_stats(_p(x.t), _p(scratch), _p(style), _p(mr), x.n, x.c, x.h, x.w, float(eps),
+                                   _stream()))
+    return style, mr
+
+
+def instance_norm(x, mean_rstd, planes=2, out_act=True, out_f32b=False):
+    assert isinstance(x, F32B)
+    dev = x.t.device
+    act = Act(x.n, x.c, x.h, x.w, planes, dev) if out_act else None
+    f = F32B(x.n, x.c, x.h, x.w, dev) if out_f32b else None
+    check(lib().dge_instance_norm(_p(x.t), _f32(mean_rstd), _p(act.t) if act else None, _p(f.t) if f else None, x.n,
+                                  x.c, x.h, x.w, planes, _stream()))
+    return act, f
+
+
+def avgpool_to_act(x, planes=2):
+    assert isinstance(x, F32B)
+    out = Act(x.n, x.c, x.h // 2, x.w // 2, planes, x.t.device)
+    check(lib().dge_avgpool_to_act(_p(x.t), _p(out.t), x.n, x.c, x.h, x.w, planes, _stream()))
+    return out
+
+
+def blend(a_src, b_src, a, b, pool):
+    assert isinstance(a_src, F32B) and isinstance(b_src, F32B)
+    ho, wo = (a_src.h // 2, a_src.w // 2) if pool else (a_src.h, a_src.w)
+    out = F32B(a_src.n, a_src.c, ho, wo, a_src.t.device)
+    check(lib().dge_blend(_p(a_src.t), _p(b_src.t), _p(out.t), float(a), float(b), int(pool), a_src.n, a_src.c, ho, wo,
+                          _stream()))
+    return out
+
+
+def launch_count():
+    return int(_lib.load().dge_launch_count())
+
+
+def launch_count_reset():
+    _lib.load().dge_launch_count_reset()

@@ -1,0 +1,158 @@
+/*
+ * dge_b200.h -- C ABI of the B200-native GAN-inversion hot path (E forward + frozen G forward).
+ *
+ * The reference (disanda/Deep-GAN-Encoders) has NO FFI / plugin layer: its hot path is a chain of
+ * ATen calls issued from Python nn.Modules.  Each entry point below replaces one such chain; the
+ * reference call site it stands in for is cited as `file:line` (paths relative to the reference
+ * repository root).  Host code (the mirrored nn.Modules under deep-gan-encoders_b200/model) binds
+ * these symbols with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch's caching allocator in the
+ *     shipped host code); the library never allocates, frees or retains device memory;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - return value: 0 = OK, negative = error; dge_last_error() returns a thread-local message;
+ *   - nothing throws across the boundary; sm_100a only (dge_device_ok() reports it).
+ *
+ * Device tensor layouts (all produced/consumed by this library only)
+ *   NCHW   fp32 [N][C][H][W]                      -- the reference's layout, used at the module boundary
+ *   ACT    bf16 [N][C/8][planes][H][W][8]         -- conv operand; planes=2 stores x = hi + lo (bf16x3
+ *                                                    split precision, ~fp32-equivalent), planes=1 is plain bf16
+ *   F32B   fp32 [N][C/8][H][W][8]                 -- channel-blocked fp32 (encoder residual stream, IN inputs)
+ *   WPK    bf16 [taps][Cin/8][planes][Cout][8]    -- packed conv weights (K-major, 16-byte K chunks)
+ *   C must be a multiple of 16 for ACT/F32B/WPK tensors.
+ */
+#ifndef DGE_B200_H_
+#define DGE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGE_OK 0
+#define DGE_ERR_BAD_ARG (-1)
+#define DGE_ERR_CUDA (-2)
+#define DGE_ERR_UNSUPPORTED (-3)
+
+/* ---- library ------------------------------------------------------------------------------- */
+const char* dge_last_error(void);
+int dge_version(void);
+/* 0 if the current device is sm_100 (B200); DGE_ERR_UNSUPPORTED otherwise. */
+int dge_device_ok(void);
+/* number of kernels launched by this library on this thread since the last reset (bench.py gpu_launches) */
+int64_t dge_launch_count(void);
+void dge_launch_count_reset(void);
+
+/* ---- conv: tcgen05 implicit-GEMM with fused epilogue ------------------------------------------ */
+enum {
+  DGE_CONV_3X3 = 0,    /* 3x3, stride 1, pad 1  (stylegan2_generator.py:897-904; E.py:59,72; lreq.py:126-156) */
+  DGE_CONV_1X1 = 1,    /* 1x1                  (E.py:81-82 conv_3; net.py:231-240 FromRGB when Cin%16==0) */
+  DGE_CONV_UP3X3 = 2   /* 3x3 transposed, stride 2, pad 0 -> raw (2H+1)x(2W+1) map, before the FIR
+                          (stylegan2_generator.py:879-895) */
+};
+enum {
+  DGE_CONV_FLAG_CHECKER = 1  /* run the slow CUDA-core checker kernel instead of tcgen05 (tests only) */
+};
+
+typedef struct dge_conv_args {
+  int32_t kind;            /* DGE_CONV_* */
+  int32_t flags;
+  int32_t n, h, w;         /* input batch / height / width */
+  int32_t cin, cout;
+  int32_t planes;          /* 1 or 2 (see ACT) -- must match x and wpk */
+  const void* x;           /* ACT  [n][cin/8][planes][h][w][8] */
+  const void* wpk;         /* WPK  [taps][cin/8][planes][cout][8] */
+  /* pointwise epilogue, applied in this order (NULL / 0 = skipped):
+       v  = acc * demod[n][co]
+       v += noise[n*noise_bstride + y*W + x] * (noise_w ? noise_w[co] : noise_scalar)
+       v += bias[co]
+       v  = (v < 0 ? v*slope : v) * gain
+       v  = blend_a * S(blend_src) + blend_b * v      (S = 2x2 mean of a double-resolution F32B tensor
+                                                        if blend_pool, else the same-resolution value) */
+  const float* demod;      /* [n][cout] */
+  const float* noise;      /* fp32, [h][w] (bstride 0) or [n][h][w] */
+  int64_t noise_bstride;
+  const float* noise_w;    /* [cout] */
+  float noise_scalar;
+  const float* bias;       /* [cout] */
+  float slope, gain;
+  const float* blend_src;  /* F32B */
+  int32_t blend_pool;
+  float blend_a, blend_b;
+  /* outputs (any subset) */
+  void* out_act;           /* ACT [n][cout/8][out_planes][h][w][8], multiplied by out_scale[n][co] if given */
+  int32_t out_planes;
+  const float* out_scale;  /* [n][cout] -- the NEXT layer's style (modulation folded into the producer) */
+  float* out_f32b;         /* F32B */
+  float* out_nchw;         /* NCHW fp32 */
+  const float* rgb_w;      /* [n][3][cout]: fused ToRGB weights (style and wscale folded in) */
+  float* rgb_out;          /* NCHW [n][3][h][w]; contributions are atomically ADDED (pre-initialise with
+                              dge_rgb_init) -- stylegan2_generator.py:515-522 */
+  float* out_raw_up;       /* DGE_CONV_UP3X3 only: F32B-like [n][cout/8][2h+1][2w+1][8] raw transposed conv */
+} dge_conv_args;
+
+int dge_conv_forward(const dge_conv_args* a, void* stream);
+
+/* ---- weight preparation ---------------------------------------------------------------------- */
+/* OIHW fp32 [cout][cin][k][k] -> WPK.  flip=1 packs the spatially flipped kernel (transposed conv,
+   stylegan2_generator.py:880).  scale multiplies every weight (wscale, :858). */
+int dge_pack_conv_weight(const float* w_oihw, void* wpk, int cout, int cin, int ksize, int flip,
+                         float scale, int planes, void* stream);
+/* W2[o][i] = sum_k (w[o][i][k]*scale)^2 -- the demodulation Gram diagonal (stylegan2_generator.py:867-870) */
+int dge_weight_sqsum(const float* w_oihw, float* w2, int cout, int cin, int ksize, float scale, void* stream);
+/* d[n][o] = rsqrt(sum_i W2[o][i]*s[n][i]^2 + eps) */
+int dge_demod(const float* w2, const float* style, float* d, int n, int cout, int cin, float eps, void* stream);
+/* rgb_w[n][ch][c] = w[ch][c]*scale*style[n][c]   (ToRGB 1x1 modulated conv without demod, :462-474) */
+int dge_rgb_weights(const float* w, const float* style, float* rgb_w, int n, int nch, int cin, float scale,
+                    void* stream);
+
+/* ---- dense (DenseBlock.forward stylegan2_generator.py:990-996; ln.Linear lreq.py:68-75) ------ */
+/* y[n][m] = act((sum_k x[n][k]*w[m][k])*wscale + b[m]*bscale + add_bias) * gain ; act = lrelu(slope) */
+int dge_dense(const float* x, const float* w, const float* b, float* y, int n, int k, int m, float wscale,
+              float bscale, float add_bias, float slope, float gain, void* stream);
+/* PixelNormLayer (stylegan2_generator.py:550-553) on [n][k] */
+int dge_pixel_norm(const float* x, float* y, int n, int k, float eps, void* stream);
+
+/* ---- layout / elementwise --------------------------------------------------------------------- */
+/* NCHW fp32 -> ACT, optionally times scale[n][c]; x_bstride = 0 broadcasts one sample (InputBlock :630-632) */
+int dge_nchw_to_act(const float* x, int64_t x_bstride, const float* scale, void* act, int n, int c, int h, int w,
+                    int planes, void* stream);
+int dge_nchw_to_f32b(const float* x, float* out, int n, int c, int h, int w, void* stream);
+int dge_f32b_to_nchw(const float* x, float* out, int n, int c, int h, int w, void* stream);
+int dge_act_to_nchw(const void* act, float* out, int n, int c, int h, int w, int planes, void* stream);
+
+/* 4x4 FIR ([1,3,3,1]x[1,3,3,1]/16, pad 1) over the raw up-conv map + demod + noise + bias + lrelu*gain,
+   output ACT times out_scale (stylegan2_generator.py:603-615 with filter padding (1,1,1,1), :907-921) */
+int dge_up_fir_epilogue(const float* raw_up, const float* demod, const float* noise, int64_t noise_bstride,
+                        float noise_scalar, const float* bias, float slope, float gain, const float* out_scale,
+                        void* out_act, float* out_nchw, int n, int c, int h_out, int w_out, int planes,
+                        void* stream);
+/* img_out[n][ch][2h][2w] = bias[ch] + up2_fir(img_in)  (UpsamplingLayer(scale 2), :603-615, skip sum :519-522);
+   img_in == NULL: img_out = bias only (first resolution, h_out x w_out given directly) */
+int dge_rgb_init(const float* img_in, const float* bias, float* img_out, int n, int nch, int h_out, int w_out,
+                 void* stream);
+
+/* ---- encoder pieces (model/E/E.py:50-85) ------------------------------------------------------- */
+/* FromRGB: 1x1 conv (cin=3) + bias + lrelu(0.2): NCHW image -> F32B  (model/utils/net.py:231-240) */
+int dge_from_rgb(const float* img, const float* w, const float* b, float* out_f32b, int n, int cimg, int c, int h,
+                 int wd, float slope, void* stream);
+/* per-(n,c) mean and biased std over H*W of an F32B tensor: style[n][0:c]=mean, style[n][c:2c]=std
+   (E.py:51-53), mean_rstd[n][c] = (mean, 1/sqrt(var+eps)) for the instance norm (E.py:23,58).
+   `scratch` = 2*n*c doubles, zeroed by the call. */
+int dge_instance_stats(const float* x_f32b, double* scratch, float* style, float* mean_rstd, int n, int c, int h,
+                       int w, float eps, void* stream);
+/* instance norm apply: F32B -> ACT (conv operand) and/or F32B */
+int dge_instance_norm(const float* x_f32b, const float* mean_rstd, void* out_act, float* out_f32b, int n, int c,
+                      int h, int w, int planes, void* stream);
+/* 2x2 average pool F32B -> ACT (residual branch, E.py:78) */
+int dge_avgpool_to_act(const float* x_f32b, void* out_act, int n, int c, int h, int w, int planes, void* stream);
+/* out = a*A' + b*B' where X' = 2x2 mean if pool else X; all F32B (E.py:76-84 when Cin==Cout) */
+int dge_blend(const float* a_src, const float* b_src, float* out, float a, float b, int pool, int n, int c,
+              int h_out, int w_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGE_B200_H_ */

@@ -1,0 +1,150 @@
+"""Kernel-level parity of the tcgen05 conv (dge_conv_forward) against a plain PyTorch fp32 reference
+of the same op (F.conv2d / F.conv_transpose2d with TF32 disabled), through the C ABI.
+
+Tolerances: split-precision bf16x3 (planes=2) 2e-4 of the output scale (observed ~1e-5);
+plain bf16 (planes=1) 3e-2.  The CUDA-core checker kernel shares packing + epilogue with the
+tcgen05 kernel and is run first so a failure localises to TMA/UMMA or to packing/epilogue.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup():
+    from dge_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return ops
+
+
+def _rel(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-20)).item()
+
+
+def _lrelu(v, slope, gain):
+    return torch.where(v < 0, v * slope, v) * gain
+
+
+PLAIN_CASES = [
+    # n, cin, cout, h, w, planes
+    (2, 32, 32, 16, 16, 2),
+    (1, 16, 16, 16, 8, 2),
+    (3, 64, 128, 20, 12, 2),
+    (2, 128, 256, 9, 17, 2),
+    (2, 64, 512, 8, 8, 2),
+    (2, 256, 64, 4, 4, 2),
+    (2, 32, 48, 33, 31, 2),
+    (2, 64, 64, 16, 16, 1),
+]
+
+
+@pytest.mark.parametrize("checker", [True, False], ids=["checker", "tcgen05"])
+@pytest.mark.parametrize("case", PLAIN_CASES, ids=lambda c: "n%d_ci%d_co%d_%dx%d_p%d" % c)
+def test_conv3x3_full_epilogue(case, checker):
+    ops = _setup()
+    n, cin, cout, h, w, planes = case
+    g = torch.Generator(device="cuda").manual_seed(1234 + cin + cout)
+    x = torch.randn(n, cin, h, w, device="cuda", generator=g)
+    wt = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / (3.0 * cin ** 0.5)
+    s_in = torch.rand(n, cin, device="cuda", generator=g) + 0.5
+    s_out = torch.rand(n, cout, device="cuda", generator=g) + 0.5
+    dm = torch.rand(n, cout, device="cuda", generator=g) + 0.5
+    bias = torch.randn(cout, device="cuda", generator=g)
+    noise = torch.randn(h, w, device="cuda", generator=g)
+    strength = 0.37
+
+    xa = ops.nchw_to_act(x, scale=s_in, planes=planes)
+    wpk = ops.pack_conv_weight(wt, scale=1.0, planes=planes)
+    res = ops.conv(xa, wpk, cout, ops.CONV_3X3, demod=dm, noise=noise, noise_scalar=strength, bias=bias, slope=0.2,
+                   gain=2 ** 0.5, out_act=True, out_scale=s_out, out_f32b=True, out_nchw=True, checker=checker)
+    torch.cuda.synchronize()
+
+    ref = F.conv2d(x * s_in[:, :, None, None], wt, padding=1) * dm[:, :, None, None]
+    ref = ref + noise[None, None] * strength + bias[None, :, None, None]
+    ref = _lrelu(ref, 0.2, 2 ** 0.5)
+    tol = 2e-4 if planes == 2 else 3e-2
+    assert _rel(res["nchw"], ref) < tol
+    assert _rel(res["f32b"].to_nchw(), ref) < tol
+    assert _rel(res["act"].to_nchw(), ref * s_out[:, :, None, None]) < (tol if planes == 2 else 4e-2)
+
+
+@pytest.mark.parametrize("checker", [True, False], ids=["checker", "tcgen05"])
+def test_conv3x3_encoder_epilogue_and_rgb(checker):
+    ops = _setup()
+    n, cin, cout, h, w = 2, 32, 64, 24, 16
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(n, cin, h, w, device="cuda", generator=g)
+    wt = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / (3.0 * cin ** 0.5)
+    nw = torch.randn(cout, device="cuda", generator=g)
+    bias = torch.randn(cout, device="cuda", generator=g)
+    noise = torch.randn(n, h, w, device="cuda", generator=g)
+    rgbw = torch.randn(n, 3, cout, device="cuda", generator=g)
+    rgb0 = torch.randn(n, 3, h, w, device="cuda", generator=g)
+    rgb = rgb0.clone()
+    xa = ops.nchw_to_act(x)
+    wpk = ops.pack_conv_weight(wt)
+    res = ops.conv(xa, wpk, cout, ops.CONV_3X3, noise=noise, noise_batched=True, noise_w=nw, bias=bias, slope=0.2,
+                   out_f32b=True, rgb_w=rgbw, rgb_out=rgb, checker=checker)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x, wt, padding=1) + noise[:, None] * nw[None, :, None, None] + bias[None, :, None, None]
+    ref = _lrelu(ref, 0.2, 1.0)
+    assert _rel(res["f32b"].to_nchw(), ref) < 2e-4
+    ref_rgb = rgb0 + torch.einsum("nchw,nkc->nkhw", ref, rgbw)
+    assert _rel(rgb, ref_rgb) < 2e-4
+
+
+@pytest.mark.parametrize("checker", [True, False], ids=["checker", "tcgen05"])
+@pytest.mark.parametrize("pool", [False, True])
+def test_conv1x1_blend(pool, checker):
+    ops = _setup()
+    n, cin, cout, h, w = 2, 32, 64, 12, 20
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(n, cin, h, w, device="cuda", generator=g)
+    wt = torch.randn(cout, cin, 1, 1, device="cuda", generator=g) / cin ** 0.5
+    bias = torch.randn(cout, device="cuda", generator=g)
+    src = torch.randn(n, cout, 2 * h if pool else h, 2 * w if pool else w, device="cuda", generator=g)
+    res = ops.conv(ops.nchw_to_act(x), ops.pack_conv_weight(wt), cout, ops.CONV_1X1, bias=bias,
+                   blend_src=ops.nchw_to_f32b(src), blend_pool=pool, blend_a=0.111, blend_b=0.889, out_f32b=True,
+                   checker=checker)
+    torch.cuda.synchronize()
+    s = F.avg_pool2d(src, 2, 2) if pool else src
+    ref = 0.111 * s + 0.889 * (F.conv2d(x, wt) + bias[None, :, None, None])
+    assert _rel(res["f32b"].to_nchw(), ref) < 2e-4
+
+
+UP_CASES = [(2, 32, 32, 8, 8), (2, 64, 32, 16, 16), (1, 64, 128, 9, 5), (2, 128, 256, 8, 8), (2, 32, 512, 4, 4)]
+
+
+@pytest.mark.parametrize("checker", [True, False], ids=["checker", "tcgen05"])
+@pytest.mark.parametrize("case", UP_CASES, ids=lambda c: "n%d_ci%d_co%d_%dx%d" % c)
+def test_up_conv_raw_and_fir(case, checker):
+    ops = _setup()
+    n, cin, cout, h, w = case
+    g = torch.Generator(device="cuda").manual_seed(99 + cout)
+    x = torch.randn(n, cin, h, w, device="cuda", generator=g)
+    wt = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / (3.0 * cin ** 0.5)
+    dm = torch.rand(n, cout, device="cuda", generator=g) + 0.5
+    bias = torch.randn(cout, device="cuda", generator=g)
+    noise = torch.randn(2 * h, 2 * w, device="cuda", generator=g)
+    s_out = torch.rand(n, cout, device="cuda", generator=g) + 0.5
+    res = ops.conv(ops.nchw_to_act(x), ops.pack_conv_weight(wt, flip=True), cout, ops.CONV_UP3X3, checker=checker)
+    torch.cuda.synchronize()
+    wf = wt.flip(2, 3).permute(1, 0, 2, 3).contiguous()  # [in, out, k, k]
+    raw_ref = F.conv_transpose2d(x, wf, stride=2)
+    raw = ops.F32B.__new__(ops.F32B)
+    raw.n, raw.c, raw.h, raw.w, raw.t = n, cout, 2 * h + 1, 2 * w + 1, res["raw_up"]
+    assert _rel(raw.to_nchw(), raw_ref) < 2e-4
+
+    fir = torch.tensor([1., 3., 3., 1.], device="cuda")
+    k2 = torch.outer(fir, fir)
+    k2 = (k2 / k2.sum() * 4.0)[None, None]
+    y = F.conv2d(F.pad(raw_ref, (1, 1, 1, 1)).reshape(n * cout, 1, 2 * h + 3, 2 * w + 3), k2).reshape(n, cout, 2 * h, 2 * w)
+    y = y * dm[:, :, None, None] + noise[None, None] * 0.5 + bias[None, :, None, None]
+    y = _lrelu(y, 0.2, 2 ** 0.5)
+    out = ops.up_fir_epilogue(res["raw_up"], n, cout, 2 * h, 2 * w, demod=dm, noise=noise, noise_scalar=0.5, bias=bias,
+                              slope=0.2, gain=2 ** 0.5, out_scale=s_out, out_act=True, out_nchw=True)
+    torch.cuda.synchronize()
+    assert _rel(out["nchw"], y) < 2e-4
+    assert _rel(out["act"].to_nchw(), y * s_out[:, :, None, None]) < 2e-4
