@@ -1,0 +1,126 @@
+"""Generate the golden fixtures in this directory by importing the UNMODIFIED reference.
+
+Run once in the dev container (needs /root/reference or $DGE_REF; neither exists on the GPU box):
+    python tests/golden/make_golden.py
+The fixtures pin oracle/ (tests/test_oracle_golden.py) and, on the GPU, the CUDA path
+(tests/test_golden_gpu.py).  Nothing else reads the reference.
+
+Small channel counts keep the files small; every zero-initialised parameter (bias, noise strength,
+noise weights, w_avg) is perturbed so that each term of the forward is exercised.
+"""
+import os
+import sys
+import types
+
+import torch
+
+REF = os.environ.get("DGE_REF", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def import_reference():
+    for n in ["matplotlib", "matplotlib.pyplot", "boto3", "botocore", "botocore.exceptions", "lpips", "tensorboardX"]:
+        sys.modules.setdefault(n, types.ModuleType(n))
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.modules["botocore.exceptions"].ClientError = Exception
+    sys.modules["botocore"].exceptions = sys.modules["botocore.exceptions"]
+    # the repo's own mirrored `model` package must not shadow the reference
+    sys.path[:] = [p for p in sys.path if "deep-gan-encoders_b200" not in p]
+    sys.path.insert(0, REF)
+
+
+def perturb(module, names, gen, scale=0.1):
+    with torch.no_grad():
+        for k, p in list(module.named_parameters()) + list(module.named_buffers()):
+            if any(k.endswith(s) for s in names):
+                p.copy_(torch.randn(p.shape, generator=gen) * scale)
+
+
+def clone_sd(m):
+    return {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
+def main():
+    import_reference()
+    import model.stylegan2_generator as sg2
+    import model.E.E as E
+
+    torch.set_grad_enabled(False)
+    gen = torch.Generator().manual_seed(4321)
+
+    # ---- StyleGAN2, resolution 32, <=64 channels, 64-d latent spaces ---------------------------
+    torch.manual_seed(1234)
+    cfg = dict(resolution=32, z_space_dim=64, w_space_dim=64, mapping_fmaps=64, fmaps_base=1024, fmaps_max=64)
+    G = sg2.StyleGAN2Generator(**cfg).eval()
+    perturb(G, ["bias", "noise_strength", "w_avg"], gen)
+    z = torch.randn(2, 64, generator=gen)
+    out = G(z, trunc_psi=0.7, trunc_layers=4, randomize_noise=False)
+    fx = {"config": cfg, "state_dict": clone_sd(G), "z": z, "trunc_psi": 0.7, "trunc_layers": 4,
+          "w": out["w"], "wp": out["wp"], "image": out["image"],
+          "styles": {k: v for k, v in out.items() if k.startswith("style") or k.startswith("output_style")}}
+    # per-block vectors (standalone ModulateConvBlock.forward): plain, up, ToRGB
+    blocks = {}
+    x = G.synthesis.early_layer(out["wp"][:, 0])
+    for idx in range(G.synthesis.num_layers - 1):
+        layer = getattr(G.synthesis, f"layer{idx}")
+        y, style = layer(x, out["wp"][:, idx])
+        blocks[f"layer{idx}"] = {"x": x.clone(), "w": out["wp"][:, idx].clone(), "y": y.clone(), "style": style.clone()}
+        x = y
+        if idx % 2 == 0:
+            o = getattr(G.synthesis, f"output{idx // 2}")
+            rgb, style = o(x, out["wp"][:, idx + 1])
+            blocks[f"output{idx // 2}"] = {"x": x.clone(), "w": out["wp"][:, idx + 1].clone(), "y": rgb.clone(),
+                                           "style": style.clone()}
+    fx["blocks"] = blocks
+    # randomize_noise=True restated with explicit noise: seed the global generator, record the draws
+    torch.manual_seed(77)
+    out_rn = G.synthesis(out["wp"], randomize_noise=True)
+    fx["image_randnoise_seed77"] = out_rn["image"]
+    torch.save(fx, os.path.join(HERE, "sg2_res32.pt"))
+    print("sg2_res32.pt: image", tuple(out["image"].shape), float(out["image"].mean()), float(out["image"].std()))
+
+    # ---- encoder BE(startf=16, maxf=64, layer_count=4) on 32x32 images ---------------------------
+    torch.manual_seed(4242)
+    ecfg = dict(startf=16, maxf=64, layer_count=4, latent_size=512, channels=3)
+    Enc = E.BE(**ecfg).eval()
+    perturb(Enc, ["noise_weight_1", "noise_weight_2", "bias_1", "bias_2", "bias"], gen)
+    img = out["image"].clone()
+    torch.manual_seed(99)
+    const, w = Enc(img)
+    efx = {"config": ecfg, "state_dict": clone_sd(Enc), "img": img, "noise_seed": 99, "const": const, "w": w}
+    # per-block vectors
+    x = Enc.FromRGB(img)
+    efx["from_rgb"] = x.clone()
+    eb = {}
+    torch.manual_seed(5)
+    for i, blk in enumerate(Enc.decode_block):
+        y, w1, w2 = blk(x)
+        eb[i] = {"x": x.clone(), "y": y.clone(), "w1": w1.clone(), "w2": w2.clone()}
+        x = y
+    efx["blocks_seed5"] = eb
+    torch.save(efx, os.path.join(HERE, "be_s16_l4.pt"))
+    print("be_s16_l4.pt: const", tuple(const.shape), float(const.mean()), float(const.std()), "w", tuple(w.shape))
+
+    # ---- E -> G round trip (the benchmark's data flow, E_align_s2.py:153,160), small ----------------
+    # encoder with 64-d latent is impossible (view(...,512) is hard-coded, E.py:131), so use a 512-d G
+    torch.manual_seed(2024)
+    cfg2 = dict(resolution=32, fmaps_base=512, fmaps_max=32, mapping_layers=1)   # w/z 512-d, channels 32,32,32,16
+    G2 = sg2.StyleGAN2Generator(**cfg2).eval()
+    perturb(G2, ["bias", "noise_strength", "w_avg"], gen)
+    torch.manual_seed(4243)
+    E2 = E.BE(startf=16, maxf=32, layer_count=4, latent_size=512, channels=3).eval()
+    perturb(E2, ["noise_weight_1", "noise_weight_2", "bias_1", "bias_2", "bias"], gen)
+    z2 = torch.randn(2, 512, generator=gen)
+    r1 = G2(z2, trunc_psi=0.7, trunc_layers=8, randomize_noise=False)
+    torch.manual_seed(123)
+    c2, w2_ = E2(r1["image"])
+    img2 = G2.synthesis(w2_)["image"]
+    torch.save({"g_config": cfg2, "e_config": dict(startf=16, maxf=32, layer_count=4, latent_size=512, channels=3),
+                "g_state_dict": clone_sd(G2), "e_state_dict": clone_sd(E2), "z": z2, "imgs1": r1["image"],
+                "wp1": r1["wp"], "noise_seed": 123, "const2": c2, "w2": w2_, "imgs2": img2},
+               os.path.join(HERE, "e2g_res32.pt"))
+    print("e2g_res32.pt: imgs2", tuple(img2.shape), float(img2.mean()), float(img2.std()))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,111 @@
+"""Pin oracle/ (the CPU restatement) against fixtures produced by the unmodified reference
+(tests/golden/make_golden.py).  CPU only; fp32; tolerance 2e-5 of the output scale."""
+import os
+
+import pytest
+import torch
+
+from oracle import encoder as oenc
+from oracle import stylegan2 as osg2
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 2e-5
+
+
+def rel(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-20)).item()
+
+
+@pytest.fixture(scope="module")
+def sg2():
+    return torch.load(os.path.join(GOLD, "sg2_res32.pt"))
+
+
+@pytest.fixture(scope="module")
+def be():
+    return torch.load(os.path.join(GOLD, "be_s16_l4.pt"))
+
+
+def test_sg2_mapping_truncation(sg2):
+    sd = sg2["state_dict"]
+    w = osg2.mapping(sd, sg2["z"])
+    assert rel(w, sg2["w"]) < TOL
+    wp = osg2.truncation(w, sd["truncation.w_avg"], 8, sg2["trunc_psi"], sg2["trunc_layers"])
+    assert rel(wp, sg2["wp"]) < TOL
+
+
+def test_sg2_blocks(sg2):
+    sd = sg2["state_dict"]
+    for name, b in sg2["blocks"].items():
+        if name.startswith("layer"):
+            idx = int(name[5:])
+            y, style = osg2.modulate_conv_block(sd, f"synthesis.{name}.", b["x"], b["w"], up=(idx % 2 == 1))
+        else:
+            y, style = osg2.modulate_conv_block(sd, f"synthesis.{name}.", b["x"], b["w"], ksize=1, demodulate=False,
+                                                add_noise=False, lrelu=False)
+        assert rel(style, b["style"]) < TOL, name
+        assert rel(y, b["y"]) < TOL, name
+
+
+def test_sg2_synthesis_and_generator(sg2):
+    sd = sg2["state_dict"]
+    out = osg2.synthesis(sd, sg2["wp"], 32)
+    assert rel(out["image"], sg2["image"]) < TOL
+    for k, v in sg2["styles"].items():
+        assert rel(out[k], v) < TOL, k
+    full = osg2.generator(sd, sg2["z"], 32, trunc_psi=sg2["trunc_psi"], trunc_layers=sg2["trunc_layers"])
+    assert rel(full["image"], sg2["image"]) < TOL
+
+
+def test_sg2_randomize_noise_stream(sg2):
+    """randomize_noise=True: torch.randn(N,1,res,res) per layer in layer order (stylegan2_generator.py:912-913)."""
+    sd = sg2["state_dict"]
+    torch.manual_seed(77)
+    res_of = lambda idx: 4 * 2 ** ((idx + 1) // 2)
+    noises = {idx: torch.randn(2, 1, res_of(idx), res_of(idx)) for idx in range(7)}
+    out = osg2.synthesis(sd, sg2["wp"], 32, noises=noises)
+    assert rel(out["image"], sg2["image_randnoise_seed77"]) < TOL
+
+
+def test_skip_upsample_is_bilinear_like():
+    """the skip upsample equals depthwise conv_transpose2d(fir, stride 2, padding 1)."""
+    import torch.nn.functional as F
+    x = torch.randn(2, 3, 5, 7)
+    k = osg2.fir_kernel(4.0).repeat(3, 1, 1, 1)
+    ref = F.conv_transpose2d(x, k, stride=2, padding=1, groups=3)
+    assert rel(osg2.upsample_skip(x), ref) < 1e-6
+
+
+def test_be_from_rgb_and_blocks(be):
+    sd = be["state_dict"]
+    x = oenc.from_rgb(sd, be["img"])
+    assert rel(x, be["from_rgb"]) < TOL
+    torch.manual_seed(5)
+    for i, b in be["blocks_seed5"].items():
+        y, w1, w2 = oenc.be_block(sd, f"decode_block.{i}.", b["x"])
+        assert rel(y, b["y"]) < TOL, i
+        assert rel(w1, b["w1"]) < TOL, i
+        assert rel(w2, b["w2"]) < TOL, i
+
+
+def test_be_forward(be):
+    torch.manual_seed(be["noise_seed"])
+    const, w = oenc.be_forward(be["state_dict"], be["img"], be["config"]["layer_count"])
+    assert rel(const, be["const"]) < TOL
+    assert rel(w, be["w"]) < TOL
+
+
+def test_e2g_roundtrip():
+    fx = torch.load(os.path.join(GOLD, "e2g_res32.pt"))
+    gsd, esd = fx["g_state_dict"], fx["e_state_dict"]
+    full = osg2.generator(gsd, fx["z"], 32, trunc_psi=0.7, trunc_layers=8) if False else None
+    w = osg2.mapping(gsd, fx["z"], num_layers=1)
+    wp = osg2.truncation(w, gsd["truncation.w_avg"], 8, 0.7, 8)
+    assert rel(wp, fx["wp1"]) < TOL
+    imgs1 = osg2.synthesis(gsd, wp, 32)["image"]
+    assert rel(imgs1, fx["imgs1"]) < TOL
+    torch.manual_seed(fx["noise_seed"])
+    c2, w2 = oenc.be_forward(esd, fx["imgs1"], 4)
+    assert rel(c2, fx["const2"]) < TOL and rel(w2, fx["w2"]) < TOL
+    imgs2 = osg2.synthesis(gsd, fx["w2"], 32)["image"]
+    assert rel(imgs2, fx["imgs2"]) < TOL
