@@ -221,6 +221,34 @@ __global__ void k_act_to_nchw(const void* __restrict__ act, float* __restrict__ 
   }
 }
 
+__global__ void k_f32b_to_act(const float* __restrict__ x, void* __restrict__ act, int n, int c, int h, int w,
+                              int planes) {
+  const int C8 = c >> 3;
+  const size_t total = (size_t)n * C8 * h * w;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const Idx4 q = decode4(i, C8, h, w);
+    float v[8];
+    load8_f32b(x, i, v);
+    store8_act(act, q.n, q.g, q.y, q.x, C8, planes, h, w, v);
+  }
+}
+
+// standalone ToRGB (1x1 modulated conv, no demod): NCHW in, NCHW out; one thread per (n, y, x)
+__global__ void k_to_rgb_nchw(const float* __restrict__ x, const float* __restrict__ rgb_w,
+                              const float* __restrict__ bias, float* __restrict__ out, int n, int c, int nch, int hw) {
+  const size_t total = (size_t)n * hw;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / hw);
+    const size_t pix = i % hw;
+    for (int ch = 0; ch < nch; ++ch) {
+      float s = bias ? bias[ch] : 0.f;
+      const float* wv = rgb_w + ((size_t)b * nch + ch) * c;
+      for (int k = 0; k < c; ++k) s = fmaf(x[((size_t)b * c + k) * hw + pix], wv[k], s);
+      out[((size_t)b * nch + ch) * hw + pix] = s;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // StyleGAN2 up path: 4x4 FIR over the raw (2H+1)x(2W+1) transposed-conv map, then the layer epilogue.
 //   out[y][x] = sum_{a,b} f[a] f[b] t[y+a-1][x+b-1],  f = [1,3,3,1]/4   (kernel/sum*gain^2 = outer/64*4)
@@ -561,6 +589,18 @@ int dge_act_to_nchw(const void* act, float* out, int n, int c, int h, int w, int
   REQ_NCHW("act_to_nchw");
   DGE_REQUIRE(planes == 1 || planes == 2, "act_to_nchw: planes=%d", planes);
   LAUNCH_1D(k_act_to_nchw, (size_t)n * (c / 8) * h * w, stream, act, out, n, c, h, w, planes);
+}
+
+int dge_f32b_to_act(const float* x, void* act, int n, int c, int h, int w, int planes, void* stream) {
+  DGE_REQUIRE(x && act, "f32b_to_act: null pointer");
+  REQ_NCHW("f32b_to_act");
+  DGE_REQUIRE(planes == 1 || planes == 2, "f32b_to_act: planes=%d", planes);
+  LAUNCH_1D(k_f32b_to_act, (size_t)n * (c / 8) * h * w, stream, x, act, n, c, h, w, planes);
+}
+int dge_to_rgb_nchw(const float* x, const float* rgb_w, const float* bias, float* out, int n, int c, int nch, int h,
+                    int w, void* stream) {
+  DGE_REQUIRE(x && rgb_w && out && n > 0 && c > 0 && nch > 0 && h > 0 && w > 0, "to_rgb_nchw: bad args");
+  LAUNCH_1D(k_to_rgb_nchw, (size_t)n * h * w, stream, x, rgb_w, bias, out, n, c, nch, h * w);
 }
 
 int dge_up_fir_epilogue(const float* raw_up, const float* demod, const float* noise, int64_t noise_bstride,

@@ -55,6 +55,8 @@ SIGNATURES = {
     "dge_nchw_to_f32b": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     "dge_f32b_to_nchw": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     "dge_act_to_nchw": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "dge_f32b_to_act": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "dge_to_rgb_nchw": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "dge_up_fir_epilogue": (c_int, [P, P, P, c_int64, c_float, P, c_float, c_float, P, P, P,
                                     c_int, c_int, c_int, c_int, c_int, P]),
     "dge_rgb_init": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),

@@ -93,6 +93,23 @@ def nchw_to_f32b(x):
     return out
 
 
+def f32b_to_act(x, planes=2):
+    assert isinstance(x, F32B)
+    out = Act(x.n, x.c, x.h, x.w, planes, x.t.device)
+    check(lib().dge_f32b_to_act(_p(x.t), _p(out.t), x.n, x.c, x.h, x.w, planes, _stream()))
+    return out
+
+
+def to_rgb_nchw(x, rgb_w, bias):
+    x = x.contiguous()
+    n, c, h, w = x.shape
+    nch = rgb_w.shape[1]
+    out = torch.empty((n, nch, h, w), dtype=torch.float32, device=x.device)
+    bb = None if bias is None else bias.detach().contiguous()
+    check(lib().dge_to_rgb_nchw(_f32(x), _f32(rgb_w), _f32(bb), _p(out), n, c, nch, h, w, _stream()))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # weights
 # ------------------------------------------------------------------------------------------------

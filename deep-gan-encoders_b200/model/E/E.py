@@ -1,0 +1,130 @@
+"""B200-native case-1 encoder -- drop-in for the reference's `model/E/E.py` (BEBlock :16-85, BE :88-135).
+
+Same classes, constructor arguments, `forward` signature/returns and state_dict keys (SURVEY
+Appendix A).  Per block the reference issues ~25 ATen kernels; here it is
+  stats -> GEMV -> IN-apply(+bf16 split) -> tcgen05 conv [noise, bias, lrelu fused]      (x2)
+  -> tcgen05 1x1 residual conv whose epilogue does the 2x2 pools and the 0.111/0.889 blend.
+Noise: the reference draws `torch.randn([N,1,H,W])` on the CPU inside each conv stage (E.py:60,73);
+`noise_mode = 'reference'` (default) does exactly that (same RNG stream => bit-identical noise),
+`'device'` draws on the GPU instead (no H2D copy; different stream).
+"""
+import torch
+import torch.nn as nn
+
+import model.utils.lreq as ln
+from model.utils.net import FromRGB
+from dge_b200 import ops
+
+DEFAULT_PLANES = 2
+
+
+class BEBlock(nn.Module):
+    def __init__(self, inputs, outputs, latent_size, has_last_conv=True, fused_scale=True):
+        super().__init__()
+        self.has_last_conv = has_last_conv
+        self.noise_weight_1 = nn.Parameter(torch.zeros(1, inputs, 1, 1))
+        self.bias_1 = nn.Parameter(torch.zeros(1, inputs, 1, 1))
+        self.instance_norm_1 = nn.InstanceNorm2d(inputs, affine=False, eps=1e-8)
+        self.inver_mod1 = ln.Linear(2 * inputs, latent_size, gain=1)
+        self.conv_1 = ln.Conv2d(inputs, inputs, 3, 1, 1, bias=False)
+        self.noise_weight_2 = nn.Parameter(torch.zeros(1, outputs, 1, 1))
+        self.bias_2 = nn.Parameter(torch.zeros(1, outputs, 1, 1))
+        self.instance_norm_2 = nn.InstanceNorm2d(inputs, affine=False, eps=1e-8)
+        self.inver_mod2 = ln.Linear(2 * inputs, latent_size, gain=1)
+        if has_last_conv:
+            if fused_scale:
+                # E.py:32-33 -- never taken by E.BE (fused_scale is hard-wired False, :106)
+                raise NotImplementedError('fused_scale=True (strided conv) belongs to model/E/E_Blur.py')
+            self.conv_2 = ln.Conv2d(inputs, outputs, 3, 1, 1, bias=False)
+        self.fused_scale = fused_scale
+        self.inputs = inputs
+        self.outputs = outputs
+        if self.inputs != self.outputs:
+            self.conv_3 = ln.Conv2d(inputs, outputs, 1, 1, 0)
+        self.planes = DEFAULT_PLANES
+        self.noise_mode = 'reference'
+
+    def _noise(self, n, h, w, device):
+        if self.noise_mode == 'device':
+            return torch.randn([n, 1, h, w], device=device)
+        return torch.randn([n, 1, h, w]).to(device)   # E.py:60 -- CPU draw, then H2D
+
+    def run(self, x):
+        """x: F32B [N, inputs, H, W] -> (F32B out, w1, w2)."""
+        n, c, h, w = x.n, x.c, x.h, x.w
+        dev = x.t.device
+        eps = self.instance_norm_1.eps
+        style1, mr1 = ops.instance_stats(x, eps)                                   # E.py:51-53 + IN stats
+        w1 = ops.dense(style1, self.inver_mod1.weight, self.inver_mod1.bias)      # :54
+        xn, _ = ops.instance_norm(x, mr1, planes=self.planes)                      # :58
+        y1 = ops.conv(xn, self.conv_1.packed(self.planes), c, ops.CONV_3X3, noise=self._noise(n, h, w, dev),
+                      noise_batched=True, noise_w=self.noise_weight_1.detach().view(-1),
+                      bias=self.bias_1.detach().view(-1), slope=0.2, out_f32b=True)['f32b']      # :59-62
+        style2, mr2 = ops.instance_stats(y1, self.instance_norm_2.eps)             # :64-66
+        w2 = ops.dense(style2, self.inver_mod2.weight, self.inver_mod2.bias)      # :67
+        if self.has_last_conv:
+            y1n, _ = ops.instance_norm(y1, mr2, planes=self.planes)                # :69
+            y2 = ops.conv(y1n, self.conv_2.packed(self.planes), self.outputs, ops.CONV_3X3,
+                          noise=self._noise(n, h, w, dev), noise_batched=True,
+                          noise_w=self.noise_weight_2.detach().view(-1), bias=self.bias_2.detach().view(-1),
+                          slope=0.2, out_f32b=True)['f32b']                        # :72-75
+            if self.inputs != self.outputs:
+                rp = ops.avgpool_to_act(x, planes=self.planes)                     # :78
+                out = ops.conv(rp, self.conv_3.packed(self.planes), self.outputs, ops.CONV_1X1,
+                               bias=self.conv_3.scaled_bias(), blend_src=y2, blend_pool=True, blend_a=0.111,
+                               blend_b=0.889, out_f32b=True)['f32b']               # :76-77, 81-84
+            else:
+                out = ops.blend(y2, x, 0.111, 0.889, pool=True)
+        else:
+            _, y1n = ops.instance_norm(y1, mr2, out_act=False, out_f32b=True)      # :69
+            if self.inputs != self.outputs:
+                out = ops.conv(ops.f32b_to_act(x, self.planes), self.conv_3.packed(self.planes), self.outputs,
+                               ops.CONV_1X1, bias=self.conv_3.scaled_bias(), blend_src=y1n, blend_pool=False,
+                               blend_a=0.111, blend_b=0.889, out_f32b=True)['f32b']
+            else:
+                out = ops.blend(y1n, x, 0.111, 0.889, pool=False)
+        return out, w1, w2
+
+    def forward(self, x):
+        """Reference signature: NCHW in -> (NCHW out, w1, w2)."""
+        ln._guard('BEBlock', x, self.conv_1.weight)
+        out, w1, w2 = self.run(ops.nchw_to_f32b(x.float()))
+        return out.to_nchw(), w1, w2
+
+
+class BE(nn.Module):
+    def __init__(self, startf=16, maxf=512, layer_count=9, latent_size=512, channels=3):
+        super().__init__()
+        self.maxf = maxf
+        self.startf = startf
+        self.latent_size = latent_size
+        self.layer_to_resolution = [0 for _ in range(layer_count)]
+        self.decode_block = nn.ModuleList()
+        self.layer_count = layer_count
+        inputs = startf
+        outputs = startf * 2
+        resolution = 1024
+        self.FromRGB = FromRGB(channels, inputs)
+        for i in range(layer_count):
+            has_last_conv = i + 1 != layer_count
+            block = BEBlock(inputs, outputs, latent_size, has_last_conv, fused_scale=False)
+            inputs = min(maxf, inputs * 2)
+            outputs = min(maxf, outputs * 2)
+            self.layer_to_resolution[i] = resolution
+            resolution /= 2
+            self.decode_block.append(block)
+
+    def set_noise_mode(self, mode):
+        assert mode in ('reference', 'device')
+        for b in self.decode_block:
+            b.noise_mode = mode
+
+    def forward(self, x, block_num=9):
+        ln._guard('BE', x, self.FromRGB.from_rgb.weight)
+        f = self.FromRGB.run(x)
+        w = torch.tensor(0)
+        for i in range(9 - block_num, self.layer_count):
+            f, w1, w2 = self.decode_block[i].run(f)
+            w_ = torch.cat((w2.view(f.n, 1, 512), w1.view(f.n, 1, 512)), dim=1)   # E.py:131 (512 is hard-coded)
+            w = w_ if i == (9 - block_num) else torch.cat((w_, w), dim=1)
+        return f.to_nchw(), w

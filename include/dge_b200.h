@@ -122,6 +122,11 @@ int dge_nchw_to_act(const float* x, int64_t x_bstride, const float* scale, void*
 int dge_nchw_to_f32b(const float* x, float* out, int n, int c, int h, int w, void* stream);
 int dge_f32b_to_nchw(const float* x, float* out, int n, int c, int h, int w, void* stream);
 int dge_act_to_nchw(const void* act, float* out, int n, int c, int h, int w, int planes, void* stream);
+int dge_f32b_to_act(const float* x, void* act, int n, int c, int h, int w, int planes, void* stream);
+/* standalone ToRGB on NCHW input: out[n][ch] = bias[ch] + sum_c x[n][c]*rgb_w[n][ch][c]
+   (ModulateConvBlock k=1, demodulate=False, stylegan2_generator.py:462-474) */
+int dge_to_rgb_nchw(const float* x, const float* rgb_w, const float* bias, float* out, int n, int c, int nch, int h,
+                    int w, void* stream);
 
 /* 4x4 FIR ([1,3,3,1]x[1,3,3,1]/16, pad 1) over the raw up-conv map + demod + noise + bias + lrelu*gain,
    output ACT times out_scale (stylegan2_generator.py:603-615 with filter padding (1,1,1,1), :907-921) */

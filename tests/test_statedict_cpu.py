@@ -1,0 +1,100 @@
+"""Host-side (no GPU) checks: the mirrored modules keep the reference's state_dict layout, attributes and error
+behaviour; the C-ABI library loads and exports every symbol include/dge_b200.h declares."""
+import os
+import re
+
+import pytest
+import torch
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from dge_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "dge_b200.h")).read()
+    declared = set(re.findall(r"\b(dge_[a-z0-9_]+)\s*\(", header))
+    declared -= {"dge_conv_args"}
+    lib = _lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/dge_b200.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+    assert lib.dge_version() >= 100
+
+
+def test_conv_args_struct_matches_header():
+    import ctypes
+    from dge_b200._lib import ConvArgs
+    assert ctypes.sizeof(ConvArgs) == 192
+    assert ConvArgs.noise_bstride.offset == 64 and ConvArgs.out_raw_up.offset == 184
+
+
+def test_sg2_state_dict_layout_matches_reference():
+    from model.stylegan2_generator import StyleGAN2Generator
+    fx = torch.load(os.path.join(GOLD, "sg2_res32.pt"))
+    G = StyleGAN2Generator(**fx["config"])
+    ref = fx["state_dict"]
+    mine = G.state_dict()
+    assert set(mine.keys()) == set(ref.keys())
+    for k in ref:
+        assert tuple(mine[k].shape) == tuple(ref[k].shape), k
+        assert mine[k].dtype == ref[k].dtype, k
+    G.load_state_dict(ref, strict=True)
+    assert "synthesis.layer1.weight" in G.pth_to_tf_var_mapping
+
+
+def test_sg2_1024_key_count_and_shapes():
+    """StyleGAN2Generator(1024) has 165 state_dict entries."""
+    from model.stylegan2_generator import StyleGAN2Generator
+    with torch.device("meta"):
+        G = StyleGAN2Generator(1024)
+    sd = G.state_dict()
+    assert len(sd) == 165
+    assert tuple(sd["synthesis.layer16.weight"].shape) == (32, 32, 3, 3)
+    assert tuple(sd["synthesis.layer15.filter.kernel"].shape) == (1, 1, 4, 4)
+    assert tuple(sd["synthesis.output8.weight"].shape) == (3, 32, 1, 1)
+    assert tuple(sd["synthesis.layer9.style.weight"].shape) == (512, 512)
+    assert tuple(sd["synthesis.upsample.kernel"].shape) == (1, 1, 4, 4)
+
+
+def test_sg2_errors():
+    from model.stylegan2_generator import StyleGAN2Generator
+    with pytest.raises(ValueError):
+        StyleGAN2Generator(100)
+    with pytest.raises(ValueError):
+        StyleGAN2Generator(32, architecture="bogus")
+    G = StyleGAN2Generator(8, z_space_dim=16, w_space_dim=16, mapping_fmaps=16, fmaps_base=128, fmaps_max=16)
+    with pytest.raises(ValueError):
+        G.mapping(torch.zeros(2, 3))
+    with pytest.raises(ValueError):
+        G.synthesis(torch.zeros(2, 3, 16))
+
+
+def test_be_state_dict_layout_and_lreq_coefs():
+    from model.E.E import BE
+    fx = torch.load(os.path.join(GOLD, "be_s16_l4.pt"))
+    E = BE(**fx["config"])
+    ref = fx["state_dict"]
+    mine = E.state_dict()
+    assert list(mine.keys()) == list(ref.keys())        # same keys, same (registration) order
+    for k in ref:
+        assert tuple(mine[k].shape) == tuple(ref[k].shape), k
+    E.load_state_dict(ref, strict=True)
+    # lr_equalization_coef contract read by LREQAdam (lreq.py:60-62,118-120)
+    c = E.decode_block[0].conv_1
+    assert abs(c.weight.lr_equalization_coef - (2 ** 0.5) / (9 * 16) ** 0.5) < 1e-7
+    lin = E.decode_block[0].inver_mod1
+    assert abs(lin.weight.lr_equalization_coef - 1.0 / (32 ** 0.5)) < 1e-7
+    assert E.decode_block[0].conv_3.bias.lr_equalization_coef == 1.0
+    assert not hasattr(E.decode_block[0].bias_1, "lr_equalization_coef")
+
+
+def test_product_path_fails_loudly_without_gpu():
+    """No CPU fallback: CPU tensors raise instead of silently computing something else."""
+    from dge_b200 import DgeError
+    from model.E.E import BE
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    E = BE(16, 32, 2, 512, 3)
+    with torch.no_grad(), pytest.raises(DgeError):
+        E(torch.zeros(1, 3, 8, 8))
