@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- E+G forward images/s on StyleGAN2-FFHQ-1024 (BASELINE.json metric / configs[2]).
+
+One "step" = the two forwards every iteration of the reference training loop performs
+(E_align_s2.py:153,160) on one batch of 8 synthetic 1024x1024 images per GPU:
+    const2, w2 = E(imgs1);  imgs2 = G.synthesis(w2)['image']
+with E = BE(startf=16, maxf=512, layer_count=9) and G = StyleGAN2Generator(1024), random-init
+weights (no checkpoints offline), fp32-equivalent split-precision bf16x3 tensor-core math.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+N > 1 is launched by the driver through torch.distributed.run (one rank per GPU); the path shards
+by sample with no data-path collective (forward-only => replicas), so scaling is "weak".
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "deep-gan-encoders_b200"))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "E+G fwd images/sec (StyleGAN2-FFHQ1024, bs=8)"
+UNIT = "images/s"
+RES, BATCH, STARTF, LAYERS = 1024, 8, 16, 9
+# algorithmic dense-conv work per image (2*MAC): G synthesis 148.5 GFLOP + E 86.7 GFLOP
+GFLOP_PER_IMAGE = 235.2
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        if torch.cuda.is_available():
+            torch.cuda.set_device(local)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
+    return rank, world, local
+
+
+# -------------------------------------------------------------------------------------------------
+# synthetic weights / inputs
+# -------------------------------------------------------------------------------------------------
+def perturb_zero_init(module, seed):
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for k, p in list(module.named_parameters()) + list(module.named_buffers()):
+            if k.endswith(("bias", "noise_strength", "w_avg", "noise_weight_1", "noise_weight_2", "bias_1", "bias_2")):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+
+
+def build_ours(device, res=RES, startf=STARTF, layers=LAYERS):
+    from model.E.E import BE
+    from model.stylegan2_generator import StyleGAN2Generator
+    torch.manual_seed(0)
+    G = StyleGAN2Generator(res).eval()
+    E = BE(startf, 512, layers, 512, 3).eval()
+    perturb_zero_init(G, 1)
+    perturb_zero_init(E, 2)
+    E.set_noise_mode("device")
+    return G.to(device), E.to(device)
+
+
+def oracle_state(res=RES, startf=STARTF, layers=LAYERS):
+    """Same seeded random-init weights as build_ours, as plain CPU state dicts for the oracle."""
+    G, E = build_ours("cpu", res, startf, layers)
+    return ({k: v.detach().float() for k, v in G.state_dict().items()},
+            {k: v.detach().float() for k, v in E.state_dict().items()})
+
+
+def oracle_step(gsd, esd, imgs1, res=RES, layers=LAYERS):
+    from oracle import encoder as oenc
+    from oracle import stylegan2 as osg2
+    const2, w2 = oenc.be_forward(esd, imgs1, layers)
+    return osg2.synthesis(gsd, w2, res)["image"], const2, w2
+
+
+def time_cpu_oracle(steps, warmup, batch=1):
+    torch.set_num_threads(os.cpu_count())
+    gsd, esd = oracle_state()
+    g = torch.Generator().manual_seed(3)
+    imgs1 = torch.randn(batch, 3, RES, RES, generator=g).clamp_(-1, 1)
+    with torch.no_grad():
+        for _ in range(warmup):
+            oracle_step(gsd, esd, imgs1)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            oracle_step(gsd, esd, imgs1)
+        dt = (time.perf_counter() - t0) / steps
+    return batch / dt, dt
+
+
+# -------------------------------------------------------------------------------------------------
+# arms
+# -------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank, world, _ = dist_setup(args.gpus)
+    if rank != 0:
+        return
+    ips, dt = time_cpu_oracle(args.steps, args.warmup, batch=1)
+    cores = os.cpu_count()
+    sample = ("batch 1 of the bs=8 workload per step (CPU images/s is batch-independent: SURVEY 6 measured 0.30 "
+              "img/s at N=1 vs 0.31 at N=8); torch fp32 MKL-DNN, oracle/ restatement of the reference forward "
+              "(the Python reference cannot travel to the GPU box)")
+    line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "StyleGAN2-FFHQ-1024 synthesis + BE(16,9) encoder forward, CPU",
+                       "sample_batch": 1},
+            "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    rank, world, local = dist_setup(args.gpus)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (ours) needs a B200; there is no CPU fallback (use --impl reference for the CPU arm)")
+    from dge_b200 import ops
+    dev = torch.device("cuda", local if world > 1 else 0)
+    torch.cuda.set_device(dev)
+    ops.lib()
+    G, E = build_ours(dev)
+    pk = peaks()
+
+    with torch.no_grad():
+        g = torch.Generator(device=dev).manual_seed(100 + rank)
+        z = torch.randn(BATCH, 512, device=dev, generator=g)
+        imgs1 = G(z, trunc_psi=0.7, trunc_layers=8, randomize_noise=False)["image"].contiguous()
+        imgs1_host = imgs1.cpu().pin_memory()
+        out_host = torch.empty((BATCH, 18 + 16, 512), dtype=torch.float32).pin_memory()  # w2 [8,18,512] + const2 [8,512,4,4]
+        mse_host = torch.empty((1,), dtype=torch.float32).pin_memory()
+
+        def step(x):
+            const2, w2 = E(x)
+            return G.synthesis(w2)["image"], const2, w2
+
+        def barrier():
+            if world > 1:
+                import torch.distributed as dist
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        def timed(fn, steps):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            barrier()
+            ms = e0.elapsed_time(e1)
+            if world > 1:
+                import torch.distributed as dist
+                t = torch.tensor([ms], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            return ms / steps
+
+        # ---- device-resident throughput ----------------------------------------------------------
+        for _ in range(max(args.warmup, 3)):
+            step(imgs1)
+        ops.launch_count_reset()
+        sampler = ClockSampler(dev.index or 0)
+        sampler.start()
+        ms = timed(lambda: step(imgs1), args.steps)
+        clocks = sampler.stop()
+        launches = ops.launch_count()
+
+        # ---- end to end: pinned host images in, latents + reconstruction MSE out, every step ---------
+        def e2e_step():
+            x = imgs1_host.to(dev, non_blocking=True)
+            img2, const2, w2 = step(x)
+            out_host[:, :18].copy_(w2, non_blocking=True)
+            out_host[:, 18:].copy_(const2.view(BATCH, 16, 512), non_blocking=True)
+            mse_host.copy_(((img2 - x) ** 2).mean().view(1), non_blocking=True)
+
+        for _ in range(2):
+            e2e_step()
+        ms_e2e = timed(e2e_step, args.steps)
+        h2d = imgs1_host.numel() * 4
+        d2h = out_host.numel() * 4 + 4
+
+        # ---- per-kernel roofline: CUDA events around every launch of one more step ------------------
+        with ops.profile() as rec:
+            for _ in range(3):
+                step(imgs1)
+        prof = rec.summary()
+
+    roof, top = roofline_from_profile(prof, pk)
+    ips = BATCH * world / (ms / 1e3)
+    ips_e2e = BATCH * world / (ms_e2e / 1e3)
+    line = {
+        "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16x3 (split bf16 hi+lo operands, fp32 accumulate: fp32-equivalent, meets the 1e-3 parity bar)",
+        "data": "synthetic",
+        "config": {"workload": "configs[2]: StyleGAN2-FFHQ-1024 synthesis + BE(startf=16, L=9) encoder forward, "
+                               "batch 8 per GPU, random-init weights, encoder noise drawn on device",
+                   "global_batch": BATCH * world, "parallelism": f"replicas x{world} (no data-path collective)",
+                   "l2": "per-step working set ~25 GB of activations >> 126 MB L2; no explicit flush"},
+        "e2e": {"value": ips_e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h,
+                "what": "pinned host imgs1 -> H2D -> E -> G.synthesis -> D2H of (w2, const2) + recon MSE scalar"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roof,
+        "achieved_conv_tflops": GFLOP_PER_IMAGE * ips / world / 1e3,
+        "top_kernels": top,
+        "peaks": pk,
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            cips, cdt = time_cpu_oracle(1, 1, batch=1)
+            line["cpu_baseline"] = {"value": cips, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                    "sample": "1 warm-up + 1 timed step at batch 1 of the same 1024 workload "
+                                              f"({cdt:.1f} s), oracle/ torch-fp32 restatement, all host threads"}
+        print(json.dumps(line), flush=True)
+
+
+def conv_flops(key, name):
+    n, h, w, cin, cout = key[:5]
+    taps = 1 if name == "conv1x1" else 9
+    return 2.0 * n * h * w * cin * cout * taps     # conv_up3x3: transposed conv over the INPUT grid
+
+
+def conv_bytes(key, name):
+    """compulsory HBM bytes: read the ACT operand once, write the output once (4 B/element each in bf16x3 mode)."""
+    n, h, w, cin, cout, planes = key
+    out_px = (2 * h + 1) * (2 * w + 1) if name == "conv_up3x3" else h * w
+    return n * (h * w * cin * 2 * planes + out_px * cout * 4)
+
+
+def roofline_from_profile(prof, pk):
+    rows = []
+    for (name, key), (cnt, ms) in prof.items():
+        rows.append({"kernel": name, "key": list(key), "launches": cnt, "ms_per_launch": ms / cnt, "ms_total": ms})
+    total = sum(r["ms_total"] for r in rows) or 1.0
+    rows.sort(key=lambda r: -r["ms_total"])
+    for r in rows:
+        r["share"] = r["ms_total"] / total
+    top = rows[:12]
+    conv = [r for r in rows if r["kernel"].startswith("conv")]
+    if not conv:
+        return None, top
+    d = conv[0]
+    key, name = tuple(d["key"]), d["kernel"]
+    fl, by = conv_flops(key, name), conv_bytes(key, name)
+    sec = d["ms_per_launch"] / 1e3
+    t_tc = fl * 3 / (pk["bf16_tflops_sustained"] * 1e12)      # bf16x3 issues 3 MMAs per algorithmic MAC
+    t_hbm = by / (pk["hbm_gbs"] * 1e9)
+    if t_tc >= t_hbm:
+        roof = {"bound": "tensor", "achieved": fl / sec / 1e12, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": fl / sec / 1e12 / pk["bf16_tflops_sustained"], "traffic": None,
+                "note": "algorithmic conv FLOPs (2*MAC) over the CUDA-event launch time; the parity mode spends 3 bf16 "
+                        "MMAs per MAC, so frac <= 0.333 by construction (x3 = tensor-pipe occupancy)"}
+    else:
+        roof = {"bound": "hbm", "achieved": by / sec / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": by / sec / 1e9 / pk["hbm_gbs"], "traffic": None}
+    roof["kernel"] = f"{name} n,h,w,cin,cout,planes={list(key)}"
+    roof["peak_source"] = pk["source"] + " (sustained bf16 / copy bandwidth, MEASURED_PEAKS.json)"
+    return roof, top
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

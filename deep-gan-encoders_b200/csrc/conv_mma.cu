@@ -107,6 +107,38 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+// epilogue-side wait: back off between polls so the spinning warps do not steal issue slots from the
+// single MMA-issuing lane that shares their SM sub-partition
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!done) {
+      __nanosleep(spin < 64 ? 32 : 256);
+      if (spin > (1u << 24)) {
+        printf("dge conv_mma: epilogue mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+        __trap();
+      }
+    }
+  }
+}
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred;
+}
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2,
                                             int c3) {
   asm volatile(
@@ -338,88 +370,96 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   if (warp == 0) {
     // =================================== TMA producer ===================================
-    if (lane == 0) {
-      const int kc8p = (p.kc >> 3) * p.planes;
-      uint32_t a_it = 0, b_it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
-        for (int ch = 0; ch < p.nchunks; ++ch) {
-          const uint32_t slot = a_it & 1, ph = (a_it >> 1) & 1;
-          mbar_wait(&a_empty[slot], ph ^ 1);
-          mbar_arrive_expect_tx(&a_full[slot], (uint32_t)p.a_slot_bytes);
-          tma_load_4d(a_smem + slot * p.a_slot_bytes, &tmA, &a_full[slot], 2 * (t.x0 - 1), t.y0 - 1, ch * kc8p, t.n);
-          ++a_it;
-          for (int e = 0; e < p.ntaps; ++e) {
-            const int q = p.taps[e].phase - t.p0;
-            if (q < 0 || q >= p.np) continue;
-            const uint32_t bs = b_it % p.b_slots, bph = (b_it / p.b_slots) & 1;
-            mbar_wait(&b_empty[bs], bph ^ 1);
-            mbar_arrive_expect_tx(&b_full[bs], (uint32_t)p.b_slot_bytes);
-            uint8_t* dst = b_smem + bs * p.b_slot_bytes;
+    // Whole warp runs the (warp-uniform) control flow; one elected lane issues.  Keeping the flow uniform lets
+    // the compiler hold addresses/descriptors in uniform registers instead of waterfall loops.
+    const int kc8p = (p.kc >> 3) * p.planes;
+    uint32_t a_slot = 0, a_ph = 0, b_slot = 0, b_ph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      for (int ch = 0; ch < p.nchunks; ++ch) {
+        mbar_wait(&a_empty[a_slot], a_ph ^ 1);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&a_full[a_slot], (uint32_t)p.a_slot_bytes);
+          tma_load_4d(a_smem + a_slot * p.a_slot_bytes, &tmA, &a_full[a_slot], 2 * (t.x0 - 1), t.y0 - 1, ch * kc8p,
+                      t.n);
+        }
+        __syncwarp();
+        if (++a_slot == 2) { a_slot = 0; a_ph ^= 1; }
+        for (int e = 0; e < p.ntaps; ++e) {
+          const int q = p.taps[e].phase - t.p0;
+          if (q < 0 || q >= p.np) continue;
+          mbar_wait(&b_empty[b_slot], b_ph ^ 1);
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&b_full[b_slot], (uint32_t)p.b_slot_bytes);
+            uint8_t* dst = b_smem + b_slot * p.b_slot_bytes;
             for (int s = 0; s * p.nsub < p.cw; ++s)
-              tma_load_3d(dst + s * p.b_sub_bytes, &tmB, &b_full[bs], 2 * (t.co0 + s * p.nsub), ch * kc8p,
+              tma_load_3d(dst + s * p.b_sub_bytes, &tmB, &b_full[b_slot], 2 * (t.co0 + s * p.nsub), ch * kc8p,
                           p.taps[e].w_tap);
-            ++b_it;
           }
+          __syncwarp();
+          if (++b_slot == (uint32_t)p.b_slots) { b_slot = 0; b_ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // =================================== MMA issuer ======================================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(p.nsub);
-      const uint32_t a_lbo = p.planes * PATCH_BYTES, a_sbo = PW * 16;
-      const uint32_t nb = p.nsub * 16;  // bytes of one (k-group, plane) slab of a B sub-block
-      const uint32_t b_lbo = p.planes * nb, b_sbo = 128;
-      uint32_t a_it = 0, b_it = 0, acc_it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
-        const uint32_t acc = acc_it & 1, acc_ph = (acc_it >> 1) & 1;
-        mbar_wait(&tm_empty[acc], acc_ph ^ 1);
+    const uint32_t idesc = make_idesc_bf16(p.nsub);
+    const uint32_t a_lbo = p.planes * PATCH_BYTES, a_sbo = PW * 16;
+    const uint32_t nb = p.nsub * 16;  // bytes of one (k-group, plane) slab of a B sub-block
+    const uint32_t b_lbo = p.planes * nb, b_sbo = 128;
+    const uint64_t a_desc0 = make_smem_desc(0, a_lbo, a_sbo), b_desc0 = make_smem_desc(0, b_lbo, b_sbo);
+    // descriptor start-address increments (16-byte units)
+    const uint32_t a_kstep = (2 * a_lbo) >> 4, b_kstep = (2 * b_lbo) >> 4;
+    const uint32_t a_lo16 = PATCH_BYTES >> 4, b_lo16 = nb >> 4, b_sub16 = (uint32_t)p.b_sub_bytes >> 4;
+    const int ksteps = p.kc >> 4, nsubs = p.cw / p.nsub;
+    const bool split = p.planes == 2;
+    uint32_t a_slot = 0, a_ph = 0, b_slot = 0, b_ph = 0, acc = 0, acc_ph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      mbar_wait(&tm_empty[acc], acc_ph ^ 1);
+      tc_fence_after();
+      const uint32_t d_base = tmem_base + acc * p.ntile;
+      uint32_t started = 0;
+      for (int ch = 0; ch < p.nchunks; ++ch) {
+        mbar_wait(&a_full[a_slot], a_ph);
         tc_fence_after();
-        const uint32_t d_base = tmem_base + acc * p.ntile;
-        uint32_t started = 0;
-        for (int ch = 0; ch < p.nchunks; ++ch) {
-          const uint32_t slot = a_it & 1, ph = (a_it >> 1) & 1;
-          mbar_wait(&a_full[slot], ph);
+        const uint32_t a_base16 = smem_u32(a_smem + a_slot * p.a_slot_bytes) >> 4;
+        for (int e = 0; e < p.ntaps; ++e) {
+          const int q = p.taps[e].phase - t.p0;
+          if (q < 0 || q >= p.np) continue;
+          mbar_wait(&b_full[b_slot], b_ph);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(a_smem + slot * p.a_slot_bytes);
-          for (int e = 0; e < p.ntaps; ++e) {
-            const int q = p.taps[e].phase - t.p0;
-            if (q < 0 || q >= p.np) continue;
-            const uint32_t bs = b_it % p.b_slots, bph = (b_it / p.b_slots) & 1;
-            mbar_wait(&b_full[bs], bph);
-            tc_fence_after();
-            const uint32_t b_base = smem_u32(b_smem + bs * p.b_slot_bytes);
-            const uint32_t a_tap = a_base + (uint32_t)p.taps[e].a_off * 16;
-            for (int s = 0; s * p.nsub < p.cw; ++s) {
+          const uint32_t b_base16 = smem_u32(b_smem + b_slot * p.b_slot_bytes) >> 4;
+          const uint64_t da_tap = a_desc0 + (a_base16 + (uint32_t)p.taps[e].a_off);
+          if (elect_one_sync()) {
+            for (int s = 0; s < nsubs; ++s) {
               const uint32_t d = d_base + q * p.cw + s * p.nsub;
-              const uint32_t sbit = 1u << (q * 2 + s);
-              const uint32_t b_sub = b_base + s * p.b_sub_bytes;
-              for (int k = 0; k < (p.kc >> 4); ++k) {
-                const uint32_t a_hi = a_tap + (2 * k) * a_lbo;
-                const uint32_t b_hi = b_sub + (2 * k) * b_lbo;
-                const uint64_t da_hi = make_smem_desc(a_hi, a_lbo, a_sbo);
-                const uint64_t db_hi = make_smem_desc(b_hi, b_lbo, b_sbo);
-                tc_mma_bf16(d, da_hi, db_hi, idesc, ((started & sbit) | k) ? 1u : 0u);
-                if (p.planes == 2) {
-                  const uint64_t da_lo = make_smem_desc(a_hi + PATCH_BYTES, a_lbo, a_sbo);
-                  const uint64_t db_lo = make_smem_desc(b_hi + nb, b_lbo, b_sbo);
-                  tc_mma_bf16(d, da_hi, db_lo, idesc, 1u);
-                  tc_mma_bf16(d, da_lo, db_hi, idesc, 1u);
+              const uint32_t first = ((started >> (q * 2 + s)) & 1u) ^ 1u;  // 1 = nothing accumulated yet
+              uint64_t da = da_tap, db = b_desc0 + (b_base16 + s * b_sub16);
+#pragma unroll 1
+              for (int k = 0; k < ksteps; ++k) {
+                tc_mma_bf16(d, da, db, idesc, (k > 0 || !first) ? 1u : 0u);
+                if (split) {
+                  tc_mma_bf16(d, da, db + b_lo16, idesc, 1u);
+                  tc_mma_bf16(d, da + a_lo16, db, idesc, 1u);
                 }
+                da += a_kstep;
+                db += b_kstep;
               }
-              started |= sbit;
             }
-            tc_commit(&b_empty[bs]);
-            ++b_it;
+            tc_commit(&b_empty[b_slot]);
           }
-          tc_commit(&a_empty[slot]);
-          ++a_it;
+          __syncwarp();
+          for (int s = 0; s < nsubs; ++s) started |= 1u << (q * 2 + s);
+          if (++b_slot == (uint32_t)p.b_slots) { b_slot = 0; b_ph ^= 1; }
         }
-        tc_commit(&tm_full[acc]);
-        ++acc_it;
+        if (elect_one_sync()) tc_commit(&a_empty[a_slot]);
+        __syncwarp();
+        if (++a_slot == 2) { a_slot = 0; a_ph ^= 1; }
       }
+      if (elect_one_sync()) tc_commit(&tm_full[acc]);
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
     }
   } else {
     // =================================== epilogue ========================================
@@ -439,7 +479,7 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (EPI == 0 && p.noise && px.valid)
         px.nz = __ldg(p.noise + (size_t)px.n * p.noise_bstride + (size_t)px.y * p.W + px.x);
       float rgb[3] = {0.f, 0.f, 0.f};
-      mbar_wait(&tm_full[acc], acc_ph);
+      mbar_wait_relaxed(&tm_full[acc], acc_ph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * p.ntile + ((uint32_t)(quarter * 32) << 16);
       for (int q = 0; q < p.np; ++q) {

@@ -31,6 +31,51 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# ------------------------------------------------------------------------------------------------
+# optional per-launch timing (bench.py roofline leg): CUDA events on the launching stream
+# ------------------------------------------------------------------------------------------------
+_prof = None
+
+
+class profile:
+    """with ops.profile() as rec: ...  -> rec.events: list of (kernel, key, start_event, end_event)."""
+
+    def __enter__(self):
+        global _prof
+        self.events = []
+        _prof = self.events
+        return self
+
+    def __exit__(self, *exc):
+        global _prof
+        _prof = None
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, key, e0, e1 in self.events:
+            d = out.setdefault((name, key), [0, 0.0])
+            d[0] += 1
+            d[1] += e0.elapsed_time(e1)
+        return out
+
+
+class _rec:
+    def __init__(self, name, key):
+        self.name, self.key = name, key
+
+    def __enter__(self):
+        if _prof is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if _prof is not None and exc[0] is None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _prof.append((self.name, self.key, self.e0, e1))
+
+
 def _p(t):
     if t is None:
         return None
@@ -223,7 +268,9 @@ def conv(x, wpk, cout, kind=CONV_3X3, *, demod=None, noise=None, noise_batched=F
             res["nchw"] = o
         if rgb_w is not None:
             a.rgb_w, a.rgb_out = ptr(rgb_w), ptr(rgb_out)
-    check(lib().dge_conv_forward(ctypes.byref(a), _stream()))
+    name = ("conv3x3", "conv1x1", "conv_up3x3")[kind]
+    with _rec(name, (x.n, x.h, x.w, x.c, cout, x.planes)):
+        check(lib().dge_conv_forward(ctypes.byref(a), _stream()))
     return res
 
 
@@ -233,10 +280,11 @@ def up_fir_epilogue(raw_up, n, c, h_out, w_out, *, demod=None, noise=None, noise
     res = {}
     act = Act(n, c, h_out, w_out, planes, dev) if out_act else None
     nchw = torch.empty((n, c, h_out, w_out), dtype=torch.float32, device=dev) if out_nchw else None
-    check(lib().dge_up_fir_epilogue(
-        _f32(raw_up), _f32(demod), _f32(noise), (h_out * w_out if noise_batched else 0), float(noise_scalar),
-        _f32(bias), float(slope), float(gain), _f32(out_scale), _p(act.t) if act else None, _p(nchw), n, c, h_out,
-        w_out, planes, _stream()))
+    with _rec("up_fir_epilogue", (n, h_out, w_out, c, planes)):
+        check(lib().dge_up_fir_epilogue(
+            _f32(raw_up), _f32(demod), _f32(noise), (h_out * w_out if noise_batched else 0), float(noise_scalar),
+            _f32(bias), float(slope), float(gain), _f32(out_scale), _p(act.t) if act else None, _p(nchw), n, c, h_out,
+            w_out, planes, _stream()))
     if act is not None:
         res["act"] = act
     if nchw is not None:
@@ -246,7 +294,8 @@ def up_fir_epilogue(raw_up, n, c, h_out, w_out, *, demod=None, noise=None, noise
 
 def rgb_init(img_in, bias, n, nch, h_out, w_out, device):
     out = torch.empty((n, nch, h_out, w_out), dtype=torch.float32, device=device)
-    check(lib().dge_rgb_init(_f32(img_in), _f32(bias), _p(out), n, nch, h_out, w_out, _stream()))
+    with _rec("rgb_init", (n, h_out, w_out)):
+        check(lib().dge_rgb_init(_f32(img_in), _f32(bias), _p(out), n, nch, h_out, w_out, _stream()))
     return out
 
 
@@ -260,7 +309,8 @@ def from_rgb(img, w, b, slope=0.2):
     c = w2.shape[0]
     out = F32B(n, c, h, wd, img.device)
     bb = None if b is None else b.detach().contiguous()
-    check(lib().dge_from_rgb(_f32(img), _f32(w2), _f32(bb), _p(out.t), n, cimg, c, h, wd, float(slope), _stream()))
+    with _rec("from_rgb", (n, h, wd, c)):
+        check(lib().dge_from_rgb(_f32(img), _f32(w2), _f32(bb), _p(out.t), n, cimg, c, h, wd, float(slope), _stream()))
     return out
 
 
@@ -271,8 +321,9 @@ def instance_stats(x, eps=1e-8):
     scratch = torch.empty((2 * x.n * x.c,), dtype=torch.float64, device=dev)
     style = torch.empty((x.n, 2 * x.c), dtype=torch.float32, device=dev)
     mr = torch.empty((x.n, x.c, 2), dtype=torch.float32, device=dev)
-    check(lib().dge_instance_stats(_p(x.t), _p(scratch), _p(style), _p(mr), x.n, x.c, x.h, x.w, float(eps),
-                                   _stream()))
+    with _rec("instance_stats", (x.n, x.h, x.w, x.c)):
+        check(lib().dge_instance_stats(_p(x.t), _p(scratch), _p(style), _p(mr), x.n, x.c, x.h, x.w, float(eps),
+                                       _stream()))
     return style, mr
 
 
@@ -281,15 +332,17 @@ def instance_norm(x, mean_rstd, planes=2, out_act=True, out_f32b=False):
     dev = x.t.device
     act = Act(x.n, x.c, x.h, x.w, planes, dev) if out_act else None
     f = F32B(x.n, x.c, x.h, x.w, dev) if out_f32b else None
-    check(lib().dge_instance_norm(_p(x.t), _f32(mean_rstd), _p(act.t) if act else None, _p(f.t) if f else None, x.n,
-                                  x.c, x.h, x.w, planes, _stream()))
+    with _rec("instance_norm", (x.n, x.h, x.w, x.c, planes)):
+        check(lib().dge_instance_norm(_p(x.t), _f32(mean_rstd), _p(act.t) if act else None, _p(f.t) if f else None,
+                                      x.n, x.c, x.h, x.w, planes, _stream()))
     return act, f
 
 
 def avgpool_to_act(x, planes=2):
     assert isinstance(x, F32B)
     out = Act(x.n, x.c, x.h // 2, x.w // 2, planes, x.t.device)
-    check(lib().dge_avgpool_to_act(_p(x.t), _p(out.t), x.n, x.c, x.h, x.w, planes, _stream()))
+    with _rec("avgpool_to_act", (x.n, x.h, x.w, x.c, planes)):
+        check(lib().dge_avgpool_to_act(_p(x.t), _p(out.t), x.n, x.c, x.h, x.w, planes, _stream()))
     return out
 
 
@@ -297,8 +350,9 @@ def blend(a_src, b_src, a, b, pool):
     assert isinstance(a_src, F32B) and isinstance(b_src, F32B)
     ho, wo = (a_src.h // 2, a_src.w // 2) if pool else (a_src.h, a_src.w)
     out = F32B(a_src.n, a_src.c, ho, wo, a_src.t.device)
-    check(lib().dge_blend(_p(a_src.t), _p(b_src.t), _p(out.t), float(a), float(b), int(pool), a_src.n, a_src.c, ho, wo,
-                          _stream()))
+    with _rec("blend", (a_src.n, ho, wo, a_src.c, int(pool))):
+        check(lib().dge_blend(_p(a_src.t), _p(b_src.t), _p(out.t), float(a), float(b), int(pool), a_src.n, a_src.c, ho,
+                              wo, _stream()))
     return out
 
 

@@ -155,7 +155,8 @@ def synthesis(sd, wp, resolution, *, prefix="synthesis.", noises=None):
 
 def generator(sd, z, resolution, *, trunc_psi=None, trunc_layers=None):
     """StyleGAN2Generator.forward in eval mode (no w_avg update / style mixing), :165-196."""
-    w = mapping(sd, z)
+    n_map = sum(1 for k in sd if k.startswith("mapping.dense") and k.endswith(".weight"))
+    w = mapping(sd, z, num_layers=n_map)
     wp = truncation(w, sd["truncation.w_avg"], num_layers_for(resolution), trunc_psi, trunc_layers)
     out = {"z": pixel_norm(z), "w": w}
     out.update(synthesis(sd, wp, resolution))
