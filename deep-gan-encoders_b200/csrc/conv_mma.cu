@@ -26,7 +26,11 @@
 namespace dge {
 
 constexpr int TH = 16, TW = 8;            // output tile (pixels); TW=8 -> one UMMA core-matrix row group per tile row
+#ifdef DGE_EXPERIMENT_ALIGNED
+constexpr int PH = TH + 2, PW = 16;       // timing experiment only: 128B-aligned core matrices (wrong results)
+#else
 constexpr int PH = TH + 2, PW = TW + 2;   // halo patch
+#endif
 constexpr int PATCH_BYTES = PH * PW * 16; // one (channel-group, plane) slab of the patch: 2880 B
 constexpr int MAX_B_SLOTS = 8;
 constexpr int NUM_THREADS = 192;          // warp0: TMA, warp1: MMA + TMEM alloc, warps 2..5: epilogue
@@ -51,6 +55,7 @@ struct ConvKParams {
   int ntaps;
   TapEntry taps[9];
   int a_slot_bytes, b_slot_bytes, b_sub_bytes, b_slots;
+  int a_slots, b_region_bytes, resident, acc_stages;
   int tmem_cols;
   // epilogue
   const float* demod;
@@ -317,41 +322,65 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int tile)
   int ty = r / p.tiles_x;
   t.y0 = ty * TH;
   t.x0 = (r - ty * p.tiles_x) * TW;
-  const int col0 = t.nt * p.ntile;
-  t.p0 = col0 / p.Cout;
-  t.co0 = col0 - t.p0 * p.Cout;
+  // an N tile holds `np` phases x `cw` channels: channels [nt*cw, (nt+1)*cw) of every phase
+  t.p0 = 0;
+  t.co0 = t.nt * p.cw;
   return t;
 }
 
 // ---------------------------------------------------------------------------------------------
 // the tcgen05 kernel
 // ---------------------------------------------------------------------------------------------
+constexpr int MAX_A_SLOTS = 4;
+constexpr int BAR_A_FULL = 0, BAR_A_EMPTY = MAX_A_SLOTS, BAR_TM_FULL = 2 * MAX_A_SLOTS, BAR_TM_EMPTY = BAR_TM_FULL + 2,
+              BAR_B_FULL = BAR_TM_EMPTY + 2, BAR_B_EMPTY = BAR_B_FULL + MAX_B_SLOTS, BAR_COUNT = BAR_B_EMPTY + MAX_B_SLOTS;
+
+// all MMAs of one (tap, K-chunk): KSTEPS x {hi*hi, hi*lo, lo*hi} into accumulator column block d
+template <bool SPLIT>
+__device__ __forceinline__ void issue_tap(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, int ksteps,
+                                          uint32_t a_kstep, uint32_t b_kstep, uint32_t a_lo16, uint32_t b_lo16,
+                                          uint32_t accumulate) {
+#pragma unroll 1
+  for (int k = 0; k < ksteps; ++k) {
+    tc_mma_bf16(d, da, db, idesc, accumulate);
+    if (SPLIT) {
+      tc_mma_bf16(d, da, db + b_lo16, idesc, 1u);
+      tc_mma_bf16(d, da + a_lo16, db, idesc, 1u);
+    }
+    accumulate = 1u;
+    da += a_kstep;
+    db += b_kstep;
+  }
+}
+
 template <int EPI>  // 0 = pointwise, 1 = raw up
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ ConvKParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* a_smem = smem;
-  uint8_t* b_smem = a_smem + 2 * p.a_slot_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + p.b_slots * p.b_slot_bytes);
-  uint64_t* a_full = bars;            // [2]
-  uint64_t* a_empty = bars + 2;       // [2]
-  uint64_t* tm_full = bars + 4;       // [2]
-  uint64_t* tm_empty = bars + 6;      // [2]
-  uint64_t* b_full = bars + 8;        // [MAX_B_SLOTS]
-  uint64_t* b_empty = bars + 8 + MAX_B_SLOTS;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * MAX_B_SLOTS);
+  uint8_t* b_smem = a_smem + p.a_slots * p.a_slot_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + p.b_region_bytes);
+  uint64_t* a_full = bars + BAR_A_FULL;
+  uint64_t* a_empty = bars + BAR_A_EMPTY;
+  uint64_t* tm_full = bars + BAR_TM_FULL;
+  uint64_t* tm_empty = bars + BAR_TM_EMPTY;
+  uint64_t* b_full = bars + BAR_B_FULL;
+  uint64_t* b_empty = bars + BAR_B_EMPTY;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < MAX_A_SLOTS; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&tm_full[i], 1);
       mbar_init(&tm_empty[i], 4);
     }
-    for (int i = 0; i < p.b_slots; ++i) {
+    for (int i = 0; i < MAX_B_SLOTS; ++i) {
       mbar_init(&b_full[i], 1);
       mbar_init(&b_empty[i], 1);
     }
@@ -367,13 +396,26 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int kc8p = (p.kc >> 3) * p.planes;
+  const int nsubs = p.cw / p.nsub;
 
   if (warp == 0) {
     // =================================== TMA producer ===================================
     // Whole warp runs the (warp-uniform) control flow; one elected lane issues.  Keeping the flow uniform lets
     // the compiler hold addresses/descriptors in uniform registers instead of waterfall loops.
-    const int kc8p = (p.kc >> 3) * p.planes;
     uint32_t a_slot = 0, a_ph = 0, b_slot = 0, b_ph = 0;
+    if (p.resident) {
+      // weights of every (chunk, tap) stay in smem for the whole kernel: one bulk load, one barrier
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(&b_full[0], (uint32_t)p.b_region_bytes);
+        for (int ch = 0; ch < p.nchunks; ++ch)
+          for (int e = 0; e < p.ntaps; ++e)
+            for (int s = 0; s < nsubs; ++s)
+              tma_load_3d(b_smem + (ch * p.ntaps + e) * p.b_slot_bytes + s * p.b_sub_bytes, &tmB, &b_full[0],
+                          2 * (s * p.nsub), ch * kc8p, p.taps[e].w_tap);
+      }
+      __syncwarp();
+    }
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       for (int ch = 0; ch < p.nchunks; ++ch) {
@@ -384,7 +426,8 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                       t.n);
         }
         __syncwarp();
-        if (++a_slot == 2) { a_slot = 0; a_ph ^= 1; }
+        if (++a_slot == (uint32_t)p.a_slots) { a_slot = 0; a_ph ^= 1; }
+        if (p.resident) continue;
         for (int e = 0; e < p.ntaps; ++e) {
           const int q = p.taps[e].phase - t.p0;
           if (q < 0 || q >= p.np) continue;
@@ -392,7 +435,7 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (elect_one_sync()) {
             mbar_arrive_expect_tx(&b_full[b_slot], (uint32_t)p.b_slot_bytes);
             uint8_t* dst = b_smem + b_slot * p.b_slot_bytes;
-            for (int s = 0; s * p.nsub < p.cw; ++s)
+            for (int s = 0; s < nsubs; ++s)
               tma_load_3d(dst + s * p.b_sub_bytes, &tmB, &b_full[b_slot], 2 * (t.co0 + s * p.nsub), ch * kc8p,
                           p.taps[e].w_tap);
           }
@@ -411,9 +454,15 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // descriptor start-address increments (16-byte units)
     const uint32_t a_kstep = (2 * a_lbo) >> 4, b_kstep = (2 * b_lbo) >> 4;
     const uint32_t a_lo16 = PATCH_BYTES >> 4, b_lo16 = nb >> 4, b_sub16 = (uint32_t)p.b_sub_bytes >> 4;
-    const int ksteps = p.kc >> 4, nsubs = p.cw / p.nsub;
+    const uint32_t b_slot16 = (uint32_t)p.b_slot_bytes >> 4;
+    const int ksteps = p.kc >> 4;
     const bool split = p.planes == 2;
+    const uint32_t b_region16 = smem_u32(b_smem) >> 4;
     uint32_t a_slot = 0, a_ph = 0, b_slot = 0, b_ph = 0, acc = 0, acc_ph = 0;
+    if (p.resident) {
+      mbar_wait(&b_full[0], 0);
+      tc_fence_after();
+    }
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       mbar_wait(&tm_empty[acc], acc_ph ^ 1);
@@ -424,52 +473,69 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait(&a_full[a_slot], a_ph);
         tc_fence_after();
         const uint32_t a_base16 = smem_u32(a_smem + a_slot * p.a_slot_bytes) >> 4;
-        for (int e = 0; e < p.ntaps; ++e) {
-          const int q = p.taps[e].phase - t.p0;
-          if (q < 0 || q >= p.np) continue;
-          mbar_wait(&b_full[b_slot], b_ph);
-          tc_fence_after();
-          const uint32_t b_base16 = smem_u32(b_smem + b_slot * p.b_slot_bytes) >> 4;
-          const uint64_t da_tap = a_desc0 + (a_base16 + (uint32_t)p.taps[e].a_off);
+        if (p.resident) {
+          // one straight run of MMAs per (tile, chunk): no per-tap barrier traffic
           if (elect_one_sync()) {
-            for (int s = 0; s < nsubs; ++s) {
-              const uint32_t d = d_base + q * p.cw + s * p.nsub;
-              const uint32_t first = ((started >> (q * 2 + s)) & 1u) ^ 1u;  // 1 = nothing accumulated yet
-              uint64_t da = da_tap, db = b_desc0 + (b_base16 + s * b_sub16);
-#pragma unroll 1
-              for (int k = 0; k < ksteps; ++k) {
-                tc_mma_bf16(d, da, db, idesc, (k > 0 || !first) ? 1u : 0u);
-                if (split) {
-                  tc_mma_bf16(d, da, db + b_lo16, idesc, 1u);
-                  tc_mma_bf16(d, da + a_lo16, db, idesc, 1u);
-                }
-                da += a_kstep;
-                db += b_kstep;
+            uint32_t b16 = b_region16 + (uint32_t)(ch * p.ntaps) * b_slot16;
+            for (int e = 0; e < p.ntaps; ++e, b16 += b_slot16) {
+              const int q = p.taps[e].phase;
+              const uint64_t da = a_desc0 + (a_base16 + (uint32_t)p.taps[e].a_off);
+              for (int s = 0; s < nsubs; ++s) {
+                const uint32_t acc_flag = (started >> (q * 2 + s)) & 1u;
+                if (split)
+                  issue_tap<true>(d_base + q * p.cw + s * p.nsub, da, b_desc0 + (b16 + s * b_sub16), idesc, ksteps,
+                                  a_kstep, b_kstep, a_lo16, b_lo16, acc_flag);
+                else
+                  issue_tap<false>(d_base + q * p.cw + s * p.nsub, da, b_desc0 + (b16 + s * b_sub16), idesc, ksteps,
+                                   a_kstep, b_kstep, a_lo16, b_lo16, acc_flag);
+                started |= 1u << (q * 2 + s);
               }
             }
-            tc_commit(&b_empty[b_slot]);
+            tc_commit(&a_empty[a_slot]);
           }
           __syncwarp();
-          for (int s = 0; s < nsubs; ++s) started |= 1u << (q * 2 + s);
-          if (++b_slot == (uint32_t)p.b_slots) { b_slot = 0; b_ph ^= 1; }
+          started = 0xffu;  // (uniform copy of the elected lane's bookkeeping: every sub-accumulator is started)
+        } else {
+          for (int e = 0; e < p.ntaps; ++e) {
+            const int q = p.taps[e].phase - t.p0;
+            if (q < 0 || q >= p.np) continue;
+            mbar_wait(&b_full[b_slot], b_ph);
+            tc_fence_after();
+            const uint32_t b_base16 = smem_u32(b_smem + b_slot * p.b_slot_bytes) >> 4;
+            const uint64_t da = a_desc0 + (a_base16 + (uint32_t)p.taps[e].a_off);
+            if (elect_one_sync()) {
+              for (int s = 0; s < nsubs; ++s) {
+                const uint32_t acc_flag = (started >> (q * 2 + s)) & 1u;
+                if (split)
+                  issue_tap<true>(d_base + q * p.cw + s * p.nsub, da, b_desc0 + (b_base16 + s * b_sub16), idesc,
+                                  ksteps, a_kstep, b_kstep, a_lo16, b_lo16, acc_flag);
+                else
+                  issue_tap<false>(d_base + q * p.cw + s * p.nsub, da, b_desc0 + (b_base16 + s * b_sub16), idesc,
+                                   ksteps, a_kstep, b_kstep, a_lo16, b_lo16, acc_flag);
+              }
+              tc_commit(&b_empty[b_slot]);
+            }
+            __syncwarp();
+            for (int s = 0; s < nsubs; ++s) started |= 1u << (q * 2 + s);
+            if (++b_slot == (uint32_t)p.b_slots) { b_slot = 0; b_ph ^= 1; }
+          }
+          if (elect_one_sync()) tc_commit(&a_empty[a_slot]);
+          __syncwarp();
         }
-        if (elect_one_sync()) tc_commit(&a_empty[a_slot]);
-        __syncwarp();
-        if (++a_slot == 2) { a_slot = 0; a_ph ^= 1; }
+        if (++a_slot == (uint32_t)p.a_slots) { a_slot = 0; a_ph ^= 1; }
       }
       if (elect_one_sync()) tc_commit(&tm_full[acc]);
       __syncwarp();
-      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+      if (++acc == (uint32_t)p.acc_stages) { acc = 0; acc_ph ^= 1; }
     }
   } else {
     // =================================== epilogue ========================================
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int m = quarter * 32 + lane;
     const int ty = m >> 3, tx = m & 7;
-    uint32_t acc_it = 0;
+    uint32_t acc = 0, acc_ph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
-      const uint32_t acc = acc_it & 1, acc_ph = (acc_it >> 1) & 1;
       PixelCtx px;
       px.n = t.n;
       px.y = t.y0 + ty;
@@ -501,7 +567,7 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int ch = 0; ch < 3; ++ch)
           atomicAdd(p.rgb_out + (((size_t)px.n * 3 + ch) * p.H + px.y) * p.W + px.x, rgb[ch]);
       }
-      ++acc_it;
+      if (++acc == (uint32_t)p.acc_stages) { acc = 0; acc_ph ^= 1; }
     }
   }
 
@@ -672,6 +738,9 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
       for (int kx = 0; kx < 3; ++kx) {
         TapEntry& t = p.taps[ky * 3 + kx];
         t.a_off = (int16_t)(ky * PW + kx);
+#ifdef DGE_EXPERIMENT_ALIGNED
+        t.a_off = (int16_t)(ky * PW);
+#endif
         t.w_tap = (int16_t)(ky * 3 + kx);
         t.phase = 0;
       }
@@ -694,32 +763,71 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
   }
   // N tiling
   const int ntot = p.P * p.Cout;
-  if (up && ntot <= 256) {
-    p.ntile = ntot; p.cw = p.Cout; p.np = 4;
-  } else if (up && 2 * p.Cout <= 256) {
-    p.ntile = 2 * p.Cout; p.cw = p.Cout; p.np = 2;
+  if (up) {
+    // all 4 output phases of a tile share one A patch: <=128 channels x 4 phases = <=512 TMEM columns
+    p.cw = largest_div(p.Cout, 128, 16);
+    p.np = 4;
+    p.ntile = 4 * p.cw;
   } else {
     p.cw = largest_div(p.Cout, 256, 16);
-    p.ntile = p.cw; p.np = 1;
+    p.ntile = p.cw;
+    p.np = 1;
   }
   p.nsub = largest_div(p.cw, 128, 16);
+  DGE_REQUIRE(p.cw > 0 && p.nsub > 0, "conv: cannot tile cout=%d", p.Cout);
   p.n_ntiles = ntot / p.ntile;
-  DGE_REQUIRE(p.cw > 0 && p.nsub > 0 && p.n_ntiles * p.ntile == ntot, "conv: cannot tile cout=%d", p.Cout);
+  DGE_REQUIRE(p.n_ntiles * p.ntile == ntot, "conv: cannot tile cout=%d", p.Cout);
   DGE_REQUIRE(p.np * (p.cw / p.nsub) <= 8 && p.cw / p.nsub <= 2, "conv: internal sub-tile bookkeeping overflow");
-  // K chunking
-  p.kc = largest_div(p.Cin, p.cw > 128 ? 32 : 64, 16);
+  p.acc_stages = (2 * p.ntile <= 512) ? 2 : 1;   // single-buffered accumulator when the tile fills TMEM
+  int cols = 32;
+  while (cols < p.acc_stages * p.ntile) cols *= 2;
+  DGE_REQUIRE(cols <= 512, "conv: TMEM overflow");
+  p.tmem_cols = cols;
+  const int tmem_occ = 512 / p.tmem_cols;
+  // K chunking + shared-memory plan
+  const int smem_cap = 224 * 1024;
+  const int bar_bytes = (BAR_COUNT + 2) * 8;
+  const long long b_all = (long long)p.ntaps * (p.Cin / 8) * p.planes * p.cw * 16;   // every tap, every channel
+  p.resident = 0;
+  if (p.n_ntiles == 1) {
+    // weights resident in smem for the whole kernel when they fit next to >= 2 patch slots
+    const int kcs[3] = {64, 32, 16};
+    for (int i = 0; i < 3 && !p.resident; ++i) {
+      const int kc = largest_div(p.Cin, kcs[i], 16);
+      const long long a_slot = (long long)(kc / 8) * p.planes * PATCH_BYTES;
+      if (b_all + 2 * a_slot + bar_bytes <= smem_cap) {
+        p.resident = 1;
+        p.kc = kc;
+      }
+    }
+  }
+  if (!p.resident) p.kc = largest_div(p.Cin, p.cw > 128 ? 32 : 64, 16);
   p.nchunks = p.Cin / p.kc;
   p.a_slot_bytes = (p.kc / 8) * p.planes * PATCH_BYTES;
   p.b_sub_bytes = (p.kc / 8) * p.planes * p.nsub * 16;
   p.b_slot_bytes = (p.cw / p.nsub) * p.b_sub_bytes;
-  const int smem_budget = 200 * 1024;
-  p.b_slots = (smem_budget - 2 * p.a_slot_bytes) / p.b_slot_bytes;
-  if (p.b_slots > MAX_B_SLOTS) p.b_slots = MAX_B_SLOTS;
-  DGE_REQUIRE(p.b_slots >= 2, "conv: smem budget too small for this shape (b_slot=%d)", p.b_slot_bytes);
-  int cols = 32;
-  while (cols < 2 * p.ntile) cols *= 2;
-  DGE_REQUIRE(cols <= 512, "conv: TMEM overflow");
-  p.tmem_cols = cols;
+  size_t smem = 0;
+  int max_occ = tmem_occ > 2 ? 2 : tmem_occ;
+  if (p.resident) {
+    p.b_region_bytes = (int)b_all;
+    p.b_slots = 1;
+    // prefer two co-resident CTAs (epilogue/mainloop overlap across CTAs) when everything fits in half an SM
+    const int half = 112 * 1024;
+    int budget = (max_occ == 2 && b_all + 2 * p.a_slot_bytes + bar_bytes <= half) ? half : smem_cap;
+    if (budget == smem_cap) max_occ = 1;
+    p.a_slots = (int)((budget - b_all - bar_bytes) / p.a_slot_bytes);
+    if (p.a_slots > MAX_A_SLOTS) p.a_slots = MAX_A_SLOTS;
+  } else {
+    p.a_slots = 2;
+    const int budget = 200 * 1024;
+    p.b_slots = (budget - p.a_slots * p.a_slot_bytes) / p.b_slot_bytes;
+    if (p.b_slots > MAX_B_SLOTS) p.b_slots = MAX_B_SLOTS;
+    DGE_REQUIRE(p.b_slots >= 2, "conv: smem budget too small for this shape (b_slot=%d)", p.b_slot_bytes);
+    p.b_region_bytes = p.b_slots * p.b_slot_bytes;
+  }
+  DGE_REQUIRE(p.a_slots >= 2, "conv: smem plan failed (a_slots=%d)", p.a_slots);
+  smem = (size_t)p.a_slots * p.a_slot_bytes + (size_t)p.b_region_bytes + bar_bytes;
+  if (smem > 113 * 1024) max_occ = 1;
   p.total_tiles = p.N * p.tiles_x * p.tiles_y * p.n_ntiles;
 
   p.demod = a->demod; p.noise = a->noise; p.noise_bstride = a->noise_bstride; p.noise_w = a->noise_w;
@@ -766,10 +874,7 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
     if (r) return r;
   }
 
-  size_t smem = (size_t)2 * p.a_slot_bytes + (size_t)p.b_slots * p.b_slot_bytes + (8 + 2 * MAX_B_SLOTS) * 8 + 16;
   // TMEM is 512 columns per SM: keep co-resident CTAs * tmem_cols <= 512 by padding the smem request.
-  int max_occ = 512 / p.tmem_cols;
-  if (max_occ > 2) max_occ = 2;
   const size_t min_smem = (227 * 1024) / (max_occ + 1) + 1024;
   if (smem < min_smem) smem = min_smem;
   static bool attr_set[2] = {false, false};

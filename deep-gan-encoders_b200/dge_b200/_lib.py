@@ -8,7 +8,7 @@ import os
 from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdge_b200.so")
+LIB_PATH = os.environ.get("DGE_LIB_PATH", os.path.join(_HERE, "libdge_b200.so"))  # env override: experiments only
 
 _lib = None
 
