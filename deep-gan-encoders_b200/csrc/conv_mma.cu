@@ -55,7 +55,7 @@ struct ConvKParams {
   int ntaps;
   TapEntry taps[9];
   int a_slot_bytes, b_slot_bytes, b_sub_bytes, b_slots;
-  int a_slots, b_region_bytes, resident, acc_stages;
+  int a_slots, b_region_bytes, resident, acc_stages, b_rb;
   int tmem_cols;
   // epilogue
   const float* demod;
@@ -411,8 +411,8 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int ch = 0; ch < p.nchunks; ++ch)
           for (int e = 0; e < p.ntaps; ++e)
             for (int s = 0; s < nsubs; ++s)
-              tma_load_3d(b_smem + (ch * p.ntaps + e) * p.b_slot_bytes + s * p.b_sub_bytes, &tmB, &b_full[0],
-                          2 * (s * p.nsub), ch * kc8p, p.taps[e].w_tap);
+              tma_load_4d(b_smem + (ch * p.ntaps + e) * p.b_slot_bytes + s * p.b_sub_bytes, &tmB, &b_full[0], 0,
+                          (s * p.nsub) / p.b_rb, ch * kc8p, p.taps[e].w_tap);
       }
       __syncwarp();
     }
@@ -436,7 +436,7 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             mbar_arrive_expect_tx(&b_full[b_slot], (uint32_t)p.b_slot_bytes);
             uint8_t* dst = b_smem + b_slot * p.b_slot_bytes;
             for (int s = 0; s < nsubs; ++s)
-              tma_load_3d(dst + s * p.b_sub_bytes, &tmB, &b_full[b_slot], 2 * (t.co0 + s * p.nsub), ch * kc8p,
+              tma_load_4d(dst + s * p.b_sub_bytes, &tmB, &b_full[b_slot], 0, (t.co0 + s * p.nsub) / p.b_rb, ch * kc8p,
                           p.taps[e].w_tap);
           }
           __syncwarp();
@@ -769,11 +769,12 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
     p.np = 4;
     p.ntile = 4 * p.cw;
   } else {
-    p.cw = largest_div(p.Cout, 256, 16);
+    // one N=256 MMA per K-step when possible: A is then fetched from smem once per 256 columns
+    p.cw = (p.Cout % 256 == 0) ? 256 : largest_div(p.Cout, 128, 16);
     p.ntile = p.cw;
     p.np = 1;
   }
-  p.nsub = largest_div(p.cw, 128, 16);
+  p.nsub = p.cw;   // one MMA covers the whole column block (N <= 256)
   DGE_REQUIRE(p.cw > 0 && p.nsub > 0, "conv: cannot tile cout=%d", p.Cout);
   p.n_ntiles = ntot / p.ntile;
   DGE_REQUIRE(p.n_ntiles * p.ntile == ntot, "conv: cannot tile cout=%d", p.Cout);
@@ -865,13 +866,17 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
     if (r) return r;
   }
   {
+    // WPK [taps][Cin/8][planes][Cout][8] viewed as uint64 [taps][c8p][Cout/rb][2*rb]: a box of (cw/rb) row blocks
+    // lands in smem as [k-group][cw rows][16 B] -- the canonical K-major operand with SBO = 128 B.
     const uint64_t c8p = (uint64_t)(p.Cin / 8) * p.planes;
     const int wtaps = (a->kind == DGE_CONV_1X1) ? 1 : 9;
-    uint64_t dims[3] = {(uint64_t)2 * p.Cout, c8p, (uint64_t)wtaps};
-    uint64_t strides[2] = {(uint64_t)p.Cout * 16, c8p * p.Cout * 16};
-    uint32_t box[3] = {(uint32_t)(2 * p.nsub), (uint32_t)((p.kc / 8) * p.planes), 1};
-    int r = make_tmap(&tmB, a->wpk, 3, dims, strides, box);
+    const int rb = p.cw > 128 ? 128 : p.cw;
+    uint64_t dims[4] = {(uint64_t)2 * rb, (uint64_t)(p.Cout / rb), c8p, (uint64_t)wtaps};
+    uint64_t strides[3] = {(uint64_t)rb * 16, (uint64_t)p.Cout * 16, c8p * p.Cout * 16};
+    uint32_t box[4] = {(uint32_t)(2 * rb), (uint32_t)(p.cw / rb), (uint32_t)((p.kc / 8) * p.planes), 1};
+    int r = make_tmap(&tmB, a->wpk, 4, dims, strides, box);
     if (r) return r;
+    p.b_rb = rb;
   }
 
   // TMEM is 512 columns per SM: keep co-resident CTAs * tmem_cols <= 512 by padding the smem request.
