@@ -513,6 +513,153 @@ __global__ void k_blend(const float* __restrict__ a_src, const float* __restrict
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// image / latent losses (training_utils.py:54-99, metric/pytorch_ssim.py:18-38): one-pass reductions.
+// Every kernel block-reduces in fp64 and does one atomicAdd(double) per block and output.
+// ---------------------------------------------------------------------------------------------
+template <int NOUT>
+__device__ __forceinline__ void block_reduce_add(double* vals, double* out) {
+  __shared__ double red[NOUT][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NOUT; ++k) {
+#pragma unroll
+    for (int off = 16; off; off >>= 1) vals[k] += __shfl_xor_sync(0xffffffffu, vals[k], off);
+    if (lane == 0) red[k][warp] = vals[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < NOUT) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[threadIdx.x][w];
+    atomicAdd(&out[threadIdx.x], t);
+  }
+}
+
+// out[0..5] += sum a, sum b, sum a^2, sum b^2, sum a*b, sum (a-b)^2
+__global__ void __launch_bounds__(256) k_pair_moments(const float* __restrict__ a, const float* __restrict__ b,
+                                                      size_t n, double* __restrict__ out) {
+  double v[6] = {0, 0, 0, 0, 0, 0};
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double x = a[i], y = b[i], d = x - y;
+    v[0] += x; v[1] += y; v[2] += x * x; v[3] += y * y; v[4] += x * y; v[5] += d * d;
+  }
+  block_reduce_add<6>(v, out);
+}
+
+// KLDivLoss(log softmax(b), softmax(a)) summed: softmax over a dimension of size D and stride `inner`
+// (torch's implicit-dim rule picks dim 1 for 4-D and dim 0 for 3-D inputs, training_utils.py:68-69)
+__global__ void __launch_bounds__(256) k_softmax_kl(const float* __restrict__ a, const float* __restrict__ b,
+                                                    size_t outer, int D, size_t inner, double* __restrict__ out) {
+  double v[1] = {0};
+  const size_t total = outer * inner;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t o = i / inner, in = i % inner;
+    const float* pa = a + o * D * inner + in;
+    const float* pb = b + o * D * inner + in;
+    float ma = -INFINITY, mb = -INFINITY;
+    for (int d = 0; d < D; ++d) {
+      ma = fmaxf(ma, pa[d * inner]);
+      mb = fmaxf(mb, pb[d * inner]);
+    }
+    float sa = 0.f, sb = 0.f;
+    for (int d = 0; d < D; ++d) {
+      sa += expf(pa[d * inner] - ma);
+      sb += expf(pb[d * inner] - mb);
+    }
+    const float lsa = logf(sa), lsb = logf(sb);
+    for (int d = 0; d < D; ++d) {
+      const float la = pa[d * inner] - ma - lsa;   // log softmax(a)
+      const float t = expf(pa[d * inner] - ma) / sa;  // softmax(a), as the reference computes it
+      const float lq = logf(expf(pb[d * inner] - mb) / sb);  // log(softmax(b)) -- reference takes log of the softmax
+      (void)lsb;
+      // xlogy convention of kl_div: 0 where target == 0
+      if (t > 0.f) v[0] += (double)(t * (logf(t) - lq));
+      (void)la;
+    }
+  }
+  block_reduce_add<1>(v, out);
+}
+
+// f x f average pooling of an NCHW tensor (repeated F.avg_pool2d(.,2,2), training_utils.py:81-84)
+__global__ void k_avgpool_nchw(const float* __restrict__ x, float* __restrict__ out, size_t planes, int ho, int wo,
+                               int f) {
+  const size_t total = planes * ho * wo;
+  const int wi = wo * f, hi = ho * f;
+  const float inv = 1.f / (float)(f * f);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int xo = (int)(i % wo);
+    const int yo = (int)((i / wo) % ho);
+    const size_t pl = i / ((size_t)wo * ho);
+    const float* src = x + pl * hi * wi + (size_t)yo * f * wi + (size_t)xo * f;
+    float s = 0.f;
+    for (int dy = 0; dy < f; ++dy)
+      for (int dx = 0; dx < f; ++dx) s += src[(size_t)dy * wi + dx];
+    out[i] = s * inv;
+  }
+}
+
+// SSIM map mean: 11x11 Gaussian (sigma 1.5) depthwise, zero padding 5, C1 = 1e-4, C2 = 9e-4; out[0] += sum of map
+__constant__ float c_gauss11[11];
+__global__ void __launch_bounds__(256) k_ssim_sum(const float* __restrict__ a, const float* __restrict__ b,
+                                                  size_t planes, int h, int w, double* __restrict__ out) {
+  double v[1] = {0};
+  const size_t total = planes * h * w;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w);
+    const int y = (int)((i / w) % h);
+    const size_t pl = i / ((size_t)w * h);
+    const float* pa = a + pl * h * w;
+    const float* pb = b + pl * h * w;
+    float m1 = 0.f, m2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
+    for (int dy = -5; dy <= 5; ++dy) {
+      const int yy = y + dy;
+      if (yy < 0 || yy >= h) continue;
+      const float gy = c_gauss11[dy + 5];
+      for (int dx = -5; dx <= 5; ++dx) {
+        const int xx = x + dx;
+        if (xx < 0 || xx >= w) continue;
+        const float g = gy * c_gauss11[dx + 5];
+        const float va = pa[(size_t)yy * w + xx], vb = pb[(size_t)yy * w + xx];
+        m1 = fmaf(g, va, m1);
+        m2 = fmaf(g, vb, m2);
+        s11 = fmaf(g, va * va, s11);
+        s22 = fmaf(g, vb * vb, s22);
+        s12 = fmaf(g, va * vb, s12);
+      }
+    }
+    const float mu1_sq = m1 * m1, mu2_sq = m2 * m2, mu12 = m1 * m2;
+    const float sg1 = s11 - mu1_sq, sg2 = s22 - mu2_sq, sg12 = s12 - mu12;
+    const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+    v[0] += (double)(((2.f * mu12 + C1) * (2.f * sg12 + C2)) / ((mu1_sq + mu2_sq + C1) * (sg1 + sg2 + C2)));
+  }
+  block_reduce_add<1>(v, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// LREQAdam (model/utils/custom_adam.py:24-76): beta1 == 0 Adam, per-tensor step size
+//   v = beta2*v + (1-beta2)*g*g ;  p -= step[t] * g / (sqrt(v) + eps)
+// multi-tensor: block b works on tensor blk_tensor[b], elements [blk_off[b], blk_off[b] + chunk)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_lreq_adam(float* const* __restrict__ params, const float* const* __restrict__ grads,
+                            float* const* __restrict__ vs, const long long* __restrict__ numel,
+                            const float* __restrict__ step, const int* __restrict__ blk_tensor,
+                            const long long* __restrict__ blk_off, int chunk, float beta2, float eps) {
+  const int t = blk_tensor[blockIdx.x];
+  const long long off = blk_off[blockIdx.x];
+  long long end = off + chunk;
+  if (end > numel[t]) end = numel[t];
+  float* p = params[t];
+  const float* g = grads[t];
+  float* v = vs[t];
+  const float st = step[t], omb = 1.f - beta2;
+  for (long long i = off + threadIdx.x; i < end; i += blockDim.x) {
+    const float gi = g[i];
+    const float vi = v[i] * beta2 + omb * gi * gi;
+    v[i] = vi;
+    p[i] = p[i] - st * (gi / (sqrtf(vi) + eps));
+  }
+}
+
 }  // namespace dge
 
 // =================================================================================================
@@ -694,6 +841,50 @@ int dge_blend(const float* a_src, const float* b_src, float* out, float a, float
   DGE_REQUIRE(a_src && b_src && out, "blend: null pointer");
   DGE_REQUIRE(n > 0 && c > 0 && c % 8 == 0 && h_out > 0 && w_out > 0, "blend: bad dims");
   LAUNCH_1D(k_blend, (size_t)n * (c / 8) * h_out * w_out, stream, a_src, b_src, out, a, b, pool, n, c, h_out, w_out);
+}
+
+int dge_pair_moments(const float* a, const float* b, int64_t n, double* out6, void* stream) {
+  DGE_REQUIRE(a && b && out6 && n > 0, "pair_moments: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(out6, 0, 6 * sizeof(double), st) != cudaSuccess) { set_error("pair_moments: memset failed"); return DGE_ERR_CUDA; }
+  LAUNCH_1D(k_pair_moments, (size_t)n / 4 + 1, stream, a, b, (size_t)n, out6);
+}
+int dge_softmax_kl_sum(const float* a, const float* b, int64_t outer, int d, int64_t inner, double* out1, void* stream) {
+  DGE_REQUIRE(a && b && out1 && outer > 0 && d > 0 && inner > 0, "softmax_kl_sum: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(out1, 0, sizeof(double), st) != cudaSuccess) { set_error("softmax_kl_sum: memset failed"); return DGE_ERR_CUDA; }
+  LAUNCH_1D(k_softmax_kl, (size_t)outer * inner, stream, a, b, (size_t)outer, d, (size_t)inner, out1);
+}
+int dge_avgpool_nchw(const float* x, float* out, int64_t planes, int h_out, int w_out, int factor, void* stream) {
+  DGE_REQUIRE(x && out && planes > 0 && h_out > 0 && w_out > 0 && factor >= 1, "avgpool_nchw: bad args");
+  LAUNCH_1D(k_avgpool_nchw, (size_t)planes * h_out * w_out, stream, x, out, (size_t)planes, h_out, w_out, factor);
+}
+int dge_ssim_sum(const float* a, const float* b, int64_t planes, int h, int w, double* out1, void* stream) {
+  DGE_REQUIRE(a && b && out1 && planes > 0 && h > 0 && w > 0, "ssim_sum: bad args");
+  static bool init = false;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!init) {
+    // gaussian(11, 1.5) normalised, as metric/pytorch_ssim.py:8-10 (fp32 torch.Tensor arithmetic)
+    float g[11], sum = 0.f;
+    for (int i = 0; i < 11; ++i) { g[i] = (float)exp(-(double)((i - 5) * (i - 5)) / (2.0 * 1.5 * 1.5)); sum += g[i]; }
+    for (int i = 0; i < 11; ++i) g[i] /= sum;
+    if (cudaMemcpyToSymbol(c_gauss11, g, sizeof(g)) != cudaSuccess) { set_error("ssim_sum: constant upload failed"); return DGE_ERR_CUDA; }
+    init = true;
+  }
+  if (cudaMemsetAsync(out1, 0, sizeof(double), st) != cudaSuccess) { set_error("ssim_sum: memset failed"); return DGE_ERR_CUDA; }
+  LAUNCH_1D(k_ssim_sum, (size_t)planes * h * w, stream, a, b, (size_t)planes, h, w, out1);
+}
+
+int dge_lreq_adam_step(void* const* params, const void* const* grads, void* const* vs, const int64_t* numel,
+                       const float* step, const int32_t* blk_tensor, const int64_t* blk_off, int n_blocks, int chunk,
+                       float beta2, float eps, void* stream) {
+  DGE_REQUIRE(params && grads && vs && numel && step && blk_tensor && blk_off, "lreq_adam_step: null pointer");
+  DGE_REQUIRE(n_blocks > 0 && chunk > 0, "lreq_adam_step: bad launch shape");
+  k_lreq_adam<<<n_blocks, 256, 0, (cudaStream_t)stream>>>((float* const*)params, (const float* const*)grads,
+                                                          (float* const*)vs, (const long long*)numel, step, blk_tensor,
+                                                          (const long long*)blk_off, chunk, beta2, eps);
+  count_launch();
+  return check_launch("k_lreq_adam");
 }
 
 }  // extern "C"

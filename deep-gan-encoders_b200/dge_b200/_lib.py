@@ -64,6 +64,11 @@ SIGNATURES = {
     "dge_instance_stats": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_float, P]),
     "dge_instance_norm": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "dge_avgpool_to_act": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "dge_lreq_adam_step": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_float, c_float, P]),
+    "dge_pair_moments": (c_int, [P, P, c_int64, P, P]),
+    "dge_softmax_kl_sum": (c_int, [P, P, c_int64, c_int, c_int64, P, P]),
+    "dge_avgpool_nchw": (c_int, [P, P, c_int64, c_int, c_int, c_int, P]),
+    "dge_ssim_sum": (c_int, [P, P, c_int64, c_int, c_int, P, P]),
     "dge_blend": (c_int, [P, P, P, c_float, c_float, c_int, c_int, c_int, c_int, c_int, P]),
 }
 

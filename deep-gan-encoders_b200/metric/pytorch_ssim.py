@@ -1,0 +1,43 @@
+"""SSIM -- drop-in for the reference's `metric/pytorch_ssim.py` (`_ssim` :18-38, `SSIM` :40-61, `ssim` :63-74).
+
+The five 11x11 depthwise gaussian convolutions, the SSIM map and its mean are one fused kernel
+(`dge_ssim_sum`); only `size_average=True` (the only mode the inversion scripts use) is implemented.
+"""
+import ctypes
+
+import torch
+
+from dge_b200 import ops
+
+
+def _ssim_mean(img1, img2):
+    if not (img1.is_cuda and img2.is_cuda):
+        raise ops.DgeError('ssim: dge_b200 runs on a B200 only; there is no CPU fallback')
+    if torch.is_grad_enabled() and (img1.requires_grad or img2.requires_grad):
+        raise NotImplementedError('ssim: dge_b200 kernels are forward-only in this build; use torch.no_grad()')
+    assert img1.shape == img2.shape and img1.ndim == 4
+    a, b = img1.float().contiguous(), img2.float().contiguous()
+    n, c, h, w = a.shape
+    out = torch.empty(1, dtype=torch.float64, device=a.device)
+    ops.check(ops.lib().dge_ssim_sum(ops._p(a), ops._p(b), n * c, h, w, ops._p(out), ops._stream()))
+    return (out / float(a.numel())).float().view(())
+
+
+class SSIM(torch.nn.Module):
+    def __init__(self, window_size=11, size_average=True):
+        super().__init__()
+        if window_size != 11 or not size_average:
+            raise NotImplementedError('dge_b200 SSIM: window_size=11, size_average=True (the reference defaults)')
+        self.window_size = window_size
+        self.size_average = size_average
+        self.channel = 1
+
+    def forward(self, img1, img2):
+        self.channel = img1.size(1)
+        return _ssim_mean(img1, img2)
+
+
+def ssim(img1, img2, window_size=11, size_average=True):
+    if window_size != 11 or not size_average:
+        raise NotImplementedError('dge_b200 ssim: window_size=11, size_average=True (the reference defaults)')
+    return _ssim_mean(img1, img2)

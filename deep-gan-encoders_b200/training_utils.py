@@ -1,0 +1,111 @@
+"""Drop-in for the reference's `training_utils.py`: `space_loss` (:54-99) as fused device reductions, plus the
+small host helpers the scripts import (`set_seed` :46-51, `truncated_noise_sample` :32-44, `one_hot` :27-30,
+`get_parameter_number` :17-20).
+
+`space_loss` semantics kept: MSE / mean-MSE / std-MSE (unbiased std), implicit-dim softmax KL (logged only,
+NaN -> 0, inf -> 1), cosine over the flattened WHOLE batch, avg-pool while H > 256, SSIM, LPIPS through the
+caller's `lpips_model`, `loss = 5*mse + 3*cos + (1-ssim) + 2*lpips`, `loss_info` of Python floats.
+One pass over the image pair produces all six moments; the whole call does ONE device->host read instead of
+the reference's seven `.item()` syncs.  Forward-only in this build.
+"""
+import math
+
+import numpy as np
+import torch
+
+import metric.pytorch_ssim as pytorch_ssim
+from dge_b200 import ops
+
+
+def get_parameter_number(net):
+    total_num = sum(p.numel() for p in net.parameters())
+    trainable_num = sum(p.numel() for p in net.parameters() if p.requires_grad)
+    return {'Total': total_num, 'Trainable': trainable_num}
+
+
+def one_hot(x, class_count=1000):
+    return torch.eye(class_count)[x, :]
+
+
+def truncated_noise_sample(batch_size=1, dim_z=128, truncation=1., seed=None):
+    from scipy.stats import truncnorm
+    state = None if seed is None else np.random.RandomState(seed)
+    values = truncnorm.rvs(-2, 2, size=(batch_size, dim_z), random_state=state).astype(np.float32)
+    return truncation * values
+
+
+def set_seed(seed):
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    torch.cuda.manual_seed_all(seed)
+    torch.backends.cudnn.deterministic = True
+
+
+def avg_pool_to_256(x):
+    """`while x.shape[2] > 256: x = F.avg_pool2d(x, 2, 2)` (:81-84) as one pooling kernel."""
+    f = 1
+    h, w = x.shape[2], x.shape[3]
+    while h > 256:
+        h, w, f = h // 2, w // 2, f * 2
+    if f == 1:
+        return x
+    out = torch.empty((x.shape[0], x.shape[1], h, w), dtype=torch.float32, device=x.device)
+    ops.check(ops.lib().dge_avgpool_nchw(ops._p(x), ops._p(out), x.shape[0] * x.shape[1], h, w, f, ops._stream()))
+    return out
+
+
+def space_loss(imgs1, imgs2, image_space=True, lpips_model=None):
+    if not (imgs1.is_cuda and imgs2.is_cuda):
+        raise ops.DgeError('space_loss: dge_b200 runs on a B200 only; there is no CPU fallback')
+    if torch.is_grad_enabled() and (imgs1.requires_grad or imgs2.requires_grad):
+        raise NotImplementedError('space_loss: dge_b200 kernels are forward-only in this build; use torch.no_grad()')
+    if imgs1.reshape(-1).shape[0] != imgs2.reshape(-1).shape[0]:
+        print('error: vector1 dimentions are not equal to vector2 dimentions')
+        return
+    a = imgs1.float().contiguous()
+    b = imgs2.float().contiguous()
+    dev = a.device
+    n = a.numel()
+    L = ops.lib()
+    acc = torch.zeros(8, dtype=torch.float64, device=dev)   # 0..5 moments, 6 kl sum, 7 ssim sum
+    ops.check(L.dge_pair_moments(ops._p(a), ops._p(b), n, ops._p(acc), ops._stream()))
+    # implicit-dim softmax: dim 0 for 0/1/3-D inputs, dim 1 otherwise (torch.nn.functional._get_softmax_dim)
+    dim = 0 if a.ndim in (0, 1, 3) else 1
+    shape = list(a.shape)
+    outer = int(np.prod(shape[:dim])) if dim > 0 else 1
+    inner = int(np.prod(shape[dim + 1:])) if dim + 1 < len(shape) else 1
+    ops.check(L.dge_softmax_kl_sum(ops._p(a), ops._p(b), outer, shape[dim], inner, ops._p(acc[6:7]), ops._stream()))
+    lp = None
+    if image_space:
+        pa, pb = avg_pool_to_256(a), avg_pool_to_256(b)
+        ops.check(L.dge_ssim_sum(ops._p(pa), ops._p(pb), pa.shape[0] * pa.shape[1], pa.shape[2], pa.shape[3],
+                                 ops._p(acc[7:8]), ops._stream()))
+        lp = lpips_model(pa, pb).mean()      # third-party LPIPS (unpinned) stays the caller's module
+        n_ssim = pa.numel()
+    host = acc.cpu().tolist()               # the one sync of this call
+    sa, sb, saa, sbb, sab, sdd, kl_sum, ssim_sum = host
+    mse1 = sdd / n
+    m1, m2 = sa / n, sb / n
+    mse2 = (m1 - m2) ** 2
+    if n > 1:
+        std1 = math.sqrt(max((saa - n * m1 * m1) / (n - 1), 0.0))
+        std2 = math.sqrt(max((sbb - n * m2 * m2) / (n - 1), 0.0))
+    else:
+        std1 = std2 = float('nan')
+    mse3 = (std1 - std2) ** 2
+    kl = kl_sum / n
+    if math.isnan(kl):
+        kl = 0.0
+    if math.isinf(kl):
+        kl = 1.0
+    denom = math.sqrt(saa) * math.sqrt(sbb)
+    cos = 1 - (sab / denom if denom > 0 else float('nan'))
+    if image_space:
+        ssim_l = 1 - ssim_sum / n_ssim
+        lp_v = float(lp.item())
+    else:
+        ssim_l, lp_v = 0, 0
+    loss = 5 * mse1 + 3 * cos + ssim_l + 2 * lp_v
+    loss_t = torch.tensor(loss, dtype=torch.float32, device=dev)
+    loss_info = [[mse1, mse2, mse3], kl, cos, ssim_l, lp_v]
+    return loss_t, loss_info

@@ -157,6 +157,27 @@ int dge_avgpool_to_act(const float* x_f32b, void* out_act, int n, int c, int h, 
 int dge_blend(const float* a_src, const float* b_src, float* out, float a, float b, int pool, int n, int c,
               int h_out, int w_out, void* stream);
 
+/* ---- losses (training_utils.py:54-99 space_loss; metric/pytorch_ssim.py:18-38) ------------------ */
+/* out6 (zeroed by the call) = sum a, sum b, sum a^2, sum b^2, sum a*b, sum (a-b)^2 over n elements:
+   MSE, mean/std MSE terms and the whole-batch cosine all derive from these (training_utils.py:63-75). */
+int dge_pair_moments(const float* a, const float* b, int64_t n, double* out6, void* stream);
+/* sum over all elements of softmax(a)*(log softmax(a) - log softmax(b)), softmax over the axis of size d with
+   stride `inner` (torch's implicit-dim softmax + KLDivLoss, training_utils.py:68-69) */
+int dge_softmax_kl_sum(const float* a, const float* b, int64_t outer, int d, int64_t inner, double* out1, void* stream);
+/* factor x factor mean pooling of [planes][h_out*factor][w_out*factor] (avg_pool2d(2,2) loop, :81-84) */
+int dge_avgpool_nchw(const float* x, float* out, int64_t planes, int h_out, int w_out, int factor, void* stream);
+/* sum of the SSIM map (11x11 gaussian sigma 1.5, zero padding, C1=1e-4, C2=9e-4) over [planes][h][w] */
+int dge_ssim_sum(const float* a, const float* b, int64_t planes, int h, int w, double* out1, void* stream);
+
+/* ---- optimiser (model/utils/custom_adam.py:24-76, LREQAdam.step) ------------------------------ */
+/* One multi-tensor launch:  v = beta2*v + (1-beta2)*g*g ;  p -= step[t]*g/(sqrt(v)+eps)   (beta1 == 0).
+   params/grads/vs: DEVICE arrays of n_tensors device pointers; numel/step: per-tensor DEVICE arrays
+   (step[t] = lr*sqrt(1-beta2^t_t)*lr_equalization_coef_t); block b updates tensor blk_tensor[b], elements
+   [blk_off[b], blk_off[b]+chunk). */
+int dge_lreq_adam_step(void* const* params, const void* const* grads, void* const* vs, const int64_t* numel,
+                       const float* step, const int32_t* blk_tensor, const int64_t* blk_off, int n_blocks, int chunk,
+                       float beta2, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -122,5 +122,62 @@ def main():
     print("e2g_res32.pt: imgs2", tuple(img2.shape), float(img2.mean()), float(img2.std()))
 
 
+def stand_in_lpips(a, b):
+    """`lpips` (PyPI, unpinned) is absent offline; the fixtures use this deterministic stand-in for the callable."""
+    return ((a - b) ** 2).mean(dim=(1, 2, 3))
+
+
+def losses_and_optimizer():
+    import warnings
+    warnings.filterwarnings("ignore")
+    import training_utils as tu
+    from model.utils.custom_adam import LREQAdam
+    torch.set_grad_enabled(False)
+    cases = {}
+    specs = {"img64": ((2, 3, 64, 64), True), "img512x384": ((1, 3, 512, 384), True), "w": ((2, 8, 512), False),
+             "const": ((2, 64, 4, 4), False)}
+    for i, (name, (shape, image_space)) in enumerate(specs.items()):
+        g = torch.Generator().manual_seed(900 + i)
+        a = torch.randn(shape, generator=g)
+        b = a + 0.3 * torch.randn(shape, generator=g)
+        loss, info = tu.space_loss(a, b, image_space=image_space, lpips_model=stand_in_lpips)
+        cases[name] = {"shape": shape, "seed": 900 + i, "image_space": image_space, "loss": float(loss), "info": info}
+    torch.save(cases, os.path.join(HERE, "space_loss.pt"))
+    print("space_loss.pt:", {k: round(v["loss"], 6) for k, v in cases.items()})
+
+    # LREQAdam: 4 tensors (two with lr_equalization_coef), 3 steps, one tensor skipped (grad None) at step 2
+    torch.set_grad_enabled(True)
+    g = torch.Generator().manual_seed(77)
+    shapes = [(16, 8, 3, 3), (64, 32), (1, 32, 1, 1), (70001,)]
+    coefs = [0.0589, 0.125, None, None]
+    params = [torch.nn.Parameter(torch.randn(s, generator=g)) for s in shapes]
+    for p, c in zip(params, coefs):
+        if c is not None:
+            p.lr_equalization_coef = c
+    init = [p.detach().clone() for p in params]
+    opt = LREQAdam(params, lr=0.0015, betas=(0.0, 0.99), weight_decay=0)
+    grads = []
+    for step in range(3):
+        gs = []
+        for i, p in enumerate(params):
+            if step == 1 and i == 2:
+                p.grad = None
+                gs.append(None)
+            else:
+                p.grad = torch.randn(p.shape, generator=g)
+                gs.append(p.grad.clone())
+        grads.append(gs)
+        opt.step()
+    torch.save({"shapes": shapes, "coefs": coefs, "init": init, "grads": grads, "lr": 0.0015, "beta2": 0.99,
+                "final": [p.detach().clone() for p in params],
+                "exp_avg_sq": [opt.state[p]["exp_avg_sq"].clone() for p in params],
+                "steps": [opt.state[p]["step"] for p in params]}, os.path.join(HERE, "lreq_adam.pt"))
+    print("lreq_adam.pt: steps", [opt.state[p]["step"] for p in params])
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "losses":
+        import_reference()
+        losses_and_optimizer()
+        sys.exit(0)
     main()

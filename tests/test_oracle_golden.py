@@ -109,3 +109,47 @@ def test_e2g_roundtrip():
     assert rel(c2, fx["const2"]) < TOL and rel(w2, fx["w2"]) < TOL
     imgs2 = osg2.synthesis(gsd, fx["w2"], 32)["image"]
     assert rel(imgs2, fx["imgs2"]) < TOL
+
+
+def _lpips_stand_in(a, b):
+    return ((a - b) ** 2).mean(dim=(1, 2, 3))
+
+
+def _loss_inputs(case):
+    g = torch.Generator().manual_seed(case["seed"])
+    a = torch.randn(case["shape"], generator=g)
+    b = a + 0.3 * torch.randn(case["shape"], generator=g)
+    return a, b
+
+
+def test_space_loss_oracle():
+    import warnings
+    from oracle import losses as olosses
+    cases = torch.load(os.path.join(GOLD, "space_loss.pt"))
+    for name, c in cases.items():
+        a, b = _loss_inputs(c)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            loss, info = olosses.space_loss(a, b, image_space=c["image_space"], lpips_model=_lpips_stand_in)
+        assert abs(float(loss) - c["loss"]) <= 1e-6 * max(1.0, abs(c["loss"])), name
+        flat = lambda i: list(i[0]) + list(i[1:])
+        for x, y in zip(flat(info), flat(c["info"])):
+            assert abs(x - y) <= 1e-6 * max(1.0, abs(y)), name
+
+
+def test_lreq_adam_oracle():
+    from oracle import optim as ooptim
+    fx = torch.load(os.path.join(GOLD, "lreq_adam.pt"))
+    params = [p.clone() for p in fx["init"]]
+    v = [torch.zeros_like(p) for p in params]
+    steps = [0] * len(params)
+    for gs in fx["grads"]:
+        for i, g in enumerate(gs):
+            if g is not None:
+                steps[i] += 1
+        ooptim.lreq_adam_step(params, gs, v, steps, fx["coefs"], fx["lr"], fx["beta2"])
+    assert steps == fx["steps"]
+    for p, q in zip(params, fx["final"]):
+        assert rel(p, q) < 1e-6
+    for a, b in zip(v, fx["exp_avg_sq"]):
+        assert rel(a, b) < 1e-6
