@@ -65,6 +65,7 @@ struct ConvKParams {
   float noise_scalar;
   const float* bias;
   float slope, gain;
+  const float* preact_add;
   const float* blend_src;
   int blend_pool;
   float blend_a, blend_b;
@@ -234,6 +235,15 @@ __device__ __forceinline__ void epi_pointwise16(const ConvKParams& p, const Pixe
   if (p.bias) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] += __ldg(p.bias + c0 + j);
+  }
+  if (p.preact_add && px.valid) {
+    float r[8];
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      load8_f32b(p.preact_add, f32b_idx32(px.n, (c0 >> 3) + g, px.y, px.x, C8, H, W), r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[8 * g + j] += r[j];
+    }
   }
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = (v[j] < 0.f ? v[j] * p.slope : v[j]) * p.gain;
@@ -833,6 +843,7 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
 
   p.demod = a->demod; p.noise = a->noise; p.noise_bstride = a->noise_bstride; p.noise_w = a->noise_w;
   p.noise_scalar = a->noise_scalar; p.bias = a->bias; p.slope = a->slope; p.gain = a->gain;
+  p.preact_add = a->preact_add;
   p.blend_src = a->blend_src; p.blend_pool = a->blend_pool; p.blend_a = a->blend_a; p.blend_b = a->blend_b;
   p.out_act = a->out_act; p.out_planes = a->out_planes; p.out_scale = a->out_scale; p.out_f32b = a->out_f32b;
   p.out_nchw = a->out_nchw; p.rgb_w = a->rgb_w; p.rgb_out = a->rgb_out; p.out_raw_up = a->out_raw_up;

@@ -445,8 +445,10 @@ __global__ void k_instance_stats_final(const double* __restrict__ scratch, float
   }
 }
 
-__global__ void k_instance_norm(const float* __restrict__ x, const float* __restrict__ mr, void* __restrict__ out_act,
-                                float* __restrict__ out_f32b, int n, int c, int h, int w, int planes) {
+__global__ void k_instance_norm(const float* __restrict__ x, const float* __restrict__ mr,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                void* __restrict__ out_act, float* __restrict__ out_f32b, int n, int c, int h, int w,
+                                int planes) {
   const int C8 = c >> 3;
   const size_t total = (size_t)n * C8 * h * w;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -457,6 +459,7 @@ __global__ void k_instance_norm(const float* __restrict__ x, const float* __rest
     for (int k = 0; k < 8; ++k) {
       const size_t s = ((size_t)q.n * c + q.g * 8 + k) * 2;
       v[k] = (v[k] - __ldg(mr + s)) * __ldg(mr + s + 1);
+      if (gamma) v[k] = v[k] * __ldg(gamma + q.g * 8 + k) + __ldg(beta + q.g * 8 + k);
     }
     if (out_f32b) store8_f32b(out_f32b, i, v);
     if (out_act) store8_act(out_act, q.n, q.g, q.y, q.x, C8, planes, h, w, v);
@@ -511,6 +514,81 @@ __global__ void k_blend(const float* __restrict__ a_src, const float* __restrict
     for (int k = 0; k < 8; ++k) va[k] = a * va[k] + b * vb[k];
     store8_f32b(out, i, va);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// PGGAN: pixel-norm over channels (one thread per pixel; the second pass over the channel groups hits L1/L2)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float pixel_rnorm(const float* x, int n, int y, int xx, int C8, int h, int w, float eps) {
+  float ss = 0.f;
+  for (int g = 0; g < C8; ++g) {
+    float v[8];
+    load8_f32b(x, f32b_idx32(n, g, y, xx, C8, h, w), v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ss = fmaf(v[k], v[k], ss);
+  }
+  return 1.f / sqrtf(ss / (float)(C8 * 8) + eps);
+}
+
+__global__ void k_pixelnorm_to_act(const float* __restrict__ x, void* __restrict__ out, int n, int c, int h, int w,
+                                   int up, float eps, int planes) {
+  const int C8 = c >> 3;
+  const size_t total = (size_t)n * h * w;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int xx = (int)(i % w);
+    const int y = (int)((i / w) % h);
+    const int b = (int)(i / ((size_t)w * h));
+    const float rn = pixel_rnorm(x, b, y, xx, C8, h, w, eps);
+    for (int g = 0; g < C8; ++g) {
+      float v[8];
+      load8_f32b(x, f32b_idx32(b, g, y, xx, C8, h, w), v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] *= rn;
+      for (int dy = 0; dy < up; ++dy)
+        for (int dx = 0; dx < up; ++dx)
+          store8_act(out, b, g, y * up + dy, xx * up + dx, C8, planes, h * up, w * up, v);
+    }
+  }
+}
+
+__global__ void k_pixelnorm_to_rgb(const float* __restrict__ x, const float* __restrict__ wt,
+                                   const float* __restrict__ bias, float* __restrict__ out, int n, int c, int nch, int h,
+                                   int w, float eps) {
+  const int C8 = c >> 3;
+  const size_t total = (size_t)n * h * w;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int xx = (int)(i % w);
+    const int y = (int)((i / w) % h);
+    const int b = (int)(i / ((size_t)w * h));
+    const float rn = pixel_rnorm(x, b, y, xx, C8, h, w, eps);
+    for (int ch = 0; ch < nch; ++ch) {
+      float s = 0.f;
+      for (int g = 0; g < C8; ++g) {
+        float v[8];
+        load8_f32b(x, f32b_idx32(b, g, y, xx, C8, h, w), v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s = fmaf(v[k] * rn, __ldg(wt + (size_t)ch * c + g * 8 + k), s);
+      }
+      out[(((size_t)b * nch + ch) * h + y) * w + xx] = s + (bias ? bias[ch] : 0.f);
+    }
+  }
+}
+
+__global__ void k_upsample_nearest_nchw(const float* __restrict__ x, float* __restrict__ out, size_t planes, int h,
+                                        int w) {
+  const size_t total = planes * 4 * h * w;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int xo = (int)(i % (2 * w));
+    const int yo = (int)((i / (2 * w)) % (2 * h));
+    const size_t pl = i / ((size_t)4 * h * w);
+    out[i] = x[(pl * h + (yo >> 1)) * w + (xo >> 1)];
+  }
+}
+
+__global__ void k_axpby(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out, float a,
+                        float b, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = a * x[i] + b * y[i];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -825,7 +903,18 @@ int dge_instance_norm(const float* x, const float* mean_rstd, void* out_act, flo
   DGE_REQUIRE(x && mean_rstd && (out_act || out_f32b), "instance_norm: null pointer");
   REQ_NCHW("instance_norm");
   DGE_REQUIRE(!out_act || planes == 1 || planes == 2, "instance_norm: planes=%d", planes);
-  LAUNCH_1D(k_instance_norm, (size_t)n * (c / 8) * h * w, stream, x, mean_rstd, out_act, out_f32b, n, c, h, w, planes);
+  LAUNCH_1D(k_instance_norm, (size_t)n * (c / 8) * h * w, stream, x, mean_rstd, (const float*)nullptr,
+            (const float*)nullptr, out_act, out_f32b, n, c, h, w, planes);
+}
+
+int dge_instance_norm_affine(const float* x, const float* mean_rstd, const float* gamma, const float* beta,
+                             void* out_act, float* out_f32b, int n, int c, int h, int w, int planes, void* stream) {
+  DGE_REQUIRE(x && mean_rstd && (out_act || out_f32b), "instance_norm_affine: null pointer");
+  DGE_REQUIRE(!gamma == !beta, "instance_norm_affine: gamma and beta must be given together");
+  REQ_NCHW("instance_norm_affine");
+  DGE_REQUIRE(!out_act || planes == 1 || planes == 2, "instance_norm_affine: planes=%d", planes);
+  LAUNCH_1D(k_instance_norm, (size_t)n * (c / 8) * h * w, stream, x, mean_rstd, gamma, beta, out_act, out_f32b, n, c, h,
+            w, planes);
 }
 
 int dge_avgpool_to_act(const float* x, void* out_act, int n, int c, int h, int w, int planes, void* stream) {
@@ -841,6 +930,27 @@ int dge_blend(const float* a_src, const float* b_src, float* out, float a, float
   DGE_REQUIRE(a_src && b_src && out, "blend: null pointer");
   DGE_REQUIRE(n > 0 && c > 0 && c % 8 == 0 && h_out > 0 && w_out > 0, "blend: bad dims");
   LAUNCH_1D(k_blend, (size_t)n * (c / 8) * h_out * w_out, stream, a_src, b_src, out, a, b, pool, n, c, h_out, w_out);
+}
+
+int dge_pixelnorm_to_act(const float* x, void* out_act, int n, int c, int h, int w, int up, float eps, int planes,
+                         void* stream) {
+  DGE_REQUIRE(x && out_act, "pixelnorm_to_act: null pointer");
+  REQ_NCHW("pixelnorm_to_act");
+  DGE_REQUIRE((up == 1 || up == 2) && (planes == 1 || planes == 2), "pixelnorm_to_act: up=%d planes=%d", up, planes);
+  LAUNCH_1D(k_pixelnorm_to_act, (size_t)n * h * w, stream, x, out_act, n, c, h, w, up, eps, planes);
+}
+int dge_pixelnorm_to_rgb(const float* x, const float* w, const float* bias, float* out, int n, int c, int nch, int h,
+                         int wd, float eps, void* stream) {
+  DGE_REQUIRE(x && w && out && n > 0 && c > 0 && c % 8 == 0 && nch > 0 && h > 0 && wd > 0, "pixelnorm_to_rgb: bad args");
+  LAUNCH_1D(k_pixelnorm_to_rgb, (size_t)n * h * wd, stream, x, w, bias, out, n, c, nch, h, wd, eps);
+}
+int dge_upsample_nearest_nchw(const float* x, float* out, int64_t planes, int h, int w, void* stream) {
+  DGE_REQUIRE(x && out && planes > 0 && h > 0 && w > 0, "upsample_nearest_nchw: bad args");
+  LAUNCH_1D(k_upsample_nearest_nchw, (size_t)planes * 4 * h * w, stream, x, out, (size_t)planes, h, w);
+}
+int dge_axpby(const float* x, const float* y, float* out, float a, float b, int64_t n, void* stream) {
+  DGE_REQUIRE(x && y && out && n > 0, "axpby: bad args");
+  LAUNCH_1D(k_axpby, (size_t)n, stream, x, y, out, a, b, (size_t)n);
 }
 
 int dge_pair_moments(const float* a, const float* b, int64_t n, double* out6, void* stream) {

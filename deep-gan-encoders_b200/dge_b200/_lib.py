@@ -33,6 +33,7 @@ class ConvArgs(Structure):
         ("out_f32b", c_void_p), ("out_nchw", c_void_p),
         ("rgb_w", c_void_p), ("rgb_out", c_void_p),
         ("out_raw_up", c_void_p),
+        ("preact_add", c_void_p),
     ]
 
 
@@ -69,6 +70,11 @@ SIGNATURES = {
     "dge_softmax_kl_sum": (c_int, [P, P, c_int64, c_int, c_int64, P, P]),
     "dge_avgpool_nchw": (c_int, [P, P, c_int64, c_int, c_int, c_int, P]),
     "dge_ssim_sum": (c_int, [P, P, c_int64, c_int, c_int, P, P]),
+    "dge_instance_norm_affine": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "dge_pixelnorm_to_act": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, P]),
+    "dge_pixelnorm_to_rgb": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P]),
+    "dge_upsample_nearest_nchw": (c_int, [P, P, c_int64, c_int, c_int, P]),
+    "dge_axpby": (c_int, [P, P, P, c_float, c_float, c_int64, P]),
     "dge_blend": (c_int, [P, P, P, c_float, c_float, c_int, c_int, c_int, c_int, c_int, P]),
 }
 

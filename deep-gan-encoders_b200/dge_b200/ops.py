@@ -219,7 +219,7 @@ def pixel_norm(x, eps=1e-8):
 # ------------------------------------------------------------------------------------------------
 def conv(x, wpk, cout, kind=CONV_3X3, *, demod=None, noise=None, noise_batched=False, noise_w=None,
          noise_scalar=0.0, bias=None, slope=1.0, gain=1.0, blend_src=None, blend_pool=False, blend_a=0.0,
-         blend_b=1.0, out_act=False, out_planes=None, out_scale=None, out_f32b=False, out_nchw=False, rgb_w=None,
+         blend_b=1.0, preact_add=None, out_act=False, out_planes=None, out_scale=None, out_f32b=False, out_nchw=False, rgb_w=None,
          rgb_out=None, checker=False):
     """tcgen05 implicit-GEMM conv with fused epilogue (dge_conv_forward). Returns a dict of outputs."""
     assert isinstance(x, Act)
@@ -250,6 +250,8 @@ def conv(x, wpk, cout, kind=CONV_3X3, *, demod=None, noise=None, noise_batched=F
         a.noise_scalar = float(noise_scalar)
         a.bias = ptr(bias)
         a.slope, a.gain = float(slope), float(gain)
+        if preact_add is not None:
+            a.preact_add = ptr(preact_add.t if isinstance(preact_add, F32B) else preact_add)
         if blend_src is not None:
             a.blend_src = ptr(blend_src.t if isinstance(blend_src, F32B) else blend_src)
             a.blend_pool, a.blend_a, a.blend_b = int(blend_pool), float(blend_a), float(blend_b)
@@ -327,15 +329,50 @@ def instance_stats(x, eps=1e-8):
     return style, mr
 
 
-def instance_norm(x, mean_rstd, planes=2, out_act=True, out_f32b=False):
+def instance_norm(x, mean_rstd, planes=2, out_act=True, out_f32b=False, gamma=None, beta=None):
     assert isinstance(x, F32B)
     dev = x.t.device
     act = Act(x.n, x.c, x.h, x.w, planes, dev) if out_act else None
     f = F32B(x.n, x.c, x.h, x.w, dev) if out_f32b else None
+    g = None if gamma is None else gamma.detach().contiguous()
+    b = None if beta is None else beta.detach().contiguous()
     with _rec("instance_norm", (x.n, x.h, x.w, x.c, planes)):
-        check(lib().dge_instance_norm(_p(x.t), _f32(mean_rstd), _p(act.t) if act else None, _p(f.t) if f else None,
-                                      x.n, x.c, x.h, x.w, planes, _stream()))
+        check(lib().dge_instance_norm_affine(_p(x.t), _f32(mean_rstd), _f32(g), _f32(b), _p(act.t) if act else None,
+                                             _p(f.t) if f else None, x.n, x.c, x.h, x.w, planes, _stream()))
     return act, f
+
+
+def pixelnorm_to_act(x, up=1, eps=1e-8, planes=2):
+    assert isinstance(x, F32B)
+    out = Act(x.n, x.c, x.h * up, x.w * up, planes, x.t.device)
+    with _rec("pixelnorm_to_act", (x.n, x.h, x.w, x.c, up)):
+        check(lib().dge_pixelnorm_to_act(_p(x.t), _p(out.t), x.n, x.c, x.h, x.w, up, float(eps), planes, _stream()))
+    return out
+
+
+def pixelnorm_to_rgb(x, w, bias, eps=1e-8):
+    assert isinstance(x, F32B)
+    w2 = w.contiguous().view(w.shape[0], -1)
+    out = torch.empty((x.n, w2.shape[0], x.h, x.w), dtype=torch.float32, device=x.t.device)
+    bb = None if bias is None else bias.detach().contiguous()
+    check(lib().dge_pixelnorm_to_rgb(_p(x.t), _f32(w2), _f32(bb), _p(out), x.n, x.c, w2.shape[0], x.h, x.w, float(eps),
+                                     _stream()))
+    return out
+
+
+def upsample_nearest_nchw(x):
+    x = x.contiguous()
+    n, c, h, w = x.shape
+    out = torch.empty((n, c, 2 * h, 2 * w), dtype=torch.float32, device=x.device)
+    check(lib().dge_upsample_nearest_nchw(_f32(x), _p(out), n * c, h, w, _stream()))
+    return out
+
+
+def axpby(x, y, a, b):
+    x, y = x.contiguous(), y.contiguous()
+    out = torch.empty_like(x)
+    check(lib().dge_axpby(_f32(x), _f32(y), _p(out), float(a), float(b), x.numel(), _stream()))
+    return out
 
 
 def avgpool_to_act(x, planes=2):

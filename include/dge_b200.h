@@ -68,6 +68,7 @@ typedef struct dge_conv_args {
        v  = acc * demod[n][co]
        v += noise[n*noise_bstride + y*W + x] * (noise_w ? noise_w[co] : noise_scalar)
        v += bias[co]
+       v += preact_add[n][co][y][x]                   (F32B residual added BEFORE the activation, E_PG.py:100)
        v  = (v < 0 ? v*slope : v) * gain
        v  = blend_a * S(blend_src) + blend_b * v      (S = 2x2 mean of a double-resolution F32B tensor
                                                         if blend_pool, else the same-resolution value) */
@@ -91,6 +92,7 @@ typedef struct dge_conv_args {
   float* rgb_out;          /* NCHW [n][3][h][w]; contributions are atomically ADDED (pre-initialise with
                               dge_rgb_init) -- stylegan2_generator.py:515-522 */
   float* out_raw_up;       /* DGE_CONV_UP3X3 only: F32B-like [n][cout/8][2h+1][2w+1][8] raw transposed conv */
+  const float* preact_add; /* F32B [n][cout/8][h][w][8] or NULL */
 } dge_conv_args;
 
 int dge_conv_forward(const dge_conv_args* a, void* stream);
@@ -151,11 +153,26 @@ int dge_instance_stats(const float* x_f32b, double* scratch, float* style, float
 /* instance norm apply: F32B -> ACT (conv operand) and/or F32B */
 int dge_instance_norm(const float* x_f32b, const float* mean_rstd, void* out_act, float* out_f32b, int n, int c,
                       int h, int w, int planes, void* stream);
+/* as dge_instance_norm with the affine InstanceNorm2d(affine=True) weight/bias (E_PG.py:59,99): gamma/beta [c] or NULL */
+int dge_instance_norm_affine(const float* x_f32b, const float* mean_rstd, const float* gamma, const float* beta,
+                             void* out_act, float* out_f32b, int n, int c, int h, int w, int planes, void* stream);
 /* 2x2 average pool F32B -> ACT (residual branch, E.py:78) */
 int dge_avgpool_to_act(const float* x_f32b, void* out_act, int n, int c, int h, int w, int planes, void* stream);
 /* out = a*A' + b*B' where X' = 2x2 mean if pool else X; all F32B (E.py:76-84 when Cin==Cout) */
 int dge_blend(const float* a_src, const float* b_src, float* out, float a, float b, int pool, int n, int c,
               int h_out, int w_out, void* stream);
+
+/* ---- PGGAN pieces (model/pggan/pggan_generator.py:214-216, 230-233, 319-339) ------------------- */
+/* PixelNormLayer over channels + optional nearest x2 upsample: F32B [n][c/8][h][w][8] -> ACT at (h*up, w*up) */
+int dge_pixelnorm_to_act(const float* x_f32b, void* out_act, int n, int c, int h, int w, int up, float eps, int planes,
+                         void* stream);
+/* output ConvBlock: pixel-norm + 1x1 conv (w [nch][c], already times wscale) + bias -> NCHW [n][nch][h][w] */
+int dge_pixelnorm_to_rgb(const float* x_f32b, const float* w, const float* bias, float* out_nchw, int n, int c, int nch,
+                         int h, int wd, float eps, void* stream);
+/* F.interpolate(scale_factor=2, mode='nearest') on NCHW */
+int dge_upsample_nearest_nchw(const float* x, float* out, int64_t planes, int h, int w, void* stream);
+/* out = a*x + b*y over n floats */
+int dge_axpby(const float* x, const float* y, float* out, float a, float b, int64_t n, void* stream);
 
 /* ---- losses (training_utils.py:54-99 space_loss; metric/pytorch_ssim.py:18-38) ------------------ */
 /* out6 (zeroed by the call) = sum a, sum b, sum a^2, sum b^2, sum a*b, sum (a-b)^2 over n elements:

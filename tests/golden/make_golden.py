@@ -175,7 +175,54 @@ def losses_and_optimizer():
     print("lreq_adam.pt: steps", [opt.state[p]["step"] for p in params])
 
 
+def pggan():
+    import contextlib
+    import io
+    import model.pggan.pggan_generator as pg
+    import model.E.E_PG as EPG
+    torch.set_grad_enabled(False)
+    gen = torch.Generator().manual_seed(555)
+    torch.manual_seed(31)
+    cfg = dict(resolution=32, z_space_dim=64, fmaps_base=1024, fmaps_max=64)
+    G = pg.PGGANGenerator(**cfg).eval()
+    perturb(G, ["bias"], gen)
+    z = torch.randn(2, 64, generator=gen)
+    fx = {"config": cfg, "state_dict": clone_sd(G), "z": z, "images": {}}
+    with contextlib.redirect_stdout(io.StringIO()):
+        for lod in (0, 1.0, 0.5, 2):
+            fx["images"][lod] = G(z, lod=lod)["image"].clone()
+        fx["z_out"] = G(z)["z"].clone()
+        x = torch.randn(2, 64, 8, 8, generator=gen)
+        fx["block_up"] = {"x": x, "y": G.layer4(x).clone()}
+        fx["block_plain"] = {"x": x, "y": G.layer3(x).clone()}
+        fx["block_out"] = {"x": x, "y": G.output1(x).clone()}
+    torch.save(fx, os.path.join(HERE, "pggan_res32.pt"))
+    print("pggan_res32.pt:", {k: tuple(v.shape) for k, v in fx["images"].items()})
+
+    torch.manual_seed(32)
+    ecfg = dict(startf=16, maxf=64, layer_count=4, latent_size=512, channels=3, pggan=False)
+    E = EPG.BE(**ecfg).eval()
+    perturb(E, ["noise_weight_1", "noise_weight_2", "bias_1", "bias_2", "bias", "instance_norm_3.weight"], gen)
+    img = fx["images"][0]
+    efx = {"config": ecfg, "state_dict": clone_sd(E), "img": img, "blocks_seed8": {}}
+    x = E.FromRGB(img)
+    torch.manual_seed(8)
+    for i, blk in enumerate(E.decode_block):
+        y, _, _ = blk(x)
+        efx["blocks_seed8"][i] = {"x": x.clone(), "y": y.clone()}
+        x = y
+    efx["features_seed8"] = x.clone()
+    out = E(img)
+    efx["forward_returns"] = [o.clone() for o in out]
+    torch.save(efx, os.path.join(HERE, "e_pg_s16_l4.pt"))
+    print("e_pg_s16_l4.pt: features", tuple(x.shape), "forward returns", out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "pggan":
+        import_reference()
+        pggan()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "losses":
         import_reference()
         losses_and_optimizer()

@@ -153,3 +153,26 @@ def test_lreq_adam_oracle():
         assert rel(p, q) < 1e-6
     for a, b in zip(v, fx["exp_avg_sq"]):
         assert rel(a, b) < 1e-6
+
+
+def test_pggan_oracle():
+    from oracle import pggan as opg
+    fx = torch.load(os.path.join(GOLD, "pggan_res32.pt"))
+    sd = fx["state_dict"]
+    for lod, img in fx["images"].items():
+        assert rel(opg.generator(sd, fx["z"], 32, lod=lod), img) < TOL, lod
+    assert rel(opg.conv_block(sd, "layer4", fx["block_up"]["x"], upsample=True), fx["block_up"]["y"]) < TOL
+    assert rel(opg.conv_block(sd, "layer3", fx["block_plain"]["x"]), fx["block_plain"]["y"]) < TOL
+    assert rel(opg.conv_block(sd, "output1", fx["block_out"]["x"], ksize=1, padding=0, gain=1.0, lrelu=False),
+               fx["block_out"]["y"]) < TOL
+
+
+def test_e_pg_oracle():
+    from oracle import pggan as opg
+    fx = torch.load(os.path.join(GOLD, "e_pg_s16_l4.pt"))
+    sd = fx["state_dict"]
+    torch.manual_seed(8)
+    for i, b in fx["blocks_seed8"].items():
+        assert rel(opg.e_pg_block(sd, f"decode_block.{i}.", b["x"]), b["y"]) < TOL, i
+    torch.manual_seed(8)
+    assert rel(opg.e_pg_features(sd, fx["img"], 4), fx["features_seed8"]) < TOL
