@@ -517,6 +517,123 @@ __global__ void k_blend(const float* __restrict__ a_src, const float* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------
+// StyleGAN1 (model/stylegan1/net.py:141-169): what sits between a conv and the next instance norm.
+//   mode 0: src = conv_1 output (F32B, same size)            -> Blur 3x3 [1,2,1]^2/16, zero padding (net.py:48-58)
+//   mode 1: src = raw stride-2 transposed-conv map (2H+1)^2  -> 2x2 box sum (== the 4-shift `transform_kernel`
+//           of lreq.py:127-131 with stride 2 / padding 1), then the same zero-padded Blur
+//   mode 2: src = feature map, no filtering (first block: x = const)
+// then  + noise_w[c]*noise[n,y,x] + bias[c] -> leaky_relu(slope)   (net.py:148-152)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_sg1_post(const float* __restrict__ src, int mode, const float* __restrict__ noise,
+                           const float* __restrict__ noise_w, const float* __restrict__ bias, float slope,
+                           float* __restrict__ out, int n, int c, int ho, int wo) {
+  const int C8 = c >> 3;
+  const size_t total = (size_t)n * C8 * ho * wo;
+  const int hs = mode == 1 ? ho + 1 : ho, ws = mode == 1 ? wo + 1 : wo;
+  const float bl[3] = {0.25f, 0.5f, 0.25f};
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const Idx4 q = decode4(i, C8, ho, wo);
+    float acc[8];
+    if (mode == 2) {
+      load8_f32b(src, i, acc);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+      for (int dy = -1; dy <= 1; ++dy) {
+        const int y = q.y + dy;
+        if (y < 0 || y >= ho) continue;
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int x = q.x + dx;
+          if (x < 0 || x >= wo) continue;
+          const float wgt = bl[dy + 1] * bl[dx + 1];
+          float v[8];
+          if (mode == 0) {
+            load8_f32b(src, f32b_idx32(q.n, q.g, y, x, C8, hs, ws), v);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = fmaf(wgt, v[k], acc[k]);
+          } else {
+            float b4[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) b4[k] = 0.f;
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+              for (int b = 0; b < 2; ++b) {
+                load8_f32b(src, f32b_idx32(q.n, q.g, y + a, x + b, C8, hs, ws), v);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) b4[k] += v[k];
+              }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = fmaf(wgt, b4[k], acc[k]);
+          }
+        }
+      }
+    }
+    const float nz = noise ? noise[((size_t)q.n * ho + q.y) * wo + q.x] : 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int ch = q.g * 8 + k;
+      float v = acc[k];
+      if (noise) v = fmaf(nz, noise_w[ch], v);
+      if (bias) v += bias[ch];
+      acc[k] = v < 0.f ? v * slope : v;
+    }
+    store8_f32b(out, i, acc);
+  }
+}
+
+// instance norm + style_mod (net.py:32-34, 154-156): y = (x-mean)*rstd*(style[n][0][c]+1) + style[n][1][c];
+// the input may hold a single sample that is broadcast over the batch (first block: x = const);
+// optional nearest x2 upsample of the result (upscale2d of the NEXT block, net.py:37-43, 143)
+__global__ void k_instance_norm_style(const float* __restrict__ x, int in_n, const float* __restrict__ mr,
+                                      const float* __restrict__ style, int up, void* __restrict__ out_act,
+                                      float* __restrict__ out_f32b, int n, int c, int h, int w, int planes) {
+  const int C8 = c >> 3;
+  const size_t total = (size_t)n * C8 * h * w;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const Idx4 q = decode4(i, C8, h, w);
+    const int sn = in_n == 1 ? 0 : q.n;
+    float v[8];
+    load8_f32b(x, f32b_idx32(sn, q.g, q.y, q.x, C8, h, w), v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int ch = q.g * 8 + k;
+      const size_t s = ((size_t)sn * c + ch) * 2;
+      float t = (v[k] - __ldg(mr + s)) * __ldg(mr + s + 1);
+      if (style) t = fmaf(t, __ldg(style + (size_t)q.n * 2 * c + ch) + 1.f, __ldg(style + (size_t)q.n * 2 * c + c + ch));
+      v[k] = t;
+    }
+    for (int dy = 0; dy < up; ++dy)
+      for (int dx = 0; dx < up; ++dx) {
+        if (out_f32b) store8_f32b(out_f32b, f32b_idx32(q.n, q.g, q.y * up + dy, q.x * up + dx, C8, h * up, w * up), v);
+        if (out_act) store8_act(out_act, q.n, q.g, q.y * up + dy, q.x * up + dx, C8, planes, h * up, w * up, v);
+      }
+  }
+}
+
+// 1x1 conv F32B -> NCHW (ToRGB, net.py:244-253); one thread per pixel
+__global__ void k_to_rgb_f32b(const float* __restrict__ x, const float* __restrict__ wt, const float* __restrict__ bias,
+                              float* __restrict__ out, int n, int c, int nch, int h, int w) {
+  const int C8 = c >> 3;
+  const size_t total = (size_t)n * h * w;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int xx = (int)(i % w);
+    const int y = (int)((i / w) % h);
+    const int b = (int)(i / ((size_t)w * h));
+    for (int ch = 0; ch < nch; ++ch) {
+      float s = bias ? bias[ch] : 0.f;
+      for (int g = 0; g < C8; ++g) {
+        float v[8];
+        load8_f32b(x, f32b_idx32(b, g, y, xx, C8, h, w), v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s = fmaf(v[k], __ldg(wt + (size_t)ch * c + g * 8 + k), s);
+      }
+      out[(((size_t)b * nch + ch) * h + y) * w + xx] = s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // PGGAN: pixel-norm over channels (one thread per pixel; the second pass over the channel groups hits L1/L2)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float pixel_rnorm(const float* x, int n, int y, int xx, int C8, int h, int w, float eps) {
@@ -930,6 +1047,29 @@ int dge_blend(const float* a_src, const float* b_src, float* out, float a, float
   DGE_REQUIRE(a_src && b_src && out, "blend: null pointer");
   DGE_REQUIRE(n > 0 && c > 0 && c % 8 == 0 && h_out > 0 && w_out > 0, "blend: bad dims");
   LAUNCH_1D(k_blend, (size_t)n * (c / 8) * h_out * w_out, stream, a_src, b_src, out, a, b, pool, n, c, h_out, w_out);
+}
+
+int dge_sg1_post(const float* src, int mode, const float* noise, const float* noise_w, const float* bias, float slope,
+                 float* out_f32b, int n, int c, int h_out, int w_out, void* stream) {
+  DGE_REQUIRE(src && out_f32b && mode >= 0 && mode <= 2, "sg1_post: bad args");
+  DGE_REQUIRE(n > 0 && c > 0 && c % 8 == 0 && h_out > 0 && w_out > 0, "sg1_post: bad dims");
+  DGE_REQUIRE(!noise == !noise_w, "sg1_post: noise and noise_w must be given together");
+  LAUNCH_1D(k_sg1_post, (size_t)n * (c / 8) * h_out * w_out, stream, src, mode, noise, noise_w, bias, slope, out_f32b, n,
+            c, h_out, w_out);
+}
+int dge_instance_norm_style(const float* x, int in_n, const float* mean_rstd, const float* style, int up, void* out_act,
+                            float* out_f32b, int n, int c, int h, int w, int planes, void* stream) {
+  DGE_REQUIRE(x && mean_rstd && (out_act || out_f32b), "instance_norm_style: null pointer");
+  REQ_NCHW("instance_norm_style");
+  DGE_REQUIRE((in_n == n || in_n == 1) && (up == 1 || up == 2), "instance_norm_style: in_n=%d up=%d", in_n, up);
+  DGE_REQUIRE(!out_act || planes == 1 || planes == 2, "instance_norm_style: planes=%d", planes);
+  LAUNCH_1D(k_instance_norm_style, (size_t)n * (c / 8) * h * w, stream, x, in_n, mean_rstd, style, up, out_act, out_f32b,
+            n, c, h, w, planes);
+}
+int dge_to_rgb_f32b(const float* x, const float* w, const float* bias, float* out, int n, int c, int nch, int h, int wd,
+                    void* stream) {
+  DGE_REQUIRE(x && w && out && n > 0 && c > 0 && c % 8 == 0 && nch > 0 && h > 0 && wd > 0, "to_rgb_f32b: bad args");
+  LAUNCH_1D(k_to_rgb_f32b, (size_t)n * h * wd, stream, x, w, bias, out, n, c, nch, h, wd);
 }
 
 int dge_pixelnorm_to_act(const float* x, void* out_act, int n, int c, int h, int w, int up, float eps, int planes,

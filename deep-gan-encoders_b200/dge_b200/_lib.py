@@ -75,6 +75,9 @@ SIGNATURES = {
     "dge_pixelnorm_to_rgb": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P]),
     "dge_upsample_nearest_nchw": (c_int, [P, P, c_int64, c_int, c_int, P]),
     "dge_axpby": (c_int, [P, P, P, c_float, c_float, c_int64, P]),
+    "dge_sg1_post": (c_int, [P, c_int, P, P, P, c_float, P, c_int, c_int, c_int, c_int, P]),
+    "dge_instance_norm_style": (c_int, [P, c_int, P, P, c_int, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "dge_to_rgb_f32b": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "dge_blend": (c_int, [P, P, P, c_float, c_float, c_int, c_int, c_int, c_int, c_int, P]),
 }
 

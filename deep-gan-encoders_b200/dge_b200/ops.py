@@ -342,6 +342,37 @@ def instance_norm(x, mean_rstd, planes=2, out_act=True, out_f32b=False, gamma=No
     return act, f
 
 
+def sg1_post(src, mode, n, c, h_out, w_out, noise=None, noise_w=None, bias=None, slope=0.2):
+    """src: F32B (modes 0, 2) or the raw_up tensor of a CONV_UP3X3 launch (mode 1)."""
+    t = src.t if isinstance(src, F32B) else src
+    out = F32B(n, c, h_out, w_out, t.device)
+    with _rec("sg1_post", (n, h_out, w_out, c, mode)):
+        check(lib().dge_sg1_post(_f32(t), mode, _f32(noise), _f32(noise_w), _f32(bias), float(slope), _p(out.t), n, c,
+                                 h_out, w_out, _stream()))
+    return out
+
+
+def instance_norm_style(x, mean_rstd, style, n, up=1, planes=2, out_act=True, out_f32b=False):
+    assert isinstance(x, F32B)
+    dev = x.t.device
+    act = Act(n, x.c, x.h * up, x.w * up, planes, dev) if out_act else None
+    f = F32B(n, x.c, x.h * up, x.w * up, dev) if out_f32b else None
+    st = None if style is None else style.contiguous()
+    with _rec("instance_norm_style", (n, x.h, x.w, x.c, up)):
+        check(lib().dge_instance_norm_style(_p(x.t), x.n, _f32(mean_rstd), _f32(st), up, _p(act.t) if act else None,
+                                            _p(f.t) if f else None, n, x.c, x.h, x.w, planes, _stream()))
+    return act, f
+
+
+def to_rgb_f32b(x, w, bias):
+    assert isinstance(x, F32B)
+    w2 = w.detach().contiguous().view(w.shape[0], -1)
+    out = torch.empty((x.n, w2.shape[0], x.h, x.w), dtype=torch.float32, device=x.t.device)
+    bb = None if bias is None else bias.detach().contiguous()
+    check(lib().dge_to_rgb_f32b(_p(x.t), _f32(w2), _f32(bb), _p(out), x.n, x.c, w2.shape[0], x.h, x.w, _stream()))
+    return out
+
+
 def pixelnorm_to_act(x, up=1, eps=1e-8, planes=2):
     assert isinstance(x, F32B)
     out = Act(x.n, x.c, x.h * up, x.w * up, planes, x.t.device)

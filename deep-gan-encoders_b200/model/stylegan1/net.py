@@ -1,0 +1,260 @@
+"""B200-native StyleGAN1 generator -- drop-in for the hot-path classes of the reference's `model/stylegan1/net.py`:
+DecodeBlock (:110-169), ToRGB (:244-253), Generator (:256-362, `decode` :331-336), Mapping (:441-466),
+plus pixel_norm / style_mod / upscale2d / downscale2d / Blur (:28-58).
+
+Same constructor arguments, state_dict keys (`const`, `decode_block.{i}.*` incl. the `blur.weight`
+buffer and the `[in, out, 3, 3]` transposed-conv weights of the fused-scale blocks, `to_rgb.{i}.to_rgb.*`), and the
+reference's quirks: the first block runs on `const` with batch 1, so its first noise draw is `[1,1,4,4]` and shared by
+the batch; noise is `torch.randn` on the CPU per stage (:148,160).
+
+Per block:  [nearest x2 -> tcgen05 3x3 conv | tcgen05 stride-2 transposed conv]  -> one kernel (2x2 box for the
+4-tap `transform_kernel`, 3x3 Blur, noise, bias, lrelu) -> stats -> one kernel (instance norm + style_mod + bf16 split
+[+ upsample for the next block]) -> tcgen05 3x3 conv with noise/bias/lrelu epilogue -> stats -> norm+style_mod.
+`decode2`/`decode3`/`forward_double` (blend / blob-removal experiments) are not on the inversion path.
+"""
+import numpy as np
+import torch
+from torch import nn
+from torch.nn import init
+from torch.nn.parameter import Parameter
+
+import model.utils.lreq as ln
+from dge_b200 import ops
+
+DEFAULT_PLANES = 2
+
+
+def pixel_norm(x, epsilon=1e-8):
+    ln._guard('pixel_norm', x)
+    return ops.pixel_norm(x.float(), epsilon)
+
+
+def upscale2d(x, factor=2):
+    ln._guard('upscale2d', x)
+    if factor != 2:
+        raise NotImplementedError('upscale2d: factor 2 only')
+    return ops.upsample_nearest_nchw(x.float())
+
+
+def downscale2d(x, factor=2):
+    from model.utils.net import downscale2d as _d
+    return _d(x, factor)
+
+
+class Blur(nn.Module):
+    """Holds the reference's `weight` buffer ([C,1,3,3] of [1,2,1]^2/16); the filtering is fused (dge_sg1_post)."""
+
+    def __init__(self, channels):
+        super().__init__()
+        f = np.array([1, 2, 1], dtype=np.float32)
+        f = f[:, np.newaxis] * f[np.newaxis, :]
+        f /= np.sum(f)
+        self.register_buffer('weight', torch.Tensor(f).view(1, 1, 3, 3).repeat(channels, 1, 1, 1))
+        self.groups = channels
+
+    def forward(self, x):
+        ln._guard('Blur', x)
+        n, c, h, w = x.shape
+        return ops.sg1_post(ops.nchw_to_f32b(x.float()), 0, n, c, h, w, slope=1.0).to_nchw()
+
+
+class DecodeBlock(nn.Module):
+    def __init__(self, inputs, outputs, latent_size, has_first_conv=True, fused_scale=True):
+        super().__init__()
+        self.has_first_conv = has_first_conv
+        self.inputs = inputs
+        self.outputs = outputs
+        self.fused_scale = fused_scale
+        if has_first_conv:
+            if fused_scale:
+                self.conv_1 = ln.ConvTranspose2d(inputs, outputs, 3, 2, 1, bias=False, transform_kernel=True)
+            else:
+                self.conv_1 = ln.Conv2d(inputs, outputs, 3, 1, 1, bias=False)
+        self.blur = Blur(outputs)
+        self.noise_weight_1 = nn.Parameter(torch.zeros(1, outputs, 1, 1))
+        self.bias_1 = nn.Parameter(torch.zeros(1, outputs, 1, 1))
+        self.instance_norm_1 = nn.InstanceNorm2d(outputs, affine=False, eps=1e-8)
+        self.style_1 = ln.Linear(latent_size, 2 * outputs, gain=1)
+        self.conv_2 = ln.Conv2d(outputs, outputs, 3, 1, 1, bias=False)
+        self.noise_weight_2 = nn.Parameter(torch.zeros(1, outputs, 1, 1))
+        self.bias_2 = nn.Parameter(torch.zeros(1, outputs, 1, 1))
+        self.instance_norm_2 = nn.InstanceNorm2d(outputs, affine=False, eps=1e-8)
+        self.style_2 = ln.Linear(latent_size, 2 * outputs, gain=1)
+        self.planes = DEFAULT_PLANES
+        self.noise_mode = 'reference'
+
+    def _noise(self, n, h, w, device):
+        if self.noise_mode == 'device':
+            return torch.randn([n, 1, h, w], device=device)
+        return torch.randn([n, 1, h, w]).to(device)
+
+    def _conv1_packed(self):
+        c = self.conv_1
+        key = (c.weight.data_ptr(), c.weight._version, self.planes)
+        if getattr(self, '_c1_key', None) != key:
+            scale = 1.0 if c.implicit_lreq else c.std
+            if self.fused_scale:     # weight is [in, out, k, k] and used un-flipped by conv_transpose2d (lreq.py:127-140)
+                w = c.weight.detach().permute(1, 0, 2, 3).contiguous()
+            else:
+                w = c.weight.detach()
+            self._c1 = ops.pack_conv_weight(w, scale=scale, planes=self.planes)
+            self._c1_key = key
+        return self._c1
+
+    def run(self, x, s1, s2, next_up=1, last=False):
+        """x: for the first block the F32B `const` (batch 1); otherwise the ACT operand of conv_1 (already
+        nearest-upsampled for the non-fused blocks).  Returns the ACT operand for the next block (upsampled if
+        `next_up == 2`), or the F32B feature map if `last`."""
+        n = s1.shape[0]
+        nw1, b1 = self.noise_weight_1.detach().view(-1), self.bias_1.detach().view(-1)
+        nw2, b2 = self.noise_weight_2.detach().view(-1), self.bias_2.detach().view(-1)
+        if not self.has_first_conv:
+            dev, h, w, nb = x.t.device, x.h, x.w, x.n
+            y = ops.sg1_post(x, 2, nb, self.outputs, h, w, noise=self._noise(nb, h, w, dev), noise_w=nw1, bias=b1)
+        elif self.fused_scale:
+            dev, h, w, nb = x.t.device, 2 * x.h, 2 * x.w, x.n
+            raw = ops.conv(x, self._conv1_packed(), self.outputs, ops.CONV_UP3X3)['raw_up']
+            y = ops.sg1_post(raw, 1, nb, self.outputs, h, w, noise=self._noise(nb, h, w, dev), noise_w=nw1, bias=b1)
+        else:
+            dev, h, w, nb = x.t.device, x.h, x.w, x.n
+            c1 = ops.conv(x, self._conv1_packed(), self.outputs, ops.CONV_3X3, out_f32b=True)['f32b']
+            y = ops.sg1_post(c1, 0, nb, self.outputs, h, w, noise=self._noise(nb, h, w, dev), noise_w=nw1, bias=b1)
+        _, mr1 = ops.instance_stats(y, self.instance_norm_1.eps)
+        st1 = ops.dense(s1.float().contiguous(), self.style_1.weight, self.style_1.bias)
+        xa, _ = ops.instance_norm_style(y, mr1, st1, n, planes=self.planes)                    # :154-156
+        y2 = ops.conv(xa, self.conv_2.packed(self.planes), self.outputs, ops.CONV_3X3, noise=self._noise(n, h, w, dev),
+                      noise_batched=True, noise_w=nw2, bias=b2, slope=0.2, out_f32b=True)['f32b']   # :158-164
+        _, mr2 = ops.instance_stats(y2, self.instance_norm_2.eps)
+        st2 = ops.dense(s2.float().contiguous(), self.style_2.weight, self.style_2.bias)
+        act, f = ops.instance_norm_style(y2, mr2, st2, n, up=next_up, planes=self.planes, out_act=not last,
+                                         out_f32b=last)                                       # :165-167
+        return f if last else act
+
+    def forward(self, x, s1, s2):
+        """Reference signature: NCHW in -> NCHW out."""
+        ln._guard('DecodeBlock', x, s1, s2, self.conv_2.weight)
+        f = ops.nchw_to_f32b(x.float())
+        if self.has_first_conv:
+            if self.fused_scale:
+                xin = ops.f32b_to_act(f, self.planes)
+            else:
+                xin = ops.f32b_to_act(ops.nchw_to_f32b(ops.upsample_nearest_nchw(x.float())), self.planes)
+        else:
+            xin = f
+        return self.run(xin, s1, s2, last=True).to_nchw()
+
+
+class FromRGB(nn.Module):
+    def __init__(self, channels, outputs):
+        super().__init__()
+        self.from_rgb = ln.Conv2d(channels, outputs, 1, 1, 0)
+
+    def forward(self, x):
+        ln._guard('FromRGB', x, self.from_rgb.weight)
+        return ops.from_rgb(x.float(), self.from_rgb.weight, self.from_rgb.scaled_bias(), slope=0.2).to_nchw()
+
+
+class ToRGB(nn.Module):
+    def __init__(self, inputs, channels):
+        super().__init__()
+        self.inputs = inputs
+        self.channels = channels
+        self.to_rgb = ln.Conv2d(inputs, channels, 1, 1, 0, gain=1)
+
+    def run(self, f):
+        return ops.to_rgb_f32b(f, self.to_rgb.weight, self.to_rgb.scaled_bias())
+
+    def forward(self, x):
+        ln._guard('ToRGB', x, self.to_rgb.weight)
+        return self.run(ops.nchw_to_f32b(x.float()))
+
+
+class Generator(nn.Module):
+    def __init__(self, startf=32, maxf=256, layer_count=3, latent_size=128, channels=3):
+        super().__init__()
+        self.maxf = maxf
+        self.startf = startf
+        self.layer_count = layer_count
+        self.channels = channels
+        self.latent_size = latent_size
+        mul = 2 ** (self.layer_count - 1)
+        inputs = min(self.maxf, startf * mul)
+        self.const = Parameter(torch.Tensor(1, inputs, 4, 4))
+        self.zeros = torch.zeros(1, 1, 1, 1)
+        init.ones_(self.const)
+        self.layer_to_resolution = [0 for _ in range(layer_count)]
+        resolution = 2
+        self.style_sizes = []
+        to_rgb = nn.ModuleList()
+        self.decode_block = nn.ModuleList()
+        for i in range(self.layer_count):
+            outputs = min(self.maxf, startf * mul)
+            has_first_conv = i != 0
+            fused_scale = resolution * 2 >= 128
+            block = DecodeBlock(inputs, outputs, latent_size, has_first_conv, fused_scale=fused_scale)
+            resolution *= 2
+            self.layer_to_resolution[i] = resolution
+            self.style_sizes += [2 * (inputs if has_first_conv else outputs), 2 * outputs]
+            to_rgb.append(ToRGB(outputs, channels))
+            self.decode_block.append(block)
+            inputs = outputs
+            mul //= 2
+        self.to_rgb = to_rgb
+
+    def set_noise_mode(self, mode):
+        assert mode in ('reference', 'device')
+        for b in self.decode_block:
+            b.noise_mode = mode
+
+    def decode(self, styles, lod, noise=0):
+        ln._guard('Generator.decode', styles, self.const)
+        x = ops.nchw_to_f32b(self.const.detach().float())
+        for i in range(lod + 1):
+            blk = self.decode_block[i]
+            last = i == lod
+            nxt = self.decode_block[i + 1] if not last else None
+            next_up = 2 if (nxt is not None and not nxt.fused_scale) else 1
+            x = blk.run(x, styles[:, 2 * i + 0], styles[:, 2 * i + 1], next_up=next_up, last=last)
+        return self.to_rgb[lod].run(x)
+
+    def forward(self, styles, lod, blend=1, remove_blob=False):
+        if remove_blob or blend != 1:
+            raise NotImplementedError('dge_b200 implements Generator.decode (blend == 1, remove_blob == False), the '
+                                      'path the inversion scripts call (E_align_s2.py:109,158)')
+        return self.decode(styles, lod, 1)
+
+
+class MappingBlock(nn.Module):
+    def __init__(self, inputs, output, lrmul=0.01):
+        super().__init__()
+        self.fc = ln.Linear(inputs, output, lrmul=lrmul)
+
+    def forward(self, x):
+        ln._guard('MappingBlock', x, self.fc.weight)
+        fc = self.fc
+        if fc.implicit_lreq:
+            return ops.dense(x.float(), fc.weight, fc.bias, slope=0.2)
+        return ops.dense(x.float(), fc.weight, fc.bias, wscale=fc.std, bscale=fc.lrmul, slope=0.2)
+
+
+class Mapping(nn.Module):
+    def __init__(self, num_layers=18, mapping_layers=8, latent_size=512, dlatent_size=512, mapping_fmaps=512,
+                 trunc_tensor=None):
+        super().__init__()
+        inputs = latent_size
+        self.mapping_layers = mapping_layers
+        self.num_layers = num_layers
+        for i in range(mapping_layers):
+            outputs = dlatent_size if i == mapping_layers - 1 else mapping_fmaps
+            setattr(self, "block_%d" % (i + 1), MappingBlock(inputs, outputs, lrmul=0.01))
+            inputs = outputs
+        self.register_buffer('buffer1', trunc_tensor)
+
+    def forward(self, z, coefs_m=0):
+        x = pixel_norm(z)
+        for i in range(self.mapping_layers):
+            x = getattr(self, "block_%d" % (i + 1))(x)
+        x = x.view(x.shape[0], 1, x.shape[1]).repeat(1, self.num_layers, 1)
+        if self.buffer1 is not None:
+            x = torch.lerp(self.buffer1.data, x, coefs_m)     # avg + (styles - avg) * coefs  (:464-465)
+        return x

@@ -162,6 +162,23 @@ int dge_avgpool_to_act(const float* x_f32b, void* out_act, int n, int c, int h, 
 int dge_blend(const float* a_src, const float* b_src, float* out, float a, float b, int pool, int n, int c,
               int h_out, int w_out, void* stream);
 
+/* ---- StyleGAN1 pieces (model/stylegan1/net.py:32-58, 141-169, 244-253) ------------------------------ */
+/* filter + noise + bias + lrelu between a conv and the next instance norm.
+   mode 0: src F32B [n][c/8][h][w][8] -> 3x3 Blur ([1,2,1]^2/16, zero pad)               (Blur, :48-58)
+   mode 1: src raw transposed-conv map [n][c/8][h+1][w+1][8] (dge_conv_forward UP3X3) -> 2x2 box sum (the
+           `transform_kernel` 4-shift sum with stride 2 / padding 1, lreq.py:127-131) -> the same Blur
+   mode 2: no filtering (first block, x = const)
+   then v = v + noise_w[c]*noise[n][y][x] + bias[c]; lrelu(slope)                           (:148-152) */
+int dge_sg1_post(const float* src, int mode, const float* noise, const float* noise_w, const float* bias, float slope,
+                 float* out_f32b, int n, int c, int h_out, int w_out, void* stream);
+/* instance norm + style_mod: y = (x-mean)*rstd*(style[n][c]+1) + style[n][C+c]  (:32-34,154-156); in_n == 1 broadcasts a
+   single input sample over the batch (x = const); up = 2 writes the nearest-upsampled result (upscale2d :37-43) */
+int dge_instance_norm_style(const float* x_f32b, int in_n, const float* mean_rstd, const float* style, int up,
+                            void* out_act, float* out_f32b, int n, int c, int h, int w, int planes, void* stream);
+/* ToRGB: 1x1 conv F32B -> NCHW [n][nch][h][w]  (:244-253) */
+int dge_to_rgb_f32b(const float* x_f32b, const float* w, const float* bias, float* out_nchw, int n, int c, int nch,
+                    int h, int wd, void* stream);
+
 /* ---- PGGAN pieces (model/pggan/pggan_generator.py:214-216, 230-233, 319-339) ------------------- */
 /* PixelNormLayer over channels + optional nearest x2 upsample: F32B [n][c/8][h][w][8] -> ACT at (h*up, w*up) */
 int dge_pixelnorm_to_act(const float* x_f32b, void* out_act, int n, int c, int h, int w, int up, float eps, int planes,

@@ -218,7 +218,52 @@ def pggan():
     print("e_pg_s16_l4.pt: features", tuple(x.shape), "forward returns", out)
 
 
+def stylegan1():
+    import model.stylegan1.net as sg1
+    torch.set_grad_enabled(False)
+    gen = torch.Generator().manual_seed(808)
+    # 6 blocks: 4..128; the last block (res 128) is a fused-scale (transposed conv) block, the others nearest-up + conv
+    torch.manual_seed(41)
+    cfg = dict(startf=16, maxf=32, layer_count=6, latent_size=64, channels=3)
+    Gs = sg1.Generator(**cfg).eval()
+    perturb(Gs, ["noise_weight_1", "noise_weight_2", "bias_1", "bias_2", "bias"], gen)
+    with torch.no_grad():
+        Gs.const.copy_(torch.randn(Gs.const.shape, generator=gen))
+    torch.manual_seed(42)
+    Gm = sg1.Mapping(num_layers=12, mapping_layers=3, latent_size=64, dlatent_size=64, mapping_fmaps=64).eval()
+    Gm.buffer1 = torch.randn(12, 64, generator=gen) * 0.1
+    coefs = torch.ones(1, 12, 1)
+    coefs[:, :6] = 0.7
+    z = torch.randn(2, 64, generator=gen)
+    styles = Gm(z, coefs)
+    fx = {"config": cfg, "state_dict": clone_sd(Gs), "map_state_dict": clone_sd(Gm), "buffer1": Gm.buffer1.clone(),
+          "coefs": coefs, "z": z, "styles": styles.clone(), "images": {}}
+    for lod in (5, 3, 0):
+        torch.manual_seed(60 + lod)
+        fx["images"][lod] = Gs.forward(styles, lod).clone()
+    # per-block vectors (seed 9): block 0 (const, batch 1), a nearest-up block, the fused-scale block
+    x = Gs.const
+    blocks = {}
+    torch.manual_seed(9)
+    for i, blk in enumerate(Gs.decode_block):
+        y = blk(x, styles[:, 2 * i], styles[:, 2 * i + 1])
+        if i < 3:
+            blocks[i] = {"x": x.clone(), "y": y.clone()}
+        x = y
+    fx["blocks_seed9"] = blocks
+    # the fused-scale block alone on a small input (it only depends on the `fused_scale` flag, not the size)
+    xs = torch.randn(2, 32, 8, 8, generator=gen)
+    torch.manual_seed(10)
+    fx["fused_block_seed10"] = {"x": xs, "y": Gs.decode_block[5](xs, styles[:, 10], styles[:, 11]).clone()}
+    torch.save(fx, os.path.join(HERE, "sg1_l6.pt"))
+    print("sg1_l6.pt:", {k: tuple(v.shape) for k, v in fx["images"].items()}, [b.fused_scale for b in Gs.decode_block])
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "sg1":
+        import_reference()
+        stylegan1()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "pggan":
         import_reference()
         pggan()

@@ -176,3 +176,35 @@ def test_e_pg_oracle():
         assert rel(opg.e_pg_block(sd, f"decode_block.{i}.", b["x"]), b["y"]) < TOL, i
     torch.manual_seed(8)
     assert rel(opg.e_pg_features(sd, fx["img"], 4), fx["features_seed8"]) < TOL
+
+
+def test_sg1_oracle():
+    from oracle import stylegan1 as osg1
+    fx = torch.load(os.path.join(GOLD, "sg1_l6.pt"))
+    sd = fx["state_dict"]
+    styles = osg1.mapping(fx["map_state_dict"], fx["z"], 12, mapping_layers=3, buffer1=fx["buffer1"], coefs=fx["coefs"])
+    assert rel(styles, fx["styles"]) < TOL
+    for lod, img in fx["images"].items():
+        torch.manual_seed(60 + lod)
+        assert rel(osg1.decode(sd, fx["styles"], lod), img) < TOL, lod
+    torch.manual_seed(9)
+    x = sd["const"]
+    for i in range(6):
+        y = osg1.decode_block(sd, f"decode_block.{i}.", x, fx["styles"][:, 2 * i], fx["styles"][:, 2 * i + 1])
+        if i in fx["blocks_seed9"]:
+            assert rel(y, fx["blocks_seed9"][i]["y"]) < TOL, i
+        x = y
+
+
+def test_sg1_fused_scale_is_box_sum_of_plain_transposed_conv():
+    """The decomposition the CUDA path uses: conv_transpose2d(x, 4-shift-sum(W), stride 2, padding 1) equals the 2x2
+    box sum of the raw stride-2/padding-0 transposed conv with the 3x3 weights (lreq.py:127-140)."""
+    import torch.nn.functional as F
+    from oracle import stylegan1 as osg1
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 5, 6, 7, generator=g)
+    w = torch.randn(5, 4, 3, 3, generator=g)
+    ref = osg1.conv_transpose_fused(x, w)
+    raw = F.conv_transpose2d(x, w, stride=2, padding=0)            # (2H+1) x (2W+1)
+    box = raw[:, :, :-1, :-1] + raw[:, :, 1:, :-1] + raw[:, :, :-1, 1:] + raw[:, :, 1:, 1:]
+    assert rel(box, ref) < 1e-5
