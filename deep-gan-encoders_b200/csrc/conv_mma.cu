@@ -39,7 +39,7 @@ struct TapEntry {
   int16_t a_off;  // patch pixel offset dy*PW+dx of this tap
   int16_t w_tap;  // tap index into WPK
   int16_t phase;  // output phase (0 for stride-1 convs, 2*py+px for the transposed conv)
-  int16_t pad;
+  int16_t in_phase;  // -1: applies to every K chunk; else only to chunks of this input phase (space-to-depth conv)
 };
 
 struct ConvKParams {
@@ -47,13 +47,14 @@ struct ConvKParams {
   int dom_h, dom_w;        // tile domain (H,W) or (H+1,W+1) for the transposed conv
   int tiles_x, tiles_y;
   int Cin, Cout, P;
+  int cin_w;               // input channels per weight tap (== Cin, or Cin/4 for the space-to-depth stride-2 conv)
   int kc, nchunks;         // channels per A chunk, number of chunks
   int ntile, cw, nsub;     // CTA columns, columns per phase, columns per MMA
   int n_ntiles, np;        // N tiles, phases per CTA tile
   int planes;
   int total_tiles;
   int ntaps;
-  TapEntry taps[9];
+  TapEntry taps[16];
   int a_slot_bytes, b_slot_bytes, b_sub_bytes, b_slots;
   int a_slots, b_region_bytes, resident, acc_stages, b_rb;
   int tmem_cols;
@@ -418,11 +419,17 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // weights of every (chunk, tap) stay in smem for the whole kernel: one bulk load, one barrier
       if (elect_one_sync()) {
         mbar_arrive_expect_tx(&b_full[0], (uint32_t)p.b_region_bytes);
-        for (int ch = 0; ch < p.nchunks; ++ch)
-          for (int e = 0; e < p.ntaps; ++e)
+        int slot = 0;
+        for (int ch = 0; ch < p.nchunks; ++ch) {
+          const int cph = (ch * p.kc) / p.cin_w, cb = ch * kc8p - cph * (p.cin_w >> 3) * p.planes;
+          for (int e = 0; e < p.ntaps; ++e) {
+            if (p.taps[e].in_phase >= 0 && p.taps[e].in_phase != cph) continue;
             for (int s = 0; s < nsubs; ++s)
-              tma_load_4d(b_smem + (ch * p.ntaps + e) * p.b_slot_bytes + s * p.b_sub_bytes, &tmB, &b_full[0], 0,
-                          (s * p.nsub) / p.b_rb, ch * kc8p, p.taps[e].w_tap);
+              tma_load_4d(b_smem + slot * p.b_slot_bytes + s * p.b_sub_bytes, &tmB, &b_full[0], 0,
+                          (s * p.nsub) / p.b_rb, cb, p.taps[e].w_tap);
+            ++slot;
+          }
+        }
       }
       __syncwarp();
     }
@@ -438,15 +445,17 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         __syncwarp();
         if (++a_slot == (uint32_t)p.a_slots) { a_slot = 0; a_ph ^= 1; }
         if (p.resident) continue;
+        const int cph = (ch * p.kc) / p.cin_w, cb = ch * kc8p - cph * (p.cin_w >> 3) * p.planes;
         for (int e = 0; e < p.ntaps; ++e) {
           const int q = p.taps[e].phase - t.p0;
           if (q < 0 || q >= p.np) continue;
+          if (p.taps[e].in_phase >= 0 && p.taps[e].in_phase != cph) continue;
           mbar_wait(&b_empty[b_slot], b_ph ^ 1);
           if (elect_one_sync()) {
             mbar_arrive_expect_tx(&b_full[b_slot], (uint32_t)p.b_slot_bytes);
             uint8_t* dst = b_smem + b_slot * p.b_slot_bytes;
             for (int s = 0; s < nsubs; ++s)
-              tma_load_4d(dst + s * p.b_sub_bytes, &tmB, &b_full[b_slot], 0, (t.co0 + s * p.nsub) / p.b_rb, ch * kc8p,
+              tma_load_4d(dst + s * p.b_sub_bytes, &tmB, &b_full[b_slot], 0, (t.co0 + s * p.nsub) / p.b_rb, cb,
                           p.taps[e].w_tap);
           }
           __syncwarp();
@@ -479,15 +488,20 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tc_fence_after();
       const uint32_t d_base = tmem_base + acc * p.ntile;
       uint32_t started = 0;
+      uint32_t res16 = b_region16;   // resident mode: running slot address, same (chunk, tap) order as the loader
       for (int ch = 0; ch < p.nchunks; ++ch) {
         mbar_wait(&a_full[a_slot], a_ph);
         tc_fence_after();
         const uint32_t a_base16 = smem_u32(a_smem + a_slot * p.a_slot_bytes) >> 4;
+        const int cph = (ch * p.kc) / p.cin_w;
         if (p.resident) {
           // one straight run of MMAs per (tile, chunk): no per-tap barrier traffic
+          uint32_t nvalid = 0;
+          for (int e = 0; e < p.ntaps; ++e) nvalid += (p.taps[e].in_phase < 0 || p.taps[e].in_phase == cph) ? 1u : 0u;
           if (elect_one_sync()) {
-            uint32_t b16 = b_region16 + (uint32_t)(ch * p.ntaps) * b_slot16;
-            for (int e = 0; e < p.ntaps; ++e, b16 += b_slot16) {
+            uint32_t b16 = res16;
+            for (int e = 0; e < p.ntaps; ++e) {
+              if (p.taps[e].in_phase >= 0 && p.taps[e].in_phase != cph) continue;
               const int q = p.taps[e].phase;
               const uint64_t da = a_desc0 + (a_base16 + (uint32_t)p.taps[e].a_off);
               for (int s = 0; s < nsubs; ++s) {
@@ -500,15 +514,18 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                    a_kstep, b_kstep, a_lo16, b_lo16, acc_flag);
                 started |= 1u << (q * 2 + s);
               }
+              b16 += b_slot16;
             }
             tc_commit(&a_empty[a_slot]);
           }
           __syncwarp();
+          res16 += nvalid * b_slot16;
           started = 0xffu;  // (uniform copy of the elected lane's bookkeeping: every sub-accumulator is started)
         } else {
           for (int e = 0; e < p.ntaps; ++e) {
             const int q = p.taps[e].phase - t.p0;
             if (q < 0 || q >= p.np) continue;
+            if (p.taps[e].in_phase >= 0 && p.taps[e].in_phase != cph) continue;
             mbar_wait(&b_full[b_slot], b_ph);
             tc_fence_after();
             const uint32_t b_base16 = smem_u32(b_smem + b_slot * p.b_slot_bytes) >> 4;
@@ -620,7 +637,9 @@ __global__ void __launch_bounds__(128) conv_checker_kernel(const __grid_constant
           const int dy = p.taps[e].a_off / PW, dx = p.taps[e].a_off % PW;
           const int iy = px.y - 1 + dy, ix = px.x - 1 + dx;
           if (iy < 0 || iy >= p.H || ix < 0 || ix >= p.W) continue;
-          for (int g = 0; g < C8in; ++g) {
+          const int C8w = p.cin_w >> 3;
+          for (int gw = 0; gw < C8w; ++gw) {
+            const int g = p.taps[e].in_phase < 0 ? gw : p.taps[e].in_phase * C8w + gw;
             float ah[8], al[8];
             const uint4* xa = reinterpret_cast<const uint4*>(p.x);
             unpack8(__ldg(xa + act_idx16(px.n, g, 0, iy, ix, C8in, p.planes, p.H, p.W)), ah);
@@ -629,7 +648,7 @@ __global__ void __launch_bounds__(128) conv_checker_kernel(const __grid_constant
               const int co = t.co0 + c + j;
               const uint4* wb = reinterpret_cast<const uint4*>(p.wpk);
               // WPK [tap][Cin/8][planes][Cout][8]
-              const size_t wi = (((size_t)p.taps[e].w_tap * C8in + g) * p.planes) * p.Cout + co;
+              const size_t wi = (((size_t)p.taps[e].w_tap * C8w + gw) * p.planes) * p.Cout + co;
               float wh[8], wl[8];
               unpack8(__ldg(wb + wi), wh);
               float acc = v[j];
@@ -715,7 +734,7 @@ static int g_num_sms = 0;
 
 int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
   DGE_REQUIRE(a != nullptr, "conv: null args");
-  DGE_REQUIRE(a->kind >= 0 && a->kind <= 2, "conv: bad kind %d", a->kind);
+  DGE_REQUIRE(a->kind >= 0 && a->kind <= 3, "conv: bad kind %d", a->kind);
   DGE_REQUIRE(a->n > 0 && a->h > 0 && a->w > 0, "conv: bad dims n=%d h=%d w=%d", a->n, a->h, a->w);
   DGE_REQUIRE(a->cin >= 16 && a->cin % 16 == 0, "conv: cin=%d must be a positive multiple of 16", a->cin);
   DGE_REQUIRE(a->cout >= 16 && a->cout % 16 == 0, "conv: cout=%d must be a positive multiple of 16", a->cout);
@@ -734,7 +753,9 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
   ConvKParams p;
   memset(&p, 0, sizeof(p));
   p.N = a->n; p.H = a->h; p.W = a->w;
+  for (int i = 0; i < 16; ++i) p.taps[i].in_phase = -1;
   p.Cin = a->cin; p.Cout = a->cout;
+  p.cin_w = a->cin;
   p.planes = a->planes;
   p.P = up ? 4 : 1;
   p.dom_h = up ? a->h + 1 : a->h;
@@ -759,6 +780,21 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
     p.taps[0].a_off = (int16_t)(1 * PW + 1);
     p.taps[0].w_tap = 0;
     p.taps[0].phase = 0;
+  } else if (a->kind == DGE_CONV_DOWN4X4S2) {
+    // out[Y][X] = sum_{ky,kx<4} W4[ky][kx] * xin[2Y+ky-1][2X+kx-1]; xin is given space-to-depth: channel block
+    // ph = 2*(row parity)+(col parity) holds xin[2y+py][2x+px].  Row 2Y+ky-1 -> parity (ky+1)%2, offset floor((ky-1)/2).
+    DGE_REQUIRE(a->cin % 64 == 0, "conv: DOWN4X4S2 needs cin (=4*C) with C %% 16 == 0");
+    p.cin_w = a->cin / 4;
+    p.ntaps = 16;
+    static const int off[4] = {-1, 0, 0, 1};
+    for (int ky = 0; ky < 4; ++ky)
+      for (int kx = 0; kx < 4; ++kx) {
+        TapEntry& t = p.taps[ky * 4 + kx];
+        t.a_off = (int16_t)((1 + off[ky]) * PW + (1 + off[kx]));
+        t.w_tap = (int16_t)(ky * 4 + kx);
+        t.phase = 0;
+        t.in_phase = (int16_t)(2 * ((ky + 1) % 2) + ((kx + 1) % 2));
+      }
   } else {
     // t[2Y+ky'][2X+kx'] += x[Y - a][X - b] * Wf[ky][kx],  ky = ky' + 2a  (ky' = ky%2, a = ky/2)
     p.ntaps = 9;
@@ -798,13 +834,14 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
   // K chunking + shared-memory plan
   const int smem_cap = 224 * 1024;
   const int bar_bytes = (BAR_COUNT + 2) * 8;
-  const long long b_all = (long long)p.ntaps * (p.Cin / 8) * p.planes * p.cw * 16;   // every tap, every channel
+  const int taps_per_chunk = (a->kind == DGE_CONV_DOWN4X4S2) ? 4 : p.ntaps;
+  const long long b_all = (long long)taps_per_chunk * (p.Cin / 8) * p.planes * p.cw * 16;   // every (tap, channel) pair in use
   p.resident = 0;
   if (p.n_ntiles == 1) {
     // weights resident in smem for the whole kernel when they fit next to >= 2 patch slots
     const int kcs[3] = {64, 32, 16};
     for (int i = 0; i < 3 && !p.resident; ++i) {
-      const int kc = largest_div(p.Cin, kcs[i], 16);
+      const int kc = largest_div(p.cin_w, kcs[i], 16);
       const long long a_slot = (long long)(kc / 8) * p.planes * PATCH_BYTES;
       if (b_all + 2 * a_slot + bar_bytes <= smem_cap) {
         p.resident = 1;
@@ -812,7 +849,7 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
       }
     }
   }
-  if (!p.resident) p.kc = largest_div(p.Cin, p.cw > 128 ? 32 : 64, 16);
+  if (!p.resident) p.kc = largest_div(p.cin_w, p.cw > 128 ? 32 : 64, 16);
   p.nchunks = p.Cin / p.kc;
   p.a_slot_bytes = (p.kc / 8) * p.planes * PATCH_BYTES;
   p.b_sub_bytes = (p.kc / 8) * p.planes * p.nsub * 16;
@@ -879,8 +916,8 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
   {
     // WPK [taps][Cin/8][planes][Cout][8] viewed as uint64 [taps][c8p][Cout/rb][2*rb]: a box of (cw/rb) row blocks
     // lands in smem as [k-group][cw rows][16 B] -- the canonical K-major operand with SBO = 128 B.
-    const uint64_t c8p = (uint64_t)(p.Cin / 8) * p.planes;
-    const int wtaps = (a->kind == DGE_CONV_1X1) ? 1 : 9;
+    const uint64_t c8p = (uint64_t)(p.cin_w / 8) * p.planes;
+    const int wtaps = (a->kind == DGE_CONV_1X1) ? 1 : (a->kind == DGE_CONV_DOWN4X4S2 ? 16 : 9);
     const int rb = p.cw > 128 ? 128 : p.cw;
     uint64_t dims[4] = {(uint64_t)2 * rb, (uint64_t)(p.Cout / rb), c8p, (uint64_t)wtaps};
     uint64_t strides[3] = {(uint64_t)rb * 16, (uint64_t)p.Cout * 16, c8p * p.Cout * 16};

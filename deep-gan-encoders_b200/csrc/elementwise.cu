@@ -483,6 +483,44 @@ __device__ __forceinline__ void pooled8(const float* src, int n, int g, int y, i
   for (int k = 0; k < 8; ++k) s[k] *= 0.25f;
 }
 
+// instance norm + zero-padded 3x3 blur; optional space-to-depth output (E_Blur.py:69-72)
+__global__ void k_instance_norm_blur(const float* __restrict__ x, const float* __restrict__ mr, void* __restrict__ out,
+                                     int s2d, int n, int c, int h, int w, int planes) {
+  const int C8 = c >> 3;
+  const size_t total = (size_t)n * C8 * h * w;
+  const float bl[3] = {0.25f, 0.5f, 0.25f};
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const Idx4 q = decode4(i, C8, h, w);
+    float m[8], r[8], acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const size_t s = ((size_t)q.n * c + q.g * 8 + k) * 2;
+      m[k] = __ldg(mr + s);
+      r[k] = __ldg(mr + s + 1);
+      acc[k] = 0.f;
+    }
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int y = q.y + dy;
+      if (y < 0 || y >= h) continue;
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int xx = q.x + dx;
+        if (xx < 0 || xx >= w) continue;
+        float v[8];
+        load8_f32b(x, f32b_idx32(q.n, q.g, y, xx, C8, h, w), v);
+        const float wgt = bl[dy + 1] * bl[dx + 1];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(wgt, (v[k] - m[k]) * r[k], acc[k]);
+      }
+    }
+    if (s2d) {
+      const int ph = 2 * (q.y & 1) + (q.x & 1);
+      store8_act(out, q.n, ph * C8 + q.g, q.y >> 1, q.x >> 1, 4 * C8, planes, h >> 1, w >> 1, acc);
+    } else {
+      store8_act(out, q.n, q.g, q.y, q.x, C8, planes, h, w, acc);
+    }
+  }
+}
+
 // x: F32B at (2*ho, 2*wo) -> ACT at (ho, wo)
 __global__ void k_avgpool_to_act(const float* __restrict__ x, void* __restrict__ out, int n, int c, int ho, int wo,
                                  int planes) {
@@ -503,13 +541,8 @@ __global__ void k_blend(const float* __restrict__ a_src, const float* __restrict
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const Idx4 q = decode4(i, C8, ho, wo);
     float va[8], vb[8];
-    if (pool) {
-      pooled8(a_src, q.n, q.g, q.y, q.x, C8, ho, wo, va);
-      pooled8(b_src, q.n, q.g, q.y, q.x, C8, ho, wo, vb);
-    } else {
-      load8_f32b(a_src, i, va);
-      load8_f32b(b_src, i, vb);
-    }
+    if (pool & 1) pooled8(a_src, q.n, q.g, q.y, q.x, C8, ho, wo, va); else load8_f32b(a_src, i, va);
+    if (pool & 2) pooled8(b_src, q.n, q.g, q.y, q.x, C8, ho, wo, vb); else load8_f32b(b_src, i, vb);
 #pragma unroll
     for (int k = 0; k < 8; ++k) va[k] = a * va[k] + b * vb[k];
     store8_f32b(out, i, va);
@@ -893,7 +926,7 @@ int dge_pack_conv_weight(const float* w, void* wpk, int cout, int cin, int ksize
                          void* stream) {
   DGE_REQUIRE(w && wpk, "pack_conv_weight: null pointer");
   DGE_REQUIRE(cin % 16 == 0 && cout % 16 == 0 && cin > 0 && cout > 0, "pack_conv_weight: cin=%d cout=%d must be multiples of 16", cin, cout);
-  DGE_REQUIRE(ksize == 1 || ksize == 3, "pack_conv_weight: ksize=%d", ksize);
+  DGE_REQUIRE(ksize == 1 || ksize == 3 || ksize == 4, "pack_conv_weight: ksize=%d", ksize);
   DGE_REQUIRE(planes == 1 || planes == 2, "pack_conv_weight: planes=%d", planes);
   LAUNCH_1D(k_pack_conv_weight, (size_t)ksize * ksize * (cin / 8) * cout, stream, w, (uint4*)wpk, cout, cin, ksize,
             flip, scale, planes);
@@ -1032,6 +1065,15 @@ int dge_instance_norm_affine(const float* x, const float* mean_rstd, const float
   DGE_REQUIRE(!out_act || planes == 1 || planes == 2, "instance_norm_affine: planes=%d", planes);
   LAUNCH_1D(k_instance_norm, (size_t)n * (c / 8) * h * w, stream, x, mean_rstd, gamma, beta, out_act, out_f32b, n, c, h,
             w, planes);
+}
+
+int dge_instance_norm_blur(const float* x, const float* mean_rstd, void* out_act, int s2d, int n, int c, int h, int w,
+                           int planes, void* stream) {
+  DGE_REQUIRE(x && mean_rstd && out_act, "instance_norm_blur: null pointer");
+  REQ_NCHW("instance_norm_blur");
+  DGE_REQUIRE(planes == 1 || planes == 2, "instance_norm_blur: planes=%d", planes);
+  DGE_REQUIRE(!s2d || (h % 2 == 0 && w % 2 == 0), "instance_norm_blur: space-to-depth needs even h, w");
+  LAUNCH_1D(k_instance_norm_blur, (size_t)n * (c / 8) * h * w, stream, x, mean_rstd, out_act, s2d, n, c, h, w, planes);
 }
 
 int dge_avgpool_to_act(const float* x, void* out_act, int n, int c, int h, int w, int planes, void* stream) {

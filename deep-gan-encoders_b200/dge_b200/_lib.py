@@ -78,6 +78,7 @@ SIGNATURES = {
     "dge_sg1_post": (c_int, [P, c_int, P, P, P, c_float, P, c_int, c_int, c_int, c_int, P]),
     "dge_instance_norm_style": (c_int, [P, c_int, P, P, c_int, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "dge_to_rgb_f32b": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "dge_instance_norm_blur": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "dge_blend": (c_int, [P, P, P, c_float, c_float, c_int, c_int, c_int, c_int, c_int, P]),
 }
 

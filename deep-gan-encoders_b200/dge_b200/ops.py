@@ -10,7 +10,7 @@ import torch
 from . import _lib
 from ._lib import ConvArgs, DgeError, check
 
-CONV_3X3, CONV_1X1, CONV_UP3X3 = 0, 1, 2
+CONV_3X3, CONV_1X1, CONV_UP3X3, CONV_DOWN4X4S2 = 0, 1, 2, 3
 FLAG_CHECKER = 1
 
 _device_checked = False
@@ -270,7 +270,7 @@ def conv(x, wpk, cout, kind=CONV_3X3, *, demod=None, noise=None, noise_batched=F
             res["nchw"] = o
         if rgb_w is not None:
             a.rgb_w, a.rgb_out = ptr(rgb_w), ptr(rgb_out)
-    name = ("conv3x3", "conv1x1", "conv_up3x3")[kind]
+    name = ("conv3x3", "conv1x1", "conv_up3x3", "conv_down4x4s2")[kind]
     with _rec(name, (x.n, x.h, x.w, x.c, cout, x.planes)):
         check(lib().dge_conv_forward(ctypes.byref(a), _stream()))
     return res
@@ -414,9 +414,21 @@ def avgpool_to_act(x, planes=2):
     return out
 
 
+def instance_norm_blur(x, mean_rstd, s2d=False, planes=2):
+    """IN + 3x3 Blur -> ACT; s2d=True writes the space-to-depth operand of CONV_DOWN4X4S2 (4C channels, half size)."""
+    assert isinstance(x, F32B)
+    out = Act(x.n, 4 * x.c, x.h // 2, x.w // 2, planes, x.t.device) if s2d else Act(x.n, x.c, x.h, x.w, planes, x.t.device)
+    with _rec("instance_norm_blur", (x.n, x.h, x.w, x.c, int(s2d))):
+        check(lib().dge_instance_norm_blur(_p(x.t), _f32(mean_rstd), _p(out.t), int(s2d), x.n, x.c, x.h, x.w, planes,
+                                           _stream()))
+    return out
+
+
 def blend(a_src, b_src, a, b, pool):
+    """pool: False/0 none, True/3 both inputs are double resolution, 1 only a_src, 2 only b_src."""
     assert isinstance(a_src, F32B) and isinstance(b_src, F32B)
-    ho, wo = (a_src.h // 2, a_src.w // 2) if pool else (a_src.h, a_src.w)
+    pool = 3 if pool is True else int(pool)
+    ho, wo = (a_src.h // 2, a_src.w // 2) if (pool & 1) else (a_src.h, a_src.w)
     out = F32B(a_src.n, a_src.c, ho, wo, a_src.t.device)
     with _rec("blend", (a_src.n, ho, wo, a_src.c, int(pool))):
         check(lib().dge_blend(_p(a_src.t), _p(b_src.t), _p(out.t), float(a), float(b), int(pool), a_src.n, a_src.c, ho,

@@ -1,0 +1,136 @@
+"""B200-native case-2 encoder -- drop-in for the reference's `model/E/E_Blur.py` (BEBlock :14-85, BE :88-134), the
+encoder `embedding_img.py` uses.  Differences from `model/E/E.py`: a depthwise 3x3 `Blur` before `conv_2`, and for
+`resolution >= 128` (counter hard-wired to start at 1024, :99,105 -- so the first FOUR blocks regardless of the image
+size) `conv_2` is the stride-2 `transform_kernel` conv (4x4 effective) instead of conv + avg-pool.
+
+Kernels: the instance-norm apply, the blur and (for the strided blocks) a space-to-depth re-layout are ONE pass
+(`dge_instance_norm_blur`); the strided conv runs on the tensor cores as a 16-tap conv over the 4 input phases
+(`DGE_CONV_DOWN4X4S2`), exact at the borders (the blurred intermediate is zero-padded).
+"""
+import torch
+import torch.nn as nn
+
+import model.utils.lreq as ln
+from model.utils.net import FromRGB
+from model.stylegan1.net import Blur
+from dge_b200 import ops
+
+DEFAULT_PLANES = 2
+
+
+class BEBlock(nn.Module):
+    def __init__(self, inputs, outputs, latent_size, has_last_conv=True, fused_scale=True):
+        super().__init__()
+        self.has_last_conv = has_last_conv
+        self.noise_weight_1 = nn.Parameter(torch.zeros(1, inputs, 1, 1))
+        self.bias_1 = nn.Parameter(torch.zeros(1, inputs, 1, 1))
+        self.instance_norm_1 = nn.InstanceNorm2d(inputs, affine=False, eps=1e-8)
+        self.inver_mod1 = ln.Linear(2 * inputs, latent_size, gain=1)
+        self.conv_1 = ln.Conv2d(inputs, inputs, 3, 1, 1, bias=False)
+        self.noise_weight_2 = nn.Parameter(torch.zeros(1, outputs, 1, 1))
+        self.bias_2 = nn.Parameter(torch.zeros(1, outputs, 1, 1))
+        self.instance_norm_2 = nn.InstanceNorm2d(inputs, affine=False, eps=1e-8)
+        self.inver_mod2 = ln.Linear(2 * inputs, latent_size, gain=1)
+        self.blur = Blur(inputs)
+        if has_last_conv:
+            if fused_scale:
+                self.conv_2 = ln.Conv2d(inputs, outputs, 3, 2, 1, bias=False, transform_kernel=True)
+            else:
+                self.conv_2 = ln.Conv2d(inputs, outputs, 3, 1, 1, bias=False)
+        self.fused_scale = fused_scale
+        self.inputs = inputs
+        self.outputs = outputs
+        if self.inputs != self.outputs:
+            self.conv_3 = ln.Conv2d(inputs, outputs, 1, 1, 0)
+        self.planes = DEFAULT_PLANES
+        self.noise_mode = 'reference'
+
+    def _noise(self, n, h, w, device):
+        if self.noise_mode == 'device':
+            return torch.randn([n, 1, h, w], device=device)
+        return torch.randn([n, 1, h, w]).to(device)
+
+    def run(self, x):
+        n, c, h, w = x.n, x.c, x.h, x.w
+        dev = x.t.device
+        style1, mr1 = ops.instance_stats(x, self.instance_norm_1.eps)
+        w1 = ops.dense(style1, self.inver_mod1.weight, self.inver_mod1.bias)
+        xn, _ = ops.instance_norm(x, mr1, planes=self.planes)
+        y1 = ops.conv(xn, self.conv_1.packed(self.planes), c, ops.CONV_3X3, noise=self._noise(n, h, w, dev),
+                      noise_batched=True, noise_w=self.noise_weight_1.detach().view(-1),
+                      bias=self.bias_1.detach().view(-1), slope=0.2, out_f32b=True)['f32b']
+        style2, mr2 = ops.instance_stats(y1, self.instance_norm_2.eps)
+        w2 = ops.dense(style2, self.inver_mod2.weight, self.inver_mod2.bias)
+        nw2, b2 = self.noise_weight_2.detach().view(-1), self.bias_2.detach().view(-1)
+        if self.has_last_conv:
+            if self.fused_scale:
+                xb = ops.instance_norm_blur(y1, mr2, s2d=True, planes=self.planes)                    # :69-71
+                y2 = ops.conv(xb, self.conv_2.packed_down4(self.planes), self.outputs, ops.CONV_DOWN4X4S2,
+                              noise=self._noise(n, h // 2, w // 2, dev), noise_batched=True, noise_w=nw2, bias=b2,
+                              slope=0.2, out_f32b=True)['f32b']                                       # :72-75
+                y2_pool = False
+            else:
+                xb = ops.instance_norm_blur(y1, mr2, s2d=False, planes=self.planes)
+                y2 = ops.conv(xb, self.conv_2.packed(self.planes), self.outputs, ops.CONV_3X3,
+                              noise=self._noise(n, h, w, dev), noise_batched=True, noise_w=nw2, bias=b2, slope=0.2,
+                              out_f32b=True)['f32b']
+                y2_pool = True                                                                        # :76-77
+            if self.inputs != self.outputs:
+                rp = ops.avgpool_to_act(x, planes=self.planes)                                        # :78
+                out = ops.conv(rp, self.conv_3.packed(self.planes), self.outputs, ops.CONV_1X1,
+                               bias=self.conv_3.scaled_bias(), blend_src=y2, blend_pool=y2_pool, blend_a=0.111,
+                               blend_b=0.889, out_f32b=True)['f32b']                                  # :80-84
+            else:
+                out = ops.blend(y2, x, 0.111, 0.889, pool=3 if y2_pool else 2)
+        else:
+            _, y1n = ops.instance_norm(y1, mr2, out_act=False, out_f32b=True)
+            if self.inputs != self.outputs:
+                out = ops.conv(ops.f32b_to_act(x, self.planes), self.conv_3.packed(self.planes), self.outputs,
+                               ops.CONV_1X1, bias=self.conv_3.scaled_bias(), blend_src=y1n, blend_pool=False,
+                               blend_a=0.111, blend_b=0.889, out_f32b=True)['f32b']
+            else:
+                out = ops.blend(y1n, x, 0.111, 0.889, pool=False)
+        return out, w1, w2
+
+    def forward(self, x):
+        ln._guard('E_Blur.BEBlock', x, self.conv_1.weight)
+        out, w1, w2 = self.run(ops.nchw_to_f32b(x.float()))
+        return out.to_nchw(), w1, w2
+
+
+class BE(nn.Module):
+    def __init__(self, startf=16, maxf=512, layer_count=9, latent_size=512, channels=3):
+        super().__init__()
+        self.maxf = maxf
+        self.startf = startf
+        self.latent_size = latent_size
+        self.layer_to_resolution = [0 for _ in range(layer_count)]
+        self.decode_block = nn.ModuleList()
+        self.layer_count = layer_count
+        inputs = startf
+        outputs = startf * 2
+        resolution = 1024
+        self.FromRGB = FromRGB(channels, inputs)
+        for i in range(layer_count):
+            has_last_conv = i + 1 != layer_count
+            fused_scale = resolution >= 128
+            self.decode_block.append(BEBlock(inputs, outputs, latent_size, has_last_conv, fused_scale=fused_scale))
+            inputs = min(maxf, inputs * 2)
+            outputs = min(maxf, outputs * 2)
+            self.layer_to_resolution[i] = resolution
+            resolution /= 2
+
+    def set_noise_mode(self, mode):
+        assert mode in ('reference', 'device')
+        for b in self.decode_block:
+            b.noise_mode = mode
+
+    def forward(self, x, block_num=9):
+        ln._guard('E_Blur.BE', x, self.FromRGB.from_rgb.weight)
+        f = self.FromRGB.run(x)
+        w = torch.tensor(0)
+        for i in range(9 - block_num, self.layer_count):
+            f, w1, w2 = self.decode_block[i].run(f)
+            w_ = torch.cat((w2.view(f.n, 1, 512), w1.view(f.n, 1, 512)), dim=1)
+            w = w_ if i == (9 - block_num) else torch.cat((w_, w), dim=1)
+        return f.to_nchw(), w

@@ -49,8 +49,12 @@ void dge_launch_count_reset(void);
 enum {
   DGE_CONV_3X3 = 0,    /* 3x3, stride 1, pad 1  (stylegan2_generator.py:897-904; E.py:59,72; lreq.py:126-156) */
   DGE_CONV_1X1 = 1,    /* 1x1                  (E.py:81-82 conv_3; net.py:231-240 FromRGB when Cin%16==0) */
-  DGE_CONV_UP3X3 = 2   /* 3x3 transposed, stride 2, pad 0 -> raw (2H+1)x(2W+1) map, before the FIR
+  DGE_CONV_UP3X3 = 2,  /* 3x3 transposed, stride 2, pad 0 -> raw (2H+1)x(2W+1) map, before the FIR
                           (stylegan2_generator.py:879-895) */
+  DGE_CONV_DOWN4X4S2 = 3 /* 4x4, stride 2, pad 1 (the `transform_kernel` strided conv of model/E/E_Blur.py:32-33,72;
+                            lreq.py:144-156).  x is the SPACE-TO-DEPTH input: ACT [n][4*C/8][planes][h][w][8] at the
+                            OUTPUT resolution, channel block 2*py+px holding xin[2y+py][2x+px]
+                            (dge_instance_norm_blur writes it); cin = 4*C; wpk has 16 taps of C channels. */
 };
 enum {
   DGE_CONV_FLAG_CHECKER = 1  /* run the slow CUDA-core checker kernel instead of tcgen05 (tests only) */
@@ -156,9 +160,14 @@ int dge_instance_norm(const float* x_f32b, const float* mean_rstd, void* out_act
 /* as dge_instance_norm with the affine InstanceNorm2d(affine=True) weight/bias (E_PG.py:59,99): gamma/beta [c] or NULL */
 int dge_instance_norm_affine(const float* x_f32b, const float* mean_rstd, const float* gamma, const float* beta,
                              void* out_act, float* out_f32b, int n, int c, int h, int w, int planes, void* stream);
+/* instance norm, then the depthwise 3x3 Blur ([1,2,1]^2/16, zero padding) of model/E/E_Blur.py:71 -> ACT.
+   s2d = 0: ACT [n][c/8][planes][h][w][8];  s2d = 1: space-to-depth ACT [n][4c/8][planes][h/2][w/2][8] for DGE_CONV_DOWN4X4S2 */
+int dge_instance_norm_blur(const float* x_f32b, const float* mean_rstd, void* out_act, int s2d, int n, int c, int h,
+                           int w, int planes, void* stream);
 /* 2x2 average pool F32B -> ACT (residual branch, E.py:78) */
 int dge_avgpool_to_act(const float* x_f32b, void* out_act, int n, int c, int h, int w, int planes, void* stream);
-/* out = a*A' + b*B' where X' = 2x2 mean if pool else X; all F32B (E.py:76-84 when Cin==Cout) */
+/* out = a*A' + b*B' where X' = 2x2 mean of a double-resolution tensor if its pool bit is set (bit 0: A, bit 1: B),
+   else X; all F32B (E.py:76-84 when Cin==Cout: pool = 3; E_Blur.py fused blocks: pool = 2) */
 int dge_blend(const float* a_src, const float* b_src, float* out, float a, float b, int pool, int n, int c,
               int h_out, int w_out, void* stream);
 

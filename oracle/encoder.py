@@ -60,3 +60,57 @@ def be_forward(sd, x, layer_count, block_num=9, noise_fn=_default_noise):
         w_ = torch.cat((w2.view(x.shape[0], 1, -1), w1.view(x.shape[0], 1, -1)), dim=1)
         w = w_ if w is None else torch.cat((w_, w), dim=1)
     return x, w
+
+
+def blur3x3(x):
+    """Blur.forward, model/utils/net.py:45-55."""
+    c = x.shape[1]
+    f = torch.tensor([1.0, 2.0, 1.0])
+    k = f[:, None] * f[None, :]
+    k = (k / k.sum()).view(1, 1, 3, 3).repeat(c, 1, 1, 1)
+    return F.conv2d(x, k, groups=c, padding=1)
+
+
+def strided_transform_conv(x, w):
+    """ln.Conv2d(3, stride 2, pad 1, transform_kernel=True).forward, model/utils/lreq.py:144-156 (implicit lreq)."""
+    w = F.pad(w, (1, 1, 1, 1))
+    w = (w[:, :, 1:, 1:] + w[:, :, :-1, 1:] + w[:, :, 1:, :-1] + w[:, :, :-1, :-1]) * 0.25
+    return F.conv2d(x, w, stride=2, padding=1)
+
+
+def be_blur_block(sd, prefix, x, fused_scale, noise_fn=_default_noise):
+    """E_Blur.BEBlock.forward, model/E/E_Blur.py:50-85."""
+    has_last_conv = (prefix + "conv_2.weight") in sd
+    w1 = F.linear(_stats(x), sd[prefix + "inver_mod1.weight"], sd[prefix + "inver_mod1.bias"])
+    residual = x
+    x = F.instance_norm(x, eps=1e-8)
+    x = F.conv2d(x, sd[prefix + "conv_1.weight"], padding=1)
+    x = torch.addcmul(x, sd[prefix + "noise_weight_1"], noise_fn([x.shape[0], 1, x.shape[2], x.shape[3]]).to(x))
+    x = F.leaky_relu(x + sd[prefix + "bias_1"], 0.2)
+    w2 = F.linear(_stats(x), sd[prefix + "inver_mod2.weight"], sd[prefix + "inver_mod2.bias"])
+    x = F.instance_norm(x, eps=1e-8)
+    if has_last_conv:
+        x = blur3x3(x)                                                                                # :71
+        if fused_scale:
+            x = strided_transform_conv(x, sd[prefix + "conv_2.weight"])                               # :72
+        else:
+            x = F.conv2d(x, sd[prefix + "conv_2.weight"], padding=1)
+        x = torch.addcmul(x, sd[prefix + "noise_weight_2"], noise_fn([x.shape[0], 1, x.shape[2], x.shape[3]]).to(x))
+        x = F.leaky_relu(x + sd[prefix + "bias_2"], 0.2)
+        if not fused_scale:
+            x = F.avg_pool2d(x, 2, 2)
+        residual = F.avg_pool2d(residual, 2, 2)
+    if (prefix + "conv_3.weight") in sd:
+        residual = F.conv2d(residual, sd[prefix + "conv_3.weight"], sd[prefix + "conv_3.bias"])
+    return 0.111 * x + 0.889 * residual, w1, w2
+
+
+def be_blur_forward(sd, x, layer_count, noise_fn=_default_noise):
+    """E_Blur.BE.forward, model/E/E_Blur.py:120-134; fused_scale = (1024 / 2^i >= 128), i.e. blocks 0..3 (:99,105)."""
+    x = from_rgb(sd, x)
+    w = None
+    for i in range(layer_count):
+        x, w1, w2 = be_blur_block(sd, f"decode_block.{i}.", x, 1024 / 2 ** i >= 128, noise_fn)
+        w_ = torch.cat((w2.view(x.shape[0], 1, -1), w1.view(x.shape[0], 1, -1)), dim=1)
+        w = w_ if w is None else torch.cat((w_, w), dim=1)
+    return x, w

@@ -259,7 +259,37 @@ def stylegan1():
     print("sg1_l6.pt:", {k: tuple(v.shape) for k, v in fx["images"].items()}, [b.fused_scale for b in Gs.decode_block])
 
 
+def e_blur():
+    import model.E.E_Blur as EB
+    torch.set_grad_enabled(False)
+    gen = torch.Generator().manual_seed(2323)
+    torch.manual_seed(51)
+    # 6 blocks on 128x128 images: blocks 0..3 use the strided transform-kernel conv, block 4 blur+conv+pool, block 5 last
+    cfg = dict(startf=16, maxf=32, layer_count=6, latent_size=512, channels=3)
+    E = EB.BE(**cfg).eval()
+    perturb(E, ["noise_weight_1", "noise_weight_2", "bias_1", "bias_2", "bias"], gen)
+    img = torch.randn(2, 3, 128, 128, generator=gen)
+    torch.manual_seed(70)
+    const, w = E(img)
+    fx = {"config": cfg, "state_dict": clone_sd(E), "img_seed": 2323, "img": img, "noise_seed": 70, "const": const,
+          "w": w, "fused": [b.fused_scale for b in E.decode_block]}
+    xs = torch.randn(2, 16, 12, 20, generator=gen)      # ragged size through one strided block
+    torch.manual_seed(71)
+    y, w1, w2 = E.decode_block[0](xs)
+    fx["block0_seed71"] = {"x": xs, "y": y.clone(), "w1": w1.clone(), "w2": w2.clone()}
+    xs4 = torch.randn(2, 32, 8, 8, generator=gen)
+    torch.manual_seed(72)
+    y, w1, w2 = E.decode_block[4](xs4)
+    fx["block4_seed72"] = {"x": xs4, "y": y.clone(), "w1": w1.clone(), "w2": w2.clone()}
+    torch.save(fx, os.path.join(HERE, "e_blur_s16_l6.pt"))
+    print("e_blur_s16_l6.pt: const", tuple(const.shape), "w", tuple(w.shape), fx["fused"])
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "eblur":
+        import_reference()
+        e_blur()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "sg1":
         import_reference()
         stylegan1()

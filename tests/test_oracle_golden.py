@@ -208,3 +208,19 @@ def test_sg1_fused_scale_is_box_sum_of_plain_transposed_conv():
     raw = F.conv_transpose2d(x, w, stride=2, padding=0)            # (2H+1) x (2W+1)
     box = raw[:, :, :-1, :-1] + raw[:, :, 1:, :-1] + raw[:, :, :-1, 1:] + raw[:, :, 1:, 1:]
     assert rel(box, ref) < 1e-5
+
+
+def test_e_blur_oracle():
+    fx = torch.load(os.path.join(GOLD, "e_blur_s16_l6.pt"))
+    sd = fx["state_dict"]
+    torch.manual_seed(fx["noise_seed"])
+    const, w = oenc.be_blur_forward(sd, fx["img"], 6)
+    assert rel(const, fx["const"]) < TOL and rel(w, fx["w"]) < TOL
+    b = fx["block0_seed71"]
+    torch.manual_seed(71)
+    y, w1, w2 = oenc.be_blur_block(sd, "decode_block.0.", b["x"], True)
+    assert rel(y, b["y"]) < TOL and rel(w1, b["w1"]) < TOL and rel(w2, b["w2"]) < TOL
+    b = fx["block4_seed72"]
+    torch.manual_seed(72)
+    y, w1, w2 = oenc.be_blur_block(sd, "decode_block.4.", b["x"], False)
+    assert rel(y, b["y"]) < TOL and rel(w1, b["w1"]) < TOL and rel(w2, b["w2"]) < TOL
