@@ -67,6 +67,7 @@ struct ConvKParams {
   const float* bias;
   float slope, gain;
   const float* preact_add;
+  int preact_c, preact_up;
   const float* blend_src;
   int blend_pool;
   float blend_a, blend_b;
@@ -241,7 +242,9 @@ __device__ __forceinline__ void epi_pointwise16(const ConvKParams& p, const Pixe
     float r[8];
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
-      load8_f32b(p.preact_add, f32b_idx32(px.n, (c0 >> 3) + g, px.y, px.x, C8, H, W), r);
+      // residual may have more channels than the output (BigGAN channel drop) and half its resolution (nearest x2)
+      load8_f32b(p.preact_add, f32b_idx32(px.n, (c0 >> 3) + g, px.y / p.preact_up, px.x / p.preact_up, p.preact_c >> 3,
+                                          H / p.preact_up, W / p.preact_up), r);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[8 * g + j] += r[j];
     }
@@ -748,6 +751,9 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
     DGE_REQUIRE(!a->out_act || a->out_planes == 1 || a->out_planes == 2, "conv: out_planes=%d", a->out_planes);
     DGE_REQUIRE(!a->rgb_w == !a->rgb_out, "conv: rgb_w and rgb_out must be given together");
     DGE_REQUIRE(!a->noise_w || a->noise, "conv: noise_w without noise");
+    DGE_REQUIRE(!a->preact_add || ((a->preact_c == 0 || (a->preact_c >= a->cout && a->preact_c % 8 == 0)) &&
+                                   (a->preact_up != 2 || (a->h % 2 == 0 && a->w % 2 == 0))),
+                "conv: bad preact residual shape (preact_c=%d preact_up=%d)", a->preact_c, a->preact_up);
   }
 
   ConvKParams p;
@@ -881,6 +887,8 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
   p.demod = a->demod; p.noise = a->noise; p.noise_bstride = a->noise_bstride; p.noise_w = a->noise_w;
   p.noise_scalar = a->noise_scalar; p.bias = a->bias; p.slope = a->slope; p.gain = a->gain;
   p.preact_add = a->preact_add;
+  p.preact_c = a->preact_c > 0 ? a->preact_c : a->cout;
+  p.preact_up = a->preact_up == 2 ? 2 : 1;
   p.blend_src = a->blend_src; p.blend_pool = a->blend_pool; p.blend_a = a->blend_a; p.blend_b = a->blend_b;
   p.out_act = a->out_act; p.out_planes = a->out_planes; p.out_scale = a->out_scale; p.out_f32b = a->out_f32b;
   p.out_nchw = a->out_nchw; p.rgb_w = a->rgb_w; p.rgb_out = a->rgb_out; p.out_raw_up = a->out_raw_up;

@@ -667,6 +667,109 @@ __global__ void k_to_rgb_f32b(const float* __restrict__ x, const float* __restri
 }
 
 // ---------------------------------------------------------------------------------------------
+// BigGAN pieces
+// ---------------------------------------------------------------------------------------------
+__global__ void k_cbn_coeffs(const float* __restrict__ scale, const float* __restrict__ offset,
+                             const float* __restrict__ weight, const float* __restrict__ bias,
+                             const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                             float* __restrict__ a_out, float* __restrict__ b_out, int n, int c) {
+  const int total = n * c;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ch = i % c;
+    const float inv = 1.f / sqrtf(var[ch] + eps);
+    const float w = scale ? 1.f + scale[i] : weight[ch];
+    const float o = offset ? offset[i] : bias[ch];
+    const float a = w * inv;
+    a_out[i] = a;
+    b_out[i] = o - mean[ch] * a;
+  }
+}
+
+__global__ void k_affine_act(const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b,
+                             int relu, int up, void* __restrict__ out_act, float* __restrict__ out_f32b, int n, int c,
+                             int h, int w, int planes) {
+  const int C8 = c >> 3;
+  const size_t total = (size_t)n * C8 * h * w;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const Idx4 q = decode4(i, C8, h, w);
+    float v[8];
+    load8_f32b(x, i, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const size_t s = (size_t)q.n * c + q.g * 8 + k;
+      float t = fmaf(v[k], __ldg(a + s), __ldg(b + s));
+      v[k] = (relu && t < 0.f) ? 0.f : t;
+    }
+    for (int dy = 0; dy < up; ++dy)
+      for (int dx = 0; dx < up; ++dx) {
+        if (out_f32b) store8_f32b(out_f32b, f32b_idx32(q.n, q.g, q.y * up + dy, q.x * up + dx, C8, h * up, w * up), v);
+        if (out_act) store8_act(out_act, q.n, q.g, q.y * up + dy, q.x * up + dx, C8, planes, h * up, w * up, v);
+      }
+  }
+}
+
+__global__ void k_maxpool2_f32b(const float* __restrict__ x, float* __restrict__ out, int n, int c, int ho, int wo) {
+  const int C8 = c >> 3;
+  const size_t total = (size_t)n * C8 * ho * wo;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const Idx4 q = decode4(i, C8, ho, wo);
+    float m[8], t[8];
+    load8_f32b(x, f32b_idx32(q.n, q.g, 2 * q.y, 2 * q.x, C8, 2 * ho, 2 * wo), m);
+#pragma unroll
+    for (int d = 1; d < 4; ++d) {
+      load8_f32b(x, f32b_idx32(q.n, q.g, 2 * q.y + (d >> 1), 2 * q.x + (d & 1), C8, 2 * ho, 2 * wo), t);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], t[k]);
+    }
+    store8_f32b(out, i, m);
+  }
+}
+
+// one thread per pixel; three passes over the channel groups (max, sum, write) -- the re-reads hit L1/L2
+__global__ void k_channel_softmax_to_act(const float* __restrict__ x, void* __restrict__ out, int n, int c, int h, int w,
+                                         int planes) {
+  const int C8 = c >> 3;
+  const size_t total = (size_t)n * h * w;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int xx = (int)(i % w);
+    const int y = (int)((i / w) % h);
+    const int b = (int)(i / ((size_t)w * h));
+    float mx = -INFINITY;
+    for (int g = 0; g < C8; ++g) {
+      float v[8];
+      load8_f32b(x, f32b_idx32(b, g, y, xx, C8, h, w), v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) mx = fmaxf(mx, v[k]);
+    }
+    float sum = 0.f;
+    for (int g = 0; g < C8; ++g) {
+      float v[8];
+      load8_f32b(x, f32b_idx32(b, g, y, xx, C8, h, w), v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sum += expf(v[k] - mx);
+    }
+    const float inv = 1.f / sum;
+    for (int g = 0; g < C8; ++g) {
+      float v[8];
+      load8_f32b(x, f32b_idx32(b, g, y, xx, C8, h, w), v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = expf(v[k] - mx) * inv;
+      store8_act(out, b, g, y, xx, C8, planes, h, w, v);
+    }
+  }
+}
+
+__global__ void k_tanh_slice_nchw(const float* __restrict__ x, float* __restrict__ out, int n, int c, int nch, int hw) {
+  const size_t total = (size_t)n * nch * hw;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t pix = i % hw;
+    const int ch = (int)((i / hw) % nch);
+    const size_t b = i / ((size_t)hw * nch);
+    out[i] = tanhf(x[(b * c + ch) * hw + pix]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // PGGAN: pixel-norm over channels (one thread per pixel; the second pass over the channel groups hits L1/L2)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float pixel_rnorm(const float* x, int n, int y, int xx, int C8, int h, int w, float eps) {
@@ -1089,6 +1192,34 @@ int dge_blend(const float* a_src, const float* b_src, float* out, float a, float
   DGE_REQUIRE(a_src && b_src && out, "blend: null pointer");
   DGE_REQUIRE(n > 0 && c > 0 && c % 8 == 0 && h_out > 0 && w_out > 0, "blend: bad dims");
   LAUNCH_1D(k_blend, (size_t)n * (c / 8) * h_out * w_out, stream, a_src, b_src, out, a, b, pool, n, c, h_out, w_out);
+}
+
+int dge_cbn_coeffs(const float* scale, const float* offset, const float* weight, const float* bias, const float* mean,
+                   const float* var, float eps, float* a_out, float* b_out, int n, int c, void* stream) {
+  DGE_REQUIRE(mean && var && a_out && b_out && n > 0 && c > 0, "cbn_coeffs: bad args");
+  DGE_REQUIRE((scale && offset) || (weight && bias), "cbn_coeffs: need (scale, offset) or (weight, bias)");
+  LAUNCH_1D(k_cbn_coeffs, (size_t)n * c, stream, scale, offset, weight, bias, mean, var, eps, a_out, b_out, n, c);
+}
+int dge_affine_act(const float* x, const float* a, const float* b, int relu, int up, void* out_act, float* out_f32b,
+                   int n, int c, int h, int w, int planes, void* stream) {
+  DGE_REQUIRE(x && a && b && (out_act || out_f32b), "affine_act: null pointer");
+  REQ_NCHW("affine_act");
+  DGE_REQUIRE((up == 1 || up == 2) && (!out_act || planes == 1 || planes == 2), "affine_act: up=%d planes=%d", up, planes);
+  LAUNCH_1D(k_affine_act, (size_t)n * (c / 8) * h * w, stream, x, a, b, relu, up, out_act, out_f32b, n, c, h, w, planes);
+}
+int dge_maxpool2_f32b(const float* x, float* out, int n, int c, int h_out, int w_out, void* stream) {
+  DGE_REQUIRE(x && out && n > 0 && c > 0 && c % 8 == 0 && h_out > 0 && w_out > 0, "maxpool2_f32b: bad args");
+  LAUNCH_1D(k_maxpool2_f32b, (size_t)n * (c / 8) * h_out * w_out, stream, x, out, n, c, h_out, w_out);
+}
+int dge_channel_softmax_to_act(const float* x, void* out_act, int n, int c, int h, int w, int planes, void* stream) {
+  DGE_REQUIRE(x && out_act, "channel_softmax_to_act: null pointer");
+  REQ_NCHW("channel_softmax_to_act");
+  DGE_REQUIRE(planes == 1 || planes == 2, "channel_softmax_to_act: planes=%d", planes);
+  LAUNCH_1D(k_channel_softmax_to_act, (size_t)n * h * w, stream, x, out_act, n, c, h, w, planes);
+}
+int dge_tanh_slice_nchw(const float* x, float* out, int n, int c, int nch, int hw, void* stream) {
+  DGE_REQUIRE(x && out && n > 0 && c >= nch && nch > 0 && hw > 0, "tanh_slice_nchw: bad args");
+  LAUNCH_1D(k_tanh_slice_nchw, (size_t)n * nch * hw, stream, x, out, n, c, nch, hw);
 }
 
 int dge_sg1_post(const float* src, int mode, const float* noise, const float* noise_w, const float* bias, float slope,

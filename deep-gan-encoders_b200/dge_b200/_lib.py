@@ -34,6 +34,7 @@ class ConvArgs(Structure):
         ("rgb_w", c_void_p), ("rgb_out", c_void_p),
         ("out_raw_up", c_void_p),
         ("preact_add", c_void_p),
+        ("preact_c", c_int32), ("preact_up", c_int32),
     ]
 
 
@@ -79,6 +80,11 @@ SIGNATURES = {
     "dge_instance_norm_style": (c_int, [P, c_int, P, P, c_int, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "dge_to_rgb_f32b": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "dge_instance_norm_blur": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "dge_cbn_coeffs": (c_int, [P, P, P, P, P, P, c_float, P, P, c_int, c_int, P]),
+    "dge_affine_act": (c_int, [P, P, P, c_int, c_int, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "dge_maxpool2_f32b": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
+    "dge_channel_softmax_to_act": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "dge_tanh_slice_nchw": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     "dge_blend": (c_int, [P, P, P, c_float, c_float, c_int, c_int, c_int, c_int, c_int, P]),
 }
 

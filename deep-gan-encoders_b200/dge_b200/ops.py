@@ -219,8 +219,8 @@ def pixel_norm(x, eps=1e-8):
 # ------------------------------------------------------------------------------------------------
 def conv(x, wpk, cout, kind=CONV_3X3, *, demod=None, noise=None, noise_batched=False, noise_w=None,
          noise_scalar=0.0, bias=None, slope=1.0, gain=1.0, blend_src=None, blend_pool=False, blend_a=0.0,
-         blend_b=1.0, preact_add=None, out_act=False, out_planes=None, out_scale=None, out_f32b=False, out_nchw=False, rgb_w=None,
-         rgb_out=None, checker=False):
+         blend_b=1.0, preact_add=None, preact_up=1, out_act=False, out_planes=None, out_scale=None, out_f32b=False,
+         out_f32b_into=None, out_nchw=False, rgb_w=None, rgb_out=None, checker=False):
     """tcgen05 implicit-GEMM conv with fused epilogue (dge_conv_forward). Returns a dict of outputs."""
     assert isinstance(x, Act)
     dev = x.t.device
@@ -252,6 +252,8 @@ def conv(x, wpk, cout, kind=CONV_3X3, *, demod=None, noise=None, noise_batched=F
         a.slope, a.gain = float(slope), float(gain)
         if preact_add is not None:
             a.preact_add = ptr(preact_add.t if isinstance(preact_add, F32B) else preact_add)
+            a.preact_c = preact_add.c if isinstance(preact_add, F32B) else 0
+            a.preact_up = int(preact_up)
         if blend_src is not None:
             a.blend_src = ptr(blend_src.t if isinstance(blend_src, F32B) else blend_src)
             a.blend_pool, a.blend_a, a.blend_b = int(blend_pool), float(blend_a), float(blend_b)
@@ -264,6 +266,9 @@ def conv(x, wpk, cout, kind=CONV_3X3, *, demod=None, noise=None, noise_batched=F
             o = F32B(x.n, cout, x.h, x.w, dev)
             a.out_f32b = ptr(o.t)
             res["f32b"] = o
+        if out_f32b_into is not None:        # write into a caller-provided F32B slice (e.g. one sample of a batch)
+            assert out_f32b_into.numel() == x.n * cout * x.h * x.w and out_f32b_into.dtype == torch.float32
+            a.out_f32b = ptr(out_f32b_into)
         if out_nchw:
             o = torch.empty((x.n, cout, x.h, x.w), dtype=torch.float32, device=dev)
             a.out_nchw = ptr(o)
@@ -370,6 +375,50 @@ def to_rgb_f32b(x, w, bias):
     out = torch.empty((x.n, w2.shape[0], x.h, x.w), dtype=torch.float32, device=x.t.device)
     bb = None if bias is None else bias.detach().contiguous()
     check(lib().dge_to_rgb_f32b(_p(x.t), _f32(w2), _f32(bb), _p(out), x.n, x.c, w2.shape[0], x.h, x.w, _stream()))
+    return out
+
+
+def cbn_coeffs(mean, var, eps, n, scale=None, offset=None, weight=None, bias=None):
+    c = mean.numel()
+    dev = mean.device
+    a = torch.empty((n, c), dtype=torch.float32, device=dev)
+    b = torch.empty((n, c), dtype=torch.float32, device=dev)
+    cg = lambda t: None if t is None else t.detach().contiguous()
+    check(lib().dge_cbn_coeffs(_f32(cg(scale)), _f32(cg(offset)), _f32(cg(weight)), _f32(cg(bias)), _f32(cg(mean)),
+                               _f32(cg(var)), float(eps), _p(a), _p(b), n, c, _stream()))
+    return a, b
+
+
+def affine_act(x, a, b, relu=False, up=1, planes=2, out_act=True, out_f32b=False):
+    assert isinstance(x, F32B)
+    dev = x.t.device
+    act = Act(x.n, x.c, x.h * up, x.w * up, planes, dev) if out_act else None
+    f = F32B(x.n, x.c, x.h * up, x.w * up, dev) if out_f32b else None
+    with _rec("affine_act", (x.n, x.h, x.w, x.c, up)):
+        check(lib().dge_affine_act(_p(x.t), _f32(a), _f32(b), int(relu), up, _p(act.t) if act else None,
+                                   _p(f.t) if f else None, x.n, x.c, x.h, x.w, planes, _stream()))
+    return act, f
+
+
+def maxpool2(x):
+    assert isinstance(x, F32B)
+    out = F32B(x.n, x.c, x.h // 2, x.w // 2, x.t.device)
+    check(lib().dge_maxpool2_f32b(_p(x.t), _p(out.t), x.n, x.c, x.h // 2, x.w // 2, _stream()))
+    return out
+
+
+def channel_softmax_to_act(x, planes=2):
+    assert isinstance(x, F32B)
+    out = Act(x.n, x.c, x.h, x.w, planes, x.t.device)
+    check(lib().dge_channel_softmax_to_act(_p(x.t), _p(out.t), x.n, x.c, x.h, x.w, planes, _stream()))
+    return out
+
+
+def tanh_slice_nchw(x, nch):
+    x = x.contiguous()
+    n, c, h, w = x.shape
+    out = torch.empty((n, nch, h, w), dtype=torch.float32, device=x.device)
+    check(lib().dge_tanh_slice_nchw(_f32(x), _p(out), n, c, nch, h * w, _stream()))
     return out
 
 

@@ -96,7 +96,10 @@ typedef struct dge_conv_args {
   float* rgb_out;          /* NCHW [n][3][h][w]; contributions are atomically ADDED (pre-initialise with
                               dge_rgb_init) -- stylegan2_generator.py:515-522 */
   float* out_raw_up;       /* DGE_CONV_UP3X3 only: F32B-like [n][cout/8][2h+1][2w+1][8] raw transposed conv */
-  const float* preact_add; /* F32B [n][cout/8][h][w][8] or NULL */
+  const float* preact_add; /* F32B [n][preact_c/8][h/preact_up][w/preact_up][8] or NULL */
+  int32_t preact_c;        /* channels of the residual tensor (0 = cout); only the first cout are used (BigGAN
+                              GenBlock channel drop, biggan_generator.py:195-197) */
+  int32_t preact_up;       /* 2 = the residual is half resolution, read with nearest x2 (:198-199); else 1 */
 } dge_conv_args;
 
 int dge_conv_forward(const dge_conv_args* a, void* stream);
@@ -187,6 +190,21 @@ int dge_instance_norm_style(const float* x_f32b, int in_n, const float* mean_rst
 /* ToRGB: 1x1 conv F32B -> NCHW [n][nch][h][w]  (:244-253) */
 int dge_to_rgb_f32b(const float* x_f32b, const float* w, const float* bias, float* out_nchw, int n, int c, int nch,
                     int h, int wd, void* stream);
+
+/* ---- BigGAN pieces (model/biggan_generator.py:58-150, 175-256; model/E/E_BIG.py:33-82) ------------------ */
+/* conditional-BN coefficients: A[n][c] = (1+scale[n][c])*rsqrt(var[c]+eps), B[n][c] = offset[n][c] - mean[c]*A[n][c]
+   (:143-148).  scale/offset NULL => plain BN with weight/bias [c] (:150): A = weight*rsqrt(var+eps), B = bias - mean*A. */
+int dge_cbn_coeffs(const float* scale, const float* offset, const float* weight, const float* bias, const float* mean,
+                   const float* var, float eps, float* a_out, float* b_out, int n, int c, void* stream);
+/* y = act(x*A[n][c] + B[n][c]), act = relu if relu != 0; optional nearest x2; F32B -> ACT and/or F32B (:178-190) */
+int dge_affine_act(const float* x_f32b, const float* a, const float* b, int relu, int up, void* out_act,
+                   float* out_f32b, int n, int c, int h, int w, int planes, void* stream);
+/* nn.MaxPool2d(2, 2) on F32B (SelfAttn, :82,91) */
+int dge_maxpool2_f32b(const float* x, float* out, int n, int c, int h_out, int w_out, void* stream);
+/* softmax over the CHANNEL axis of an F32B tensor -> ACT (attention rows: channels = keys, :85-86) */
+int dge_channel_softmax_to_act(const float* x_f32b, void* out_act, int n, int c, int h, int w, int planes, void* stream);
+/* out[n][0:nch] = tanh(x[n][0:nch]) from NCHW [n][c][h][w] (:250-253) */
+int dge_tanh_slice_nchw(const float* x, float* out, int n, int c, int nch, int hw, void* stream);
 
 /* ---- PGGAN pieces (model/pggan/pggan_generator.py:214-216, 230-233, 319-339) ------------------- */
 /* PixelNormLayer over channels + optional nearest x2 upsample: F32B [n][c/8][h][w][8] -> ACT at (h*up, w*up) */

@@ -285,7 +285,76 @@ def e_blur():
     print("e_blur_s16_l6.pt: const", tuple(const.shape), "w", tuple(w.shape), fx["fused"])
 
 
+def biggan():
+    import model.biggan_generator as bg
+    from model.utils.biggan_config import BigGANConfig
+    import model.E.E_BIG as EBIG
+    torch.set_grad_enabled(False)
+    gen = torch.Generator().manual_seed(9090)
+    torch.manual_seed(61)
+    cfg = dict(output_dim=64, z_dim=16, class_embed_dim=16, channel_width=32, num_classes=10,
+               layers=[[False, 16, 16], [True, 16, 8], [True, 8, 4], [True, 4, 2], [True, 2, 1]],
+               attention_layer_position=2, eps=1e-4, n_stats=11)
+    G = bg.BigGAN(BigGANConfig.from_dict(cfg)).eval()
+    for k, p in list(G.named_parameters()) + list(G.named_buffers()):
+        if k.endswith("running_means") or k.endswith(".bias"):
+            p.copy_(torch.randn(p.shape, generator=gen) * 0.2)
+        elif k.endswith("running_vars"):
+            p.copy_(torch.rand(p.shape, generator=gen) + 0.5)
+        elif k.endswith("bn.weight"):
+            p.copy_(1 + 0.2 * torch.randn(p.shape, generator=gen))      # uninitialised memory upstream (:124-125)
+        elif k.endswith("gamma"):
+            p.fill_(0.7)
+    z = torch.randn(2, 16, generator=gen) * 0.4
+    label = torch.zeros(2, 10)
+    label[0, 3] = 1
+    label[1, 7] = 1
+    # spectral-norm u/v start random: converge them with train-mode forwards (one power iteration each), then freeze
+    G.train()
+    for _ in range(30):
+        G(z, label, 0.4)
+    G.eval()
+    fx = {"config": cfg, "state_dict": clone_sd(G), "z": z, "label": label, "images": {}}
+    for trunc in (0.4, 0.37):
+        img, cond = G(z, label, trunc)
+        fx["images"][trunc] = img.clone()
+    fx["cond"] = cond.clone()
+    x8 = torch.randn(2, 256, 8, 8, generator=gen)
+    fx["attn"] = {"x": x8, "y": G.generator.layers[2](x8).clone()}
+    fx["block_up_drop"] = {"x": x8, "y": G.generator.layers[3](x8, cond, 0.4).clone()}
+    torch.save(fx, os.path.join(HERE, "biggan_small.pt"))
+    print("biggan_small.pt: image", tuple(img.shape), float(img.mean()), float(img.std()), "keys", len(fx["state_dict"]))
+
+    torch.manual_seed(62)
+    ecfg = dict(startf=16, maxf=64, layer_count=4, latent_size=512, channels=3, biggan=False)
+    E = EBIG.BE(**ecfg).eval()
+    perturb(E, ["noise_weight_1", "noise_weight_2", "bias_1", "bias_2", "bias"], gen)
+    img32 = torch.randn(2, 3, 32, 32, generator=gen)
+    cond256 = torch.randn(2, 256, generator=gen) * 0.3
+    E.train()
+    for _ in range(30):
+        E.features_unused = None
+        xx = E.FromRGB(img32)
+        for blk in E.decode_block:
+            xx, _, _ = blk(xx, cond256, truncation=0.4)
+    E.eval()
+    efx = {"config": ecfg, "state_dict": clone_sd(E), "img": img32, "cond": cond256, "blocks_seed13": {}}
+    x = E.FromRGB(img32)
+    torch.manual_seed(13)
+    for i, blk in enumerate(E.decode_block):
+        y, _, _ = blk(x, cond256, truncation=0.4)
+        efx["blocks_seed13"][i] = {"x": x.clone(), "y": y.clone()}
+        x = y
+    efx["features_seed13"] = x.clone()
+    torch.save(efx, os.path.join(HERE, "e_big_s16_l4.pt"))
+    print("e_big_s16_l4.pt: features", tuple(x.shape), "keys", len(efx["state_dict"]))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "biggan":
+        import_reference()
+        biggan()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "eblur":
         import_reference()
         e_blur()

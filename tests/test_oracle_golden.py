@@ -224,3 +224,27 @@ def test_e_blur_oracle():
     torch.manual_seed(72)
     y, w1, w2 = oenc.be_blur_block(sd, "decode_block.4.", b["x"], False)
     assert rel(y, b["y"]) < TOL and rel(w1, b["w1"]) < TOL and rel(w2, b["w2"]) < TOL
+
+
+def test_biggan_oracle():
+    from oracle import biggan as obg
+    fx = torch.load(os.path.join(GOLD, "biggan_small.pt"))
+    sd, cfg = fx["state_dict"], fx["config"]
+    for trunc, img in fx["images"].items():
+        out, cond = obg.biggan(sd, cfg, fx["z"], fx["label"], trunc)
+        assert rel(out, img) < 5e-5, trunc
+        assert rel(cond, fx["cond"]) < TOL
+    assert rel(obg.self_attn(sd, "generator.layers.2.", fx["attn"]["x"]), fx["attn"]["y"]) < 5e-5
+    assert rel(obg.gen_block(sd, "generator.layers.3.", fx["block_up_drop"]["x"], fx["cond"], 0.4, True, cfg["eps"]),
+               fx["block_up_drop"]["y"]) < 5e-5
+
+
+def test_e_big_oracle():
+    from oracle import biggan as obg
+    fx = torch.load(os.path.join(GOLD, "e_big_s16_l4.pt"))
+    sd = fx["state_dict"]
+    torch.manual_seed(13)
+    for i, b in fx["blocks_seed13"].items():
+        assert rel(obg.e_big_block(sd, f"decode_block.{i}.", b["x"], fx["cond"]), b["y"]) < 5e-5, i
+    torch.manual_seed(13)
+    assert rel(obg.e_big_features(sd, fx["img"], fx["cond"], 4), fx["features_seed13"]) < 5e-5
