@@ -967,6 +967,178 @@ __global__ void __launch_bounds__(256) k_ssim_sum(const float* __restrict__ a, c
 }
 
 // ---------------------------------------------------------------------------------------------
+// Grad-CAM / Grad-CAM++ maps (metric/grad_cam.py:101-194) from the hooked feature / gradient tensors (NCHW fp32).
+// The reference does this per image on the host in NumPy (float64 for the ++ variant) + cv2.resize.
+// ---------------------------------------------------------------------------------------------
+// first-max argmax per row (np.argmax) -> idx[n]; then mode with smallest-index tie break (np.argmax(np.bincount))
+__global__ void k_argmax_rows(const float* __restrict__ logits, int n, int k, long long* __restrict__ idx) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const float* p = logits + (size_t)r * k;
+  float best = p[0];
+  int bi = 0;
+  for (int i = 1; i < k; ++i)
+    if (p[i] > best) { best = p[i]; bi = i; }
+  idx[r] = bi;
+}
+__global__ void k_mode(const long long* __restrict__ idx, int n, long long* __restrict__ mode) {
+  if (blockIdx.x || threadIdx.x) return;
+  long long best = -1;
+  int bc = 0;
+  for (int i = 0; i < n; ++i) {
+    int c = 0;
+    for (int j = 0; j < n; ++j) c += idx[j] == idx[i];
+    if (c > bc || (c == bc && idx[i] < best)) { bc = c; best = idx[i]; }
+  }
+  *mode = best;
+}
+
+// one block per (n, c): plus == 1: w = sum(relu(g) * (1/sum relu(g)))  (0 if the sum is 0)   [Grad-CAM++ as coded, :170-178]
+//                       plus == 0: w = mean(g)                                               [Grad-CAM, :117]
+__global__ void __launch_bounds__(128) k_gradcam_weights(const float* __restrict__ grad, int hw, int plus,
+                                                         double* __restrict__ wout) {
+  const float* g = grad + (size_t)blockIdx.x * hw;
+  __shared__ float sred[4];
+  __shared__ double dred[4];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < hw; i += blockDim.x) s += plus ? fmaxf(g[i], 0.f) : g[i];
+  for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = s;
+  __syncthreads();
+  const float tot = sred[0] + sred[1] + sred[2] + sred[3];
+  if (!plus) {
+    if (threadIdx.x == 0) wout[blockIdx.x] = (double)(tot / (float)hw);     // np.mean of float32 stays float32
+    return;
+  }
+  const float inv = tot > 0.f ? 1.f / tot : 0.f;                            // float32 array element (:173-174)
+  double d = 0.0;
+  for (int i = threadIdx.x; i < hw; i += blockDim.x) d += (double)fmaxf(g[i], 0.f) * (double)inv;
+  for (int off = 16; off; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+  if ((threadIdx.x & 31) == 0) dred[threadIdx.x >> 5] = d;
+  __syncthreads();
+  if (threadIdx.x == 0) wout[blockIdx.x] = dred[0] + dred[1] + dred[2] + dred[3];
+}
+
+// one block per image: cam = sum_c feat_c * w_c  [relu if !plus]; cam -= min; cam /= max   (:179-186 / :118-125)
+__global__ void __launch_bounds__(256) k_gradcam_map(const float* __restrict__ feat, const double* __restrict__ w,
+                                                     int c, int hw, int plus, double* __restrict__ cam) {
+  const int n = blockIdx.x;
+  __shared__ double smin[8], smax[8];
+  double lmin = INFINITY, lmax = -INFINITY;
+  for (int i = threadIdx.x; i < hw; i += blockDim.x) {
+    double v;
+    if (plus) {
+      double a = 0.0;
+      for (int ch = 0; ch < c; ++ch) a += (double)feat[((size_t)n * c + ch) * hw + i] * w[(size_t)n * c + ch];
+      v = a;
+    } else {
+      float a = 0.f;                                                       // float32 path of the base class
+      for (int ch = 0; ch < c; ++ch) a += feat[((size_t)n * c + ch) * hw + i] * (float)w[(size_t)n * c + ch];
+      v = (double)fmaxf(a, 0.f);
+    }
+    cam[(size_t)n * hw + i] = v;
+    lmin = fmin(lmin, v);
+    lmax = fmax(lmax, v);
+  }
+  for (int off = 16; off; off >>= 1) {
+    lmin = fmin(lmin, __shfl_xor_sync(0xffffffffu, lmin, off));
+    lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, off));
+  }
+  if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lmin; smax[threadIdx.x >> 5] = lmax; }
+  __syncthreads();
+  double mn = smin[0], mx = smax[0];
+  for (int i = 1; i < 8; ++i) { mn = fmin(mn, smin[i]); mx = fmax(mx, smax[i]); }
+  const double denom = plus ? (mx - mn) : (double)((float)mx - (float)mn);
+  for (int i = threadIdx.x; i < hw; i += blockDim.x) {
+    const size_t o = (size_t)n * hw + i;
+    cam[o] = plus ? (cam[o] - mn) / denom : (double)(((float)cam[o] - (float)mn) / (float)denom);
+  }
+}
+
+// cv2.resize(src, (wo, ho)) INTER_LINEAR for a single-channel float image: half-pixel centres, float coefficients,
+// edge clamping (OpenCV resizeGeneric / HResizeLinear / VResizeLinear)
+__global__ void k_resize_bilinear(const double* __restrict__ src, int n, int hi, int wi, int ho, int wo, int f32path,
+                                  double* __restrict__ dst) {
+  const size_t total = (size_t)n * ho * wo;
+  const double sx_scale = (double)wi / wo, sy_scale = (double)hi / ho;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int dx = (int)(i % wo), dy = (int)((i / wo) % ho);
+    const size_t b = i / ((size_t)wo * ho);
+    float fx = (float)((dx + 0.5) * sx_scale - 0.5);
+    int sx = (int)floorf(fx);
+    fx -= sx;
+    if (sx < 0) { fx = 0.f; sx = 0; }
+    if (sx >= wi - 1) { fx = 0.f; sx = wi - 1; }
+    float fy = (float)((dy + 0.5) * sy_scale - 0.5);
+    int sy = (int)floorf(fy);
+    fy -= sy;
+    if (sy < 0) { fy = 0.f; sy = 0; }
+    if (sy >= hi - 1) { fy = 0.f; sy = hi - 1; }
+    const int sx1 = sx + 1 < wi ? sx + 1 : sx, sy1 = sy + 1 < hi ? sy + 1 : sy;
+    const double* p = src + b * (size_t)hi * wi;
+    if (f32path) {
+      const float a0 = 1.f - fx, a1 = fx, b0 = 1.f - fy, b1 = fy;
+      const float r0 = (float)p[(size_t)sy * wi + sx] * a0 + (float)p[(size_t)sy * wi + sx1] * a1;
+      const float r1 = (float)p[(size_t)sy1 * wi + sx] * a0 + (float)p[(size_t)sy1 * wi + sx1] * a1;
+      dst[i] = (double)(r0 * b0 + r1 * b1);
+    } else {
+      const double a0 = (double)(1.f - fx), a1 = (double)fx, b0 = (double)(1.f - fy), b1 = (double)fy;
+      const double r0 = p[(size_t)sy * wi + sx] * a0 + p[(size_t)sy * wi + sx1] * a1;
+      const double r1 = p[(size_t)sy1 * wi + sx] * a0 + p[(size_t)sy1 * wi + sx1] * a1;
+      dst[i] = r0 * b0 + r1 * b1;
+    }
+  }
+}
+
+// mask2cam (metric/grad_cam.py:234-251): JET colour map of the mask + overlay on the image
+__device__ __forceinline__ void atomic_min_f(float* addr, float v) {
+  if (v >= 0.f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f(float* addr, float v) {
+  if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+// heat[n][c][p] = lut_rgb[(uint8)(255*mask[n][p])][c] / 255 ; cam = heat + img
+__global__ void k_jet_overlay(const double* __restrict__ mask, const float* __restrict__ img,
+                              const float* __restrict__ lut_rgb, float* __restrict__ heat, float* __restrict__ cam,
+                              int n, int hw) {
+  const size_t total = (size_t)n * 3 * hw;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t p = i % hw;
+    const int c = (int)((i / hw) % 3);
+    const size_t b = i / ((size_t)3 * hw);
+    const unsigned char q = (unsigned char)(long long)(255.0 * mask[b * hw + p]);   // np.uint8(255 * j): truncation
+    const float hv = lut_rgb[q * 3 + c] / 255.f;
+    heat[i] = hv;
+    cam[i] = img[i];          // cam starts as a copy of the images (:239); image i gets its overlay inside the loop
+  }
+}
+// out[0] = min(x[0:n]), out[1] = max(x[0:n]); out must be pre-set to (+inf, -inf)
+__global__ void k_minmax(const float* __restrict__ x, size_t n, float* __restrict__ out) {
+  float mn = INFINITY, mx = -INFINITY;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    mn = fminf(mn, x[i]);
+    mx = fmaxf(mx, x[i]);
+  }
+  for (int off = 16; off; off >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomic_min_f(out, mn);
+    atomic_max_f(out + 1, mx);
+  }
+}
+// x = (x - *sub) ; or x = x / *div   (device scalars)
+__global__ void k_sub_or_div(float* __restrict__ x, size_t n, const float* __restrict__ sub,
+                             const float* __restrict__ div) {
+  const float s = sub ? *sub : 0.f, d = div ? *div : 1.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    x[i] = (x[i] - s) / d;
+}
+
+// ---------------------------------------------------------------------------------------------
 // LREQAdam (model/utils/custom_adam.py:24-76): beta1 == 0 Adam, per-tensor step size
 //   v = beta2*v + (1-beta2)*g*g ;  p -= step[t] * g / (sqrt(v) + eps)
 // multi-tensor: block b works on tensor blk_tensor[b], elements [blk_off[b], blk_off[b] + chunk)
@@ -1296,6 +1468,55 @@ int dge_ssim_sum(const float* a, const float* b, int64_t planes, int h, int w, d
   }
   if (cudaMemsetAsync(out1, 0, sizeof(double), st) != cudaSuccess) { set_error("ssim_sum: memset failed"); return DGE_ERR_CUDA; }
   LAUNCH_1D(k_ssim_sum, (size_t)planes * h * w, stream, a, b, (size_t)planes, h, w, out1);
+}
+
+int dge_argmax_mode(const float* logits, int n, int k, int64_t* idx_out, int64_t* mode_out, void* stream) {
+  DGE_REQUIRE(logits && idx_out && mode_out && n > 0 && k > 0, "argmax_mode: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  k_argmax_rows<<<(n + 127) / 128, 128, 0, st>>>(logits, n, k, (long long*)idx_out);
+  count_launch();
+  k_mode<<<1, 32, 0, st>>>((const long long*)idx_out, n, (long long*)mode_out);
+  count_launch();
+  return check_launch("k_argmax_rows/k_mode");
+}
+int dge_gradcam(const float* feature, const float* gradient, int plus, double* w_scratch, double* cam_scratch,
+                double* out, int n, int c, int h, int w, int h_out, int w_out, void* stream) {
+  DGE_REQUIRE(feature && gradient && w_scratch && cam_scratch && out, "gradcam: null pointer");
+  DGE_REQUIRE(n > 0 && c > 0 && h > 0 && w > 0 && h_out > 0 && w_out > 0, "gradcam: bad dims");
+  cudaStream_t st = (cudaStream_t)stream;
+  k_gradcam_weights<<<n * c, 128, 0, st>>>(gradient, h * w, plus, w_scratch);
+  count_launch();
+  k_gradcam_map<<<n, 256, 0, st>>>(feature, w_scratch, c, h * w, plus, cam_scratch);
+  count_launch();
+  k_resize_bilinear<<<grid_for((size_t)n * h_out * w_out, 256), 256, 0, st>>>(cam_scratch, n, h, w, h_out, w_out,
+                                                                            plus ? 0 : 1, out);
+  count_launch();
+  return check_launch("gradcam");
+}
+
+int dge_mask2cam(const double* mask, const float* img, const float* lut_rgb, float* heat, float* cam, float* scratch4,
+                 int n, int h, int w, void* stream) {
+  DGE_REQUIRE(mask && img && lut_rgb && heat && cam && scratch4 && n > 0 && h > 0 && w > 0, "mask2cam: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t per = (size_t)3 * h * w;
+  k_jet_overlay<<<grid_for((size_t)n * per, 256), 256, 0, st>>>(mask, img, lut_rgb, heat, cam, n, h * w);
+  count_launch();
+  const float init[4] = {INFINITY, -INFINITY, INFINITY, -INFINITY};
+  for (int i = 0; i < n; ++i) {
+    // cam[i] -= np.max(np.min(cam), 0)  -- the min over the WHOLE array as it is at this point (:248); then /= max(cam[i])
+    if (cudaMemcpyAsync(scratch4, init, sizeof(init), cudaMemcpyHostToDevice, st) != cudaSuccess) {
+      set_error("mask2cam: scratch init failed");
+      return DGE_ERR_CUDA;
+    }
+    k_axpby<<<grid_for(per, 256), 256, 0, st>>>(heat + i * per, img + i * per, cam + i * per, 1.f, 1.f, per);   // :246
+    count_launch();
+    k_minmax<<<grid_for((size_t)n * per / 4 + 1, 256), 256, 0, st>>>(cam, (size_t)n * per, scratch4);
+    k_sub_or_div<<<grid_for(per, 256), 256, 0, st>>>(cam + i * per, per, scratch4, nullptr);
+    k_minmax<<<grid_for(per / 4 + 1, 256), 256, 0, st>>>(cam + i * per, per, scratch4 + 2);
+    k_sub_or_div<<<grid_for(per, 256), 256, 0, st>>>(cam + i * per, per, nullptr, scratch4 + 3);
+    for (int k = 0; k < 4; ++k) count_launch();
+  }
+  return check_launch("mask2cam");
 }
 
 int dge_lreq_adam_step(void* const* params, const void* const* grads, void* const* vs, const int64_t* numel,

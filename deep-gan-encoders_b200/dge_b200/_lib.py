@@ -85,6 +85,9 @@ SIGNATURES = {
     "dge_maxpool2_f32b": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     "dge_channel_softmax_to_act": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "dge_tanh_slice_nchw": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
+    "dge_argmax_mode": (c_int, [P, c_int, c_int, P, P, P]),
+    "dge_gradcam": (c_int, [P, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "dge_mask2cam": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P]),
     "dge_blend": (c_int, [P, P, P, c_float, c_float, c_int, c_int, c_int, c_int, c_int, P]),
 }
 

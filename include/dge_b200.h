@@ -230,6 +230,23 @@ int dge_avgpool_nchw(const float* x, float* out, int64_t planes, int h_out, int 
 /* sum of the SSIM map (11x11 gaussian sigma 1.5, zero padding, C1=1e-4, C2=9e-4) over [planes][h][w] */
 int dge_ssim_sum(const float* a, const float* b, int64_t planes, int h, int w, double* out1, void* stream);
 
+/* ---- Grad-CAM (metric/grad_cam.py:101-194) ---------------------------------------------------- */
+/* idx_out[n] = np.argmax(logits, axis=1) (first maximum); *mode_out = np.argmax(np.bincount(idx)) (:164-165). Bit-exact. */
+int dge_argmax_mode(const float* logits, int n, int k, int64_t* idx_out, int64_t* mode_out, void* stream);
+/* CAM maps from the hooked layer: feature / gradient NCHW fp32 [n][c][h][w] -> out float64 [n][h_out][w_out].
+   plus = 1: Grad-CAM++ as coded (:169-190, float64): w_c = sum(relu(g_c) * 1/sum(relu(g_c))), cam = sum_c f_c*w_c,
+             cam -= min, cam /= max, cv2.resize bilinear to (w_out, h_out);
+   plus = 0: Grad-CAM (:113-126, float32): w_c = mean(g_c), relu(cam), same normalisation / resize.
+   w_scratch: n*c doubles, cam_scratch: n*h*w doubles. */
+int dge_gradcam(const float* feature, const float* gradient, int plus, double* w_scratch, double* cam_scratch,
+                double* out, int n, int c, int h, int w, int h_out, int w_out, void* stream);
+
+/* mask2cam (:234-251): heat = JET(uint8(255*mask)) / 255 (RGB, `lut_rgb` = the 256x3 colour table), cam = heat + img,
+   then per image i: cam[i] -= min(cam) (whole array, as upstream), cam[i] /= max(cam[i]).  mask float64 [n][h][w],
+   img / heat / cam fp32 NCHW [n][3][h][w]; scratch4 = 4 floats. */
+int dge_mask2cam(const double* mask, const float* img, const float* lut_rgb, float* heat, float* cam, float* scratch4,
+                 int n, int h, int w, void* stream);
+
 /* ---- optimiser (model/utils/custom_adam.py:24-76, LREQAdam.step) ------------------------------ */
 /* One multi-tensor launch:  v = beta2*v + (1-beta2)*g*g ;  p -= step[t]*g/(sqrt(v)+eps)   (beta1 == 0).
    params/grads/vs: DEVICE arrays of n_tensors device pointers; numel/step: per-tensor DEVICE arrays

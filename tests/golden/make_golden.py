@@ -350,7 +350,63 @@ def biggan():
     print("e_big_s16_l4.pt: features", tuple(x.shape), "keys", len(efx["state_dict"]))
 
 
+def tiny_vgg():
+    """VGG-like stand-in (torchvision VGG16 weights are unavailable offline): the hooked conv is followed by an
+    in-place ReLU, as `features.28` is in VGG16."""
+    import torch.nn as nn
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.features = nn.Sequential(nn.Conv2d(3, 8, 3, padding=1), nn.ReLU(inplace=True), nn.MaxPool2d(2),
+                                          nn.Conv2d(8, 16, 3, padding=1), nn.ReLU(inplace=True), nn.MaxPool2d(2))
+            self.pool = nn.AdaptiveAvgPool2d(2)
+            self.classifier = nn.Linear(64, 10)
+
+        def forward(self, x):
+            return self.classifier(torch.flatten(self.pool(self.features(x)), 1))
+
+    return Net()
+
+
+def gradcam():
+    import contextlib
+    import io
+    import warnings
+    warnings.filterwarnings("ignore")
+    import metric.grad_cam as gc
+    torch.set_grad_enabled(True)
+    gen = torch.Generator().manual_seed(4040)
+    torch.manual_seed(71)
+    net = tiny_vgg()
+    imgs = torch.randn(3, 3, 40, 24, generator=gen)
+    fx = {"net_state": clone_sd(net), "imgs": imgs}
+    with contextlib.redirect_stdout(io.StringIO()):
+        for name, cls in (("pp", gc.GradCamPlusPlus), ("base", gc.GradCAM)):
+            cam = cls(net, "features.3")
+            x = imgs.clone().requires_grad_(True)
+            out = cam(x, None)
+            fx[name] = {"out": out.clone(), "feature": cam.feature.detach().clone(),
+                        "gradient": cam.gradient.detach().clone()}
+            cam.remove_handlers()
+        logits = net(imgs).detach()
+    fx["logits"] = logits
+    fx["index"] = torch.tensor(np.argmax(logits.numpy(), axis=1))
+    fx["index_max"] = int(np.argmax(np.bincount(np.argmax(logits.numpy(), axis=1))))
+    mask = fx["pp"]["out"]
+    heat, camimg = gc.mask2cam(mask, imgs)
+    fx["mask2cam"] = {"heat": heat, "cam": camimg}
+    torch.save(fx, os.path.join(HERE, "gradcam_tiny.pt"))
+    print("gradcam_tiny.pt: out", tuple(mask.shape), mask.dtype, "index", fx["index"].tolist(), fx["index_max"])
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "gradcam":
+        import numpy as np
+        globals()["np"] = np
+        import_reference()
+        gradcam()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "biggan":
         import_reference()
         biggan()

@@ -248,3 +248,16 @@ def test_e_big_oracle():
         assert rel(obg.e_big_block(sd, f"decode_block.{i}.", b["x"], fx["cond"]), b["y"]) < 5e-5, i
     torch.manual_seed(13)
     assert rel(obg.e_big_features(sd, fx["img"], fx["cond"], 4), fx["features_seed13"]) < 5e-5
+
+
+def test_gradcam_oracle():
+    from oracle import gradcam as ogc
+    fx = torch.load(os.path.join(GOLD, "gradcam_tiny.pt"))
+    idx, mode = ogc.class_index(fx["logits"])
+    assert idx.tolist() == fx["index"].tolist() and mode == fx["index_max"]
+    pp = ogc.gradcam_pp(fx["pp"]["feature"], fx["pp"]["gradient"], (40, 24))
+    assert pp.dtype == torch.float64 and rel(pp, fx["pp"]["out"]) < 1e-9
+    base = ogc.gradcam(fx["base"]["feature"], fx["base"]["gradient"], (40, 24))
+    assert rel(base, fx["base"]["out"]) < 1e-7
+    heat, cam = ogc.mask2cam(fx["pp"]["out"], fx["imgs"])
+    assert rel(heat, fx["mask2cam"]["heat"]) < 1e-7 and rel(cam, fx["mask2cam"]["cam"]) < 1e-6
