@@ -826,6 +826,19 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
     p.ntile = p.cw;
     p.np = 1;
   }
+  // small problems (<= 32x32 maps): shrink the N tile until the grid covers the SMs -- a 128x256 tile over K = 9*512 is
+  // ~100 us of MMA time on ONE SM, so 16..32 such tiles would leave most of the chip idle
+  {
+    if (g_num_sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+      if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    const long long mtiles = (long long)p.N * p.tiles_x * p.tiles_y;
+    while (mtiles * (p.Cout / p.cw) * 4 < (long long)g_num_sms * 3 && p.cw >= 64 && (p.cw / 2) % 16 == 0) p.cw /= 2;
+    p.ntile = p.np * p.cw;
+  }
   p.nsub = p.cw;   // one MMA covers the whole column block (N <= 256)
   DGE_REQUIRE(p.cw > 0 && p.nsub > 0, "conv: cannot tile cout=%d", p.Cout);
   p.n_ntiles = ntot / p.ntile;
