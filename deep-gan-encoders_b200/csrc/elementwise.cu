@@ -362,23 +362,34 @@ __global__ void k_rgb_init(const float* __restrict__ in, const float* __restrict
 // ---------------------------------------------------------------------------------------------
 // encoder pieces
 // ---------------------------------------------------------------------------------------------
-__global__ void k_from_rgb(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ b,
-                           float* __restrict__ out, int n, int cimg, int c, int h, int wd, float slope) {
+// one thread per pixel: the (<= 4) image channels are read once, every output channel group is produced from weights
+// staged in shared memory (broadcast reads), stores are 32-byte vectors contiguous across the warp
+__global__ void __launch_bounds__(256)
+k_from_rgb(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ b,
+           float* __restrict__ out, int n, int cimg, int c, int h, int wd, float slope) {
+  extern __shared__ float sw[];            // [c][cimg] weights then [c] bias
+  for (int i = threadIdx.x; i < c * cimg; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < c; i += blockDim.x) sw[c * cimg + i] = b ? b[i] : 0.f;
+  __syncthreads();
   const int C8 = c >> 3;
-  const size_t total = (size_t)n * C8 * h * wd;
+  const size_t total = (size_t)n * h * wd;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const Idx4 q = decode4(i, C8, h, wd);
-    float v[8];
+    const int x = (int)(i % wd);
+    const int y = (int)((i / wd) % h);
+    const int bn = (int)(i / ((size_t)wd * h));
+    float px[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int ci = 0; ci < cimg && ci < 4; ++ci) px[ci] = img[(((size_t)bn * cimg + ci) * h + y) * wd + x];
+    for (int g = 0; g < C8; ++g) {
+      float v[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = b ? b[q.g * 8 + k] : 0.f;
-    for (int ci = 0; ci < cimg; ++ci) {
-      const float px = img[(((size_t)q.n * cimg + ci) * h + q.y) * wd + q.x];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = fmaf(px, w[(size_t)(q.g * 8 + k) * cimg + ci], v[k]);
+      for (int k = 0; k < 8; ++k) {
+        const int ch = g * 8 + k;
+        float a = sw[c * cimg + ch];
+        for (int ci = 0; ci < cimg && ci < 4; ++ci) a = fmaf(px[ci], sw[ch * cimg + ci], a);
+        v[k] = a < 0.f ? a * slope : a;
+      }
+      store8_f32b(out, f32b_idx32(bn, g, y, x, C8, h, wd), v);
     }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = v[k] < 0.f ? v[k] * slope : v[k];
-    store8_f32b(out, i, v);
   }
 }
 
@@ -1295,8 +1306,11 @@ int dge_rgb_init(const float* img_in, const float* bias, float* img_out, int n, 
 int dge_from_rgb(const float* img, const float* w, const float* b, float* out, int n, int cimg, int c, int h, int wd,
                  float slope, void* stream) {
   DGE_REQUIRE(img && w && out, "from_rgb: null pointer");
-  DGE_REQUIRE(n > 0 && cimg > 0 && c > 0 && c % 8 == 0 && h > 0 && wd > 0, "from_rgb: bad dims");
-  LAUNCH_1D(k_from_rgb, (size_t)n * (c / 8) * h * wd, stream, img, w, b, out, n, cimg, c, h, wd, slope);
+  DGE_REQUIRE(n > 0 && cimg > 0 && cimg <= 4 && c > 0 && c % 8 == 0 && c <= 2048 && h > 0 && wd > 0, "from_rgb: bad dims");
+  k_from_rgb<<<grid_for((size_t)n * h * wd, 256), 256, (size_t)(c * cimg + c) * sizeof(float), (cudaStream_t)stream>>>(
+      img, w, b, out, n, cimg, c, h, wd, slope);
+  count_launch();
+  return check_launch("k_from_rgb");
 }
 
 int dge_instance_stats(const float* x, double* scratch, float* style, float* mean_rstd, int n, int c, int h, int w,
