@@ -42,6 +42,25 @@ struct TapEntry {
   int16_t in_phase;  // -1: applies to every K chunk; else only to chunks of this input phase (space-to-depth conv)
 };
 
+// division by a runtime constant: q = (umulhi(n, mul) + n) >> shr   (host computes mul/shr, n < 2^31)
+struct FastDiv {
+  uint32_t mul, shr;
+};
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, FastDiv d) {
+  return (uint32_t)(((uint64_t)__umulhi(n, d.mul) + n) >> d.shr);
+}
+static FastDiv make_fast_div(uint32_t d) {
+  FastDiv f;
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;
+  f.mul = (uint32_t)((((1ull << l) - d) << 32) / d + 1);
+  f.shr = l;
+  return f;
+}
+
+constexpr int EPI_TAB_COLS = 256;                      // widest CTA column block
+constexpr int EPI_TAB_BYTES = 7 * EPI_TAB_COLS * 4;    // A, B, NW, S, RGB[3] rows of the per-(sample, N tile) table
+
 struct ConvKParams {
   int N, H, W;             // input dims
   int dom_h, dom_w;        // tile domain (H,W) or (H+1,W+1) for the transposed conv
@@ -58,6 +77,12 @@ struct ConvKParams {
   int a_slot_bytes, b_slot_bytes, b_sub_bytes, b_slots;
   int a_slots, b_region_bytes, resident, acc_stages, b_rb;
   int tmem_cols;
+  int tpc;                 // taps issued per K chunk (ntaps, or 4 for the space-to-depth conv)
+  int stack;               // 1: hi|lo weight planes stacked on N (A_hi x [B_hi|B_lo] + A_lo x B_hi: 2 MMAs instead of 3)
+  int acc_cols;            // TMEM columns of one phase block = cw * (stack ? 2 : 1)
+  int tm_stride;           // TMEM columns of one accumulator stage = np * acc_cols
+  FastDiv div_ntiles, div_per_img, div_tiles_x;
+  int act_mode;            // 0: identity (slope == 1), 1: max(v, v*slope) (0 <= slope <= 1), 2: select form
   // epilogue
   const float* demod;
   const float* noise;
@@ -328,12 +353,12 @@ struct TileCoord {
 };
 __device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int tile) {
   TileCoord t;
-  t.nt = tile % p.n_ntiles;
-  int mt = tile / p.n_ntiles;
+  const int mt = (int)fast_div((uint32_t)tile, p.div_ntiles);
+  t.nt = tile - mt * p.n_ntiles;
   const int per_img = p.tiles_x * p.tiles_y;
-  t.n = mt / per_img;
-  int r = mt - t.n * per_img;
-  int ty = r / p.tiles_x;
+  t.n = (int)fast_div((uint32_t)mt, p.div_per_img);
+  const int r = mt - t.n * per_img;
+  const int ty = (int)fast_div((uint32_t)r, p.div_tiles_x);
   t.y0 = ty * TH;
   t.x0 = (r - ty * p.tiles_x) * TW;
   // an N tile holds `np` phases x `cw` channels: channels [nt*cw, (nt+1)*cw) of every phase
@@ -343,32 +368,248 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int tile)
 }
 
 // ---------------------------------------------------------------------------------------------
+// lean epilogue of the tcgen05 kernel
+//   Per-channel parameters come from a shared-memory table (rows A, B, NW, S, RGB0..2 of EPI_TAB_COLS floats) that the
+//   128 epilogue threads refill only when the (sample, N tile) changes.  With g = gain (lrelu is positively
+//   homogeneous, so the gain is folded into the affine part):
+//     A[c] = demod[n][c]*g   B[c] = bias[c]*g   NW[c] = noise weight*g   S[c] = next-layer style   RGB = ToRGB weights
+//     v = max(z, z*slope),  z = acc*A + B + nz*NW   (+ residual*g)
+// ---------------------------------------------------------------------------------------------
+struct EpiPix {
+  int n, y, x;
+  bool valid;
+  float nz;
+};
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ void epi_fill_table(const ConvKParams& p, float* tab, int n, int co0, int et) {
+  for (int c = et; c < p.cw; c += 128) {
+    const int co = co0 + c;
+    tab[c] = (p.demod ? __ldg(p.demod + (size_t)n * p.Cout + co) : 1.f) * p.gain;
+    tab[EPI_TAB_COLS + c] = (p.bias ? __ldg(p.bias + co) : 0.f) * p.gain;
+    tab[2 * EPI_TAB_COLS + c] = (p.noise ? (p.noise_w ? __ldg(p.noise_w + co) : p.noise_scalar) : 0.f) * p.gain;
+    tab[3 * EPI_TAB_COLS + c] = p.out_scale ? __ldg(p.out_scale + (size_t)n * p.Cout + co) : 1.f;
+    if (p.rgb_w) {
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch)
+        tab[(4 + ch) * EPI_TAB_COLS + c] = __ldg(p.rgb_w + ((size_t)n * 3 + ch) * p.Cout + co);
+    }
+  }
+}
+
+__device__ __forceinline__ void tm_ld16_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+// the "+r" operands tie the loaded registers to the wait so no use can be scheduled ahead of it
+__device__ __forceinline__ void tm_ld16_wait(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+
+// 8 floats -> bf16 hi chunk and bf16 lo chunk (x ~= hi + lo): 2 packed converts, 2 unpacks and 2 subtracts per pair
+__device__ __forceinline__ void split8_fast(const float* v, uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 hb = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hb);
+    const float r0 = v[2 * i] - __uint_as_float(h[i] << 16);
+    const float r1 = v[2 * i + 1] - __uint_as_float(h[i] & 0xffff0000u);
+    const __nv_bfloat162 lb = __floats2bfloat162_rn(r0, r1);
+    l[i] = *reinterpret_cast<const uint32_t*>(&lb);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// r += s (fp32 bit patterns): the two column halves of a stacked accumulator
+__device__ __forceinline__ void epi_fold16(uint32_t* r, const uint32_t* s) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(s[j]));
+}
+
+template <int EPI>
+__device__ __forceinline__ void epi_group16(const ConvKParams& p, const float* tab, const EpiPix& px, int co0, int p0,
+                                            int q, int c, const uint32_t* r, float* rgb) {
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+  if (EPI == 1) {
+    epi_rawup16(p, px.n, px.y, px.x, px.valid, p0 + q, co0 + c, v);
+    __syncwarp();
+    return;
+  }
+  const float4* A4 = reinterpret_cast<const float4*>(tab + c);
+  const float4* B4 = reinterpret_cast<const float4*>(tab + EPI_TAB_COLS + c);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float4 a = A4[k], b = B4[k];
+    v[4 * k] = fmaf(v[4 * k], a.x, b.x);
+    v[4 * k + 1] = fmaf(v[4 * k + 1], a.y, b.y);
+    v[4 * k + 2] = fmaf(v[4 * k + 2], a.z, b.z);
+    v[4 * k + 3] = fmaf(v[4 * k + 3], a.w, b.w);
+  }
+  if (p.noise) {
+    const float4* N4 = reinterpret_cast<const float4*>(tab + 2 * EPI_TAB_COLS + c);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 w = N4[k];
+      v[4 * k] = fmaf(px.nz, w.x, v[4 * k]);
+      v[4 * k + 1] = fmaf(px.nz, w.y, v[4 * k + 1]);
+      v[4 * k + 2] = fmaf(px.nz, w.z, v[4 * k + 2]);
+      v[4 * k + 3] = fmaf(px.nz, w.w, v[4 * k + 3]);
+    }
+  }
+  const int H = p.H, W = p.W, C8 = p.Cout >> 3, g0 = (co0 + c) >> 3;
+  if (p.preact_add && px.valid) {
+    float t[8];
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      // residual may have more channels than the output (BigGAN channel drop) and half its resolution (nearest x2)
+      load8_f32b(p.preact_add, f32b_idx32(px.n, g0 + g, px.y / p.preact_up, px.x / p.preact_up, p.preact_c >> 3,
+                                          H / p.preact_up, W / p.preact_up), t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[8 * g + j] = fmaf(t[j], p.gain, v[8 * g + j]);
+    }
+  }
+  if (p.act_mode == 1) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], v[j] * p.slope);
+  } else if (p.act_mode == 2) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = v[j] < 0.f ? v[j] * p.slope : v[j];
+  }
+  if (px.valid) {
+    if (p.blend_src) {
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        float sv[8];
+        if (p.blend_pool) {
+          float t[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sv[j] = 0.f;
+#pragma unroll
+          for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+              load8_f32b(p.blend_src, f32b_idx32(px.n, g0 + g, 2 * px.y + dy, 2 * px.x + dx, C8, 2 * H, 2 * W), t);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) sv[j] += t[j];
+            }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sv[j] *= 0.25f;
+        } else {
+          load8_f32b(p.blend_src, f32b_idx32(px.n, g0 + g, px.y, px.x, C8, H, W), sv);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[8 * g + j] = p.blend_a * sv[j] + p.blend_b * v[8 * g + j];
+      }
+    }
+    if (p.rgb_w) {
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        const float4* R4 = reinterpret_cast<const float4*>(tab + (4 + ch) * EPI_TAB_COLS + c);
+        float acc = rgb[ch];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 w = R4[k];
+          acc = fmaf(v[4 * k], w.x, acc);
+          acc = fmaf(v[4 * k + 1], w.y, acc);
+          acc = fmaf(v[4 * k + 2], w.z, acc);
+          acc = fmaf(v[4 * k + 3], w.w, acc);
+        }
+        rgb[ch] = acc;
+      }
+    }
+    const size_t HW = (size_t)H * W, pix = (size_t)px.y * W + px.x;
+    if (p.out_f32b) {
+      float4* o = reinterpret_cast<float4*>(p.out_f32b) + (((size_t)px.n * C8 + g0) * HW + pix) * 2;
+      o[0] = make_float4(v[0], v[1], v[2], v[3]);
+      o[1] = make_float4(v[4], v[5], v[6], v[7]);
+      o[2 * HW] = make_float4(v[8], v[9], v[10], v[11]);
+      o[2 * HW + 1] = make_float4(v[12], v[13], v[14], v[15]);
+    }
+    if (p.out_nchw) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) p.out_nchw[((size_t)px.n * p.Cout + co0 + c + j) * HW + pix] = v[j];
+    }
+    if (p.out_act) {
+      const float4* S4 = reinterpret_cast<const float4*>(tab + 3 * EPI_TAB_COLS + c);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 w = S4[k];
+        v[4 * k] *= w.x; v[4 * k + 1] *= w.y; v[4 * k + 2] *= w.z; v[4 * k + 3] *= w.w;
+      }
+      uint4* o = reinterpret_cast<uint4*>(p.out_act) + ((size_t)px.n * C8 + g0) * p.out_planes * HW + pix;
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        uint4 hi, lo;
+        split8_fast(v + 8 * g, hi, lo);
+        o[(size_t)g * p.out_planes * HW] = hi;
+        if (p.out_planes == 2) o[(size_t)g * p.out_planes * HW + HW] = lo;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
 // the tcgen05 kernel
 // ---------------------------------------------------------------------------------------------
 constexpr int MAX_A_SLOTS = 4;
 constexpr int BAR_A_FULL = 0, BAR_A_EMPTY = MAX_A_SLOTS, BAR_TM_FULL = 2 * MAX_A_SLOTS, BAR_TM_EMPTY = BAR_TM_FULL + 2,
               BAR_B_FULL = BAR_TM_EMPTY + 2, BAR_B_EMPTY = BAR_B_FULL + MAX_B_SLOTS, BAR_COUNT = BAR_B_EMPTY + MAX_B_SLOTS;
 
-// all MMAs of one (tap, K-chunk): KSTEPS x {hi*hi, hi*lo, lo*hi} into accumulator column block d
-template <bool SPLIT>
-__device__ __forceinline__ void issue_tap(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, int ksteps,
-                                          uint32_t a_kstep, uint32_t b_kstep, uint32_t a_lo16, uint32_t b_lo16,
-                                          uint32_t accumulate) {
+// all MMAs of one (tap, K-chunk) into accumulator column block d.
+//   MODE 0: plain bf16 (1 MMA per K-step)
+//   MODE 1: split precision, 3 MMAs per K-step: hi*hi, hi*lo, lo*hi
+//   MODE 2: split precision with the weight planes stacked on N: A_hi x [B_hi|B_lo] (N = 2*cw, the hi and lo rows
+//           of one k-group are contiguous in smem) + A_lo x B_hi -- 2 MMAs per K-step.  For cw <= 32 an MMA is bound
+//           by the 4 KB A-operand read from shared memory (32 clk) whatever N is, so this is 1.5x fewer tensor-pipe
+//           cycles; the epilogue adds the two column halves.
+template <int MODE>
+__device__ __forceinline__ void issue_tap(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t idesc2,
+                                          int ksteps, uint32_t a_kstep, uint32_t b_kstep, uint32_t a_lo16,
+                                          uint32_t b_lo16, uint32_t accumulate) {
 #pragma unroll 1
   for (int k = 0; k < ksteps; ++k) {
-    tc_mma_bf16(d, da, db, idesc, accumulate);
-    if (SPLIT) {
-      tc_mma_bf16(d, da, db + b_lo16, idesc, 1u);
+    if (MODE == 2) {
+      tc_mma_bf16(d, da, db, idesc2, accumulate);
       tc_mma_bf16(d, da + a_lo16, db, idesc, 1u);
+    } else {
+      tc_mma_bf16(d, da, db, idesc, accumulate);
+      if (MODE == 1) {
+        tc_mma_bf16(d, da, db + b_lo16, idesc, 1u);
+        tc_mma_bf16(d, da + a_lo16, db, idesc, 1u);
+      }
     }
     accumulate = 1u;
     da += a_kstep;
     db += b_kstep;
   }
 }
+__device__ __forceinline__ void issue_tap_mode(int mode, uint32_t d, uint64_t da, uint64_t db, uint32_t idesc,
+                                               uint32_t idesc2, int ksteps, uint32_t a_kstep, uint32_t b_kstep,
+                                               uint32_t a_lo16, uint32_t b_lo16, uint32_t accumulate) {
+  if (mode == 2)
+    issue_tap<2>(d, da, db, idesc, idesc2, ksteps, a_kstep, b_kstep, a_lo16, b_lo16, accumulate);
+  else if (mode == 1)
+    issue_tap<1>(d, da, db, idesc, idesc2, ksteps, a_kstep, b_kstep, a_lo16, b_lo16, accumulate);
+  else
+    issue_tap<0>(d, da, db, idesc, idesc2, ksteps, a_kstep, b_kstep, a_lo16, b_lo16, accumulate);
+}
 
 template <int EPI>  // 0 = pointwise, 1 = raw up
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS, 2)
 conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ ConvKParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -382,6 +623,8 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* b_full = bars + BAR_B_FULL;
   uint64_t* b_empty = bars + BAR_B_EMPTY;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
+  float* epi_tab = reinterpret_cast<float*>(bars + BAR_COUNT + 2);   // EPI_TAB_BYTES, 16-byte aligned
+  uint4* issue_list = reinterpret_cast<uint4*>(epi_tab + 7 * EPI_TAB_COLS);   // nchunks * tpc entries
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -468,93 +711,74 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp == 1) {
     // =================================== MMA issuer ======================================
-    const uint32_t idesc = make_idesc_bf16(p.nsub);
+    // Warp-uniform control flow; only the tcgen05 instructions are predicated on the elected lane, so descriptors stay
+    // in uniform registers.  The per-(chunk, tap) issue parameters are precomputed once into a shared-memory list:
+    // for 16/32-channel layers a tile is only ~18-54 small MMAs and the issue path, not the tensor pipe, was the
+    // critical path when every tap re-derived its descriptor from the parameter block.
+    const uint32_t idesc = make_idesc_bf16(p.nsub), idesc2 = make_idesc_bf16(2 * p.nsub);
+    const int mma_mode = p.planes == 2 ? (p.stack ? 2 : 1) : 0;
     const uint32_t a_lbo = p.planes * PATCH_BYTES, a_sbo = PW * 16;
-    const uint32_t nb = p.nsub * 16;  // bytes of one (k-group, plane) slab of a B sub-block
+    const uint32_t nb = p.nsub * 16;  // bytes of one (k-group, plane) slab of the B block
     const uint32_t b_lbo = p.planes * nb, b_sbo = 128;
     const uint64_t a_desc0 = make_smem_desc(0, a_lbo, a_sbo), b_desc0 = make_smem_desc(0, b_lbo, b_sbo);
     // descriptor start-address increments (16-byte units)
     const uint32_t a_kstep = (2 * a_lbo) >> 4, b_kstep = (2 * b_lbo) >> 4;
-    const uint32_t a_lo16 = PATCH_BYTES >> 4, b_lo16 = nb >> 4, b_sub16 = (uint32_t)p.b_sub_bytes >> 4;
+    const uint32_t a_lo16 = PATCH_BYTES >> 4, b_lo16 = nb >> 4;
     const uint32_t b_slot16 = (uint32_t)p.b_slot_bytes >> 4;
     const int ksteps = p.kc >> 4;
-    const bool split = p.planes == 2;
     const uint32_t b_region16 = smem_u32(b_smem) >> 4;
+    const bool leader = elect_one_sync() != 0;
+    // issue list: entry (chunk ch, j-th valid tap) = {A offset, B slab (resident mode), accumulator column, accumulate}
+    for (int ch = lane; ch < p.nchunks; ch += 32) {
+      const int cph = (ch * p.kc) / p.cin_w;
+      int j = 0;
+      uint32_t seen = 0;
+      for (int e = 0; e < p.ntaps; ++e) {
+        if (p.taps[e].in_phase >= 0 && p.taps[e].in_phase != cph) continue;
+        const uint32_t q = (uint32_t)p.taps[e].phase;
+        const uint32_t first = (ch == 0 && !((seen >> q) & 1u)) ? 1u : 0u;
+        seen |= 1u << q;
+        const int idx = ch * p.tpc + j;
+        issue_list[idx] = make_uint4((uint32_t)p.taps[e].a_off, b_region16 + (uint32_t)idx * b_slot16,
+                                     q * (uint32_t)p.acc_cols, first ? 0u : 1u);
+        ++j;
+      }
+    }
+    __syncwarp();
     uint32_t a_slot = 0, a_ph = 0, b_slot = 0, b_ph = 0, acc = 0, acc_ph = 0;
     if (p.resident) {
       mbar_wait(&b_full[0], 0);
       tc_fence_after();
     }
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
       mbar_wait(&tm_empty[acc], acc_ph ^ 1);
       tc_fence_after();
-      const uint32_t d_base = tmem_base + acc * p.ntile;
-      uint32_t started = 0;
-      uint32_t res16 = b_region16;   // resident mode: running slot address, same (chunk, tap) order as the loader
+      const uint32_t d_base = tmem_base + acc * p.tm_stride;
       for (int ch = 0; ch < p.nchunks; ++ch) {
         mbar_wait(&a_full[a_slot], a_ph);
         tc_fence_after();
         const uint32_t a_base16 = smem_u32(a_smem + a_slot * p.a_slot_bytes) >> 4;
-        const int cph = (ch * p.kc) / p.cin_w;
-        if (p.resident) {
-          // one straight run of MMAs per (tile, chunk): no per-tap barrier traffic
-          uint32_t nvalid = 0;
-          for (int e = 0; e < p.ntaps; ++e) nvalid += (p.taps[e].in_phase < 0 || p.taps[e].in_phase == cph) ? 1u : 0u;
-          if (elect_one_sync()) {
-            uint32_t b16 = res16;
-            for (int e = 0; e < p.ntaps; ++e) {
-              if (p.taps[e].in_phase >= 0 && p.taps[e].in_phase != cph) continue;
-              const int q = p.taps[e].phase;
-              const uint64_t da = a_desc0 + (a_base16 + (uint32_t)p.taps[e].a_off);
-              for (int s = 0; s < nsubs; ++s) {
-                const uint32_t acc_flag = (started >> (q * 2 + s)) & 1u;
-                if (split)
-                  issue_tap<true>(d_base + q * p.cw + s * p.nsub, da, b_desc0 + (b16 + s * b_sub16), idesc, ksteps,
-                                  a_kstep, b_kstep, a_lo16, b_lo16, acc_flag);
-                else
-                  issue_tap<false>(d_base + q * p.cw + s * p.nsub, da, b_desc0 + (b16 + s * b_sub16), idesc, ksteps,
-                                   a_kstep, b_kstep, a_lo16, b_lo16, acc_flag);
-                started |= 1u << (q * 2 + s);
-              }
-              b16 += b_slot16;
-            }
-            tc_commit(&a_empty[a_slot]);
-          }
-          __syncwarp();
-          res16 += nvalid * b_slot16;
-          started = 0xffu;  // (uniform copy of the elected lane's bookkeeping: every sub-accumulator is started)
-        } else {
-          for (int e = 0; e < p.ntaps; ++e) {
-            const int q = p.taps[e].phase - t.p0;
-            if (q < 0 || q >= p.np) continue;
-            if (p.taps[e].in_phase >= 0 && p.taps[e].in_phase != cph) continue;
+        const uint4* ent = issue_list + ch * p.tpc;
+        for (int j = 0; j < p.tpc; ++j) {
+          const uint4 e4 = ent[j];
+          uint32_t b16 = e4.y;
+          if (!p.resident) {
             mbar_wait(&b_full[b_slot], b_ph);
             tc_fence_after();
-            const uint32_t b_base16 = smem_u32(b_smem + b_slot * p.b_slot_bytes) >> 4;
-            const uint64_t da = a_desc0 + (a_base16 + (uint32_t)p.taps[e].a_off);
-            if (elect_one_sync()) {
-              for (int s = 0; s < nsubs; ++s) {
-                const uint32_t acc_flag = (started >> (q * 2 + s)) & 1u;
-                if (split)
-                  issue_tap<true>(d_base + q * p.cw + s * p.nsub, da, b_desc0 + (b_base16 + s * b_sub16), idesc,
-                                  ksteps, a_kstep, b_kstep, a_lo16, b_lo16, acc_flag);
-                else
-                  issue_tap<false>(d_base + q * p.cw + s * p.nsub, da, b_desc0 + (b_base16 + s * b_sub16), idesc,
-                                   ksteps, a_kstep, b_kstep, a_lo16, b_lo16, acc_flag);
-              }
-              tc_commit(&b_empty[b_slot]);
-            }
-            __syncwarp();
-            for (int s = 0; s < nsubs; ++s) started |= 1u << (q * 2 + s);
+            b16 = b_region16 + b_slot * b_slot16;
+          }
+          if (leader)
+            issue_tap_mode(mma_mode, d_base + e4.z, a_desc0 + (a_base16 + e4.x), b_desc0 + b16, idesc, idesc2, ksteps,
+                           a_kstep, b_kstep, a_lo16, b_lo16, e4.w);
+          if (!p.resident) {
+            if (leader) tc_commit(&b_empty[b_slot]);
             if (++b_slot == (uint32_t)p.b_slots) { b_slot = 0; b_ph ^= 1; }
           }
-          if (elect_one_sync()) tc_commit(&a_empty[a_slot]);
-          __syncwarp();
         }
+        if (leader) tc_commit(&a_empty[a_slot]);
         if (++a_slot == (uint32_t)p.a_slots) { a_slot = 0; a_ph ^= 1; }
       }
-      if (elect_one_sync()) tc_commit(&tm_full[acc]);
+      if (leader) tc_commit(&tm_full[acc]);
       __syncwarp();
       if (++acc == (uint32_t)p.acc_stages) { acc = 0; acc_ph ^= 1; }
     }
@@ -563,10 +787,21 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int m = quarter * 32 + lane;
     const int ty = m >> 3, tx = m & 7;
+    const int et = (int)threadIdx.x - 64;   // 0..127 among the epilogue threads
+    int cur_n = -1, cur_co0 = -1;
     uint32_t acc = 0, acc_ph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
-      PixelCtx px;
+      if (EPI == 0 && (t.n != cur_n || t.co0 != cur_co0)) {
+        // per-(sample, N tile) parameter table: one cooperative reload when the sample changes (tiles are visited
+        // in sample order), then every per-channel parameter is a broadcast LDS.128 instead of a global load
+        epi_bar_sync();
+        epi_fill_table(p, epi_tab, t.n, t.co0, et);
+        epi_bar_sync();
+        cur_n = t.n;
+        cur_co0 = t.co0;
+      }
+      EpiPix px;
       px.n = t.n;
       px.y = t.y0 + ty;
       px.x = t.x0 + tx;
@@ -577,16 +812,34 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       float rgb[3] = {0.f, 0.f, 0.f};
       mbar_wait_relaxed(&tm_full[acc], acc_ph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * p.ntile + ((uint32_t)(quarter * 32) << 16);
+      const uint32_t taddr = tmem_base + acc * p.tm_stride + ((uint32_t)(quarter * 32) << 16);
       for (int q = 0; q < p.np; ++q) {
-        for (int c = 0; c < p.cw; c += 16) {
-          float v[16];
-          __syncwarp();  // .sync.aligned TMEM load needs a converged warp (the epilogue body diverges on px.valid)
-          tc_ld16(taddr + q * p.cw + c, v);
-          if (EPI == 0)
-            epi_pointwise16(p, px, t.co0 + c, v, rgb);
-          else
-            epi_rawup16(p, px.n, px.y, px.x, px.valid, t.p0 + q, t.co0 + c, v);
+        const uint32_t tq = taddr + q * p.acc_cols;
+        // software pipeline over 16-column groups: the TMEM load of group g+1 is in flight while group g is processed
+        // (stacked mode: the lo-product half `sx` is folded into the group right after its wait, then reloaded)
+        uint32_t r0[16], r1[16], sx[16];
+        tm_ld16_issue(tq, r0);
+        if (p.stack) tm_ld16_issue(tq + p.cw, sx);
+        for (int c = 0; c < p.cw; c += 32) {
+          const bool more = c + 16 < p.cw;
+          tm_ld16_wait(r0);
+          if (more) tm_ld16_issue(tq + c + 16, r1);
+          if (p.stack) {
+            tm_ld16_wait(sx);   // (waits for every outstanding load; r1 is simply complete early)
+            epi_fold16(r0, sx);
+            if (more) tm_ld16_issue(tq + p.cw + c + 16, sx);
+          }
+          epi_group16<EPI>(p, epi_tab, px, t.co0, t.p0, q, c, r0, rgb);
+          if (!more) break;
+          const bool more2 = c + 32 < p.cw;
+          tm_ld16_wait(r1);
+          if (more2) tm_ld16_issue(tq + c + 32, r0);
+          if (p.stack) {
+            tm_ld16_wait(sx);
+            epi_fold16(r1, sx);
+            if (more2) tm_ld16_issue(tq + p.cw + c + 32, sx);
+          }
+          epi_group16<EPI>(p, epi_tab, px, t.co0, t.p0, q, c + 16, r1, rgb);
         }
       }
       tc_fence_before();
@@ -844,16 +1097,22 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
   p.n_ntiles = ntot / p.ntile;
   DGE_REQUIRE(p.n_ntiles * p.ntile == ntot, "conv: cannot tile cout=%d", p.Cout);
   DGE_REQUIRE(p.np * (p.cw / p.nsub) <= 8 && p.cw / p.nsub <= 2, "conv: internal sub-tile bookkeeping overflow");
-  p.acc_stages = (2 * p.ntile <= 512) ? 2 : 1;   // single-buffered accumulator when the tile fills TMEM
+  // hi|lo stacking on N pays while the MMA is bound by its A-operand read (2*cw <= 96 columns)
+  p.stack = (p.planes == 2 && p.cw <= 48 && p.np * 2 * p.cw <= 512) ? 1 : 0;
+  p.acc_cols = p.cw * (p.stack ? 2 : 1);
+  p.tm_stride = p.np * p.acc_cols;
+  p.acc_stages = (2 * p.tm_stride <= 512) ? 2 : 1;   // single-buffered accumulator when the tile fills TMEM
   int cols = 32;
-  while (cols < p.acc_stages * p.ntile) cols *= 2;
+  while (cols < p.acc_stages * p.tm_stride) cols *= 2;
   DGE_REQUIRE(cols <= 512, "conv: TMEM overflow");
   p.tmem_cols = cols;
   const int tmem_occ = 512 / p.tmem_cols;
   // K chunking + shared-memory plan
   const int smem_cap = 224 * 1024;
-  const int bar_bytes = (BAR_COUNT + 2) * 8;
   const int taps_per_chunk = (a->kind == DGE_CONV_DOWN4X4S2) ? 4 : p.ntaps;
+  p.tpc = taps_per_chunk;
+  // barriers + TMEM slot, epilogue parameter table, MMA issue list (<= Cin/16 chunks x tpc entries x 16 B)
+  const int bar_bytes = (BAR_COUNT + 2) * 8 + EPI_TAB_BYTES + p.Cin * taps_per_chunk;
   const long long b_all = (long long)taps_per_chunk * (p.Cin / 8) * p.planes * p.cw * 16;   // every (tap, channel) pair in use
   p.resident = 0;
   if (p.n_ntiles == 1) {
@@ -896,6 +1155,11 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
   smem = (size_t)p.a_slots * p.a_slot_bytes + (size_t)p.b_region_bytes + bar_bytes;
   if (smem > 113 * 1024) max_occ = 1;
   p.total_tiles = p.N * p.tiles_x * p.tiles_y * p.n_ntiles;
+  DGE_REQUIRE((long long)p.N * p.tiles_x * p.tiles_y * p.n_ntiles < (1ll << 31), "conv: too many tiles");
+  p.div_ntiles = make_fast_div((uint32_t)p.n_ntiles);
+  p.div_per_img = make_fast_div((uint32_t)(p.tiles_x * p.tiles_y));
+  p.div_tiles_x = make_fast_div((uint32_t)p.tiles_x);
+  p.act_mode = (a->slope == 1.f) ? 0 : ((a->slope >= 0.f && a->slope <= 1.f) ? 1 : 2);
 
   p.demod = a->demod; p.noise = a->noise; p.noise_bstride = a->noise_bstride; p.noise_w = a->noise_w;
   p.noise_scalar = a->noise_scalar; p.bias = a->bias; p.slope = a->slope; p.gain = a->gain;
