@@ -61,6 +61,13 @@ static FastDiv make_fast_div(uint32_t d) {
 constexpr int EPI_TAB_COLS = 256;                      // widest CTA column block
 constexpr int EPI_TAB_BYTES = 7 * EPI_TAB_COLS * 4;    // A, B, NW, S, RGB[3] rows of the per-(sample, N tile) table
 
+struct IssueEnt {
+  int16_t a_off;   // patch pixel offset of the tap (16-byte units into the A slab)
+  int16_t dcol;    // accumulator column block of the tap's output phase
+  int16_t first;   // 1: first tap of its phase in issue order (clears the accumulator on the first K chunk)
+  int16_t w_tap;
+};
+
 struct ConvKParams {
   int N, H, W;             // input dims
   int dom_h, dom_w;        // tile domain (H,W) or (H+1,W+1) for the transposed conv
@@ -77,6 +84,8 @@ struct ConvKParams {
   int a_slot_bytes, b_slot_bytes, b_sub_bytes, b_slots;
   int a_slots, b_region_bytes, resident, acc_stages, b_rb;
   int tmem_cols;
+  IssueEnt ilist[16];      // issue order: [input phase (space-to-depth conv only)][tpc]
+  int n_cph;               // input phases in ilist (1, or 4 for the space-to-depth conv)
   int tpc;                 // taps issued per K chunk (ntaps, or 4 for the space-to-depth conv)
   int stack;               // 1: hi|lo weight planes stacked on N (A_hi x [B_hi|B_lo] + A_lo x B_hi: 2 MMAs instead of 3)
   int acc_cols;            // TMEM columns of one phase block = cw * (stack ? 2 : 1)
@@ -108,6 +117,18 @@ struct ConvKParams {
   const void* x;
   const void* wpk;
 };
+
+// role timing (experiments only: `make exp` builds tools/_exp/libdge_exp.so with -DDGE_ROLE_TIMING)
+#ifdef DGE_ROLE_TIMING
+__device__ unsigned long long g_role_cycles[16];
+#define ROLE_T0() long long _rt0 = clock64()
+#define ROLE_ACC(var) do { long long _t = clock64(); (var) += _t - _rt0; _rt0 = _t; } while (0)
+#define ROLE_FLUSH(slot, var) do { if (lane == 0) atomicAdd(&g_role_cycles[slot], (unsigned long long)(var)); } while (0)
+#else
+#define ROLE_T0() do {} while (0)
+#define ROLE_ACC(var) do {} while (0)
+#define ROLE_FLUSH(slot, var) do {} while (0)
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -576,36 +597,156 @@ constexpr int BAR_A_FULL = 0, BAR_A_EMPTY = MAX_A_SLOTS, BAR_TM_FULL = 2 * MAX_A
 //           of one k-group are contiguous in smem) + A_lo x B_hi -- 2 MMAs per K-step.  For cw <= 32 an MMA is bound
 //           by the 4 KB A-operand read from shared memory (32 clk) whatever N is, so this is 1.5x fewer tensor-pipe
 //           cycles; the epilogue adds the two column halves.
+//   KSTEPS > 0 unrolls the K loop (straight-line issue); 0 = runtime count.
+struct IssueConsts {
+  uint32_t idesc, idesc2, a_kstep, b_kstep, a_lo16, b_lo16;
+  int ksteps;
+};
 template <int MODE>
-__device__ __forceinline__ void issue_tap(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t idesc2,
-                                          int ksteps, uint32_t a_kstep, uint32_t b_kstep, uint32_t a_lo16,
-                                          uint32_t b_lo16, uint32_t accumulate) {
-#pragma unroll 1
-  for (int k = 0; k < ksteps; ++k) {
-    if (MODE == 2) {
-      tc_mma_bf16(d, da, db, idesc2, accumulate);
-      tc_mma_bf16(d, da + a_lo16, db, idesc, 1u);
-    } else {
-      tc_mma_bf16(d, da, db, idesc, accumulate);
-      if (MODE == 1) {
-        tc_mma_bf16(d, da, db + b_lo16, idesc, 1u);
-        tc_mma_bf16(d, da + a_lo16, db, idesc, 1u);
-      }
+__device__ __forceinline__ void issue_kstep(uint32_t d, uint64_t da, uint64_t db, const IssueConsts& c,
+                                            uint32_t accumulate) {
+  if (MODE == 2) {
+    tc_mma_bf16(d, da, db, c.idesc2, accumulate);
+    tc_mma_bf16(d, da + c.a_lo16, db, c.idesc, 1u);
+  } else {
+    tc_mma_bf16(d, da, db, c.idesc, accumulate);
+    if (MODE == 1) {
+      tc_mma_bf16(d, da, db + c.b_lo16, c.idesc, 1u);
+      tc_mma_bf16(d, da + c.a_lo16, db, c.idesc, 1u);
     }
-    accumulate = 1u;
-    da += a_kstep;
-    db += b_kstep;
   }
 }
-__device__ __forceinline__ void issue_tap_mode(int mode, uint32_t d, uint64_t da, uint64_t db, uint32_t idesc,
-                                               uint32_t idesc2, int ksteps, uint32_t a_kstep, uint32_t b_kstep,
-                                               uint32_t a_lo16, uint32_t b_lo16, uint32_t accumulate) {
-  if (mode == 2)
-    issue_tap<2>(d, da, db, idesc, idesc2, ksteps, a_kstep, b_kstep, a_lo16, b_lo16, accumulate);
-  else if (mode == 1)
-    issue_tap<1>(d, da, db, idesc, idesc2, ksteps, a_kstep, b_kstep, a_lo16, b_lo16, accumulate);
-  else
-    issue_tap<0>(d, da, db, idesc, idesc2, ksteps, a_kstep, b_kstep, a_lo16, b_lo16, accumulate);
+template <int MODE, int KSTEPS>
+__device__ __forceinline__ void issue_tap(uint32_t d, uint64_t da, uint64_t db, const IssueConsts& c,
+                                          uint32_t accumulate) {
+  if (KSTEPS > 0) {
+#pragma unroll
+    for (int k = 0; k < KSTEPS; ++k)
+      issue_kstep<MODE>(d, da + (uint32_t)k * c.a_kstep, db + (uint32_t)k * c.b_kstep, c, k == 0 ? accumulate : 1u);
+  } else {
+#pragma unroll 1
+    for (int k = 0; k < c.ksteps; ++k) {
+      issue_kstep<MODE>(d, da, db, c, accumulate);
+      accumulate = 1u;
+      da += c.a_kstep;
+      db += c.b_kstep;
+    }
+  }
+}
+
+// per-CTA barrier / shared-memory handles of the MMA role
+struct MmaBars {
+  uint64_t *a_full, *a_empty, *b_full, *b_empty, *tm_full, *tm_empty;
+  uint32_t a_smem16, b_region16, a_slot16, b_slot16, tm_base;
+};
+
+// The MMA role's tile loop.  A single warp issues every MMA of the CTA, and a taken branch costs it ~25 cycles, so for
+// the 16/32-channel layers (18..54 small MMAs per tile) the issue path -- not the tensor pipe -- is the critical path
+// unless the per-chunk code is straight-line: TPC (taps per chunk) and KSTEPS > 0 unroll everything between two
+// barrier waits; all operands derive from kernel parameters and uniform counters.  TPC == 0 / KSTEPS == 0 are the
+// generic runtime-loop forms.
+template <int MODE, bool RESIDENT, int TPC, int KSTEPS>
+__device__ __forceinline__ void mma_tiles(const ConvKParams& p, const MmaBars& m, const IssueConsts& ic,
+                                          uint64_t a_desc0, uint64_t b_desc0) {
+  uint32_t a_slot = 0, a_ph = 0, b_slot = 0, b_ph = 0, acc = 0, acc_ph = 0;
+  [[maybe_unused]] long long rt_tm = 0, rt_a = 0, rt_issue = 0;
+  [[maybe_unused]] const int lane = threadIdx.x & 31;
+  const int tpc = TPC > 0 ? TPC : p.tpc;
+  if (RESIDENT) {
+    mbar_wait(&m.b_full[0], 0);
+    tc_fence_after();
+  }
+  ROLE_T0();
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    ROLE_ACC(rt_issue);
+    mbar_wait(&m.tm_empty[acc], acc_ph ^ 1);
+    ROLE_ACC(rt_tm);
+    tc_fence_after();
+    const uint32_t d_base = m.tm_base + acc * p.tm_stride;
+    uint32_t b_res16 = m.b_region16;     // resident mode: slabs in (chunk, tap) issue order
+    for (int ch = 0; ch < p.nchunks; ++ch) {
+      ROLE_ACC(rt_issue);
+      mbar_wait(&m.a_full[a_slot], a_ph);
+      ROLE_ACC(rt_a);
+      tc_fence_after();
+      const uint64_t a_desc = a_desc0 + (m.a_smem16 + a_slot * m.a_slot16);
+      const int l0 = (p.n_cph > 1) ? ((ch * p.kc) / p.cin_w) * tpc : 0;
+      const uint32_t first_chunk = ch == 0 ? 1u : 0u;
+      if (RESIDENT) {
+        if (elect_one_sync()) {
+          if (TPC > 0) {
+#pragma unroll
+            for (int j = 0; j < TPC; ++j) {
+              const IssueEnt ent = p.ilist[l0 + j];
+              issue_tap<MODE, KSTEPS>(d_base + (uint32_t)ent.dcol, a_desc + (uint32_t)ent.a_off,
+                                      b_desc0 + (b_res16 + (uint32_t)j * m.b_slot16), ic,
+                                      (first_chunk & (uint32_t)ent.first) ^ 1u);
+            }
+          } else {
+#pragma unroll 1
+            for (int j = 0; j < tpc; ++j) {
+              const IssueEnt ent = p.ilist[l0 + j];
+              issue_tap<MODE, KSTEPS>(d_base + (uint32_t)ent.dcol, a_desc + (uint32_t)ent.a_off,
+                                      b_desc0 + (b_res16 + (uint32_t)j * m.b_slot16), ic,
+                                      (first_chunk & (uint32_t)ent.first) ^ 1u);
+            }
+          }
+          tc_commit(&m.a_empty[a_slot]);
+        }
+        __syncwarp();
+        b_res16 += (uint32_t)tpc * m.b_slot16;
+      } else {
+#pragma unroll 1
+        for (int j = 0; j < tpc; ++j) {
+          const IssueEnt ent = p.ilist[l0 + j];
+          mbar_wait(&m.b_full[b_slot], b_ph);
+          tc_fence_after();
+          if (elect_one_sync()) {
+            issue_tap<MODE, KSTEPS>(d_base + (uint32_t)ent.dcol, a_desc + (uint32_t)ent.a_off,
+                                    b_desc0 + (m.b_region16 + b_slot * m.b_slot16), ic,
+                                    (first_chunk & (uint32_t)ent.first) ^ 1u);
+            tc_commit(&m.b_empty[b_slot]);
+          }
+          __syncwarp();
+          if (++b_slot == (uint32_t)p.b_slots) { b_slot = 0; b_ph ^= 1; }
+        }
+        if (elect_one_sync()) tc_commit(&m.a_empty[a_slot]);
+        __syncwarp();
+      }
+      if (++a_slot == (uint32_t)p.a_slots) { a_slot = 0; a_ph ^= 1; }
+    }
+    if (elect_one_sync()) tc_commit(&m.tm_full[acc]);
+    __syncwarp();
+    if (++acc == (uint32_t)p.acc_stages) { acc = 0; acc_ph ^= 1; }
+  }
+  ROLE_ACC(rt_issue);
+  ROLE_FLUSH(2, rt_tm);
+  ROLE_FLUSH(3, rt_a);
+  ROLE_FLUSH(4, rt_issue);
+}
+
+// pick the unrolled form for the shapes the hot layers use; everything else runs the generic loops
+template <int MODE, bool RESIDENT>
+__device__ __forceinline__ void mma_dispatch(const ConvKParams& p, const MmaBars& m, const IssueConsts& ic,
+                                             uint64_t a_desc0, uint64_t b_desc0) {
+  const int key = p.tpc * 8 + ic.ksteps;
+  if (RESIDENT) {
+    switch (key) {
+      case 9 * 8 + 1: mma_tiles<MODE, true, 9, 1>(p, m, ic, a_desc0, b_desc0); break;
+      case 9 * 8 + 2: mma_tiles<MODE, true, 9, 2>(p, m, ic, a_desc0, b_desc0); break;
+      case 9 * 8 + 4: mma_tiles<MODE, true, 9, 4>(p, m, ic, a_desc0, b_desc0); break;
+      case 1 * 8 + 1: mma_tiles<MODE, true, 1, 1>(p, m, ic, a_desc0, b_desc0); break;
+      case 1 * 8 + 2: mma_tiles<MODE, true, 1, 2>(p, m, ic, a_desc0, b_desc0); break;
+      case 1 * 8 + 4: mma_tiles<MODE, true, 1, 4>(p, m, ic, a_desc0, b_desc0); break;
+      default: mma_tiles<MODE, true, 0, 0>(p, m, ic, a_desc0, b_desc0); break;
+    }
+  } else {
+    switch (ic.ksteps) {
+      case 2: mma_tiles<MODE, false, 0, 2>(p, m, ic, a_desc0, b_desc0); break;
+      case 4: mma_tiles<MODE, false, 0, 4>(p, m, ic, a_desc0, b_desc0); break;
+      default: mma_tiles<MODE, false, 0, 0>(p, m, ic, a_desc0, b_desc0); break;
+    }
+  }
 }
 
 template <int EPI>  // 0 = pointwise, 1 = raw up
@@ -624,7 +765,6 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* b_empty = bars + BAR_B_EMPTY;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
   float* epi_tab = reinterpret_cast<float*>(bars + BAR_COUNT + 2);   // EPI_TAB_BYTES, 16-byte aligned
-  uint4* issue_list = reinterpret_cast<uint4*>(epi_tab + 7 * EPI_TAB_COLS);   // nchunks * tpc entries
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -679,10 +819,14 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       __syncwarp();
     }
+    [[maybe_unused]] long long rt_wait = 0, rt_work = 0;
+    ROLE_T0();
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       for (int ch = 0; ch < p.nchunks; ++ch) {
+        ROLE_ACC(rt_work);
         mbar_wait(&a_empty[a_slot], a_ph ^ 1);
+        ROLE_ACC(rt_wait);
         if (elect_one_sync()) {
           mbar_arrive_expect_tx(&a_full[a_slot], (uint32_t)p.a_slot_bytes);
           tma_load_4d(a_smem + a_slot * p.a_slot_bytes, &tmA, &a_full[a_slot], 2 * (t.x0 - 1), t.y0 - 1, ch * kc8p,
@@ -709,78 +853,42 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
     }
+    ROLE_ACC(rt_work);
+    ROLE_FLUSH(0, rt_wait);
+    ROLE_FLUSH(1, rt_work);
   } else if (warp == 1) {
     // =================================== MMA issuer ======================================
-    // Warp-uniform control flow; only the tcgen05 instructions are predicated on the elected lane, so descriptors stay
-    // in uniform registers.  The per-(chunk, tap) issue parameters are precomputed once into a shared-memory list:
-    // for 16/32-channel layers a tile is only ~18-54 small MMAs and the issue path, not the tensor pipe, was the
-    // critical path when every tap re-derived its descriptor from the parameter block.
-    const uint32_t idesc = make_idesc_bf16(p.nsub), idesc2 = make_idesc_bf16(2 * p.nsub);
-    const int mma_mode = p.planes == 2 ? (p.stack ? 2 : 1) : 0;
+    // Warp-uniform control flow with elected issue; every MMA operand derives from provably uniform sources (kernel
+    // parameters in the constant bank, uniform counters, a shuffled TMEM base) -- see mma_tiles.
     const uint32_t a_lbo = p.planes * PATCH_BYTES, a_sbo = PW * 16;
     const uint32_t nb = p.nsub * 16;  // bytes of one (k-group, plane) slab of the B block
     const uint32_t b_lbo = p.planes * nb, b_sbo = 128;
     const uint64_t a_desc0 = make_smem_desc(0, a_lbo, a_sbo), b_desc0 = make_smem_desc(0, b_lbo, b_sbo);
-    // descriptor start-address increments (16-byte units)
-    const uint32_t a_kstep = (2 * a_lbo) >> 4, b_kstep = (2 * b_lbo) >> 4;
-    const uint32_t a_lo16 = PATCH_BYTES >> 4, b_lo16 = nb >> 4;
-    const uint32_t b_slot16 = (uint32_t)p.b_slot_bytes >> 4;
-    const int ksteps = p.kc >> 4;
-    const uint32_t b_region16 = smem_u32(b_smem) >> 4;
-    const bool leader = elect_one_sync() != 0;
-    // issue list: entry (chunk ch, j-th valid tap) = {A offset, B slab (resident mode), accumulator column, accumulate}
-    for (int ch = lane; ch < p.nchunks; ch += 32) {
-      const int cph = (ch * p.kc) / p.cin_w;
-      int j = 0;
-      uint32_t seen = 0;
-      for (int e = 0; e < p.ntaps; ++e) {
-        if (p.taps[e].in_phase >= 0 && p.taps[e].in_phase != cph) continue;
-        const uint32_t q = (uint32_t)p.taps[e].phase;
-        const uint32_t first = (ch == 0 && !((seen >> q) & 1u)) ? 1u : 0u;
-        seen |= 1u << q;
-        const int idx = ch * p.tpc + j;
-        issue_list[idx] = make_uint4((uint32_t)p.taps[e].a_off, b_region16 + (uint32_t)idx * b_slot16,
-                                     q * (uint32_t)p.acc_cols, first ? 0u : 1u);
-        ++j;
-      }
-    }
-    __syncwarp();
-    uint32_t a_slot = 0, a_ph = 0, b_slot = 0, b_ph = 0, acc = 0, acc_ph = 0;
+    IssueConsts ic;
+    ic.idesc = make_idesc_bf16(p.nsub);
+    ic.idesc2 = make_idesc_bf16(2 * p.nsub);
+    ic.a_kstep = (2 * a_lbo) >> 4;   // descriptor start-address increments per K step (16-byte units)
+    ic.b_kstep = (2 * b_lbo) >> 4;
+    ic.a_lo16 = PATCH_BYTES >> 4;
+    ic.b_lo16 = nb >> 4;
+    ic.ksteps = p.kc >> 4;
+    MmaBars mb;
+    mb.a_full = a_full; mb.a_empty = a_empty; mb.b_full = b_full; mb.b_empty = b_empty;
+    mb.tm_full = tm_full; mb.tm_empty = tm_empty;
+    mb.a_smem16 = smem_u32(a_smem) >> 4;
+    mb.b_region16 = smem_u32(b_smem) >> 4;
+    mb.a_slot16 = (uint32_t)p.a_slot_bytes >> 4;
+    mb.b_slot16 = (uint32_t)p.b_slot_bytes >> 4;
+    mb.tm_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const int mma_mode = p.planes == 2 ? (p.stack ? 2 : 1) : 0;
     if (p.resident) {
-      mbar_wait(&b_full[0], 0);
-      tc_fence_after();
-    }
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      mbar_wait(&tm_empty[acc], acc_ph ^ 1);
-      tc_fence_after();
-      const uint32_t d_base = tmem_base + acc * p.tm_stride;
-      for (int ch = 0; ch < p.nchunks; ++ch) {
-        mbar_wait(&a_full[a_slot], a_ph);
-        tc_fence_after();
-        const uint32_t a_base16 = smem_u32(a_smem + a_slot * p.a_slot_bytes) >> 4;
-        const uint4* ent = issue_list + ch * p.tpc;
-        for (int j = 0; j < p.tpc; ++j) {
-          const uint4 e4 = ent[j];
-          uint32_t b16 = e4.y;
-          if (!p.resident) {
-            mbar_wait(&b_full[b_slot], b_ph);
-            tc_fence_after();
-            b16 = b_region16 + b_slot * b_slot16;
-          }
-          if (leader)
-            issue_tap_mode(mma_mode, d_base + e4.z, a_desc0 + (a_base16 + e4.x), b_desc0 + b16, idesc, idesc2, ksteps,
-                           a_kstep, b_kstep, a_lo16, b_lo16, e4.w);
-          if (!p.resident) {
-            if (leader) tc_commit(&b_empty[b_slot]);
-            if (++b_slot == (uint32_t)p.b_slots) { b_slot = 0; b_ph ^= 1; }
-          }
-        }
-        if (leader) tc_commit(&a_empty[a_slot]);
-        if (++a_slot == (uint32_t)p.a_slots) { a_slot = 0; a_ph ^= 1; }
-      }
-      if (leader) tc_commit(&tm_full[acc]);
-      __syncwarp();
-      if (++acc == (uint32_t)p.acc_stages) { acc = 0; acc_ph ^= 1; }
+      if (mma_mode == 2) mma_dispatch<2, true>(p, mb, ic, a_desc0, b_desc0);
+      else if (mma_mode == 1) mma_dispatch<1, true>(p, mb, ic, a_desc0, b_desc0);
+      else mma_dispatch<0, true>(p, mb, ic, a_desc0, b_desc0);
+    } else {
+      if (mma_mode == 2) mma_dispatch<2, false>(p, mb, ic, a_desc0, b_desc0);
+      else if (mma_mode == 1) mma_dispatch<1, false>(p, mb, ic, a_desc0, b_desc0);
+      else mma_dispatch<0, false>(p, mb, ic, a_desc0, b_desc0);
     }
   } else {
     // =================================== epilogue ========================================
@@ -790,6 +898,8 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int et = (int)threadIdx.x - 64;   // 0..127 among the epilogue threads
     int cur_n = -1, cur_co0 = -1;
     uint32_t acc = 0, acc_ph = 0;
+    [[maybe_unused]] long long rt_full = 0, rt_proc = 0;
+    ROLE_T0();
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       if (EPI == 0 && (t.n != cur_n || t.co0 != cur_co0)) {
@@ -810,7 +920,9 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (EPI == 0 && p.noise && px.valid)
         px.nz = __ldg(p.noise + (size_t)px.n * p.noise_bstride + (size_t)px.y * p.W + px.x);
       float rgb[3] = {0.f, 0.f, 0.f};
+      ROLE_ACC(rt_proc);
       mbar_wait_relaxed(&tm_full[acc], acc_ph);
+      ROLE_ACC(rt_full);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * p.tm_stride + ((uint32_t)(quarter * 32) << 16);
       for (int q = 0; q < p.np; ++q) {
@@ -851,6 +963,11 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           atomicAdd(p.rgb_out + (((size_t)px.n * 3 + ch) * p.H + px.y) * p.W + px.x, rgb[ch]);
       }
       if (++acc == (uint32_t)p.acc_stages) { acc = 0; acc_ph ^= 1; }
+    }
+    ROLE_ACC(rt_proc);
+    if (warp == 2) {
+      ROLE_FLUSH(5, rt_full);
+      ROLE_FLUSH(6, rt_proc);
     }
   }
 
@@ -1111,8 +1228,25 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
   const int smem_cap = 224 * 1024;
   const int taps_per_chunk = (a->kind == DGE_CONV_DOWN4X4S2) ? 4 : p.ntaps;
   p.tpc = taps_per_chunk;
-  // barriers + TMEM slot, epilogue parameter table, MMA issue list (<= Cin/16 chunks x tpc entries x 16 B)
-  const int bar_bytes = (BAR_COUNT + 2) * 8 + EPI_TAB_BYTES + p.Cin * taps_per_chunk;
+  // issue order of the taps of one K chunk (the TMA producer loads the weight slabs in the same order)
+  p.n_cph = (a->kind == DGE_CONV_DOWN4X4S2) ? 4 : 1;
+  for (int cph = 0; cph < p.n_cph; ++cph) {
+    int j = 0;
+    unsigned seen = 0;
+    for (int e = 0; e < p.ntaps; ++e) {
+      if (p.taps[e].in_phase >= 0 && p.taps[e].in_phase != cph) continue;
+      IssueEnt& ie = p.ilist[cph * p.tpc + j];
+      ie.a_off = p.taps[e].a_off;
+      ie.dcol = (int16_t)(p.taps[e].phase * p.acc_cols);
+      ie.first = (cph == 0 && !((seen >> p.taps[e].phase) & 1u)) ? 1 : 0;
+      ie.w_tap = p.taps[e].w_tap;
+      seen |= 1u << p.taps[e].phase;
+      ++j;
+    }
+    DGE_REQUIRE(j == p.tpc, "conv: internal tap list mismatch");
+  }
+  // barriers + TMEM slot, epilogue parameter table
+  const int bar_bytes = (BAR_COUNT + 2) * 8 + EPI_TAB_BYTES;
   const long long b_all = (long long)taps_per_chunk * (p.Cin / 8) * p.planes * p.cw * 16;   // every (tap, channel) pair in use
   p.resident = 0;
   if (p.n_ntiles == 1) {
@@ -1237,6 +1371,20 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
 }
 
 }  // namespace dge
+
+#ifdef DGE_ROLE_TIMING
+// slots: 0 producer wait a_empty, 1 producer work, 2 MMA wait tm_empty, 3 MMA wait a_full, 4 MMA issue,
+//        5 epilogue (warp 2) wait tm_full, 6 epilogue work   -- cycles summed over CTAs
+extern "C" int dge_exp_role_cycles(unsigned long long* out16, int reset) {
+  cudaDeviceSynchronize();
+  if (out16) cudaMemcpyFromSymbol(out16, dge::g_role_cycles, sizeof(unsigned long long) * 16);
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(dge::g_role_cycles, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 
 extern "C" int dge_conv_forward(const dge_conv_args* a, void* stream) {
   return dge::conv_forward(a, static_cast<cudaStream_t>(stream));

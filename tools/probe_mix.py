@@ -84,4 +84,18 @@ for name, fn in cases:
         fn()
     e1.record()
     torch.cuda.synchronize()
-    print(f"{name:45s} {e0.elapsed_time(e1) / iters:.3f} ms")
+    ms = e0.elapsed_time(e1) / iters
+    print(f"{name:45s} {ms:.3f} ms")
+    L = ops.lib()
+    if hasattr(L, "dge_exp_role_cycles"):      # experiment build only (DGE_LIB_PATH=tools/_exp/libdge_exp.so)
+        import ctypes
+        buf = (ctypes.c_uint64 * 16)()
+        L.dge_exp_role_cycles(None, 1)
+        fn()
+        L.dge_exp_role_cycles(buf, 1)
+        names = ["prod wait a_empty", "prod work", "mma wait tm_empty", "mma wait a_full", "mma issue",
+                 "epi wait tm_full", "epi work"]
+        tot = buf[0] + buf[1]
+        print("    role cycles (sum over CTAs; % of the producer's total): " +
+              ", ".join(f"{nm} {100.0 * buf[i] / max(tot, 1):.0f}%" for i, nm in enumerate(names)) +
+              f"; cycles/CTA ~{tot / 296:.0f} (if 296 CTAs)")
