@@ -25,18 +25,19 @@
 
 namespace dge {
 
-constexpr int TH = 16, TW = 8;            // output tile (pixels); TW=8 -> one UMMA core-matrix row group per tile row
-#ifdef DGE_EXPERIMENT_ALIGNED
-constexpr int PH = TH + 2, PW = 16;       // timing experiment only: 128B-aligned core matrices (wrong results)
-#else
-constexpr int PH = TH + 2, PW = TW + 2;   // halo patch
-#endif
-constexpr int PATCH_BYTES = PH * PW * 16; // one (channel-group, plane) slab of the patch: 2880 B
+// One MMA covers an M block of 16x8 output pixels (BW=8 -> one UMMA core-matrix row group per block row).  A CTA tile is
+// msub = 1, 2 or 4 such blocks (16x8, 16x16, 32x16 pixels) that share one halo patch (tile_h+2) x (tile_w+2): the
+// per-tile fixed costs (barrier round trips, tile decode, parameter checks) amortise over up to 512 pixels, the
+// epilogue overlaps the TMEM load of one block with the arithmetic of the previous one, and the halo overhead drops
+// from 1.41x to 1.20x.
+constexpr int BH = 16, BW = 8;
 constexpr int MAX_B_SLOTS = 8;
-constexpr int NUM_THREADS = 192;          // warp0: TMA, warp1: MMA + TMEM alloc, warps 2..5: epilogue
+constexpr int NUM_EPI_WARPS = 8;          // two warps per TMEM lane quarter; they split a tile's (M block, column group) units
+constexpr int NUM_EPI_THREADS = NUM_EPI_WARPS * 32;
+constexpr int NUM_THREADS = 64 + NUM_EPI_THREADS;   // warp0: TMA, warp1: MMA + TMEM alloc, warps 2..9: epilogue; 1 CTA / SM
 
 struct TapEntry {
-  int16_t a_off;  // patch pixel offset dy*PW+dx of this tap
+  int16_t a_off;  // patch pixel offset dy*pw+dx of this tap
   int16_t w_tap;  // tap index into WPK
   int16_t phase;  // output phase (0 for stride-1 convs, 2*py+px for the transposed conv)
   int16_t in_phase;  // -1: applies to every K chunk; else only to chunks of this input phase (space-to-depth conv)
@@ -84,12 +85,19 @@ struct ConvKParams {
   int a_slot_bytes, b_slot_bytes, b_sub_bytes, b_slots;
   int a_slots, b_region_bytes, resident, acc_stages, b_rb;
   int tmem_cols;
+  int msub;                // M blocks per tile
+  int tile_h, tile_w;      // tile extent in pixels
+  int pw, ph, patch_bytes; // halo patch extent and bytes of one (channel-group, plane) slab
+  int sb_off[4];           // patch pixel offset of M block sb
+  int sb_y[4], sb_x[4];    // pixel offset of M block sb inside the tile
+  int sb_cols;             // TMEM columns of one M block = np * acc_cols
+  int np_shift;            // log2(np)
   IssueEnt ilist[16];      // issue order: [input phase (space-to-depth conv only)][tpc]
   int n_cph;               // input phases in ilist (1, or 4 for the space-to-depth conv)
   int tpc;                 // taps issued per K chunk (ntaps, or 4 for the space-to-depth conv)
   int stack;               // 1: hi|lo weight planes stacked on N (A_hi x [B_hi|B_lo] + A_lo x B_hi: 2 MMAs instead of 3)
   int acc_cols;            // TMEM columns of one phase block = cw * (stack ? 2 : 1)
-  int tm_stride;           // TMEM columns of one accumulator stage = np * acc_cols
+  int tm_stride;           // TMEM columns of one accumulator stage = msub * np * acc_cols
   FastDiv div_ntiles, div_per_img, div_tiles_x;
   int act_mode;            // 0: identity (slope == 1), 1: max(v, v*slope) (0 <= slope <= 1), 2: select form
   // epilogue
@@ -380,8 +388,8 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int tile)
   t.n = (int)fast_div((uint32_t)mt, p.div_per_img);
   const int r = mt - t.n * per_img;
   const int ty = (int)fast_div((uint32_t)r, p.div_tiles_x);
-  t.y0 = ty * TH;
-  t.x0 = (r - ty * p.tiles_x) * TW;
+  t.y0 = ty * p.tile_h;
+  t.x0 = (r - ty * p.tiles_x) * p.tile_w;
   // an N tile holds `np` phases x `cw` channels: channels [nt*cw, (nt+1)*cw) of every phase
   t.p0 = 0;
   t.co0 = t.nt * p.cw;
@@ -402,10 +410,10 @@ struct EpiPix {
   float nz;
 };
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_THREADS) : "memory"); }
 
 __device__ __forceinline__ void epi_fill_table(const ConvKParams& p, float* tab, int n, int co0, int et) {
-  for (int c = et; c < p.cw; c += 128) {
+  for (int c = et; c < p.cw; c += NUM_EPI_THREADS) {
     const int co = co0 + c;
     tab[c] = (p.demod ? __ldg(p.demod + (size_t)n * p.Cout + co) : 1.f) * p.gain;
     tab[EPI_TAB_COLS + c] = (p.bias ? __ldg(p.bias + co) : 0.f) * p.gain;
@@ -458,6 +466,7 @@ __device__ __forceinline__ void epi_fold16(uint32_t* r, const uint32_t* s) {
   for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(s[j]));
 }
 
+// experiment switches (timing only, wrong results): -DDGE_X_NOSTORE / _NORGB / _NOMATH
 template <int EPI>
 __device__ __forceinline__ void epi_group16(const ConvKParams& p, const float* tab, const EpiPix& px, int co0, int p0,
                                             int q, int c, const uint32_t* r, float* rgb) {
@@ -535,6 +544,7 @@ __device__ __forceinline__ void epi_group16(const ConvKParams& p, const float* t
         for (int j = 0; j < 8; ++j) v[8 * g + j] = p.blend_a * sv[j] + p.blend_b * v[8 * g + j];
       }
     }
+#ifndef DGE_X_NORGB
     if (p.rgb_w) {
 #pragma unroll
       for (int ch = 0; ch < 3; ++ch) {
@@ -551,13 +561,18 @@ __device__ __forceinline__ void epi_group16(const ConvKParams& p, const float* t
         rgb[ch] = acc;
       }
     }
+#endif
     const size_t HW = (size_t)H * W, pix = (size_t)px.y * W + px.x;
+#ifdef DGE_X_NOSTORE
+    float xsum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) xsum += v[j];
+    if (xsum != -1.2345e30f) { __syncwarp(); return; }
+#endif
     if (p.out_f32b) {
-      float4* o = reinterpret_cast<float4*>(p.out_f32b) + (((size_t)px.n * C8 + g0) * HW + pix) * 2;
-      o[0] = make_float4(v[0], v[1], v[2], v[3]);
-      o[1] = make_float4(v[4], v[5], v[6], v[7]);
-      o[2 * HW] = make_float4(v[8], v[9], v[10], v[11]);
-      o[2 * HW + 1] = make_float4(v[12], v[13], v[14], v[15]);
+      const size_t o = ((size_t)px.n * C8 + g0) * HW + pix;
+      store8_f32b(p.out_f32b, o, v);
+      store8_f32b(p.out_f32b, o + HW, v + 8);
     }
     if (p.out_nchw) {
 #pragma unroll
@@ -674,21 +689,26 @@ __device__ __forceinline__ void mma_tiles(const ConvKParams& p, const MmaBars& m
       const uint32_t first_chunk = ch == 0 ? 1u : 0u;
       if (RESIDENT) {
         if (elect_one_sync()) {
-          if (TPC > 0) {
-#pragma unroll
-            for (int j = 0; j < TPC; ++j) {
-              const IssueEnt ent = p.ilist[l0 + j];
-              issue_tap<MODE, KSTEPS>(d_base + (uint32_t)ent.dcol, a_desc + (uint32_t)ent.a_off,
-                                      b_desc0 + (b_res16 + (uint32_t)j * m.b_slot16), ic,
-                                      (first_chunk & (uint32_t)ent.first) ^ 1u);
-            }
-          } else {
 #pragma unroll 1
-            for (int j = 0; j < tpc; ++j) {
-              const IssueEnt ent = p.ilist[l0 + j];
-              issue_tap<MODE, KSTEPS>(d_base + (uint32_t)ent.dcol, a_desc + (uint32_t)ent.a_off,
-                                      b_desc0 + (b_res16 + (uint32_t)j * m.b_slot16), ic,
-                                      (first_chunk & (uint32_t)ent.first) ^ 1u);
+          for (int sb = 0; sb < p.msub; ++sb) {
+            const uint64_t a_sb = a_desc + (uint32_t)p.sb_off[sb];
+            const uint32_t d_sb = d_base + (uint32_t)(sb * p.sb_cols);
+            if (TPC > 0) {
+#pragma unroll
+              for (int j = 0; j < TPC; ++j) {
+                const IssueEnt ent = p.ilist[l0 + j];
+                issue_tap<MODE, KSTEPS>(d_sb + (uint32_t)ent.dcol, a_sb + (uint32_t)ent.a_off,
+                                        b_desc0 + (b_res16 + (uint32_t)j * m.b_slot16), ic,
+                                        (first_chunk & (uint32_t)ent.first) ^ 1u);
+              }
+            } else {
+#pragma unroll 1
+              for (int j = 0; j < tpc; ++j) {
+                const IssueEnt ent = p.ilist[l0 + j];
+                issue_tap<MODE, KSTEPS>(d_sb + (uint32_t)ent.dcol, a_sb + (uint32_t)ent.a_off,
+                                        b_desc0 + (b_res16 + (uint32_t)j * m.b_slot16), ic,
+                                        (first_chunk & (uint32_t)ent.first) ^ 1u);
+              }
             }
           }
           tc_commit(&m.a_empty[a_slot]);
@@ -702,9 +722,12 @@ __device__ __forceinline__ void mma_tiles(const ConvKParams& p, const MmaBars& m
           mbar_wait(&m.b_full[b_slot], b_ph);
           tc_fence_after();
           if (elect_one_sync()) {
-            issue_tap<MODE, KSTEPS>(d_base + (uint32_t)ent.dcol, a_desc + (uint32_t)ent.a_off,
-                                    b_desc0 + (m.b_region16 + b_slot * m.b_slot16), ic,
-                                    (first_chunk & (uint32_t)ent.first) ^ 1u);
+#pragma unroll 1
+            for (int sb = 0; sb < p.msub; ++sb)
+              issue_tap<MODE, KSTEPS>(d_base + (uint32_t)(sb * p.sb_cols + ent.dcol),
+                                      a_desc + (uint32_t)(p.sb_off[sb] + ent.a_off),
+                                      b_desc0 + (m.b_region16 + b_slot * m.b_slot16), ic,
+                                      (first_chunk & (uint32_t)ent.first) ^ 1u);
             tc_commit(&m.b_empty[b_slot]);
           }
           __syncwarp();
@@ -750,7 +773,7 @@ __device__ __forceinline__ void mma_dispatch(const ConvKParams& p, const MmaBars
 }
 
 template <int EPI>  // 0 = pointwise, 1 = raw up
-__global__ void __launch_bounds__(NUM_THREADS, 2)
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ ConvKParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -775,7 +798,7 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tm_full[i], 1);
-      mbar_init(&tm_empty[i], 4);
+      mbar_init(&tm_empty[i], NUM_EPI_WARPS);
     }
     for (int i = 0; i < MAX_B_SLOTS; ++i) {
       mbar_init(&b_full[i], 1);
@@ -860,7 +883,7 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // =================================== MMA issuer ======================================
     // Warp-uniform control flow with elected issue; every MMA operand derives from provably uniform sources (kernel
     // parameters in the constant bank, uniform counters, a shuffled TMEM base) -- see mma_tiles.
-    const uint32_t a_lbo = p.planes * PATCH_BYTES, a_sbo = PW * 16;
+    const uint32_t a_lbo = p.planes * p.patch_bytes, a_sbo = p.pw * 16;
     const uint32_t nb = p.nsub * 16;  // bytes of one (k-group, plane) slab of the B block
     const uint32_t b_lbo = p.planes * nb, b_sbo = 128;
     const uint64_t a_desc0 = make_smem_desc(0, a_lbo, a_sbo), b_desc0 = make_smem_desc(0, b_lbo, b_sbo);
@@ -869,7 +892,7 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     ic.idesc2 = make_idesc_bf16(2 * p.nsub);
     ic.a_kstep = (2 * a_lbo) >> 4;   // descriptor start-address increments per K step (16-byte units)
     ic.b_kstep = (2 * b_lbo) >> 4;
-    ic.a_lo16 = PATCH_BYTES >> 4;
+    ic.a_lo16 = (uint32_t)p.patch_bytes >> 4;
     ic.b_lo16 = nb >> 4;
     ic.ksteps = p.kc >> 4;
     MmaBars mb;
@@ -895,11 +918,32 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int m = quarter * 32 + lane;
     const int ty = m >> 3, tx = m & 7;
-    const int et = (int)threadIdx.x - 64;   // 0..127 among the epilogue threads
+    const int et = (int)threadIdx.x - 64;   // index among the epilogue threads
+    const int wg = (warp - 2) >> 2;         // 0 / 1: which half of the tile's units this warp handles
     int cur_n = -1, cur_co0 = -1;
     uint32_t acc = 0, acc_ph = 0;
     [[maybe_unused]] long long rt_full = 0, rt_proc = 0;
     ROLE_T0();
+    const int nsq = p.msub * p.np;                  // (M block, phase) pairs of a tile, each cw columns wide
+    const bool split_sq = nsq >= 2;
+    const int c_step = split_sq ? 16 : 32, sq_step = split_sq ? 2 : 1, c_start = split_sq ? 0 : 16 * wg;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    // The per-pixel noise values are fetched one tile ahead: their global-load latency (L2 / HBM) would otherwise sit
+    // on the per-tile critical path of the epilogue warps.
+    float nz_next[4] = {0.f, 0.f, 0.f, 0.f};
+    auto fetch_noise = [&](int tile_idx) {
+      const TileCoord tn = decode_tile(p, tile_idx);
+#pragma unroll
+      for (int sb = 0; sb < 4; ++sb) {
+        nz_next[sb] = 0.f;
+        if (sb < p.msub) {
+          const int y = tn.y0 + p.sb_y[sb] + ty, x = tn.x0 + p.sb_x[sb] + tx;
+          if (y < p.dom_h && x < p.dom_w)
+            nz_next[sb] = __ldg(p.noise + (size_t)tn.n * p.noise_bstride + (size_t)y * p.W + x);
+        }
+      }
+    };
+    if (EPI == 0 && p.noise && (int)blockIdx.x < p.total_tiles) fetch_noise(blockIdx.x);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       if (EPI == 0 && (t.n != cur_n || t.co0 != cur_co0)) {
@@ -911,57 +955,75 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         cur_n = t.n;
         cur_co0 = t.co0;
       }
-      EpiPix px;
-      px.n = t.n;
-      px.y = t.y0 + ty;
-      px.x = t.x0 + tx;
-      px.valid = (px.y < p.dom_h) && (px.x < p.dom_w);
-      px.nz = 0.f;
-      if (EPI == 0 && p.noise && px.valid)
-        px.nz = __ldg(p.noise + (size_t)px.n * p.noise_bstride + (size_t)px.y * p.W + px.x);
-      float rgb[3] = {0.f, 0.f, 0.f};
+      float nz_cur[4];
+#pragma unroll
+      for (int sb = 0; sb < 4; ++sb) nz_cur[sb] = nz_next[sb];
+      if (EPI == 0 && p.noise && tile + (int)gridDim.x < p.total_tiles) fetch_noise(tile + (int)gridDim.x);
       ROLE_ACC(rt_proc);
       mbar_wait_relaxed(&tm_full[acc], acc_ph);
       ROLE_ACC(rt_full);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * p.tm_stride + ((uint32_t)(quarter * 32) << 16);
-      for (int q = 0; q < p.np; ++q) {
-        const uint32_t tq = taddr + q * p.acc_cols;
-        // software pipeline over 16-column groups: the TMEM load of group g+1 is in flight while group g is processed
-        // (stacked mode: the lo-product half `sx` is folded into the group right after its wait, then reloaded)
-        uint32_t r0[16], r1[16], sx[16];
-        tm_ld16_issue(tq, r0);
-        if (p.stack) tm_ld16_issue(tq + p.cw, sx);
-        for (int c = 0; c < p.cw; c += 32) {
-          const bool more = c + 16 < p.cw;
-          tm_ld16_wait(r0);
-          if (more) tm_ld16_issue(tq + c + 16, r1);
-          if (p.stack) {
-            tm_ld16_wait(sx);   // (waits for every outstanding load; r1 is simply complete early)
-            epi_fold16(r0, sx);
-            if (more) tm_ld16_issue(tq + p.cw + c + 16, sx);
-          }
-          epi_group16<EPI>(p, epi_tab, px, t.co0, t.p0, q, c, r0, rgb);
-          if (!more) break;
-          const bool more2 = c + 32 < p.cw;
-          tm_ld16_wait(r1);
-          if (more2) tm_ld16_issue(tq + c + 32, r0);
-          if (p.stack) {
-            tm_ld16_wait(sx);
-            epi_fold16(r1, sx);
-            if (more2) tm_ld16_issue(tq + p.cw + c + 32, sx);
-          }
-          epi_group16<EPI>(p, epi_tab, px, t.co0, t.p0, q, c + 16, r1, rgb);
+      const uint32_t taddr = lane_base + acc * p.tm_stride;
+      // Units = (M block / phase pair sq, 16-column group c), walked in TMEM column order.  The TMEM load of unit u+1 is
+      // in flight while unit u is processed (also across M blocks: a 16-channel layer has ONE group per block, and the
+      // exposed tcgen05.ld latency was a third of its tile time).  Stacked mode: the lo-product half `sx` is folded
+      // into the group right after its wait, then reloaded.
+      EpiPix px;
+      px.n = t.n;
+      px.y = 0; px.x = 0; px.valid = false; px.nz = 0.f;
+      float rgb[3] = {0.f, 0.f, 0.f};
+      // the two warps of a lane quarter split the units: by (M block, phase) parity when a tile has several, else by
+      // column-group parity
+      int u_sq = split_sq ? wg : 0, u_c = split_sq ? 0 : 16 * wg;
+      int cur_sb = -1;
+      uint32_t r0[16], r1[16], sx[16];
+      const bool any = u_sq < nsq && u_c < p.cw;
+      if (any) {
+        tm_ld16_issue(taddr + u_sq * p.acc_cols + u_c, r0);
+        if (p.stack) tm_ld16_issue(taddr + u_sq * p.acc_cols + u_c + p.cw, sx);
+      }
+      auto step = [&](uint32_t (&bc)[16], uint32_t (&bn)[16]) -> bool {
+        tm_ld16_wait(bc);
+        int n_sq = u_sq, n_c = u_c + c_step;
+        if (n_c >= p.cw) { n_c = c_start; n_sq += sq_step; }
+        const bool n_valid = n_sq < nsq;
+        const uint32_t n_addr = taddr + n_sq * p.acc_cols + n_c;
+        if (n_valid) tm_ld16_issue(n_addr, bn);
+        if (p.stack) {
+          tm_ld16_wait(sx);   // (waits for every outstanding load; bn is simply complete early)
+          epi_fold16(bc, sx);
+          if (n_valid) tm_ld16_issue(n_addr + p.cw, sx);
         }
+        const int q = u_sq & (p.np - 1);
+        const int sb = u_sq >> p.np_shift;
+        if (sb != cur_sb) {                 // first unit of an M block: its pixel
+          cur_sb = sb;
+          px.y = t.y0 + p.sb_y[sb] + ty;
+          px.x = t.x0 + p.sb_x[sb] + tx;
+          px.valid = (px.y < p.dom_h) && (px.x < p.dom_w);
+          px.nz = sb == 0 ? nz_cur[0] : (sb == 1 ? nz_cur[1] : (sb == 2 ? nz_cur[2] : nz_cur[3]));
+        }
+        epi_group16<EPI>(p, epi_tab, px, t.co0, t.p0, q, u_c, bc, rgb);
+        if (EPI == 0 && p.rgb_w && (!n_valid || (n_sq >> p.np_shift) != sb)) {   // last unit of an M block
+          if (px.valid) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch)
+              atomicAdd(p.rgb_out + (((size_t)px.n * 3 + ch) * p.H + px.y) * p.W + px.x, rgb[ch]);
+          }
+          rgb[0] = rgb[1] = rgb[2] = 0.f;
+          __syncwarp();
+        }
+        u_sq = n_sq;
+        u_c = n_c;
+        return n_valid;
+      };
+      while (any) {
+        if (!step(r0, r1)) break;
+        if (!step(r1, r0)) break;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tm_empty[acc]);
-      if (EPI == 0 && p.rgb_w && px.valid) {
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch)
-          atomicAdd(p.rgb_out + (((size_t)px.n * 3 + ch) * p.H + px.y) * p.W + px.x, rgb[ch]);
-      }
       if (++acc == (uint32_t)p.acc_stages) { acc = 0; acc_ph ^= 1; }
     }
     ROLE_ACC(rt_proc);
@@ -1007,7 +1069,7 @@ __global__ void __launch_bounds__(128) conv_checker_kernel(const __grid_constant
         for (int j = 0; j < 16; ++j) v[j] = 0.f;
         for (int e = 0; e < p.ntaps; ++e) {
           if (p.taps[e].phase != t.p0 + q) continue;
-          const int dy = p.taps[e].a_off / PW, dx = p.taps[e].a_off % PW;
+          const int dy = p.taps[e].a_off / p.pw, dx = p.taps[e].a_off % p.pw;
           const int iy = px.y - 1 + dy, ix = px.x - 1 + dx;
           if (iy < 0 || iy >= p.H || ix < 0 || ix >= p.W) continue;
           const int C8w = p.cin_w >> 3;
@@ -1136,53 +1198,8 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
   p.P = up ? 4 : 1;
   p.dom_h = up ? a->h + 1 : a->h;
   p.dom_w = up ? a->w + 1 : a->w;
-  p.tiles_x = (p.dom_w + TW - 1) / TW;
-  p.tiles_y = (p.dom_h + TH - 1) / TH;
-  // taps
-  if (a->kind == DGE_CONV_3X3) {
-    p.ntaps = 9;
-    for (int ky = 0; ky < 3; ++ky)
-      for (int kx = 0; kx < 3; ++kx) {
-        TapEntry& t = p.taps[ky * 3 + kx];
-        t.a_off = (int16_t)(ky * PW + kx);
-#ifdef DGE_EXPERIMENT_ALIGNED
-        t.a_off = (int16_t)(ky * PW);
-#endif
-        t.w_tap = (int16_t)(ky * 3 + kx);
-        t.phase = 0;
-      }
-  } else if (a->kind == DGE_CONV_1X1) {
-    p.ntaps = 1;
-    p.taps[0].a_off = (int16_t)(1 * PW + 1);
-    p.taps[0].w_tap = 0;
-    p.taps[0].phase = 0;
-  } else if (a->kind == DGE_CONV_DOWN4X4S2) {
-    // out[Y][X] = sum_{ky,kx<4} W4[ky][kx] * xin[2Y+ky-1][2X+kx-1]; xin is given space-to-depth: channel block
-    // ph = 2*(row parity)+(col parity) holds xin[2y+py][2x+px].  Row 2Y+ky-1 -> parity (ky+1)%2, offset floor((ky-1)/2).
-    DGE_REQUIRE(a->cin % 64 == 0, "conv: DOWN4X4S2 needs cin (=4*C) with C %% 16 == 0");
-    p.cin_w = a->cin / 4;
-    p.ntaps = 16;
-    static const int off[4] = {-1, 0, 0, 1};
-    for (int ky = 0; ky < 4; ++ky)
-      for (int kx = 0; kx < 4; ++kx) {
-        TapEntry& t = p.taps[ky * 4 + kx];
-        t.a_off = (int16_t)((1 + off[ky]) * PW + (1 + off[kx]));
-        t.w_tap = (int16_t)(ky * 4 + kx);
-        t.phase = 0;
-        t.in_phase = (int16_t)(2 * ((ky + 1) % 2) + ((kx + 1) % 2));
-      }
-  } else {
-    // t[2Y+ky'][2X+kx'] += x[Y - a][X - b] * Wf[ky][kx],  ky = ky' + 2a  (ky' = ky%2, a = ky/2)
-    p.ntaps = 9;
-    for (int ky = 0; ky < 3; ++ky)
-      for (int kx = 0; kx < 3; ++kx) {
-        TapEntry& t = p.taps[ky * 3 + kx];
-        const int dy = 1 - ky / 2, dx = 1 - kx / 2;  // patch offset of input pixel (Y - ky/2, X - kx/2)
-        t.a_off = (int16_t)(dy * PW + dx);
-        t.w_tap = (int16_t)(ky * 3 + kx);
-        t.phase = (int16_t)(2 * (ky % 2) + (kx % 2));
-      }
-  }
+  p.tiles_x = (p.dom_w + BW - 1) / BW;   // (base 16x8 blocks; re-derived once the tile shape is chosen)
+  p.tiles_y = (p.dom_h + BH - 1) / BH;
   // N tiling
   const int ntot = p.P * p.Cout;
   if (up) {
@@ -1217,7 +1234,96 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
   // hi|lo stacking on N pays while the MMA is bound by its A-operand read (2*cw <= 96 columns)
   p.stack = (p.planes == 2 && p.cw <= 48 && p.np * 2 * p.cw <= 512) ? 1 : 0;
   p.acc_cols = p.cw * (p.stack ? 2 : 1);
-  p.tm_stride = p.np * p.acc_cols;
+  p.sb_cols = p.np * p.acc_cols;
+  p.np_shift = p.np == 4 ? 2 : 0;
+  const int bar_bytes = (BAR_COUNT + 2) * 8 + EPI_TAB_BYTES;   // barriers + TMEM slot, epilogue parameter table
+  const int smem_cap = 224 * 1024;
+  const int taps_per_chunk = (a->kind == DGE_CONV_DOWN4X4S2) ? 4 : (a->kind == DGE_CONV_1X1 ? 1 : 9);
+  const long long b_all = (long long)taps_per_chunk * (p.Cin / 8) * p.planes * p.cw * 16;   // every (tap, channel) pair in use
+  // tile shape: 4 or 2 M blocks per tile when the weights stay resident next to two (larger) patch slots, both
+  // accumulator stages still fit TMEM, and there are enough tiles to balance the SMs
+  p.msub = 1;
+  if (!(a->flags & DGE_CONV_FLAG_CHECKER) && p.Cout == p.cw) {
+    const int cands[2] = {4, 2};
+    for (int ci = 0; ci < 2 && p.msub == 1; ++ci) {
+      const int ms = cands[ci], th = ms == 4 ? 2 * BH : BH, tw = 2 * BW;
+      if (p.dom_h < th || p.dom_w < tw) continue;
+      if (2 * ms * p.sb_cols > 512) continue;
+      const long long tiles = (long long)p.N * ((p.dom_h + th - 1) / th) * ((p.dom_w + tw - 1) / tw);
+      if (tiles < 4ll * g_num_sms) continue;
+      const long long patch = (long long)(th + 2) * (tw + 2) * 16;
+      const int kcs[3] = {64, 32, 16};
+      for (int i = 0; i < 3; ++i) {
+        const int kc = largest_div(a->kind == DGE_CONV_DOWN4X4S2 ? p.Cin / 4 : p.Cin, kcs[i], 16);
+        if (kc > 0 && b_all + 2 * (kc / 8) * p.planes * patch + bar_bytes <= smem_cap) {
+          p.msub = ms;
+          break;
+        }
+      }
+    }
+  }
+  p.tile_h = p.msub == 4 ? 2 * BH : BH;
+  p.tile_w = p.msub >= 2 ? 2 * BW : BW;
+  p.pw = p.tile_w + 2;
+#ifdef DGE_X_ALIGNED   // timing experiment only (wrong results): 128-byte aligned core matrices for every tap
+  p.pw = p.tile_w + 8;
+#endif
+  p.ph = p.tile_h + 2;
+  p.patch_bytes = p.ph * p.pw * 16;
+  for (int sb = 0; sb < 4; ++sb) {
+    const int sby = p.msub == 4 ? (sb >> 1) : 0, sbx = p.msub == 4 ? (sb & 1) : sb;
+    p.sb_y[sb] = sby * BH;
+    p.sb_x[sb] = sbx * BW;
+    p.sb_off[sb] = sby * BH * p.pw + sbx * BW;
+  }
+  p.tiles_x = (p.dom_w + p.tile_w - 1) / p.tile_w;
+  p.tiles_y = (p.dom_h + p.tile_h - 1) / p.tile_h;
+  // taps (patch offsets need the patch width of the chosen tile shape)
+  if (a->kind == DGE_CONV_3X3) {
+    p.ntaps = 9;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        TapEntry& t = p.taps[ky * 3 + kx];
+        t.a_off = (int16_t)(ky * p.pw + kx);
+#ifdef DGE_X_ALIGNED
+        t.a_off = (int16_t)(ky * p.pw);
+#endif
+        t.w_tap = (int16_t)(ky * 3 + kx);
+        t.phase = 0;
+      }
+  } else if (a->kind == DGE_CONV_1X1) {
+    p.ntaps = 1;
+    p.taps[0].a_off = (int16_t)(1 * p.pw + 1);
+    p.taps[0].w_tap = 0;
+    p.taps[0].phase = 0;
+  } else if (a->kind == DGE_CONV_DOWN4X4S2) {
+    // out[Y][X] = sum_{ky,kx<4} W4[ky][kx] * xin[2Y+ky-1][2X+kx-1]; xin is given space-to-depth: channel block
+    // ph = 2*(row parity)+(col parity) holds xin[2y+py][2x+px].  Row 2Y+ky-1 -> parity (ky+1)%2, offset floor((ky-1)/2).
+    DGE_REQUIRE(a->cin % 64 == 0, "conv: DOWN4X4S2 needs cin (=4*C) with C %% 16 == 0");
+    p.cin_w = a->cin / 4;
+    p.ntaps = 16;
+    static const int off[4] = {-1, 0, 0, 1};
+    for (int ky = 0; ky < 4; ++ky)
+      for (int kx = 0; kx < 4; ++kx) {
+        TapEntry& t = p.taps[ky * 4 + kx];
+        t.a_off = (int16_t)((1 + off[ky]) * p.pw + (1 + off[kx]));
+        t.w_tap = (int16_t)(ky * 4 + kx);
+        t.phase = 0;
+        t.in_phase = (int16_t)(2 * ((ky + 1) % 2) + ((kx + 1) % 2));
+      }
+  } else {
+    // t[2Y+ky'][2X+kx'] += x[Y - a][X - b] * Wf[ky][kx],  ky = ky' + 2a  (ky' = ky%2, a = ky/2)
+    p.ntaps = 9;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        TapEntry& t = p.taps[ky * 3 + kx];
+        const int dy = 1 - ky / 2, dx = 1 - kx / 2;  // patch offset of input pixel (Y - ky/2, X - kx/2)
+        t.a_off = (int16_t)(dy * p.pw + dx);
+        t.w_tap = (int16_t)(ky * 3 + kx);
+        t.phase = (int16_t)(2 * (ky % 2) + (kx % 2));
+      }
+  }
+  p.tm_stride = p.msub * p.sb_cols;
   p.acc_stages = (2 * p.tm_stride <= 512) ? 2 : 1;   // single-buffered accumulator when the tile fills TMEM
   int cols = 32;
   while (cols < p.acc_stages * p.tm_stride) cols *= 2;
@@ -1225,8 +1331,7 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
   p.tmem_cols = cols;
   const int tmem_occ = 512 / p.tmem_cols;
   // K chunking + shared-memory plan
-  const int smem_cap = 224 * 1024;
-  const int taps_per_chunk = (a->kind == DGE_CONV_DOWN4X4S2) ? 4 : p.ntaps;
+  DGE_REQUIRE(taps_per_chunk == ((a->kind == DGE_CONV_DOWN4X4S2) ? 4 : p.ntaps), "conv: internal tap count mismatch");
   p.tpc = taps_per_chunk;
   // issue order of the taps of one K chunk (the TMA producer loads the weight slabs in the same order)
   p.n_cph = (a->kind == DGE_CONV_DOWN4X4S2) ? 4 : 1;
@@ -1245,16 +1350,13 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
     }
     DGE_REQUIRE(j == p.tpc, "conv: internal tap list mismatch");
   }
-  // barriers + TMEM slot, epilogue parameter table
-  const int bar_bytes = (BAR_COUNT + 2) * 8 + EPI_TAB_BYTES;
-  const long long b_all = (long long)taps_per_chunk * (p.Cin / 8) * p.planes * p.cw * 16;   // every (tap, channel) pair in use
   p.resident = 0;
   if (p.n_ntiles == 1) {
     // weights resident in smem for the whole kernel when they fit next to >= 2 patch slots
     const int kcs[3] = {64, 32, 16};
     for (int i = 0; i < 3 && !p.resident; ++i) {
       const int kc = largest_div(p.cin_w, kcs[i], 16);
-      const long long a_slot = (long long)(kc / 8) * p.planes * PATCH_BYTES;
+      const long long a_slot = (long long)(kc / 8) * p.planes * p.patch_bytes;
       if (b_all + 2 * a_slot + bar_bytes <= smem_cap) {
         p.resident = 1;
         p.kc = kc;
@@ -1263,18 +1365,16 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
   }
   if (!p.resident) p.kc = largest_div(p.cin_w, p.cw > 128 ? 32 : 64, 16);
   p.nchunks = p.Cin / p.kc;
-  p.a_slot_bytes = (p.kc / 8) * p.planes * PATCH_BYTES;
+  p.a_slot_bytes = (p.kc / 8) * p.planes * p.patch_bytes;
   p.b_sub_bytes = (p.kc / 8) * p.planes * p.nsub * 16;
   p.b_slot_bytes = (p.cw / p.nsub) * p.b_sub_bytes;
   size_t smem = 0;
-  int max_occ = tmem_occ > 2 ? 2 : tmem_occ;
+  (void)tmem_occ;
+  int max_occ = 1;   // one CTA (2 + 8 warps) per SM
   if (p.resident) {
     p.b_region_bytes = (int)b_all;
     p.b_slots = 1;
-    // prefer two co-resident CTAs (epilogue/mainloop overlap across CTAs) when everything fits in half an SM
-    const int half = 112 * 1024;
-    int budget = (max_occ == 2 && b_all + 2 * p.a_slot_bytes + bar_bytes <= half) ? half : smem_cap;
-    if (budget == smem_cap) max_occ = 1;
+    const int budget = smem_cap;
     p.a_slots = (int)((budget - b_all - bar_bytes) / p.a_slot_bytes);
     if (p.a_slots > MAX_A_SLOTS) p.a_slots = MAX_A_SLOTS;
   } else {
@@ -1328,7 +1428,7 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
     const uint64_t c8p = (uint64_t)(p.Cin / 8) * p.planes;
     uint64_t dims[4] = {(uint64_t)2 * p.W, (uint64_t)p.H, c8p, (uint64_t)p.N};
     uint64_t strides[3] = {(uint64_t)p.W * 16, (uint64_t)p.H * p.W * 16, c8p * p.H * p.W * 16};
-    uint32_t box[4] = {2 * PW, PH, (uint32_t)((p.kc / 8) * p.planes), 1};
+    uint32_t box[4] = {(uint32_t)(2 * p.pw), (uint32_t)p.ph, (uint32_t)((p.kc / 8) * p.planes), 1};
     int r = make_tmap(&tmA, a->x, 4, dims, strides, box);
     if (r) return r;
   }

@@ -71,16 +71,19 @@ __device__ __forceinline__ size_t f32b_idx32(int n, int c8, int y, int x, int C8
   return (((size_t)n * C8 + c8) * H + y) * (size_t)W + x;
 }
 
+// One F32B chunk (8 floats = one 32-byte sector) moves as a single 256-bit access (LDG/STG.E.256, sm_100): half the
+// LSU instructions of two float4 accesses, and a store never leaves a sector half written.
 __device__ __forceinline__ void load8_f32b(const float* base, size_t idx32, float* v) {
-  const float4* p = reinterpret_cast<const float4*>(base) + idx32 * 2;
-  float4 a = __ldg(p), b = __ldg(p + 1);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  const float* p = base + idx32 * 8;
+  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
 }
 __device__ __forceinline__ void store8_f32b(float* base, size_t idx32, const float* v) {
-  float4* p = reinterpret_cast<float4*>(base) + idx32 * 2;
-  p[0] = make_float4(v[0], v[1], v[2], v[3]);
-  p[1] = make_float4(v[4], v[5], v[6], v[7]);
+  float* p = base + idx32 * 8;
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+               "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
 }
 __device__ __forceinline__ void store8_act(void* base, int n, int c8, int y, int x, int C8, int planes, int H, int W,
                                            const float* v) {

@@ -94,7 +94,7 @@ for name, fn in cases:
         fn()
         L.dge_exp_role_cycles(buf, 1)
         names = ["prod wait a_empty", "prod work", "mma wait tm_empty", "mma wait a_full", "mma issue",
-                 "epi wait tm_full", "epi work"]
+                 "epi wait tm_full", "epi head", "epi tmem-ld wait", "epi groups", "epi tail"]
         tot = buf[0] + buf[1]
         print("    role cycles (sum over CTAs; % of the producer's total): " +
               ", ".join(f"{nm} {100.0 * buf[i] / max(tot, 1):.0f}%" for i, nm in enumerate(names)) +
