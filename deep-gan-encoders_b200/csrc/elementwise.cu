@@ -249,83 +249,6 @@ __global__ void k_to_rgb_nchw(const float* __restrict__ x, const float* __restri
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// StyleGAN2 up path: 4x4 FIR over the raw (2H+1)x(2W+1) transposed-conv map, then the layer epilogue.
-//   out[y][x] = sum_{a,b} f[a] f[b] t[y+a-1][x+b-1],  f = [1,3,3,1]/4   (kernel/sum*gain^2 = outer/64*4)
-// ---------------------------------------------------------------------------------------------
-// one thread = one (n, channel group, x) column strip of FIR_R output rows: the horizontal 4-tap pass is done once
-// per input row and kept in a 4-row register ring, so each output costs ~(R+3)/R * 4 chunk loads instead of 16.
-constexpr int FIR_R = 8;
-__global__ void __launch_bounds__(256)
-k_up_fir_epilogue(const float* __restrict__ t, const float* __restrict__ demod, const float* __restrict__ noise,
-                  long long noise_bstride, float noise_scalar, const float* __restrict__ bias, float slope,
-                  float gain, const float* __restrict__ out_scale, void* __restrict__ out_act,
-                  float* __restrict__ out_nchw, int n, int c, int ho, int wo, int planes) {
-  const int C8 = c >> 3, hi = ho + 1, wi = wo + 1;
-  const int strips = (ho + FIR_R - 1) / FIR_R;
-  const size_t total = (size_t)n * C8 * strips * wo;
-  const float f[4] = {0.25f, 0.75f, 0.75f, 0.25f};
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const Idx4 q = decode4(i, C8, strips, wo);  // q.y = strip index
-    const int y0 = q.y * FIR_R;
-    float dm[8], bs[8], sc[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int ch = q.g * 8 + k;
-      dm[k] = demod ? __ldg(demod + (size_t)q.n * c + ch) : 1.f;
-      bs[k] = bias ? __ldg(bias + ch) : 0.f;
-      sc[k] = out_scale ? __ldg(out_scale + (size_t)q.n * c + ch) : 1.f;
-    }
-    float ring[4][8];
-#pragma unroll
-    for (int r = 0; r < FIR_R + 3; ++r) {
-      const int yy = y0 + r - 1;
-      float h[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) h[k] = 0.f;
-      if (yy >= 0 && yy < hi) {
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const int xx = q.x + b - 1;
-          if (xx < 0 || xx >= wi) continue;
-          float v[8];
-          load8_f32b(t, f32b_idx32(q.n, q.g, yy, xx, C8, hi, wi), v);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) h[k] = fmaf(f[b], v[k], h[k]);
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) ring[r & 3][k] = h[k];
-      if (r < 3) continue;
-      const int y = y0 + r - 3;
-      if (y >= ho) continue;
-      float acc[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        // rows y-1 .. y+2 live in ring slots (r-3 .. r) & 3 with taps f[0..3]
-        float v = f[0] * ring[(r - 3) & 3][k] + f[1] * ring[(r - 2) & 3][k] + f[2] * ring[(r - 1) & 3][k] +
-                  f[3] * ring[r & 3][k];
-        acc[k] = v;
-      }
-      const float nz = noise ? __ldg(noise + (size_t)q.n * noise_bstride + (size_t)y * wo + q.x) * noise_scalar : 0.f;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float v = acc[k] * dm[k] + nz + bs[k];
-        acc[k] = (v < 0.f ? v * slope : v) * gain;
-      }
-      if (out_nchw) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) out_nchw[(((size_t)q.n * c + q.g * 8 + k) * ho + y) * wo + q.x] = acc[k];
-      }
-      if (out_act) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] *= sc[k];
-        store8_act(out_act, q.n, q.g, y, q.x, C8, planes, ho, wo, acc);
-      }
-    }
-  }
-}
-
 // skip-branch RGB upsample: zero-insert x2, pad (2,1), 4x4 FIR (f = [1,3,3,1]/4 per axis after the x4 gain):
 //   out[2m]   = (x[m-1] + 3 x[m]) / 4 ,  out[2m+1] = (3 x[m] + x[m+1]) / 4   per axis
 __global__ void k_rgb_init(const float* __restrict__ in, const float* __restrict__ bias, float* __restrict__ out,
@@ -1282,18 +1205,6 @@ int dge_to_rgb_nchw(const float* x, const float* rgb_w, const float* bias, float
                     int w, void* stream) {
   DGE_REQUIRE(x && rgb_w && out && n > 0 && c > 0 && nch > 0 && h > 0 && w > 0, "to_rgb_nchw: bad args");
   LAUNCH_1D(k_to_rgb_nchw, (size_t)n * h * w, stream, x, rgb_w, bias, out, n, c, nch, h * w);
-}
-
-int dge_up_fir_epilogue(const float* raw_up, const float* demod, const float* noise, int64_t noise_bstride,
-                        float noise_scalar, const float* bias, float slope, float gain, const float* out_scale,
-                        void* out_act, float* out_nchw, int n, int c, int h_out, int w_out, int planes, void* stream) {
-  DGE_REQUIRE(raw_up && (out_act || out_nchw), "up_fir_epilogue: null pointer");
-  DGE_REQUIRE(n > 0 && c > 0 && c % 8 == 0 && h_out > 0 && w_out > 0 && h_out % 2 == 0 && w_out % 2 == 0,
-              "up_fir_epilogue: bad dims n=%d c=%d h=%d w=%d", n, c, h_out, w_out);
-  DGE_REQUIRE(!out_act || planes == 1 || planes == 2, "up_fir_epilogue: planes=%d", planes);
-  LAUNCH_1D(k_up_fir_epilogue, (size_t)n * (c / 8) * ((h_out + FIR_R - 1) / FIR_R) * w_out, stream, raw_up, demod, noise,
-            (long long)noise_bstride, noise_scalar, bias, slope, gain, out_scale, out_act, out_nchw, n, c, h_out, w_out,
-            planes);
 }
 
 int dge_rgb_init(const float* img_in, const float* bias, float* img_out, int n, int nch, int h_out, int w_out,

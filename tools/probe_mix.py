@@ -59,7 +59,18 @@ def e_stats_norm(h, c):
     return run
 
 
+def fir_only(h, c):
+    raw = torch.randn(n, c // 8, 2 * h + 1, 2 * h + 1, 8, device=dev)
+    dm, sc = torch.rand(n, c, device=dev) + 0.5, torch.rand(n, c, device=dev) + 0.5
+    bias, noise = torch.randn(c, device=dev), torch.randn(2 * h, 2 * h, device=dev)
+    return lambda: ops.up_fir_epilogue(raw, n, c, 2 * h, 2 * h, demod=dm, noise=noise, noise_scalar=0.3, bias=bias,
+                                       slope=0.2, gain=1.414, out_scale=sc)
+
+
 cases = [
+    ("FIR 32ch -> 1024", fir_only(512, 32)),
+    ("FIR 64ch -> 512", fir_only(256, 64)),
+    ("FIR 512ch -> 64", fir_only(32, 512)),
     ("G conv3x3 32->32 @1024 (+ToRGB)", g_plain(1024, 32)),
     ("G conv3x3 64->64 @512 (+ToRGB)", g_plain(512, 64)),
     ("G conv3x3 128->128 @256 (+ToRGB)", g_plain(256, 128)),
