@@ -122,6 +122,7 @@ struct ConvKParams {
   const float* rgb_w;
   float* rgb_out;
   float* out_raw_up;
+  int out_pool;
   // checker kernel only
   const void* x;
   const void* wpk;
@@ -445,6 +446,24 @@ __device__ __forceinline__ void epi_group16(const ConvKParams& p, const float* t
   } else if (p.act_mode == 2) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = v[j] < 0.f ? v[j] * p.slope : v[j];
+  }
+  if (p.out_pool) {
+    // 2x2 mean across the lanes (x ^ 1 <-> lane ^ 1, y ^ 1 <-> lane ^ 8); the even/even lane stores the pooled pixel
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float sm = v[j] + __shfl_xor_sync(0xffffffffu, v[j], 1);
+      sm += __shfl_xor_sync(0xffffffffu, sm, 8);
+      v[j] = 0.25f * sm;
+    }
+    if (px.valid && !(lane & 9)) {
+      const size_t HWp = (size_t)(H >> 1) * (W >> 1);
+      const size_t o = ((size_t)px.n * C8 + g0) * HWp + (size_t)(px.y >> 1) * (W >> 1) + (px.x >> 1);
+      store8_f32b(p.out_f32b, o, v);
+      store8_f32b(p.out_f32b, o + HWp, v + 8);
+    }
+    __syncwarp();
+    return;
   }
   if (px.valid) {
     if (p.blend_src) {
@@ -1111,6 +1130,9 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
     DGE_REQUIRE(!a->out_act || a->out_planes == 1 || a->out_planes == 2, "conv: out_planes=%d", a->out_planes);
     DGE_REQUIRE(!a->rgb_w == !a->rgb_out, "conv: rgb_w and rgb_out must be given together");
     DGE_REQUIRE(!a->noise_w || a->noise, "conv: noise_w without noise");
+    DGE_REQUIRE(!a->out_pool || (a->out_f32b && !a->out_act && !a->out_nchw && !a->rgb_out && !a->blend_src &&
+                                 a->h % 2 == 0 && a->w % 2 == 0 && !(a->flags & DGE_CONV_FLAG_CHECKER)),
+                "conv: out_pool needs even h/w and out_f32b as the only output (tcgen05 path)");
     DGE_REQUIRE(!a->preact_add || ((a->preact_c == 0 || (a->preact_c >= a->cout && a->preact_c % 8 == 0)) &&
                                    (a->preact_up != 2 || (a->h % 2 == 0 && a->w % 2 == 0))),
                 "conv: bad preact residual shape (preact_c=%d preact_up=%d)", a->preact_c, a->preact_up);
@@ -1331,6 +1353,7 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
   p.blend_src = a->blend_src; p.blend_pool = a->blend_pool; p.blend_a = a->blend_a; p.blend_b = a->blend_b;
   p.out_act = a->out_act; p.out_planes = a->out_planes; p.out_scale = a->out_scale; p.out_f32b = a->out_f32b;
   p.out_nchw = a->out_nchw; p.rgb_w = a->rgb_w; p.rgb_out = a->rgb_out; p.out_raw_up = a->out_raw_up;
+  p.out_pool = a->out_pool ? 1 : 0;
   p.x = a->x; p.wpk = a->wpk;
 
   if (g_num_sms == 0) {

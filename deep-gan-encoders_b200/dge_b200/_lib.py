@@ -35,6 +35,7 @@ class ConvArgs(Structure):
         ("out_raw_up", c_void_p),
         ("preact_add", c_void_p),
         ("preact_c", c_int32), ("preact_up", c_int32),
+        ("out_pool", c_int32),
     ]
 
 

@@ -220,7 +220,7 @@ def pixel_norm(x, eps=1e-8):
 def conv(x, wpk, cout, kind=CONV_3X3, *, demod=None, noise=None, noise_batched=False, noise_w=None,
          noise_scalar=0.0, bias=None, slope=1.0, gain=1.0, blend_src=None, blend_pool=False, blend_a=0.0,
          blend_b=1.0, preact_add=None, preact_up=1, out_act=False, out_planes=None, out_scale=None, out_f32b=False,
-         out_f32b_into=None, out_nchw=False, rgb_w=None, rgb_out=None, checker=False):
+         out_f32b_into=None, out_f32b_pool=False, out_nchw=False, rgb_w=None, rgb_out=None, checker=False):
     """tcgen05 implicit-GEMM conv with fused epilogue (dge_conv_forward). Returns a dict of outputs."""
     assert isinstance(x, Act)
     dev = x.t.device
@@ -266,6 +266,10 @@ def conv(x, wpk, cout, kind=CONV_3X3, *, demod=None, noise=None, noise_batched=F
             o = F32B(x.n, cout, x.h, x.w, dev)
             a.out_f32b = ptr(o.t)
             res["f32b"] = o
+        if out_f32b_pool:                    # 2x2 mean of the epilogue value at half resolution (E.py:78-84)
+            o = F32B(x.n, cout, x.h // 2, x.w // 2, dev)
+            a.out_f32b, a.out_pool = ptr(o.t), 1
+            res["f32b_pool"] = o
         if out_f32b_into is not None:        # write into a caller-provided F32B slice (e.g. one sample of a batch)
             assert out_f32b_into.numel() == x.n * cout * x.h * x.w and out_f32b_into.dtype == torch.float32
             a.out_f32b = ptr(out_f32b_into)

@@ -64,17 +64,19 @@ class BEBlock(nn.Module):
         w2 = ops.dense(style2, self.inver_mod2.weight, self.inver_mod2.bias)      # :67
         if self.has_last_conv:
             y1n, _ = ops.instance_norm(y1, mr2, planes=self.planes)                # :69
-            y2 = ops.conv(y1n, self.conv_2.packed(self.planes), self.outputs, ops.CONV_3X3,
-                          noise=self._noise(n, h, w, dev), noise_batched=True,
-                          noise_w=self.noise_weight_2.detach().view(-1), bias=self.bias_2.detach().view(-1),
-                          slope=0.2, out_f32b=True)['f32b']                        # :72-75
+            # conv_2's output is only ever consumed through avg_pool2d (:76-77, 84): the 2x2 mean is taken in the
+            # conv epilogue, so the full-resolution tensor is never written or re-read
+            y2p = ops.conv(y1n, self.conv_2.packed(self.planes), self.outputs, ops.CONV_3X3,
+                           noise=self._noise(n, h, w, dev), noise_batched=True,
+                           noise_w=self.noise_weight_2.detach().view(-1), bias=self.bias_2.detach().view(-1),
+                           slope=0.2, out_f32b_pool=True)['f32b_pool']             # :72-75 + :76-77
             if self.inputs != self.outputs:
                 rp = ops.avgpool_to_act(x, planes=self.planes)                     # :78
                 out = ops.conv(rp, self.conv_3.packed(self.planes), self.outputs, ops.CONV_1X1,
-                               bias=self.conv_3.scaled_bias(), blend_src=y2, blend_pool=True, blend_a=0.111,
-                               blend_b=0.889, out_f32b=True)['f32b']               # :76-77, 81-84
+                               bias=self.conv_3.scaled_bias(), blend_src=y2p, blend_pool=False, blend_a=0.111,
+                               blend_b=0.889, out_f32b=True)['f32b']               # :81-84
             else:
-                out = ops.blend(y2, x, 0.111, 0.889, pool=True)
+                out = ops.blend(y2p, x, 0.111, 0.889, pool=2)
         else:
             _, y1n = ops.instance_norm(y1, mr2, out_act=False, out_f32b=True)      # :69
             if self.inputs != self.outputs:

@@ -100,6 +100,9 @@ typedef struct dge_conv_args {
   int32_t preact_c;        /* channels of the residual tensor (0 = cout); only the first cout are used (BigGAN
                               GenBlock channel drop, biggan_generator.py:195-197) */
   int32_t preact_up;       /* 2 = the residual is half resolution, read with nearest x2 (:198-199); else 1 */
+  int32_t out_pool;        /* 1: out_f32b is [n][cout/8][h/2][w/2][8] and receives the 2x2 MEAN of the epilogue value
+                              (avg_pool2d(2,2) fused into the producer: model/E/E.py:78-84 only ever reads conv_2's
+                              output pooled).  Needs even h, w; out_f32b must be the only output. */
 } dge_conv_args;
 
 int dge_conv_forward(const dge_conv_args* a, void* stream);

@@ -114,6 +114,26 @@ def test_conv1x1_blend(pool, checker):
     assert _rel(res["f32b"].to_nchw(), ref) < 2e-4
 
 
+@pytest.mark.parametrize("case", [(2, 16, 32, 32, 16), (2, 32, 64, 64, 32), (1, 64, 128, 16, 24)],
+                         ids=lambda c: "n%d_ci%d_co%d_%dx%d" % c)
+def test_conv3x3_pooled_output(case):
+    """out_pool: the epilogue value averaged over 2x2 (avg_pool2d(2,2) fused into the producer, E.py:76-77)."""
+    ops = _setup()
+    n, cin, cout, h, w = case
+    g = torch.Generator(device="cuda").manual_seed(5 + cout)
+    x = torch.randn(n, cin, h, w, device="cuda", generator=g)
+    wt = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / (3.0 * cin ** 0.5)
+    nw = torch.randn(cout, device="cuda", generator=g)
+    bias = torch.randn(cout, device="cuda", generator=g)
+    noise = torch.randn(n, h, w, device="cuda", generator=g)
+    res = ops.conv(ops.nchw_to_act(x), ops.pack_conv_weight(wt), cout, ops.CONV_3X3, noise=noise, noise_batched=True,
+                   noise_w=nw, bias=bias, slope=0.2, out_f32b_pool=True)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x, wt, padding=1) + noise[:, None] * nw[None, :, None, None] + bias[None, :, None, None]
+    ref = F.avg_pool2d(_lrelu(ref, 0.2, 1.0), 2, 2)
+    assert _rel(res["f32b_pool"].to_nchw(), ref) < 2e-4
+
+
 UP_CASES = [(2, 32, 32, 8, 8), (2, 64, 32, 16, 16), (1, 64, 128, 9, 5), (2, 128, 256, 8, 8), (2, 32, 512, 4, 4)]
 
 
