@@ -189,8 +189,9 @@ def run_ours(args):
     pk = peaks()
 
     with torch.no_grad():
-        g = torch.Generator(device=dev).manual_seed(100 + rank)
-        z = torch.randn(BATCH, 512, device=dev, generator=g)
+        from dge_b200 import dist as ddist
+        # the GLOBAL latent batch is drawn from one seed and sliced by rank (SURVEY 8e caveat 3)
+        z = ddist.global_latents(100, BATCH * world, 512, rank, world, device=dev)
         imgs1 = G(z, trunc_psi=0.7, trunc_layers=8, randomize_noise=False)["image"].contiguous()
         imgs1_host = imgs1.cpu().pin_memory()
         out_host = torch.empty((BATCH, 18 + 16, 512), dtype=torch.float32).pin_memory()  # w2 [8,18,512] + const2 [8,512,4,4]
@@ -214,13 +215,7 @@ def run_ours(args):
                 fn()
             e1.record()
             barrier()
-            ms = e0.elapsed_time(e1)
-            if world > 1:
-                import torch.distributed as dist
-                t = torch.tensor([ms], device=dev)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                ms = float(t.item())
-            return ms / steps
+            return ddist.max_over_ranks(e0.elapsed_time(e1), dev) / steps
 
         # ---- device-resident throughput ----------------------------------------------------------
         for _ in range(max(args.warmup, 3)):
