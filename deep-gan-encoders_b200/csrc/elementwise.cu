@@ -455,6 +455,101 @@ __global__ void k_instance_norm_blur(const float* __restrict__ x, const float* _
   }
 }
 
+// instance norm of a 2x2 block of pixels + the 2x2 mean of the RAW input: one pass over x feeds both the conv_1
+// operand (E.py:58) and the residual branch's avg_pool2d (E.py:78).  Thread = one pooled pixel of one channel group.
+__global__ void k_instance_norm_pool(const float* __restrict__ x, const float* __restrict__ mr,
+                                     void* __restrict__ out_act, void* __restrict__ out_pool, int n, int c, int ho,
+                                     int wo, int planes) {
+  const int C8 = c >> 3, h = 2 * ho, w = 2 * wo;
+  const size_t total = (size_t)n * C8 * ho * wo;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const Idx4 q = decode4(i, C8, ho, wo);
+    float m[8], r[8], s[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const size_t o = ((size_t)q.n * c + q.g * 8 + k) * 2;
+      m[k] = __ldg(mr + o);
+      r[k] = __ldg(mr + o + 1);
+      s[k] = 0.f;
+    }
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        float v[8];
+        load8_f32b(x, f32b_idx32(q.n, q.g, 2 * q.y + dy, 2 * q.x + dx, C8, h, w), v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          s[k] += v[k];
+          v[k] = (v[k] - m[k]) * r[k];
+        }
+        store8_act(out_act, q.n, q.g, 2 * q.y + dy, 2 * q.x + dx, C8, planes, h, w, v);
+      }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] *= 0.25f;
+    store8_act(out_pool, q.n, q.g, q.y, q.x, C8, planes, ho, wo, s);
+  }
+}
+
+// FromRGB (net.py:231-240) that also accumulates the per-(sample, channel) sum and sum of squares of its OUTPUT
+// (the first block's instance statistics, E.py:51-53,58) -- saves one full read of the 1024^2 feature map.
+// grid (blocks, n); C8 channel groups (c <= 32).  fp32 partials over a thread's few pixels, fp64 across threads.
+template <int C8T>
+__global__ void __launch_bounds__(256)
+k_from_rgb_stats(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ b,
+                 float* __restrict__ out, double* __restrict__ scratch, int cimg, int h, int wd, float slope) {
+  constexpr int C = C8T * 8;
+  __shared__ float sw[C * 4 + C];
+  __shared__ double red[8][2 * C];
+  for (int i = threadIdx.x; i < C * cimg; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sw[C * cimg + i] = b ? b[i] : 0.f;
+  __syncthreads();
+  const int bn = blockIdx.y;
+  const size_t hw = (size_t)h * wd;
+  float s1[C], s2[C];
+#pragma unroll
+  for (int k = 0; k < C; ++k) s1[k] = s2[k] = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < hw; i += (size_t)gridDim.x * blockDim.x) {
+    float px[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int ci = 0; ci < cimg && ci < 4; ++ci) px[ci] = img[((size_t)bn * cimg + ci) * hw + i];
+#pragma unroll
+    for (int g = 0; g < C8T; ++g) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int ch = g * 8 + k;
+        float a = sw[C * cimg + ch];
+        for (int ci = 0; ci < cimg && ci < 4; ++ci) a = fmaf(px[ci], sw[ch * cimg + ci], a);
+        v[k] = a < 0.f ? a * slope : a;
+        s1[ch] += v[k];
+        s2[ch] = fmaf(v[k], v[k], s2[ch]);
+      }
+      store8_f32b(out, ((size_t)bn * C8T + g) * hw + i, v);
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < C; ++k) {
+    // fp32 tree over the warp (512 pixels in all), fp64 from there on
+    float a = s1[k], q = s2[k];
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, off);
+      q += __shfl_xor_sync(0xffffffffu, q, off);
+    }
+    if (lane == 0) {
+      red[warp][2 * k] = (double)a;
+      red[warp][2 * k + 1] = (double)q;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * C) {
+    double t = 0.0;
+    for (int wv = 0; wv < 8; ++wv) t += red[wv][threadIdx.x];
+    atomicAdd(&scratch[(size_t)bn * 2 * C + threadIdx.x], t);   // [n][c][2] like k_instance_stats_partial
+  }
+}
+
 // x: F32B at (2*ho, 2*wo) -> ACT at (ho, wo)
 __global__ void k_avgpool_to_act(const float* __restrict__ x, void* __restrict__ out, int n, int c, int ho, int wo,
                                  int planes) {
@@ -1274,6 +1369,44 @@ int dge_instance_norm_blur(const float* x, const float* mean_rstd, void* out_act
   DGE_REQUIRE(planes == 1 || planes == 2, "instance_norm_blur: planes=%d", planes);
   DGE_REQUIRE(!s2d || (h % 2 == 0 && w % 2 == 0), "instance_norm_blur: space-to-depth needs even h, w");
   LAUNCH_1D(k_instance_norm_blur, (size_t)n * (c / 8) * h * w, stream, x, mean_rstd, out_act, s2d, n, c, h, w, planes);
+}
+
+int dge_instance_norm_pool(const float* x, const float* mean_rstd, void* out_act, void* out_pool_act, int n, int c, int h,
+                           int w, int planes, void* stream) {
+  DGE_REQUIRE(x && mean_rstd && out_act && out_pool_act, "instance_norm_pool: null pointer");
+  REQ_NCHW("instance_norm_pool");
+  DGE_REQUIRE(h % 2 == 0 && w % 2 == 0, "instance_norm_pool: odd input size %dx%d", h, w);
+  DGE_REQUIRE(planes == 1 || planes == 2, "instance_norm_pool: planes=%d", planes);
+  LAUNCH_1D(k_instance_norm_pool, (size_t)n * (c / 8) * (h / 2) * (w / 2), stream, x, mean_rstd, out_act, out_pool_act, n,
+            c, h / 2, w / 2, planes);
+}
+
+int dge_from_rgb_stats(const float* img, const float* w, const float* b, float* out, double* scratch, float* style,
+                       float* mean_rstd, int n, int cimg, int c, int h, int wd, float slope, float eps, void* stream) {
+  DGE_REQUIRE(img && w && out && scratch && (style || mean_rstd), "from_rgb_stats: null pointer");
+  DGE_REQUIRE(n > 0 && cimg > 0 && cimg <= 4 && (c == 16 || c == 32) && h > 0 && wd > 0,
+              "from_rgb_stats: bad dims (c must be 16 or 32; use dge_from_rgb + dge_instance_stats otherwise)");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * (size_t)n * c, st);
+  if (e != cudaSuccess) {
+    set_error("from_rgb_stats memset: %s", cudaGetErrorString(e));
+    return DGE_ERR_CUDA;
+  }
+  const size_t hw = (size_t)h * wd;
+  int bx = (int)((hw + 256 * 16 - 1) / (256 * 16));   // ~16 pixels per thread: the block reduction amortises
+  if (bx < 1) bx = 1;
+  if (bx > 2048) bx = 2048;
+  dim3 grid(bx, n);
+  if (c == 16)
+    k_from_rgb_stats<2><<<grid, 256, 0, st>>>(img, w, b, out, scratch, cimg, h, wd, slope);
+  else
+    k_from_rgb_stats<4><<<grid, 256, 0, st>>>(img, w, b, out, scratch, cimg, h, wd, slope);
+  count_launch();
+  int r = check_launch("k_from_rgb_stats");
+  if (r) return r;
+  k_instance_stats_final<<<grid_for((size_t)n * c, 256), 256, 0, st>>>(scratch, style, mean_rstd, n, c, (int)hw, eps);
+  count_launch();
+  return check_launch("k_instance_stats_final");
 }
 
 int dge_avgpool_to_act(const float* x, void* out_act, int n, int c, int h, int w, int planes, void* stream) {

@@ -66,6 +66,8 @@ SIGNATURES = {
     "dge_from_rgb": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P]),
     "dge_instance_stats": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_float, P]),
     "dge_instance_norm": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "dge_instance_norm_pool": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "dge_from_rgb_stats": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, P]),
     "dge_avgpool_to_act": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "dge_lreq_adam_step": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_float, c_float, P]),
     "dge_pair_moments": (c_int, [P, P, c_int64, P, P]),

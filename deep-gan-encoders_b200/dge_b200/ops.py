@@ -325,6 +325,36 @@ def from_rgb(img, w, b, slope=0.2):
     return out
 
 
+def from_rgb_stats(img, w, b, slope=0.2, eps=1e-8):
+    """FromRGB + the instance statistics of its output in one pass -> (F32B, style, mean_rstd); c in (16, 32)."""
+    img = img.contiguous()
+    n, cimg, h, wd = img.shape
+    w2 = w.detach().contiguous().view(w.shape[0], -1)
+    c = w2.shape[0]
+    dev = img.device
+    out = F32B(n, c, h, wd, dev)
+    scratch = torch.empty((2 * n * c,), dtype=torch.float64, device=dev)
+    style = torch.empty((n, 2 * c), dtype=torch.float32, device=dev)
+    mr = torch.empty((n, c, 2), dtype=torch.float32, device=dev)
+    bb = None if b is None else b.detach().contiguous()
+    with _rec("from_rgb_stats", (n, h, wd, c)):
+        check(lib().dge_from_rgb_stats(_f32(img), _f32(w2), _f32(bb), _p(out.t), _p(scratch), _p(style), _p(mr), n, cimg,
+                                       c, h, wd, float(slope), float(eps), _stream()))
+    return out, style, mr
+
+
+def instance_norm_pool(x, mean_rstd, planes=2):
+    """IN(x) -> ACT and avg_pool2d(x, 2, 2) -> ACT in one pass over x."""
+    assert isinstance(x, F32B)
+    dev = x.t.device
+    act = Act(x.n, x.c, x.h, x.w, planes, dev)
+    pool = Act(x.n, x.c, x.h // 2, x.w // 2, planes, dev)
+    with _rec("instance_norm_pool", (x.n, x.h, x.w, x.c, planes)):
+        check(lib().dge_instance_norm_pool(_p(x.t), _f32(mean_rstd), _p(act.t), _p(pool.t), x.n, x.c, x.h, x.w, planes,
+                                           _stream()))
+    return act, pool
+
+
 def instance_stats(x, eps=1e-8):
     """F32B -> (style [n][2c] = mean||std, mean_rstd [n][c][2])."""
     assert isinstance(x, F32B)

@@ -49,14 +49,19 @@ class BEBlock(nn.Module):
             return torch.randn([n, 1, h, w], device=device)
         return torch.randn([n, 1, h, w]).to(device)   # E.py:60 -- CPU draw, then H2D
 
-    def run(self, x):
-        """x: F32B [N, inputs, H, W] -> (F32B out, w1, w2)."""
+    def run(self, x, stats=None):
+        """x: F32B [N, inputs, H, W] -> (F32B out, w1, w2).  `stats` = (style, mean_rstd) of x when its producer
+        already computed them (FromRGB)."""
         n, c, h, w = x.n, x.c, x.h, x.w
         dev = x.t.device
         eps = self.instance_norm_1.eps
-        style1, mr1 = ops.instance_stats(x, eps)                                   # E.py:51-53 + IN stats
+        style1, mr1 = stats if stats is not None else ops.instance_stats(x, eps)   # E.py:51-53 + IN stats
         w1 = ops.dense(style1, self.inver_mod1.weight, self.inver_mod1.bias)      # :54
-        xn, _ = ops.instance_norm(x, mr1, planes=self.planes)                      # :58
+        rp = None
+        if self.has_last_conv and self.inputs != self.outputs:
+            xn, rp = ops.instance_norm_pool(x, mr1, planes=self.planes)            # :58 and :78 in one pass over x
+        else:
+            xn, _ = ops.instance_norm(x, mr1, planes=self.planes)                  # :58
         y1 = ops.conv(xn, self.conv_1.packed(self.planes), c, ops.CONV_3X3, noise=self._noise(n, h, w, dev),
                       noise_batched=True, noise_w=self.noise_weight_1.detach().view(-1),
                       bias=self.bias_1.detach().view(-1), slope=0.2, out_f32b=True)['f32b']      # :59-62
@@ -71,7 +76,6 @@ class BEBlock(nn.Module):
                            noise_w=self.noise_weight_2.detach().view(-1), bias=self.bias_2.detach().view(-1),
                            slope=0.2, out_f32b_pool=True)['f32b_pool']             # :72-75 + :76-77
             if self.inputs != self.outputs:
-                rp = ops.avgpool_to_act(x, planes=self.planes)                     # :78
                 out = ops.conv(rp, self.conv_3.packed(self.planes), self.outputs, ops.CONV_1X1,
                                bias=self.conv_3.scaled_bias(), blend_src=y2p, blend_pool=False, blend_a=0.111,
                                blend_b=0.889, out_f32b=True)['f32b']               # :81-84
@@ -123,10 +127,12 @@ class BE(nn.Module):
 
     def forward(self, x, block_num=9):
         ln._guard('BE', x, self.FromRGB.from_rgb.weight)
-        f = self.FromRGB.run(x)
+        first = 9 - block_num
+        eps0 = self.decode_block[first].instance_norm_1.eps if first < self.layer_count else 1e-8
+        f, style0, mr0 = self.FromRGB.run_with_stats(x, eps0)
         w = torch.tensor(0)
-        for i in range(9 - block_num, self.layer_count):
-            f, w1, w2 = self.decode_block[i].run(f)
+        for i in range(first, self.layer_count):
+            f, w1, w2 = self.decode_block[i].run(f, stats=(style0, mr0) if i == first else None)
             w_ = torch.cat((w2.view(f.n, 1, 512), w1.view(f.n, 1, 512)), dim=1)   # E.py:131 (512 is hard-coded)
             w = w_ if i == (9 - block_num) else torch.cat((w_, w), dim=1)
         return f.to_nchw(), w

@@ -21,6 +21,17 @@ class FromRGB(nn.Module):
         w = c.weight.detach() if scale == 1.0 else c.weight.detach() * scale
         return ops.from_rgb(x.float(), w, c.scaled_bias(), slope=0.2)
 
+    def run_with_stats(self, x, eps=1e-8):
+        """-> (F32B feature map, style [N, 2C] = mean||std, mean_rstd): the first block's instance statistics come out
+        of the same pass when the fused kernel covers the width (C in 16, 32), else from dge_instance_stats."""
+        c = self.from_rgb
+        if c.weight.shape[0] not in (16, 32):
+            f = self.run(x)
+            return (f,) + ops.instance_stats(f, eps)
+        scale = 1.0 if c.implicit_lreq else c.std
+        w = c.weight.detach() if scale == 1.0 else c.weight.detach() * scale
+        return ops.from_rgb_stats(x.float(), w, c.scaled_bias(), slope=0.2, eps=eps)
+
     def forward(self, x):
         ln._guard('FromRGB', x, self.from_rgb.weight)
         return self.run(x).to_nchw()

@@ -170,6 +170,14 @@ int dge_instance_norm_affine(const float* x_f32b, const float* mean_rstd, const 
    s2d = 0: ACT [n][c/8][planes][h][w][8];  s2d = 1: space-to-depth ACT [n][4c/8][planes][h/2][w/2][8] for DGE_CONV_DOWN4X4S2 */
 int dge_instance_norm_blur(const float* x_f32b, const float* mean_rstd, void* out_act, int s2d, int n, int c, int h,
                            int w, int planes, void* stream);
+/* instance norm (as dge_instance_norm, F32B -> ACT) fused with the 2x2 average pool of the RAW input -> ACT at
+   (h/2, w/2): one pass over x feeds conv_1's operand (E.py:58) and the residual branch (E.py:78) */
+int dge_instance_norm_pool(const float* x_f32b, const float* mean_rstd, void* out_act, void* out_pool_act, int n, int c,
+                           int h, int w, int planes, void* stream);
+/* dge_from_rgb that also produces the instance statistics of its output (style = mean||std, mean_rstd as
+   dge_instance_stats; `scratch` = 2*n*c doubles): net.py:231-240 + E.py:51-53,58.  c must be 16 or 32. */
+int dge_from_rgb_stats(const float* img, const float* w, const float* b, float* out_f32b, double* scratch, float* style,
+                       float* mean_rstd, int n, int cimg, int c, int h, int wd, float slope, float eps, void* stream);
 /* 2x2 average pool F32B -> ACT (residual branch, E.py:78) */
 int dge_avgpool_to_act(const float* x_f32b, void* out_act, int n, int c, int h, int w, int planes, void* stream);
 /* out = a*A' + b*B' where X' = 2x2 mean of a double-resolution tensor if its pool bit is set (bit 0: A, bit 1: B),
