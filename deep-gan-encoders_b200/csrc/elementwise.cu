@@ -282,6 +282,50 @@ __global__ void k_rgb_init(const float* __restrict__ in, const float* __restrict
   }
 }
 
+// vectorised form: one thread = 2 output rows x 4 output columns (12 input reads, two 16-byte stores); wo % 4 == 0
+__global__ void k_rgb_init_v4(const float* __restrict__ in, const float* __restrict__ bias, float* __restrict__ out,
+                              int n, int nch, int ho, int wo) {
+  const int hin = ho >> 1, win = wo >> 1, wq = win >> 1;
+  const size_t total = (size_t)n * nch * hin * wq;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int q = (int)(i % wq);
+    size_t tt = i / wq;
+    const int my = (int)(tt % hin);
+    tt /= hin;
+    const int ch = (int)(tt % nch);
+    const float b = bias ? bias[ch] : 0.f;
+    const float* src = in + tt * (size_t)hin * win;
+    const int c0 = 2 * q;
+    float r[3][4];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int yy = my - 1 + dy;
+      const bool vy = yy >= 0 && yy < hin;
+#pragma unroll
+      for (int dx = 0; dx < 4; ++dx) {
+        const int xx = c0 - 1 + dx;
+        r[dy][dx] = (vy && xx >= 0 && xx < win) ? __ldg(src + (size_t)yy * win + xx) : 0.f;
+      }
+    }
+    float hz[3][4];   // horizontal pass: 4 output columns per input row
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      hz[dy][0] = 0.25f * r[dy][0] + 0.75f * r[dy][1];
+      hz[dy][1] = 0.75f * r[dy][1] + 0.25f * r[dy][2];
+      hz[dy][2] = 0.25f * r[dy][1] + 0.75f * r[dy][2];
+      hz[dy][3] = 0.75f * r[dy][2] + 0.25f * r[dy][3];
+    }
+    float4 o0, o1;
+    o0.x = b + 0.25f * hz[0][0] + 0.75f * hz[1][0]; o1.x = b + 0.75f * hz[1][0] + 0.25f * hz[2][0];
+    o0.y = b + 0.25f * hz[0][1] + 0.75f * hz[1][1]; o1.y = b + 0.75f * hz[1][1] + 0.25f * hz[2][1];
+    o0.z = b + 0.25f * hz[0][2] + 0.75f * hz[1][2]; o1.z = b + 0.75f * hz[1][2] + 0.25f * hz[2][2];
+    o0.w = b + 0.25f * hz[0][3] + 0.75f * hz[1][3]; o1.w = b + 0.75f * hz[1][3] + 0.25f * hz[2][3];
+    float* dst = out + (tt * (size_t)ho + 2 * my) * wo + 4 * q;
+    *reinterpret_cast<float4*>(dst) = o0;
+    *reinterpret_cast<float4*>(dst + wo) = o1;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // encoder pieces
 // ---------------------------------------------------------------------------------------------
@@ -1306,6 +1350,10 @@ int dge_rgb_init(const float* img_in, const float* bias, float* img_out, int n, 
                  void* stream) {
   DGE_REQUIRE(img_out && n > 0 && nch > 0 && h_out > 0 && w_out > 0, "rgb_init: bad args");
   DGE_REQUIRE(!img_in || (h_out % 2 == 0 && w_out % 2 == 0), "rgb_init: odd output size with an input image");
+  if (img_in && w_out % 4 == 0 && (reinterpret_cast<uintptr_t>(img_out) & 15) == 0) {
+    LAUNCH_1D(k_rgb_init_v4, (size_t)n * nch * (h_out / 2) * (w_out / 4), stream, img_in, bias, img_out, n, nch, h_out,
+              w_out);
+  }
   LAUNCH_1D(k_rgb_init, (size_t)n * nch * h_out * w_out, stream, img_in, bias, img_out, n, nch, h_out, w_out);
 }
 
