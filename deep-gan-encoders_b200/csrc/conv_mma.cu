@@ -20,6 +20,7 @@
 //   EPI  : 4 warps, one TMEM lane (= pixel) per thread: demod, noise, bias, lrelu, residual blend, fused
 //          ToRGB partial sums, next-layer style scale, bf16 hi/lo split, 16/32-byte vector stores.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "dge_common.cuh"
 #include "tma_ptx.cuh"
@@ -81,6 +82,10 @@ struct ConvKParams {
   int n_ntiles, np;        // N tiles, phases per CTA tile
   int planes;
   int total_tiles;
+  int sched_tiles;         // scheduling units: tiles, or tile PAIRS (two M tiles, same N tile) in pair mode
+  int mtiles;              // M tiles (sample x tile rows x tile columns)
+  int pair;                // 1: CTA pair (cta_group::2) launch
+  int nsub_local;          // weight rows this CTA holds in smem per slab (= nsub, or nsub/2 in pair mode)
   int ntaps;
   TapEntry taps[16];
   int a_slot_bytes, b_slot_bytes, b_sub_bytes, b_slots;
@@ -145,17 +150,64 @@ __device__ unsigned long long g_role_cycles[16];
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// PAIR = the CTA pair form (cta_group::2): one MMA spans both SMs of a 2-CTA cluster (M = 256: 128 output pixels per
+// CTA), each CTA supplies its own A patch and HALF of the weight rows, so the weight operand is fetched from shared
+// memory once per pair instead of once per SM.  The commit is multicast to the same barrier offset in both CTAs.
+template <bool PAIR>
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
+  if (PAIR)
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+  else
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
 }
+template <bool PAIR>
 __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                             uint32_t accumulate) {
+  if (PAIR)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of `addr` (a shared::cta address) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion is signalled on a barrier of the pair's leader CTA (`bar_cluster` = mapa address)
+__device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* tm, uint32_t bar_cluster, int c0, int c1,
+                                                int c2, int c3) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+      "%6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
@@ -182,8 +234,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;                // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
 }
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n
-__device__ __forceinline__ uint32_t make_idesc_bf16(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc_bf16(int n, int m = 128) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -564,31 +616,32 @@ struct IssueConsts {
   uint32_t idesc, idesc2, a_kstep, b_kstep, a_lo16, b_lo16;
   int ksteps;
 };
-template <int MODE>
+template <int MODE, bool PAIR>
 __device__ __forceinline__ void issue_kstep(uint32_t d, uint64_t da, uint64_t db, const IssueConsts& c,
                                             uint32_t accumulate) {
   if (MODE == 2) {
-    tc_mma_bf16(d, da, db, c.idesc2, accumulate);
-    tc_mma_bf16(d, da + c.a_lo16, db, c.idesc, 1u);
+    tc_mma_bf16<PAIR>(d, da, db, c.idesc2, accumulate);
+    tc_mma_bf16<PAIR>(d, da + c.a_lo16, db, c.idesc, 1u);
   } else {
-    tc_mma_bf16(d, da, db, c.idesc, accumulate);
+    tc_mma_bf16<PAIR>(d, da, db, c.idesc, accumulate);
     if (MODE == 1) {
-      tc_mma_bf16(d, da, db + c.b_lo16, c.idesc, 1u);
-      tc_mma_bf16(d, da + c.a_lo16, db, c.idesc, 1u);
+      tc_mma_bf16<PAIR>(d, da, db + c.b_lo16, c.idesc, 1u);
+      tc_mma_bf16<PAIR>(d, da + c.a_lo16, db, c.idesc, 1u);
     }
   }
 }
-template <int MODE, int KSTEPS>
+template <int MODE, int KSTEPS, bool PAIR>
 __device__ __forceinline__ void issue_tap(uint32_t d, uint64_t da, uint64_t db, const IssueConsts& c,
                                           uint32_t accumulate) {
   if (KSTEPS > 0) {
 #pragma unroll
     for (int k = 0; k < KSTEPS; ++k)
-      issue_kstep<MODE>(d, da + (uint32_t)k * c.a_kstep, db + (uint32_t)k * c.b_kstep, c, k == 0 ? accumulate : 1u);
+      issue_kstep<MODE, PAIR>(d, da + (uint32_t)k * c.a_kstep, db + (uint32_t)k * c.b_kstep, c,
+                              k == 0 ? accumulate : 1u);
   } else {
 #pragma unroll 1
     for (int k = 0; k < c.ksteps; ++k) {
-      issue_kstep<MODE>(d, da, db, c, accumulate);
+      issue_kstep<MODE, PAIR>(d, da, db, c, accumulate);
       accumulate = 1u;
       da += c.a_kstep;
       db += c.b_kstep;
@@ -607,7 +660,7 @@ struct MmaBars {
 // unless the per-chunk code is straight-line: TPC (taps per chunk) and KSTEPS > 0 unroll everything between two
 // barrier waits; all operands derive from kernel parameters and uniform counters.  TPC == 0 / KSTEPS == 0 are the
 // generic runtime-loop forms.
-template <int MODE, bool RESIDENT, int TPC, int KSTEPS>
+template <int MODE, bool RESIDENT, int TPC, int KSTEPS, bool PAIR>
 __device__ __forceinline__ void mma_tiles(const ConvKParams& p, const MmaBars& m, const IssueConsts& ic,
                                           uint64_t a_desc0, uint64_t b_desc0) {
   uint32_t a_slot = 0, a_ph = 0, b_slot = 0, b_ph = 0, acc = 0, acc_ph = 0;
@@ -619,7 +672,9 @@ __device__ __forceinline__ void mma_tiles(const ConvKParams& p, const MmaBars& m
     tc_fence_after();
   }
   ROLE_T0();
-  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+  const int t_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int t_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  for (int tile = t_first; tile < p.sched_tiles; tile += t_step) {
     ROLE_ACC(rt_issue);
     mbar_wait(&m.tm_empty[acc], acc_ph ^ 1);
     ROLE_ACC(rt_tm);
@@ -644,7 +699,7 @@ __device__ __forceinline__ void mma_tiles(const ConvKParams& p, const MmaBars& m
 #pragma unroll
               for (int j = 0; j < TPC; ++j) {
                 const IssueEnt ent = p.ilist[l0 + j];
-                issue_tap<MODE, KSTEPS>(d_sb + (uint32_t)ent.dcol, a_sb + (uint32_t)ent.a_off,
+                issue_tap<MODE, KSTEPS, PAIR>(d_sb + (uint32_t)ent.dcol, a_sb + (uint32_t)ent.a_off,
                                         b_desc0 + (b_res16 + (uint32_t)j * m.b_slot16), ic,
                                         (first_chunk & (uint32_t)ent.first) ^ 1u);
               }
@@ -652,13 +707,13 @@ __device__ __forceinline__ void mma_tiles(const ConvKParams& p, const MmaBars& m
 #pragma unroll 1
               for (int j = 0; j < tpc; ++j) {
                 const IssueEnt ent = p.ilist[l0 + j];
-                issue_tap<MODE, KSTEPS>(d_sb + (uint32_t)ent.dcol, a_sb + (uint32_t)ent.a_off,
+                issue_tap<MODE, KSTEPS, PAIR>(d_sb + (uint32_t)ent.dcol, a_sb + (uint32_t)ent.a_off,
                                         b_desc0 + (b_res16 + (uint32_t)j * m.b_slot16), ic,
                                         (first_chunk & (uint32_t)ent.first) ^ 1u);
               }
             }
           }
-          tc_commit(&m.a_empty[a_slot]);
+          tc_commit<PAIR>(&m.a_empty[a_slot]);
         }
         __syncwarp();
         b_res16 += (uint32_t)tpc * m.b_slot16;
@@ -671,21 +726,21 @@ __device__ __forceinline__ void mma_tiles(const ConvKParams& p, const MmaBars& m
           if (elect_one_sync()) {
 #pragma unroll 1
             for (int sb = 0; sb < p.msub; ++sb)
-              issue_tap<MODE, KSTEPS>(d_base + (uint32_t)(sb * p.sb_cols + ent.dcol),
+              issue_tap<MODE, KSTEPS, PAIR>(d_base + (uint32_t)(sb * p.sb_cols + ent.dcol),
                                       a_desc + (uint32_t)(p.sb_off[sb] + ent.a_off),
                                       b_desc0 + (m.b_region16 + b_slot * m.b_slot16), ic,
                                       (first_chunk & (uint32_t)ent.first) ^ 1u);
-            tc_commit(&m.b_empty[b_slot]);
+            tc_commit<PAIR>(&m.b_empty[b_slot]);
           }
           __syncwarp();
           if (++b_slot == (uint32_t)p.b_slots) { b_slot = 0; b_ph ^= 1; }
         }
-        if (elect_one_sync()) tc_commit(&m.a_empty[a_slot]);
+        if (elect_one_sync()) tc_commit<PAIR>(&m.a_empty[a_slot]);
         __syncwarp();
       }
       if (++a_slot == (uint32_t)p.a_slots) { a_slot = 0; a_ph ^= 1; }
     }
-    if (elect_one_sync()) tc_commit(&m.tm_full[acc]);
+    if (elect_one_sync()) tc_commit<PAIR>(&m.tm_full[acc]);
     __syncwarp();
     if (++acc == (uint32_t)p.acc_stages) { acc = 0; acc_ph ^= 1; }
   }
@@ -696,30 +751,57 @@ __device__ __forceinline__ void mma_tiles(const ConvKParams& p, const MmaBars& m
 }
 
 // pick the unrolled form for the shapes the hot layers use; everything else runs the generic loops
-template <int MODE, bool RESIDENT>
+template <int MODE, bool RESIDENT, bool PAIR>
 __device__ __forceinline__ void mma_dispatch(const ConvKParams& p, const MmaBars& m, const IssueConsts& ic,
                                              uint64_t a_desc0, uint64_t b_desc0) {
   const int key = p.tpc * 8 + ic.ksteps;
   if (RESIDENT) {
     switch (key) {
-      case 9 * 8 + 1: mma_tiles<MODE, true, 9, 1>(p, m, ic, a_desc0, b_desc0); break;
-      case 9 * 8 + 2: mma_tiles<MODE, true, 9, 2>(p, m, ic, a_desc0, b_desc0); break;
-      case 9 * 8 + 4: mma_tiles<MODE, true, 9, 4>(p, m, ic, a_desc0, b_desc0); break;
-      case 1 * 8 + 1: mma_tiles<MODE, true, 1, 1>(p, m, ic, a_desc0, b_desc0); break;
-      case 1 * 8 + 2: mma_tiles<MODE, true, 1, 2>(p, m, ic, a_desc0, b_desc0); break;
-      case 1 * 8 + 4: mma_tiles<MODE, true, 1, 4>(p, m, ic, a_desc0, b_desc0); break;
-      default: mma_tiles<MODE, true, 0, 0>(p, m, ic, a_desc0, b_desc0); break;
+      case 9 * 8 + 1: mma_tiles<MODE, true, 9, 1, PAIR>(p, m, ic, a_desc0, b_desc0); break;
+      case 9 * 8 + 2: mma_tiles<MODE, true, 9, 2, PAIR>(p, m, ic, a_desc0, b_desc0); break;
+      case 9 * 8 + 4: mma_tiles<MODE, true, 9, 4, PAIR>(p, m, ic, a_desc0, b_desc0); break;
+      case 1 * 8 + 1: mma_tiles<MODE, true, 1, 1, PAIR>(p, m, ic, a_desc0, b_desc0); break;
+      case 1 * 8 + 2: mma_tiles<MODE, true, 1, 2, PAIR>(p, m, ic, a_desc0, b_desc0); break;
+      case 1 * 8 + 4: mma_tiles<MODE, true, 1, 4, PAIR>(p, m, ic, a_desc0, b_desc0); break;
+      default: mma_tiles<MODE, true, 0, 0, PAIR>(p, m, ic, a_desc0, b_desc0); break;
     }
   } else {
     switch (ic.ksteps) {
-      case 2: mma_tiles<MODE, false, 0, 2>(p, m, ic, a_desc0, b_desc0); break;
-      case 4: mma_tiles<MODE, false, 0, 4>(p, m, ic, a_desc0, b_desc0); break;
-      default: mma_tiles<MODE, false, 0, 0>(p, m, ic, a_desc0, b_desc0); break;
+      case 2: mma_tiles<MODE, false, 0, 2, PAIR>(p, m, ic, a_desc0, b_desc0); break;
+      case 4: mma_tiles<MODE, false, 0, 4, PAIR>(p, m, ic, a_desc0, b_desc0); break;
+      default: mma_tiles<MODE, false, 0, 0, PAIR>(p, m, ic, a_desc0, b_desc0); break;
     }
   }
 }
 
-template <int EPI>  // 0 = pointwise, 1 = raw up
+template <bool PAIR>
+__device__ __forceinline__ uint32_t mapa_or_local(uint64_t* bar) {
+  return PAIR ? mapa_shared(smem_u32(bar), 0) : smem_u32(bar);
+}
+template <bool PAIR>
+__device__ __forceinline__ void arrive_expect_tx(uint64_t* bar, uint32_t leader_addr, uint32_t bytes) {
+  if (PAIR) mbar_arrive_expect_tx_cluster(leader_addr, bytes); else mbar_arrive_expect_tx(bar, bytes);
+}
+template <bool PAIR>
+__device__ __forceinline__ void tma_load(void* dst, const CUtensorMap* tm, uint64_t* bar, uint32_t leader_addr, int c0,
+                                         int c1, int c2, int c3) {
+  if (PAIR) tma_load_4d_2sm(dst, tm, leader_addr, c0, c1, c2, c3); else tma_load_4d(dst, tm, bar, c0, c1, c2, c3);
+}
+
+// scheduling unit -> tile index of THIS CTA.  Pair mode: unit u covers M tiles 2*(u / n_ntiles) + {0, 1} of N tile
+// u % n_ntiles; a pair whose second M tile does not exist re-runs the last tile with every store masked.
+template <bool PAIR>
+__device__ __forceinline__ int sched_tile(const ConvKParams& p, int unit, uint32_t rank, bool& live) {
+  live = true;
+  if (!PAIR) return unit;
+  const int mtp = (int)fast_div((uint32_t)unit, p.div_ntiles);
+  const int nt = unit - mtp * p.n_ntiles;
+  int mt = 2 * mtp + (int)rank;
+  if (mt >= p.mtiles) { mt = p.mtiles - 1; live = false; }
+  return mt * p.n_ntiles + nt;
+}
+
+template <int EPI, bool PAIR>  // EPI: 0 = pointwise, 1 = raw up
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ ConvKParams p) {
@@ -738,33 +820,46 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  // pair mode: the "full" barriers of the LEADER CTA (rank 0) collect the TMA bytes of both CTAs (one
+  // arrive.expect_tx per CTA); the leader's tm_empty collects the epilogue warps of both; "empty"/tm_full barriers
+  // are local and receive the leader's multicast commits.
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const uint32_t npeers = PAIR ? 2u : 1u;
   if (threadIdx.x == 0) {
     for (int i = 0; i < MAX_A_SLOTS; ++i) {
-      mbar_init(&a_full[i], 1);
+      mbar_init(&a_full[i], npeers);
       mbar_init(&a_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tm_full[i], 1);
-      mbar_init(&tm_empty[i], NUM_EPI_WARPS);
+      mbar_init(&tm_empty[i], npeers * NUM_EPI_WARPS);
     }
     for (int i = 0; i < MAX_B_SLOTS; ++i) {
-      mbar_init(&b_full[i], 1);
+      mbar_init(&b_full[i], npeers);
       mbar_init(&b_empty[i], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)p.tmem_cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)p.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)p.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int t_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int t_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int kc8p = (p.kc >> 3) * p.planes;
-  const int nsubs = p.cw / p.nsub;
 
   if (warp == 0) {
     // =================================== TMA producer ===================================
@@ -774,15 +869,15 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (p.resident) {
       // weights of every (chunk, tap) stay in smem for the whole kernel: one bulk load, one barrier
       if (elect_one_sync()) {
-        mbar_arrive_expect_tx(&b_full[0], (uint32_t)p.b_region_bytes);
+        const uint32_t bfull0 = mapa_or_local<PAIR>(&b_full[0]);
+        arrive_expect_tx<PAIR>(&b_full[0], bfull0, (uint32_t)p.b_region_bytes);
         int slot = 0;
         for (int ch = 0; ch < p.nchunks; ++ch) {
           const int cph = (ch * p.kc) / p.cin_w, cb = ch * kc8p - cph * (p.cin_w >> 3) * p.planes;
           for (int e = 0; e < p.ntaps; ++e) {
             if (p.taps[e].in_phase >= 0 && p.taps[e].in_phase != cph) continue;
-            for (int s = 0; s < nsubs; ++s)
-              tma_load_4d(b_smem + slot * p.b_slot_bytes + s * p.b_sub_bytes, &tmB, &b_full[0], 0,
-                          (s * p.nsub) / p.b_rb, cb, p.taps[e].w_tap);
+            tma_load<PAIR>(b_smem + slot * p.b_slot_bytes, &tmB, &b_full[0], bfull0, 0,
+                           (int)(rank * p.nsub_local) / p.b_rb, cb, p.taps[e].w_tap);
             ++slot;
           }
         }
@@ -791,16 +886,18 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     [[maybe_unused]] long long rt_wait = 0, rt_work = 0;
     ROLE_T0();
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
+    for (int unit = t_first; unit < p.sched_tiles; unit += t_step) {
+      bool live;
+      const TileCoord t = decode_tile(p, sched_tile<PAIR>(p, unit, rank, live));
       for (int ch = 0; ch < p.nchunks; ++ch) {
         ROLE_ACC(rt_work);
         mbar_wait(&a_empty[a_slot], a_ph ^ 1);
         ROLE_ACC(rt_wait);
         if (elect_one_sync()) {
-          mbar_arrive_expect_tx(&a_full[a_slot], (uint32_t)p.a_slot_bytes);
-          tma_load_4d(a_smem + a_slot * p.a_slot_bytes, &tmA, &a_full[a_slot], 2 * (t.x0 - 1), t.y0 - 1, ch * kc8p,
-                      t.n);
+          const uint32_t afull = mapa_or_local<PAIR>(&a_full[a_slot]);
+          arrive_expect_tx<PAIR>(&a_full[a_slot], afull, (uint32_t)p.a_slot_bytes);
+          tma_load<PAIR>(a_smem + a_slot * p.a_slot_bytes, &tmA, &a_full[a_slot], afull, 2 * (t.x0 - 1), t.y0 - 1,
+                         ch * kc8p, t.n);
         }
         __syncwarp();
         if (++a_slot == (uint32_t)p.a_slots) { a_slot = 0; a_ph ^= 1; }
@@ -812,11 +909,10 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (p.taps[e].in_phase >= 0 && p.taps[e].in_phase != cph) continue;
           mbar_wait(&b_empty[b_slot], b_ph ^ 1);
           if (elect_one_sync()) {
-            mbar_arrive_expect_tx(&b_full[b_slot], (uint32_t)p.b_slot_bytes);
-            uint8_t* dst = b_smem + b_slot * p.b_slot_bytes;
-            for (int s = 0; s < nsubs; ++s)
-              tma_load_4d(dst + s * p.b_sub_bytes, &tmB, &b_full[b_slot], 0, (t.co0 + s * p.nsub) / p.b_rb, cb,
-                          p.taps[e].w_tap);
+            const uint32_t bfull = mapa_or_local<PAIR>(&b_full[b_slot]);
+            arrive_expect_tx<PAIR>(&b_full[b_slot], bfull, (uint32_t)p.b_slot_bytes);
+            tma_load<PAIR>(b_smem + b_slot * p.b_slot_bytes, &tmB, &b_full[b_slot], bfull, 0,
+                           (t.co0 + (int)(rank * p.nsub_local)) / p.b_rb, cb, p.taps[e].w_tap);
           }
           __syncwarp();
           if (++b_slot == (uint32_t)p.b_slots) { b_slot = 0; b_ph ^= 1; }
@@ -831,12 +927,12 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // Warp-uniform control flow with elected issue; every MMA operand derives from provably uniform sources (kernel
     // parameters in the constant bank, uniform counters, a shuffled TMEM base) -- see mma_tiles.
     const uint32_t a_lbo = p.planes * p.patch_bytes, a_sbo = p.pw * 16;
-    const uint32_t nb = p.nsub * 16;  // bytes of one (k-group, plane) slab of the B block
+    const uint32_t nb = p.nsub_local * 16;  // bytes of one (k-group, plane) slab of the B block held by this CTA
     const uint32_t b_lbo = p.planes * nb, b_sbo = 128;
     const uint64_t a_desc0 = make_smem_desc(0, a_lbo, a_sbo), b_desc0 = make_smem_desc(0, b_lbo, b_sbo);
     IssueConsts ic;
-    ic.idesc = make_idesc_bf16(p.nsub);
-    ic.idesc2 = make_idesc_bf16(2 * p.nsub);
+    ic.idesc = make_idesc_bf16(p.nsub, PAIR ? 256 : 128);
+    ic.idesc2 = make_idesc_bf16(2 * p.nsub, PAIR ? 256 : 128);
     ic.a_kstep = (2 * a_lbo) >> 4;   // descriptor start-address increments per K step (16-byte units)
     ic.b_kstep = (2 * b_lbo) >> 4;
     ic.a_lo16 = (uint32_t)p.patch_bytes >> 4;
@@ -851,14 +947,25 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     mb.b_slot16 = (uint32_t)p.b_slot_bytes >> 4;
     mb.tm_base = __shfl_sync(0xffffffffu, tmem_base, 0);
     const int mma_mode = p.planes == 2 ? (p.stack ? 2 : 1) : 0;
-    if (p.resident) {
-      if (mma_mode == 2) mma_dispatch<2, true>(p, mb, ic, a_desc0, b_desc0);
-      else if (mma_mode == 1) mma_dispatch<1, true>(p, mb, ic, a_desc0, b_desc0);
-      else mma_dispatch<0, true>(p, mb, ic, a_desc0, b_desc0);
+    if (PAIR) {
+      // only the leader CTA issues (its MMAs drive both SMs); the stacked mode is not used with pairs
+      if (rank == 0) {
+        if (p.resident) {
+          if (mma_mode == 1) mma_dispatch<1, true, true>(p, mb, ic, a_desc0, b_desc0);
+          else mma_dispatch<0, true, true>(p, mb, ic, a_desc0, b_desc0);
+        } else {
+          if (mma_mode == 1) mma_dispatch<1, false, true>(p, mb, ic, a_desc0, b_desc0);
+          else mma_dispatch<0, false, true>(p, mb, ic, a_desc0, b_desc0);
+        }
+      }
+    } else if (p.resident) {
+      if (mma_mode == 2) mma_dispatch<2, true, false>(p, mb, ic, a_desc0, b_desc0);
+      else if (mma_mode == 1) mma_dispatch<1, true, false>(p, mb, ic, a_desc0, b_desc0);
+      else mma_dispatch<0, true, false>(p, mb, ic, a_desc0, b_desc0);
     } else {
-      if (mma_mode == 2) mma_dispatch<2, false>(p, mb, ic, a_desc0, b_desc0);
-      else if (mma_mode == 1) mma_dispatch<1, false>(p, mb, ic, a_desc0, b_desc0);
-      else mma_dispatch<0, false>(p, mb, ic, a_desc0, b_desc0);
+      if (mma_mode == 2) mma_dispatch<2, false, false>(p, mb, ic, a_desc0, b_desc0);
+      else if (mma_mode == 1) mma_dispatch<1, false, false>(p, mb, ic, a_desc0, b_desc0);
+      else mma_dispatch<0, false, false>(p, mb, ic, a_desc0, b_desc0);
     }
   } else {
     // =================================== epilogue ========================================
@@ -878,8 +985,9 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // The per-pixel noise values are fetched one tile ahead: their global-load latency (L2 / HBM) would otherwise sit
     // on the per-tile critical path of the epilogue warps.
     float nz_next[4] = {0.f, 0.f, 0.f, 0.f};
-    auto fetch_noise = [&](int tile_idx) {
-      const TileCoord tn = decode_tile(p, tile_idx);
+    auto fetch_noise = [&](int unit_idx) {
+      bool live_n;
+      const TileCoord tn = decode_tile(p, sched_tile<PAIR>(p, unit_idx, rank, live_n));
 #pragma unroll
       for (int sb = 0; sb < 4; ++sb) {
         nz_next[sb] = 0.f;
@@ -890,9 +998,11 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
     };
-    if (EPI == 0 && p.noise && (int)blockIdx.x < p.total_tiles) fetch_noise(blockIdx.x);
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
+    if (EPI == 0 && p.noise && t_first < p.sched_tiles) fetch_noise(t_first);
+    const uint32_t tm_empty_leader = PAIR ? mapa_shared(smem_u32(&tm_empty[0]), 0) : 0u;
+    for (int unit = t_first; unit < p.sched_tiles; unit += t_step) {
+      bool live;
+      const TileCoord t = decode_tile(p, sched_tile<PAIR>(p, unit, rank, live));
       if (EPI == 0 && (t.n != cur_n || t.co0 != cur_co0)) {
         // per-(sample, N tile) parameter table: one cooperative reload when the sample changes (tiles are visited
         // in sample order), then every per-channel parameter is a broadcast LDS.128 instead of a global load
@@ -905,7 +1015,7 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       float nz_cur[4];
 #pragma unroll
       for (int sb = 0; sb < 4; ++sb) nz_cur[sb] = nz_next[sb];
-      if (EPI == 0 && p.noise && tile + (int)gridDim.x < p.total_tiles) fetch_noise(tile + (int)gridDim.x);
+      if (EPI == 0 && p.noise && unit + t_step < p.sched_tiles) fetch_noise(unit + t_step);
       ROLE_ACC(rt_proc);
       mbar_wait_relaxed(&tm_full[acc], acc_ph);
       ROLE_ACC(rt_full);
@@ -947,7 +1057,7 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           cur_sb = sb;
           px.y = t.y0 + p.sb_y[sb] + ty;
           px.x = t.x0 + p.sb_x[sb] + tx;
-          px.valid = (px.y < p.dom_h) && (px.x < p.dom_w);
+          px.valid = live && (px.y < p.dom_h) && (px.x < p.dom_w);
           px.nz = sb == 0 ? nz_cur[0] : (sb == 1 ? nz_cur[1] : (sb == 2 ? nz_cur[2] : nz_cur[3]));
         }
         epi_group16<EPI>(p, epi_tab, px, t.co0, t.p0, q, u_c, bc, rgb);
@@ -970,7 +1080,9 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tm_empty[acc]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(tm_empty_leader + acc * 8u); else mbar_arrive(&tm_empty[acc]);
+      }
       if (++acc == (uint32_t)p.acc_stages) { acc = 0; acc_ph ^= 1; }
     }
     ROLE_ACC(rt_proc);
@@ -981,12 +1093,16 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
-                 : "memory");
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                   : "memory");
   }
 }
 
@@ -1228,6 +1344,17 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
   }
   p.tiles_x = (p.dom_w + p.tile_w - 1) / p.tile_w;
   p.tiles_y = (p.dom_h + p.tile_h - 1) / p.tile_h;
+  // CTA pairs (cta_group::2) for the wide column blocks: each CTA keeps half of the weight rows, so the weight operand
+  // costs half the shared-memory bandwidth per SM (the limiter of the N >= 128 MMAs) and half the L2->smem traffic
+  p.mtiles = p.N * p.tiles_x * p.tiles_y;
+  {
+    static int no_pair = -1;
+    if (no_pair < 0) no_pair = getenv("DGE_NO_PAIR") ? 1 : 0;   // A/B switch for experiments
+    p.pair = (!no_pair && !(a->flags & DGE_CONV_FLAG_CHECKER) && !p.stack && p.msub == 1 && p.cw >= 128 &&
+              p.mtiles >= 2 && g_num_sms >= 2) ? 1 : 0;
+  }
+  p.nsub_local = p.pair ? p.cw / 2 : p.cw;
+  const long long b_all_cta = p.pair ? b_all / 2 : b_all;   // weight bytes one CTA holds when resident
   // taps (patch offsets need the patch width of the chosen tile shape)
   if (a->kind == DGE_CONV_3X3) {
     p.ntaps = 9;
@@ -1307,7 +1434,7 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
     for (int i = 0; i < 3 && !p.resident; ++i) {
       const int kc = largest_div(p.cin_w, kcs[i], 16);
       const long long a_slot = (long long)(kc / 8) * p.planes * p.patch_bytes;
-      if (b_all + 2 * a_slot + bar_bytes <= smem_cap) {
+      if (b_all_cta + 2 * a_slot + bar_bytes <= smem_cap) {
         p.resident = 1;
         p.kc = kc;
       }
@@ -1316,16 +1443,16 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
   if (!p.resident) p.kc = largest_div(p.cin_w, p.cw > 128 ? 32 : 64, 16);
   p.nchunks = p.Cin / p.kc;
   p.a_slot_bytes = (p.kc / 8) * p.planes * p.patch_bytes;
-  p.b_sub_bytes = (p.kc / 8) * p.planes * p.nsub * 16;
-  p.b_slot_bytes = (p.cw / p.nsub) * p.b_sub_bytes;
+  p.b_sub_bytes = (p.kc / 8) * p.planes * p.nsub_local * 16;
+  p.b_slot_bytes = p.b_sub_bytes;
   size_t smem = 0;
   (void)tmem_occ;
   int max_occ = 1;   // one CTA (2 + 8 warps) per SM
   if (p.resident) {
-    p.b_region_bytes = (int)b_all;
+    p.b_region_bytes = (int)b_all_cta;
     p.b_slots = 1;
     const int budget = smem_cap;
-    p.a_slots = (int)((budget - b_all - bar_bytes) / p.a_slot_bytes);
+    p.a_slots = (int)((budget - b_all_cta - bar_bytes) / p.a_slot_bytes);
     if (p.a_slots > MAX_A_SLOTS) p.a_slots = MAX_A_SLOTS;
   } else {
     p.a_slots = 2;
@@ -1339,6 +1466,7 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
   smem = (size_t)p.a_slots * p.a_slot_bytes + (size_t)p.b_region_bytes + bar_bytes;
   if (smem > 113 * 1024) max_occ = 1;
   p.total_tiles = p.N * p.tiles_x * p.tiles_y * p.n_ntiles;
+  p.sched_tiles = p.pair ? ((p.mtiles + 1) / 2) * p.n_ntiles : p.total_tiles;
   DGE_REQUIRE((long long)p.N * p.tiles_x * p.tiles_y * p.n_ntiles < (1ll << 31), "conv: too many tiles");
   p.div_ntiles = make_fast_div((uint32_t)p.n_ntiles);
   p.div_per_img = make_fast_div((uint32_t)(p.tiles_x * p.tiles_y));
@@ -1388,10 +1516,10 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
     // lands in smem as [k-group][cw rows][16 B] -- the canonical K-major operand with SBO = 128 B.
     const uint64_t c8p = (uint64_t)(p.cin_w / 8) * p.planes;
     const int wtaps = (a->kind == DGE_CONV_1X1) ? 1 : (a->kind == DGE_CONV_DOWN4X4S2 ? 16 : 9);
-    const int rb = p.cw > 128 ? 128 : p.cw;
+    const int rb = p.nsub_local > 128 ? 128 : p.nsub_local;   // (pair mode: each CTA loads its half of the rows)
     uint64_t dims[4] = {(uint64_t)2 * rb, (uint64_t)(p.Cout / rb), c8p, (uint64_t)wtaps};
     uint64_t strides[3] = {(uint64_t)rb * 16, (uint64_t)p.Cout * 16, c8p * p.Cout * 16};
-    uint32_t box[4] = {(uint32_t)(2 * rb), (uint32_t)(p.cw / rb), (uint32_t)((p.kc / 8) * p.planes), 1};
+    uint32_t box[4] = {(uint32_t)(2 * rb), (uint32_t)(p.nsub_local / rb), (uint32_t)((p.kc / 8) * p.planes), 1};
     int r = make_tmap(&tmB, a->wpk, 4, dims, strides, box);
     if (r) return r;
     p.b_rb = rb;
@@ -1400,11 +1528,12 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
   // TMEM is 512 columns per SM: keep co-resident CTAs * tmem_cols <= 512 by padding the smem request.
   const size_t min_smem = (227 * 1024) / (max_occ + 1) + 1024;
   if (smem < min_smem) smem = min_smem;
-  static bool attr_set[2] = {false, false};
-  const int ei = up ? 1 : 0;
+  static bool attr_set[4] = {false, false, false, false};
+  const int ei = (up ? 1 : 0) + (p.pair ? 2 : 0);
+  const void* kfn = p.pair ? (up ? (const void*)conv_mma_kernel<1, true> : (const void*)conv_mma_kernel<0, true>)
+                           : (up ? (const void*)conv_mma_kernel<1, false> : (const void*)conv_mma_kernel<0, false>);
   if (!attr_set[ei]) {
-    cudaError_t e = up ? cudaFuncSetAttribute(conv_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
-                       : cudaFuncSetAttribute(conv_mma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(smem) failed: %s", cudaGetErrorString(e));
       return DGE_ERR_CUDA;
@@ -1412,11 +1541,30 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
     attr_set[ei] = true;
   }
   int grid = g_num_sms * max_occ;
-  if (grid > p.total_tiles) grid = p.total_tiles;
-  if (up)
-    conv_mma_kernel<1><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, p);
-  else
-    conv_mma_kernel<0><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, p);
+  if (p.pair) {
+    grid &= ~1;
+    if (grid > 2 * p.sched_tiles) grid = 2 * p.sched_tiles;
+  } else if (grid > p.total_tiles) {
+    grid = p.total_tiles;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = p.pair ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  void* kargs[3] = {(void*)&tmA, (void*)&tmB, (void*)&p};
+  cudaError_t le = cudaLaunchKernelExC(&cfg, kfn, kargs);
+  if (le != cudaSuccess) {
+    set_error("conv_mma_kernel launch failed: %s", cudaGetErrorString(le));
+    return DGE_ERR_CUDA;
+  }
   count_launch();
   return check_launch("conv_mma_kernel");
 }
