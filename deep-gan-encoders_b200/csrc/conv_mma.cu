@@ -1298,7 +1298,12 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
   DGE_REQUIRE(p.n_ntiles * p.ntile == ntot, "conv: cannot tile cout=%d", p.Cout);
   DGE_REQUIRE(p.np * (p.cw / p.nsub) <= 8 && p.cw / p.nsub <= 2, "conv: internal sub-tile bookkeeping overflow");
   // hi|lo stacking on N pays while the MMA is bound by its A-operand read (2*cw <= 96 columns)
-  p.stack = (p.planes == 2 && p.cw <= 48 && p.np * 2 * p.cw <= 512) ? 1 : 0;
+  {
+    static int stack_max = -1;
+    if (stack_max < 0) stack_max = getenv("DGE_STACK_MAX") ? atoi(getenv("DGE_STACK_MAX")) : 64;   // A/B switch
+    const int lim = p.np == 1 ? stack_max : 48;   // (4-phase tiles: 2*cw*4 columns must leave room for two stages)
+    p.stack = (p.planes == 2 && p.cw <= lim && p.np * 2 * p.cw <= 512) ? 1 : 0;
+  }
   p.acc_cols = p.cw * (p.stack ? 2 : 1);
   p.sb_cols = p.np * p.acc_cols;
   p.np_shift = p.np == 4 ? 2 : 0;
