@@ -1355,7 +1355,9 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
   {
     static int no_pair = -1;
     if (no_pair < 0) no_pair = getenv("DGE_NO_PAIR") ? 1 : 0;   // A/B switch for experiments
-    p.pair = (!no_pair && !(a->flags & DGE_CONV_FLAG_CHECKER) && !p.stack && p.msub == 1 && p.cw >= 128 &&
+    static int pair_min = -1;
+    if (pair_min < 0) pair_min = getenv("DGE_PAIR_MIN") ? atoi(getenv("DGE_PAIR_MIN")) : 64;
+    p.pair = (!no_pair && !(a->flags & DGE_CONV_FLAG_CHECKER) && !p.stack && p.msub == 1 && p.cw >= pair_min &&
               p.mtiles >= 2 && g_num_sms >= 2) ? 1 : 0;
   }
   p.nsub_local = p.pair ? p.cw / 2 : p.cw;
