@@ -948,7 +948,7 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     mb.tm_base = __shfl_sync(0xffffffffu, tmem_base, 0);
     const int mma_mode = p.planes == 2 ? (p.stack ? 2 : 1) : 0;
     if (PAIR) {
-      // only the leader CTA issues (its MMAs drive both SMs); the stacked mode is not used with pairs
+      // only the leader CTA issues (its MMAs drive both SMs); pairs are never combined with the stacked mode
       if (rank == 0) {
         if (p.resident) {
           if (mma_mode == 1) mma_dispatch<1, true, true>(p, mb, ic, a_desc0, b_desc0);
@@ -1357,6 +1357,8 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
     if (no_pair < 0) no_pair = getenv("DGE_NO_PAIR") ? 1 : 0;   // A/B switch for experiments
     static int pair_min = -1;
     if (pair_min < 0) pair_min = getenv("DGE_PAIR_MIN") ? atoi(getenv("DGE_PAIR_MIN")) : 64;
+    // (measured: pairs lose on the narrow stacked / multi-block tiles -- E 16->16 @1024^2 0.29 -> 0.49 ms -- so they
+    //  are used only where the weight operand is a large share of the shared-memory traffic)
     p.pair = (!no_pair && !(a->flags & DGE_CONV_FLAG_CHECKER) && !p.stack && p.msub == 1 && p.cw >= pair_min &&
               p.mtiles >= 2 && g_num_sms >= 2) ? 1 : 0;
   }
