@@ -133,6 +133,70 @@ __global__ void k_dense(const float* __restrict__ x, const float* __restrict__ w
 }
 
 // one warp per row
+// one block per (layer item, sample): style affine -> shared memory -> demod coefficients / ToRGB weights.
+// Both contractions are latency-bound GEMVs: a warp works on 4 output rows at once with 16-byte loads (16 independent
+// loads in flight per lane) against a vector held in shared memory.
+__device__ __forceinline__ void gemv4_rows(const float* __restrict__ w, int ld, int len, const float* sv, int lane,
+                                           float* acc) {
+  acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+  for (int k = lane * 4; k < len; k += 128) {
+    const float4 xv = *reinterpret_cast<const float4*>(sv + k);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (size_t)j * ld + k));
+      acc[j] = fmaf(wv.x, xv.x, fmaf(wv.y, xv.y, fmaf(wv.z, xv.z, fmaf(wv.w, xv.w, acc[j]))));
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int off = 16; off; off >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
+}
+
+__global__ void __launch_bounds__(256)
+k_sg2_prep(const dge_sg2_prep_item* __restrict__ items, const float* __restrict__ wp, float* __restrict__ arena,
+           int num_layers, int wdim) {
+  __shared__ __align__(16) float s_x[2048];       // the w vector, then style^2 for the demod contraction
+  __shared__ __align__(16) float s_style[2048];
+  const dge_sg2_prep_item it = items[blockIdx.x];
+  const int n = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const float* x = wp + ((size_t)n * num_layers + it.wp_index) * wdim;
+  for (int k = threadIdx.x; k < wdim; k += blockDim.x) s_x[k] = __ldg(x + k);
+  __syncthreads();
+  for (int c = warp * 4; c < it.cin; c += nwarps * 4) {   // cin, wdim are multiples of 4 (host-checked)
+    float acc[4];
+    gemv4_rows(it.st_w + (size_t)c * wdim, wdim, wdim, s_x, lane, acc);
+    if (lane < 4) {
+      const int cc = c + lane;
+      const float a = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
+      const float v = a * it.st_wscale + (it.st_b ? __ldg(it.st_b + cc) * it.st_bscale : 0.f) + it.st_add_bias;
+      s_style[cc] = v;
+      if (it.style_off >= 0) arena[it.style_off + (size_t)n * it.cin + cc] = v;
+    }
+  }
+  __syncthreads();
+  if (it.w2 && it.demod_off >= 0) {
+    for (int k = threadIdx.x; k < it.cin; k += blockDim.x) s_x[k] = s_style[k] * s_style[k];
+    __syncthreads();
+    for (int o = warp * 4; o < it.cout; o += nwarps * 4) {
+      float acc[4];
+      gemv4_rows(it.w2 + (size_t)o * it.cin, it.cin, it.cin, s_x, lane, acc);
+      if (lane < 4) {
+        const float a = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
+        arena[it.demod_off + (size_t)n * it.cout + o + lane] = rsqrtf(a + it.eps);
+      }
+    }
+  }
+  if (it.rgb_w && it.rgbw_off >= 0) {
+    const int total = it.nch * it.cin;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int c = i % it.cin;
+      arena[it.rgbw_off + (size_t)n * total + i] = __ldg(it.rgb_w + i) * it.rgb_scale * s_style[c];
+    }
+  }
+}
+
 __global__ void k_pixel_norm(const float* __restrict__ x, float* __restrict__ y, int n, int k, float eps) {
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
@@ -1300,6 +1364,16 @@ int dge_dense(const float* x, const float* w, const float* b, float* y, int n, i
               float bscale, float add_bias, float slope, float gain, void* stream) {
   DGE_REQUIRE(x && w && y && n > 0 && k > 0 && m > 0, "dense: bad args");
   LAUNCH_1D(k_dense, (size_t)n * m * 32, stream, x, w, b, y, n, k, m, wscale, bscale, add_bias, slope, gain);
+}
+
+int dge_sg2_prep(const dge_sg2_prep_item* items, int n_items, const float* wp, float* arena, int n, int num_layers,
+                 int wdim, void* stream) {
+  DGE_REQUIRE(items && wp && arena && n_items > 0 && n > 0 && num_layers > 0 && wdim > 0 && wdim % 4 == 0 && wdim <= 2048,
+              "sg2_prep: bad args (w dimension must be a multiple of 4, <= 2048; channel counts multiples of 4, <= 2048)");
+  dim3 grid(n_items, n);
+  k_sg2_prep<<<grid, 256, 0, (cudaStream_t)stream>>>(items, wp, arena, num_layers, wdim);
+  count_launch();
+  return check_launch("k_sg2_prep");
 }
 
 int dge_pixel_norm(const float* x, float* y, int n, int k, float eps, void* stream) {

@@ -84,7 +84,8 @@ k_up_fir_tma(const __grid_constant__ CUtensorMap tm, const __grid_constant__ Fir
   uint32_t ph0 = 0, ph1 = 0;
   int stage = 0;
   int cur_ng = -1;
-  float dm[4] = {1.f, 1.f, 1.f, 1.f}, bs[4] = {0.f, 0.f, 0.f, 0.f}, sc[4] = {1.f, 1.f, 1.f, 1.f};
+  float dm[4] = {1.f, 1.f, 1.f, 1.f}, bs[4] = {0.f, 0.f, 0.f, 0.f}, gs[4] = {1.f, 1.f, 1.f, 1.f};   // gs = gain * next style
+  const bool lrelu_max = p.slope >= 0.f && p.slope <= 1.f;
   for (int tile = t0; tile < p.total_tiles; tile += stride) {
     const int ng = tile / per_ng, r = tile - ng * per_ng;
     const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
@@ -98,7 +99,7 @@ k_up_fir_tma(const __grid_constant__ CUtensorMap tm, const __grid_constant__ Fir
         const int ch = g * 8 + 4 * half + k;
         dm[k] = p.demod ? __ldg(p.demod + (size_t)nidx * p.c + ch) : 1.f;
         bs[k] = p.bias ? __ldg(p.bias + ch) : 0.f;
-        sc[k] = p.out_scale ? __ldg(p.out_scale + (size_t)nidx * p.c + ch) : 1.f;
+        gs[k] = (p.out_scale ? __ldg(p.out_scale + (size_t)nidx * p.c + ch) : 1.f) * p.gain;
       }
     }
     // the tile's noise values are requested before waiting for the window (their latency overlaps the TMA wait)
@@ -139,19 +140,19 @@ k_up_fir_tma(const __grid_constant__ CUtensorMap tm, const __grid_constant__ Fir
           // window rows oy .. oy+3 live in ring slots (rr-3 .. rr) & 3 with taps f[0..3]
           const float v = f[0] * ring[(rr - 3) & 3][k] + f[1] * ring[(rr - 2) & 3][k] + f[2] * ring[(rr - 1) & 3][k] +
                           f[3] * ring[rr & 3][k];
-          const float z = v * dm[k] + nz[oy] + bs[k];
-          acc[k] = (z < 0.f ? z * p.slope : z) * p.gain;
+          const float z = fmaf(v, dm[k], nz[oy] + bs[k]);
+          acc[k] = lrelu_max ? fmaxf(z, z * p.slope) : (z < 0.f ? z * p.slope : z);   // (gain applied with the scale)
         }
         if (p.out_nchw) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            p.out_nchw[(((size_t)nidx * p.c + g * 8 + 4 * half + k) * p.ho + y) * p.wo + x] = acc[k];
+            p.out_nchw[(((size_t)nidx * p.c + g * 8 + 4 * half + k) * p.ho + y) * p.wo + x] = acc[k] * p.gain;
         }
         if (p.out_act) {
           uint32_t hw[2], lw[2];
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
-            const float a = acc[2 * i] * sc[2 * i], b2 = acc[2 * i + 1] * sc[2 * i + 1];
+            const float a = acc[2 * i] * gs[2 * i], b2 = acc[2 * i + 1] * gs[2 * i + 1];
             const __nv_bfloat162 hb = __floats2bfloat162_rn(a, b2);
             hw[i] = *reinterpret_cast<const uint32_t*>(&hb);
             const __nv_bfloat162 lb = __floats2bfloat162_rn(a - __uint_as_float(hw[i] << 16),

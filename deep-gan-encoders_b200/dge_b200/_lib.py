@@ -39,6 +39,17 @@ class ConvArgs(Structure):
     ]
 
 
+class Sg2PrepItem(Structure):
+    """Mirror of `dge_sg2_prep_item` (include/dge_b200.h)."""
+    _fields_ = [
+        ("st_w", c_void_p), ("st_b", c_void_p), ("w2", c_void_p), ("rgb_w", c_void_p),
+        ("style_off", c_int64), ("demod_off", c_int64), ("rgbw_off", c_int64),
+        ("wp_index", c_int32), ("cin", c_int32), ("cout", c_int32), ("nch", c_int32),
+        ("st_wscale", c_float), ("st_bscale", c_float), ("st_add_bias", c_float), ("rgb_scale", c_float),
+        ("eps", c_float), ("pad_", c_int32),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/dge_b200.h declares
 P = c_void_p
 SIGNATURES = {
@@ -52,6 +63,7 @@ SIGNATURES = {
     "dge_weight_sqsum": (c_int, [P, P, c_int, c_int, c_int, c_float, P]),
     "dge_demod": (c_int, [P, P, P, c_int, c_int, c_int, c_float, P]),
     "dge_rgb_weights": (c_int, [P, P, P, c_int, c_int, c_int, c_float, P]),
+    "dge_sg2_prep": (c_int, [P, c_int, P, P, c_int, c_int, c_int, P]),
     "dge_dense": (c_int, [P, P, P, P, c_int, c_int, c_int, c_float, c_float, c_float, c_float, c_float, P]),
     "dge_pixel_norm": (c_int, [P, P, c_int, c_int, c_float, P]),
     "dge_nchw_to_act": (c_int, [P, c_int64, P, P, c_int, c_int, c_int, c_int, c_int, P]),

@@ -194,6 +194,12 @@ def rgb_weights(w, style, scale):
     return out
 
 
+def sg2_prep(items_dev, n_items, wp, arena, n, num_layers, wdim):
+    """All style affines + demod coefficients + ToRGB weights of one synthesis pass in one launch (dge_sg2_prep)."""
+    with _rec("sg2_prep", (n, n_items)):
+        check(lib().dge_sg2_prep(_p(items_dev), n_items, _f32(wp), _p(arena), n, num_layers, wdim, _stream()))
+
+
 def dense(x, w, b=None, wscale=1.0, bscale=1.0, add_bias=0.0, slope=1.0, gain=1.0):
     x = x.contiguous()
     w = w.detach().contiguous()

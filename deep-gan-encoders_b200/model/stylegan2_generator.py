@@ -367,11 +367,14 @@ class ModulateConvBlock(nn.Module):
             return torch.randn(batch, 1, self.res, self.res).to(device).contiguous(), True
         return self.noise, False
 
-    def run(self, xa, style, randomize_noise=False, next_style=None, want_act=True, want_nchw=False, rgb=None):
-        """Chained form: `xa` is an ACT tensor already multiplied by this layer's style."""
+    def run(self, xa, style, randomize_noise=False, next_style=None, want_act=True, want_nchw=False, rgb=None,
+            dm=None):
+        """Chained form: `xa` is an ACT tensor already multiplied by this layer's style; `dm` = precomputed
+        demodulation coefficients (dge_sg2_prep), else they are computed here."""
         p = self._prepared()
         n = xa.n
-        dm = ops.demod(p['w2'], style, self.eps) if self.demodulate else None
+        if dm is None:
+            dm = ops.demod(p['w2'], style, self.eps) if self.demodulate else None
         noise, batched = self._noise(n, randomize_noise, xa.t.device)
         if self.use_conv2d_transpose:
             raw = ops.conv(xa, p['wpk'], self.out_c, ops.CONV_UP3X3)['raw_up']
@@ -468,6 +471,75 @@ class SynthesisModule(nn.Module):
     def get_nf(self, res):
         return min(self.fmaps_base // res, self.fmaps_max)
 
+    def _prep(self, wp32, layers, outputs):
+        """-> (styles, demods, rgb_styles, rgb_weights), all views into one arena filled by `dge_sg2_prep`.
+        The item table (device array of `dge_sg2_prep_item`) is rebuilt only when a parameter or the batch size
+        changes."""
+        import ctypes
+        from dge_b200._lib import Sg2PrepItem
+        n, dev = wp32.shape[0], wp32.device
+        srcs = []
+        for m in list(layers) + list(outputs):
+            srcs += [m.weight, m.style.weight] + ([m.style.bias] if m.style.bias is not None else [])
+        if not hasattr(self, '_prep_cache'):
+            self._prep_cache = _Cache()
+
+        def build():
+            items = (Sg2PrepItem * (len(layers) + len(outputs)))()
+            keep, views, off = [], [], 0
+            for j, m in enumerate(list(layers) + list(outputs)):
+                it = items[j]
+                is_rgb = j >= len(layers)
+                st = m.style
+                it.st_w = st.weight.data_ptr()
+                it.st_b = st.bias.data_ptr() if st.bias is not None else None
+                it.wp_index = (2 * (j - len(layers)) + 1) if is_rgb else j
+                it.cin, it.cout, it.nch = m.in_c, m.out_c, (m.out_c if is_rgb else 0)
+                it.st_wscale, it.st_bscale, it.st_add_bias = st.wscale, st.bscale, st.additional_bias
+                it.eps = m.eps
+                it.style_off = off
+                v = {'style': (off, (n, m.in_c))}
+                off += n * m.in_c
+                it.demod_off = it.rgbw_off = -1
+                if is_rgb:
+                    w = m.weight.detach().contiguous().view(m.out_c, -1)
+                    keep.append(w)
+                    it.rgb_w, it.rgb_scale = w.data_ptr(), m.wscale
+                    it.rgbw_off = off
+                    v['rgbw'] = (off, (n, m.out_c, m.in_c))
+                    off += n * m.out_c * m.in_c
+                elif m.demodulate:
+                    w2 = m._prepared()['w2']
+                    keep.append(w2)
+                    it.w2 = w2.data_ptr()
+                    it.demod_off = off
+                    v['demod'] = (off, (n, m.out_c))
+                    off += n * m.out_c
+                views.append(v)
+            raw = torch.frombuffer(bytearray(bytes(items)), dtype=torch.uint8).to(dev)
+            return {'items': raw, 'n_items': len(items), 'views': views, 'floats': off, 'keep': keep, 'n': n}
+
+        c = self._prep_cache.get(srcs, build)
+        if c['n'] != n:
+            self._prep_cache.key = None
+            c = self._prep_cache.get(srcs, build)
+        arena = torch.empty(c['floats'], dtype=torch.float32, device=dev)
+        ops.sg2_prep(c['items'], c['n_items'], wp32, arena, n, self.num_layers, self.w_space_dim)
+
+        def view(spec):
+            o, shape = spec
+            numel = 1
+            for d in shape:
+                numel *= d
+            return arena[o:o + numel].view(*shape)
+
+        nl = len(layers)
+        styles = [view(c['views'][i]['style']) for i in range(nl)]
+        demods = [view(c['views'][i]['demod']) if 'demod' in c['views'][i] else None for i in range(nl)]
+        rgb_styles = [view(c['views'][nl + k]['style']) for k in range(len(outputs))]
+        rgb_ws = [view(c['views'][nl + k]['rgbw']) for k in range(len(outputs))]
+        return styles, demods, rgb_styles, rgb_ws
+
     def forward(self, wp, randomize_noise=False):
         if wp.ndim != 3 or wp.shape[1:] != (self.num_layers, self.w_space_dim):
             raise ValueError(f'Input tensor should be with shape [batch_size, num_layers, w_space_dim], where '
@@ -481,13 +553,13 @@ class SynthesisModule(nn.Module):
         nl = self.num_layers
         layers = [getattr(self, f'layer{i}') for i in range(nl - 1)]
         outputs = [getattr(self, f'output{k}') for k in range(nl // 2)]
-        # all style affines up front: layer i reads wp[:, i], ToRGB k reads wp[:, 2k+1]   (:511-517)
-        styles = [layers[i].style(wp32[:, i].contiguous()) for i in range(nl - 1)]
-        rgb_styles = [outputs[k].style(wp32[:, 2 * k + 1].contiguous()) for k in range(nl // 2)]
-        for i, s in enumerate(styles):
-            results[f'style{i:02d}'] = s
-        for k, s in enumerate(rgb_styles):
-            results[f'output_style{k}'] = s
+        # every per-layer scalar -- style affines (layer i reads wp[:, i], ToRGB k reads wp[:, 2k+1], :511-517), the
+        # demodulation coefficients and the ToRGB weights -- comes out of ONE launch into one arena
+        styles, demods, rgb_styles, rgb_ws = self._prep(wp32.contiguous(), layers, outputs)
+        for i, st in enumerate(styles):
+            results[f'style{i:02d}'] = st
+        for k, st in enumerate(rgb_styles):
+            results[f'output_style{k}'] = st
 
         planes = layers[0].planes
         # InputBlock: const.repeat(N) (:630-632), pre-multiplied by layer0's style
@@ -497,7 +569,7 @@ class SynthesisModule(nn.Module):
             layer = layers[i]
             nxt = styles[i + 1] if i + 1 < nl - 1 else None
             if i % 2 == 1:
-                xa = layer.run(xa, styles[i], randomize_noise, next_style=nxt)['act']
+                xa = layer.run(xa, styles[i], randomize_noise, next_style=nxt, dm=demods[i])['act']
                 continue
             k = i // 2
             out_l = outputs[k]
@@ -505,7 +577,7 @@ class SynthesisModule(nn.Module):
             # image_k = bias + up2(image_{k-1}); the conv epilogue adds the ToRGB contribution (:515-522)
             image = ops.rgb_init(image, out_l._prepared()['bias'], n, self.image_channels, res, res, dev)
             r = layer.run(xa, styles[i], randomize_noise, next_style=nxt, want_act=nxt is not None,
-                          rgb=(out_l.rgb_weights(rgb_styles[k]), image))
+                          rgb=(rgb_ws[k], image), dm=demods[i])
             xa = r.get('act')
         results['image'] = self.final_activate(image)
         return results

@@ -120,6 +120,28 @@ int dge_demod(const float* w2, const float* style, float* d, int n, int cout, in
 int dge_rgb_weights(const float* w, const float* style, float* rgb_w, int n, int nch, int cin, float scale,
                     void* stream);
 
+/* ---- all per-layer scalars of one StyleGAN2 synthesis pass in ONE launch ---------------------- */
+/* For every layer: style = Dense(wp[:, wp_index]) (stylegan2_generator.py:872-877, 990-996), then either the
+   demodulation coefficients d[n][o] = rsqrt(sum_i W2[o][i]*style[n][i]^2 + eps) (:867-870) or the ToRGB weights
+   rgbw[n][ch][c] = w[ch][c]*scale*style[n][c] (:462-474).  Replaces ~53 tiny launches (dge_dense / dge_demod /
+   dge_rgb_weights per layer) of a 1024^2 pass.  Outputs go to one caller-provided arena at the given float offsets
+   (a negative offset = output not wanted).  `items` is a DEVICE array. */
+typedef struct dge_sg2_prep_item {
+  const float* st_w;       /* style weight [cin][wdim] */
+  const float* st_b;       /* style bias [cin] or NULL */
+  const float* w2;         /* [cout][cin] from dge_weight_sqsum, or NULL */
+  const float* rgb_w;      /* ToRGB weight [nch][cin], or NULL */
+  int64_t style_off;       /* -> arena: style [n][cin] */
+  int64_t demod_off;       /* -> arena: demod [n][cout] */
+  int64_t rgbw_off;        /* -> arena: rgb weights [n][nch][cin] */
+  int32_t wp_index;
+  int32_t cin, cout, nch;
+  float st_wscale, st_bscale, st_add_bias, rgb_scale, eps;
+  int32_t pad_;
+} dge_sg2_prep_item;
+int dge_sg2_prep(const dge_sg2_prep_item* items, int n_items, const float* wp, float* arena, int n, int num_layers,
+                 int wdim, void* stream);
+
 /* ---- dense (DenseBlock.forward stylegan2_generator.py:990-996; ln.Linear lreq.py:68-75) ------ */
 /* y[n][m] = act((sum_k x[n][k]*w[m][k])*wscale + b[m]*bscale + add_bias) * gain ; act = lrelu(slope) */
 int dge_dense(const float* x, const float* w, const float* b, float* y, int n, int k, int m, float wscale,
