@@ -107,9 +107,9 @@ k_up_fir_tma(const __grid_constant__ CUtensorMap tm, const __grid_constant__ Fir
 #pragma unroll
     for (int oy = 0; oy < FIR_RPG; ++oy) {
       const int y = y0 + oy;
-      nz[oy] = (p.noise && active && y < p.ho)
-                   ? __ldg(p.noise + (size_t)nidx * p.noise_bstride + (size_t)y * p.wo + x) * p.noise_scalar
-                   : 0.f;
+      // (raw value: multiplying by the strength here would stall on the load before the TMA wait)
+      nz[oy] = (p.noise && active && y < p.ho) ? __ldg(p.noise + (size_t)nidx * p.noise_bstride + (size_t)y * p.wo + x)
+                                               : 0.f;
     }
     mbar_wait(&full[stage], stage ? ph1 : ph0);
     if (stage) ph1 ^= 1; else ph0 ^= 1;
@@ -140,7 +140,7 @@ k_up_fir_tma(const __grid_constant__ CUtensorMap tm, const __grid_constant__ Fir
           // window rows oy .. oy+3 live in ring slots (rr-3 .. rr) & 3 with taps f[0..3]
           const float v = f[0] * ring[(rr - 3) & 3][k] + f[1] * ring[(rr - 2) & 3][k] + f[2] * ring[(rr - 1) & 3][k] +
                           f[3] * ring[rr & 3][k];
-          const float z = fmaf(v, dm[k], nz[oy] + bs[k]);
+          const float z = fmaf(v, dm[k], fmaf(nz[oy], p.noise_scalar, bs[k]));
           acc[k] = lrelu_max ? fmaxf(z, z * p.slope) : (z < 0.f ? z * p.slope : z);   // (gain applied with the scale)
         }
         if (p.out_nchw) {
