@@ -74,6 +74,8 @@ cases = [
     ("G conv3x3 32->32 @1024 (+ToRGB)", g_plain(1024, 32)),
     ("G conv3x3 64->64 @512 (+ToRGB)", g_plain(512, 64)),
     ("G conv3x3 128->128 @256 (+ToRGB)", g_plain(256, 128)),
+    ("G conv3x3 256->256 @128 (+ToRGB)", g_plain(128, 256)),
+    ("G conv3x3 512->512 @64 (+ToRGB)", g_plain(64, 512)),
     ("G up 64->32 @512->1024 (conv_up + fir)", g_up(512, 64, 32)),
     ("G up 256->128 @128->256 (conv_up + fir)", g_up(128, 256, 128)),
     ("E conv3x3 16->16 @1024", e_conv(1024, 16, 16)),
