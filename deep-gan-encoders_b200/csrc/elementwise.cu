@@ -398,28 +398,29 @@ __global__ void k_rgb_init_v4(const float* __restrict__ in, const float* __restr
 __global__ void __launch_bounds__(256)
 k_from_rgb(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ b,
            float* __restrict__ out, int n, int cimg, int c, int h, int wd, float slope) {
-  extern __shared__ float sw[];            // [c][cimg] weights then [c] bias
-  for (int i = threadIdx.x; i < c * cimg; i += blockDim.x) sw[i] = w[i];
-  for (int i = threadIdx.x; i < c; i += blockDim.x) sw[c * cimg + i] = b ? b[i] : 0.f;
+  extern __shared__ __align__(16) float sw[];            // [c][4] weights (zero-padded beyond cimg) then [c] bias
+  float* sb = sw + 4 * c;
+  for (int i = threadIdx.x; i < c * 4; i += blockDim.x) sw[i] = ((i & 3) < cimg) ? w[(i >> 2) * cimg + (i & 3)] : 0.f;
+  for (int i = threadIdx.x; i < c; i += blockDim.x) sb[i] = b ? b[i] : 0.f;
   __syncthreads();
   const int C8 = c >> 3;
-  const size_t total = (size_t)n * h * wd;
+  const size_t hw = (size_t)h * wd, total = (size_t)n * hw;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int x = (int)(i % wd);
-    const int y = (int)((i / wd) % h);
-    const int bn = (int)(i / ((size_t)wd * h));
+    const size_t bn = i / hw, pix = i - bn * hw;
     float px[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int ci = 0; ci < cimg && ci < 4; ++ci) px[ci] = img[(((size_t)bn * cimg + ci) * h + y) * wd + x];
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci)
+      if (ci < cimg) px[ci] = __ldg(img + (bn * cimg + ci) * hw + pix);
     for (int g = 0; g < C8; ++g) {
       float v[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int ch = g * 8 + k;
-        float a = sw[c * cimg + ch];
-        for (int ci = 0; ci < cimg && ci < 4; ++ci) a = fmaf(px[ci], sw[ch * cimg + ci], a);
+        const float4 wv = *reinterpret_cast<const float4*>(sw + 4 * ch);   // one 16-byte broadcast read per channel
+        const float a = fmaf(px[0], wv.x, fmaf(px[1], wv.y, fmaf(px[2], wv.z, fmaf(px[3], wv.w, sb[ch]))));
         v[k] = a < 0.f ? a * slope : a;
       }
-      store8_f32b(out, f32b_idx32(bn, g, y, x, C8, h, wd), v);
+      store8_f32b(out, (bn * C8 + g) * hw + pix, v);
     }
   }
 }
@@ -607,10 +608,11 @@ __global__ void __launch_bounds__(256)
 k_from_rgb_stats(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ b,
                  float* __restrict__ out, double* __restrict__ scratch, int cimg, int h, int wd, float slope) {
   constexpr int C = C8T * 8;
-  __shared__ float sw[C * 4 + C];
+  __shared__ __align__(16) float sw4[C * 4];
+  __shared__ float sb[C];
   __shared__ double red[8][2 * C];
-  for (int i = threadIdx.x; i < C * cimg; i += blockDim.x) sw[i] = w[i];
-  for (int i = threadIdx.x; i < C; i += blockDim.x) sw[C * cimg + i] = b ? b[i] : 0.f;
+  for (int i = threadIdx.x; i < C * 4; i += blockDim.x) sw4[i] = ((i & 3) < cimg) ? w[(i >> 2) * cimg + (i & 3)] : 0.f;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sb[i] = b ? b[i] : 0.f;
   __syncthreads();
   const int bn = blockIdx.y;
   const size_t hw = (size_t)h * wd;
@@ -619,16 +621,19 @@ k_from_rgb_stats(const float* __restrict__ img, const float* __restrict__ w, con
   for (int k = 0; k < C; ++k) s1[k] = s2[k] = 0.f;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < hw; i += (size_t)gridDim.x * blockDim.x) {
     float px[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int ci = 0; ci < cimg && ci < 4; ++ci) px[ci] = img[((size_t)bn * cimg + ci) * hw + i];
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci)
+      if (ci < cimg) px[ci] = __ldg(img + ((size_t)bn * cimg + ci) * hw + i);
 #pragma unroll
     for (int g = 0; g < C8T; ++g) {
       float v[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int ch = g * 8 + k;
-        float a = sw[C * cimg + ch];
-        for (int ci = 0; ci < cimg && ci < 4; ++ci) a = fmaf(px[ci], sw[ch * cimg + ci], a);
-        v[k] = a < 0.f ? a * slope : a;
+        // weights as 16-byte broadcast reads of a [ch][4] table (zero-padded beyond cimg): 2 LDS per channel, not 4
+        const float4 wv = *reinterpret_cast<const float4*>(sw4 + 4 * ch);
+        const float a = fmaf(px[0], wv.x, fmaf(px[1], wv.y, fmaf(px[2], wv.z, fmaf(px[3], wv.w, sb[ch]))));
+        v[k] = fmaxf(a, a * slope);
         s1[ch] += v[k];
         s2[ch] = fmaf(v[k], v[k], s2[ch]);
       }
@@ -1435,7 +1440,7 @@ int dge_from_rgb(const float* img, const float* w, const float* b, float* out, i
                  float slope, void* stream) {
   DGE_REQUIRE(img && w && out, "from_rgb: null pointer");
   DGE_REQUIRE(n > 0 && cimg > 0 && cimg <= 4 && c > 0 && c % 8 == 0 && c <= 2048 && h > 0 && wd > 0, "from_rgb: bad dims");
-  k_from_rgb<<<grid_for((size_t)n * h * wd, 256), 256, (size_t)(c * cimg + c) * sizeof(float), (cudaStream_t)stream>>>(
+  k_from_rgb<<<grid_for((size_t)n * h * wd, 256), 256, (size_t)(5 * c) * sizeof(float), (cudaStream_t)stream>>>(
       img, w, b, out, n, cimg, c, h, wd, slope);
   count_launch();
   return check_launch("k_from_rgb");
@@ -1506,7 +1511,7 @@ int dge_instance_norm_pool(const float* x, const float* mean_rstd, void* out_act
 int dge_from_rgb_stats(const float* img, const float* w, const float* b, float* out, double* scratch, float* style,
                        float* mean_rstd, int n, int cimg, int c, int h, int wd, float slope, float eps, void* stream) {
   DGE_REQUIRE(img && w && out && scratch && (style || mean_rstd), "from_rgb_stats: null pointer");
-  DGE_REQUIRE(n > 0 && cimg > 0 && cimg <= 4 && (c == 16 || c == 32) && h > 0 && wd > 0,
+  DGE_REQUIRE(n > 0 && cimg > 0 && cimg <= 4 && (c == 16 || c == 32) && h > 0 && wd > 0 && slope >= 0.f && slope <= 1.f,
               "from_rgb_stats: bad dims (c must be 16 or 32; use dge_from_rgb + dge_instance_stats otherwise)");
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * (size_t)n * c, st);
