@@ -37,6 +37,11 @@ PLAIN_CASES = [
     (2, 256, 64, 4, 4, 2),
     (2, 32, 48, 33, 31, 2),
     (2, 64, 64, 16, 16, 1),
+    (1, 64, 128, 16, 24, 2),     # CTA-pair mode with an ODD number of M tiles (the last pair has a dead second tile)
+    (3, 128, 256, 16, 8, 2),     # pair mode, 3 M tiles x 1 N tile
+    (1, 32, 512, 16, 24, 2),     # pair mode, odd M tiles x 2 N tiles
+    (2, 16, 32, 64, 48, 2),      # 4-block tiles (32x16) with a ragged right edge
+    (1, 16, 16, 40, 24, 2),      # 2x2-block tiles, ragged bottom edge
 ]
 
 
@@ -134,7 +139,8 @@ def test_conv3x3_pooled_output(case):
     assert _rel(res["f32b_pool"].to_nchw(), ref) < 2e-4
 
 
-UP_CASES = [(2, 32, 32, 8, 8), (2, 64, 32, 16, 16), (1, 64, 128, 9, 5), (2, 128, 256, 8, 8), (2, 32, 512, 4, 4)]
+UP_CASES = [(2, 32, 32, 8, 8), (2, 64, 32, 16, 16), (1, 64, 128, 9, 5), (2, 128, 256, 8, 8), (2, 32, 512, 4, 4),
+            (1, 128, 64, 16, 24), (3, 256, 128, 8, 8)]   # (the last two: pair mode with odd tile counts)
 
 
 @pytest.mark.parametrize("checker", [True, False], ids=["checker", "tcgen05"])
