@@ -929,6 +929,58 @@ __global__ void k_maxpool2_f32b(const float* __restrict__ x, float* __restrict__
 }
 
 // one thread per pixel; three passes over the channel groups (max, sum, write) -- the re-reads hit L1/L2
+// one WARP per pixel: lane l holds channel groups l, l+32, ... (<= 8 of them, c <= 2048) in registers, so the tensor is
+// read once and the max / sum are warp shuffles.  (The one-thread-per-pixel form below has only h*w threads per
+// sample -- 4096 for BigGAN's 64x64 attention map -- and reads the tensor three times.)
+__global__ void __launch_bounds__(256)
+k_channel_softmax_warp(const float* __restrict__ x, void* __restrict__ out, int n, int c, int h, int w, int planes) {
+  const int C8 = c >> 3;
+  const int lane = threadIdx.x & 31;
+  const size_t total = (size_t)n * h * w;
+  const size_t warp0 = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t i = warp0; i < total; i += nwarps) {
+    const int xx = (int)(i % w);
+    const int y = (int)((i / w) % h);
+    const int b = (int)(i / ((size_t)w * h));
+    float v[8][8];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = lane + 32 * j;
+      if (g < C8) {
+        load8_f32b(x, f32b_idx32(b, g, y, xx, C8, h, w), v[j]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mx = fmaxf(mx, v[j][k]);
+      }
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (lane + 32 * j < C8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          v[j][k] = expf(v[j][k] - mx);
+          sum += v[j][k];
+        }
+      }
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = lane + 32 * j;
+      if (g < C8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[j][k] *= inv;
+        store8_act(out, b, g, y, xx, C8, planes, h, w, v[j]);
+      }
+    }
+  }
+}
+
 __global__ void k_channel_softmax_to_act(const float* __restrict__ x, void* __restrict__ out, int n, int c, int h, int w,
                                          int planes) {
   const int C8 = c >> 3;
@@ -1638,6 +1690,7 @@ int dge_channel_softmax_to_act(const float* x, void* out_act, int n, int c, int 
   DGE_REQUIRE(x && out_act, "channel_softmax_to_act: null pointer");
   REQ_NCHW("channel_softmax_to_act");
   DGE_REQUIRE(planes == 1 || planes == 2, "channel_softmax_to_act: planes=%d", planes);
+  if (c <= 2048) LAUNCH_1D(k_channel_softmax_warp, (size_t)n * h * w * 32, stream, x, out_act, n, c, h, w, planes);
   LAUNCH_1D(k_channel_softmax_to_act, (size_t)n * h * w, stream, x, out_act, n, c, h, w, planes);
 }
 int dge_tanh_slice_nchw(const float* x, float* out, int n, int c, int nch, int hw, void* stream) {

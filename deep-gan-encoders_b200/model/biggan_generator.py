@@ -161,8 +161,14 @@ class BigGANBatchNorm(nn.Module):
         """Per-(n, c) affine (A, B) with y = x*A + B  ==  (x - mean)/sqrt(var+eps)*weight + bias  (:138-150)."""
         mean, var = self.stats(truncation)
         if self.conditional:
-            s = ops.dense(condition_vector.float(), sn_weight(self.scale).detach(), None)
-            o = ops.dense(condition_vector.float(), sn_weight(self.offset).detach(), None)
+            # effective spectral-norm weights: cached per parameter version in eval mode (the wrapper's hook costs three
+            # tiny library launches per layer per forward; train mode still runs it -- it updates u)
+            if not hasattr(self, '_prep'):
+                self._prep = _Prep()
+            ws, wo = self._prep.get(self, _sn_sources(self.scale) + _sn_sources(self.offset),
+                                    lambda: (sn_weight(self.scale).detach().clone(), sn_weight(self.offset).detach().clone()))
+            s = ops.dense(condition_vector.float(), ws, None)
+            o = ops.dense(condition_vector.float(), wo, None)
             return ops.cbn_coeffs(mean, var, self.eps, n, scale=s, offset=o)
         return ops.cbn_coeffs(mean, var, self.eps, n, weight=self.weight, bias=self.bias)
 
@@ -253,7 +259,10 @@ class Generator(nn.Module):
         ch = self.config.channel_width
         n = cond_vector.shape[0]
         cv = cond_vector.float().contiguous()
-        z = ops.dense(cv, sn_weight(self.gen_z).detach(), self.gen_z.bias)                 # :233
+        if not hasattr(self, '_prep_z'):
+            self._prep_z = _Prep()
+        wz = self._prep_z.get(self, _sn_sources(self.gen_z), lambda: sn_weight(self.gen_z).detach().clone())
+        z = ops.dense(cv, wz, self.gen_z.bias)                                             # :233
         z = z.view(-1, 4, 4, 16 * ch).permute(0, 3, 1, 2).contiguous()                    # TF NHWC -> NCHW (:237-239)
         x = ops.nchw_to_f32b(z)
         for layer in self.layers:

@@ -68,8 +68,9 @@ with torch.no_grad():
         perturb(m, 1)
     Gs, Gm, E1 = Gs.to(dev), Gm.to(dev), E1.to(dev)
     Gm.buffer1 = Gm.buffer1.to(dev)
-    if hasattr(E1, "set_noise_mode"):
-        E1.set_noise_mode("device")
+    for m in (E1, Gs):          # ours: draw the per-stage noise on the device (the reference draws it on the CPU)
+        if hasattr(m, "set_noise_mode"):
+            m.set_noise_mode("device")
     coefs = torch.ones(14, 1, device=dev)
     coefs[:7] = 0.7
     z = torch.randn(16, 512, device=dev)
@@ -92,6 +93,8 @@ with torch.no_grad():
     Ep = BE_PG(64, 512, 7, 512, 3, pggan=True).eval()
     perturb(Ep, 2)
     Ep = Ep.to(dev)
+    if hasattr(Ep, "set_noise_mode"):
+        Ep.set_noise_mode("device")
     for bs in (2, 16):
         zp = torch.randn(bs, 512, device=dev)
 
@@ -111,6 +114,8 @@ with torch.no_grad():
     Eb = BE_BIG(64, 512, 7, 512, 3, biggan=True).eval()
     perturb(Eb, 3)
     Eb = Eb.to(dev)
+    if hasattr(Eb, "set_noise_mode"):
+        Eb.set_noise_mode("device")
     zb = torch.randn(32, 128, device=dev).clamp_(-0.8, 0.8)
     label = torch.zeros(32, 1000, device=dev)
     label[:, 30] = 1
