@@ -450,7 +450,7 @@ __device__ __forceinline__ void epi_fold16(uint32_t* r, const uint32_t* s) {
 // experiment switches (timing only, wrong results): -DDGE_X_NOSTORE / _NORGB / _NOMATH
 template <int EPI>
 __device__ __forceinline__ void epi_group16(const ConvKParams& p, const float* tab, const EpiPix& px, int co0, int p0,
-                                            int q, int c, const uint32_t* r, float* rgb) {
+                                            int q, int c, const uint32_t* r, float* rgb, const float* bl = nullptr) {
   float v[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
@@ -536,6 +536,9 @@ __device__ __forceinline__ void epi_group16(const ConvKParams& p, const float* t
             }
 #pragma unroll
           for (int j = 0; j < 8; ++j) sv[j] *= 0.25f;
+        } else if (bl) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sv[j] = bl[8 * g + j];   // fetched one unit ahead (see the unit loop)
         } else {
           load8_f32b(p.blend_src, f32b_idx32(px.n, g0 + g, px.y, px.x, C8, H, W), sv);
         }
@@ -801,7 +804,7 @@ __device__ __forceinline__ int sched_tile(const ConvKParams& p, int unit, uint32
   return mt * p.n_ntiles + nt;
 }
 
-template <int EPI, bool PAIR>  // EPI: 0 = pointwise, 1 = raw up
+template <int EPI, bool PAIR>  // EPI: 0 = pointwise, 1 = raw up, 2 = pointwise with the residual blend fetched ahead
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ ConvKParams p) {
@@ -998,12 +1001,12 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
     };
-    if (EPI == 0 && p.noise && t_first < p.sched_tiles) fetch_noise(t_first);
+    if (EPI != 1 && p.noise && t_first < p.sched_tiles) fetch_noise(t_first);
     const uint32_t tm_empty_leader = PAIR ? mapa_shared(smem_u32(&tm_empty[0]), 0) : 0u;
     for (int unit = t_first; unit < p.sched_tiles; unit += t_step) {
       bool live;
       const TileCoord t = decode_tile(p, sched_tile<PAIR>(p, unit, rank, live));
-      if (EPI == 0 && (t.n != cur_n || t.co0 != cur_co0)) {
+      if (EPI != 1 && (t.n != cur_n || t.co0 != cur_co0)) {
         // per-(sample, N tile) parameter table: one cooperative reload when the sample changes (tiles are visited
         // in sample order), then every per-channel parameter is a broadcast LDS.128 instead of a global load
         epi_bar_sync();
@@ -1015,7 +1018,7 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       float nz_cur[4];
 #pragma unroll
       for (int sb = 0; sb < 4; ++sb) nz_cur[sb] = nz_next[sb];
-      if (EPI == 0 && p.noise && unit + t_step < p.sched_tiles) fetch_noise(unit + t_step);
+      if (EPI != 1 && p.noise && unit + t_step < p.sched_tiles) fetch_noise(unit + t_step);
       ROLE_ACC(rt_proc);
       mbar_wait_relaxed(&tm_full[acc], acc_ph);
       ROLE_ACC(rt_full);
@@ -1035,9 +1038,26 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int cur_sb = -1;
       uint32_t r0[16], r1[16], sx[16];
       const bool any = u_sq < nsq && u_c < p.cw;
+      // same-resolution residual blend (E.py:81-84 with the pooled conv_2 output): its 2 x 32 bytes per unit are
+      // requested ONE UNIT AHEAD into the (otherwise unused) `sx` registers -- fetched at the point of use, their
+      // L2/HBM latency was the critical path of the 1x1 residual convs
+      constexpr bool blend_pf = EPI == 2;   // (own instantiation: the prefetch registers must not weigh on the other paths)
+      auto blend_fetch = [&](int sq, int c) {
+        const int sbn = sq >> p.np_shift;
+        const int y = t.y0 + p.sb_y[sbn] + ty, x = t.x0 + p.sb_x[sbn] + tx;
+        if (live && y < p.dom_h && x < p.dom_w) {
+          const int C8 = p.Cout >> 3;
+          float tmp[16];
+          load8_f32b(p.blend_src, f32b_idx32(t.n, ((t.co0 + c) >> 3), y, x, C8, p.H, p.W), tmp);
+          load8_f32b(p.blend_src, f32b_idx32(t.n, ((t.co0 + c) >> 3) + 1, y, x, C8, p.H, p.W), tmp + 8);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sx[j] = __float_as_uint(tmp[j]);
+        }
+      };
       if (any) {
         tm_ld16_issue(taddr + u_sq * p.acc_cols + u_c, r0);
         if (p.stack) tm_ld16_issue(taddr + u_sq * p.acc_cols + u_c + p.cw, sx);
+        if (blend_pf) blend_fetch(u_sq, u_c);
       }
       auto step = [&](uint32_t (&bc)[16], uint32_t (&bn)[16]) -> bool {
         tm_ld16_wait(bc);
@@ -1060,8 +1080,16 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           px.valid = live && (px.y < p.dom_h) && (px.x < p.dom_w);
           px.nz = sb == 0 ? nz_cur[0] : (sb == 1 ? nz_cur[1] : (sb == 2 ? nz_cur[2] : nz_cur[3]));
         }
-        epi_group16<EPI>(p, epi_tab, px, t.co0, t.p0, q, u_c, bc, rgb);
-        if (EPI == 0 && p.rgb_w && (!n_valid || (n_sq >> p.np_shift) != sb)) {   // last unit of an M block
+        if (blend_pf) {
+          float bl[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) bl[j] = __uint_as_float(sx[j]);
+          if (n_valid) blend_fetch(n_sq, n_c);
+          epi_group16<EPI>(p, epi_tab, px, t.co0, t.p0, q, u_c, bc, rgb, bl);
+        } else {
+          epi_group16<EPI>(p, epi_tab, px, t.co0, t.p0, q, u_c, bc, rgb);
+        }
+        if (EPI != 1 && p.rgb_w && (!n_valid || (n_sq >> p.np_shift) != sb)) {   // last unit of an M block
           if (px.valid) {
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch)
@@ -1122,7 +1150,7 @@ __global__ void __launch_bounds__(128) conv_checker_kernel(const __grid_constant
     px.x = t.x0 + tx;
     px.valid = (px.y < p.dom_h) && (px.x < p.dom_w);
     px.nz = 0.f;
-    if (EPI == 0 && p.noise && px.valid)
+    if (EPI != 1 && p.noise && px.valid)
       px.nz = __ldg(p.noise + (size_t)px.n * p.noise_bstride + (size_t)px.y * p.W + px.x);
     float rgb[3] = {0.f, 0.f, 0.f};
     for (int q = 0; q < p.np; ++q) {
@@ -1161,13 +1189,13 @@ __global__ void __launch_bounds__(128) conv_checker_kernel(const __grid_constant
             }
           }
         }
-        if (EPI == 0)
+        if (EPI != 1)
           epi_pointwise16(p, px, t.co0 + c, v, rgb);
         else
           epi_rawup16(p, px.n, px.y, px.x, px.valid, t.p0 + q, t.co0 + c, v);
       }
     }
-    if (EPI == 0 && p.rgb_w && px.valid) {
+    if (EPI != 1 && p.rgb_w && px.valid) {
       for (int ch = 0; ch < 3; ++ch)
         atomicAdd(p.rgb_out + (((size_t)px.n * 3 + ch) * p.H + px.y) * p.W + px.x, rgb[ch]);
     }
@@ -1303,6 +1331,8 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
     if (stack_max < 0) stack_max = getenv("DGE_STACK_MAX") ? atoi(getenv("DGE_STACK_MAX")) : 64;   // A/B switch
     const int lim = p.np == 1 ? stack_max : 48;   // (4-phase tiles: 2*cw*4 columns must leave room for two stages)
     p.stack = (p.planes == 2 && p.cw <= lim && p.np * 2 * p.cw <= 512) ? 1 : 0;
+    // the 1x1 residual convs are bound by their blend loads, not by MMAs: keep `sx` free for the blend prefetch
+    if (a->kind == DGE_CONV_1X1 && a->blend_src && !a->blend_pool) p.stack = 0;
   }
   p.acc_cols = p.cw * (p.stack ? 2 : 1);
   p.sb_cols = p.np * p.acc_cols;
@@ -1537,10 +1567,14 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
   // TMEM is 512 columns per SM: keep co-resident CTAs * tmem_cols <= 512 by padding the smem request.
   const size_t min_smem = (227 * 1024) / (max_occ + 1) + 1024;
   if (smem < min_smem) smem = min_smem;
-  static bool attr_set[4] = {false, false, false, false};
-  const int ei = (up ? 1 : 0) + (p.pair ? 2 : 0);
-  const void* kfn = p.pair ? (up ? (const void*)conv_mma_kernel<1, true> : (const void*)conv_mma_kernel<0, true>)
-                           : (up ? (const void*)conv_mma_kernel<1, false> : (const void*)conv_mma_kernel<0, false>);
+  static bool attr_set[6] = {false, false, false, false, false, false};
+  // EPI 2: 1x1 residual convs with a same-resolution blend (their blend loads are prefetched one unit ahead)
+  const int epi = up ? 1 : ((a->kind == DGE_CONV_1X1 && a->blend_src && !a->blend_pool && !p.stack) ? 2 : 0);
+  const int ei = epi + (p.pair ? 3 : 0);
+  const void* ktab[6] = {(const void*)conv_mma_kernel<0, false>, (const void*)conv_mma_kernel<1, false>,
+                         (const void*)conv_mma_kernel<2, false>, (const void*)conv_mma_kernel<0, true>,
+                         (const void*)conv_mma_kernel<1, true>,  (const void*)conv_mma_kernel<2, true>};
+  const void* kfn = ktab[ei];
   if (!attr_set[ei]) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
