@@ -355,7 +355,7 @@ def conv_bytes(key, name):
 
 def ncu_traffic(name, key):
     """DRAM bytes per launch of this launch class from the committed ncu capture (None if it was not captured)."""
-    path = os.path.join(ROOT, "profiles", "r1c_top_kernels_ncu.json")
+    path = os.path.join(ROOT, "profiles", "r1d_top_kernels_ncu.json")
     if not os.path.exists(path) or name != "conv3x3":
         return None
     n, h, w, cin, cout = key[:5]
@@ -393,7 +393,7 @@ def conv_roofline(d, pk):
                 "note": "algorithmic bytes = ACT operand read once + output written once (4 B/element each)"}
     roof["traffic"] = ncu_traffic(name, key)
     roof["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum of one launch of this shape from the committed "
-                            "ncu --set full capture (profiles/r1c_top_kernels_ncu.json)") if roof["traffic"] else None
+                            "ncu --set full capture (profiles/r1d_top_kernels_ncu.json)") if roof["traffic"] else None
     roof["kernel"] = f"{name} n,h,w,cin,cout,planes={list(key)}"
     roof["ms_per_launch"] = d["ms_per_launch"]
     roof["peak_source"] = pk["source"] + " (sustained bf16 / copy bandwidth, MEASURED_PEAKS.json)"
