@@ -85,6 +85,10 @@ struct ConvKParams {
   int sched_tiles;         // scheduling units: tiles, or tile PAIRS (two M tiles, same N tile) in pair mode
   int mtiles;              // M tiles (sample x tile rows x tile columns)
   int pair;                // 1: CTA pair (cta_group::2) launch
+  int ksplit;              // split-K factor: unit = (tile or pair, K part); partial sums are ADDED atomically to `ws`
+  int sched_units;         // sched_tiles * ksplit
+  FastDiv div_ksplit;
+  float* ws;               // split-K scratch, F32B [n][cout/8][h][w][8] (zeroed by the host wrapper)
   int nsub_local;          // weight rows this CTA holds in smem per slab (= nsub, or nsub/2 in pair mode)
   int ntaps;
   TapEntry taps[16];
@@ -247,10 +251,9 @@ struct PixelCtx {
   float nz;
 };
 
-// pointwise epilogue on 16 consecutive output channels c0..c0+15 of one pixel
-__device__ __forceinline__ void epi_pointwise16(const ConvKParams& p, const PixelCtx& px, int c0, float* v,
-                                                float* rgb) {
-  const int H = p.H, W = p.W, C8 = p.Cout >> 3;
+// value part of the pointwise epilogue: demod, noise, bias, pre-activation residual, activation, gain
+__device__ __forceinline__ void epi_value16(const ConvKParams& p, const PixelCtx& px, int c0, float* v) {
+  const int H = p.H, W = p.W;
   if (p.demod) {
     const float4* d = reinterpret_cast<const float4*>(p.demod + (size_t)px.n * p.Cout + c0);
 #pragma unroll
@@ -286,6 +289,14 @@ __device__ __forceinline__ void epi_pointwise16(const ConvKParams& p, const Pixe
   }
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = (v[j] < 0.f ? v[j] * p.slope : v[j]) * p.gain;
+}
+
+// pointwise epilogue on 16 consecutive output channels c0..c0+15 of one pixel (generic form: the CUDA-core checker
+// kernel and the split-K finish kernel; the tcgen05 kernel has its own table-driven version, epi_group16)
+__device__ __forceinline__ void epi_pointwise16(const ConvKParams& p, const PixelCtx& px, int c0, float* v,
+                                                float* rgb) {
+  const int H = p.H, W = p.W, C8 = p.Cout >> 3;
+  epi_value16(p, px, c0, v);
   if (!px.valid) return;
   if (p.blend_src) {
 #pragma unroll
@@ -347,6 +358,7 @@ __device__ __forceinline__ void epi_pointwise16(const ConvKParams& p, const Pixe
 }
 
 // raw transposed-conv epilogue: pixel (Y,X) of the (H+1)x(W+1) domain, phase (py,px) -> t[2Y+py][2X+px]
+template <bool SPLITK>
 __device__ __forceinline__ void epi_rawup16(const ConvKParams& p, int n, int Y, int X, bool valid, int phase, int c0,
                                             const float* v) {
   const int py = phase >> 1, pxs = phase & 1;
@@ -354,6 +366,15 @@ __device__ __forceinline__ void epi_rawup16(const ConvKParams& p, int n, int Y, 
   const int oy = 2 * Y + py, ox = 2 * X + pxs;
   if (!valid || oy >= Ho || ox >= Wo) return;
   const int C8 = p.Cout >> 3;
+  if (SPLITK) {   // split-K: the raw map is linear in the accumulator -- partial sums are added in place
+    float4* o0 = reinterpret_cast<float4*>(p.out_raw_up) + f32b_idx32(n, c0 >> 3, oy, ox, C8, Ho, Wo) * 2;
+    float4* o1 = reinterpret_cast<float4*>(p.out_raw_up) + f32b_idx32(n, (c0 >> 3) + 1, oy, ox, C8, Ho, Wo) * 2;
+    atomicAdd(o0, make_float4(v[0], v[1], v[2], v[3]));
+    atomicAdd(o0 + 1, make_float4(v[4], v[5], v[6], v[7]));
+    atomicAdd(o1, make_float4(v[8], v[9], v[10], v[11]));
+    atomicAdd(o1 + 1, make_float4(v[12], v[13], v[14], v[15]));
+    return;
+  }
   store8_f32b(p.out_raw_up, f32b_idx32(n, c0 >> 3, oy, ox, C8, Ho, Wo), v);
   store8_f32b(p.out_raw_up, f32b_idx32(n, (c0 >> 3) + 1, oy, ox, C8, Ho, Wo), v + 8);
 }
@@ -448,14 +469,29 @@ __device__ __forceinline__ void epi_fold16(uint32_t* r, const uint32_t* s) {
 }
 
 // experiment switches (timing only, wrong results): -DDGE_X_NOSTORE / _NORGB / _NOMATH
-template <int EPI>
+template <int EPI, bool SPLITK>
 __device__ __forceinline__ void epi_group16(const ConvKParams& p, const float* tab, const EpiPix& px, int co0, int p0,
                                             int q, int c, const uint32_t* r, float* rgb, const float* bl = nullptr) {
   float v[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
   if (EPI == 1) {
-    epi_rawup16(p, px.n, px.y, px.x, px.valid, p0 + q, co0 + c, v);
+    epi_rawup16<SPLITK>(p, px.n, px.y, px.x, px.valid, p0 + q, co0 + c, v);
+    __syncwarp();
+    return;
+  }
+  if (SPLITK) {
+    // split-K: this CTA holds a partial sum over its K chunks -- add it to the scratch map; the nonlinear epilogue
+    // runs in conv_splitk_finish_kernel once every part has landed
+    if (px.valid) {
+      const size_t HWs = (size_t)p.H * p.W;
+      float4* o = reinterpret_cast<float4*>(p.ws) +
+                  ((((size_t)px.n * (p.Cout >> 3) + ((co0 + c) >> 3)) * HWs + (size_t)px.y * p.W + px.x) * 2);
+      atomicAdd(o, make_float4(v[0], v[1], v[2], v[3]));
+      atomicAdd(o + 1, make_float4(v[4], v[5], v[6], v[7]));
+      atomicAdd(o + 2 * HWs, make_float4(v[8], v[9], v[10], v[11]));
+      atomicAdd(o + 2 * HWs + 1, make_float4(v[12], v[13], v[14], v[15]));
+    }
     __syncwarp();
     return;
   }
@@ -652,6 +688,21 @@ __device__ __forceinline__ void issue_tap(uint32_t d, uint64_t da, uint64_t db, 
   }
 }
 
+// split-K: scheduling unit u = su * ksplit + ks works on K chunks [c0, c1) of tile unit su
+template <bool SPLITK>
+__device__ __forceinline__ int sched_split(const ConvKParams& p, int unit, int& c0, int& c1) {
+  if (!SPLITK) {
+    c0 = 0;
+    c1 = p.nchunks;
+    return unit;
+  }
+  const int su = (int)fast_div((uint32_t)unit, p.div_ksplit);
+  const int ks = unit - su * p.ksplit;
+  c0 = (ks * p.nchunks) / p.ksplit;
+  c1 = ((ks + 1) * p.nchunks) / p.ksplit;
+  return su;
+}
+
 // per-CTA barrier / shared-memory handles of the MMA role
 struct MmaBars {
   uint64_t *a_full, *a_empty, *b_full, *b_empty, *tm_full, *tm_empty;
@@ -663,7 +714,7 @@ struct MmaBars {
 // unless the per-chunk code is straight-line: TPC (taps per chunk) and KSTEPS > 0 unroll everything between two
 // barrier waits; all operands derive from kernel parameters and uniform counters.  TPC == 0 / KSTEPS == 0 are the
 // generic runtime-loop forms.
-template <int MODE, bool RESIDENT, int TPC, int KSTEPS, bool PAIR>
+template <int MODE, bool RESIDENT, int TPC, int KSTEPS, bool PAIR, bool SPLITK>
 __device__ __forceinline__ void mma_tiles(const ConvKParams& p, const MmaBars& m, const IssueConsts& ic,
                                           uint64_t a_desc0, uint64_t b_desc0) {
   uint32_t a_slot = 0, a_ph = 0, b_slot = 0, b_ph = 0, acc = 0, acc_ph = 0;
@@ -677,21 +728,23 @@ __device__ __forceinline__ void mma_tiles(const ConvKParams& p, const MmaBars& m
   ROLE_T0();
   const int t_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int t_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  for (int tile = t_first; tile < p.sched_tiles; tile += t_step) {
+  for (int unit = t_first; unit < p.sched_units; unit += t_step) {
+    int ch0, ch1;
+    sched_split<SPLITK>(p, unit, ch0, ch1);
     ROLE_ACC(rt_issue);
     mbar_wait(&m.tm_empty[acc], acc_ph ^ 1);
     ROLE_ACC(rt_tm);
     tc_fence_after();
     const uint32_t d_base = m.tm_base + acc * p.tm_stride;
-    uint32_t b_res16 = m.b_region16;     // resident mode: slabs in (chunk, tap) issue order
-    for (int ch = 0; ch < p.nchunks; ++ch) {
+    uint32_t b_res16 = m.b_region16 + (uint32_t)(ch0 * tpc) * m.b_slot16;   // resident: slabs in (chunk, tap) order
+    for (int ch = ch0; ch < ch1; ++ch) {
       ROLE_ACC(rt_issue);
       mbar_wait(&m.a_full[a_slot], a_ph);
       ROLE_ACC(rt_a);
       tc_fence_after();
       const uint64_t a_desc = a_desc0 + (m.a_smem16 + a_slot * m.a_slot16);
       const int l0 = (p.n_cph > 1) ? ((ch * p.kc) / p.cin_w) * tpc : 0;
-      const uint32_t first_chunk = ch == 0 ? 1u : 0u;
+      const uint32_t first_chunk = ch == ch0 ? 1u : 0u;
       if (RESIDENT) {
         if (elect_one_sync()) {
 #pragma unroll 1
@@ -754,25 +807,25 @@ __device__ __forceinline__ void mma_tiles(const ConvKParams& p, const MmaBars& m
 }
 
 // pick the unrolled form for the shapes the hot layers use; everything else runs the generic loops
-template <int MODE, bool RESIDENT, bool PAIR>
+template <int MODE, bool RESIDENT, bool PAIR, bool SPLITK>
 __device__ __forceinline__ void mma_dispatch(const ConvKParams& p, const MmaBars& m, const IssueConsts& ic,
                                              uint64_t a_desc0, uint64_t b_desc0) {
   const int key = p.tpc * 8 + ic.ksteps;
   if (RESIDENT) {
     switch (key) {
-      case 9 * 8 + 1: mma_tiles<MODE, true, 9, 1, PAIR>(p, m, ic, a_desc0, b_desc0); break;
-      case 9 * 8 + 2: mma_tiles<MODE, true, 9, 2, PAIR>(p, m, ic, a_desc0, b_desc0); break;
-      case 9 * 8 + 4: mma_tiles<MODE, true, 9, 4, PAIR>(p, m, ic, a_desc0, b_desc0); break;
-      case 1 * 8 + 1: mma_tiles<MODE, true, 1, 1, PAIR>(p, m, ic, a_desc0, b_desc0); break;
-      case 1 * 8 + 2: mma_tiles<MODE, true, 1, 2, PAIR>(p, m, ic, a_desc0, b_desc0); break;
-      case 1 * 8 + 4: mma_tiles<MODE, true, 1, 4, PAIR>(p, m, ic, a_desc0, b_desc0); break;
-      default: mma_tiles<MODE, true, 0, 0, PAIR>(p, m, ic, a_desc0, b_desc0); break;
+      case 9 * 8 + 1: mma_tiles<MODE, true, 9, 1, PAIR, SPLITK>(p, m, ic, a_desc0, b_desc0); break;
+      case 9 * 8 + 2: mma_tiles<MODE, true, 9, 2, PAIR, SPLITK>(p, m, ic, a_desc0, b_desc0); break;
+      case 9 * 8 + 4: mma_tiles<MODE, true, 9, 4, PAIR, SPLITK>(p, m, ic, a_desc0, b_desc0); break;
+      case 1 * 8 + 1: mma_tiles<MODE, true, 1, 1, PAIR, SPLITK>(p, m, ic, a_desc0, b_desc0); break;
+      case 1 * 8 + 2: mma_tiles<MODE, true, 1, 2, PAIR, SPLITK>(p, m, ic, a_desc0, b_desc0); break;
+      case 1 * 8 + 4: mma_tiles<MODE, true, 1, 4, PAIR, SPLITK>(p, m, ic, a_desc0, b_desc0); break;
+      default: mma_tiles<MODE, true, 0, 0, PAIR, SPLITK>(p, m, ic, a_desc0, b_desc0); break;
     }
   } else {
     switch (ic.ksteps) {
-      case 2: mma_tiles<MODE, false, 0, 2, PAIR>(p, m, ic, a_desc0, b_desc0); break;
-      case 4: mma_tiles<MODE, false, 0, 4, PAIR>(p, m, ic, a_desc0, b_desc0); break;
-      default: mma_tiles<MODE, false, 0, 0, PAIR>(p, m, ic, a_desc0, b_desc0); break;
+      case 2: mma_tiles<MODE, false, 0, 2, PAIR, SPLITK>(p, m, ic, a_desc0, b_desc0); break;
+      case 4: mma_tiles<MODE, false, 0, 4, PAIR, SPLITK>(p, m, ic, a_desc0, b_desc0); break;
+      default: mma_tiles<MODE, false, 0, 0, PAIR, SPLITK>(p, m, ic, a_desc0, b_desc0); break;
     }
   }
 }
@@ -804,7 +857,8 @@ __device__ __forceinline__ int sched_tile(const ConvKParams& p, int unit, uint32
   return mt * p.n_ntiles + nt;
 }
 
-template <int EPI, bool PAIR>  // EPI: 0 = pointwise, 1 = raw up, 2 = pointwise with the residual blend fetched ahead
+template <int EPI, bool PAIR, bool SPLITK>  // EPI: 0 = pointwise, 1 = raw up, 2 = pointwise with the residual blend
+                                           // fetched ahead; SPLITK: partial sums over a K range, added atomically
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ ConvKParams p) {
@@ -889,10 +943,12 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     [[maybe_unused]] long long rt_wait = 0, rt_work = 0;
     ROLE_T0();
-    for (int unit = t_first; unit < p.sched_tiles; unit += t_step) {
+    for (int unit = t_first; unit < p.sched_units; unit += t_step) {
       bool live;
-      const TileCoord t = decode_tile(p, sched_tile<PAIR>(p, unit, rank, live));
-      for (int ch = 0; ch < p.nchunks; ++ch) {
+      int ch0, ch1;
+      const int su = sched_split<SPLITK>(p, unit, ch0, ch1);
+      const TileCoord t = decode_tile(p, sched_tile<PAIR>(p, su, rank, live));
+      for (int ch = ch0; ch < ch1; ++ch) {
         ROLE_ACC(rt_work);
         mbar_wait(&a_empty[a_slot], a_ph ^ 1);
         ROLE_ACC(rt_wait);
@@ -954,21 +1010,21 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // only the leader CTA issues (its MMAs drive both SMs); pairs are never combined with the stacked mode
       if (rank == 0) {
         if (p.resident) {
-          if (mma_mode == 1) mma_dispatch<1, true, true>(p, mb, ic, a_desc0, b_desc0);
-          else mma_dispatch<0, true, true>(p, mb, ic, a_desc0, b_desc0);
+          if (mma_mode == 1) mma_dispatch<1, true, true, SPLITK>(p, mb, ic, a_desc0, b_desc0);
+          else mma_dispatch<0, true, true, SPLITK>(p, mb, ic, a_desc0, b_desc0);
         } else {
-          if (mma_mode == 1) mma_dispatch<1, false, true>(p, mb, ic, a_desc0, b_desc0);
-          else mma_dispatch<0, false, true>(p, mb, ic, a_desc0, b_desc0);
+          if (mma_mode == 1) mma_dispatch<1, false, true, SPLITK>(p, mb, ic, a_desc0, b_desc0);
+          else mma_dispatch<0, false, true, SPLITK>(p, mb, ic, a_desc0, b_desc0);
         }
       }
     } else if (p.resident) {
-      if (mma_mode == 2) mma_dispatch<2, true, false>(p, mb, ic, a_desc0, b_desc0);
-      else if (mma_mode == 1) mma_dispatch<1, true, false>(p, mb, ic, a_desc0, b_desc0);
-      else mma_dispatch<0, true, false>(p, mb, ic, a_desc0, b_desc0);
+      if (mma_mode == 2) mma_dispatch<2, true, false, SPLITK>(p, mb, ic, a_desc0, b_desc0);
+      else if (mma_mode == 1) mma_dispatch<1, true, false, SPLITK>(p, mb, ic, a_desc0, b_desc0);
+      else mma_dispatch<0, true, false, SPLITK>(p, mb, ic, a_desc0, b_desc0);
     } else {
-      if (mma_mode == 2) mma_dispatch<2, false, false>(p, mb, ic, a_desc0, b_desc0);
-      else if (mma_mode == 1) mma_dispatch<1, false, false>(p, mb, ic, a_desc0, b_desc0);
-      else mma_dispatch<0, false, false>(p, mb, ic, a_desc0, b_desc0);
+      if (mma_mode == 2) mma_dispatch<2, false, false, SPLITK>(p, mb, ic, a_desc0, b_desc0);
+      else if (mma_mode == 1) mma_dispatch<1, false, false, SPLITK>(p, mb, ic, a_desc0, b_desc0);
+      else mma_dispatch<0, false, false, SPLITK>(p, mb, ic, a_desc0, b_desc0);
     }
   } else {
     // =================================== epilogue ========================================
@@ -990,7 +1046,8 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     float nz_next[4] = {0.f, 0.f, 0.f, 0.f};
     auto fetch_noise = [&](int unit_idx) {
       bool live_n;
-      const TileCoord tn = decode_tile(p, sched_tile<PAIR>(p, unit_idx, rank, live_n));
+      int cu0, cu1;
+      const TileCoord tn = decode_tile(p, sched_tile<PAIR>(p, sched_split<SPLITK>(p, unit_idx, cu0, cu1), rank, live_n));
 #pragma unroll
       for (int sb = 0; sb < 4; ++sb) {
         nz_next[sb] = 0.f;
@@ -1001,12 +1058,14 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
     };
-    if (EPI != 1 && p.noise && t_first < p.sched_tiles) fetch_noise(t_first);
+    const bool want_noise = EPI != 1 && !SPLITK && p.noise;
+    if (want_noise && t_first < p.sched_units) fetch_noise(t_first);
     const uint32_t tm_empty_leader = PAIR ? mapa_shared(smem_u32(&tm_empty[0]), 0) : 0u;
-    for (int unit = t_first; unit < p.sched_tiles; unit += t_step) {
+    for (int unit = t_first; unit < p.sched_units; unit += t_step) {
       bool live;
-      const TileCoord t = decode_tile(p, sched_tile<PAIR>(p, unit, rank, live));
-      if (EPI != 1 && (t.n != cur_n || t.co0 != cur_co0)) {
+      int cu0, cu1;
+      const TileCoord t = decode_tile(p, sched_tile<PAIR>(p, sched_split<SPLITK>(p, unit, cu0, cu1), rank, live));
+      if (EPI != 1 && !SPLITK && (t.n != cur_n || t.co0 != cur_co0)) {
         // per-(sample, N tile) parameter table: one cooperative reload when the sample changes (tiles are visited
         // in sample order), then every per-channel parameter is a broadcast LDS.128 instead of a global load
         epi_bar_sync();
@@ -1018,7 +1077,7 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       float nz_cur[4];
 #pragma unroll
       for (int sb = 0; sb < 4; ++sb) nz_cur[sb] = nz_next[sb];
-      if (EPI != 1 && p.noise && unit + t_step < p.sched_tiles) fetch_noise(unit + t_step);
+      if (want_noise && unit + t_step < p.sched_units) fetch_noise(unit + t_step);
       ROLE_ACC(rt_proc);
       mbar_wait_relaxed(&tm_full[acc], acc_ph);
       ROLE_ACC(rt_full);
@@ -1085,9 +1144,9 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
           for (int j = 0; j < 16; ++j) bl[j] = __uint_as_float(sx[j]);
           if (n_valid) blend_fetch(n_sq, n_c);
-          epi_group16<EPI>(p, epi_tab, px, t.co0, t.p0, q, u_c, bc, rgb, bl);
+          epi_group16<EPI, SPLITK>(p, epi_tab, px, t.co0, t.p0, q, u_c, bc, rgb, bl);
         } else {
-          epi_group16<EPI>(p, epi_tab, px, t.co0, t.p0, q, u_c, bc, rgb);
+          epi_group16<EPI, SPLITK>(p, epi_tab, px, t.co0, t.p0, q, u_c, bc, rgb);
         }
         if (EPI != 1 && p.rgb_w && (!n_valid || (n_sq >> p.np_shift) != sb)) {   // last unit of an M block
           if (px.valid) {
@@ -1131,6 +1190,61 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     else
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
                    : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// split-K finish: the complete (generic) pointwise epilogue over the summed scratch map.  One thread per
+// (sample, pixel, 16-channel group); with out_pool one thread per POOLED pixel (it evaluates the four source pixels).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv_splitk_finish_kernel(const __grid_constant__ ConvKParams p) {
+  const int C16 = p.Cout >> 4, C8 = p.Cout >> 3;
+  const int Ho = p.out_pool ? p.H >> 1 : p.H, Wo = p.out_pool ? p.W >> 1 : p.W;
+  const size_t total = (size_t)p.N * C16 * Ho * Wo;
+  const size_t HW = (size_t)p.H * p.W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % Wo);
+    size_t tt = i / Wo;
+    const int y = (int)(tt % Ho);
+    tt /= Ho;
+    const int g16 = (int)(tt % C16);
+    const int n = (int)(tt / C16);
+    const int c0 = g16 * 16;
+    auto load_px = [&](int yy, int xx, float* v, PixelCtx& px) {
+      px.n = n; px.y = yy; px.x = xx; px.valid = true;
+      px.nz = p.noise ? __ldg(p.noise + (size_t)n * p.noise_bstride + (size_t)yy * p.W + xx) : 0.f;
+      load8_f32b(p.ws, ((size_t)n * C8 + (c0 >> 3)) * HW + (size_t)yy * p.W + xx, v);
+      load8_f32b(p.ws, ((size_t)n * C8 + (c0 >> 3) + 1) * HW + (size_t)yy * p.W + xx, v + 8);
+    };
+    if (p.out_pool) {
+      float acc[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+      for (int dy = 0; dy < 2; ++dy)
+        for (int dx = 0; dx < 2; ++dx) {
+          float v[16];
+          PixelCtx px;
+          load_px(2 * y + dy, 2 * x + dx, v, px);
+          epi_value16(p, px, c0, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] += v[j];
+        }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] *= 0.25f;
+      const size_t HWp = (size_t)Ho * Wo;
+      const size_t o = ((size_t)n * C8 + (c0 >> 3)) * HWp + (size_t)y * Wo + x;
+      store8_f32b(p.out_f32b, o, acc);
+      store8_f32b(p.out_f32b, o + HWp, acc + 8);
+    } else {
+      float v[16], rgb[3] = {0.f, 0.f, 0.f};
+      PixelCtx px;
+      load_px(y, x, v, px);
+      epi_pointwise16(p, px, c0, v, rgb);
+      if (p.rgb_w) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) atomicAdd(p.rgb_out + (((size_t)n * 3 + ch) * p.H + y) * p.W + x, rgb[ch]);
+      }
+    }
   }
 }
 
@@ -1192,7 +1306,7 @@ __global__ void __launch_bounds__(128) conv_checker_kernel(const __grid_constant
         if (EPI != 1)
           epi_pointwise16(p, px, t.co0 + c, v, rgb);
         else
-          epi_rawup16(p, px.n, px.y, px.x, px.valid, t.p0 + q, t.co0 + c, v);
+          epi_rawup16<false>(p, px.n, px.y, px.x, px.valid, t.p0 + q, t.co0 + c, v);
       }
     }
     if (EPI != 1 && p.rgb_w && px.valid) {
@@ -1258,6 +1372,27 @@ static int largest_div(int value, int cap, int step) {
 
 static int g_num_sms = 0;
 
+// Split-K is used for the small maps (<= 16x16 at batch 8): so few output tiles that most SMs would idle while each
+// CTA walks the full serial K chain (9 taps x 512 channels = 288 K steps, ~26 us).  The K chunks are divided over up to 8
+// CTAs per tile; partial sums are added to a zeroed fp32 scratch map and a small finish kernel applies the epilogue.
+// (The transposed conv's raw map is linear in the accumulator, so its parts are added in place -- no scratch.)
+static bool splitk_wanted(const dge_conv_args* a, int cw_full, int num_sms) {
+  static int off = -1;
+  if (off < 0) off = getenv("DGE_NO_SPLITK") ? 1 : 0;
+  if (off || (a->flags & DGE_CONV_FLAG_CHECKER)) return false;
+  const bool up = a->kind == DGE_CONV_UP3X3;
+  const int dom_h = up ? a->h + 1 : a->h, dom_w = up ? a->w + 1 : a->w;
+  const long long mt = (long long)a->n * ((dom_h + BH - 1) / BH) * ((dom_w + BW - 1) / BW);
+  const long long ctas = mt * (a->cout / cw_full);
+  const int cin_w = a->kind == DGE_CONV_DOWN4X4S2 ? a->cin / 4 : a->cin;
+  const int taps = a->kind == DGE_CONV_1X1 ? 1 : (a->kind == DGE_CONV_DOWN4X4S2 ? 4 : 9);
+  return ctas * 2 <= num_sms && (long long)taps * (cin_w / 16) >= 64 && a->cin >= 256;
+}
+static int conv_cw_full(const dge_conv_args* a) {
+  if (a->kind == DGE_CONV_UP3X3) return largest_div(a->cout, 128, 16);
+  return (a->cout % 256 == 0) ? 256 : largest_div(a->cout, 128, 16);
+}
+
 int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
   DGE_REQUIRE(a != nullptr, "conv: null args");
   DGE_REQUIRE(a->kind >= 0 && a->kind <= 3, "conv: bad kind %d", a->kind);
@@ -1307,6 +1442,7 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
     p.ntile = p.cw;
     p.np = 1;
   }
+  bool want_sk = false;
   // small problems (<= 32x32 maps): shrink the N tile until the grid covers the SMs -- a 128x256 tile over K = 9*512 is
   // ~100 us of MMA time on ONE SM, so 16..32 such tiles would leave most of the chip idle
   {
@@ -1317,7 +1453,9 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
       if (g_num_sms <= 0) g_num_sms = 148;
     }
     const long long mtiles = (long long)p.N * p.tiles_x * p.tiles_y;
-    while (mtiles * (p.Cout / p.cw) * 4 < (long long)g_num_sms * 3 && p.cw >= 64 && (p.cw / 2) % 16 == 0) p.cw /= 2;
+    want_sk = (up || a->splitk_ws != nullptr) && splitk_wanted(a, p.cw, g_num_sms);
+    if (!want_sk)
+      while (mtiles * (p.Cout / p.cw) * 4 < (long long)g_num_sms * 3 && p.cw >= 64 && (p.cw / 2) % 16 == 0) p.cw /= 2;
     p.ntile = p.np * p.cw;
   }
   p.nsub = p.cw;   // one MMA covers the whole column block (N <= 256)
@@ -1459,7 +1597,7 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
       IssueEnt& ie = p.ilist[cph * p.tpc + j];
       ie.a_off = p.taps[e].a_off;
       ie.dcol = (int16_t)(p.taps[e].phase * p.acc_cols);
-      ie.first = (cph == 0 && !((seen >> p.taps[e].phase) & 1u)) ? 1 : 0;
+      ie.first = !((seen >> p.taps[e].phase) & 1u) ? 1 : 0;   // (consulted only for the first chunk of a K range)
       ie.w_tap = p.taps[e].w_tap;
       seen |= 1u << p.taps[e].phase;
       ++j;
@@ -1506,6 +1644,17 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
   if (smem > 113 * 1024) max_occ = 1;
   p.total_tiles = p.N * p.tiles_x * p.tiles_y * p.n_ntiles;
   p.sched_tiles = p.pair ? ((p.mtiles + 1) / 2) * p.n_ntiles : p.total_tiles;
+  p.ksplit = 1;
+  if (want_sk) {
+    const int ctas = p.pair ? 2 * p.sched_tiles : p.sched_tiles;
+    int ks = g_num_sms / (ctas > 0 ? ctas : 1);
+    if (ks > 8) ks = 8;
+    if (ks > p.nchunks / 2) ks = p.nchunks / 2;
+    if (ks >= 2) p.ksplit = ks;
+  }
+  p.sched_units = p.sched_tiles * p.ksplit;
+  p.div_ksplit = make_fast_div((uint32_t)p.ksplit);
+  p.ws = a->splitk_ws;
   DGE_REQUIRE((long long)p.N * p.tiles_x * p.tiles_y * p.n_ntiles < (1ll << 31), "conv: too many tiles");
   p.div_ntiles = make_fast_div((uint32_t)p.n_ntiles);
   p.div_per_img = make_fast_div((uint32_t)(p.tiles_x * p.tiles_y));
@@ -1567,13 +1716,15 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
   // TMEM is 512 columns per SM: keep co-resident CTAs * tmem_cols <= 512 by padding the smem request.
   const size_t min_smem = (227 * 1024) / (max_occ + 1) + 1024;
   if (smem < min_smem) smem = min_smem;
-  static bool attr_set[6] = {false, false, false, false, false, false};
+  static bool attr_set[10] = {false, false, false, false, false, false, false, false, false, false};
   // EPI 2: 1x1 residual convs with a same-resolution blend (their blend loads are prefetched one unit ahead)
-  const int epi = up ? 1 : ((a->kind == DGE_CONV_1X1 && a->blend_src && !a->blend_pool && !p.stack) ? 2 : 0);
-  const int ei = epi + (p.pair ? 3 : 0);
-  const void* ktab[6] = {(const void*)conv_mma_kernel<0, false>, (const void*)conv_mma_kernel<1, false>,
-                         (const void*)conv_mma_kernel<2, false>, (const void*)conv_mma_kernel<0, true>,
-                         (const void*)conv_mma_kernel<1, true>,  (const void*)conv_mma_kernel<2, true>};
+  const int epi = up ? 1 : ((a->kind == DGE_CONV_1X1 && a->blend_src && !a->blend_pool && !p.stack && p.ksplit == 1) ? 2 : 0);
+  const int ei = p.ksplit > 1 ? 6 + epi + (p.pair ? 2 : 0) : epi + (p.pair ? 3 : 0);
+  const void* ktab[10] = {(const void*)conv_mma_kernel<0, false, false>, (const void*)conv_mma_kernel<1, false, false>,
+                          (const void*)conv_mma_kernel<2, false, false>, (const void*)conv_mma_kernel<0, true, false>,
+                          (const void*)conv_mma_kernel<1, true, false>,  (const void*)conv_mma_kernel<2, true, false>,
+                          (const void*)conv_mma_kernel<0, false, true>,  (const void*)conv_mma_kernel<1, false, true>,
+                          (const void*)conv_mma_kernel<0, true, true>,   (const void*)conv_mma_kernel<1, true, true>};
   const void* kfn = ktab[ei];
   if (!attr_set[ei]) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1586,9 +1737,19 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
   int grid = g_num_sms * max_occ;
   if (p.pair) {
     grid &= ~1;
-    if (grid > 2 * p.sched_tiles) grid = 2 * p.sched_tiles;
-  } else if (grid > p.total_tiles) {
-    grid = p.total_tiles;
+    if (grid > 2 * p.sched_units) grid = 2 * p.sched_units;
+  } else if (grid > p.sched_units) {
+    grid = p.sched_units;
+  }
+  if (p.ksplit > 1) {   // the partial sums are accumulated into a zeroed map
+    void* z = up ? (void*)a->out_raw_up : (void*)a->splitk_ws;
+    const size_t zb = up ? (size_t)a->n * a->cout * (2 * a->h + 1) * (2 * a->w + 1) * 4
+                         : (size_t)a->n * a->cout * a->h * a->w * 4;
+    cudaError_t me = cudaMemsetAsync(z, 0, zb, stream);
+    if (me != cudaSuccess) {
+      set_error("conv: split-K memset failed: %s", cudaGetErrorString(me));
+      return DGE_ERR_CUDA;
+    }
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
@@ -1609,7 +1770,25 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
     return DGE_ERR_CUDA;
   }
   count_launch();
-  return check_launch("conv_mma_kernel");
+  int lr = check_launch("conv_mma_kernel");
+  if (lr || p.ksplit == 1 || up) return lr;
+  const size_t work = (size_t)p.N * (p.Cout / 16) * (p.out_pool ? (p.H / 2) * (p.W / 2) : p.H * p.W);
+  int fgrid = (int)((work + 255) / 256);
+  if (fgrid > 8 * g_num_sms) fgrid = 8 * g_num_sms;
+  conv_splitk_finish_kernel<<<fgrid, 256, 0, stream>>>(p);
+  count_launch();
+  return check_launch("conv_splitk_finish_kernel");
+}
+
+size_t conv_splitk_ws_bytes(const dge_conv_args* a) {
+  if (!a || a->kind == DGE_CONV_UP3X3 || a->cout % 16 || a->cin % 16) return 0;
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return splitk_wanted(a, conv_cw_full(a), g_num_sms) ? (size_t)a->n * a->cout * a->h * a->w * 4 : 0;
 }
 
 }  // namespace dge
@@ -1627,6 +1806,8 @@ extern "C" int dge_exp_role_cycles(unsigned long long* out16, int reset) {
   return 0;
 }
 #endif
+
+extern "C" size_t dge_conv_splitk_ws_bytes(const dge_conv_args* a) { return dge::conv_splitk_ws_bytes(a); }
 
 extern "C" int dge_conv_forward(const dge_conv_args* a, void* stream) {
   return dge::conv_forward(a, static_cast<cudaStream_t>(stream));

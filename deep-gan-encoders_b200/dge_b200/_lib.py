@@ -35,6 +35,7 @@ class ConvArgs(Structure):
         ("out_raw_up", c_void_p),
         ("preact_add", c_void_p),
         ("preact_c", c_int32), ("preact_up", c_int32),
+        ("splitk_ws", c_void_p),
         ("out_pool", c_int32),
     ]
 
@@ -59,6 +60,7 @@ SIGNATURES = {
     "dge_launch_count": (c_int64, []),
     "dge_launch_count_reset": (None, []),
     "dge_conv_forward": (c_int, [POINTER(ConvArgs), P]),
+    "dge_conv_splitk_ws_bytes": (ctypes.c_size_t, [POINTER(ConvArgs)]),
     "dge_pack_conv_weight": (c_int, [P, P, c_int, c_int, c_int, c_int, c_float, c_int, P]),
     "dge_weight_sqsum": (c_int, [P, P, c_int, c_int, c_int, c_float, P]),
     "dge_demod": (c_int, [P, P, P, c_int, c_int, c_int, c_float, P]),

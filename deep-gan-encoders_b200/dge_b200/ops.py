@@ -285,6 +285,11 @@ def conv(x, wpk, cout, kind=CONV_3X3, *, demod=None, noise=None, noise_batched=F
             res["nchw"] = o
         if rgb_w is not None:
             a.rgb_w, a.rgb_out = ptr(rgb_w), ptr(rgb_out)
+    if not checker:
+        wsb = int(lib().dge_conv_splitk_ws_bytes(ctypes.byref(a)))
+        if wsb:                              # small maps: split-K scratch (zeroed by the call)
+            ws = torch.empty((wsb // 4,), dtype=torch.float32, device=dev)
+            a.splitk_ws = ptr(ws)
     name = ("conv3x3", "conv1x1", "conv_up3x3", "conv_down4x4s2")[kind]
     with _rec(name, (x.n, x.h, x.w, x.c, cout, x.planes)):
         check(lib().dge_conv_forward(ctypes.byref(a), _stream()))

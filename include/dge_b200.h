@@ -100,12 +100,17 @@ typedef struct dge_conv_args {
   int32_t preact_c;        /* channels of the residual tensor (0 = cout); only the first cout are used (BigGAN
                               GenBlock channel drop, biggan_generator.py:195-197) */
   int32_t preact_up;       /* 2 = the residual is half resolution, read with nearest x2 (:198-199); else 1 */
+  float* splitk_ws;        /* optional split-K scratch of dge_conv_splitk_ws_bytes(args) bytes (NULL: never split K).
+                              Small maps (<= 16x16 at batch 8) divide the K loop over several CTAs per tile and sum the
+                              parts here before the epilogue; the call zeroes it. */
   int32_t out_pool;        /* 1: out_f32b is [n][cout/8][h/2][w/2][8] and receives the 2x2 MEAN of the epilogue value
                               (avg_pool2d(2,2) fused into the producer: model/E/E.py:78-84 only ever reads conv_2's
                               output pooled).  Needs even h, w; out_f32b must be the only output. */
 } dge_conv_args;
 
 int dge_conv_forward(const dge_conv_args* a, void* stream);
+/* bytes of scratch dge_conv_forward would use for this problem through args->splitk_ws (0: split-K not applicable) */
+size_t dge_conv_splitk_ws_bytes(const dge_conv_args* a);
 
 /* ---- weight preparation ---------------------------------------------------------------------- */
 /* OIHW fp32 [cout][cin][k][k] -> WPK.  flip=1 packs the spatially flipped kernel (transposed conv,

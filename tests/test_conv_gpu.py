@@ -42,6 +42,10 @@ PLAIN_CASES = [
     (1, 32, 512, 16, 24, 2),     # pair mode, odd M tiles x 2 N tiles
     (2, 16, 32, 64, 48, 2),      # 4-block tiles (32x16) with a ragged right edge
     (1, 16, 16, 40, 24, 2),      # 2x2-block tiles, ragged bottom edge
+    (8, 512, 512, 4, 4, 2),      # split-K (small map, long K chain): partial sums + finish kernel
+    (8, 512, 512, 8, 8, 2),
+    (4, 256, 512, 16, 16, 2),
+    (1, 512, 256, 5, 7, 2),
 ]
 
 
@@ -119,7 +123,8 @@ def test_conv1x1_blend(pool, checker):
     assert _rel(res["f32b"].to_nchw(), ref) < 2e-4
 
 
-@pytest.mark.parametrize("case", [(2, 16, 32, 32, 16), (2, 32, 64, 64, 32), (1, 64, 128, 16, 24)],
+@pytest.mark.parametrize("case", [(2, 16, 32, 32, 16), (2, 32, 64, 64, 32), (1, 64, 128, 16, 24), (8, 512, 512, 8, 8),
+                                  (8, 512, 512, 16, 16)],
                          ids=lambda c: "n%d_ci%d_co%d_%dx%d" % c)
 def test_conv3x3_pooled_output(case):
     """out_pool: the epilogue value averaged over 2x2 (avg_pool2d(2,2) fused into the producer, E.py:76-77)."""
@@ -140,7 +145,8 @@ def test_conv3x3_pooled_output(case):
 
 
 UP_CASES = [(2, 32, 32, 8, 8), (2, 64, 32, 16, 16), (1, 64, 128, 9, 5), (2, 128, 256, 8, 8), (2, 32, 512, 4, 4),
-            (1, 128, 64, 16, 24), (3, 256, 128, 8, 8)]   # (the last two: pair mode with odd tile counts)
+            (1, 128, 64, 16, 24), (3, 256, 128, 8, 8),   # (pair mode with odd tile counts)
+            (8, 512, 512, 4, 4), (8, 512, 512, 8, 8)]    # (split-K: parts added in place into the raw map)
 
 
 @pytest.mark.parametrize("checker", [True, False], ids=["checker", "tcgen05"])

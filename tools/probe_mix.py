@@ -82,6 +82,9 @@ cases = [
     ("E conv3x3 16->32 @1024", e_conv(1024, 16, 32)),
     ("E conv3x3 32->64 @512", e_conv(512, 32, 64)),
     ("E stats+IN 16 @1024", e_stats_norm(1024, 16)),
+    ("small G conv3x3 512->512 @8", g_plain(8, 512)),
+    ("small G conv3x3 512->512 @16", g_plain(16, 512)),
+    ("small E conv3x3 512->512 @4", e_conv(4, 512, 512)),
 ]
 sel = os.environ.get("PROBE_SEL")
 for name, fn in cases:
