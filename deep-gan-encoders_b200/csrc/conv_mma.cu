@@ -517,7 +517,7 @@ __device__ __forceinline__ void epi_group16(const ConvKParams& p, const float* t
     }
   }
   const int H = p.H, W = p.W, C8 = p.Cout >> 3, g0 = (co0 + c) >> 3;
-  if (p.preact_add && px.valid) {
+  if (EPI != 3 && p.preact_add && px.valid) {
     float t[8];
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
@@ -535,7 +535,7 @@ __device__ __forceinline__ void epi_group16(const ConvKParams& p, const float* t
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = v[j] < 0.f ? v[j] * p.slope : v[j];
   }
-  if (p.out_pool) {
+  if (EPI != 3 && p.out_pool) {
     // 2x2 mean across the lanes (x ^ 1 <-> lane ^ 1, y ^ 1 <-> lane ^ 8); the even/even lane stores the pooled pixel
     const int lane = threadIdx.x & 31;
 #pragma unroll
@@ -554,7 +554,7 @@ __device__ __forceinline__ void epi_group16(const ConvKParams& p, const float* t
     return;
   }
   if (px.valid) {
-    if (p.blend_src) {
+    if (EPI != 3 && p.blend_src) {
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
         float sv[8];
@@ -612,7 +612,7 @@ __device__ __forceinline__ void epi_group16(const ConvKParams& p, const float* t
       store8_f32b(p.out_f32b, o, v);
       store8_f32b(p.out_f32b, o + HW, v + 8);
     }
-    if (p.out_nchw) {
+    if (EPI != 3 && p.out_nchw) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) p.out_nchw[((size_t)px.n * p.Cout + co0 + c + j) * HW + pix] = v[j];
     }
@@ -858,7 +858,9 @@ __device__ __forceinline__ int sched_tile(const ConvKParams& p, int unit, uint32
 }
 
 template <int EPI, bool PAIR, bool SPLITK>  // EPI: 0 = pointwise, 1 = raw up, 2 = pointwise with the residual blend
-                                           // fetched ahead; SPLITK: partial sums over a K range, added atomically
+                                           // fetched ahead, 3 = pointwise without the rare options (residuals,
+                                           // blend, pooled / NCHW outputs: the generator's and conv_1's epilogue);
+                                           // SPLITK: partial sums over a K range, added atomically
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ ConvKParams p) {
@@ -1716,13 +1718,16 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
   // TMEM is 512 columns per SM: keep co-resident CTAs * tmem_cols <= 512 by padding the smem request.
   const size_t min_smem = (227 * 1024) / (max_occ + 1) + 1024;
   if (smem < min_smem) smem = min_smem;
-  static bool attr_set[10] = {false, false, false, false, false, false, false, false, false, false};
-  // EPI 2: 1x1 residual convs with a same-resolution blend (their blend loads are prefetched one unit ahead)
-  const int epi = up ? 1 : ((a->kind == DGE_CONV_1X1 && a->blend_src && !a->blend_pool && !p.stack && p.ksplit == 1) ? 2 : 0);
-  const int ei = p.ksplit > 1 ? 6 + epi + (p.pair ? 2 : 0) : epi + (p.pair ? 3 : 0);
-  const void* ktab[10] = {(const void*)conv_mma_kernel<0, false, false>, (const void*)conv_mma_kernel<1, false, false>,
-                          (const void*)conv_mma_kernel<2, false, false>, (const void*)conv_mma_kernel<0, true, false>,
-                          (const void*)conv_mma_kernel<1, true, false>,  (const void*)conv_mma_kernel<2, true, false>,
+  static bool attr_set[12] = {false, false, false, false, false, false, false, false, false, false, false, false};
+  // EPI 2: 1x1 residual convs with a same-resolution blend (their blend loads are prefetched one unit ahead);
+  // EPI 3: no residual / blend / pooled / NCHW output -- a leaner instantiation for the most common launches
+  int epi = up ? 1 : ((a->kind == DGE_CONV_1X1 && a->blend_src && !a->blend_pool && !p.stack && p.ksplit == 1) ? 2 : 0);
+  if (epi == 0 && p.ksplit == 1 && !a->preact_add && !a->blend_src && !a->out_nchw && !a->out_pool) epi = 3;
+  const int ei = p.ksplit > 1 ? 8 + epi + (p.pair ? 2 : 0) : epi + (p.pair ? 4 : 0);
+  const void* ktab[12] = {(const void*)conv_mma_kernel<0, false, false>, (const void*)conv_mma_kernel<1, false, false>,
+                          (const void*)conv_mma_kernel<2, false, false>, (const void*)conv_mma_kernel<3, false, false>,
+                          (const void*)conv_mma_kernel<0, true, false>,  (const void*)conv_mma_kernel<1, true, false>,
+                          (const void*)conv_mma_kernel<2, true, false>,  (const void*)conv_mma_kernel<3, true, false>,
                           (const void*)conv_mma_kernel<0, false, true>,  (const void*)conv_mma_kernel<1, false, true>,
                           (const void*)conv_mma_kernel<0, true, true>,   (const void*)conv_mma_kernel<1, true, true>};
   const void* kfn = ktab[ei];
