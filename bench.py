@@ -96,9 +96,8 @@ def dist_setup(n):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         import torch.distributed as dist
-        # keep stdout to the ONE JSON line: NCCL prints its version banner there at VERSION/INFO level
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", ""):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # keep stdout to the ONE JSON line: NCCL writes its version banner / debug log to stdout unless redirected
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         if torch.cuda.is_available():
             torch.cuda.set_device(local)
         if not dist.is_initialized():
