@@ -49,8 +49,11 @@ static inline int grid_for(size_t work, int block) {
 // weight preparation
 // ---------------------------------------------------------------------------------------------
 // WPK [taps][Cin/8][planes][Cout][8]; one thread per (tap, cin-group, cout)
+// transpose = 1 packs the data-gradient weight of the same layer: W'[i][o][ky][kx] = W[o][i][k-1-ky][k-1-kx], i.e. the
+// returned operand has `cin` output columns and contracts over `cout` (cout/cin below are those of the PACKED operand;
+// src_cin is the input-channel count of the stored OIHW tensor)
 __global__ void k_pack_conv_weight(const float* __restrict__ w, uint4* __restrict__ out, int cout, int cin, int ks,
-                                   int flip, float scale, int planes) {
+                                   int flip, float scale, int planes, int transpose, int src_cin) {
   const int taps = ks * ks, C8 = cin >> 3;
   const size_t total = (size_t)taps * C8 * cout;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -61,7 +64,10 @@ __global__ void k_pack_conv_weight(const float* __restrict__ w, uint4* __restric
     if (flip) { ky = ks - 1 - ky; kx = ks - 1 - kx; }
     float v[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = w[(((size_t)co * cin + g * 8 + k) * ks + ky) * ks + kx] * scale;
+    for (int k = 0; k < 8; ++k) {
+      const size_t so = transpose ? (size_t)(g * 8 + k) * src_cin + co : (size_t)co * src_cin + g * 8 + k;
+      v[k] = w[(so * ks + ky) * ks + kx] * scale;
+    }
     uint4 hi, lo;
     split8(v, hi, lo);
     const size_t o = (((size_t)tap * C8 + g) * planes) * cout + co;
@@ -1459,7 +1465,19 @@ int dge_pack_conv_weight(const float* w, void* wpk, int cout, int cin, int ksize
   DGE_REQUIRE(ksize == 1 || ksize == 3 || ksize == 4, "pack_conv_weight: ksize=%d", ksize);
   DGE_REQUIRE(planes == 1 || planes == 2, "pack_conv_weight: planes=%d", planes);
   LAUNCH_1D(k_pack_conv_weight, (size_t)ksize * ksize * (cin / 8) * cout, stream, w, (uint4*)wpk, cout, cin, ksize,
-            flip, scale, planes);
+            flip, scale, planes, 0, cin);
+}
+
+int dge_pack_conv_weight_dgrad(const float* w, void* wpk, int cout, int cin, int ksize, float scale, int planes,
+                               void* stream) {
+  DGE_REQUIRE(w && wpk, "pack_conv_weight_dgrad: null pointer");
+  DGE_REQUIRE(cin % 16 == 0 && cout % 16 == 0 && cin > 0 && cout > 0,
+              "pack_conv_weight_dgrad: cin=%d cout=%d must be multiples of 16", cin, cout);
+  DGE_REQUIRE(ksize == 1 || ksize == 3, "pack_conv_weight_dgrad: ksize=%d", ksize);
+  DGE_REQUIRE(planes == 1 || planes == 2, "pack_conv_weight_dgrad: planes=%d", planes);
+  // packed operand: cin output columns, contraction over cout, spatially flipped
+  LAUNCH_1D(k_pack_conv_weight, (size_t)ksize * ksize * (cout / 8) * cin, stream, w, (uint4*)wpk, cin, cout, ksize, 1,
+            scale, planes, 1, cin);
 }
 
 int dge_weight_sqsum(const float* w, float* w2, int cout, int cin, int ksize, float scale, void* stream) {

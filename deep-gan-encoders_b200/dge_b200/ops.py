@@ -168,6 +168,16 @@ def pack_conv_weight(w, scale=1.0, flip=False, planes=2):
     return out
 
 
+def pack_conv_weight_dgrad(w, scale=1.0, planes=2):
+    """OIHW fp32 -> the data-gradient operand (transposed + flipped): conv(dy_act, this, cin) = dL/dx of conv2d(x, w)."""
+    w = w.detach().contiguous()
+    cout, cin, k, k2 = w.shape
+    assert k == k2
+    out = torch.empty((k * k, cout // 8, planes, cin, 8), dtype=torch.bfloat16, device=w.device)
+    check(lib().dge_pack_conv_weight_dgrad(_f32(w), _p(out), cout, cin, k, float(scale), planes, _stream()))
+    return out
+
+
 def weight_sqsum(w, scale=1.0):
     w = w.detach().contiguous()
     cout, cin, k, _ = w.shape

@@ -117,6 +117,12 @@ size_t dge_conv_splitk_ws_bytes(const dge_conv_args* a);
    stylegan2_generator.py:880).  scale multiplies every weight (wscale, :858). */
 int dge_pack_conv_weight(const float* w_oihw, void* wpk, int cout, int cin, int ksize, int flip,
                          float scale, int planes, void* stream);
+/* Data-gradient operand of the same layer: OIHW fp32 [cout][cin][k][k] -> WPK [taps][cout/8][planes][cin][8] holding
+   W'[i][o][ky][kx] = W[o][i][k-1-ky][k-1-kx]*scale.  dge_conv_forward(dy as ACT with `cout` channels, this operand,
+   cout := cin) then computes dL/dx of y = conv2d(x, W, pad (k-1)/2) (torch.nn.functional.conv2d backward w.r.t. input;
+   lreq.py:126-156, stylegan2_generator.py:897-904) -- the first building block of the training step. */
+int dge_pack_conv_weight_dgrad(const float* w_oihw, void* wpk, int cout, int cin, int ksize, float scale, int planes,
+                               void* stream);
 /* W2[o][i] = sum_k (w[o][i][k]*scale)^2 -- the demodulation Gram diagonal (stylegan2_generator.py:867-870) */
 int dge_weight_sqsum(const float* w_oihw, float* w2, int cout, int cin, int ksize, float scale, void* stream);
 /* d[n][o] = rsqrt(sum_i W2[o][i]*s[n][i]^2 + eps) */

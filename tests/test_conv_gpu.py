@@ -180,3 +180,23 @@ def test_up_conv_raw_and_fir(case, checker):
     torch.cuda.synchronize()
     assert _rel(out["nchw"], y) < 2e-4
     assert _rel(out["act"].to_nchw(), y * s_out[:, :, None, None]) < 2e-4
+
+
+@pytest.mark.parametrize("case", [(2, 32, 64, 24, 16, 3), (2, 128, 64, 16, 16, 3), (1, 64, 128, 9, 17, 1)],
+                         ids=lambda c: "n%d_ci%d_co%d_%dx%d_k%d" % c)
+def test_conv_data_gradient(case):
+    """dL/dx of y = conv2d(x, W) through the same tcgen05 kernel with the transposed + flipped operand
+    (dge_pack_conv_weight_dgrad), against torch.autograd."""
+    ops = _setup()
+    n, cin, cout, h, w, k = case
+    g = torch.Generator(device="cuda").manual_seed(31 + cout)
+    x = torch.randn(n, cin, h, w, device="cuda", generator=g, requires_grad=True)
+    wt = torch.randn(cout, cin, k, k, device="cuda", generator=g) / (k * cin ** 0.5)
+    dy = torch.randn(n, cout, h, w, device="cuda", generator=g)
+    y = F.conv2d(x, wt, padding=k // 2)
+    (dx_ref,) = torch.autograd.grad(y, x, dy)
+    wd = ops.pack_conv_weight_dgrad(wt)
+    kind = ops.CONV_3X3 if k == 3 else ops.CONV_1X1
+    dx = ops.conv(ops.nchw_to_act(dy), wd, cin, kind, out_f32b=True)["f32b"].to_nchw()
+    torch.cuda.synchronize()
+    assert _rel(dx, dx_ref) < 2e-4
