@@ -63,6 +63,7 @@ SIGNATURES = {
     "dge_conv_splitk_ws_bytes": (ctypes.c_size_t, [POINTER(ConvArgs)]),
     "dge_pack_conv_weight": (c_int, [P, P, c_int, c_int, c_int, c_int, c_float, c_int, P]),
     "dge_pack_conv_weight_dgrad": (c_int, [P, P, c_int, c_int, c_int, c_float, c_int, P]),
+    "dge_conv_wgrad": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "dge_weight_sqsum": (c_int, [P, P, c_int, c_int, c_int, c_float, P]),
     "dge_demod": (c_int, [P, P, P, c_int, c_int, c_int, c_float, P]),
     "dge_rgb_weights": (c_int, [P, P, P, c_int, c_int, c_int, c_float, P]),

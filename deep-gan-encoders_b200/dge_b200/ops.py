@@ -178,6 +178,20 @@ def pack_conv_weight_dgrad(w, scale=1.0, planes=2):
     return out
 
 
+def conv_wgrad(dy, x, ksize, out=None, accumulate=False):
+    """dL/dW of conv2d(x, W, padding=ksize//2): `dy` and `x` are Act tensors (same batch, size and planes); returns
+    the fp32 [cout, cin, k, k] gradient (added into `out` when accumulate=True)."""
+    assert isinstance(dy, Act) and isinstance(x, Act)
+    assert (dy.n, dy.h, dy.w, dy.planes) == (x.n, x.h, x.w, x.planes), "conv_wgrad: dy / x geometry mismatch"
+    if out is None:
+        assert not accumulate
+        out = torch.empty((dy.c, x.c, ksize, ksize), dtype=torch.float32, device=x.t.device)
+    assert out.shape == (dy.c, x.c, ksize, ksize) and out.dtype == torch.float32 and out.is_contiguous()
+    check(lib().dge_conv_wgrad(_p(dy.t), _p(x.t), _f32(out), x.n, dy.c, x.c, x.h, x.w, ksize, x.planes,
+                               1 if accumulate else 0, _stream()))
+    return out
+
+
 def weight_sqsum(w, scale=1.0):
     w = w.detach().contiguous()
     cout, cin, k, _ = w.shape

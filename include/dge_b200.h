@@ -123,6 +123,15 @@ int dge_pack_conv_weight(const float* w_oihw, void* wpk, int cout, int cin, int 
    lreq.py:126-156, stylegan2_generator.py:897-904) -- the first building block of the training step. */
 int dge_pack_conv_weight_dgrad(const float* w_oihw, void* wpk, int cout, int cin, int ksize, float scale, int planes,
                                void* stream);
+/* Weight gradient of y = conv2d(x, W, padding k/2), stride 1, k in {1, 3} (autograd of lreq.py:126-156 as driven by
+   E_align_s2.py:205-233): dw[o][i][ky][kx] (+)= sum_{n,y,x} dy[n][o][y][x] * x[n][i][y+ky-k/2][x+kx-k/2].
+   dy_act / x_act: ACT tensors ([n][c/8][planes][h][w][8] bf16) with cout / cin channels and the same `planes`
+   (2 = split precision hi+lo, ~fp32 result; 1 = plain bf16).  dw: fp32 [cout][cin][k][k] (the layout of the
+   parameter's .grad).  accumulate=0 zeroes dw first; 1 adds to it.  tcgen05 kernel, contraction over pixels with both
+   operands read as MN-major tiles straight from the ACT layout; partial sums merge with fp32 atomics (run-to-run
+   differences at the 1e-7 relative level).  cout, cin multiples of 8. */
+int dge_conv_wgrad(const void* dy_act, const void* x_act, float* dw, int n, int cout, int cin, int h, int w, int ksize,
+                   int planes, int accumulate, void* stream);
 /* W2[o][i] = sum_k (w[o][i][k]*scale)^2 -- the demodulation Gram diagonal (stylegan2_generator.py:867-870) */
 int dge_weight_sqsum(const float* w_oihw, float* w2, int cout, int cin, int ksize, float scale, void* stream);
 /* d[n][o] = rsqrt(sum_i W2[o][i]*s[n][i]^2 + eps) */

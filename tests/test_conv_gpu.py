@@ -200,3 +200,41 @@ def test_conv_data_gradient(case):
     dx = ops.conv(ops.nchw_to_act(dy), wd, cin, kind, out_f32b=True)["f32b"].to_nchw()
     torch.cuda.synchronize()
     assert _rel(dx, dx_ref) < 2e-4
+
+
+@pytest.mark.parametrize("case", [(2, 16, 32, 24, 16, 3), (2, 128, 128, 16, 16, 3), (1, 64, 128, 9, 17, 1),
+                                  (2, 512, 512, 4, 4, 3), (1, 144, 192, 20, 40, 3), (2, 32, 32, 64, 80, 3),
+                                  (3, 256, 64, 33, 31, 1)],
+                         ids=lambda c: "n%d_ci%d_co%d_%dx%d_k%d" % c)
+def test_conv_weight_gradient(case):
+    """dL/dW of y = conv2d(x, W) (dge_conv_wgrad: pixels are the contraction index, both operands MN-major tiles of the
+    ACT layout), against torch.autograd in fp32 (TF32 off).  Ragged maps, partial channel blocks, tiny maps, 1x1."""
+    ops = _setup()
+    n, cin, cout, h, w, k = case
+    g = torch.Generator(device="cuda").manual_seed(57 + cout + h)
+    x = torch.randn(n, cin, h, w, device="cuda", generator=g)
+    wt = (torch.randn(cout, cin, k, k, device="cuda", generator=g) / (k * cin ** 0.5)).requires_grad_(True)
+    dy = torch.randn(n, cout, h, w, device="cuda", generator=g)
+    y = F.conv2d(x, wt, padding=k // 2)
+    (dw_ref,) = torch.autograd.grad(y, wt, dy)
+    dw = ops.conv_wgrad(ops.nchw_to_act(dy), ops.nchw_to_act(x), k)
+    torch.cuda.synchronize()
+    assert dw.shape == dw_ref.shape
+    assert _rel(dw, dw_ref) < 2e-4
+    # accumulate=True adds a second gradient into the same buffer
+    ops.conv_wgrad(ops.nchw_to_act(dy), ops.nchw_to_act(x), k, out=dw, accumulate=True)
+    torch.cuda.synchronize()
+    assert _rel(dw, 2 * dw_ref) < 2e-4
+
+
+def test_conv_weight_gradient_plain_bf16_is_close():
+    """planes=1 (plain bf16 operands) is the fast mode: close, but not the parity mode."""
+    ops = _setup()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(2, 64, 32, 32, device="cuda", generator=g)
+    dy = torch.randn(2, 64, 32, 32, device="cuda", generator=g)
+    wt = torch.zeros(64, 64, 3, 3, device="cuda", requires_grad=True)
+    (dw_ref,) = torch.autograd.grad(F.conv2d(x, wt, padding=1), wt, dy)
+    dw = ops.conv_wgrad(ops.nchw_to_act(dy, planes=1), ops.nchw_to_act(x, planes=1), 3)
+    torch.cuda.synchronize()
+    assert _rel(dw, dw_ref) < 2e-2
