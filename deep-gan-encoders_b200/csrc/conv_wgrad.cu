@@ -36,6 +36,11 @@ struct WgradParams {
   int a_groups, b_groups;          // 8-channel groups per TMA box (x planes)
   uint32_t dy_tile_bytes, x_tile_bytes, dy_bytes, x_bytes, stage_bytes;
   int stages, tmem_cols;
+  int stacked;                     // all 9 taps side by side in N (Cin <= 32): x is staged as 9 shifted tiles
+  int n1, n2;                      // stacked: N of the first / second MMA of a K step (n2 = 0: one MMA)
+  uint32_t slot_bytes;             // stacked: bytes of one tap's x tile set
+  int rowpair;                     // maps <= 8 pixels wide: a K step is 8 pixels of row r + 8 pixels of row r+1
+  int atomic, accumulate;          // chunks > 1: partial sums merge with atomics; else plain store / add
   float* dw;
 };
 
@@ -83,7 +88,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
   // block coordinates
   const int cib = blockIdx.y % p.cin_blocks;
   const int cob = (blockIdx.y / p.cin_blocks) % p.cout_blocks;
-  const int ky = blockIdx.y / (p.cin_blocks * p.cout_blocks);
+  const int ky = blockIdx.y / (p.cin_blocks * p.cout_blocks);   // 0 in stacked mode (grid.y = cout blocks)
   const int t0 = (int)(((long long)blockIdx.x * p.tiles_total) / p.chunks);
   const int t1 = (int)(((long long)(blockIdx.x + 1) * p.tiles_total) / p.chunks);
 
@@ -118,21 +123,32 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
         const int y0 = ty * p.th, x0 = tx * p.tw;
         uint8_t* st = smem + (size_t)s * p.stage_bytes;
-        mbar_arrive_expect_tx(&full_bar[s], p.dy_bytes + p.x_bytes);
-        tma_load_4d(st, &tm_dy, &full_bar[s], 2 * x0, y0, cob * 16 * p.planes, n);
-        tma_load_4d(st + (size_t)16 * p.planes * p.dy_tile_bytes, &tm_x, &full_bar[s], 2 * (x0 - p.pad),
-                    y0 + ky - p.pad, cib * (p.nblk / 8) * p.planes, n);
+        uint8_t* sx = st + (size_t)16 * p.planes * p.dy_tile_bytes;
+        if (p.stacked) {
+          mbar_arrive_expect_tx(&full_bar[s], p.dy_bytes + 9u * p.x_bytes);
+          tma_load_4d(st, &tm_dy, &full_bar[s], 2 * x0, y0, cob * 16 * p.planes, n);
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap)
+            tma_load_4d(sx + (size_t)tap * p.slot_bytes, &tm_x, &full_bar[s], 2 * (x0 + tap % 3 - 1), y0 + tap / 3 - 1,
+                        0, n);
+        } else {
+          mbar_arrive_expect_tx(&full_bar[s], p.dy_bytes + p.x_bytes);
+          tma_load_4d(st, &tm_dy, &full_bar[s], 2 * x0, y0, cob * 16 * p.planes, n);
+          tma_load_4d(sx, &tm_x, &full_bar[s], 2 * (x0 - p.pad), y0 + ky - p.pad, cib * (p.nblk / 8) * p.planes, n);
+        }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // =================================== MMA issuer ======================================
     if (lane == 0) {
-      const uint32_t idesc = wg_idesc(p.nblk);
+      const uint32_t idesc = wg_idesc(p.nblk), idesc1 = wg_idesc(p.n1), idesc2 = wg_idesc(p.n2 ? p.n2 : 16);
       const uint32_t a_sbo = p.planes * p.dy_tile_bytes, b_sbo = p.planes * p.x_tile_bytes;
-      const uint64_t a_desc0 = wg_desc(0, 128, a_sbo), b_desc0 = wg_desc(0, 128, b_sbo);
+      // the two 8-pixel K groups of a K step: neighbours in a row (128 B apart), or the same 8 columns of two rows
+      const uint32_t a_lbo = p.rowpair ? (uint32_t)p.tw * 16u : 128u, b_lbo = p.rowpair ? (uint32_t)p.pw * 16u : 128u;
+      const uint64_t a_desc0 = wg_desc(0, a_lbo, a_sbo), b_desc0 = wg_desc(0, b_lbo, b_sbo);
       const uint32_t a_lo = p.dy_tile_bytes >> 4, b_lo = p.x_tile_bytes >> 4;   // plane 1 (lo) offsets, 16-byte units
-      const int segs = p.tw / 16;
+      const int segs = p.rowpair ? 1 : p.tw / 16, rstep = p.rowpair ? 2 : 1;
       for (int t = t0, it = 0; t < t1; ++t, ++it) {
         const int s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
@@ -140,18 +156,37 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
         wg_fence_after();
         const uint32_t a_base = smem_u32(smem + (size_t)s * p.stage_bytes);
         const uint32_t b_base = a_base + 16u * p.planes * p.dy_tile_bytes;
-        for (int r = 0; r < p.th; ++r) {
+        for (int r = 0; r < p.th; r += rstep) {
           for (int sg = 0; sg < segs; ++sg) {
             const uint64_t da = a_desc0 + (uint64_t)(((a_base >> 4) + (uint32_t)(r * p.tw + sg * 16)) & 0x3fff);
             const uint32_t acc0 = (it == 0 && r == 0 && sg == 0) ? 0u : 1u;
-            for (int kx = 0; kx < p.taps_x; ++kx) {
-              const uint64_t db =
-                  b_desc0 + (uint64_t)(((b_base >> 4) + (uint32_t)(r * p.pw + sg * 16 + kx)) & 0x3fff);
-              const uint32_t d = tmem + (uint32_t)(kx * p.nblk);
-              wg_mma(d, da, db, idesc, acc0);
+            if (p.stacked) {
+              // one (or two) wide MMAs cover all 9 taps: N group g = tap * (Cin/8) + channel group, uniform stride
+              const uint64_t db = b_desc0 + (uint64_t)(((b_base >> 4) + (uint32_t)(r * p.tw + sg * 16)) & 0x3fff);
+              wg_mma(tmem, da, db, idesc1, acc0);
               if (p.planes == 2) {
-                wg_mma(d, da, db + b_lo, idesc, 1u);
-                wg_mma(d, da + a_lo, db, idesc, 1u);
+                wg_mma(tmem, da, db + b_lo, idesc1, 1u);
+                wg_mma(tmem, da + a_lo, db, idesc1, 1u);
+              }
+              if (p.n2) {
+                const uint64_t db2 = db + (uint64_t)((5u * p.slot_bytes) >> 4);
+                const uint32_t d2 = tmem + (uint32_t)p.n1;
+                wg_mma(d2, da, db2, idesc2, acc0);
+                if (p.planes == 2) {
+                  wg_mma(d2, da, db2 + b_lo, idesc2, 1u);
+                  wg_mma(d2, da + a_lo, db2, idesc2, 1u);
+                }
+              }
+            } else {
+              for (int kx = 0; kx < p.taps_x; ++kx) {
+                const uint64_t db =
+                    b_desc0 + (uint64_t)(((b_base >> 4) + (uint32_t)(r * p.pw + sg * 16 + kx)) & 0x3fff);
+                const uint32_t d = tmem + (uint32_t)(kx * p.nblk);
+                wg_mma(d, da, db, idesc, acc0);
+                if (p.planes == 2) {
+                  wg_mma(d, da, db + b_lo, idesc, 1u);
+                  wg_mma(d, da + a_lo, db, idesc, 1u);
+                }
               }
             }
           }
@@ -168,7 +203,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
   wg_fence_after();
   const int co = cob * 128 + warp * 32 + lane;
   if (cob * 128 + warp * 32 < p.Cout && t1 > t0) {
-    const int ncols = p.taps_x * p.nblk;
+    const int ncols = (p.stacked ? 9 : p.taps_x) * p.nblk;
+    const int tap_base = p.stacked ? 0 : ky * p.ksize;
     const int kk = p.ksize * p.ksize;
     for (int c0 = 0; c0 < ncols; c0 += 16) {
       uint32_t r[16];
@@ -180,13 +216,19 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
             "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      const int kx = c0 / p.nblk;            // nblk is a multiple of 16: a 16-column group never straddles taps
-      const int ci0 = cib * p.nblk + (c0 - kx * p.nblk);
+      const int tl = c0 / p.nblk;            // nblk is a multiple of 16: a 16-column group never straddles taps
+      const int ci0 = cib * p.nblk + (c0 - tl * p.nblk);
+      const int tap = tap_base + tl;
       if (co < p.Cout) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int ci = ci0 + i;
-          if (ci < p.Cin) atomicAdd(p.dw + ((size_t)co * p.Cin + ci) * kk + ky * p.ksize + kx, __uint_as_float(r[i]));
+          if (ci < p.Cin) {
+            float* q = p.dw + ((size_t)co * p.Cin + ci) * kk + tap;
+            const float v = __uint_as_float(r[i]);
+            if (p.atomic) atomicAdd(q, v);
+            else *q = p.accumulate ? *q + v : v;     // this CTA is the only writer of its dW block
+          }
         }
       }
     }
@@ -227,12 +269,25 @@ extern "C" int dge_conv_wgrad(const void* dy_act, const void* x_act, float* dw, 
   p.N = n; p.H = h; p.W = w; p.Cout = cout; p.Cin = cin; p.ksize = ksize; p.planes = planes;
   p.taps_x = ksize;
   p.pad = ksize / 2;
-  int segs = (w + 15) / 16;
-  if (segs > 4) segs = 4;
-  p.tw = 16 * segs;
-  p.th = 64 / p.tw;
-  if (p.th > h) p.th = h;
-  p.pw = p.tw + 2 * p.pad;
+  if (w <= 8) {
+    p.rowpair = 1;
+    p.tw = 8;
+    p.th = (h + 1) & ~1;
+    if (p.th > 8) p.th = 8;
+  } else {
+    int segs = (w + 15) / 16;
+    if (segs > 4) segs = 4;
+    p.tw = 16 * segs;
+    p.th = 64 / p.tw;
+    if (p.th > h) p.th = h;
+  }
+  // tap-stacked mode for the thin layers of the encoder (E.py: 16 and 32 input channels at 1024^2 / 512^2): with
+  // N = Cin per tap an MMA is bound by the 4 KB A fetch (~64 clk) whatever N is, so nine N=16 MMAs cost 9x one N=144
+  // MMA.  x is staged as 9 shifted tiles (9x a small tile) so that (tap, channel group) is ONE uniform N stride.
+  static int no_stack = -1;
+  if (no_stack < 0) no_stack = getenv("DGE_WGRAD_NO_STACK") ? 1 : 0;
+  p.stacked = (ksize == 3 && cin % 16 == 0 && cin <= 32 && !no_stack) ? 1 : 0;
+  p.pw = p.stacked ? p.tw : p.tw + 2 * p.pad;
   p.tiles_x = (w + p.tw - 1) / p.tw;
   p.tiles_y = (h + p.th - 1) / p.th;
   const long long tiles = (long long)n * p.tiles_x * p.tiles_y;
@@ -241,6 +296,10 @@ extern "C" int dge_conv_wgrad(const void* dy_act, const void* x_act, float* dw, 
   const int cin16 = (cin + 15) / 16 * 16;
   p.nblk = cin16 < 128 ? cin16 : 128;
   p.cin_blocks = (cin + p.nblk - 1) / p.nblk;
+  if (p.stacked) {
+    p.n1 = 9 * cin <= 256 ? 9 * cin : 5 * cin;
+    p.n2 = 9 * cin - p.n1;
+  }
   p.cout_blocks = (cout + 127) / 128;
   const int a_groups_total = (cout / 8) * planes, b_groups_total = (cin / 8) * planes;
   p.a_groups = 16 * planes < a_groups_total ? 16 * planes : a_groups_total;
@@ -250,19 +309,40 @@ extern "C" int dge_conv_wgrad(const void* dy_act, const void* x_act, float* dw, 
   p.dy_bytes = p.dy_tile_bytes * p.a_groups;
   p.x_bytes = p.x_tile_bytes * p.b_groups;
   // smem image per stage keeps room for the full 16 / nblk/8 groups so the descriptor strides do not depend on clamping
-  const uint32_t x_region = p.x_tile_bytes * (uint32_t)((p.nblk / 8) * planes);
+  p.slot_bytes = p.x_tile_bytes * (uint32_t)((p.nblk / 8) * planes);
+  const uint32_t x_region = p.slot_bytes * (p.stacked ? 9u : 1u);
   p.stage_bytes = (16u * planes * p.dy_tile_bytes + x_region + 127u) & ~127u;
   p.stages = (int)((216u * 1024u) / p.stage_bytes);
   if (p.stages > WG_MAX_STAGES) p.stages = WG_MAX_STAGES;
   DGE_REQUIRE(p.stages >= 2, "conv_wgrad: stage of %u bytes does not fit twice in shared memory", p.stage_bytes);
   int cols = 32;
-  while (cols < p.taps_x * p.nblk) cols *= 2;
+  while (cols < (p.stacked ? 9 : p.taps_x) * p.nblk) cols *= 2;
   p.tmem_cols = cols;
-  const int blocks_y = ksize * p.cout_blocks * p.cin_blocks;
-  int chunks = (2 * g_wg_sms + blocks_y - 1) / blocks_y;
-  if (chunks > p.tiles_total) chunks = p.tiles_total;
-  if (chunks < 1) chunks = 1;
+  const int blocks_y = p.stacked ? p.cout_blocks : ksize * p.cout_blocks * p.cin_blocks;
+  // split of the contraction: c chunks shorten every CTA's MMA loop by c but each adds one pass of fp32 atomics over dW
+  // (~200 G atomics/s measured); with one chunk the CTA owns its dW block and stores it (no memset, no atomics).
+  const int ksteps_tile = p.rowpair ? p.th / 2 : p.th * (p.tw / 16);
+  const int mma_n = p.stacked ? p.n1 : p.nblk;
+  const double clk_mma = mma_n / 2 > 64 ? mma_n / 2 : 64;     // A fetch (4 KB at ~64 B/clk) or the math, whichever is longer
+  const double mmas_kstep = (planes == 2 ? 3.0 : 1.0) * (p.stacked ? (p.n2 ? 2 : 1) : p.taps_x);
+  const double cta_us = (double)p.tiles_total * ksteps_tile * mmas_kstep * clk_mma / 1900.0;
+  const double pass_us = (double)cout * cin * ksize * ksize / 200e3;
+  int max_chunks = (2 * g_wg_sms + blocks_y - 1) / blocks_y;
+  if (max_chunks > p.tiles_total) max_chunks = p.tiles_total;
+  if (max_chunks < 1) max_chunks = 1;
+  int chunks = 1;
+  double best = cta_us * ((blocks_y + g_wg_sms - 1) / g_wg_sms);
+  for (int c = 2; c <= max_chunks; ++c) {
+    const int waves = (blocks_y * c + g_wg_sms - 1) / g_wg_sms;
+    const double t = cta_us / c * waves + pass_us * c + 3.0;   // + memset and the atomics' tail
+    if (t < best) {
+      best = t;
+      chunks = c;
+    }
+  }
   p.chunks = chunks;
+  p.atomic = chunks > 1;
+  p.accumulate = accumulate;
   p.dw = dw;
 
   CUtensorMap tm_dy, tm_x;
@@ -293,7 +373,7 @@ extern "C" int dge_conv_wgrad(const void* dy_act, const void* x_act, float* dw, 
     }
     attr_smem = smem;
   }
-  if (!accumulate) {
+  if (!accumulate && p.atomic) {
     cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)cout * cin * ksize * ksize * sizeof(float), stream);
     if (e != cudaSuccess) {
       set_error("conv_wgrad: cudaMemsetAsync failed: %s", cudaGetErrorString(e));

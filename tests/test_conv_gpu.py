@@ -204,7 +204,8 @@ def test_conv_data_gradient(case):
 
 @pytest.mark.parametrize("case", [(2, 16, 32, 24, 16, 3), (2, 128, 128, 16, 16, 3), (1, 64, 128, 9, 17, 1),
                                   (2, 512, 512, 4, 4, 3), (1, 144, 192, 20, 40, 3), (2, 32, 32, 64, 80, 3),
-                                  (3, 256, 64, 33, 31, 1)],
+                                  (3, 256, 64, 33, 31, 1), (2, 64, 64, 7, 8, 3), (3, 32, 48, 11, 5, 3),
+                                  (8, 512, 512, 8, 8, 3)],
                          ids=lambda c: "n%d_ci%d_co%d_%dx%d_k%d" % c)
 def test_conv_weight_gradient(case):
     """dL/dW of y = conv2d(x, W) (dge_conv_wgrad: pixels are the contraction index, both operands MN-major tiles of the
