@@ -7,12 +7,20 @@ Appendix A).  Per block the reference issues ~25 ATen kernels; here it is
 Noise: the reference draws `torch.randn([N,1,H,W])` on the CPU inside each conv stage (E.py:60,73);
 `noise_mode = 'reference'` (default) does exactly that (same RNG stream => bit-identical noise),
 `'device'` draws on the GPU instead (no H2D copy; different stream).
+
+Training (`loss.backward()` in E_align_s2.py:205, embedding_img.py:100-128): when autograd is recording and a
+parameter requires grad, `forward` builds a differentiable graph instead (`_forward_autograd`): every 3x3 / 1x1
+conv -- forward, data gradient and weight gradient -- runs on the tcgen05 kernels through dge_b200.autograd.conv2d;
+the point-wise and reduction steps between them are torch CUDA ops in this build (their fused backward kernels are
+the next row of SURVEY 8f-1).  Same noise draws, same return values.
 """
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 import model.utils.lreq as ln
 from model.utils.net import FromRGB
+from dge_b200 import autograd as tc
 from dge_b200 import ops
 
 DEFAULT_PLANES = 2
@@ -91,11 +99,49 @@ class BEBlock(nn.Module):
                 out = ops.blend(y1n, x, 0.111, 0.889, pool=False)
         return out, w1, w2
 
+    def _forward_autograd(self, x):
+        """Differentiable form of the block (E.py:50-85) on NCHW tensors; convs on the tensor-core kernels."""
+        n, c, h, w = x.shape
+        dev = x.device
+        w1 = F.linear(_mean_std(x), self.inver_mod1.weight, self.inver_mod1.bias)                 # :51-54
+        res = x
+        y = tc.conv2d(F.instance_norm(x, eps=self.instance_norm_1.eps), self.conv_1.weight, self.planes)   # :58-59
+        y = F.leaky_relu(torch.addcmul(y, self.noise_weight_1, self._noise(n, h, w, dev)) + self.bias_1, 0.2)  # :60-62
+        w2 = F.linear(_mean_std(y), self.inver_mod2.weight, self.inver_mod2.bias)                 # :64-67
+        y = F.instance_norm(y, eps=self.instance_norm_2.eps)                                       # :69
+        if self.has_last_conv:
+            y = tc.conv2d(y, self.conv_2.weight, self.planes)                                      # :72
+            y = F.leaky_relu(torch.addcmul(y, self.noise_weight_2, self._noise(n, h, w, dev)) + self.bias_2, 0.2)
+            y = F.avg_pool2d(y, 2, 2)                                                              # :76-77
+            res = F.avg_pool2d(res, 2, 2)                                                          # :78
+        if self.inputs != self.outputs:
+            res = tc.conv2d(res, self.conv_3.weight, self.planes) + self.conv_3.bias.view(1, -1, 1, 1)   # :81-82
+        return 0.111 * y + 0.889 * res, w1, w2                                                     # :84
+
     def forward(self, x):
         """Reference signature: NCHW in -> (NCHW out, w1, w2)."""
+        if _wants_grad(self, x):
+            return self._forward_autograd(x.float())
         ln._guard('BEBlock', x, self.conv_1.weight)
         out, w1, w2 = self.run(ops.nchw_to_f32b(x.float()))
         return out.to_nchw(), w1, w2
+
+
+def _mean_std(x):
+    """[N, 2C] = per-channel mean || biased std over (H, W), no epsilon (E.py:51-53, 64-66)."""
+    mean = x.mean(dim=(2, 3), keepdim=True)
+    std = ((x - mean) ** 2).mean(dim=(2, 3), keepdim=True).sqrt()
+    return torch.cat((mean, std), dim=1).flatten(1)
+
+
+def _wants_grad(module, x):
+    """True when this call must be recorded for backward: autograd is on and the input or a parameter needs grad."""
+    if not torch.is_grad_enabled():
+        return False
+    if not x.is_cuda:
+        raise ops.DgeError(f'{type(module).__name__}: dge_b200 runs on a B200 only (got a {x.device} tensor); '
+                           'no CPU fallback')
+    return x.requires_grad or any(p.requires_grad for p in module.parameters())
 
 
 class BE(nn.Module):
@@ -125,7 +171,22 @@ class BE(nn.Module):
         for b in self.decode_block:
             b.noise_mode = mode
 
+    def _forward_autograd(self, x, block_num):
+        """Training path: same data flow as `forward`, recorded for backward (see the module docstring)."""
+        c = self.FromRGB.from_rgb
+        if not c.implicit_lreq:
+            raise NotImplementedError('training path: explicit lreq scaling is not used by the reference (lreq.py:23-24)')
+        f = F.leaky_relu(F.conv2d(x, c.weight, c.bias), 0.2)          # net.py:231-240 (3 input channels: point-wise)
+        w = torch.tensor(0)
+        for i in range(9 - block_num, self.layer_count):
+            f, w1, w2 = self.decode_block[i]._forward_autograd(f)
+            w_ = torch.cat((w2.view(f.shape[0], 1, 512), w1.view(f.shape[0], 1, 512)), dim=1)      # E.py:131
+            w = w_ if i == (9 - block_num) else torch.cat((w_, w), dim=1)
+        return f, w
+
     def forward(self, x, block_num=9):
+        if _wants_grad(self, x):
+            return self._forward_autograd(x.float(), block_num)
         ln._guard('BE', x, self.FromRGB.from_rgb.weight)
         first = 9 - block_num
         eps0 = self.decode_block[first].instance_norm_1.eps if first < self.layer_count else 1e-8

@@ -400,7 +400,34 @@ def gradcam():
     print("gradcam_tiny.pt: out", tuple(mask.shape), mask.dtype, "index", fx["index"].tolist(), fx["index_max"])
 
 
+def encoder_grads():
+    """Training-step fixture: gradients of a fixed scalar loss w.r.t. every parameter of the reference encoder
+    (loss.backward() as in E_align_s2.py:205), on the weights / image of be_s16_l4.pt with the noise seed 99."""
+    import model.E.E as E
+    fx = torch.load(os.path.join(HERE, "be_s16_l4.pt"))
+    Enc = E.BE(**fx["config"])
+    Enc.load_state_dict(fx["state_dict"], strict=True)
+    torch.set_grad_enabled(True)
+    g = torch.Generator().manual_seed(1234)
+    t_const = torch.randn(fx["const"].shape, generator=g)
+    t_w = torch.randn(fx["w"].shape, generator=g)
+    torch.manual_seed(fx["noise_seed"])
+    const, w = Enc(fx["img"])
+    loss = ((const - t_const) ** 2).mean() + ((w - t_w) ** 2).mean()     # MSE terms of space_loss (training_utils.py:82-88)
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in Enc.named_parameters() if p.grad is not None}
+    unused = [k for k, p in Enc.named_parameters() if p.grad is None]    # parameters the forward never touches
+    torch.save({"t_const": t_const, "t_w": t_w, "loss": loss.detach(), "grads": grads, "unused": unused},
+               os.path.join(HERE, "be_s16_l4_grads.pt"))
+    print("be_s16_l4_grads.pt: loss", float(loss), "params", len(grads), "unused", unused,
+          "max|g|", max(float(v.abs().max()) for v in grads.values()))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "encoder_grads":
+        import_reference()
+        encoder_grads()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "gradcam":
         import numpy as np
         globals()["np"] = np

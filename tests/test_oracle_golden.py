@@ -95,6 +95,22 @@ def test_be_forward(be):
     assert rel(w, be["w"]) < TOL
 
 
+def test_be_gradients(be):
+    """Training step: autograd through the oracle == loss.backward() through the unmodified reference
+    (be_s16_l4_grads.pt, E_align_s2.py:205)."""
+    gx = torch.load(os.path.join(GOLD, "be_s16_l4_grads.pt"))
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in be["state_dict"].items()}
+    torch.manual_seed(be["noise_seed"])
+    with torch.enable_grad():
+        const, w = oenc.be_forward(sd, be["img"], be["config"]["layer_count"])
+        loss = ((const - gx["t_const"]) ** 2).mean() + ((w - gx["t_w"]) ** 2).mean()
+        loss.backward()
+    assert abs(float(loss) - float(gx["loss"])) < 1e-5 * abs(float(gx["loss"]))
+    assert set(k for k, v in sd.items() if v.grad is not None) == set(gx["grads"])
+    for k, g in gx["grads"].items():
+        assert rel(sd[k].grad, g) < 1e-4, k
+
+
 def test_e2g_roundtrip():
     fx = torch.load(os.path.join(GOLD, "e2g_res32.pt"))
     gsd, esd = fx["g_state_dict"], fx["e_state_dict"]

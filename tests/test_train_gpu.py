@@ -1,0 +1,106 @@
+"""Training step of the case-1 encoder on the GPU: `loss.backward()` through the mirrored `BE` (convs -- forward,
+data gradient, weight gradient -- on the tcgen05 kernels) against (a) the gradients the unmodified reference produced
+(tests/golden/be_s16_l4_grads.pt) and (b) the CPU oracle's autograd on fresh inputs; then one LREQAdam step.
+
+Bar: 1e-3 of each gradient tensor's scale (north_star tolerance); observed ~1e-5.
+"""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-3
+
+
+def rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-20)).item()
+
+
+def rel99(a, b):
+    """99th percentile of |a - b| over the scale of b.  leaky_relu's derivative jumps at 0: an activation whose
+    pre-activation is within rounding (~1e-5) of zero takes the other slope on the other device and moves the gradient
+    of the few elements that depend on it alone by up to 0.8x -- on ANY two implementations (CPU vs cuDNN too).  Sums
+    over many pixels (parameter gradients) dilute it, a per-pixel image gradient does not, hence the percentile."""
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    d = (a - b).abs().flatten()
+    return (torch.quantile(d, 0.99) / b.abs().max().clamp_min(1e-20)).item()
+
+
+def _encoder():
+    from model.E.E import BE
+    fx = torch.load(os.path.join(GOLD, "be_s16_l4.pt"))
+    E = BE(**fx["config"])
+    E.load_state_dict(fx["state_dict"], strict=True)
+    return fx, E.cuda()
+
+
+def test_encoder_backward_matches_reference_gradients():
+    fx, E = _encoder()
+    gx = torch.load(os.path.join(GOLD, "be_s16_l4_grads.pt"))
+    torch.manual_seed(fx["noise_seed"])
+    const, w = E(fx["img"].cuda())
+    assert const.requires_grad and w.requires_grad
+    assert rel(const, fx["const"]) < 2e-4 and rel(w, fx["w"]) < 2e-4      # the recorded forward is the same forward
+    loss = ((const - gx["t_const"].cuda()) ** 2).mean() + ((w - gx["t_w"].cuda()) ** 2).mean()
+    loss.backward()
+    assert abs(float(loss) - float(gx["loss"])) < 1e-4 * abs(float(gx["loss"]))
+    got = {k: p.grad for k, p in E.named_parameters() if p.grad is not None}
+    assert set(got) == set(gx["grads"])
+    for k, g in gx["grads"].items():
+        assert rel(got[k], g) < TOL, k
+
+
+def test_encoder_backward_vs_oracle_autograd_fresh_inputs():
+    """Batch 3, a fresh image, gradient also w.r.t. the image (the data gradient of the first convs)."""
+    from oracle import encoder as oenc
+    fx, E = _encoder()
+    g = torch.Generator().manual_seed(11)
+    img = torch.randn(3, 3, 32, 32, generator=g)
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in fx["state_dict"].items()}
+    img_ref = img.clone().requires_grad_(True)
+    torch.manual_seed(21)
+    const_r, w_r = oenc.be_forward(sd, img_ref, fx["config"]["layer_count"])
+    (const_r.sum() + (w_r ** 2).mean()).backward()
+    img_dev = img.cuda().requires_grad_(True)
+    torch.manual_seed(21)
+    const, w = E(img_dev)
+    (const.sum() + (w ** 2).mean()).backward()
+    assert rel99(img_dev.grad, img_ref.grad) < TOL and rel(img_dev.grad, img_ref.grad) < 0.2
+    for k, p in E.named_parameters():
+        if sd[k].grad is not None:
+            assert rel99(p.grad, sd[k].grad) < TOL and rel(p.grad, sd[k].grad) < 0.05, k
+
+
+def test_inference_path_unchanged_under_no_grad():
+    """no_grad / eval keeps the fused forward-only kernels (the benchmarked path)."""
+    from dge_b200 import ops
+    fx, E = _encoder()
+    ops.launch_count_reset()
+    with torch.no_grad():
+        torch.manual_seed(fx["noise_seed"])
+        const, w = E(fx["img"].cuda())
+    assert not const.requires_grad
+    assert rel(const, fx["const"]) < 2e-4 and rel(w, fx["w"]) < 2e-4
+    assert ops.launch_count() > 0
+
+
+def test_one_training_iteration_with_lreq_adam():
+    """E_align_s2.py:205-207 shape of an iteration: backward, LREQAdam.step, the loss goes down on the same batch."""
+    from model.utils.custom_adam import LREQAdam
+    fx, E = _encoder()
+    opt = LREQAdam(E.parameters(), lr=0.0015, betas=(0.0, 0.99), weight_decay=0)
+    img = fx["img"].cuda()
+    target = torch.randn(fx["w"].shape, generator=torch.Generator().manual_seed(3)).cuda()
+    losses = []
+    for _ in range(4):
+        torch.manual_seed(7)
+        _, w = E(img)
+        loss = ((w - target) ** 2).mean()
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert losses[-1] < losses[0]
