@@ -2,19 +2,41 @@
 
 The five 11x11 depthwise gaussian convolutions, the SSIM map and its mean are one fused kernel
 (`dge_ssim_sum`); only `size_average=True` (the only mode the inversion scripts use) is implemented.
+Inputs that require grad (training) take the differentiable torch form `_ssim_mean_autograd` instead.
 """
 import ctypes
 
 import torch
+import torch.nn.functional as F
 
 from dge_b200 import ops
+
+
+def _ssim_mean_autograd(a, b):
+    """Differentiable mean SSIM (training path, `_ssim` :18-38): normalised 11-tap gaussian (sigma 1.5) applied
+    separably per channel with zero padding 5, local moments, C1 = 0.01^2, C2 = 0.03^2, mean of the map."""
+    c = a.shape[1]
+    t = torch.arange(11, dtype=torch.float32, device=a.device) - 5.0
+    g = torch.exp(-(t * t) / (2 * 1.5 ** 2))
+    g = g / g.sum()
+    win = (g[:, None] * g[None, :]).expand(c, 1, 11, 11).contiguous()
+
+    def blur(v):
+        return F.conv2d(v, win, padding=5, groups=c)
+
+    mu_a, mu_b = blur(a), blur(b)
+    var_a, var_b, cov = blur(a * a) - mu_a * mu_a, blur(b * b) - mu_b * mu_b, blur(a * b) - mu_a * mu_b
+    c1, c2 = 0.01 ** 2, 0.03 ** 2
+    num = (2 * mu_a * mu_b + c1) * (2 * cov + c2)
+    den = (mu_a * mu_a + mu_b * mu_b + c1) * (var_a + var_b + c2)
+    return (num / den).mean()
 
 
 def _ssim_mean(img1, img2):
     if not (img1.is_cuda and img2.is_cuda):
         raise ops.DgeError('ssim: dge_b200 runs on a B200 only; there is no CPU fallback')
     if torch.is_grad_enabled() and (img1.requires_grad or img2.requires_grad):
-        raise NotImplementedError('ssim: dge_b200 kernels are forward-only in this build; use torch.no_grad()')
+        return _ssim_mean_autograd(img1.float(), img2.float())
     assert img1.shape == img2.shape and img1.ndim == 4
     a, b = img1.float().contiguous(), img2.float().contiguous()
     n, c, h, w = a.shape

@@ -6,8 +6,13 @@ the reference load unchanged.  The arithmetic is NOT PyTorch: every dense layer,
 convolution, FIR up-sampling and ToRGB accumulation runs in the hand-written sm_100a kernels behind
 the C ABI (include/dge_b200.h); PyTorch only owns device memory and the stream.
 
-Forward-only this round: calling with autograd enabled on tensors that require grad raises
-(backward kernels are SURVEY 8f-1).  No CPU fallback: CPU tensors raise DgeError.
+Inference (`torch.no_grad()`, or no input that requires grad) runs the fused forward-only kernels.  Training
+(E_align_s2.py:160: `generator.synthesis(w2)['image']` with w2 produced by the encoder under autograd):
+`SynthesisModule.forward` records a differentiable graph w.r.t. `wp` (`_forward_autograd`): the generator is
+frozen in every training script (only `E.parameters()` reach LREQAdam, E_align_s2.py:97), so its parameters enter
+as constants and its never-read `.grad` is not accumulated; the stride-1 3x3 modulated convs run forward and
+backward on the tcgen05 kernels (dge_b200.autograd.conv2d), the x2 transposed convs and the point-wise steps are
+torch CUDA ops in this build.  The mapping network stays forward-only.  No CPU fallback: CPU tensors raise DgeError.
 
 Reference behaviours kept on purpose: result-dict keys, train-mode `w_avg` EMA + style mixing with
 the same RNG calls (:177-191), `randomize_noise=True` drawing `torch.randn(N,1,res,res)` on the CPU
@@ -16,7 +21,9 @@ per layer in layer order (:912-913), ValueErrors on bad shapes (:99-105, :247-25
 import numpy as np
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
+from dge_b200 import autograd as tc
 from dge_b200 import ops
 
 __all__ = ['StyleGAN2Generator']
@@ -388,6 +395,34 @@ class ModulateConvBlock(nn.Module):
                         noise_scalar=p['strength'], bias=p['bias'], slope=self.slope, gain=self.activate_scale,
                         out_act=want_act, out_scale=next_style, out_nchw=want_nchw, rgb_w=rgb_w, rgb_out=rgb_out)
 
+    def _forward_autograd(self, x, w_latent, randomize_noise=False):
+        """Differentiable w.r.t. x and w_latent (parameters are constants): :855-922 in the shared-weight form
+        y = d[n,o] * conv(x * s[n,i], W) of SURVEY Appendix E-1.  NCHW in, (NCHW out, style)."""
+        n = x.shape[0]
+        st = self.style
+        sb = None if st.bias is None else st.bias.detach() * st.bscale
+        style = F.linear(w_latent, st.weight.detach() * st.wscale, sb) + st.additional_bias       # :862, 990-996
+        wgt = self.weight.detach() * self.wscale                                                   # :858
+        xs = x * style.view(n, self.in_c, 1, 1)                                                    # :877
+        if self.use_conv2d_transpose:
+            y = F.conv_transpose2d(xs, wgt.flip(2, 3).transpose(0, 1), stride=2)                   # :879-895
+            y = _fir4(y, self.filter.kernel, (1, 1, 1, 1))                                         # :896
+        elif self.ksize == 3 and self.in_c % 16 == 0 and self.out_c % 16 == 0:
+            y = tc.conv2d(xs, wgt, self.planes)                                                    # :897-904 (tcgen05)
+        else:
+            y = F.conv2d(xs, wgt, padding=self.ksize // 2)                                         # ToRGB (3 outputs)
+        if self.demodulate:
+            d = torch.rsqrt((wgt.square().sum(dim=(2, 3))[None] * style.square()[:, None]).sum(dim=2) + self.eps)
+            y = y * d.view(n, self.out_c, 1, 1)                                                    # :867-870, 908-909
+        if self.add_noise:
+            noise, _ = self._noise(n, randomize_noise, x.device)
+            y = y + noise * self.noise_strength.detach()                                           # :911-916
+        if self.bias is not None:
+            y = y + (self.bias.detach() * self.bscale).view(1, -1, 1, 1)                           # :918-920
+        if self.slope != 1.0:
+            y = F.leaky_relu(y, self.slope) * self.activate_scale                                  # :921
+        return y, style
+
     def rgb_weights(self, style):
         """ToRGB layers (k=1, no demod): per-sample [N][3][Cin] weights with style and wscale folded in."""
         return ops.rgb_weights(self.weight, style, self.wscale)
@@ -407,6 +442,22 @@ class ModulateConvBlock(nn.Module):
         xa = ops.nchw_to_act(x.float(), scale=style, planes=self.planes)
         out = self.run(xa, style, randomize_noise, want_act=False, want_nchw=True)
         return out['nchw'], style
+
+
+def _fir4(x, kernel, pad):
+    """Depth-wise 4x4 FIR of an NCHW tensor after zero padding `pad` (left, right, top, bottom) -- UpsamplingLayer
+    :592-615 (training path only; the inference kernels fuse it)."""
+    n, c, h, w = x.shape
+    y = F.conv2d(F.pad(x.reshape(n * c, 1, h, w), pad), kernel.to(x))
+    return y.view(n, c, y.shape[2], y.shape[3])
+
+
+def _fir_up2(img, kernel):
+    """Skip-branch x2 upsample (:556-615, scale_factor=2): zero insertion, pad (2,1,2,1), 4x4 FIR."""
+    n, c, h, w = img.shape
+    z = img.new_zeros(n, c, 2 * h, 2 * w)
+    z[:, :, ::2, ::2] = img
+    return _fir4(z, kernel, (2, 1, 2, 1))
 
 
 class SynthesisModule(nn.Module):
@@ -540,13 +591,31 @@ class SynthesisModule(nn.Module):
         rgb_ws = [view(c['views'][nl + k]['rgbw']) for k in range(len(outputs))]
         return styles, demods, rgb_styles, rgb_ws
 
+    def _forward_autograd(self, wp, randomize_noise=False):
+        """Training path: the same result dict, recorded for backward w.r.t. `wp` (see the module docstring)."""
+        n, nl = wp.shape[0], self.num_layers
+        wp32 = wp.float()
+        results = {'wp': wp}
+        x = self.early_layer.const.detach().float().expand(n, -1, -1, -1)                          # :630-632
+        image = None
+        for i in range(nl - 1):
+            x, style = getattr(self, f'layer{i}')._forward_autograd(x, wp32[:, i], randomize_noise)
+            results[f'style{i:02d}'] = style
+            if i % 2 == 0:                                                                         # :511-522
+                rgb, style = getattr(self, f'output{i // 2}')._forward_autograd(x, wp32[:, i + 1])
+                results[f'output_style{i // 2}'] = style
+                image = rgb if image is None else rgb + _fir_up2(image, self.upsample.kernel)
+        results['image'] = self.final_activate(image)
+        return results
+
     def forward(self, wp, randomize_noise=False):
         if wp.ndim != 3 or wp.shape[1:] != (self.num_layers, self.w_space_dim):
             raise ValueError(f'Input tensor should be with shape [batch_size, num_layers, w_space_dim], where '
                              f'`num_layers` equals to {self.num_layers}, and `w_space_dim` equals to '
                              f'{self.w_space_dim}!\nBut `{wp.shape}` is received!')
         _require_cuda(wp, 'SynthesisModule')
-        _check_no_grad(wp)
+        if torch.is_grad_enabled() and wp.requires_grad:
+            return self._forward_autograd(wp, randomize_noise)
         n, dev = wp.shape[0], wp.device
         wp32 = wp.float()
         results = {'wp': wp}

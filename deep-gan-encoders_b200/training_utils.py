@@ -6,12 +6,14 @@ small host helpers the scripts import (`set_seed` :46-51, `truncated_noise_sampl
 NaN -> 0, inf -> 1), cosine over the flattened WHOLE batch, avg-pool while H > 256, SSIM, LPIPS through the
 caller's `lpips_model`, `loss = 5*mse + 3*cos + (1-ssim) + 2*lpips`, `loss_info` of Python floats.
 One pass over the image pair produces all six moments; the whole call does ONE device->host read instead of
-the reference's seven `.item()` syncs.  Forward-only in this build.
+the reference's seven `.item()` syncs.  When an input requires grad (the training scripts back-propagate through
+this loss) the loss terms are recorded for autograd instead -- see `_space_loss_autograd`.
 """
 import math
 
 import numpy as np
 import torch
+import torch.nn.functional as F
 
 import metric.pytorch_ssim as pytorch_ssim
 from dge_b200 import ops
@@ -54,20 +56,12 @@ def avg_pool_to_256(x):
     return out
 
 
-def space_loss(imgs1, imgs2, image_space=True, lpips_model=None):
-    if not (imgs1.is_cuda and imgs2.is_cuda):
-        raise ops.DgeError('space_loss: dge_b200 runs on a B200 only; there is no CPU fallback')
-    if torch.is_grad_enabled() and (imgs1.requires_grad or imgs2.requires_grad):
-        raise NotImplementedError('space_loss: dge_b200 kernels are forward-only in this build; use torch.no_grad()')
-    if imgs1.reshape(-1).shape[0] != imgs2.reshape(-1).shape[0]:
-        print('error: vector1 dimentions are not equal to vector2 dimentions')
-        return
-    a = imgs1.float().contiguous()
-    b = imgs2.float().contiguous()
-    dev = a.device
-    n = a.numel()
+def _pair_stats(a, b):
+    """One pass of `dge_pair_moments` + one of `dge_softmax_kl_sum` over two equal-sized fp32 tensors and ONE host
+    sync -> dict of the scalar statistics `space_loss` reports (training_utils.py:63-77)."""
+    dev, n = a.device, a.numel()
     L = ops.lib()
-    acc = torch.zeros(8, dtype=torch.float64, device=dev)   # 0..5 moments, 6 kl sum, 7 ssim sum
+    acc = torch.zeros(8, dtype=torch.float64, device=dev)   # 0..5 moments, 6 kl sum, 7 ssim sum (filled by the caller)
     ops.check(L.dge_pair_moments(ops._p(a), ops._p(b), n, ops._p(acc), ops._stream()))
     # implicit-dim softmax: dim 0 for 0/1/3-D inputs, dim 1 otherwise (torch.nn.functional._get_softmax_dim)
     dim = 0 if a.ndim in (0, 1, 3) else 1
@@ -75,15 +69,11 @@ def space_loss(imgs1, imgs2, image_space=True, lpips_model=None):
     outer = int(np.prod(shape[:dim])) if dim > 0 else 1
     inner = int(np.prod(shape[dim + 1:])) if dim + 1 < len(shape) else 1
     ops.check(L.dge_softmax_kl_sum(ops._p(a), ops._p(b), outer, shape[dim], inner, ops._p(acc[6:7]), ops._stream()))
-    lp = None
-    if image_space:
-        pa, pb = avg_pool_to_256(a), avg_pool_to_256(b)
-        ops.check(L.dge_ssim_sum(ops._p(pa), ops._p(pb), pa.shape[0] * pa.shape[1], pa.shape[2], pa.shape[3],
-                                 ops._p(acc[7:8]), ops._stream()))
-        lp = lpips_model(pa, pb).mean()      # third-party LPIPS (unpinned) stays the caller's module
-        n_ssim = pa.numel()
-    host = acc.cpu().tolist()               # the one sync of this call
-    sa, sb, saa, sbb, sab, sdd, kl_sum, ssim_sum = host
+    return acc
+
+
+def _stats_from_sums(host, n):
+    sa, sb, saa, sbb, sab, sdd, kl_sum = host[:7]
     mse1 = sdd / n
     m1, m2 = sa / n, sb / n
     mse2 = (m1 - m2) ** 2
@@ -100,8 +90,57 @@ def space_loss(imgs1, imgs2, image_space=True, lpips_model=None):
         kl = 1.0
     denom = math.sqrt(saa) * math.sqrt(sbb)
     cos = 1 - (sab / denom if denom > 0 else float('nan'))
+    return mse1, mse2, mse3, kl, cos
+
+
+def _space_loss_autograd(a, b, image_space, lpips_model):
+    """Training form (E_align_s2.py:184-205 back-propagates through this loss): the four terms that make up the loss
+    are recorded for backward as torch CUDA ops; the statistics that are only logged (mean / std MSE, KL) still come
+    from the fused reduction kernels on the detached values."""
+    n = a.numel()
+    host = _pair_stats(a.detach(), b.detach()).cpu().tolist()
+    mse1, mse2, mse3, kl, _ = _stats_from_sums(host, n)
+    fa, fb = a.reshape(-1), b.reshape(-1)
+    mse = (fa - fb).square().mean()                                                # :63
+    cos = 1 - fa.dot(fb) / (fa.dot(fa).sqrt() * fb.dot(fb).sqrt())                 # :74-76
     if image_space:
-        ssim_l = 1 - ssim_sum / n_ssim
+        f = 1
+        while a.shape[2] // f > 256:                                               # :81-84 (2x2 means compose)
+            f *= 2
+        pa, pb = (a, b) if f == 1 else (F.avg_pool2d(a, f, f), F.avg_pool2d(b, f, f))
+        ssim_l = 1 - pytorch_ssim.ssim(pa, pb)                                     # :87-88
+        lp = lpips_model(pa, pb).mean()                                            # :93
+    else:
+        ssim_l, lp = torch.tensor(0), torch.tensor(0)                              # :90, 95
+    loss = 5 * mse + 3 * cos + ssim_l + 2 * lp                                     # :97
+    return loss, [[mse1, mse2, mse3], kl, cos.item(), ssim_l.item(), lp.item()]
+
+
+def space_loss(imgs1, imgs2, image_space=True, lpips_model=None):
+    if not (imgs1.is_cuda and imgs2.is_cuda):
+        raise ops.DgeError('space_loss: dge_b200 runs on a B200 only; there is no CPU fallback')
+    if imgs1.reshape(-1).shape[0] != imgs2.reshape(-1).shape[0]:
+        print('error: vector1 dimentions are not equal to vector2 dimentions')
+        return
+    a = imgs1.float().contiguous()
+    b = imgs2.float().contiguous()
+    if torch.is_grad_enabled() and (a.requires_grad or b.requires_grad):
+        return _space_loss_autograd(a, b, image_space, lpips_model)
+    dev = a.device
+    n = a.numel()
+    L = ops.lib()
+    acc = _pair_stats(a, b)
+    lp = None
+    if image_space:
+        pa, pb = avg_pool_to_256(a), avg_pool_to_256(b)
+        ops.check(L.dge_ssim_sum(ops._p(pa), ops._p(pb), pa.shape[0] * pa.shape[1], pa.shape[2], pa.shape[3],
+                                 ops._p(acc[7:8]), ops._stream()))
+        lp = lpips_model(pa, pb).mean()      # third-party LPIPS (unpinned) stays the caller's module
+        n_ssim = pa.numel()
+    host = acc.cpu().tolist()               # the one sync of this call
+    mse1, mse2, mse3, kl, cos = _stats_from_sums(host, n)
+    if image_space:
+        ssim_l = 1 - host[7] / n_ssim
         lp_v = float(lp.item())
     else:
         ssim_l, lp_v = 0, 0

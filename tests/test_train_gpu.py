@@ -104,3 +104,57 @@ def test_one_training_iteration_with_lreq_adam():
         opt.step()
         losses.append(float(loss))
     assert losses[-1] < losses[0]
+
+
+def _lpips_stand_in(a, b):
+    """Differentiable stand-in for the third-party LPIPS module (not installed): per-sample scalar."""
+    return ((a - b) ** 2).mean(dim=(1, 2, 3), keepdim=True) + 0.1 * (a - b).abs().mean(dim=(1, 2, 3), keepdim=True)
+
+
+def test_full_training_iteration_gradients_vs_oracle():
+    """E_align_s2.py:152-207 on the small E/G pair: imgs1 = G(z) under no_grad, (const2, w2) = E(imgs1),
+    imgs2 = G.synthesis(w2)['image'], image-space + latent-space `space_loss`, backward into E.  Every encoder
+    gradient against autograd through the CPU oracle of the same chain."""
+    from model.E.E import BE
+    from model.stylegan2_generator import StyleGAN2Generator
+    import training_utils as tu
+    from oracle import encoder as oenc
+    from oracle import losses as oloss
+    from oracle import stylegan2 as osg2
+    fx = torch.load(os.path.join(GOLD, "e2g_res32.pt"))
+    G = StyleGAN2Generator(**fx["g_config"])
+    G.load_state_dict(fx["g_state_dict"], strict=True)
+    E = BE(**fx["e_config"])
+    E.load_state_dict(fx["e_state_dict"], strict=True)
+    G, E = G.cuda().eval(), E.cuda()
+    with torch.no_grad():
+        r1 = G(fx["z"].cuda(), trunc_psi=0.7, trunc_layers=8, randomize_noise=False)
+    imgs1, w1 = r1["image"], r1["wp"]
+    torch.manual_seed(fx["noise_seed"])
+    const2, w2 = E(imgs1)
+    imgs2 = G.synthesis(w2)["image"]
+    assert imgs2.requires_grad and rel(imgs2, fx["imgs2"]) < 1e-3
+    l_img, info_img = tu.space_loss(imgs1, imgs2, lpips_model=_lpips_stand_in)
+    l_w, info_w = tu.space_loss(w1, w2, image_space=False)
+    (l_img + 0.01 * l_w).backward()
+    assert all(p.grad is None for p in G.parameters())          # the frozen generator accumulates nothing
+
+    # the same chain through the CPU oracle
+    esd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in fx["e_state_dict"].items()}
+    gsd = fx["g_state_dict"]
+    imgs1_c, w1_c = imgs1.cpu(), w1.cpu()
+    torch.manual_seed(fx["noise_seed"])
+    const2_r, w2_r = oenc.be_forward(esd, imgs1_c, fx["e_config"]["layer_count"])
+    imgs2_r = osg2.synthesis(gsd, w2_r, fx["g_config"]["resolution"])["image"]
+    l_img_r, info_img_r = oloss.space_loss(imgs1_c, imgs2_r, lpips_model=_lpips_stand_in)
+    l_w_r, info_w_r = oloss.space_loss(w1_c, w2_r, image_space=False)
+    (l_img_r + 0.01 * l_w_r).backward()
+    assert abs(float(l_img.detach()) - float(l_img_r.detach())) < 1e-3 * abs(float(l_img_r.detach()))
+    assert abs(float(l_w.detach()) - float(l_w_r.detach())) < 1e-3 * abs(float(l_w_r.detach()))
+    for got, want in ((info_img, info_img_r), (info_w, info_w_r)):
+        flat = lambda i: list(i[0]) + list(i[1:])
+        for u, v in zip(flat(got), flat(want)):
+            assert abs(u - v) <= 2e-3 * abs(v) + 1e-6
+    for k, p in E.named_parameters():
+        if esd[k].grad is not None:
+            assert rel99(p.grad, esd[k].grad) < TOL and rel(p.grad, esd[k].grad) < 0.05, k

@@ -1,0 +1,89 @@
+"""Host logic of the training path on CPU: the graphs `BE._forward_autograd` and `SynthesisModule._forward_autograd`
+record, with the one CUDA-only node (dge_b200.autograd.conv2d -> tcgen05 kernels) swapped for ATen's conv, against the
+golden fixtures of the unmodified reference and autograd through the oracle.  The kernels themselves are covered on
+the GPU (tests/test_conv_gpu.py, tests/test_train_gpu.py); the public entry points still refuse CPU tensors."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rel(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-20)).item()
+
+
+@pytest.fixture()
+def aten_conv(monkeypatch):
+    import model.E.E as EM
+    import model.stylegan2_generator as SG
+
+    def conv(x, w, planes=2):
+        return F.conv2d(x, w, padding=w.shape[-1] // 2)
+
+    monkeypatch.setattr(EM.tc, "conv2d", conv)
+    monkeypatch.setattr(SG.tc, "conv2d", conv)
+
+
+def test_encoder_graph_matches_reference_gradients(aten_conv):
+    from model.E.E import BE
+    fx = torch.load(os.path.join(GOLD, "be_s16_l4.pt"))
+    gx = torch.load(os.path.join(GOLD, "be_s16_l4_grads.pt"))
+    E = BE(**fx["config"])
+    E.load_state_dict(fx["state_dict"], strict=True)
+    torch.manual_seed(fx["noise_seed"])
+    const, w = E._forward_autograd(fx["img"], 9)
+    assert rel(const, fx["const"]) < 2e-5 and rel(w, fx["w"]) < 2e-5
+    (((const - gx["t_const"]) ** 2).mean() + ((w - gx["t_w"]) ** 2).mean()).backward()
+    got = {k: p.grad for k, p in E.named_parameters() if p.grad is not None}
+    assert set(got) == set(gx["grads"])
+    for k, g in gx["grads"].items():
+        assert rel(got[k], g) < 1e-4, k
+
+
+def test_synthesis_graph_matches_oracle_gradient(aten_conv):
+    from model.stylegan2_generator import StyleGAN2Generator
+    from oracle import stylegan2 as osg2
+    fx = torch.load(os.path.join(GOLD, "sg2_res32.pt"))
+    G = StyleGAN2Generator(**fx["config"])
+    G.load_state_dict(fx["state_dict"], strict=True)
+    wp = fx["wp"].clone().requires_grad_(True)
+    out = G.synthesis._forward_autograd(wp)
+    assert rel(out["image"], fx["image"]) < 2e-5
+    target = torch.randn(out["image"].shape, generator=torch.Generator().manual_seed(1))
+    ((out["image"] - target) ** 2).mean().backward()
+    assert all(p.grad is None for p in G.parameters())       # frozen generator: constants
+    wp_r = fx["wp"].clone().requires_grad_(True)
+    ref = osg2.synthesis(fx["state_dict"], wp_r, fx["config"]["resolution"])
+    ((ref["image"] - target) ** 2).mean().backward()
+    assert set(out) == set(ref)
+    assert rel(wp.grad, wp_r.grad) < 1e-5
+    torch.manual_seed(77)
+    out_rn = G.synthesis._forward_autograd(fx["wp"].clone().requires_grad_(True), randomize_noise=True)
+    assert rel(out_rn["image"], fx["image_randnoise_seed77"]) < 2e-5
+
+
+def test_differentiable_ssim_matches_oracle():
+    import metric.pytorch_ssim as ps
+    from oracle import losses as ol
+    g = torch.Generator().manual_seed(3)
+    a = torch.rand(2, 3, 40, 40, generator=g).requires_grad_(True)
+    b = torch.rand(2, 3, 40, 40, generator=g)
+    s1 = ps._ssim_mean_autograd(a, b)
+    (g1,) = torch.autograd.grad(s1, a)
+    s2 = ol.ssim(a, b)
+    (g2,) = torch.autograd.grad(s2, a)
+    assert abs(float(s1.detach()) - float(s2.detach())) < 1e-6 and rel(g1, g2) < 1e-5
+
+
+def test_public_entry_points_still_refuse_cpu_tensors():
+    from dge_b200 import ops
+    from model.E.E import BE
+    E = BE(startf=16, maxf=32, layer_count=4)
+    with pytest.raises(ops.DgeError):
+        E(torch.zeros(1, 3, 32, 32))
+    from dge_b200 import autograd as tc
+    with pytest.raises(ops.DgeError):
+        tc.conv2d(torch.zeros(1, 16, 8, 8), torch.zeros(16, 16, 3, 3))
