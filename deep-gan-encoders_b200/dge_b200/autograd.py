@@ -38,8 +38,19 @@ class _Conv2dTC(torch.autograd.Function):
             dx = ops.conv(dya, ops.pack_conv_weight_dgrad(w, planes=ctx.planes), cin, ctx.kind, out_nchw=True)["nchw"]
         if ctx.needs_input_grad[1]:
             dw = ops.conv_wgrad(dya, ctx.xa, k)
-        ctx.xa = None
+        # ctx.xa stays: E_align_s2.py:205 calls backward(retain_graph=True) and walks the encoder's graph a second time
         return dx, dw, None
+
+
+def require_fp32_library_convs():
+    """The training path still sends a few convolutions through cuDNN (from_rgb / ToRGB with 3 channels, the x2
+    transposed convs, the FIR and SSIM windows).  PyTorch lets cuDNN run those in TF32 by default: operands rounded
+    to 10 mantissa bits, ~5e-4 relative error per conv, outside the 1e-3 parity bar once chained (measured: 1e-2 on
+    the image gradient).  The reference's numbers are fp32, so the path pins the library convs to fp32."""
+    if torch.backends.cudnn.allow_tf32:
+        torch.backends.cudnn.allow_tf32 = False
+    if torch.backends.cuda.matmul.allow_tf32:
+        torch.backends.cuda.matmul.allow_tf32 = False
 
 
 def conv2d(x, w, planes=2):

@@ -15,6 +15,8 @@ from dge_b200 import ops
 def _ssim_mean_autograd(a, b):
     """Differentiable mean SSIM (training path, `_ssim` :18-38): normalised 11-tap gaussian (sigma 1.5) applied
     separably per channel with zero padding 5, local moments, C1 = 0.01^2, C2 = 0.03^2, mean of the map."""
+    from dge_b200 import autograd as tc
+    tc.require_fp32_library_convs()
     c = a.shape[1]
     t = torch.arange(11, dtype=torch.float32, device=a.device) - 5.0
     g = torch.exp(-(t * t) / (2 * 1.5 ** 2))

@@ -593,6 +593,7 @@ class SynthesisModule(nn.Module):
 
     def _forward_autograd(self, wp, randomize_noise=False):
         """Training path: the same result dict, recorded for backward w.r.t. `wp` (see the module docstring)."""
+        tc.require_fp32_library_convs()
         n, nl = wp.shape[0], self.num_layers
         wp32 = wp.float()
         results = {'wp': wp}

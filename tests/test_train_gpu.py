@@ -88,7 +88,8 @@ def test_inference_path_unchanged_under_no_grad():
 
 
 def test_one_training_iteration_with_lreq_adam():
-    """E_align_s2.py:205-207 shape of an iteration: backward, LREQAdam.step, the loss goes down on the same batch."""
+    """E_align_s2.py:205-233 shape of an iteration: backward(retain_graph=True), LREQAdam.step, a second backward
+    through the same graph, step; the loss goes down on the same batch."""
     from model.utils.custom_adam import LREQAdam
     fx, E = _encoder()
     opt = LREQAdam(E.parameters(), lr=0.0015, betas=(0.0, 0.99), weight_decay=0)
@@ -100,9 +101,13 @@ def test_one_training_iteration_with_lreq_adam():
         _, w = E(img)
         loss = ((w - target) ** 2).mean()
         opt.zero_grad()
-        loss.backward()
+        loss.backward(retain_graph=True)
         opt.step()
-        losses.append(float(loss))
+        loss_b = (w - target).abs().mean()      # second backward through the SAME graph, as E_align_s2.py:205-233 does
+        opt.zero_grad()
+        loss_b.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
     assert losses[-1] < losses[0]
 
 
