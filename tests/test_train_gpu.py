@@ -2,12 +2,22 @@
 data gradient, weight gradient -- on the tcgen05 kernels) against (a) the gradients the unmodified reference produced
 (tests/golden/be_s16_l4_grads.pt) and (b) the CPU oracle's autograd on fresh inputs; then one LREQAdam step.
 
-Bar: 1e-3 of each gradient tensor's scale (north_star tolerance); observed ~1e-5.
+Bar: 1e-3 of each gradient tensor's scale (north_star tolerance); observed ~3e-5.
+
+leaky_relu's derivative jumps at 0.  An activation whose pre-activation lies within rounding (~1e-5 of the tensor's
+scale) of zero takes the other slope on another implementation -- CPU vs cuDNN as much as CPU vs these kernels -- and
+that ONE element moves every upstream gradient by a visible amount (measured on the e2g fixture: a single flipped
+activation of 4096 in the generator's 8x8 layer shifts the encoder gradients by 2.6e-3 of their scale; with the
+pattern held fixed the difference is 3e-5).  The oracle comparisons below therefore evaluate the oracle at the
+activation pattern the GPU run produced (`record_masks` / `replay_masks`), which tests the arithmetic and not the
+coin flips; the fixture comparison (reference gradients, no replay possible) has no activation that close to zero.
 """
+import contextlib
 import os
 
 import pytest
 import torch
+import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -19,14 +29,39 @@ def rel(a, b):
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-20)).item()
 
 
-def rel99(a, b):
-    """99th percentile of |a - b| over the scale of b.  leaky_relu's derivative jumps at 0: an activation whose
-    pre-activation is within rounding (~1e-5) of zero takes the other slope on the other device and moves the gradient
-    of the few elements that depend on it alone by up to 0.8x -- on ANY two implementations (CPU vs cuDNN too).  Sums
-    over many pixels (parameter gradients) dilute it, a per-pixel image gradient does not, hence the percentile."""
-    a, b = a.detach().float().cpu(), b.detach().float().cpu()
-    d = (a - b).abs().flatten()
-    return (torch.quantile(d, 0.99) / b.abs().max().clamp_min(1e-20)).item()
+@contextlib.contextmanager
+def record_masks(store):
+    """Record the sign pattern of every leaky_relu input, in call order (product path and oracle call it in the same
+    order: from_rgb, then per block / per layer)."""
+    orig = F.leaky_relu
+
+    def lrelu(x, negative_slope=0.01, inplace=False):
+        store.append((x.detach() > 0).cpu())
+        return orig(x, negative_slope)
+
+    F.leaky_relu = lrelu
+    try:
+        yield
+    finally:
+        F.leaky_relu = orig
+
+
+@contextlib.contextmanager
+def replay_masks(store):
+    """leaky_relu with the recorded pattern instead of the sign of its own input."""
+    orig = F.leaky_relu
+    it = iter(store)
+
+    def lrelu(x, negative_slope=0.01, inplace=False):
+        m = next(it)
+        assert m.shape == x.shape
+        return torch.where(m, x, x * negative_slope)
+
+    F.leaky_relu = lrelu
+    try:
+        yield
+    finally:
+        F.leaky_relu = orig
 
 
 def _encoder():
@@ -59,19 +94,23 @@ def test_encoder_backward_vs_oracle_autograd_fresh_inputs():
     fx, E = _encoder()
     g = torch.Generator().manual_seed(11)
     img = torch.randn(3, 3, 32, 32, generator=g)
+    img_dev = img.cuda().requires_grad_(True)
+    masks = []
+    torch.manual_seed(21)
+    with record_masks(masks):
+        const, w = E(img_dev)
+    (const.sum() + (w ** 2).mean()).backward()
     sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in fx["state_dict"].items()}
     img_ref = img.clone().requires_grad_(True)
     torch.manual_seed(21)
-    const_r, w_r = oenc.be_forward(sd, img_ref, fx["config"]["layer_count"])
+    with replay_masks(masks):
+        const_r, w_r = oenc.be_forward(sd, img_ref, fx["config"]["layer_count"])
     (const_r.sum() + (w_r ** 2).mean()).backward()
-    img_dev = img.cuda().requires_grad_(True)
-    torch.manual_seed(21)
-    const, w = E(img_dev)
-    (const.sum() + (w ** 2).mean()).backward()
-    assert rel99(img_dev.grad, img_ref.grad) < TOL and rel(img_dev.grad, img_ref.grad) < 0.2
+    assert rel(const, const_r) < 2e-4 and rel(w, w_r) < 2e-4
+    assert rel(img_dev.grad, img_ref.grad) < TOL
     for k, p in E.named_parameters():
         if sd[k].grad is not None:
-            assert rel99(p.grad, sd[k].grad) < TOL and rel(p.grad, sd[k].grad) < 0.05, k
+            assert rel(p.grad, sd[k].grad) < TOL, k
 
 
 def test_inference_path_unchanged_under_no_grad():
@@ -135,9 +174,11 @@ def test_full_training_iteration_gradients_vs_oracle():
     with torch.no_grad():
         r1 = G(fx["z"].cuda(), trunc_psi=0.7, trunc_layers=8, randomize_noise=False)
     imgs1, w1 = r1["image"], r1["wp"]
+    masks = []
     torch.manual_seed(fx["noise_seed"])
-    const2, w2 = E(imgs1)
-    imgs2 = G.synthesis(w2)["image"]
+    with record_masks(masks):
+        const2, w2 = E(imgs1)
+        imgs2 = G.synthesis(w2)["image"]
     assert imgs2.requires_grad and rel(imgs2, fx["imgs2"]) < 1e-3
     l_img, info_img = tu.space_loss(imgs1, imgs2, lpips_model=_lpips_stand_in)
     l_w, info_w = tu.space_loss(w1, w2, image_space=False)
@@ -149,8 +190,9 @@ def test_full_training_iteration_gradients_vs_oracle():
     gsd = fx["g_state_dict"]
     imgs1_c, w1_c = imgs1.cpu(), w1.cpu()
     torch.manual_seed(fx["noise_seed"])
-    const2_r, w2_r = oenc.be_forward(esd, imgs1_c, fx["e_config"]["layer_count"])
-    imgs2_r = osg2.synthesis(gsd, w2_r, fx["g_config"]["resolution"])["image"]
+    with replay_masks(masks):
+        const2_r, w2_r = oenc.be_forward(esd, imgs1_c, fx["e_config"]["layer_count"])
+        imgs2_r = osg2.synthesis(gsd, w2_r, fx["g_config"]["resolution"])["image"]
     l_img_r, info_img_r = oloss.space_loss(imgs1_c, imgs2_r, lpips_model=_lpips_stand_in)
     l_w_r, info_w_r = oloss.space_loss(w1_c, w2_r, image_space=False)
     (l_img_r + 0.01 * l_w_r).backward()
@@ -162,4 +204,4 @@ def test_full_training_iteration_gradients_vs_oracle():
             assert abs(u - v) <= 2e-3 * abs(v) + 1e-6
     for k, p in E.named_parameters():
         if esd[k].grad is not None:
-            assert rel99(p.grad, esd[k].grad) < TOL and rel(p.grad, esd[k].grad) < 0.05, k
+            assert rel(p.grad, esd[k].grad) < TOL, k
