@@ -25,6 +25,7 @@
 #ifndef DGE_B200_H_
 #define DGE_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus

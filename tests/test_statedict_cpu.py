@@ -98,3 +98,46 @@ def test_product_path_fails_loudly_without_gpu():
     E = BE(16, 32, 2, 512, 3)
     with torch.no_grad(), pytest.raises(DgeError):
         E(torch.zeros(1, 3, 8, 8))
+
+
+def test_header_is_plain_c_and_structs_match_ctypes_field_by_field(tmp_path):
+    """include/dge_b200.h must compile as C99 (the boundary is a C ABI, not C++), and every field of the two structs
+    that cross it must sit at the offset the ctypes mirror assumes."""
+    import ctypes
+    import shutil
+    import subprocess
+    from dge_b200._lib import ConvArgs, Sg2PrepItem
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    pairs = [("dge_conv_args", ConvArgs), ("dge_sg2_prep_item", Sg2PrepItem)]
+    lines = ['#include "dge_b200.h"', "#include <stdio.h>", "int main(void) {"]
+    for cname, st in pairs:
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in st._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run([gcc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                    "-o", str(exe)], check=True, capture_output=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, st in pairs:
+        assert int(got[cname]) == ctypes.sizeof(st), cname
+        for fname, _ in st._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(st, fname).offset, f"{cname}.{fname}"
+
+
+def test_ctypes_signatures_have_the_declared_argument_counts():
+    """Every prototype in the header against the ctypes table: same number of parameters."""
+    from dge_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "dge_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    protos = re.findall(r"\b(dge_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", header)
+    assert len(protos) >= 50
+    for name, params in protos:
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        restype, argtypes = _lib.SIGNATURES[name]
+        assert len(argtypes) == n, f"{name}: header has {n} parameters, ctypes table {len(argtypes)}"
