@@ -11,14 +11,22 @@ Per block:  [nearest x2 -> tcgen05 3x3 conv | tcgen05 stride-2 transposed conv] 
 4-tap `transform_kernel`, 3x3 Blur, noise, bias, lrelu) -> stats -> one kernel (instance norm + style_mod + bf16 split
 [+ upsample for the next block]) -> tcgen05 3x3 conv with noise/bias/lrelu epilogue -> stats -> norm+style_mod.
 `decode2`/`decode3`/`forward_double` (blend / blob-removal experiments) are not on the inversion path.
+
+Training (E_align_s2.py:158: `Gs.forward(w2, lod)` with w2 from the encoder under autograd): when `styles` requires
+grad, `Generator.forward` records a differentiable graph w.r.t. `styles` (`_decode_autograd`; the generator is frozen,
+its parameters are constants): the stride-1 3x3 convs run forward and backward on the tcgen05 kernels
+(dge_b200.autograd.conv2d), the stride-2 transposed convs of the fused-scale blocks and the point-wise steps are torch
+CUDA ops in this build.
 """
 import numpy as np
 import torch
+import torch.nn.functional as F
 from torch import nn
 from torch.nn import init
 from torch.nn.parameter import Parameter
 
 import model.utils.lreq as ln
+from dge_b200 import autograd as tc
 from dge_b200 import ops
 
 DEFAULT_PLANES = 2
@@ -130,6 +138,35 @@ class DecodeBlock(nn.Module):
                                          out_f32b=last)                                       # :165-167
         return f if last else act
 
+    def _forward_autograd(self, x, s1, s2):
+        """Differentiable w.r.t. x, s1, s2 (parameters are constants): net.py:141-169 on NCHW tensors."""
+        def wgt(conv):
+            return conv.weight.detach() if conv.implicit_lreq else conv.weight.detach() * conv.std
+
+        def style_mod(v, lin, s):                                                          # :32-34
+            lb = None if lin.bias is None else (lin.bias.detach() if lin.implicit_lreq else lin.bias.detach() * lin.lrmul)
+            st = F.linear(s, lin.weight.detach() if lin.implicit_lreq else lin.weight.detach() * lin.std, lb)
+            st = st.view(st.shape[0], 2, v.shape[1], 1, 1)
+            return torch.addcmul(st[:, 1], v, st[:, 0] + 1)
+
+        if self.has_first_conv:
+            if self.fused_scale:                                                           # lreq.py:127-140
+                w = F.pad(wgt(self.conv_1), (1, 1, 1, 1))
+                w = w[:, :, 1:, 1:] + w[:, :, :-1, 1:] + w[:, :, 1:, :-1] + w[:, :, :-1, :-1]
+                x = F.conv_transpose2d(x, w, stride=2, padding=1)
+            else:                                                                          # upscale2d :37-43, conv :145
+                x = tc.conv2d(F.interpolate(x, scale_factor=2, mode='nearest'), wgt(self.conv_1), self.planes)
+            x = F.conv2d(x, self.blur.weight, groups=self.blur.groups, padding=1)          # :48-58
+        n, _, h, w_ = x.shape
+        x = torch.addcmul(x, self.noise_weight_1.detach(), self._noise(n, h, w_, x.device))    # :148 (batch 1 in block 0)
+        x = F.instance_norm(F.leaky_relu(x + self.bias_1.detach(), 0.2), eps=self.instance_norm_1.eps)
+        x = style_mod(x, self.style_1, s1)                                                 # :154-156
+        x = tc.conv2d(x, wgt(self.conv_2), self.planes)                                    # :158
+        n = x.shape[0]
+        x = torch.addcmul(x, self.noise_weight_2.detach(), self._noise(n, h, w_, x.device))    # :160
+        x = F.instance_norm(F.leaky_relu(x + self.bias_2.detach(), 0.2), eps=self.instance_norm_2.eps)
+        return style_mod(x, self.style_2, s2)                                              # :165-167
+
     def forward(self, x, s1, s2):
         """Reference signature: NCHW in -> NCHW out."""
         ln._guard('DecodeBlock', x, s1, s2, self.conv_2.weight)
@@ -206,7 +243,22 @@ class Generator(nn.Module):
         for b in self.decode_block:
             b.noise_mode = mode
 
+    def _decode_autograd(self, styles, lod):
+        """Training path of `decode` (:331-336): recorded for backward w.r.t. `styles`; see the module docstring."""
+        tc.require_fp32_library_convs()
+        styles = styles.float()
+        x = self.const.detach().float()
+        for i in range(lod + 1):
+            x = self.decode_block[i]._forward_autograd(x, styles[:, 2 * i + 0], styles[:, 2 * i + 1])
+        c = self.to_rgb[lod].to_rgb
+        w = c.weight.detach() if c.implicit_lreq else c.weight.detach() * c.std
+        return F.conv2d(x, w, c.scaled_bias())                                             # :244-253
+
     def decode(self, styles, lod, noise=0):
+        if torch.is_grad_enabled() and styles.requires_grad:
+            if not styles.is_cuda:
+                raise ops.DgeError('Generator.decode: dge_b200 runs on a B200 only; there is no CPU fallback')
+            return self._decode_autograd(styles, lod)
         ln._guard('Generator.decode', styles, self.const)
         x = ops.nchw_to_f32b(self.const.detach().float())
         for i in range(lod + 1):

@@ -205,3 +205,31 @@ def test_full_training_iteration_gradients_vs_oracle():
     for k, p in E.named_parameters():
         if esd[k].grad is not None:
             assert rel(p.grad, esd[k].grad) < TOL, k
+
+
+def test_stylegan1_generator_backward_vs_oracle():
+    """E_align_s2.py:158 (mtype 1): `Gs.forward(w2, lod)` with styles that require grad -- the recorded graph's image
+    against the reference fixture and d(loss)/d(styles) against autograd through the oracle (same activation pattern),
+    for a plain-conv lod and a fused-scale (stride-2 transposed conv) lod.  The frozen generator accumulates nothing."""
+    from model.stylegan1.net import Generator
+    from oracle import stylegan1 as osg1
+    fx = torch.load(os.path.join(GOLD, "sg1_l6.pt"))
+    Gs = Generator(**fx["config"])
+    Gs.load_state_dict(fx["state_dict"], strict=True)
+    Gs = Gs.cuda()
+    for lod, img in fx["images"].items():
+        styles = fx["styles"].cuda().requires_grad_(True)
+        masks = []
+        torch.manual_seed(60 + lod)
+        with record_masks(masks):
+            out = Gs.forward(styles, lod)
+        assert out.requires_grad and rel(out, img) < 2e-4, lod
+        target = torch.randn(out.shape, generator=torch.Generator().manual_seed(2))
+        ((out - target.cuda()) ** 2).mean().backward()
+        styles_r = fx["styles"].clone().requires_grad_(True)
+        torch.manual_seed(60 + lod)
+        with replay_masks(masks):
+            ref = osg1.decode(fx["state_dict"], styles_r, lod)
+        ((ref - target) ** 2).mean().backward()
+        assert rel(styles.grad, styles_r.grad) < TOL, lod
+    assert all(p.grad is None for p in Gs.parameters())

@@ -23,8 +23,10 @@ def aten_conv(monkeypatch):
     def conv(x, w, planes=2):
         return F.conv2d(x, w, padding=w.shape[-1] // 2)
 
+    import model.stylegan1.net as S1
     monkeypatch.setattr(EM.tc, "conv2d", conv)
     monkeypatch.setattr(SG.tc, "conv2d", conv)
+    monkeypatch.setattr(S1.tc, "conv2d", conv)
 
 
 def test_encoder_graph_matches_reference_gradients(aten_conv):
@@ -63,6 +65,26 @@ def test_synthesis_graph_matches_oracle_gradient(aten_conv):
     torch.manual_seed(77)
     out_rn = G.synthesis._forward_autograd(fx["wp"].clone().requires_grad_(True), randomize_noise=True)
     assert rel(out_rn["image"], fx["image_randnoise_seed77"]) < 2e-5
+
+
+def test_stylegan1_graph_matches_fixture_and_oracle_gradient(aten_conv):
+    from model.stylegan1.net import Generator
+    from oracle import stylegan1 as osg1
+    fx = torch.load(os.path.join(GOLD, "sg1_l6.pt"))
+    Gs = Generator(**fx["config"])
+    Gs.load_state_dict(fx["state_dict"], strict=True)
+    for lod, img in fx["images"].items():
+        styles = fx["styles"].clone().requires_grad_(True)
+        torch.manual_seed(60 + lod)
+        out = Gs._decode_autograd(styles, lod)
+        assert rel(out, img) < 2e-5, lod
+        target = torch.randn(out.shape, generator=torch.Generator().manual_seed(2))
+        ((out - target) ** 2).mean().backward()
+        styles_r = fx["styles"].clone().requires_grad_(True)
+        torch.manual_seed(60 + lod)
+        ((osg1.decode(fx["state_dict"], styles_r, lod) - target) ** 2).mean().backward()
+        assert rel(styles.grad, styles_r.grad) < 1e-5, lod
+    assert all(p.grad is None for p in Gs.parameters())
 
 
 def test_differentiable_ssim_matches_oracle():
