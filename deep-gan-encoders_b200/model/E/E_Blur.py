@@ -6,13 +6,20 @@ size) `conv_2` is the stride-2 `transform_kernel` conv (4x4 effectiv
 Kernels: the instance-norm apply, the blur and (for the strided blocks) a space-to-depth re-layout are ONE pass
 (`dge_instance_norm_blur`); the strided conv runs on the tensor cores as a 16-tap conv over the 4 input phases
 (`DGE_CONV_DOWN4X4S2`), exact at the borders (the blurred intermediate is zero-padded).
+
+Training: as in `model/E/E.py`, a call that must be recorded for backward builds a differentiable graph whose stride-1
+3x3 / 1x1 convs run forward / data-gradient / weight-gradient on the tcgen05 kernels; the stride-2 `transform_kernel`
+conv of the first four blocks, the blur and the point-wise steps are torch CUDA ops in this build.
 """
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 import model.utils.lreq as ln
+from model.E.E import _mean_std, _wants_grad
 from model.utils.net import FromRGB
 from model.stylegan1.net import Blur
+from dge_b200 import autograd as tc
 from dge_b200 import ops
 
 DEFAULT_PLANES = 2
@@ -92,7 +99,37 @@ class BEBlock(nn.Module):
                 out = ops.blend(y1n, x, 0.111, 0.889, pool=False)
         return out, w1, w2
 
+    def _forward_autograd(self, x):
+        """Differentiable form of the block (E_Blur.py:50-85) on NCHW tensors."""
+        tc.require_fp32_library_convs()
+        n, c, h, w = x.shape
+        dev = x.device
+        w1 = F.linear(_mean_std(x), self.inver_mod1.weight, self.inver_mod1.bias)
+        res = x
+        y = tc.conv2d(F.instance_norm(x, eps=self.instance_norm_1.eps), self.conv_1.weight, self.planes)
+        y = F.leaky_relu(torch.addcmul(y, self.noise_weight_1, self._noise(n, h, w, dev)) + self.bias_1, 0.2)
+        w2 = F.linear(_mean_std(y), self.inver_mod2.weight, self.inver_mod2.bias)
+        y = F.instance_norm(y, eps=self.instance_norm_2.eps)
+        if self.has_last_conv:
+            y = F.conv2d(y, self.blur.weight, groups=self.blur.groups, padding=1)                  # :71
+            if self.fused_scale:                                                                   # :72, lreq.py:144-156
+                k = F.pad(self.conv_2.weight, (1, 1, 1, 1))
+                k = (k[:, :, 1:, 1:] + k[:, :, :-1, 1:] + k[:, :, 1:, :-1] + k[:, :, :-1, :-1]) * 0.25
+                y = F.conv2d(y, k, stride=2, padding=1)
+            else:
+                y = tc.conv2d(y, self.conv_2.weight, self.planes)
+            nh, nw = y.shape[2], y.shape[3]
+            y = F.leaky_relu(torch.addcmul(y, self.noise_weight_2, self._noise(n, nh, nw, dev)) + self.bias_2, 0.2)
+            if not self.fused_scale:
+                y = F.avg_pool2d(y, 2, 2)
+            res = F.avg_pool2d(res, 2, 2)
+        if self.inputs != self.outputs:
+            res = tc.conv2d(res, self.conv_3.weight, self.planes) + self.conv_3.bias.view(1, -1, 1, 1)
+        return 0.111 * y + 0.889 * res, w1, w2
+
     def forward(self, x):
+        if _wants_grad(self, x):
+            return self._forward_autograd(x.float())
         ln._guard('E_Blur.BEBlock', x, self.conv_1.weight)
         out, w1, w2 = self.run(ops.nchw_to_f32b(x.float()))
         return out.to_nchw(), w1, w2
@@ -125,7 +162,22 @@ class BE(nn.Module):
         for b in self.decode_block:
             b.noise_mode = mode
 
+    def _forward_autograd(self, x, block_num):
+        tc.require_fp32_library_convs()
+        c = self.FromRGB.from_rgb
+        if not c.implicit_lreq:
+            raise NotImplementedError('training path: explicit lreq scaling is not used by the reference (lreq.py:23-24)')
+        f = F.leaky_relu(F.conv2d(x, c.weight, c.bias), 0.2)
+        w = torch.tensor(0)
+        for i in range(9 - block_num, self.layer_count):
+            f, w1, w2 = self.decode_block[i]._forward_autograd(f)
+            w_ = torch.cat((w2.view(f.shape[0], 1, 512), w1.view(f.shape[0], 1, 512)), dim=1)
+            w = w_ if i == (9 - block_num) else torch.cat((w_, w), dim=1)
+        return f, w
+
     def forward(self, x, block_num=9):
+        if _wants_grad(self, x):
+            return self._forward_autograd(x.float(), block_num)
         ln._guard('E_Blur.BE', x, self.FromRGB.from_rgb.weight)
         f = self.FromRGB.run(x)
         w = torch.tensor(0)

@@ -233,3 +233,28 @@ def test_stylegan1_generator_backward_vs_oracle():
         ((ref - target) ** 2).mean().backward()
         assert rel(styles.grad, styles_r.grad) < TOL, lod
     assert all(p.grad is None for p in Gs.parameters())
+
+
+def test_e_blur_backward_vs_oracle():
+    """Case-2 encoder (`model/E/E_Blur.py`, the encoder of embedding_img.py): recorded forward against the reference
+    fixture, every parameter gradient against autograd through the oracle at the same activation pattern."""
+    from model.E.E_Blur import BE
+    from oracle import encoder as oenc
+    fx = torch.load(os.path.join(GOLD, "e_blur_s16_l6.pt"))
+    E = BE(**fx["config"])
+    E.load_state_dict(fx["state_dict"], strict=True)
+    E = E.cuda()
+    masks = []
+    torch.manual_seed(fx["noise_seed"])
+    with record_masks(masks):
+        const, w = E(fx["img"].cuda())
+    assert const.requires_grad and rel(const, fx["const"]) < 2e-4 and rel(w, fx["w"]) < 2e-4
+    (const.sum() + (w ** 2).mean()).backward()
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in fx["state_dict"].items()}
+    torch.manual_seed(fx["noise_seed"])
+    with replay_masks(masks):
+        const_r, w_r = oenc.be_blur_forward(sd, fx["img"], fx["config"]["layer_count"])
+    (const_r.sum() + (w_r ** 2).mean()).backward()
+    for k, p in E.named_parameters():
+        if sd[k].grad is not None:
+            assert rel(p.grad, sd[k].grad) < TOL, k

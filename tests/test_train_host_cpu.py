@@ -24,6 +24,8 @@ def aten_conv(monkeypatch):
         return F.conv2d(x, w, padding=w.shape[-1] // 2)
 
     import model.stylegan1.net as S1
+    import model.E.E_Blur as EB
+    monkeypatch.setattr(EB.tc, "conv2d", conv)
     monkeypatch.setattr(EM.tc, "conv2d", conv)
     monkeypatch.setattr(SG.tc, "conv2d", conv)
     monkeypatch.setattr(S1.tc, "conv2d", conv)
@@ -85,6 +87,30 @@ def test_stylegan1_graph_matches_fixture_and_oracle_gradient(aten_conv):
         ((osg1.decode(fx["state_dict"], styles_r, lod) - target) ** 2).mean().backward()
         assert rel(styles.grad, styles_r.grad) < 1e-5, lod
     assert all(p.grad is None for p in Gs.parameters())
+
+
+def test_e_blur_graph_matches_fixture_and_oracle_gradients(aten_conv):
+    """Case-2 encoder (strided transform_kernel convs + blur).  Two fp32 evaluations of this chain differ by ~6e-5 from
+    the fp64 value on the 4x4 blocks, hence 3e-4 here."""
+    from model.E.E_Blur import BE
+    from oracle import encoder as oenc
+    fx = torch.load(os.path.join(GOLD, "e_blur_s16_l6.pt"))
+    E = BE(**fx["config"])
+    E.load_state_dict(fx["state_dict"], strict=True)
+    torch.manual_seed(fx["noise_seed"])
+    const, w = E._forward_autograd(fx["img"], 9)
+    assert rel(const, fx["const"]) < 2e-5 and rel(w, fx["w"]) < 2e-5
+    (const.sum() + (w ** 2).mean()).backward()
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in fx["state_dict"].items()}
+    torch.manual_seed(fx["noise_seed"])
+    const_r, w_r = oenc.be_blur_forward(sd, fx["img"], fx["config"]["layer_count"])
+    (const_r.sum() + (w_r ** 2).mean()).backward()
+    checked = 0
+    for k, p in E.named_parameters():
+        if sd[k].grad is not None:
+            assert rel(p.grad, sd[k].grad) < 3e-4, k
+            checked += 1
+    assert checked > 50
 
 
 def test_differentiable_ssim_matches_oracle():
