@@ -5,13 +5,19 @@
 Block (reference order kept): CBN1 (no activation; running stats are the constant 0/1 buffers, eps 1e-12)
 -> conv_1 -> noise, bias, lrelu -> CBN2 -> conv_2 -> noise, bias, lrelu [-> lrelu AGAIN when channels change, :163]
 -> + residual (conv_3(CBN3(x)) when channels change) -> 2x2 avg-pool.  `truncation` is hard-wired to 0.4 (:222).
+
+Training: as in `model/E/E.py` -- a call that must be recorded for backward builds a differentiable graph whose 3x3 /
+1x1 convs run forward / data-gradient / weight-gradient on the tcgen05 kernels; the conditional-BN affines (whose
+spectral-norm `scale` / `offset` layers are trainable here) and the point-wise steps are torch CUDA ops in this build.
 """
 import torch
 import torch.nn as nn
 import torch.nn.functional as F  # noqa: F401
 
 import model.utils.lreq as ln
+from model.E.E import _wants_grad
 from model.biggan_generator import BigGANBatchNorm, snlinear  # noqa: F401  (identical classes upstream)
+from dge_b200 import autograd as tc
 from dge_b200 import ops
 
 DEFAULT_PLANES = 2
@@ -86,7 +92,29 @@ class BEBlock(nn.Module):
                       blend_src=res, blend_a=1.0, blend_b=1.0, out_f32b=True)['f32b']                      # :151-164
         return ops.blend(y2, y2, 1.0, 0.0, pool=3)                                                         # :165-166
 
+    def _forward_autograd(self, x, cond_vector, truncation=0.4):
+        """Differentiable form of the block (E_BIG.py:129-169) on NCHW tensors."""
+        n, c, h, w = x.shape
+        dev = x.device
+        res = x
+        y = self.batch_norm_1._forward_autograd(x, truncation, cond_vector, frozen=False)                 # :134
+        y = tc.conv2d(y, self.conv_1.weight, self.planes)                                                 # :135
+        y = F.leaky_relu(torch.addcmul(y, self.noise_weight_1, self._noise(n, h, w, dev)) + self.bias_1, 0.2)
+        if not self.has_second_conv:
+            return y
+        y = self.batch_norm_2._forward_autograd(y, truncation, cond_vector, frozen=False)                 # :150
+        y = tc.conv2d(y, self.conv_2.weight, self.planes)                                                 # :151
+        y = F.leaky_relu(torch.addcmul(y, self.noise_weight_2, self._noise(n, h, w, dev)) + self.bias_2, 0.2)
+        if self.inputs != self.outputs:
+            res = self.batch_norm_3._forward_autograd(res, truncation, cond_vector, frozen=False)         # :160
+            res = tc.conv2d(res, self.conv_3.weight, self.planes) + self.conv_3.bias.view(1, -1, 1, 1)    # :161
+            y = F.leaky_relu(y, 0.2)                                                                      # :163
+        return F.avg_pool2d(y + res, 2, 2)                                                                # :164-166
+
     def forward(self, x, cond_vector, truncation=0.4):
+        if _wants_grad(self, x):
+            tc.require_fp32_library_convs()
+            return self._forward_autograd(x.float(), cond_vector.float(), truncation), 0, 0
         ln._guard('E_BIG.BEBlock', x, cond_vector, self.conv_1.weight)
         return self.run(ops.nchw_to_f32b(x.float()), cond_vector.float().contiguous(), truncation).to_nchw(), 0, 0
 
@@ -126,7 +154,22 @@ class BE(nn.Module):
             f = self.decode_block[i].run(f, cv, truncation=0.4)
         return f.to_nchw()
 
+    def _features_autograd(self, x, cond_vector, block_num=9):
+        tc.require_fp32_library_convs()
+        cv = cond_vector.float()
+        c = self.FromRGB.from_rgb
+        f = F.leaky_relu(F.conv2d(x.float(), c.weight, c.bias), 0.2)                                      # :84-92
+        for i in range(9 - block_num, self.layer_count):
+            f = self.decode_block[i]._forward_autograd(f, cv, truncation=0.4)
+        return f
+
     def forward(self, x, cond_vector, block_num=9):
+        if _wants_grad(self, x):
+            x = self._features_autograd(x, cond_vector, block_num)
+            if self.biggan:
+                c_v = F.linear(x.reshape(x.shape[0], -1), self.new_final_1.weight, self.new_final_1.bias)
+                z = F.linear(c_v, self.new_final_2.weight, self.new_final_2.bias)
+            return c_v, z
         x = self.features(x, cond_vector, block_num)
         if self.biggan:
             c_v = self.new_final_1(x.view(x.shape[0], -1))

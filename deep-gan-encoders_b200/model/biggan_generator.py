@@ -12,12 +12,20 @@ dge_b200 kernel:
   self-attention: q.k^T and attn.v are 1x1 tcgen05 convs whose "weights" are the per-sample key / value maps
   (the ACT layout of a [C, HW] map IS the packed-weight layout), softmax over keys = `dge_channel_softmax_to_act`.
 `truncation` follows the reference's Python arithmetic (`math.modf(truncation / step)`), tensors included.
+
+Training (E_align_s2.py:162, mtype 4: `generator(w2, conditions, truncation)` with w2 from the encoder under autograd):
+when `z` requires grad, `BigGAN.forward` records a differentiable graph w.r.t. `z` (`_forward_autograd`); the generator
+is frozen (its effective spectral-norm weights enter as constants), the 1x1 / 3x3 convs whose channel counts are
+multiples of 16 run forward and backward on the tcgen05 kernels (dge_b200.autograd.conv2d), the conditional-BN
+affines, the attention products and the remaining point-wise steps are torch CUDA ops in this build.
 """
 import math
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
+from dge_b200 import autograd as tc
 from dge_b200 import ops
 from model.utils.biggan_config import BigGANConfig  # noqa: F401
 
@@ -42,6 +50,16 @@ def _guard(name, *tensors):
             raise ops.DgeError(f'{name}: dge_b200 runs on a B200 only (got a {t.device} tensor); no CPU fallback')
     if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
         raise NotImplementedError(f'{name}: dge_b200 kernels are forward-only in this build; use torch.no_grad()')
+
+
+def _conv_autograd(x, w, b, planes):
+    """Differentiable stride-1 'same' conv of the training path: tensor cores when the channel counts allow it."""
+    k = w.shape[-1]
+    if w.shape[0] % 16 == 0 and w.shape[1] % 16 == 0:
+        y = tc.conv2d(x, w, planes)
+    else:
+        y = F.conv2d(x, w, padding=k // 2)
+    return y if b is None else y + b.view(1, -1, 1, 1)
 
 
 def sn_weight(module):
@@ -124,6 +142,18 @@ class SelfAttn(nn.Module):
         return ops.conv(ga, p['o'], ch, ops.CONV_1X1, gain=p['gamma'], blend_src=x, blend_a=1.0, blend_b=1.0,
                         out_f32b=True)['f32b']                                                        # :95-97
 
+    def _forward_autograd(self, x):
+        """:75-97 on NCHW tensors, recorded for backward (frozen weights)."""
+        n, ch, h, w = x.shape
+        wt = [sn_weight(l).detach() for l in (self.snconv1x1_theta, self.snconv1x1_phi, self.snconv1x1_g,
+                                              self.snconv1x1_o_conv)]
+        theta = _conv_autograd(x, wt[0], None, self.planes).view(n, ch // 8, h * w)
+        phi = F.max_pool2d(_conv_autograd(x, wt[1], None, self.planes), 2, 2).view(n, ch // 8, h * w // 4)
+        attn = torch.softmax(torch.bmm(theta.transpose(1, 2), phi), dim=-1)
+        g = F.max_pool2d(_conv_autograd(x, wt[2], None, self.planes), 2, 2).view(n, ch // 2, h * w // 4)
+        attn_g = torch.bmm(g, attn.transpose(1, 2)).view(n, ch // 2, h, w)
+        return x + self.gamma.detach() * _conv_autograd(attn_g, wt[3], None, self.planes)
+
     def forward(self, x):
         _guard('SelfAttn', x)
         return self.run(ops.nchw_to_f32b(x.float())).to_nchw()
@@ -171,6 +201,17 @@ class BigGANBatchNorm(nn.Module):
             o = ops.dense(condition_vector.float(), wo, None)
             return ops.cbn_coeffs(mean, var, self.eps, n, scale=s, offset=o)
         return ops.cbn_coeffs(mean, var, self.eps, n, weight=self.weight, bias=self.bias)
+
+    def _forward_autograd(self, x, truncation, condition_vector=None, frozen=True):
+        """:138-150 recorded for backward.  `frozen`: the layer's own parameters are constants (generator) or
+        trainable (the BigGAN encoder re-uses this class, E_BIG.py:33-82)."""
+        mean, var = self.stats(truncation)
+        keep = (lambda t: t.detach()) if frozen else (lambda t: t)
+        if self.conditional:
+            weight = 1 + F.linear(condition_vector, keep(sn_weight(self.scale)))[:, :, None, None]
+            bias = F.linear(condition_vector, keep(sn_weight(self.offset)))[:, :, None, None]
+            return (x - mean[None, :, None, None]) / torch.sqrt(var[None, :, None, None] + self.eps) * weight + bias
+        return F.batch_norm(x, mean, var, keep(self.weight), keep(self.bias), False, 0.0, self.eps)
 
     def forward(self, x, truncation, condition_vector=None):
         _guard('BigGANBatchNorm', x, condition_vector)
@@ -228,6 +269,25 @@ class GenBlock(nn.Module):
         return ops.conv(t, p['w'][3], self.out_size, ops.CONV_1X1, bias=p['b'][3], preact_add=x,
                         preact_up=2 if self.up_sample else 1, out_f32b=True)['f32b']
 
+    def _forward_autograd(self, x, cond_vector, truncation):
+        """:175-203 recorded for backward (frozen weights)."""
+        def conv(layer, v):
+            return _conv_autograd(v, sn_weight(layer).detach(), layer.bias.detach(), self.planes)
+
+        x0 = x
+        x = conv(self.conv_0, F.relu(self.bn_0._forward_autograd(x, truncation, cond_vector)))
+        x = F.relu(self.bn_1._forward_autograd(x, truncation, cond_vector))
+        if self.up_sample:
+            x = F.interpolate(x, scale_factor=2, mode='nearest')
+        x = conv(self.conv_1, x)
+        x = conv(self.conv_2, F.relu(self.bn_2._forward_autograd(x, truncation, cond_vector)))
+        x = conv(self.conv_3, F.relu(self.bn_3._forward_autograd(x, truncation, cond_vector)))
+        if self.drop_channels:
+            x0 = x0[:, :x0.shape[1] // 2]                                                 # :195-197
+        if self.up_sample:
+            x0 = F.interpolate(x0, scale_factor=2, mode='nearest')
+        return x + x0
+
     def forward(self, x, cond_vector, truncation):
         _guard('GenBlock', x, cond_vector)
         return self.run(ops.nchw_to_f32b(x.float()), cond_vector, truncation).to_nchw()
@@ -254,7 +314,24 @@ class Generator(nn.Module):
         self.planes = DEFAULT_PLANES
         self._prep = _Prep()
 
+    def _forward_autograd(self, cond_vector, truncation):
+        """:232-256 recorded for backward w.r.t. the condition vector (frozen weights)."""
+        tc.require_fp32_library_convs()
+        ch = self.config.channel_width
+        x = F.linear(cond_vector, sn_weight(self.gen_z).detach(), self.gen_z.bias.detach())
+        x = x.view(-1, 4, 4, 16 * ch).permute(0, 3, 1, 2).contiguous()
+        for layer in self.layers:
+            x = layer._forward_autograd(x, cond_vector, truncation) if isinstance(layer, GenBlock) \
+                else layer._forward_autograd(x)
+        x = F.relu(self.bn._forward_autograd(x, truncation))
+        x = _conv_autograd(x, sn_weight(self.conv_to_rgb).detach(), self.conv_to_rgb.bias.detach(), self.planes)
+        return torch.tanh(x[:, :3])
+
     def forward(self, cond_vector, truncation):
+        if torch.is_grad_enabled() and cond_vector.requires_grad:
+            if not cond_vector.is_cuda:
+                raise ops.DgeError('BigGAN.Generator: dge_b200 runs on a B200 only; there is no CPU fallback')
+            return self._forward_autograd(cond_vector.float(), truncation)
         _guard('BigGAN.Generator', cond_vector)
         ch = self.config.channel_width
         n = cond_vector.shape[0]
@@ -292,6 +369,12 @@ class BigGAN(nn.Module):
 
     def forward(self, z, class_label, truncation):
         assert 0 < truncation <= 1
+        if torch.is_grad_enabled() and z.requires_grad:
+            if not z.is_cuda:
+                raise ops.DgeError('BigGAN: dge_b200 runs on a B200 only; there is no CPU fallback')
+            embed = F.linear(class_label.float(), self.embeddings.weight.detach())          # :299
+            cond_vector = torch.cat((z.float(), embed), dim=1)                              # :301
+            return self.generator._forward_autograd(cond_vector, truncation), cond_vector
         _guard('BigGAN', z, class_label)
         embed = ops.dense(class_label.float(), self.embeddings.weight, None)               # :299
         cond_vector = torch.cat((z.float(), embed), dim=1)                                  # :301

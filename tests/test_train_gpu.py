@@ -31,25 +31,29 @@ def rel(a, b):
 
 @contextlib.contextmanager
 def record_masks(store):
-    """Record the sign pattern of every leaky_relu input, in call order (product path and oracle call it in the same
-    order: from_rgb, then per block / per layer)."""
-    orig = F.leaky_relu
+    """Record the sign pattern of every leaky_relu / relu input, in call order (product path and oracle call them in
+    the same order: from_rgb, then per block / per layer)."""
+    orig_l, orig_r = F.leaky_relu, F.relu
 
     def lrelu(x, negative_slope=0.01, inplace=False):
         store.append((x.detach() > 0).cpu())
-        return orig(x, negative_slope)
+        return orig_l(x, negative_slope)
 
-    F.leaky_relu = lrelu
+    def relu(x, inplace=False):
+        store.append((x.detach() > 0).cpu())
+        return orig_r(x)
+
+    F.leaky_relu, F.relu = lrelu, relu
     try:
         yield
     finally:
-        F.leaky_relu = orig
+        F.leaky_relu, F.relu = orig_l, orig_r
 
 
 @contextlib.contextmanager
 def replay_masks(store):
-    """leaky_relu with the recorded pattern instead of the sign of its own input."""
-    orig = F.leaky_relu
+    """leaky_relu / relu with the recorded pattern instead of the sign of their own input."""
+    orig_l, orig_r = F.leaky_relu, F.relu
     it = iter(store)
 
     def lrelu(x, negative_slope=0.01, inplace=False):
@@ -57,11 +61,16 @@ def replay_masks(store):
         assert m.shape == x.shape
         return torch.where(m, x, x * negative_slope)
 
-    F.leaky_relu = lrelu
+    def relu(x, inplace=False):
+        m = next(it)
+        assert m.shape == x.shape
+        return torch.where(m, x, torch.zeros_like(x))
+
+    F.leaky_relu, F.relu = lrelu, relu
     try:
         yield
     finally:
-        F.leaky_relu = orig
+        F.leaky_relu, F.relu = orig_l, orig_r
 
 
 def _encoder():
@@ -257,4 +266,57 @@ def test_e_blur_backward_vs_oracle():
     (const_r.sum() + (w_r ** 2).mean()).backward()
     for k, p in E.named_parameters():
         if sd[k].grad is not None:
+            assert rel(p.grad, sd[k].grad) < TOL, k
+
+
+def test_biggan_generator_backward_vs_oracle():
+    """E_align_s2.py:162 (mtype 4): `generator(w2, conditions, truncation)` with a latent that requires grad: image
+    against the reference fixture, d(loss)/dz against the oracle at the same ReLU pattern."""
+    from model.biggan_generator import BigGAN
+    from model.utils.biggan_config import BigGANConfig
+    from oracle import biggan as obg
+    fx = torch.load(os.path.join(GOLD, "biggan_small.pt"))
+    G = BigGAN(BigGANConfig.from_dict(fx["config"]))
+    G.load_state_dict(fx["state_dict"], strict=True)
+    G = G.cuda().eval()
+    for trunc, img in fx["images"].items():
+        z = fx["z"].cuda().requires_grad_(True)
+        masks = []
+        with record_masks(masks):
+            out, cond = G(z, fx["label"].cuda(), trunc)
+        assert out.requires_grad and rel(out, img) < 2e-4 and rel(cond, fx["cond"]) < 2e-4
+        target = torch.randn(out.shape, generator=torch.Generator().manual_seed(4))
+        ((out - target.cuda()) ** 2).mean().backward()
+        z_r = fx["z"].clone().requires_grad_(True)
+        with replay_masks(masks):
+            ref, _ = obg.biggan(fx["state_dict"], fx["config"], z_r, fx["label"], trunc)
+        ((ref - target) ** 2).mean().backward()
+        assert rel(z.grad, z_r.grad) < TOL, trunc
+    assert all(p.grad is None for p in G.parameters())
+
+
+def test_e_big_backward_vs_oracle():
+    """BigGAN encoder (`model/E/E_BIG.py`): feature map against the reference fixture, every parameter gradient (incl.
+    the spectral-norm `weight_orig` of the conditional-BN layers) against the oracle at the same activation pattern."""
+    from model.E.E_BIG import BE
+    from oracle import biggan as obg
+    fx = torch.load(os.path.join(GOLD, "e_big_s16_l4.pt"))
+    E = BE(**fx["config"])
+    E.load_state_dict(fx["state_dict"], strict=True)
+    E = E.cuda().eval()
+    masks = []
+    torch.manual_seed(13)
+    with record_masks(masks):
+        f = E._features_autograd(fx["img"].cuda(), fx["cond"].cuda())
+    assert rel(f, fx["features_seed13"]) < 2e-4
+    (f ** 2).mean().backward()
+    frozen = ("_u", "_v", "running_means", "running_vars")
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and not k.endswith(frozen))
+          for k, v in fx["state_dict"].items()}
+    torch.manual_seed(13)
+    with replay_masks(masks):
+        f_r = obg.e_big_features(sd, fx["img"], fx["cond"], fx["config"]["layer_count"])
+    (f_r ** 2).mean().backward()
+    for k, p in E.named_parameters():
+        if p.grad is not None:
             assert rel(p.grad, sd[k].grad) < TOL, k

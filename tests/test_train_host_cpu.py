@@ -25,6 +25,10 @@ def aten_conv(monkeypatch):
 
     import model.stylegan1.net as S1
     import model.E.E_Blur as EB
+    import model.E.E_BIG as EG
+    import model.biggan_generator as BG
+    monkeypatch.setattr(EG.tc, "conv2d", conv)
+    monkeypatch.setattr(BG.tc, "conv2d", conv)
     monkeypatch.setattr(EB.tc, "conv2d", conv)
     monkeypatch.setattr(EM.tc, "conv2d", conv)
     monkeypatch.setattr(SG.tc, "conv2d", conv)
@@ -111,6 +115,53 @@ def test_e_blur_graph_matches_fixture_and_oracle_gradients(aten_conv):
             assert rel(p.grad, sd[k].grad) < 3e-4, k
             checked += 1
     assert checked > 50
+
+
+def test_biggan_graph_matches_fixture_and_oracle_gradient(aten_conv):
+    from model.biggan_generator import BigGAN
+    from model.utils.biggan_config import BigGANConfig
+    from oracle import biggan as obg
+    fx = torch.load(os.path.join(GOLD, "biggan_small.pt"))
+    G = BigGAN(BigGANConfig.from_dict(fx["config"]))
+    G.load_state_dict(fx["state_dict"], strict=True)
+    G.eval()
+    for trunc, img in fx["images"].items():
+        z = fx["z"].clone().requires_grad_(True)
+        cond = torch.cat((z, F.linear(fx["label"], G.embeddings.weight.detach())), dim=1)
+        out = G.generator._forward_autograd(cond, trunc)
+        assert rel(out, img) < 2e-5, trunc
+        target = torch.randn(out.shape, generator=torch.Generator().manual_seed(4))
+        ((out - target) ** 2).mean().backward()
+        z_r = fx["z"].clone().requires_grad_(True)
+        ref, _ = obg.biggan(fx["state_dict"], fx["config"], z_r, fx["label"], trunc)
+        ((ref - target) ** 2).mean().backward()
+        assert rel(z.grad, z_r.grad) < 1e-5, trunc
+    assert all(p.grad is None for p in G.parameters())
+
+
+def test_e_big_graph_matches_fixture_and_oracle_gradients(aten_conv):
+    """BigGAN encoder: the conditional-BN scale / offset layers are spectral-norm wrapped AND trainable here."""
+    from model.E.E_BIG import BE
+    from oracle import biggan as obg
+    fx = torch.load(os.path.join(GOLD, "e_big_s16_l4.pt"))
+    E = BE(**fx["config"])
+    E.load_state_dict(fx["state_dict"], strict=True)
+    E.eval()
+    torch.manual_seed(13)
+    f = E._features_autograd(fx["img"], fx["cond"])
+    assert rel(f, fx["features_seed13"]) < 2e-5
+    (f ** 2).mean().backward()
+    frozen = ("_u", "_v", "running_means", "running_vars")
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and not k.endswith(frozen))
+          for k, v in fx["state_dict"].items()}
+    torch.manual_seed(13)
+    (obg.e_big_features(sd, fx["img"], fx["cond"], fx["config"]["layer_count"]) ** 2).mean().backward()
+    checked = 0
+    for k, p in E.named_parameters():
+        if p.grad is not None:
+            assert rel(p.grad, sd[k].grad) < 1e-4, k
+            checked += 1
+    assert checked >= 40
 
 
 def test_differentiable_ssim_matches_oracle():
