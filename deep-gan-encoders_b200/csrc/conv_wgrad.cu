@@ -17,6 +17,7 @@
 //   TMEM   : taps_x accumulators of [128 x nblk] fp32 side by side (<= 384 columns), live for the whole CTA.
 //   planes == 2 => split precision as in the forward kernel: dy = dh+dl, x = xh+xl, acc += dh*xh + dh*xl + dl*xh.
 #include <stdlib.h>
+#include <string.h>
 
 #include "dge_common.cuh"
 #include "tma_ptx.cuh"
