@@ -141,3 +141,23 @@ def test_ctypes_signatures_have_the_declared_argument_counts():
         n = 0 if params in ("", "void") else params.count(",") + 1
         restype, argtypes = _lib.SIGNATURES[name]
         assert len(argtypes) == n, f"{name}: header has {n} parameters, ctypes table {len(argtypes)}"
+
+
+def test_wgrad_entry_point_validates_arguments_before_touching_the_device():
+    """Error behaviour of the C ABI (no GPU needed): bad arguments come back as a negative code + message."""
+    import ctypes
+    from dge_b200 import _lib
+    lib = _lib.load()
+    buf = ctypes.create_string_buffer(64)
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    cases = [
+        ((None, p, p, 1, 16, 16, 8, 8, 3, 2, 0, None), "null pointer"),
+        ((p, p, p, 1, 16, 16, 8, 8, 2, 2, 0, None), "ksize"),
+        ((p, p, p, 1, 16, 16, 8, 8, 3, 3, 0, None), "planes"),
+        ((p, p, p, 0, 16, 16, 8, 8, 3, 2, 0, None), "empty input"),
+        ((p, p, p, 1, 12, 16, 8, 8, 3, 2, 0, None), "multiples of 8"),
+    ]
+    for args, needle in cases:
+        rc = lib.dge_conv_wgrad(*args)
+        assert rc < 0
+        assert needle in lib.dge_last_error().decode(), (needle, lib.dge_last_error())
