@@ -31,9 +31,9 @@ def rel(a, b):
 
 @contextlib.contextmanager
 def record_masks(store):
-    """Record the sign pattern of every leaky_relu / relu input, in call order (product path and oracle call them in
-    the same order: from_rgb, then per block / per layer)."""
-    orig_l, orig_r = F.leaky_relu, F.relu
+    """Record, in call order, the sign pattern of every leaky_relu / relu input and the arg-max of every max-pool
+    window (product path and oracle call them in the same order: from_rgb, then per block / per layer)."""
+    orig_l, orig_r, orig_p = F.leaky_relu, F.relu, F.max_pool2d
 
     def lrelu(x, negative_slope=0.01, inplace=False):
         store.append((x.detach() > 0).cpu())
@@ -43,17 +43,22 @@ def record_masks(store):
         store.append((x.detach() > 0).cpu())
         return orig_r(x)
 
-    F.leaky_relu, F.relu = lrelu, relu
+    def max_pool2d(x, kernel_size, stride=None, padding=0, dilation=1, ceil_mode=False, return_indices=False):
+        out, idx = orig_p(x, kernel_size, stride, padding, dilation, ceil_mode, True)
+        store.append(idx.cpu())
+        return out
+
+    F.leaky_relu, F.relu, F.max_pool2d = lrelu, relu, max_pool2d
     try:
         yield
     finally:
-        F.leaky_relu, F.relu = orig_l, orig_r
+        F.leaky_relu, F.relu, F.max_pool2d = orig_l, orig_r, orig_p
 
 
 @contextlib.contextmanager
 def replay_masks(store):
-    """leaky_relu / relu with the recorded pattern instead of the sign of their own input."""
-    orig_l, orig_r = F.leaky_relu, F.relu
+    """leaky_relu / relu / max_pool2d with the recorded pattern instead of the one their own input would give."""
+    orig_l, orig_r, orig_p = F.leaky_relu, F.relu, F.max_pool2d
     it = iter(store)
 
     def lrelu(x, negative_slope=0.01, inplace=False):
@@ -66,11 +71,15 @@ def replay_masks(store):
         assert m.shape == x.shape
         return torch.where(m, x, torch.zeros_like(x))
 
-    F.leaky_relu, F.relu = lrelu, relu
+    def max_pool2d(x, kernel_size, stride=None, padding=0, dilation=1, ceil_mode=False, return_indices=False):
+        idx = next(it)
+        return x.flatten(2).gather(2, idx.flatten(2)).view(idx.shape)
+
+    F.leaky_relu, F.relu, F.max_pool2d = lrelu, relu, max_pool2d
     try:
         yield
     finally:
-        F.leaky_relu, F.relu = orig_l, orig_r
+        F.leaky_relu, F.relu, F.max_pool2d = orig_l, orig_r, orig_p
 
 
 def _encoder():
@@ -320,3 +329,35 @@ def test_e_big_backward_vs_oracle():
     for k, p in E.named_parameters():
         if p.grad is not None:
             assert rel(p.grad, sd[k].grad) < TOL, k
+
+
+def test_lpips_vgg_distance_and_gradient_vs_oracle():
+    """`lpips.LPIPS(net='vgg')` stand-in (third-party package absent => structure parity with random
+    weights): the VGG16 convs run on the tcgen05 kernels forward and data-gradient; distance and image gradient against
+    the oracle restatement at the same ReLU pattern."""
+    import lpips
+    from oracle import lpips as olp
+    torch.manual_seed(0)
+    m = lpips.LPIPS(net="vgg", verbose=False)
+    with torch.no_grad():
+        for k in range(5):
+            getattr(m, f"lin{k}").model[1].weight.abs_()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m = m.cuda()
+    g = torch.Generator().manual_seed(1)
+    a = torch.rand(2, 3, 64, 64, generator=g) * 2 - 1
+    b = torch.rand(2, 3, 64, 64, generator=g) * 2 - 1
+    a_dev = a.cuda().requires_grad_(True)
+    masks = []
+    with record_masks(masks):
+        d = m(a_dev, b.cuda())
+    assert d.shape == (2, 1, 1, 1)
+    d.mean().backward()
+    a_r = a.clone().requires_grad_(True)
+    with replay_masks(masks):
+        d_r = olp.lpips_vgg(sd, a_r, b)
+    d_r.mean().backward()
+    assert rel(d, d_r) < TOL
+    assert rel(a_dev.grad, a_r.grad) < TOL
+    with torch.no_grad():
+        assert float(m(b.cuda(), b.cuda()).abs().max()) == 0.0

@@ -26,6 +26,8 @@ def aten_conv(monkeypatch):
     import model.stylegan1.net as S1
     import model.E.E_Blur as EB
     import model.E.E_BIG as EG
+    import lpips as LP
+    monkeypatch.setattr(LP.tc, "conv2d", conv)
     import model.biggan_generator as BG
     monkeypatch.setattr(EG.tc, "conv2d", conv)
     monkeypatch.setattr(BG.tc, "conv2d", conv)
@@ -162,6 +164,43 @@ def test_e_big_graph_matches_fixture_and_oracle_gradients(aten_conv):
             assert rel(p.grad, sd[k].grad) < 1e-4, k
             checked += 1
     assert checked >= 40
+
+
+def test_lpips_structure_matches_oracle_and_torchvision(aten_conv):
+    """LPIPS-VGG16 stand-in (third-party package absent, parity unpinned): distance and image gradient against the
+    oracle restatement of the published algorithm, feature stack against torchvision's VGG16 with the same weights,
+    state_dict keys of the package."""
+    import lpips
+    from oracle import lpips as olp
+    from torchvision.models import vgg16
+    torch.manual_seed(0)
+    m = lpips.LPIPS(net="vgg", verbose=False)
+    with torch.no_grad():
+        for k in range(5):
+            getattr(m, f"lin{k}").model[1].weight.abs_()
+    sd = m.state_dict()
+    assert {"scaling_layer.shift", "net.slice1.0.weight", "net.slice5.28.bias", "lin4.model.1.weight",
+            "lins.0.model.1.weight"} <= set(sd)
+    assert all(not p.requires_grad for p in m.net.parameters())
+    g = torch.Generator().manual_seed(1)
+    a = (torch.rand(2, 3, 64, 64, generator=g) * 2 - 1).requires_grad_(True)
+    b = torch.rand(2, 3, 64, 64, generator=g) * 2 - 1
+    d = m._distance(a, b)
+    assert d.shape == (2, 1, 1, 1)
+    (ga,) = torch.autograd.grad(d.mean(), a)
+    a_r = a.detach().clone().requires_grad_(True)
+    d_r = olp.lpips_vgg(sd, a_r, b)
+    (ga_r,) = torch.autograd.grad(d_r.mean(), a_r)
+    assert rel(d, d_r) < 1e-5 and rel(ga, ga_r) < 1e-4
+    assert float(m._distance(b, b).abs().max()) == 0.0
+    v = vgg16(weights=None).features
+    v.load_state_dict({f"{i}.{n}": sd[f"net.slice{k + 1}.{i}.{n}"] for k, idxs in enumerate(olp.TAPS) for i in idxs
+                       for n in ("weight", "bias")})
+    x = torch.rand(1, 3, 32, 32, generator=g)
+    with torch.no_grad():
+        assert rel(m.net(x)[4], v[:30](x)) < 1e-5
+    with pytest.raises(Exception):
+        m(a, b)                                     # public entry point: CUDA only
 
 
 def test_differentiable_ssim_matches_oracle():
