@@ -359,5 +359,5 @@ def test_lpips_vgg_distance_and_gradient_vs_oracle():
     d_r.mean().backward()
     assert rel(d, d_r) < TOL
     assert rel(a_dev.grad, a_r.grad) < TOL
-    with torch.no_grad():
-        assert float(m(b.cuda(), b.cuda()).abs().max()) == 0.0
+    with torch.no_grad():       # identical inputs: zero up to the run-to-run rounding of the split-K atomics on the 4x4 / 8x8 maps
+        assert float(m(b.cuda(), b.cuda()).abs().max()) < 1e-9
