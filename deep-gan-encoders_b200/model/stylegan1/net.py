@@ -276,17 +276,43 @@ class Generator(nn.Module):
         return self.decode(styles, lod, 1)
 
 
+def _staged(module, name, t, dev):
+    """Device copy of a tensor the caller left on the CPU, cached per version.  The training scripts never move the
+    mapping network: `Gm` and `z` stay on the CPU and only the result is `.cuda()`-ed (E_align_s2.py:33-44, 108).  The
+    drop-in keeps that call working by staging the (tiny) operands onto the current CUDA device and running the same
+    kernels there -- it is not a CPU path: without a CUDA device `ops.lib()` raises."""
+    if t is None or t.device == dev:
+        return t
+    cache = module.__dict__.setdefault('_dge_staged', {})
+    key = (t.data_ptr(), t._version, str(dev))
+    hit = cache.get(name)
+    if hit is None or hit[0] != key:
+        hit = (key, t.detach().to(dev))
+        cache[name] = hit
+    return hit[1]
+
+
+def _compute_device(t):
+    if t.is_cuda:
+        return t.device
+    ops.lib()                                   # raises DgeError when there is no B200 to run on
+    return torch.device('cuda', torch.cuda.current_device())
+
+
 class MappingBlock(nn.Module):
     def __init__(self, inputs, output, lrmul=0.01):
         super().__init__()
         self.fc = ln.Linear(inputs, output, lrmul=lrmul)
 
     def forward(self, x):
-        ln._guard('MappingBlock', x, self.fc.weight)
+        dev = _compute_device(x)
+        x = x.to(dev)
         fc = self.fc
+        w, b = _staged(self, 'w', fc.weight, dev), _staged(self, 'b', fc.bias, dev)
+        ln._guard('MappingBlock', x, fc.weight)
         if fc.implicit_lreq:
-            return ops.dense(x.float(), fc.weight, fc.bias, slope=0.2)
-        return ops.dense(x.float(), fc.weight, fc.bias, wscale=fc.std, bscale=fc.lrmul, slope=0.2)
+            return ops.dense(x.float(), w, b, slope=0.2)
+        return ops.dense(x.float(), w, b, wscale=fc.std, bscale=fc.lrmul, slope=0.2)
 
 
 class Mapping(nn.Module):
@@ -303,10 +329,12 @@ class Mapping(nn.Module):
         self.register_buffer('buffer1', trunc_tensor)
 
     def forward(self, z, coefs_m=0):
-        x = pixel_norm(z)
+        dev = _compute_device(z)                # z / parameters / coefs may all live on the CPU (see `_staged`)
+        x = pixel_norm(z.to(dev))
         for i in range(self.mapping_layers):
             x = getattr(self, "block_%d" % (i + 1))(x)
         x = x.view(x.shape[0], 1, x.shape[1]).repeat(1, self.num_layers, 1)
         if self.buffer1 is not None:
-            x = torch.lerp(self.buffer1.data, x, coefs_m)     # avg + (styles - avg) * coefs  (:464-465)
+            coefs = coefs_m.to(dev) if torch.is_tensor(coefs_m) else coefs_m
+            x = torch.lerp(_staged(self, 'buffer1', self.buffer1.data, dev), x, coefs)   # avg + (styles - avg) * coefs (:464-465)
         return x
