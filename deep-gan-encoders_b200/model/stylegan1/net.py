@@ -309,7 +309,9 @@ class MappingBlock(nn.Module):
         x = x.to(dev)
         fc = self.fc
         w, b = _staged(self, 'w', fc.weight, dev), _staged(self, 'b', fc.bias, dev)
-        ln._guard('MappingBlock', x, fc.weight)
+        ln._guard('MappingBlock', x, w)
+        if torch.is_grad_enabled() and fc.weight.requires_grad:
+            raise NotImplementedError('MappingBlock: the mapping network is forward-only in this build; use torch.no_grad()')
         if fc.implicit_lreq:
             return ops.dense(x.float(), w, b, slope=0.2)
         return ops.dense(x.float(), w, b, wscale=fc.std, bscale=fc.lrmul, slope=0.2)
