@@ -85,19 +85,3 @@ def test_config1_stylegan1_256_vs_oracle():
         out = Gc.forward(styles.cuda(), 6)
     assert out.shape == (4, 3, 256, 256)
     assert rel(out, ref) < 1e-3
-
-
-def test_sg1_mapping_left_on_the_cpu_as_the_scripts_do():
-    """E_align_s2.py:33-44,108: `Gm` is never moved to the GPU and `z` / `coefs` are CPU tensors; only the result is
-    `.cuda()`-ed.  The drop-in stages the operands and still runs the kernels on the device."""
-    from model.stylegan1.net import Mapping
-    fx = torch.load(os.path.join(GOLD, "sg1_l6.pt"))
-    Gm = Mapping(num_layers=12, mapping_layers=3, latent_size=64, dlatent_size=64, mapping_fmaps=64)
-    Gm.buffer1 = torch.zeros(12, 64)
-    Gm.load_state_dict(fx["map_state_dict"], strict=True)
-    Gm.eval()                                        # stays on the CPU
-    with torch.no_grad():
-        styles = Gm(fx["z"], coefs_m=fx["coefs"]).cuda()
-    assert styles.is_cuda and rel(styles, fx["styles"]) < TOL
-    with torch.no_grad():                            # second call hits the staged-operand cache
-        assert rel(Gm(fx["z"], coefs_m=fx["coefs"]), fx["styles"]) < TOL

@@ -361,3 +361,19 @@ def test_lpips_vgg_distance_and_gradient_vs_oracle():
     assert rel(a_dev.grad, a_r.grad) < TOL
     with torch.no_grad():       # identical inputs: zero up to the run-to-run rounding of the split-K atomics on the 4x4 / 8x8 maps
         assert float(m(b.cuda(), b.cuda()).abs().max()) < 1e-9
+
+
+def test_sg1_mapping_left_on_the_cpu_as_the_scripts_do():
+    """E_align_s2.py:33-44,108: `Gm` is never moved to the GPU and `z` / `coefs` are CPU tensors; only the result is
+    `.cuda()`-ed.  The drop-in stages the operands and still runs the kernels on the device."""
+    from model.stylegan1.net import Mapping
+    fx = torch.load(os.path.join(GOLD, "sg1_l6.pt"))
+    Gm = Mapping(num_layers=12, mapping_layers=3, latent_size=64, dlatent_size=64, mapping_fmaps=64)
+    Gm.buffer1 = torch.zeros(12, 64)
+    Gm.load_state_dict(fx["map_state_dict"], strict=True)
+    Gm.eval()                                        # stays on the CPU
+    with torch.no_grad():
+        styles = Gm(fx["z"], coefs_m=fx["coefs"]).cuda()
+    assert styles.is_cuda and rel(styles, fx["styles"]) < 2e-4
+    with torch.no_grad():                            # second call hits the staged-operand cache
+        assert rel(Gm(fx["z"], coefs_m=fx["coefs"]), fx["styles"]) < 2e-4
