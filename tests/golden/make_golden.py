@@ -423,7 +423,85 @@ def encoder_grads():
           "max|g|", max(float(v.abs().max()) for v in grads.values()))
 
 
+def _summ(g):
+    """Compact pin of a gradient tensor: full values when small, else (l2 norm, sum, first 16 values)."""
+    g = g.detach().clone()
+    if g.numel() <= 4096:
+        return {"full": g}
+    return {"l2": g.norm().double().item(), "sum": g.double().sum().item(), "head": g.flatten()[:16].clone(),
+            "shape": tuple(g.shape)}
+
+
+def training_grads():
+    """Training-path fixtures for the other families: gradients `loss.backward()` produces through the UNMODIFIED
+    reference modules, on the weights / inputs of the existing fixtures (sg2_res32, sg1_l6, biggan_small, e_blur_s16_l6,
+    e_big_s16_l4).  Latent gradients are stored in full, parameter gradients as compact pins (`_summ`)."""
+    import model.stylegan2_generator as sg2
+    import model.stylegan1.net as sg1
+    import model.biggan_generator as bg
+    from model.utils.biggan_config import BigGANConfig
+    import model.E.E_Blur as EB
+    import model.E.E_BIG as EBIG
+    torch.set_grad_enabled(True)
+    out = {}
+    tgt = lambda shape, seed: torch.randn(shape, generator=torch.Generator().manual_seed(seed))
+
+    fx = torch.load(os.path.join(HERE, "sg2_res32.pt"))
+    G = sg2.StyleGAN2Generator(**fx["config"]).eval()
+    G.load_state_dict(fx["state_dict"], strict=True)
+    wp = fx["wp"].clone().requires_grad_(True)
+    img = G.synthesis(wp)["image"]
+    ((img - tgt(img.shape, 1)) ** 2).mean().backward()
+    out["sg2_dwp"] = wp.grad.clone()
+
+    fx = torch.load(os.path.join(HERE, "sg1_l6.pt"))
+    Gs = sg1.Generator(**fx["config"]).eval()
+    Gs.load_state_dict(fx["state_dict"], strict=True)
+    out["sg1_dstyles"] = {}
+    for lod in fx["images"]:
+        st = fx["styles"].clone().requires_grad_(True)
+        torch.manual_seed(60 + lod)
+        img = Gs.forward(st, lod)
+        ((img - tgt(img.shape, 2)) ** 2).mean().backward()
+        out["sg1_dstyles"][lod] = st.grad.clone()
+
+    fx = torch.load(os.path.join(HERE, "biggan_small.pt"))
+    Gb = bg.BigGAN(BigGANConfig.from_dict(fx["config"])).eval()
+    Gb.load_state_dict(fx["state_dict"], strict=True)
+    out["biggan_dz"] = {}
+    for trunc in fx["images"]:
+        z = fx["z"].clone().requires_grad_(True)
+        img, _ = Gb(z, fx["label"], trunc)
+        ((img - tgt(img.shape, 4)) ** 2).mean().backward()
+        out["biggan_dz"][trunc] = z.grad.clone()
+
+    fx = torch.load(os.path.join(HERE, "e_blur_s16_l6.pt"))
+    E = EB.BE(**fx["config"])
+    E.load_state_dict(fx["state_dict"], strict=True)
+    torch.manual_seed(fx["noise_seed"])
+    const, w = E(fx["img"])
+    (const.sum() + (w ** 2).mean()).backward()
+    out["e_blur"] = {k: _summ(p.grad) for k, p in E.named_parameters() if p.grad is not None}
+
+    fx = torch.load(os.path.join(HERE, "e_big_s16_l4.pt"))
+    E = EBIG.BE(**fx["config"]).eval()
+    E.load_state_dict(fx["state_dict"], strict=True)
+    x = E.FromRGB(fx["img"])
+    torch.manual_seed(13)
+    for blk in E.decode_block:
+        x = blk(x, fx["cond"], truncation=0.4)
+        x = x[0] if isinstance(x, (tuple, list)) else x
+    (x ** 2).mean().backward()
+    out["e_big"] = {k: _summ(p.grad) for k, p in E.named_parameters() if p.grad is not None}
+    torch.save(out, os.path.join(HERE, "train_grads.pt"))
+    print("train_grads.pt:", {k: (len(v) if isinstance(v, dict) else tuple(v.shape)) for k, v in out.items()})
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "training_grads":
+        import_reference()
+        training_grads()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "encoder_grads":
         import_reference()
         encoder_grads()

@@ -111,6 +111,67 @@ def test_be_gradients(be):
         assert rel(sd[k].grad, g) < 1e-4, k
 
 
+def _check_pin(g, pin, tol, name=""):
+    """Compare a gradient with the compact pin make_golden.training_grads stored for it."""
+    if "full" in pin:
+        assert rel(g, pin["full"]) < tol, name
+        return
+    assert tuple(g.shape) == pin["shape"], name
+    assert abs(g.norm().double().item() - pin["l2"]) <= tol * pin["l2"], name
+    scale = pin["l2"] / g.numel() ** 0.5
+    assert abs(g.double().sum().item() - pin["sum"]) <= tol * max(abs(pin["sum"]), scale * g.numel() ** 0.5), name
+    assert (g.flatten()[:16] - pin["head"]).abs().max().item() <= tol * max(pin["head"].abs().max().item(), scale), name
+
+
+def test_training_gradients_of_the_other_families_match_the_reference():
+    """Autograd through the oracle == `loss.backward()` through the unmodified reference (train_grads.pt): StyleGAN2
+    synthesis (d/dwp), StyleGAN1 decode (d/dstyles), BigGAN (d/dz), E_Blur and E_BIG (every parameter)."""
+    from oracle import biggan as obg
+    from oracle import stylegan1 as osg1
+    gx = torch.load(os.path.join(GOLD, "train_grads.pt"))
+    tgt = lambda shape, seed: torch.randn(shape, generator=torch.Generator().manual_seed(seed))
+    with torch.enable_grad():
+        fx = torch.load(os.path.join(GOLD, "sg2_res32.pt"))
+        wp = fx["wp"].clone().requires_grad_(True)
+        img = osg2.synthesis(fx["state_dict"], wp, fx["config"]["resolution"])["image"]
+        ((img - tgt(img.shape, 1)) ** 2).mean().backward()
+        assert rel(wp.grad, gx["sg2_dwp"]) < 1e-4
+
+        fx = torch.load(os.path.join(GOLD, "sg1_l6.pt"))
+        for lod, want in gx["sg1_dstyles"].items():
+            st = fx["styles"].clone().requires_grad_(True)
+            torch.manual_seed(60 + lod)
+            img = osg1.decode(fx["state_dict"], st, lod)
+            ((img - tgt(img.shape, 2)) ** 2).mean().backward()
+            assert rel(st.grad, want) < 1e-4, lod
+
+        fx = torch.load(os.path.join(GOLD, "biggan_small.pt"))
+        for trunc, want in gx["biggan_dz"].items():
+            z = fx["z"].clone().requires_grad_(True)
+            img, _ = obg.biggan(fx["state_dict"], fx["config"], z, fx["label"], trunc)
+            ((img - tgt(img.shape, 4)) ** 2).mean().backward()
+            assert rel(z.grad, want) < 1e-4, trunc
+
+        fx = torch.load(os.path.join(GOLD, "e_blur_s16_l6.pt"))
+        sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in fx["state_dict"].items()}
+        torch.manual_seed(fx["noise_seed"])
+        const, w = oenc.be_blur_forward(sd, fx["img"], fx["config"]["layer_count"])
+        (const.sum() + (w ** 2).mean()).backward()
+        assert {k for k, v in sd.items() if v.grad is not None} == set(gx["e_blur"])
+        for k, pin in gx["e_blur"].items():
+            _check_pin(sd[k].grad, pin, 5e-4, k)
+
+        fx = torch.load(os.path.join(GOLD, "e_big_s16_l4.pt"))
+        frozen = ("_u", "_v", "running_means", "running_vars")
+        sd = {k: v.clone().requires_grad_(v.is_floating_point() and not k.endswith(frozen))
+              for k, v in fx["state_dict"].items()}
+        torch.manual_seed(13)
+        (obg.e_big_features(sd, fx["img"], fx["cond"], fx["config"]["layer_count"]) ** 2).mean().backward()
+        assert {k for k, v in sd.items() if v.grad is not None} == set(gx["e_big"])
+        for k, pin in gx["e_big"].items():
+            _check_pin(sd[k].grad, pin, 5e-4, k)
+
+
 def test_e2g_roundtrip():
     fx = torch.load(os.path.join(GOLD, "e2g_res32.pt"))
     gsd, esd = fx["g_state_dict"], fx["e_state_dict"]

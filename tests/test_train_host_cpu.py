@@ -15,6 +15,24 @@ def rel(a, b):
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-20)).item()
 
 
+def _check_pin(g, pin, tol, name=""):
+    """Compare a gradient with the compact pin tests/golden/make_golden.py::training_grads stored for it."""
+    if "full" in pin:
+        assert rel(g, pin["full"]) < tol, name
+        return
+    assert tuple(g.shape) == pin["shape"], name
+    assert abs(g.norm().double().item() - pin["l2"]) <= tol * pin["l2"], name
+    scale = pin["l2"] / g.numel() ** 0.5
+    assert abs(g.double().sum().item() - pin["sum"]) <= tol * max(abs(pin["sum"]), scale * g.numel() ** 0.5), name
+    assert (g.flatten()[:16] - pin["head"]).abs().max().item() <= tol * max(pin["head"].abs().max().item(), scale), name
+
+
+@pytest.fixture(scope="module")
+def ref_grads():
+    """Gradients produced by `loss.backward()` through the unmodified reference (train_grads.pt)."""
+    return torch.load(os.path.join(GOLD, "train_grads.pt"))
+
+
 @pytest.fixture()
 def aten_conv(monkeypatch):
     import model.E.E as EM
@@ -53,7 +71,7 @@ def test_encoder_graph_matches_reference_gradients(aten_conv):
         assert rel(got[k], g) < 1e-4, k
 
 
-def test_synthesis_graph_matches_oracle_gradient(aten_conv):
+def test_synthesis_graph_matches_oracle_gradient(aten_conv, ref_grads):
     from model.stylegan2_generator import StyleGAN2Generator
     from oracle import stylegan2 as osg2
     fx = torch.load(os.path.join(GOLD, "sg2_res32.pt"))
@@ -70,12 +88,13 @@ def test_synthesis_graph_matches_oracle_gradient(aten_conv):
     ((ref["image"] - target) ** 2).mean().backward()
     assert set(out) == set(ref)
     assert rel(wp.grad, wp_r.grad) < 1e-5
+    assert rel(wp.grad, ref_grads["sg2_dwp"]) < 1e-4          # ... and the reference's own backward
     torch.manual_seed(77)
     out_rn = G.synthesis._forward_autograd(fx["wp"].clone().requires_grad_(True), randomize_noise=True)
     assert rel(out_rn["image"], fx["image_randnoise_seed77"]) < 2e-5
 
 
-def test_stylegan1_graph_matches_fixture_and_oracle_gradient(aten_conv):
+def test_stylegan1_graph_matches_fixture_and_oracle_gradient(aten_conv, ref_grads):
     from model.stylegan1.net import Generator
     from oracle import stylegan1 as osg1
     fx = torch.load(os.path.join(GOLD, "sg1_l6.pt"))
@@ -92,10 +111,11 @@ def test_stylegan1_graph_matches_fixture_and_oracle_gradient(aten_conv):
         torch.manual_seed(60 + lod)
         ((osg1.decode(fx["state_dict"], styles_r, lod) - target) ** 2).mean().backward()
         assert rel(styles.grad, styles_r.grad) < 1e-5, lod
+        assert rel(styles.grad, ref_grads["sg1_dstyles"][lod]) < 1e-4, lod
     assert all(p.grad is None for p in Gs.parameters())
 
 
-def test_e_blur_graph_matches_fixture_and_oracle_gradients(aten_conv):
+def test_e_blur_graph_matches_fixture_and_oracle_gradients(aten_conv, ref_grads):
     """Case-2 encoder (strided transform_kernel convs + blur).  Two fp32 evaluations of this chain differ by ~6e-5 from
     the fp64 value on the 4x4 blocks, hence 3e-4 here."""
     from model.E.E_Blur import BE
@@ -115,11 +135,12 @@ def test_e_blur_graph_matches_fixture_and_oracle_gradients(aten_conv):
     for k, p in E.named_parameters():
         if sd[k].grad is not None:
             assert rel(p.grad, sd[k].grad) < 3e-4, k
+            _check_pin(p.grad, ref_grads["e_blur"][k], 5e-4, k)
             checked += 1
-    assert checked > 50
+    assert checked > 50 and checked == len(ref_grads["e_blur"])
 
 
-def test_biggan_graph_matches_fixture_and_oracle_gradient(aten_conv):
+def test_biggan_graph_matches_fixture_and_oracle_gradient(aten_conv, ref_grads):
     from model.biggan_generator import BigGAN
     from model.utils.biggan_config import BigGANConfig
     from oracle import biggan as obg
@@ -138,10 +159,11 @@ def test_biggan_graph_matches_fixture_and_oracle_gradient(aten_conv):
         ref, _ = obg.biggan(fx["state_dict"], fx["config"], z_r, fx["label"], trunc)
         ((ref - target) ** 2).mean().backward()
         assert rel(z.grad, z_r.grad) < 1e-5, trunc
+        assert rel(z.grad, ref_grads["biggan_dz"][trunc]) < 1e-4, trunc
     assert all(p.grad is None for p in G.parameters())
 
 
-def test_e_big_graph_matches_fixture_and_oracle_gradients(aten_conv):
+def test_e_big_graph_matches_fixture_and_oracle_gradients(aten_conv, ref_grads):
     """BigGAN encoder: the conditional-BN scale / offset layers are spectral-norm wrapped AND trainable here."""
     from model.E.E_BIG import BE
     from oracle import biggan as obg
@@ -162,8 +184,9 @@ def test_e_big_graph_matches_fixture_and_oracle_gradients(aten_conv):
     for k, p in E.named_parameters():
         if p.grad is not None:
             assert rel(p.grad, sd[k].grad) < 1e-4, k
+            _check_pin(p.grad, ref_grads["e_big"][k], 5e-4, k)
             checked += 1
-    assert checked >= 40
+    assert checked >= 40 and checked == len(ref_grads["e_big"])
 
 
 def test_lpips_structure_matches_oracle_and_torchvision(aten_conv):
