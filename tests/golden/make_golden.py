@@ -493,6 +493,28 @@ def training_grads():
         x = x[0] if isinstance(x, (tuple, list)) else x
     (x ** 2).mean().backward()
     out["e_big"] = {k: _summ(p.grad) for k, p in E.named_parameters() if p.grad is not None}
+    # the whole iteration of E_align_s2.py:152-207 on the small E/G pair of e2g_res32.pt: imgs1 -> E -> G.synthesis ->
+    # image-space + latent-space space_loss (stand-in LPIPS, the package is absent) -> backward into E
+    import training_utils as tu
+    fx = torch.load(os.path.join(HERE, "e2g_res32.pt"))
+    G = sg2.StyleGAN2Generator(**fx["g_config"]).eval()
+    G.load_state_dict(fx["g_state_dict"], strict=True)
+    import model.E.E as E1
+    E = E1.BE(**fx["e_config"])
+    E.load_state_dict(fx["e_state_dict"], strict=True)
+
+    def lp(a, b):
+        return ((a - b) ** 2).mean(dim=(1, 2, 3), keepdim=True) + 0.1 * (a - b).abs().mean(dim=(1, 2, 3), keepdim=True)
+
+    imgs1, w1 = fx["imgs1"], fx["wp1"]
+    torch.manual_seed(fx["noise_seed"])
+    const2, w2 = E(imgs1)
+    imgs2 = G.synthesis(w2)["image"]
+    l_img, info_img = tu.space_loss(imgs1, imgs2, lpips_model=lp)
+    l_w, info_w = tu.space_loss(w1, w2, image_space=False)
+    (l_img + 0.01 * l_w).backward()
+    out["e2g_iteration"] = {"l_img": float(l_img), "l_w": float(l_w), "info_img": info_img, "info_w": info_w,
+                            "grads": {k: _summ(p.grad) for k, p in E.named_parameters() if p.grad is not None}}
     torch.save(out, os.path.join(HERE, "train_grads.pt"))
     print("train_grads.pt:", {k: (len(v) if isinstance(v, dict) else tuple(v.shape)) for k, v in out.items()})
 

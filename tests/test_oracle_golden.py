@@ -172,6 +172,36 @@ def test_training_gradients_of_the_other_families_match_the_reference():
             _check_pin(sd[k].grad, pin, 5e-4, k)
 
 
+def test_full_training_iteration_of_the_oracle_matches_the_reference():
+    """E_align_s2.py:152-207 through the oracle (encoder -> synthesis -> image-space + latent-space space_loss ->
+    backward) == the same chain through the unmodified reference modules and its own `space_loss`
+    (train_grads.pt['e2g_iteration']).  This is the checker tests/test_train_gpu.py holds the CUDA path to."""
+    from oracle import losses as oloss
+    gx = torch.load(os.path.join(GOLD, "train_grads.pt"))["e2g_iteration"]
+    fx = torch.load(os.path.join(GOLD, "e2g_res32.pt"))
+
+    def lp(a, b):
+        return ((a - b) ** 2).mean(dim=(1, 2, 3), keepdim=True) + 0.1 * (a - b).abs().mean(dim=(1, 2, 3), keepdim=True)
+
+    esd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in fx["e_state_dict"].items()}
+    with torch.enable_grad():
+        torch.manual_seed(fx["noise_seed"])
+        const2, w2 = oenc.be_forward(esd, fx["imgs1"], fx["e_config"]["layer_count"])
+        imgs2 = osg2.synthesis(fx["g_state_dict"], w2, fx["g_config"]["resolution"])["image"]
+        l_img, info_img = oloss.space_loss(fx["imgs1"], imgs2, lpips_model=lp)
+        l_w, info_w = oloss.space_loss(fx["wp1"], w2, image_space=False)
+        (l_img + 0.01 * l_w).backward()
+    assert abs(float(l_img.detach()) - gx["l_img"]) < 1e-5 * abs(gx["l_img"])
+    assert abs(float(l_w.detach()) - gx["l_w"]) < 1e-5 * abs(gx["l_w"])
+    flat = lambda i: list(i[0]) + list(i[1:])
+    for got, want in ((info_img, gx["info_img"]), (info_w, gx["info_w"])):
+        for u, v in zip(flat(got), flat(want)):
+            assert abs(u - v) <= 1e-4 * abs(v) + 1e-7
+    assert {k for k, v in esd.items() if v.grad is not None} == set(gx["grads"])
+    for k, pin in gx["grads"].items():
+        _check_pin(esd[k].grad, pin, 5e-4, k)
+
+
 def test_e2g_roundtrip():
     fx = torch.load(os.path.join(GOLD, "e2g_res32.pt"))
     gsd, esd = fx["g_state_dict"], fx["e_state_dict"]
