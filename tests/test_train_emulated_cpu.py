@@ -1,0 +1,204 @@
+"""The GPU training tests, dry-run on the CPU under a MODEL of the kernels' arithmetic.
+
+`tests/test_train_gpu.py` can only run on a B200.  Here the one CUDA-only node of the recorded graphs
+(dge_b200.autograd.conv2d) is replaced by an emulation of what the tcgen05 kernels compute -- bf16 hi + bf16 lo operands,
+the three products hi*hi + hi*lo + lo*hi, fp32 accumulation, for the forward, the data gradient and the weight
+gradient -- and the same comparisons are made with the same helpers (`record_masks` / `replay_masks`).  It checks, without
+a GPU, (a) that split precision meets the gradient bar with margin, (b) the activation-pattern argument of the GPU
+tests: with the pattern held the difference to the oracle is ~1e-5, without it a single flipped unit moves whole
+gradients by 1e-3..1e-2, (c) the call-order bookkeeping of the helpers for every family.
+"""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import test_train_gpu as T          # helpers only; its tests are gpu-marked
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+rel = T.rel
+
+
+def _split(t):
+    hi = t.to(torch.bfloat16).float()
+    return hi, (t - hi).to(torch.bfloat16).float()
+
+
+class _SplitPrecisionConv(torch.autograd.Function):
+    """conv2d(x, w, padding=k//2) the way the kernels evaluate it (csrc/conv_mma.cu, conv_wgrad.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, w, planes):
+        p = w.shape[-1] // 2
+        xh, xl = _split(x)
+        wh, wl = _split(w)
+        ctx.save_for_backward(xh, xl, w)
+        ctx.p = p
+        return F.conv2d(xh, wh, padding=p) + F.conv2d(xh, wl, padding=p) + F.conv2d(xl, wh, padding=p)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xh, xl, w = ctx.saved_tensors
+        p = ctx.p
+        dh, dl = _split(dy)
+        wh, wl = _split(w)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            gi = lambda d, ww: torch.nn.grad.conv2d_input(xh.shape, ww, d, padding=p)
+            dx = gi(dh, wh) + gi(dh, wl) + gi(dl, wh)
+        if ctx.needs_input_grad[1]:
+            gw = lambda d, xx: torch.nn.grad.conv2d_weight(xx, w.shape, d, padding=p)
+            dw = gw(dh, xh) + gw(dh, xl) + gw(dl, xh)
+        return dx, dw, None
+
+
+@pytest.fixture()
+def emulated_conv(monkeypatch):
+    import lpips as LP
+    import model.E.E as EM
+    import model.E.E_BIG as EG
+    import model.E.E_Blur as EB
+    import model.biggan_generator as BG
+    import model.stylegan1.net as S1
+    import model.stylegan2_generator as SG
+
+    def conv(x, w, planes=2):
+        return _SplitPrecisionConv.apply(x, w, planes)
+
+    for m in (LP, EM, EG, EB, BG, S1, SG):
+        monkeypatch.setattr(m.tc, "conv2d", conv)
+
+
+def _lp(a, b):
+    return ((a - b) ** 2).mean(dim=(1, 2, 3), keepdim=True) + 0.1 * (a - b).abs().mean(dim=(1, 2, 3), keepdim=True)
+
+
+def test_full_iteration_under_split_precision(emulated_conv):
+    """The chain of test_full_training_iteration_gradients_vs_oracle: with the activation pattern replayed the encoder
+    gradients agree to ~3e-5; evaluated at its own pattern the oracle differs by >1e-3 on this fixture (one unit of
+    the generator's 8x8 layer has a pre-activation within rounding of zero)."""
+    from model.E.E import BE
+    from model.stylegan2_generator import StyleGAN2Generator
+    from oracle import encoder as oenc
+    from oracle import losses as oloss
+    from oracle import stylegan2 as osg2
+    fx = torch.load(os.path.join(GOLD, "e2g_res32.pt"))
+    G = StyleGAN2Generator(**fx["g_config"])
+    G.load_state_dict(fx["g_state_dict"], strict=True)
+    G.eval()
+    E = BE(**fx["e_config"])
+    E.load_state_dict(fx["e_state_dict"], strict=True)
+    imgs1, w1 = fx["imgs1"], fx["wp1"]
+    masks = []
+    torch.manual_seed(fx["noise_seed"])
+    with T.record_masks(masks):
+        _, w2 = E._forward_autograd(imgs1, 9)
+        imgs2 = G.synthesis._forward_autograd(w2)["image"]
+    assert rel(imgs2, fx["imgs2"]) < 2e-4
+    l1, _ = oloss.space_loss(imgs1, imgs2, lpips_model=_lp)
+    l2, _ = oloss.space_loss(w1, w2, image_space=False)
+    (l1 + 0.01 * l2).backward()
+
+    def oracle_grads(replay):
+        esd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in fx["e_state_dict"].items()}
+        torch.manual_seed(fx["noise_seed"])
+        ctx = T.replay_masks(masks) if replay else T.record_masks([])
+        with ctx:
+            _, w2_r = oenc.be_forward(esd, imgs1, fx["e_config"]["layer_count"])
+            imgs2_r = osg2.synthesis(fx["g_state_dict"], w2_r, fx["g_config"]["resolution"])["image"]
+        a, _ = oloss.space_loss(imgs1, imgs2_r, lpips_model=_lp)
+        b, _ = oloss.space_loss(w1, w2_r, image_space=False)
+        (a + 0.01 * b).backward()
+        return esd
+
+    held, free = oracle_grads(True), oracle_grads(False)
+    worst_held = max(rel(p.grad, held[k].grad) for k, p in E.named_parameters() if held[k].grad is not None)
+    worst_free = max(rel(p.grad, free[k].grad) for k, p in E.named_parameters() if free[k].grad is not None)
+    assert worst_held < 2e-4
+    assert worst_free > 5 * worst_held          # the flip, not the arithmetic, is what a plain comparison would see
+
+
+def test_biggan_and_lpips_under_split_precision(emulated_conv):
+    """ReLU patterns and max-pool arg-maxes are replayed too (BigGAN attention, VGG16)."""
+    import lpips
+    from model.biggan_generator import BigGAN
+    from model.utils.biggan_config import BigGANConfig
+    from oracle import biggan as obg
+    from oracle import lpips as olp
+    fx = torch.load(os.path.join(GOLD, "biggan_small.pt"))
+    G = BigGAN(BigGANConfig.from_dict(fx["config"]))
+    G.load_state_dict(fx["state_dict"], strict=True)
+    G.eval()
+    trunc, img = next(iter(fx["images"].items()))
+    z = fx["z"].clone().requires_grad_(True)
+    masks = []
+    with T.record_masks(masks):
+        cond = torch.cat((z, F.linear(fx["label"], G.embeddings.weight.detach())), dim=1)
+        out = G.generator._forward_autograd(cond, trunc)
+    assert rel(out, img) < 2e-4
+    target = torch.randn(out.shape, generator=torch.Generator().manual_seed(4))
+    ((out - target) ** 2).mean().backward()
+    z_r = fx["z"].clone().requires_grad_(True)
+    with T.replay_masks(masks):
+        ref, _ = obg.biggan(fx["state_dict"], fx["config"], z_r, fx["label"], trunc)
+    ((ref - target) ** 2).mean().backward()
+    assert rel(z.grad, z_r.grad) < 2e-4
+
+    torch.manual_seed(0)
+    m = lpips.LPIPS(net="vgg", verbose=False)
+    with torch.no_grad():
+        for k in range(5):
+            getattr(m, f"lin{k}").model[1].weight.abs_()
+    g = torch.Generator().manual_seed(1)
+    a = (torch.rand(1, 3, 32, 32, generator=g) * 2 - 1).requires_grad_(True)
+    b = torch.rand(1, 3, 32, 32, generator=g) * 2 - 1
+    masks = []
+    with T.record_masks(masks):
+        d = m._distance(a, b)
+    d.mean().backward()
+    a_r = a.detach().clone().requires_grad_(True)
+    with T.replay_masks(masks):
+        d_r = olp.lpips_vgg(m.state_dict(), a_r, b)
+    d_r.mean().backward()
+    assert rel(d, d_r) < 2e-4 and rel(a.grad, a_r.grad) < 2e-4
+
+
+def test_stylegan1_and_case2_encoder_under_split_precision(emulated_conv):
+    from model.E.E_Blur import BE
+    from model.stylegan1.net import Generator
+    from oracle import encoder as oenc
+    from oracle import stylegan1 as osg1
+    fx = torch.load(os.path.join(GOLD, "sg1_l6.pt"))
+    Gs = Generator(**fx["config"])
+    Gs.load_state_dict(fx["state_dict"], strict=True)
+    lod = 5
+    styles = fx["styles"].clone().requires_grad_(True)
+    masks = []
+    torch.manual_seed(60 + lod)
+    with T.record_masks(masks):
+        out = Gs._decode_autograd(styles, lod)
+    assert rel(out, fx["images"][lod]) < 2e-4
+    target = torch.randn(out.shape, generator=torch.Generator().manual_seed(2))
+    ((out - target) ** 2).mean().backward()
+    styles_r = fx["styles"].clone().requires_grad_(True)
+    torch.manual_seed(60 + lod)
+    with T.replay_masks(masks):
+        ref = osg1.decode(fx["state_dict"], styles_r, lod)
+    ((ref - target) ** 2).mean().backward()
+    assert rel(styles.grad, styles_r.grad) < 2e-4
+
+    fb = torch.load(os.path.join(GOLD, "e_blur_s16_l6.pt"))
+    E = BE(**fb["config"])
+    E.load_state_dict(fb["state_dict"], strict=True)
+    masks = []
+    torch.manual_seed(fb["noise_seed"])
+    with T.record_masks(masks):
+        const, w = E._forward_autograd(fb["img"], 9)
+    (const.sum() + (w ** 2).mean()).backward()
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in fb["state_dict"].items()}
+    torch.manual_seed(fb["noise_seed"])
+    with T.replay_masks(masks):
+        const_r, w_r = oenc.be_blur_forward(sd, fb["img"], fb["config"]["layer_count"])
+    (const_r.sum() + (w_r ** 2).mean()).backward()
+    assert max(rel(p.grad, sd[k].grad) for k, p in E.named_parameters() if sd[k].grad is not None) < 3e-4
