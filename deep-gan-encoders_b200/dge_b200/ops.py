@@ -15,6 +15,38 @@ FLAG_CHECKER = 1
 
 _device_checked = False
 
+# ------------------------------------------------------------------------------------------------
+# weight-cache epoch
+# ------------------------------------------------------------------------------------------------
+# The modules cache tensors DERIVED from their parameters (packed WPK weights, demodulation Gram diagonals, ...).
+# torch's per-tensor `_version` only sees in-place ops on the Parameter object itself: an optimiser that writes through
+# `p.data` (the reference's LREQAdam: `p.data.addcdiv_`, custom_adam.py:74) or through a raw device pointer
+# (dge_lreq_adam_step) changes the values without bumping it.  Every cache key therefore also carries this epoch, which
+# is advanced by EVERY torch optimiser step (global post-step hook below) and by LREQAdam.step itself; code that
+# mutates `p.data` by hand outside an optimiser calls `invalidate_weight_caches()`.
+_weights_epoch = 0
+
+
+def weights_epoch():
+    return _weights_epoch
+
+
+def invalidate_weight_caches():
+    global _weights_epoch
+    _weights_epoch += 1
+
+
+def weight_key(*tensors):
+    """Cache key of tensors derived from these parameters: storage, in-place version and the optimiser epoch."""
+    return (_weights_epoch,) + tuple((t.data_ptr(), t._version, str(t.device)) for t in tensors)
+
+
+try:  # any torch.optim.Optimizer subclass, including the unmodified reference LREQAdam
+    from torch.optim.optimizer import register_optimizer_step_post_hook as _reg_post_hook
+    _reg_post_hook(lambda *_a, **_k: invalidate_weight_caches())
+except ImportError:  # pragma: no cover - torch < 2.1
+    pass
+
 
 def lib():
     global _device_checked
@@ -99,6 +131,14 @@ class Act:
         self.n, self.c, self.h, self.w, self.planes = n, c, h, w, planes
         self.t = torch.empty((n, c // 8, planes, h, w, 8), dtype=torch.bfloat16, device=device)
 
+    @classmethod
+    def wrap(cls, t, n, c, h, w, planes=2):
+        """View an existing bf16 buffer of the right size as an ACT tensor (saved-for-backward storage)."""
+        assert t.dtype == torch.bfloat16 and t.is_contiguous() and t.numel() == n * c * planes * h * w
+        o = cls.__new__(cls)
+        o.n, o.c, o.h, o.w, o.planes, o.t = n, c, h, w, planes, t
+        return o
+
     def to_nchw(self):
         out = torch.empty((self.n, self.c, self.h, self.w), dtype=torch.float32, device=self.t.device)
         check(lib().dge_act_to_nchw(_p(self.t), _p(out), self.n, self.c, self.h, self.w, self.planes, _stream()))
@@ -112,6 +152,13 @@ class F32B:
         assert c % 8 == 0
         self.n, self.c, self.h, self.w = n, c, h, w
         self.t = torch.empty((n, c // 8, h, w, 8), dtype=torch.float32, device=device)
+
+    @classmethod
+    def wrap(cls, t, n, c, h, w):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == n * c * h * w
+        o = cls.__new__(cls)
+        o.n, o.c, o.h, o.w, o.t = n, c, h, w, t
+        return o
 
     def to_nchw(self):
         out = torch.empty((self.n, self.c, self.h, self.w), dtype=torch.float32, device=self.t.device)

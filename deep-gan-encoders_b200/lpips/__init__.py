@@ -18,12 +18,37 @@ data-gradient (the VGG weights are frozen: `requires_grad=False` as in the packa
 dge_b200.autograd.conv2d; the 3-channel first conv, ReLU, max-pool and the small reductions are torch CUDA ops in this
 build.  CUDA-only (DgeError on CPU tensors), like every other module of this tree.
 """
+import importlib.machinery
+import os
+import sys
+
+# A real `lpips` installation wins: this directory sits first on sys.path (it mirrors the reference tree), so look for
+# another distribution of the same name further down the path and hand the import over to it.
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_real = importlib.machinery.PathFinder.find_spec(
+    'lpips', [p for p in sys.path if os.path.abspath(p or '.') != os.path.dirname(_HERE)])
+if _real is not None and _real.origin and os.path.dirname(os.path.abspath(_real.origin)) != _HERE:
+    import importlib.util
+    _mod = importlib.util.module_from_spec(_real)
+    sys.modules['lpips'] = _mod
+    _real.loader.exec_module(_mod)
+    globals().update(_mod.__dict__)
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
 from dge_b200 import autograd as tc
 from dge_b200 import ops
+
+
+def _find_weights():
+    """Published weights, if the user has them offline: $DGE_LPIPS_VGG16 / torch-hub cache for the torchvision VGG16
+    backbone, $DGE_LPIPS_LIN for the package's `weights/v0.1/vgg.pth` (linear layers)."""
+    hub = os.path.join(os.environ.get('TORCH_HOME', os.path.expanduser('~/.cache/torch')), 'hub', 'checkpoints')
+    vgg = os.environ.get('DGE_LPIPS_VGG16') or os.path.join(hub, 'vgg16-397923af.pth')
+    lin = os.environ.get('DGE_LPIPS_LIN')
+    return (vgg if os.path.exists(vgg) else None), (lin if lin and os.path.exists(lin) else None)
 
 # torchvision vgg16.features: (index, in_channels, out_channels) of the convs of each LPIPS slice; a slice after the
 # first starts with the 2x2 max-pool that precedes its first conv (features[4], [9], [16], [23])
@@ -84,7 +109,7 @@ class _VGG16Features(nn.Module):
                 if w.shape[1] % 16 == 0 and w.shape[0] % 16 == 0:
                     h = tc.conv2d(h, w, self.planes) + conv.bias.view(1, -1, 1, 1)
                 else:                                   # 3 input channels: point-wise cost, library conv
-                    h = F.conv2d(h, w, conv.bias, padding=1)
+                    h = tc.lib_conv2d(h, w, conv.bias, padding=1)
                 h = F.relu(h)
             taps.append(h)
         return taps
@@ -110,13 +135,57 @@ class LPIPS(nn.Module):
         for k, c in enumerate(self.chns):
             setattr(self, f'lin{k}', NetLinLayer(c, use_dropout=use_dropout))
         self.lins = nn.ModuleList([getattr(self, f'lin{k}') for k in range(self.L)])
-        if model_path is not None:
-            self.load_state_dict(torch.load(model_path, map_location='cpu'), strict=False)
-        elif pretrained and verbose:
-            print('dge_b200 LPIPS: the pretrained VGG16 / linear-layer weights are not available offline; parameters are '
-                  'randomly initialised -- pass model_path=... or load_state_dict() to use the published weights')
+        self._load_weights(pretrained, pnet_rand, model_path, verbose)
         if eval_mode:
             self.eval()
+
+    def _load_weights(self, pretrained, pnet_rand, model_path, verbose):
+        """The published metric = torchvision's ImageNet VGG16 backbone + the package's trained `lin` layers.  Neither
+        file exists offline, and silently training against a random metric is worse than failing: random weights need
+        the explicit opt-in `pnet_rand=True` + `pretrained=False` (the package's own switches), or
+        DGE_LPIPS_ALLOW_RANDOM=1 in the environment (synthetic benchmarks / tests of unmodified scripts)."""
+        allow_random = os.environ.get('DGE_LPIPS_ALLOW_RANDOM') == '1'
+        vgg_path, lin_path = _find_weights()
+        if not pnet_rand:
+            if vgg_path is not None:
+                sd = torch.load(vgg_path, map_location='cpu')
+                mine = {}
+                for k, convs in enumerate(_SLICES):
+                    for idx, _, _ in convs:
+                        for s in ('weight', 'bias'):
+                            mine[f'net.slice{k + 1}.{idx}.{s}'] = sd[f'features.{idx}.{s}']
+                missing = [k for k in self.state_dict() if k.startswith('net.') and k not in mine]
+                if missing:
+                    raise RuntimeError(f'dge_b200 LPIPS: {vgg_path} lacks backbone tensors {missing[:4]}...')
+                self.load_state_dict(mine, strict=False)
+            elif not allow_random:
+                raise FileNotFoundError(
+                    "dge_b200 LPIPS: no pretrained VGG16 backbone found (looked for $DGE_LPIPS_VGG16 and the torch-hub "
+                    "cache file vgg16-397923af.pth).  Pass pnet_rand=True, pretrained=False for a randomly initialised "
+                    "metric, or set DGE_LPIPS_ALLOW_RANDOM=1.")
+        if pretrained or model_path is not None:
+            path = model_path or lin_path
+            if path is not None:
+                sd = torch.load(path, map_location='cpu')
+                res = self.load_state_dict(sd, strict=False)
+                lin_missing = [k for k in res.missing_keys if k.startswith('lin')]
+                if lin_missing:
+                    raise RuntimeError(f'dge_b200 LPIPS: {path} lacks the linear layers {lin_missing}')
+                if any(k.startswith('net.') for k in res.missing_keys) and vgg_path is None and not (pnet_rand or allow_random):
+                    raise RuntimeError(f'dge_b200 LPIPS: {path} holds only the linear layers and no VGG16 backbone '
+                                       'weights were found; the backbone would stay randomly initialised')
+                return
+            if not allow_random:
+                raise FileNotFoundError(
+                    "dge_b200 LPIPS: pretrained=True but the trained linear layers (lpips/weights/v0.1/vgg.pth) are not "
+                    "available offline: pass model_path=..., set $DGE_LPIPS_LIN, or construct with pretrained=False.")
+        # randomly initialised linear layers: keep them non-negative like the trained ones (the package clamps them),
+        # so the distance stays a non-negative number
+        with torch.no_grad():
+            for lin in self.lins:
+                lin.model[1].weight.abs_()
+        if verbose and (pretrained or not pnet_rand):
+            print('dge_b200 LPIPS: running with RANDOMLY INITIALISED weights (explicit opt-in) -- not the published metric')
 
     def forward(self, in0, in1, retPerLayer=False, normalize=False):
         if not (in0.is_cuda and in1.is_cuda):
@@ -124,7 +193,6 @@ class LPIPS(nn.Module):
         return self._distance(in0, in1, retPerLayer, normalize)
 
     def _distance(self, in0, in1, retPerLayer=False, normalize=False):
-        tc.require_fp32_library_convs()
         if normalize:                                    # [0, 1] -> [-1, 1]
             in0, in1 = 2 * in0 - 1, 2 * in1 - 1
         f0 = self.net(self.scaling_layer(in0.float()))

@@ -16,7 +16,6 @@ def _ssim_mean_autograd(a, b):
     """Differentiable mean SSIM (training path, `_ssim` :18-38): normalised 11-tap gaussian (sigma 1.5) applied
     separably per channel with zero padding 5, local moments, C1 = 0.01^2, C2 = 0.03^2, mean of the map."""
     from dge_b200 import autograd as tc
-    tc.require_fp32_library_convs()
     c = a.shape[1]
     t = torch.arange(11, dtype=torch.float32, device=a.device) - 5.0
     g = torch.exp(-(t * t) / (2 * 1.5 ** 2))
@@ -24,7 +23,7 @@ def _ssim_mean_autograd(a, b):
     win = (g[:, None] * g[None, :]).expand(c, 1, 11, 11).contiguous()
 
     def blur(v):
-        return F.conv2d(v, win, padding=5, groups=c)
+        return tc.lib_conv2d(v, win, padding=5, groups=c)
 
     mu_a, mu_b = blur(a), blur(b)
     var_a, var_b, cov = blur(a * a) - mu_a * mu_a, blur(b * b) - mu_b * mu_b, blur(a * b) - mu_a * mu_b

@@ -101,7 +101,6 @@ class BEBlock(nn.Module):
 
     def _forward_autograd(self, x):
         """Differentiable form of the block (E.py:50-85) on NCHW tensors; convs on the tensor-core kernels."""
-        tc.require_fp32_library_convs()
         n, c, h, w = x.shape
         dev = x.device
         w1 = F.linear(_mean_std(x), self.inver_mod1.weight, self.inver_mod1.bias)                 # :51-54
@@ -174,11 +173,10 @@ class BE(nn.Module):
 
     def _forward_autograd(self, x, block_num):
         """Training path: same data flow as `forward`, recorded for backward (see the module docstring)."""
-        tc.require_fp32_library_convs()
         c = self.FromRGB.from_rgb
         if not c.implicit_lreq:
             raise NotImplementedError('training path: explicit lreq scaling is not used by the reference (lreq.py:23-24)')
-        f = F.leaky_relu(F.conv2d(x, c.weight, c.bias), 0.2)          # net.py:231-240 (3 input channels: point-wise)
+        f = F.leaky_relu(tc.lib_conv2d(x, c.weight, c.bias), 0.2)          # net.py:231-240 (3 input channels: point-wise)
         w = torch.tensor(0)
         for i in range(9 - block_num, self.layer_count):
             f, w1, w2 = self.decode_block[i]._forward_autograd(f)

@@ -113,7 +113,6 @@ class BEBlock(nn.Module):
 
     def forward(self, x, cond_vector, truncation=0.4):
         if _wants_grad(self, x):
-            tc.require_fp32_library_convs()
             return self._forward_autograd(x.float(), cond_vector.float(), truncation), 0, 0
         ln._guard('E_BIG.BEBlock', x, cond_vector, self.conv_1.weight)
         return self.run(ops.nchw_to_f32b(x.float()), cond_vector.float().contiguous(), truncation).to_nchw(), 0, 0
@@ -155,10 +154,9 @@ class BE(nn.Module):
         return f.to_nchw()
 
     def _features_autograd(self, x, cond_vector, block_num=9):
-        tc.require_fp32_library_convs()
         cv = cond_vector.float()
         c = self.FromRGB.from_rgb
-        f = F.leaky_relu(F.conv2d(x.float(), c.weight, c.bias), 0.2)                                      # :84-92
+        f = F.leaky_relu(tc.lib_conv2d(x.float(), c.weight, c.bias), 0.2)                                      # :84-92
         for i in range(9 - block_num, self.layer_count):
             f = self.decode_block[i]._forward_autograd(f, cv, truncation=0.4)
         return f

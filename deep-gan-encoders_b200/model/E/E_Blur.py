@@ -101,7 +101,6 @@ class BEBlock(nn.Module):
 
     def _forward_autograd(self, x):
         """Differentiable form of the block (E_Blur.py:50-85) on NCHW tensors."""
-        tc.require_fp32_library_convs()
         n, c, h, w = x.shape
         dev = x.device
         w1 = F.linear(_mean_std(x), self.inver_mod1.weight, self.inver_mod1.bias)
@@ -111,11 +110,11 @@ class BEBlock(nn.Module):
         w2 = F.linear(_mean_std(y), self.inver_mod2.weight, self.inver_mod2.bias)
         y = F.instance_norm(y, eps=self.instance_norm_2.eps)
         if self.has_last_conv:
-            y = F.conv2d(y, self.blur.weight, groups=self.blur.groups, padding=1)                  # :71
+            y = tc.lib_conv2d(y, self.blur.weight, groups=self.blur.groups, padding=1)                  # :71
             if self.fused_scale:                                                                   # :72, lreq.py:144-156
                 k = F.pad(self.conv_2.weight, (1, 1, 1, 1))
                 k = (k[:, :, 1:, 1:] + k[:, :, :-1, 1:] + k[:, :, 1:, :-1] + k[:, :, :-1, :-1]) * 0.25
-                y = F.conv2d(y, k, stride=2, padding=1)
+                y = tc.lib_conv2d(y, k, stride=2, padding=1)
             else:
                 y = tc.conv2d(y, self.conv_2.weight, self.planes)
             nh, nw = y.shape[2], y.shape[3]
@@ -163,11 +162,10 @@ class BE(nn.Module):
             b.noise_mode = mode
 
     def _forward_autograd(self, x, block_num):
-        tc.require_fp32_library_convs()
         c = self.FromRGB.from_rgb
         if not c.implicit_lreq:
             raise NotImplementedError('training path: explicit lreq scaling is not used by the reference (lreq.py:23-24)')
-        f = F.leaky_relu(F.conv2d(x, c.weight, c.bias), 0.2)
+        f = F.leaky_relu(tc.lib_conv2d(x, c.weight, c.bias), 0.2)
         w = torch.tensor(0)
         for i in range(9 - block_num, self.layer_count):
             f, w1, w2 = self.decode_block[i]._forward_autograd(f)

@@ -58,7 +58,7 @@ def _conv_autograd(x, w, b, planes):
     if w.shape[0] % 16 == 0 and w.shape[1] % 16 == 0:
         y = tc.conv2d(x, w, planes)
     else:
-        y = F.conv2d(x, w, padding=k // 2)
+        y = tc.lib_conv2d(x, w, padding=k // 2)
     return y if b is None else y + b.view(1, -1, 1, 1)
 
 
@@ -77,7 +77,7 @@ class _Prep:
         self.key, self.val = None, None
 
     def get(self, module, tensors, build):
-        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        key = ops.weight_key(*tensors)
         if module.training or key != self.key:
             self.val, self.key = build(), key
         return self.val
@@ -316,7 +316,6 @@ class Generator(nn.Module):
 
     def _forward_autograd(self, cond_vector, truncation):
         """:232-256 recorded for backward w.r.t. the condition vector (frozen weights)."""
-        tc.require_fp32_library_convs()
         ch = self.config.channel_width
         x = F.linear(cond_vector, sn_weight(self.gen_z).detach(), self.gen_z.bias.detach())
         x = x.view(-1, 4, 4, 16 * ch).permute(0, 3, 1, 2).contiguous()

@@ -173,7 +173,7 @@ class ConvBlock(nn.Module):
         self._key, self._prep = None, None
 
     def _prepared(self):
-        key = (self.weight.data_ptr(), self.weight._version, self.planes)
+        key = (ops.weight_key(self.weight), self.planes)
         if key != self._key:
             d = {}
             w = self.weight.detach()

@@ -98,7 +98,7 @@ class DecodeBlock(nn.Module):
 
     def _conv1_packed(self):
         c = self.conv_1
-        key = (c.weight.data_ptr(), c.weight._version, self.planes)
+        key = (ops.weight_key(c.weight), self.planes)
         if getattr(self, '_c1_key', None) != key:
             scale = 1.0 if c.implicit_lreq else c.std
             if self.fused_scale:     # weight is [in, out, k, k] and used un-flipped by conv_transpose2d (lreq.py:127-140)
@@ -153,10 +153,10 @@ class DecodeBlock(nn.Module):
             if self.fused_scale:                                                           # lreq.py:127-140
                 w = F.pad(wgt(self.conv_1), (1, 1, 1, 1))
                 w = w[:, :, 1:, 1:] + w[:, :, :-1, 1:] + w[:, :, 1:, :-1] + w[:, :, :-1, :-1]
-                x = F.conv_transpose2d(x, w, stride=2, padding=1)
+                x = tc.lib_conv_transpose2d(x, w, stride=2, padding=1)
             else:                                                                          # upscale2d :37-43, conv :145
                 x = tc.conv2d(F.interpolate(x, scale_factor=2, mode='nearest'), wgt(self.conv_1), self.planes)
-            x = F.conv2d(x, self.blur.weight, groups=self.blur.groups, padding=1)          # :48-58
+            x = tc.lib_conv2d(x, self.blur.weight, groups=self.blur.groups, padding=1)          # :48-58
         n, _, h, w_ = x.shape
         x = torch.addcmul(x, self.noise_weight_1.detach(), self._noise(n, h, w_, x.device))    # :148 (batch 1 in block 0)
         x = F.instance_norm(F.leaky_relu(x + self.bias_1.detach(), 0.2), eps=self.instance_norm_1.eps)
@@ -245,14 +245,13 @@ class Generator(nn.Module):
 
     def _decode_autograd(self, styles, lod):
         """Training path of `decode` (:331-336): recorded for backward w.r.t. `styles`; see the module docstring."""
-        tc.require_fp32_library_convs()
         styles = styles.float()
         x = self.const.detach().float()
         for i in range(lod + 1):
             x = self.decode_block[i]._forward_autograd(x, styles[:, 2 * i + 0], styles[:, 2 * i + 1])
         c = self.to_rgb[lod].to_rgb
         w = c.weight.detach() if c.implicit_lreq else c.weight.detach() * c.std
-        return F.conv2d(x, w, c.scaled_bias())                                             # :244-253
+        return tc.lib_conv2d(x, w, c.scaled_bias())                                             # :244-253
 
     def decode(self, styles, lod, noise=0):
         if torch.is_grad_enabled() and styles.requires_grad:
@@ -284,7 +283,7 @@ def _staged(module, name, t, dev):
     if t is None or t.device == dev:
         return t
     cache = module.__dict__.setdefault('_dge_staged', {})
-    key = (t.data_ptr(), t._version, str(dev))
+    key = (ops.weight_key(t), str(dev))
     hit = cache.get(name)
     if hit is None or hit[0] != key:
         hit = (key, t.detach().to(dev))

@@ -57,7 +57,7 @@ class _Cache:
         self.key, self.val = None, None
 
     def get(self, tensors, build):
-        key = tuple((t.data_ptr(), t._version, t.device) for t in tensors)
+        key = ops.weight_key(*tensors)
         if key != self.key:
             self.val = build()
             self.key = key
@@ -405,12 +405,12 @@ class ModulateConvBlock(nn.Module):
         wgt = self.weight.detach() * self.wscale                                                   # :858
         xs = x * style.view(n, self.in_c, 1, 1)                                                    # :877
         if self.use_conv2d_transpose:
-            y = F.conv_transpose2d(xs, wgt.flip(2, 3).transpose(0, 1), stride=2)                   # :879-895
+            y = tc.lib_conv_transpose2d(xs, wgt.flip(2, 3).transpose(0, 1), stride=2)                   # :879-895
             y = _fir4(y, self.filter.kernel, (1, 1, 1, 1))                                         # :896
         elif self.ksize == 3 and self.in_c % 16 == 0 and self.out_c % 16 == 0:
             y = tc.conv2d(xs, wgt, self.planes)                                                    # :897-904 (tcgen05)
         else:
-            y = F.conv2d(xs, wgt, padding=self.ksize // 2)                                         # ToRGB (3 outputs)
+            y = tc.lib_conv2d(xs, wgt, padding=self.ksize // 2)                                         # ToRGB (3 outputs)
         if self.demodulate:
             d = torch.rsqrt((wgt.square().sum(dim=(2, 3))[None] * style.square()[:, None]).sum(dim=2) + self.eps)
             y = y * d.view(n, self.out_c, 1, 1)                                                    # :867-870, 908-909
@@ -448,7 +448,7 @@ def _fir4(x, kernel, pad):
     """Depth-wise 4x4 FIR of an NCHW tensor after zero padding `pad` (left, right, top, bottom) -- UpsamplingLayer
     :592-615 (training path only; the inference kernels fuse it)."""
     n, c, h, w = x.shape
-    y = F.conv2d(F.pad(x.reshape(n * c, 1, h, w), pad), kernel.to(x))
+    y = tc.lib_conv2d(F.pad(x.reshape(n * c, 1, h, w), pad), kernel.to(x))
     return y.view(n, c, y.shape[2], y.shape[3])
 
 
@@ -593,7 +593,6 @@ class SynthesisModule(nn.Module):
 
     def _forward_autograd(self, wp, randomize_noise=False):
         """Training path: the same result dict, recorded for backward w.r.t. `wp` (see the module docstring)."""
-        tc.require_fp32_library_convs()
         n, nl = wp.shape[0], self.num_layers
         wp32 = wp.float()
         results = {'wp': wp}

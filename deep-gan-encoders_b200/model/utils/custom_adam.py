@@ -88,4 +88,7 @@ class LREQAdam(Optimizer):
                                                    vp(plan['numel']), vp(step_t), vp(plan['blk_t']), vp(plan['blk_o']),
                                                    plan['n_blocks'], _CHUNK, float(group['beta_2']),
                                                    float(group['eps']), ops._stream()))
+        # the kernel writes the parameters through raw pointers (no torch version bump): retire every tensor derived
+        # from them (packed conv weights etc.) -- see ops.weight_key
+        ops.invalidate_weight_caches()
         return loss

@@ -142,7 +142,7 @@ class Conv2d(nn.Module):
 
     def packed(self, planes=2):
         """WPK weights, cached per parameter version (the weights change every optimiser step)."""
-        key = (self.weight.data_ptr(), self.weight._version, planes)
+        key = (ops.weight_key(self.weight), planes)
         if getattr(self, '_wpk_key', None) != key:
             scale = 1.0 if self.implicit_lreq else self.std
             self._wpk = ops.pack_conv_weight(self.weight, scale=scale, planes=planes)
@@ -153,7 +153,7 @@ class Conv2d(nn.Module):
         """`transform_kernel` strided conv (lreq.py:144-147): W4 = 0.25 * (sum of the four 1-pixel shifts of the zero-padded
         3x3 kernel), used with stride 2 / padding 1 -> 16-tap WPK for DGE_CONV_DOWN4X4S2."""
         assert self.transform_kernel and not self.transpose and self.stride == (2, 2) and self.kernel_size == (3, 3)
-        key = (self.weight.data_ptr(), self.weight._version, planes, 'down4')
+        key = (ops.weight_key(self.weight), planes, 'down4')
         if getattr(self, '_wpk4_key', None) != key:
             w = torch.nn.functional.pad(self.weight.detach(), (1, 1, 1, 1))
             w4 = (w[:, :, 1:, 1:] + w[:, :, :-1, 1:] + w[:, :, 1:, :-1] + w[:, :, :-1, :-1]) * 0.25

@@ -1,6 +1,8 @@
 """Drop-in for the reference's `training_utils.py`: `space_loss` (:54-99) as fused device reductions, plus the
 small host helpers the scripts import (`set_seed` :46-51, `truncated_noise_sample` :32-44, `one_hot` :27-30,
-`get_parameter_number` :17-20).
+`get_parameter_number` :17-20, `imgPath2loader` / `loader` :10-15, `get_para_GByte` :22-25).  The scripts do
+`from training_utils import *` and rely on the names that leaks (`torchvision`, `Image`, `truncnorm`, `F`, `np`,
+`torch`, `pytorch_ssim`), so the same modules are imported at module level here.
 
 `space_loss` semantics kept: MSE / mean-MSE / std-MSE (unbiased std), implicit-dim softmax KL (logged only,
 NaN -> 0, inf -> 1), cosine over the flattened WHOLE batch, avg-pool while H > 256, SSIM, LPIPS through the
@@ -13,10 +15,27 @@ import math
 
 import numpy as np
 import torch
-import torch.nn.functional as F
+import torchvision
+from PIL import Image
+from scipy.stats import truncnorm
+from torch.nn import functional as F
 
 import metric.pytorch_ssim as pytorch_ssim
 from dge_b200 import ops
+
+# host-side image loading (embedding_img.py:214, embedding_v2_*.py): PIL file -> RGB -> size x size -> [3, size, size] in [0, 1]
+loader = torchvision.transforms.Compose([torchvision.transforms.ToTensor()])
+
+
+def imgPath2loader(image_name, size):
+    image = Image.open(image_name).convert('RGB').resize((size, size))
+    return loader(image).to(torch.float)
+
+
+def get_para_GByte(parameter_number):
+    # the reference reports the TOTAL count under both keys (and spells the second one 'Trainable_BG'), :22-25
+    gb = parameter_number['Total'] * 8 / 1024 / 1024 / 1024
+    return {'Total_GB': gb, 'Trainable_BG': gb}
 
 
 def get_parameter_number(net):
@@ -30,7 +49,6 @@ def one_hot(x, class_count=1000):
 
 
 def truncated_noise_sample(batch_size=1, dim_z=128, truncation=1., seed=None):
-    from scipy.stats import truncnorm
     state = None if seed is None else np.random.RandomState(seed)
     values = truncnorm.rvs(-2, 2, size=(batch_size, dim_z), random_state=state).astype(np.float32)
     return truncation * values

@@ -146,7 +146,7 @@ def test_biggan_and_lpips_under_split_precision(emulated_conv):
     assert rel(z.grad, z_r.grad) < 2e-4
 
     torch.manual_seed(0)
-    m = lpips.LPIPS(net="vgg", verbose=False)
+    m = lpips.LPIPS(net="vgg", pretrained=False, pnet_rand=True, verbose=False)
     with torch.no_grad():
         for k in range(5):
             getattr(m, f"lin{k}").model[1].weight.abs_()

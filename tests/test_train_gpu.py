@@ -338,7 +338,7 @@ def test_lpips_vgg_distance_and_gradient_vs_oracle():
     import lpips
     from oracle import lpips as olp
     torch.manual_seed(0)
-    m = lpips.LPIPS(net="vgg", verbose=False)
+    m = lpips.LPIPS(net="vgg", pretrained=False, pnet_rand=True, verbose=False)
     with torch.no_grad():
         for k in range(5):
             getattr(m, f"lin{k}").model[1].weight.abs_()

@@ -197,7 +197,7 @@ def test_lpips_structure_matches_oracle_and_torchvision(aten_conv):
     from oracle import lpips as olp
     from torchvision.models import vgg16
     torch.manual_seed(0)
-    m = lpips.LPIPS(net="vgg", verbose=False)
+    m = lpips.LPIPS(net="vgg", pretrained=False, pnet_rand=True, verbose=False)
     with torch.no_grad():
         for k in range(5):
             getattr(m, f"lin{k}").model[1].weight.abs_()
