@@ -107,6 +107,11 @@ SIGNATURES = {
     "dge_argmax_mode": (c_int, [P, c_int, c_int, P, P, P]),
     "dge_gradcam": (c_int, [P, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "dge_mask2cam": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P]),
+    "dge_be_head_bwd": (c_int, [P, P, P, c_float, c_float, c_float, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "dge_in_bwd_stats": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P]),
+    "dge_in_bwd_apply": (c_int, [P, P, P, P, P, P, c_int, P, c_float, c_int, P, c_float, P, P, P, c_int, c_int, c_int,
+                                 c_int, c_int, P]),
+    "dge_from_rgb_bwd": (c_int, [P, P, P, c_float, P, c_int, c_int, c_int, c_int, c_int, P]),
     "dge_blend": (c_int, [P, P, P, c_float, c_float, c_int, c_int, c_int, c_int, c_int, P]),
 }
 

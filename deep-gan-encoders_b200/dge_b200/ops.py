@@ -425,6 +425,27 @@ def from_rgb_stats(img, w, b, slope=0.2, eps=1e-8):
     return out, style, mr
 
 
+def from_rgb_stats_any(img, w, b, slope=0.2, eps=1e-8):
+    """FromRGB + instance statistics for any width: the one-pass kernel for c in (16, 32), else two kernels."""
+    if w.shape[0] in (16, 32):
+        return from_rgb_stats(img, w, b, slope, eps)
+    f = from_rgb(img, w, b, slope)
+    return (f,) + instance_stats(f, eps)
+
+
+def scale_f32b(x, a, to_act=False, planes=2):
+    """a * x on an F32B map (tiny maps of the last encoder block), optionally as an ACT operand."""
+    assert isinstance(x, F32B)
+    y = F32B.wrap(x.t * float(a), x.n, x.c, x.h, x.w)
+    return f32b_to_act(y, planes) if to_act else y
+
+
+def f32b_channel_sums(x):
+    """[c] = sum over (n, h, w) of an F32B map (tiny maps only: a torch reduction)."""
+    assert isinstance(x, F32B)
+    return x.t.sum(dim=(0, 2, 3)).reshape(-1)
+
+
 def instance_norm_pool(x, mean_rstd, planes=2):
     """IN(x) -> ACT and avg_pool2d(x, 2, 2) -> ACT in one pass over x."""
     assert isinstance(x, F32B)
@@ -599,6 +620,70 @@ def blend(a_src, b_src, a, b, pool):
         check(lib().dge_blend(_p(a_src.t), _p(b_src.t), _p(out.t), float(a), float(b), int(pool), a_src.n, a_src.c, ho,
                               wo, _stream()))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# training step: point-wise / reduction backward kernels (csrc/train_bwd.cu)
+# ------------------------------------------------------------------------------------------------
+def be_head_bwd(d_out, y2, noise, ga, gb, slope, want_dres=True, planes=2):
+    """Backward of an encoder block's tail (E.py:72-84) -> (dy2 Act, dres Act | None, sums fp32 [3, co])."""
+    assert isinstance(d_out, F32B) and isinstance(y2, F32B)
+    assert (y2.n, y2.c, y2.h, y2.w) == (d_out.n, d_out.c, 2 * d_out.h, 2 * d_out.w), "be_head_bwd: geometry mismatch"
+    dev = y2.t.device
+    dy2 = Act(y2.n, y2.c, y2.h, y2.w, planes, dev)
+    dres = Act(d_out.n, d_out.c, d_out.h, d_out.w, planes, dev) if want_dres else None
+    sums = torch.empty((3, y2.c), dtype=torch.float32, device=dev)
+    with _rec("be_head_bwd", (y2.n, y2.h, y2.w, y2.c, planes)):
+        check(lib().dge_be_head_bwd(_p(d_out.t), _p(y2.t), _f32(noise), float(ga), float(gb), float(slope), _p(dy2.t),
+                                    _p(dres.t) if dres is not None else None, _p(sums), y2.n, y2.c, y2.h, y2.w, planes,
+                                    _stream()))
+    return dy2, dres, sums
+
+
+def in_bwd_stats(g, x, mean_rstd):
+    """Reduction pass of the instance-norm backward -> fp64 [n, c, 2] = (sum g, sum g*xn)."""
+    assert isinstance(g, F32B) and isinstance(x, F32B) and (g.n, g.c, g.h, g.w) == (x.n, x.c, x.h, x.w)
+    sums = torch.empty((x.n, x.c, 2), dtype=torch.float64, device=x.t.device)
+    with _rec("in_bwd_stats", (x.n, x.h, x.w, x.c)):
+        check(lib().dge_in_bwd_stats(_p(g.t), _p(x.t), _f32(mean_rstd), _p(sums), x.n, x.c, x.h, x.w, _stream()))
+    return sums
+
+
+def in_bwd_apply(g, x, mean_rstd, style, dstyle, sums, mode, res=None, rscale=0.0, res_pool=False, noise=None,
+                 slope=0.2, planes=2):
+    """Apply pass of the instance-norm backward.  mode 0 -> F32B dx (+ rscale*res); mode 1 -> (Act dx*lrelu'(x),
+    sums2 fp32 [2, c] = bias / noise-weight gradients)."""
+    assert isinstance(g, F32B) and isinstance(x, F32B) and (g.n, g.c, g.h, g.w) == (x.n, x.c, x.h, x.w)
+    dev = x.t.device
+    ds = None if dstyle is None else dstyle.contiguous()
+    if mode == 0:
+        out = F32B(x.n, x.c, x.h, x.w, dev)
+        if res is not None:
+            assert isinstance(res, F32B) and res.c == x.c and res.n == x.n
+            assert (res.h, res.w) == ((x.h // 2, x.w // 2) if res_pool else (x.h, x.w)), "in_bwd_apply: residual size"
+        with _rec("in_bwd_apply0", (x.n, x.h, x.w, x.c)):
+            check(lib().dge_in_bwd_apply(_p(g.t), _p(x.t), _f32(mean_rstd), _f32(style), _f32(ds), _p(sums), 0,
+                                         _p(res.t) if res is not None else None, float(rscale), int(bool(res_pool)), None,
+                                         float(slope), _p(out.t), None, None, x.n, x.c, x.h, x.w, planes, _stream()))
+        return out
+    out = Act(x.n, x.c, x.h, x.w, planes, dev)
+    sums2 = torch.empty((2, x.c), dtype=torch.float32, device=dev)
+    with _rec("in_bwd_apply1", (x.n, x.h, x.w, x.c, planes)):
+        check(lib().dge_in_bwd_apply(_p(g.t), _p(x.t), _f32(mean_rstd), _f32(style), _f32(ds), _p(sums), 1, None, 0.0, 0,
+                                     _f32(noise), float(slope), None, _p(out.t), _p(sums2), x.n, x.c, x.h, x.w, planes,
+                                     _stream()))
+    return out, sums2
+
+
+def from_rgb_bwd(d_f, f, img, slope=0.2):
+    """FromRGB backward -> fp32 [c, 4] = (dW[c, 0..2], db[c])."""
+    assert isinstance(d_f, F32B) and isinstance(f, F32B)
+    img = img.contiguous()
+    sums = torch.empty((f.c, 4), dtype=torch.float32, device=f.t.device)
+    with _rec("from_rgb_bwd", (f.n, f.h, f.w, f.c)):
+        check(lib().dge_from_rgb_bwd(_p(d_f.t), _p(f.t), _f32(img), float(slope), _p(sums), f.n, img.shape[1], f.c, f.h,
+                                     f.w, _stream()))
+    return sums
 
 
 def launch_count():

@@ -1,0 +1,230 @@
+"""Fused training path of the case-1 encoder (model/E/E.py:50-135 under `loss.backward()`, E_align_s2.py:152-221).
+
+One autograd node per encoder block instead of ~25 ATen nodes.  Tensors travel between the nodes in the kernels' own
+layout (F32B, fp32 [N][C/8][H][W][8]); a node's forward is the inference chain of `BEBlock.run` (stats -> IN -> tcgen05
+conv with fused noise/bias/lrelu -> ... -> 1x1 residual conv with the pool + blend epilogue) and its backward is
+
+    be_head_bwd      d_out -> ga/4 * lrelu' -> ACT operand (+ bias_2 / noise_weight_2 / conv_3.bias gradients)
+    conv_wgrad       conv_2.weight.grad                       dge_conv_forward (dgrad operand) -> d(IN_2 output)
+    in_bwd_stats / in_bwd_apply (mode 1)   IN_2 Jacobian + style_2 (mean, std) gradient + lrelu' -> ACT operand
+                                           (+ bias_1 / noise_weight_1 gradients)
+    conv_wgrad       conv_1.weight.grad                       dge_conv_forward (dgrad operand) -> d(IN_1 output)
+    conv_wgrad / dge_conv_forward          conv_3 (1x1 residual): weight gradient, data gradient
+    in_bwd_stats / in_bwd_apply (mode 0)   IN_1 Jacobian + style_1 gradient + pooled residual gradient -> d_x (F32B)
+
+i.e. 11 launches per block, every one a dge_b200 kernel.  The two `inver_mod` Linear layers stay torch ops on the
+[N, 2C] style vectors the node returns (two tiny GEMMs per block).  `K` is the kernel namespace (dge_b200.ops); the CPU
+tests swap it for a torch emulation of the same C-ABI functions to check the chain rule without a GPU.
+"""
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import ops
+
+K = ops          # kernel namespace (tests/emu_ops.py replaces it on the CPU)
+
+GA, GB = 0.111, 0.889          # E.py:84
+SLOPE = 0.2                    # E.py:62,75; net.py:239
+
+
+def _f32b(t):
+    n, c8, h, w, _ = t.shape
+    return K.F32B.wrap(t, n, c8 * 8, h, w)
+
+
+class _FromRGBFn(torch.autograd.Function):
+    """img NCHW -> (f F32B tensor, style0, mean_rstd0): net.py:231-240 + the first block's statistics (E.py:51-53)."""
+
+    @staticmethod
+    def forward(ctx, img, weight, bias, eps):
+        f, style, mr = K.from_rgb_stats_any(img, weight, bias, SLOPE, eps)
+        ctx.save_for_backward(img, f.t, weight)
+        ctx.mark_non_differentiable(style, mr)
+        return f.t, style, mr
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_f, _ds, _dmr):
+        img, f_t, weight = ctx.saved_tensors
+        sums = K.from_rgb_bwd(_f32b(d_f.contiguous()), _f32b(f_t), img, SLOPE)
+        cimg = img.shape[1]
+        dw = sums[:, :cimg].reshape(weight.shape)
+        db = sums[:, 3].contiguous()
+        d_img = None
+        if ctx.needs_input_grad[0]:
+            # only a caller that optimises the input image itself gets here (none of the encoder scripts does):
+            # d_img = W^T (d_f * lrelu'(f)) as two small torch ops on the NCHW views
+            dpre = _f32b(d_f.contiguous()).to_nchw() * torch.where(_f32b(f_t).to_nchw() > 0, 1.0, SLOPE)
+            d_img = torch.einsum('nchw,ci->nihw', dpre, weight.view(weight.shape[0], cimg))
+        return d_img, dw, db, None
+
+
+class _BEBlockFn(torch.autograd.Function):
+    """One BEBlock (E.py:50-85).  Inputs: x (F32B tensor), optional precomputed (style1, mean_rstd1), the block's
+    parameters.  Outputs: (out F32B tensor, style1 [N, 2C], style2 [N, 2C])."""
+
+    @staticmethod
+    def forward(ctx, x_t, pre_style, pre_mr, w1, w2, w3, b3, nw1, b1, nw2, b2, cfg):
+        has_last, planes, eps1, eps2, noise1, noise2 = cfg
+        x = _f32b(x_t)
+        n, c, h, w = x.n, x.c, x.h, x.w
+        cout = w2.shape[0] if has_last else (w3.shape[0] if w3 is not None else c)
+        if pre_style is not None:
+            style1, mr1 = pre_style, pre_mr
+        else:
+            style1, mr1 = K.instance_stats(x, eps1)                                            # E.py:51-53 + IN stats
+        rp = None
+        if has_last and w3 is not None:
+            xn, rp = K.instance_norm_pool(x, mr1, planes=planes)                               # :58 and :78
+        else:
+            xn, _ = K.instance_norm(x, mr1, planes=planes)                                     # :58
+        y1 = K.conv(xn, K.pack_conv_weight(w1, planes=planes), c, K.CONV_3X3, noise=noise1, noise_batched=True,
+                    noise_w=nw1.detach().reshape(-1), bias=b1.detach().reshape(-1), slope=SLOPE, out_f32b=True)['f32b']
+        style2, mr2 = K.instance_stats(y1, eps2)                                               # :64-66
+        y2 = None
+        if has_last:
+            y1n, _ = K.instance_norm(y1, mr2, planes=planes)                                   # :69
+            # training keeps the full-resolution activated conv_2 output: its sign is the leaky-ReLU mask of the backward
+            y2 = K.conv(y1n, K.pack_conv_weight(w2, planes=planes), cout, K.CONV_3X3, noise=noise2, noise_batched=True,
+                        noise_w=nw2.detach().reshape(-1), bias=b2.detach().reshape(-1), slope=SLOPE,
+                        out_f32b=True)['f32b']                                                  # :72-75
+            if w3 is not None:
+                out = K.conv(rp, K.pack_conv_weight(w3, planes=planes), cout, K.CONV_1X1, bias=b3.detach(),
+                             blend_src=y2, blend_pool=True, blend_a=GA, blend_b=GB, out_f32b=True)['f32b']   # :76-84
+            else:
+                out = K.blend(y2, x, GA, GB, pool=3)
+        else:
+            y1n = None
+            _, y1n_f = K.instance_norm(y1, mr2, out_act=False, out_f32b=True)                  # :69
+            if w3 is not None:
+                rp = K.f32b_to_act(x, planes)
+                out = K.conv(rp, K.pack_conv_weight(w3, planes=planes), cout, K.CONV_1X1, bias=b3.detach(),
+                             blend_src=y1n_f, blend_pool=False, blend_a=GA, blend_b=GB, out_f32b=True)['f32b']
+            else:
+                out = K.blend(y1n_f, x, GA, GB, pool=False)
+        ctx.cfg = (has_last, planes, (n, c, h, w), cout)
+        ctx.has = (w3 is not None, y1n is not None, rp is not None, y2 is not None)
+        saved = [x_t, mr1, style1, xn.t, y1.t, mr2, style2, noise1, w1]
+        if has_last:
+            saved += [y1n.t, y2.t, noise2, w2]
+        if w3 is not None:
+            saved += [rp.t, w3]
+        ctx.save_for_backward(*saved)
+        s1 = style1.clone() if pre_style is not None else style1
+        return out.t, s1, style2
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_out_t, d_style1, d_style2):
+        has_last, planes, (n, c, h, w), cout = ctx.cfg
+        has_w3 = ctx.has[0]
+        sv = list(ctx.saved_tensors)
+        x_t, mr1, style1, xn_t, y1_t, mr2, style2, noise1, w1 = sv[:9]
+        p = 9
+        if has_last:
+            y1n_t, y2_t, noise2, w2 = sv[p:p + 4]
+            p += 4
+        if has_w3:
+            rp_t, w3 = sv[p:p + 2]
+        x, y1 = _f32b(x_t), _f32b(y1_t)
+        xn = K.Act.wrap(xn_t, n, c, h, w, planes)
+        d_out = _f32b(d_out_t.contiguous())
+        dw2 = dnw2 = db2 = dw3 = db3 = None
+        if has_last:
+            y2 = _f32b(y2_t)
+            dy2, dres, s = K.be_head_bwd(d_out, y2, noise2, GA, GB, SLOPE, want_dres=has_w3, planes=planes)
+            db2, dnw2 = s[0].view(1, -1, 1, 1), s[1].view(1, -1, 1, 1)
+            if has_w3:
+                db3 = s[2]
+            dw2 = K.conv_wgrad(dy2, K.Act.wrap(y1n_t, n, c, h, w, planes), 3)
+            g1 = K.conv(dy2, K.pack_conv_weight_dgrad(w2, planes=planes), c, K.CONV_3X3, out_f32b=True)['f32b']
+            del dy2
+        else:
+            g1 = K.scale_f32b(d_out, GA)                       # out = GA * IN_2(y1) + GB * residual  (E.py:69,84)
+            dres = None
+            if has_w3:
+                dres = K.scale_f32b(d_out, GB, to_act=True, planes=planes)
+                db3 = GB * K.f32b_channel_sums(d_out)
+        # IN_2 + the style (mean, std) of y1 + lrelu' of conv_1's activation  ->  operand of conv_1's gradients
+        st2 = K.in_bwd_stats(g1, y1, mr2)
+        dy1, s = K.in_bwd_apply(g1, y1, mr2, style2, d_style2, st2, 1, noise=noise1, slope=SLOPE, planes=planes)
+        db1, dnw1 = s[0].view(1, -1, 1, 1), s[1].view(1, -1, 1, 1)
+        del g1
+        dw1 = K.conv_wgrad(dy1, xn, 3)
+        g0 = K.conv(dy1, K.pack_conv_weight_dgrad(w1, planes=planes), c, K.CONV_3X3, out_f32b=True)['f32b']
+        del dy1
+        # residual branch (E.py:78-84)
+        if has_w3:
+            rh, rw = (h // 2, w // 2) if has_last else (h, w)
+            dw3 = K.conv_wgrad(dres, K.Act.wrap(rp_t, n, c, rh, rw, planes), 1)
+            d_rp = K.conv(dres, K.pack_conv_weight_dgrad(w3, planes=planes), c, K.CONV_1X1, out_f32b=True)['f32b']
+            rscale = 0.25 if has_last else 1.0
+        else:
+            d_rp, rscale = d_out, GB * (0.25 if has_last else 1.0)
+        st1 = K.in_bwd_stats(g0, x, mr1)
+        d_x = K.in_bwd_apply(g0, x, mr1, style1, d_style1, st1, 0, res=d_rp, rscale=rscale, res_pool=has_last)
+        return d_x.t, None, None, dw1, dw2, dw3, db3, dnw1, db1, dnw2, db2, None
+
+
+class _F32BToNCHW(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t):
+        return _f32b(t).to_nchw()
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        return K.nchw_to_f32b(g.contiguous().float()).t
+
+
+class _NCHWToF32B(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return K.nchw_to_f32b(x.contiguous().float()).t
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        return _f32b(g.contiguous()).to_nchw()
+
+
+def nchw_to_f32b(x):
+    return _NCHWToF32B.apply(x)
+
+
+def f32b_to_nchw(t):
+    return _F32BToNCHW.apply(t)
+
+
+def block_forward(block, x_t, pre=None):
+    """BEBlock under autograd on an F32B tensor -> (out F32B tensor, w1, w2)  (E.py:50-85)."""
+    n, _, h, w, _ = x_t.shape
+    dev = x_t.device
+    noise1 = block._noise(n, h, w, dev).reshape(n, h, w).contiguous()                          # E.py:60 (RNG order kept)
+    noise2 = block._noise(n, h, w, dev).reshape(n, h, w).contiguous() if block.has_last_conv else None   # :73
+    has_w3 = block.inputs != block.outputs
+    cfg = (block.has_last_conv, block.planes, block.instance_norm_1.eps, block.instance_norm_2.eps, noise1, noise2)
+    pre_style, pre_mr = pre if pre is not None else (None, None)
+    out_t, style1, style2 = _BEBlockFn.apply(
+        x_t, pre_style, pre_mr, block.conv_1.weight, block.conv_2.weight if block.has_last_conv else None,
+        block.conv_3.weight if has_w3 else None, block.conv_3.bias if has_w3 else None, block.noise_weight_1,
+        block.bias_1, block.noise_weight_2, block.bias_2, cfg)
+    lin = torch.nn.functional.linear
+    w1 = lin(style1, block.inver_mod1.weight, block.inver_mod1.bias)                           # :54
+    w2 = lin(style2, block.inver_mod2.weight, block.inver_mod2.bias)                           # :67
+    return out_t, w1, w2
+
+
+def encoder_forward(E, x, block_num=9):
+    """`BE.forward` (E.py:122-135) recorded for backward with one fused node per block."""
+    conv = E.FromRGB.from_rgb
+    first = 9 - block_num
+    eps0 = E.decode_block[first].instance_norm_1.eps if first < E.layer_count else 1e-8
+    f_t, style0, mr0 = _FromRGBFn.apply(x.float().contiguous(), conv.weight, conv.bias, eps0)
+    w = torch.tensor(0)
+    n = x.shape[0]
+    for i in range(first, E.layer_count):
+        f_t, w1, w2 = block_forward(E.decode_block[i], f_t, pre=(style0, mr0) if i == first else None)
+        w_ = torch.cat((w2.view(n, 1, 512), w1.view(n, 1, 512)), dim=1)                        # E.py:131
+        w = w_ if i == first else torch.cat((w_, w), dim=1)
+    return _F32BToNCHW.apply(f_t), w

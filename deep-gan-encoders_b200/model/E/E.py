@@ -9,10 +9,11 @@ Noise: the reference draws `torch.randn([N,1,H,W])` on the CPU inside each conv 
 `'device'` draws on the GPU instead (no H2D copy; different stream).
 
 Training (`loss.backward()` in E_align_s2.py:205, embedding_img.py:100-128): when autograd is recording and a
-parameter requires grad, `forward` builds a differentiable graph instead (`_forward_autograd`): every 3x3 / 1x1
-conv -- forward, data gradient and weight gradient -- runs on the tcgen05 kernels through dge_b200.autograd.conv2d;
-the point-wise and reduction steps between them are torch CUDA ops in this build (their fused backward kernels are
-the next row of SURVEY 8f-1).  Same noise draws, same return values.
+parameter requires grad, `forward` records ONE fused autograd node per block (dge_b200/train_e.py): the forward of a
+node is the same kernel chain as inference, its backward is 11 dge_b200 launches (tcgen05 data / weight gradients and the
+fused point-wise backward kernels of csrc/train_bwd.cu).  Same noise draws, same return values.
+`_forward_autograd` is the same computation as ~25 separate torch nodes per block with only the convs on the tcgen05
+kernels: it is kept as the cross-check of the fused path (tests) and is selected with `FUSED_TRAIN = False`.
 """
 import torch
 import torch.nn as nn
@@ -23,7 +24,10 @@ from model.utils.net import FromRGB
 from dge_b200 import autograd as tc
 from dge_b200 import ops
 
+from dge_b200 import train_e
+
 DEFAULT_PLANES = 2
+FUSED_TRAIN = True     # False: the unfused torch-node graph (`_forward_autograd`)
 
 
 class BEBlock(nn.Module):
@@ -121,6 +125,9 @@ class BEBlock(nn.Module):
     def forward(self, x):
         """Reference signature: NCHW in -> (NCHW out, w1, w2)."""
         if _wants_grad(self, x):
+            if FUSED_TRAIN:
+                out_t, w1, w2 = train_e.block_forward(self, train_e.nchw_to_f32b(x.float()))
+                return train_e.f32b_to_nchw(out_t), w1, w2
             return self._forward_autograd(x.float())
         ln._guard('BEBlock', x, self.conv_1.weight)
         out, w1, w2 = self.run(ops.nchw_to_f32b(x.float()))
@@ -186,6 +193,8 @@ class BE(nn.Module):
 
     def forward(self, x, block_num=9):
         if _wants_grad(self, x):
+            if FUSED_TRAIN and self.FromRGB.from_rgb.implicit_lreq:
+                return train_e.encoder_forward(self, x, block_num)
             return self._forward_autograd(x.float(), block_num)
         ln._guard('BE', x, self.FromRGB.from_rgb.weight)
         first = 9 - block_num

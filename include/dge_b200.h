@@ -301,6 +301,40 @@ int dge_gradcam(const float* feature, const float* gradient, int plus, double* w
 int dge_mask2cam(const double* mask, const float* img, const float* lut_rgb, float* heat, float* cam, float* scratch4,
                  int n, int h, int w, void* stream);
 
+/* ---- training step: point-wise / reduction backward kernels ----------------------- */
+/* These replace what torch.autograd runs for `loss.backward()` in E_align_s2.py:205,220 between the convolutions of
+   model/E/E.py:50-85.  Gradients arrive as F32B maps (what a data-gradient dge_conv_forward wrote) and leave as the ACT
+   operand of the next contraction; per-channel parameter gradients are reduced in the same pass.  Every `sums` output
+   is zeroed by the call and accumulated with atomics (run-to-run differences at the 1e-7 relative level). */
+
+/* Tail of an encoder block, backward (E.py:72-84: out = ga*avg_pool2d(lrelu(conv_2 + nw2*noise + b2)) + gb*residual).
+   d_out F32B [n][co/8][h/2][w/2][8]; y2 F32B [n][co/8][h][w][8] = the ACTIVATED conv_2 output (its sign is the
+   pre-activation's); noise [n][h][w] or NULL.
+   dy2_act  ACT [n][co/8][planes][h][w][8]     = ga/4 * d_out[y/2][x/2] * (y2 > 0 ? 1 : slope)   -> dgrad / wgrad of conv_2
+   dres_act ACT [n][co/8][planes][h/2][w/2][8] = gb * d_out  (NULL: not wanted)                   -> dgrad / wgrad of conv_3
+   sums fp32 [3][co]: sum dy2 (bias_2.grad), sum dy2*noise (noise_weight_2.grad), sum gb*d_out (conv_3.bias.grad) */
+int dge_be_head_bwd(const float* d_out, const float* y2, const float* noise, float ga, float gb, float slope,
+                    void* dy2_act, void* dres_act, float* sums, int n, int co, int h, int w, int planes, void* stream);
+/* Instance-norm backward, reduction pass (nn.InstanceNorm2d, E.py:58,69): sums fp64 [n][c][2] = (sum g, sum g*xn) over
+   h*w with xn = (x - mean)*rstd; g, x F32B; mean_rstd as written by dge_instance_stats. */
+int dge_in_bwd_stats(const float* g, const float* x, const float* mean_rstd, double* sums, int n, int c, int h, int w,
+                     void* stream);
+/* Instance-norm backward, apply pass.  dx = rstd*(g - mean(g) - xn*mean(g*xn))  [sums from dge_in_bwd_stats]
+                                           + dstyle[n][c]/HW + dstyle[n][C+c]*(x - mean)/(HW*std)
+   where style = mean || std [n][2c] is the block's second output (E.py:51-54, 64-67) and dstyle its gradient (NULL: none).
+   mode 0: dx += rscale * res  (res F32B at the same resolution, or half resolution read through the 2x2-pool broadcast when
+           res_pool; NULL: none) -> out_f32b                                            (block input; E.py:78-84 residual)
+   mode 1: dx *= (x > 0 ? 1 : slope) -> out_act [n][c/8][planes][h][w][8]; sums2 fp32 [2][c] = sum dx, sum dx*noise
+           (x = lrelu(conv_1 + nw1*noise + b1), E.py:60-62: bias_1.grad and noise_weight_1.grad) */
+int dge_in_bwd_apply(const float* g, const float* x, const float* mean_rstd, const float* style, const float* dstyle,
+                     const double* sums, int mode, const float* res, float rscale, int res_pool, const float* noise,
+                     float slope, float* out_f32b, void* out_act, float* sums2, int n, int c, int h, int w, int planes,
+                     void* stream);
+/* FromRGB backward (net.py:231-240, f = lrelu(conv1x1(img, W) + b)): sums fp32 [c][4] = (dW[c][0..2], db[c]) with
+   d_pre = d_f * (f > 0 ? 1 : slope); d_f, f F32B [n][c/8][h][w][8]; img NCHW [n][cimg<=3][h][w]. */
+int dge_from_rgb_bwd(const float* d_f, const float* f, const float* img, float slope, float* sums, int n, int cimg, int c,
+                     int h, int w, void* stream);
+
 /* ---- optimiser (model/utils/custom_adam.py:24-76, LREQAdam.step) ------------------------------ */
 /* One multi-tensor launch:  v = beta2*v + (1-beta2)*g*g ;  p -= step[t]*g/(sqrt(v)+eps)   (beta1 == 0).
    params/grads/vs: DEVICE arrays of n_tensors device pointers; numel/step: per-tensor DEVICE arrays

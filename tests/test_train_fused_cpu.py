@@ -1,0 +1,78 @@
+"""Chain rule of the FUSED training path (dge_b200/train_e.py, train_g.py) checked on the CPU: the kernel namespace is
+swapped for tests/emu_ops.py -- a plain-torch statement of each C-ABI function on the kernels' own layouts, including
+the bf16 hi + lo operand split -- and the resulting parameter gradients are held to the fixtures `loss.backward()`
+produced through the UNMODIFIED reference (tests/golden/make_golden.py).  The CUDA kernels are compared with the same
+emulation, function by function, on the GPU (tests/test_train_kernels_gpu.py)."""
+import os
+
+import pytest
+import torch
+
+import emu_ops
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rel(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-20)).item()
+
+
+@pytest.fixture()
+def emu(monkeypatch):
+    from dge_b200 import train_e
+    monkeypatch.setattr(train_e, "K", emu_ops)
+    return emu_ops
+
+
+def test_fused_encoder_matches_reference_gradients(emu):
+    from dge_b200 import train_e
+    from model.E.E import BE
+    fx = torch.load(os.path.join(GOLD, "be_s16_l4.pt"))
+    gx = torch.load(os.path.join(GOLD, "be_s16_l4_grads.pt"))
+    E = BE(**fx["config"])
+    E.load_state_dict(fx["state_dict"], strict=True)
+    torch.manual_seed(fx["noise_seed"])
+    const, w = train_e.encoder_forward(E, fx["img"], 9)
+    assert rel(const, fx["const"]) < 2e-4 and rel(w, fx["w"]) < 2e-4
+    (((const - gx["t_const"]) ** 2).mean() + ((w - gx["t_w"]) ** 2).mean()).backward()
+    got = {k: p.grad for k, p in E.named_parameters() if p.grad is not None}
+    assert set(got) == set(gx["grads"])
+    worst = {k: rel(got[k], g) for k, g in gx["grads"].items()}
+    bad = {k: v for k, v in worst.items() if v >= 1e-3}
+    assert not bad, bad
+
+
+def test_fused_encoder_second_backward_and_block_num(emu):
+    """E_align_s2.py:205,220: two backward passes over one recorded graph (retain_graph) and the progressive
+    `block_num` entry (E.py:122-135) give the gradients of the unfused graph."""
+    import torch.nn.functional as F
+    import model.E.E as EM
+    from dge_b200 import train_e
+    fx = torch.load(os.path.join(GOLD, "be_s16_l4.pt"))
+    E = EM.BE(**fx["config"])
+    E.load_state_dict(fx["state_dict"], strict=True)
+    torch.manual_seed(3)
+    const, w = train_e.encoder_forward(E, fx["img"], 9)
+    (const ** 2).mean().backward(retain_graph=True)
+    g1 = {k: p.grad.clone() for k, p in E.named_parameters() if p.grad is not None}
+    E.zero_grad()
+    (w ** 2).mean().backward()
+    g2 = {k: p.grad.clone() for k, p in E.named_parameters() if p.grad is not None}
+    E.zero_grad()
+    # the unfused graph with ATen convs on the same noise
+    orig = EM.tc.conv2d
+    EM.tc.conv2d = lambda x, w_, planes=2: F.conv2d(x, w_, padding=w_.shape[-1] // 2)
+    try:
+        torch.manual_seed(3)
+        const_r, w_r = E._forward_autograd(fx["img"], 9)
+        (const_r ** 2).mean().backward(retain_graph=True)
+        r1 = {k: p.grad.clone() for k, p in E.named_parameters() if p.grad is not None}
+        E.zero_grad()
+        (w_r ** 2).mean().backward()
+        r2 = {k: p.grad.clone() for k, p in E.named_parameters() if p.grad is not None}
+    finally:
+        EM.tc.conv2d = orig
+    for got, ref in ((g1, r1), (g2, r2)):
+        assert set(got) == set(ref)
+        for k in ref:
+            assert rel(got[k], ref[k]) < 1e-3, k

@@ -1,0 +1,222 @@
+"""The fused training path on the B200 (dge_b200/train_e.py + csrc/train_bwd.cu): (1) every new backward kernel against
+tests/emu_ops.py, the plain-torch statement of its C-ABI function; (2) encoder parameter gradients against the fixture
+`loss.backward()` produced through the UNMODIFIED reference; (3) fused vs unfused graph on fresh inputs; (4) weights
+changed by an optimiser step are the weights the next inference forward uses (packed-weight cache epoch).
+Bar: 1e-3 of each tensor's scale (north_star); observed ~1e-5."""
+import os
+
+import pytest
+import torch
+
+import emu_ops as emu
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-3
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-20)).item()
+
+
+def _dev_f32b(x):
+    from dge_b200 import ops
+    return ops.nchw_to_f32b(x.cuda())
+
+
+@pytest.mark.parametrize("n,c,h,w,want_dres", [(2, 16, 8, 12, True), (3, 32, 34, 18, False), (1, 64, 64, 64, True)])
+def test_be_head_bwd_kernel(n, c, h, w, want_dres):
+    from dge_b200 import ops
+    g = torch.Generator().manual_seed(h * w + c)
+    d_out = torch.randn(n, c, h // 2, w // 2, generator=g)
+    y2 = torch.randn(n, c, h, w, generator=g)
+    noise = torch.randn(n, h, w, generator=g)
+    dy2, dres, sums = ops.be_head_bwd(_dev_f32b(d_out), _dev_f32b(y2), noise.cuda(), 0.111, 0.889, 0.2, want_dres)
+    e_dy2, e_dres, e_sums = emu.be_head_bwd(emu.F32B.of(d_out), emu.F32B.of(y2), noise, 0.111, 0.889, 0.2, want_dres)
+    assert rel(dy2.to_nchw(), e_dy2.to_nchw()) < 1e-6
+    assert torch.equal(dy2.t.cpu(), e_dy2.t)                      # same hi / lo bf16 split, bit for bit
+    assert (dres is None) == (not want_dres)
+    if want_dres:
+        assert torch.equal(dres.t.cpu(), e_dres.t)
+    scale = e_dy2.to_nchw().abs().sum(dim=(0, 2, 3)).max()
+    assert ((sums.cpu() - e_sums).abs().max() / scale).item() < 1e-5
+
+
+@pytest.mark.parametrize("n,c,h,w", [(2, 16, 8, 12), (3, 24, 33, 17), (1, 64, 128, 128)])
+def test_instance_norm_backward_kernels(n, c, h, w):
+    from dge_b200 import ops
+    g = torch.Generator().manual_seed(h + w + c)
+    x = torch.randn(n, c, h, w, generator=g) * 1.5 + 0.3
+    gr = torch.randn(n, c, h, w, generator=g)
+    noise = torch.randn(n, h, w, generator=g)
+    dstyle = torch.randn(n, 2 * c, generator=g)
+    xe = emu.F32B.of(x)
+    style, mr = emu.instance_stats(xe, 1e-8)
+    xd, gd = _dev_f32b(x), _dev_f32b(gr)
+    style_d, mr_d = ops.instance_stats(xd, 1e-8)
+    assert rel(style_d, style) < 1e-5 and rel(mr_d, mr) < 1e-5
+    st = ops.in_bwd_stats(gd, xd, mr_d)
+    e_st = emu.in_bwd_stats(emu.F32B.of(gr), xe, mr)
+    assert ((st.cpu() - e_st).abs().max() / e_st.abs().max()).item() < 1e-5
+    # mode 0: plain, with a same-resolution residual, with a pooled residual (even maps only)
+    cases = [(None, False)]
+    cases.append((torch.randn(n, c, h, w, generator=g), False))
+    if h % 2 == 0 and w % 2 == 0:
+        cases.append((torch.randn(n, c, h // 2, w // 2, generator=g), True))
+    for res, pool in cases:
+        for ds in (None, dstyle):
+            got = ops.in_bwd_apply(gd, xd, mr_d, style_d, None if ds is None else ds.cuda(), st, 0,
+                                   res=None if res is None else _dev_f32b(res), rscale=0.37, res_pool=pool)
+            ref = emu.in_bwd_apply(emu.F32B.of(gr), xe, mr, style, ds, e_st, 0,
+                                   res=None if res is None else emu.F32B.of(res), rscale=0.37, res_pool=pool)
+            assert rel(got.to_nchw(), ref.to_nchw()) < 2e-5
+    if c % 16 == 0:
+        got, s2 = ops.in_bwd_apply(gd, xd, mr_d, style_d, dstyle.cuda(), st, 1, noise=noise.cuda(), slope=0.2)
+        ref, e_s2 = emu.in_bwd_apply(emu.F32B.of(gr), xe, mr, style, dstyle, e_st, 1, noise=noise, slope=0.2)
+        assert rel(got.to_nchw(), ref.to_nchw()) < 2e-5
+        scale = ref.to_nchw().abs().sum(dim=(0, 2, 3)).max()
+        assert ((s2.cpu() - e_s2).abs().max() / scale).item() < 1e-5
+
+
+def test_instance_norm_backward_is_the_autograd_of_the_forward():
+    """The two kernels together = d/dx of (IN(x), mean, std) as torch.autograd derives it."""
+    from dge_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    n, c, h, w = 2, 16, 20, 12
+    x = (torch.randn(n, c, h, w, generator=g) * 2 + 1).requires_grad_(True)
+    gr = torch.randn(n, c, h, w, generator=g)
+    dstyle = torch.randn(n, 2 * c, generator=g)
+    mean = x.mean(dim=(2, 3), keepdim=True)
+    std = ((x - mean) ** 2).mean(dim=(2, 3), keepdim=True).sqrt()
+    y = torch.nn.functional.instance_norm(x, eps=1e-8)
+    style = torch.cat((mean, std), dim=1).flatten(1)
+    ((y * gr).sum() + (style * dstyle).sum()).backward()
+    xd, gd = _dev_f32b(x.detach()), _dev_f32b(gr)
+    style_d, mr_d = ops.instance_stats(xd, 1e-8)
+    st = ops.in_bwd_stats(gd, xd, mr_d)
+    got = ops.in_bwd_apply(gd, xd, mr_d, style_d, dstyle.cuda(), st, 0)
+    assert rel(got.to_nchw(), x.grad) < 2e-5
+
+
+@pytest.mark.parametrize("n,c,h,w", [(2, 16, 16, 24), (1, 32, 40, 40), (2, 64, 9, 7)])
+def test_from_rgb_bwd_kernel(n, c, h, w):
+    from dge_b200 import ops
+    g = torch.Generator().manual_seed(c + h)
+    img = torch.randn(n, 3, h, w, generator=g)
+    f = torch.randn(n, c, h, w, generator=g)
+    d = torch.randn(n, c, h, w, generator=g)
+    got = ops.from_rgb_bwd(_dev_f32b(d), _dev_f32b(f), img.cuda(), 0.2)
+    ref = emu.from_rgb_bwd(emu.F32B.of(d), emu.F32B.of(f), img, 0.2)
+    assert ((got.cpu() - ref).abs().max() / ref.abs().max()).item() < 1e-5
+
+
+def _encoder():
+    from model.E.E import BE
+    fx = torch.load(os.path.join(GOLD, "be_s16_l4.pt"))
+    E = BE(**fx["config"])
+    E.load_state_dict(fx["state_dict"], strict=True)
+    return fx, E.cuda()
+
+
+def test_fused_encoder_matches_reference_gradients():
+    import model.E.E as EM
+    assert EM.FUSED_TRAIN
+    fx, E = _encoder()
+    gx = torch.load(os.path.join(GOLD, "be_s16_l4_grads.pt"))
+    torch.manual_seed(fx["noise_seed"])
+    const, w = E(fx["img"].cuda())
+    assert const.requires_grad and w.requires_grad and const.grad_fn is not None
+    assert "F32BToNCHW" in type(const.grad_fn).__name__                    # the fused graph, not the torch-node one
+    assert rel(const, fx["const"]) < 2e-4 and rel(w, fx["w"]) < 2e-4
+    loss = ((const - gx["t_const"].cuda()) ** 2).mean() + ((w - gx["t_w"].cuda()) ** 2).mean()
+    loss.backward()
+    got = {k: p.grad for k, p in E.named_parameters() if p.grad is not None}
+    assert set(got) == set(gx["grads"])
+    for k, g in gx["grads"].items():
+        assert rel(got[k], g) < TOL, k
+
+
+@pytest.mark.parametrize("cfg,size,bn", [((16, 512, 3), 32, 9), ((16, 64, 4), 64, 9), ((64, 64, 9), 16, 3)])
+def test_fused_vs_unfused_graph(cfg, size, bn):
+    """Fresh weights / inputs, progressive entry (`block_num`), the no-last-conv block with a 1x1 residual conv
+    ((16, 512, 3): 64 -> 128 on the last block), retain_graph + second backward, gradient w.r.t. the image.
+    Both graphs run the same forward kernels up to fusion order, so an activation within rounding of zero can still
+    take the other slope in one of them; the maps here are large enough that one such unit stays below the bar."""
+    import model.E.E as EM
+    startf, maxf, layers = cfg
+    torch.manual_seed(1)
+    E = EM.BE(startf, maxf, layers, 512, 3).cuda()
+    with torch.no_grad():
+        for k, p in E.named_parameters():
+            if k.endswith(("bias", "noise_weight_1", "noise_weight_2", "bias_1", "bias_2")):
+                p.copy_(torch.randn_like(p) * 0.1)
+    assert E.decode_block[9 - bn].inputs == startf      # (progressive entry needs FromRGB width == the entry block's)
+    img = torch.randn(2, 3, size, size, device="cuda")
+    res = {}
+    for fused in (True, False):
+        EM.FUSED_TRAIN = fused
+        try:
+            x = img.clone().requires_grad_(True)
+            E.zero_grad()
+            torch.manual_seed(9)
+            const, w = E(x, bn)
+            (const ** 2).mean().backward(retain_graph=True)
+            ga = {k: p.grad.clone() for k, p in E.named_parameters() if p.grad is not None}
+            gx = x.grad.clone()
+            E.zero_grad()
+            (w ** 2).mean().backward()
+            gb = {k: p.grad.clone() for k, p in E.named_parameters() if p.grad is not None}
+            res[fused] = (const.detach(), w.detach(), ga, gx, gb)
+        finally:
+            EM.FUSED_TRAIN = True
+    f, u = res[True], res[False]
+    assert rel(f[0], u[0]) < 2e-4 and rel(f[1], u[1]) < 2e-4
+    assert rel(f[3], u[3]) < 5e-3
+    for a, b in ((f[2], u[2]), (f[4], u[4])):
+        assert set(a) == set(b)
+        for k in b:
+            assert rel(a[k], b[k]) < 5e-3, k
+
+
+def _reference_style_step(params, lr):
+    """What the reference's optimiser does to a parameter: an in-place update THROUGH `.data` (custom_adam.py:74),
+    which torch's version counter never sees."""
+    class RefStyle(torch.optim.Optimizer):
+        def __init__(self, ps):
+            super().__init__(ps, {})
+
+        def step(self):
+            for gr in self.param_groups:
+                for p in gr["params"]:
+                    if p.grad is not None:
+                        p.data.add_(p.grad.data, alpha=-lr)
+    return RefStyle(params)
+
+
+@pytest.mark.parametrize("which", ["lreq_adam", "reference_style"])
+def test_inference_after_an_optimiser_step_uses_the_new_weights(which):
+    """no_grad E(x) -> train step -> no_grad E(x): the second call must see the updated weights (the packed-weight
+    caches are keyed on an epoch every optimiser step advances), checked against the oracle on the updated state_dict."""
+    from model.utils.custom_adam import LREQAdam
+    from oracle import encoder as oenc
+    fx, E = _encoder()
+    img = fx["img"].cuda()
+    with torch.no_grad():
+        torch.manual_seed(3)
+        c0, w0 = E(img)
+    opt = LREQAdam(E.parameters(), lr=0.05, betas=(0.0, 0.99)) if which == "lreq_adam" else \
+        _reference_style_step(list(E.parameters()), 0.5)
+    torch.manual_seed(4)
+    const, w = E(img)
+    ((const ** 2).mean() + (w ** 2).mean()).backward()
+    opt.step()
+    with torch.no_grad():
+        torch.manual_seed(3)
+        c1, w1 = E(img)
+    sd = {k: v.detach().cpu().clone() for k, v in E.state_dict().items()}
+    torch.manual_seed(3)
+    with torch.no_grad():
+        c_ref, w_ref = oenc.be_forward(sd, fx["img"], fx["config"]["layer_count"])
+    assert rel(w0, w_ref) > 1e-2                      # the step really moved the function ...
+    assert rel(c1, c_ref) < 2e-4 and rel(w1, w_ref) < 2e-4   # ... and the cached operands followed it

@@ -34,6 +34,13 @@ def record_masks(store):
     """Record, in call order, the sign pattern of every leaky_relu / relu input and the arg-max of every max-pool
     window (product path and oracle call them in the same order: from_rgb, then per block / per layer)."""
     orig_l, orig_r, orig_p = F.leaky_relu, F.relu, F.max_pool2d
+    # the pattern can only be observed on the graph of separate torch nodes: the fused training path (one node per
+    # block / per synthesis pass, tests/test_train_fused_gpu.py) is switched off while recording
+    import model.E.E as _EM
+    import model.stylegan2_generator as _SG
+    fused = (_EM.FUSED_TRAIN, getattr(_SG, "FUSED_TRAIN", False))
+    _EM.FUSED_TRAIN = False
+    _SG.FUSED_TRAIN = False
 
     def lrelu(x, negative_slope=0.01, inplace=False):
         store.append((x.detach() > 0).cpu())
@@ -53,6 +60,7 @@ def record_masks(store):
         yield
     finally:
         F.leaky_relu, F.relu, F.max_pool2d = orig_l, orig_r, orig_p
+        _EM.FUSED_TRAIN, _SG.FUSED_TRAIN = fused
 
 
 @contextlib.contextmanager
