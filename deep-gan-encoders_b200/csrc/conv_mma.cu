@@ -1403,6 +1403,10 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
   DGE_REQUIRE(a->cout >= 16 && a->cout % 16 == 0, "conv: cout=%d must be a positive multiple of 16", a->cout);
   DGE_REQUIRE(a->planes == 1 || a->planes == 2, "conv: planes=%d must be 1 or 2", a->planes);
   DGE_REQUIRE(a->x && a->wpk, "conv: null x / wpk");
+  DGE_REQUIRE((a->in_h == 0 || a->in_h >= a->h) && (a->in_w == 0 || a->in_w >= a->w) &&
+                  ((a->in_h == 0 && a->in_w == 0) || (a->kind != DGE_CONV_UP3X3 && !(a->flags & DGE_CONV_FLAG_CHECKER))),
+              "conv: in_h/in_w (%d, %d) must cover the output domain (tcgen05 path, not the transposed conv)", a->in_h,
+              a->in_w);
   const bool up = a->kind == DGE_CONV_UP3X3;
   if (up) {
     DGE_REQUIRE(a->out_raw_up != nullptr, "conv: UP3X3 needs out_raw_up");
@@ -1695,8 +1699,10 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
   CUtensorMap tmA, tmB;
   {
     const uint64_t c8p = (uint64_t)(p.Cin / 8) * p.planes;
-    uint64_t dims[4] = {(uint64_t)2 * p.W, (uint64_t)p.H, c8p, (uint64_t)p.N};
-    uint64_t strides[3] = {(uint64_t)p.W * 16, (uint64_t)p.H * p.W * 16, c8p * p.H * p.W * 16};
+    // the stored map may extend beyond the output domain (in_h / in_w): the halo then reads real rows / columns there
+    const uint64_t ih = a->in_h ? a->in_h : p.H, iw = a->in_w ? a->in_w : p.W;
+    uint64_t dims[4] = {2 * iw, ih, c8p, (uint64_t)p.N};
+    uint64_t strides[3] = {iw * 16, ih * iw * 16, c8p * ih * iw * 16};
     uint32_t box[4] = {(uint32_t)(2 * p.pw), (uint32_t)p.ph, (uint32_t)((p.kc / 8) * p.planes), 1};
     int r = make_tmap(&tmA, a->x, 4, dims, strides, box);
     if (r) return r;

@@ -277,6 +277,198 @@ k_from_rgb_bwd(const float* __restrict__ d_f, const float* __restrict__ f, const
   if (threadIdx.x < 32) atomicAdd(sums + (size_t)(grp * 8 + (threadIdx.x >> 2)) * 4 + (threadIdx.x & 3), t);
 }
 
+// ---------------------------------------------------------------------------------------------
+// StyleGAN2 synthesis layer, backward of everything after the contraction (stylegan2_generator.py:907-921, 515-522):
+//   y = lrelu(conv * dm + noise * ns + b) * gain ;  next layer reads y * s_next ;  ToRGB reads sum_c rgbw[ch][c] * y[c]
+// The forward kept y only as the NEXT layer's operand ya = y * s_next (ACT), so y = ya / s_next.
+//   dy     = dxs * s_next + sum_ch rgbw[n][ch][c] * dimg[n][ch]
+//   d_pre  = dy * gain * lrelu'(y) ;  d_conv = d_pre * dm   -> ACT (plain conv) or F32B (x2 layer: input of the FIR transpose)
+//   sums[n][c] = ( S = sum dxs * y            -> d s_next[n][c]
+//                  T0..T2 = sum dimg[ch] * y  -> d rgbw[n][ch][c]
+//                  D = sum d_pre * (pre - noise*ns - b), pre = pre-activation (recovered from y)  -> d dm[n][c] * dm[n][c] )
+// ---------------------------------------------------------------------------------------------
+struct Sg2BwdParams {
+  const void* ya;
+  const float* ya_scale;
+  const float* dxs;
+  const float* dimg;
+  const float* rgbw;
+  const float* noise;
+  long long noise_bstride;
+  float noise_scalar;
+  const float* bias;
+  const float* demod;
+  float gain, slope;
+  void* out_act;
+  float* out_f32b;
+  float* sums;
+  int c, hw, planes, out_planes;
+};
+
+__global__ void __launch_bounds__(TB_THREADS)
+k_sg2_layer_bwd(const __grid_constant__ Sg2BwdParams p) {
+  __shared__ float red[TB_THREADS / 32][40];
+  const int c = p.c, C8 = c >> 3, ng = blockIdx.y, nidx = ng / C8, grp = ng - nidx * C8;
+  const size_t hw = (size_t)p.hw;
+  float sn[8], isn[8], dm[8], bs[8], rw[3][8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int ch = grp * 8 + k;
+    sn[k] = p.ya_scale ? __ldg(p.ya_scale + (size_t)nidx * c + ch) : 1.f;
+    isn[k] = sn[k] != 0.f ? 1.f / sn[k] : 0.f;
+    dm[k] = p.demod ? __ldg(p.demod + (size_t)nidx * c + ch) : 1.f;
+    bs[k] = p.bias ? __ldg(p.bias + ch) : 0.f;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) rw[q][k] = p.rgbw ? __ldg(p.rgbw + ((size_t)nidx * 3 + q) * c + ch) : 0.f;
+  }
+  const float g_pos = p.gain, g_neg = p.gain * p.slope;
+  const float ig_pos = 1.f / p.gain, ig_neg = p.slope != 0.f ? 1.f / (p.gain * p.slope) : 0.f;
+  float acc[40];
+#pragma unroll
+  for (int i = 0; i < 40; ++i) acc[i] = 0.f;
+  const uint4* ya = reinterpret_cast<const uint4*>(p.ya) + (size_t)ng * p.planes * hw;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < hw; i += (size_t)gridDim.x * blockDim.x) {
+    float y[8], dx[8], v[8];
+    unpack8(__ldg(ya + i), y);
+    if (p.planes == 2) {
+      float l[8];
+      unpack8(__ldg(ya + hw + i), l);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) y[k] += l[k];
+    }
+    if (p.dxs) {
+      load8_f32b(p.dxs, (size_t)ng * hw + i, dx);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dx[k] = 0.f;
+    }
+    float di[3] = {0.f, 0.f, 0.f};
+    if (p.dimg) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) di[q] = __ldg(p.dimg + ((size_t)nidx * 3 + q) * hw + i);
+    }
+    const float nzs = p.noise ? __ldg(p.noise + (size_t)nidx * p.noise_bstride + i) * p.noise_scalar : 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float yv = y[k] * isn[k];
+      float dy = dx[k] * sn[k];
+      dy = fmaf(rw[0][k], di[0], fmaf(rw[1][k], di[1], fmaf(rw[2][k], di[2], dy)));
+      acc[k] = fmaf(dx[k], yv, acc[k]);
+      acc[8 + k] = fmaf(di[0], yv, acc[8 + k]);
+      acc[16 + k] = fmaf(di[1], yv, acc[16 + k]);
+      acc[24 + k] = fmaf(di[2], yv, acc[24 + k]);
+      const bool pos = yv > 0.f;
+      const float dpre = dy * (pos ? g_pos : g_neg);
+      const float pre = yv * (pos ? ig_pos : ig_neg);
+      acc[32 + k] = fmaf(dpre, pre - nzs - bs[k], acc[32 + k]);
+      v[k] = dpre * dm[k];
+    }
+    if (p.out_act) store8_act_at(p.out_act, (size_t)ng * p.out_planes * hw + i, hw, p.out_planes, v);
+    if (p.out_f32b) store8_f32b(p.out_f32b, (size_t)ng * hw + i, v);
+  }
+  const float t = block_sums<40>(acc, red);
+  if (threadIdx.x < 40)
+    atomicAdd(p.sums + ((size_t)nidx * c + grp * 8 + (threadIdx.x & 7)) * 5 + (threadIdx.x >> 3), t);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Transpose of the x2 layer's FIR (stylegan2_generator.py:603-615, pad (1,1,1,1), f = [1,3,3,1]/4 per axis), written
+// as the SPACE-TO-DEPTH operand of the stride-2 data-gradient conv:
+//   dt[u][v] = sum_{a,b<4} f[a] f[b] dconv[u-a+1][v-b+1]          u in [0, 2H], v in [0, 2W]   (dconv = 0 outside)
+//   out ACT [n][4*C/8][planes][H+1][W+1][8], channel block (2*py+px)*C/8 + g holds dt[2Y+py][2X+px] (0 beyond the map)
+// DGE_CONV_DOWN4X4S2 with a zero first kernel row / column then is the 3x3 stride-2 conv that inverts the transposed conv.
+// Thread = one (Y, X, channel group): a 5x5 window of dconv -> the four phases.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TB_THREADS)
+k_up_fir_bwd_s2d(const float* __restrict__ dconv, void* __restrict__ out, int n, int c, int H, int W, int planes) {
+  const int C8 = c >> 3, Hs = H + 1, Ws = W + 1, Ho = 2 * H, Wo = 2 * W;
+  const size_t total = (size_t)n * C8 * Hs * Ws;
+  const float wv[2][5] = {{0.25f, 0.75f, 0.75f, 0.25f, 0.f}, {0.f, 0.25f, 0.75f, 0.75f, 0.25f}};
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int X = (int)(i % Ws);
+    size_t t = i / Ws;
+    const int Y = (int)(t % Hs);
+    t /= Hs;
+    const int g = (int)(t % C8), nidx = (int)(t / C8);
+    float o[4][8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[q][k] = 0.f;
+    const size_t base = ((size_t)nidx * C8 + g) * Ho * (size_t)Wo;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const int r = 2 * Y - 2 + j;
+      if (r < 0 || r >= Ho) continue;
+      float h0[8], h1[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) h0[k] = h1[k] = 0.f;
+#pragma unroll
+      for (int b = 0; b < 5; ++b) {
+        const int cc = 2 * X - 2 + b;
+        if (cc < 0 || cc >= Wo) continue;
+        float v[8];
+        load8_f32b(dconv, base + (size_t)r * Wo + cc, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          h0[k] = fmaf(wv[0][b], v[k], h0[k]);
+          h1[k] = fmaf(wv[1][b], v[k], h1[k]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        o[0][k] = fmaf(wv[0][j], h0[k], o[0][k]);
+        o[1][k] = fmaf(wv[0][j], h1[k], o[1][k]);
+        o[2][k] = fmaf(wv[1][j], h0[k], o[2][k]);
+        o[3][k] = fmaf(wv[1][j], h1[k], o[3][k]);
+      }
+    }
+    const size_t hws = (size_t)Hs * Ws, pix = (size_t)Y * Ws + X;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      // phases beyond the (2H+1) x (2W+1) map are padding: finite zeros (their weights are zero, 0 * NaN is not)
+      const bool inside = (2 * Y + (q >> 1) <= Ho) && (2 * X + (q & 1) <= Wo);
+      if (!inside) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[q][k] = 0.f;
+      }
+      store8_act_at(out, (((size_t)nidx * 4 + q) * C8 + g) * planes * hws + pix, hws, planes, o[q]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Transpose of the skip branch's x2 up-sampling (dge_rgb_init / stylegan2_generator.py:519-522, 603-615):
+//   forward per axis: out[2m] = (x[m-1] + 3 x[m]) / 4, out[2m+1] = (3 x[m] + x[m+1]) / 4
+//   d_in[m] = (d[2m-1] + 3 d[2m] + 3 d[2m+1] + d[2m+2]) / 4 per axis (d = 0 outside);  planes = n * channels
+// ---------------------------------------------------------------------------------------------
+__global__ void k_rgb_up_bwd(const float* __restrict__ d_out, float* __restrict__ d_in, size_t planes, int hin, int win) {
+  const size_t total = planes * hin * win;
+  const int ho = 2 * hin, wo = 2 * win;
+  const float f[4] = {0.25f, 0.75f, 0.75f, 0.25f};
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int mx = (int)(i % win);
+    size_t t = i / win;
+    const int my = (int)(t % hin);
+    t /= hin;
+    const float* src = d_out + t * (size_t)ho * wo;
+    float s = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int y = 2 * my - 1 + a;
+      if (y < 0 || y >= ho) continue;
+      float r = 0.f;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int x = 2 * mx - 1 + b;
+        if (x >= 0 && x < wo) r = fmaf(f[b], __ldg(src + (size_t)y * wo + x), r);
+      }
+      s = fmaf(f[a], r, s);
+    }
+    d_in[i] = s;
+  }
+}
+
 }  // namespace dge
 
 using namespace dge;
@@ -351,4 +543,50 @@ extern "C" int dge_from_rgb_bwd(const float* d_f, const float* f, const float* i
   k_from_rgb_bwd<<<grid, TB_THREADS, 0, TB_STREAM>>>(d_f, f, img, slope, sums, cimg, c, h * w);
   count_launch();
   return check_launch("k_from_rgb_bwd");
+}
+
+extern "C" int dge_sg2_layer_bwd(const void* ya_act, const float* ya_scale, const float* dxs, const float* dimg,
+                                 const float* rgbw, const float* noise, int64_t noise_bstride, float noise_scalar,
+                                 const float* bias, const float* demod, float gain, float slope, void* out_act,
+                                 int out_planes, float* out_f32b, float* sums, int n, int c, int h, int w, int planes,
+                                 void* stream) {
+  DGE_REQUIRE(ya_act && sums && (out_act || out_f32b), "sg2_layer_bwd: null pointer");
+  DGE_REQUIRE(n > 0 && c >= 16 && c % 16 == 0 && h > 0 && w > 0, "sg2_layer_bwd: bad dims n=%d c=%d h=%d w=%d", n, c, h, w);
+  DGE_REQUIRE((planes == 1 || planes == 2) && (!out_act || out_planes == 1 || out_planes == 2),
+              "sg2_layer_bwd: planes=%d out_planes=%d", planes, out_planes);
+  DGE_REQUIRE(!dimg == !rgbw, "sg2_layer_bwd: dimg and rgbw go together");
+  DGE_REQUIRE(gain != 0.f, "sg2_layer_bwd: gain must be non-zero");
+  TB_ZERO(sums, (size_t)5 * n * c * sizeof(float));
+  Sg2BwdParams p;
+  p.ya = ya_act; p.ya_scale = ya_scale; p.dxs = dxs; p.dimg = dimg; p.rgbw = rgbw; p.noise = noise;
+  p.noise_bstride = noise_bstride; p.noise_scalar = noise_scalar; p.bias = bias; p.demod = demod; p.gain = gain;
+  p.slope = slope; p.out_act = out_act; p.out_f32b = out_f32b; p.sums = sums; p.c = c; p.hw = h * w; p.planes = planes;
+  p.out_planes = out_planes;
+  dim3 grid(tb_splits((long long)h * w, (long long)n * (c / 8)), n * (c / 8));
+  k_sg2_layer_bwd<<<grid, TB_THREADS, 0, TB_STREAM>>>(p);
+  count_launch();
+  return check_launch("k_sg2_layer_bwd");
+}
+
+extern "C" int dge_up_fir_bwd_s2d(const float* dconv, void* out_act, int n, int c, int h, int w, int planes,
+                                  void* stream) {
+  DGE_REQUIRE(dconv && out_act, "up_fir_bwd_s2d: null pointer");
+  DGE_REQUIRE(n > 0 && c >= 16 && c % 16 == 0 && h > 0 && w > 0, "up_fir_bwd_s2d: bad dims n=%d c=%d h=%d w=%d", n, c, h, w);
+  DGE_REQUIRE(planes == 1 || planes == 2, "up_fir_bwd_s2d: planes=%d", planes);
+  const size_t work = (size_t)n * (c / 8) * (h + 1) * (w + 1);
+  size_t g = (work + TB_THREADS - 1) / TB_THREADS;
+  if (g > (size_t)tb_sms() * 32) g = (size_t)tb_sms() * 32;
+  k_up_fir_bwd_s2d<<<(int)g, TB_THREADS, 0, TB_STREAM>>>(dconv, out_act, n, c, h, w, planes);
+  count_launch();
+  return check_launch("k_up_fir_bwd_s2d");
+}
+
+extern "C" int dge_rgb_up_bwd(const float* d_out, float* d_in, int64_t planes, int h_in, int w_in, void* stream) {
+  DGE_REQUIRE(d_out && d_in && planes > 0 && h_in > 0 && w_in > 0, "rgb_up_bwd: bad arguments");
+  const size_t work = (size_t)planes * h_in * w_in;
+  size_t g = (work + 255) / 256;
+  if (g > (size_t)tb_sms() * 32) g = (size_t)tb_sms() * 32;
+  k_rgb_up_bwd<<<(int)g, 256, 0, TB_STREAM>>>(d_out, d_in, (size_t)planes, h_in, w_in);
+  count_launch();
+  return check_launch("k_rgb_up_bwd");
 }

@@ -37,6 +37,7 @@ class ConvArgs(Structure):
         ("preact_c", c_int32), ("preact_up", c_int32),
         ("splitk_ws", c_void_p),
         ("out_pool", c_int32),
+        ("in_h", c_int32), ("in_w", c_int32),
     ]
 
 
@@ -112,6 +113,10 @@ SIGNATURES = {
     "dge_in_bwd_apply": (c_int, [P, P, P, P, P, P, c_int, P, c_float, c_int, P, c_float, P, P, P, c_int, c_int, c_int,
                                  c_int, c_int, P]),
     "dge_from_rgb_bwd": (c_int, [P, P, P, c_float, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "dge_sg2_layer_bwd": (c_int, [P, P, P, P, P, P, c_int64, c_float, P, P, c_float, c_float, P, c_int, P, P, c_int, c_int,
+                                  c_int, c_int, c_int, P]),
+    "dge_up_fir_bwd_s2d": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "dge_rgb_up_bwd": (c_int, [P, P, c_int64, c_int, c_int, P]),
     "dge_blend": (c_int, [P, P, P, c_float, c_float, c_int, c_int, c_int, c_int, c_int, P]),
 }
 

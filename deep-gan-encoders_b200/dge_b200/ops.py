@@ -297,13 +297,18 @@ def pixel_norm(x, eps=1e-8):
 def conv(x, wpk, cout, kind=CONV_3X3, *, demod=None, noise=None, noise_batched=False, noise_w=None,
          noise_scalar=0.0, bias=None, slope=1.0, gain=1.0, blend_src=None, blend_pool=False, blend_a=0.0,
          blend_b=1.0, preact_add=None, preact_up=1, out_act=False, out_planes=None, out_scale=None, out_f32b=False,
-         out_f32b_into=None, out_f32b_pool=False, out_nchw=False, rgb_w=None, rgb_out=None, checker=False):
-    """tcgen05 implicit-GEMM conv with fused epilogue (dge_conv_forward). Returns a dict of outputs."""
+         out_f32b_into=None, out_f32b_pool=False, out_nchw=False, rgb_w=None, rgb_out=None, checker=False,
+         out_hw=None):
+    """tcgen05 implicit-GEMM conv with fused epilogue (dge_conv_forward). Returns a dict of outputs.
+    `out_hw` = (h, w) smaller than x's stored extent: only that top-left output domain is computed (args in_h / in_w)."""
     assert isinstance(x, Act)
     dev = x.t.device
     a = ConvArgs()
     a.kind, a.flags = kind, (FLAG_CHECKER if checker else 0)
     a.n, a.h, a.w, a.cin, a.cout, a.planes = x.n, x.h, x.w, x.c, cout, x.planes
+    if out_hw is not None and tuple(out_hw) != (x.h, x.w):
+        a.h, a.w, a.in_h, a.in_w = int(out_hw[0]), int(out_hw[1]), x.h, x.w
+    oh, ow = a.h, a.w
     a.x, a.wpk = x.t.data_ptr(), wpk.data_ptr()
     keep = [x.t, wpk]
     res = {}
@@ -322,7 +327,7 @@ def conv(x, wpk, cout, kind=CONV_3X3, *, demod=None, noise=None, noise_batched=F
     else:
         a.demod = ptr(demod)
         a.noise = ptr(noise)
-        a.noise_bstride = x.h * x.w if (noise is not None and noise_batched) else 0
+        a.noise_bstride = oh * ow if (noise is not None and noise_batched) else 0
         a.noise_w = ptr(noise_w)
         a.noise_scalar = float(noise_scalar)
         a.bias = ptr(bias)
@@ -335,23 +340,23 @@ def conv(x, wpk, cout, kind=CONV_3X3, *, demod=None, noise=None, noise_batched=F
             a.blend_src = ptr(blend_src.t if isinstance(blend_src, F32B) else blend_src)
             a.blend_pool, a.blend_a, a.blend_b = int(blend_pool), float(blend_a), float(blend_b)
         if out_act:
-            o = Act(x.n, cout, x.h, x.w, out_planes or x.planes, dev)
+            o = Act(x.n, cout, oh, ow, out_planes or x.planes, dev)
             a.out_act, a.out_planes = ptr(o.t), o.planes
             a.out_scale = ptr(out_scale)
             res["act"] = o
         if out_f32b:
-            o = F32B(x.n, cout, x.h, x.w, dev)
+            o = F32B(x.n, cout, oh, ow, dev)
             a.out_f32b = ptr(o.t)
             res["f32b"] = o
         if out_f32b_pool:                    # 2x2 mean of the epilogue value at half resolution (E.py:78-84)
-            o = F32B(x.n, cout, x.h // 2, x.w // 2, dev)
+            o = F32B(x.n, cout, oh // 2, ow // 2, dev)
             a.out_f32b, a.out_pool = ptr(o.t), 1
             res["f32b_pool"] = o
         if out_f32b_into is not None:        # write into a caller-provided F32B slice (e.g. one sample of a batch)
-            assert out_f32b_into.numel() == x.n * cout * x.h * x.w and out_f32b_into.dtype == torch.float32
+            assert out_f32b_into.numel() == x.n * cout * oh * ow and out_f32b_into.dtype == torch.float32
             a.out_f32b = ptr(out_f32b_into)
         if out_nchw:
-            o = torch.empty((x.n, cout, x.h, x.w), dtype=torch.float32, device=dev)
+            o = torch.empty((x.n, cout, oh, ow), dtype=torch.float32, device=dev)
             a.out_nchw = ptr(o)
             res["nchw"] = o
         if rgb_w is not None:
@@ -362,7 +367,7 @@ def conv(x, wpk, cout, kind=CONV_3X3, *, demod=None, noise=None, noise_batched=F
             ws = torch.empty((wsb // 4,), dtype=torch.float32, device=dev)
             a.splitk_ws = ptr(ws)
     name = ("conv3x3", "conv1x1", "conv_up3x3", "conv_down4x4s2")[kind]
-    with _rec(name, (x.n, x.h, x.w, x.c, cout, x.planes)):
+    with _rec(name, (x.n, oh, ow, x.c, cout, x.planes)):
         check(lib().dge_conv_forward(ctypes.byref(a), _stream()))
     return res
 
@@ -684,6 +689,49 @@ def from_rgb_bwd(d_f, f, img, slope=0.2):
         check(lib().dge_from_rgb_bwd(_p(d_f.t), _p(f.t), _f32(img), float(slope), _p(sums), f.n, img.shape[1], f.c, f.h,
                                      f.w, _stream()))
     return sums
+
+
+def sg2_prep_all(S, wp32, layers, outputs):
+    """(styles, demods, rgb_styles, rgb_weights) of one synthesis pass: one launch (SynthesisModule._prep)."""
+    return S._prep(wp32, layers, outputs)
+
+
+def sg2_layer_bwd(ya, ya_scale, dxs, dimg, rgbw, noise, noise_batched, noise_scalar, bias, demod, gain, slope,
+                  out_kind="act", planes=2):
+    """Backward of a synthesis layer's epilogue + its consumers -> (d_conv as Act | F32B, sums fp32 [n, c, 5])."""
+    assert isinstance(ya, Act) and (dxs is None or (isinstance(dxs, F32B) and (dxs.n, dxs.c, dxs.h, dxs.w) ==
+                                                    (ya.n, ya.c, ya.h, ya.w)))
+    dev = ya.t.device
+    out = Act(ya.n, ya.c, ya.h, ya.w, planes, dev) if out_kind == "act" else F32B(ya.n, ya.c, ya.h, ya.w, dev)
+    sums = torch.empty((ya.n, ya.c, 5), dtype=torch.float32, device=dev)
+    di = None if dimg is None else dimg.contiguous()
+    with _rec("sg2_layer_bwd", (ya.n, ya.h, ya.w, ya.c, out_kind)):
+        check(lib().dge_sg2_layer_bwd(
+            _p(ya.t), _f32(ya_scale), _p(dxs.t) if dxs is not None else None, _f32(di), _f32(rgbw), _f32(noise),
+            (ya.h * ya.w if (noise is not None and noise_batched) else 0), float(noise_scalar), _f32(bias), _f32(demod),
+            float(gain), float(slope), _p(out.t) if out_kind == "act" else None, planes,
+            _p(out.t) if out_kind != "act" else None, _p(sums), ya.n, ya.c, ya.h, ya.w, ya.planes, _stream()))
+    return out, sums
+
+
+def up_fir_bwd_s2d(dconv, planes=2):
+    """FIR transpose of the x2 layer as the space-to-depth operand of the stride-2 data-gradient conv:
+    F32B [n, c, 2h, 2w] -> Act [n, 4c, h+1, w+1]."""
+    assert isinstance(dconv, F32B) and dconv.h % 2 == 0 and dconv.w % 2 == 0
+    h, w = dconv.h // 2, dconv.w // 2
+    out = Act(dconv.n, 4 * dconv.c, h + 1, w + 1, planes, dconv.t.device)
+    with _rec("up_fir_bwd_s2d", (dconv.n, h, w, dconv.c)):
+        check(lib().dge_up_fir_bwd_s2d(_p(dconv.t), _p(out.t), dconv.n, dconv.c, h, w, planes, _stream()))
+    return out
+
+
+def rgb_up_bwd(d_out):
+    """Transpose of the skip image's x2 up-sampling: [n, ch, 2h, 2w] -> [n, ch, h, w]."""
+    d_out = d_out.contiguous()
+    n, ch, ho, wo = d_out.shape
+    out = torch.empty((n, ch, ho // 2, wo // 2), dtype=torch.float32, device=d_out.device)
+    check(lib().dge_rgb_up_bwd(_f32(d_out), _p(out), n * ch, ho // 2, wo // 2, _stream()))
+    return out
 
 
 def launch_count():

@@ -8,11 +8,13 @@ the C ABI (include/dge_b200.h); PyTorch only owns device memory and the stream.
 
 Inference (`torch.no_grad()`, or no input that requires grad) runs the fused forward-only kernels.  Training
 (E_align_s2.py:160: `generator.synthesis(w2)['image']` with w2 produced by the encoder under autograd):
-`SynthesisModule.forward` records a differentiable graph w.r.t. `wp` (`_forward_autograd`): the generator is
-frozen in every training script (only `E.parameters()` reach LREQAdam, E_align_s2.py:97), so its parameters enter
-as constants and its never-read `.grad` is not accumulated; the stride-1 3x3 modulated convs run forward and
-backward on the tcgen05 kernels (dge_b200.autograd.conv2d), the x2 transposed convs and the point-wise steps are
-torch CUDA ops in this build.  The mapping network stays forward-only.  No CPU fallback: CPU tensors raise DgeError.
+`SynthesisModule.forward` records ONE autograd node for the whole pass (dge_b200/train_g.py): the same forward kernel
+chain, and a backward made of dge_b200 kernels only (fused point-wise backward + tcgen05 data-gradient convs, the x2
+layers through the stride-2 conv over a space-to-depth map).  The generator is frozen in every training script (only
+`E.parameters()` reach LREQAdam, E_align_s2.py:97), so its parameters enter as constants and its never-read `.grad`
+is not accumulated (a one-time warning says so when they have requires_grad=True).  `_forward_autograd` is the same
+computation as separate torch nodes (cross-check of the fused path; `FUSED_TRAIN = False` selects it).  The mapping
+network stays forward-only.  No CPU fallback: CPU tensors raise DgeError.
 
 Reference behaviours kept on purpose: result-dict keys, train-mode `w_avg` EMA + style mixing with
 the same RNG calls (:177-191), `randomize_noise=True` drawing `torch.randn(N,1,res,res)` on the CPU
@@ -23,8 +25,14 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+import warnings
+
 from dge_b200 import autograd as tc
 from dge_b200 import ops
+from dge_b200 import train_g
+
+FUSED_TRAIN = True     # False: the unfused torch-node graph (`_forward_autograd`)
+_warned_frozen = False
 
 __all__ = ['StyleGAN2Generator']
 
@@ -41,8 +49,8 @@ DEFAULT_PLANES = 2
 def _check_no_grad(*tensors):
     if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
         raise NotImplementedError(
-            'dge_b200 StyleGAN2 kernels are forward-only in this build: wrap the call in torch.no_grad() '
-            '(backward kernels are the next scope row, SURVEY.md 8f-1)')
+            'this stand-alone dge_b200 StyleGAN2 module is forward-only: wrap the call in torch.no_grad().  The '
+            'training path is `generator.synthesis(wp)` (gradient w.r.t. wp, as E_align_s2.py:160 uses it)')
 
 
 def _require_cuda(t, what):
@@ -615,6 +623,14 @@ class SynthesisModule(nn.Module):
                              f'{self.w_space_dim}!\nBut `{wp.shape}` is received!')
         _require_cuda(wp, 'SynthesisModule')
         if torch.is_grad_enabled() and wp.requires_grad:
+            global _warned_frozen
+            if not _warned_frozen and any(p.requires_grad for p in self.parameters()):
+                _warned_frozen = True
+                warnings.warn('dge_b200 SynthesisModule: the generator is treated as FROZEN in the training path -- '
+                              'gradients flow to `wp` only; its parameters receive no .grad (the inversion scripts '
+                              'never read it).', stacklevel=2)
+            if FUSED_TRAIN:
+                return train_g.synthesis_forward(self, wp, randomize_noise)
             return self._forward_autograd(wp, randomize_noise)
         n, dev = wp.shape[0], wp.device
         wp32 = wp.float()

@@ -107,6 +107,10 @@ typedef struct dge_conv_args {
   int32_t out_pool;        /* 1: out_f32b is [n][cout/8][h/2][w/2][8] and receives the 2x2 MEAN of the epilogue value
                               (avg_pool2d(2,2) fused into the producer: model/E/E.py:78-84 only ever reads conv_2's
                               output pooled).  Needs even h, w; out_f32b must be the only output. */
+  int32_t in_h, in_w;      /* 0 = h, w.  Otherwise the stored extent of x when it is LARGER than the output domain h x w
+                              (rows / columns beyond the domain are read by the halo instead of zero padding): the
+                              stride-2 data gradient of the x2 layer reads an (h+1) x (w+1) space-to-depth map
+                              (dge_up_fir_bwd_s2d) and produces h x w.  in_h >= h, in_w >= w. */
 } dge_conv_args;
 
 int dge_conv_forward(const dge_conv_args* a, void* stream);
@@ -334,6 +338,32 @@ int dge_in_bwd_apply(const float* g, const float* x, const float* mean_rstd, con
    d_pre = d_f * (f > 0 ? 1 : slope); d_f, f F32B [n][c/8][h][w][8]; img NCHW [n][cimg<=3][h][w]. */
 int dge_from_rgb_bwd(const float* d_f, const float* f, const float* img, float slope, float* sums, int n, int cimg, int c,
                      int h, int w, void* stream);
+
+/* Backward of everything that follows the contraction in a StyleGAN2 synthesis layer (stylegan2_generator.py:907-921:
+   y = lrelu(conv*dm + noise*ns + b)*gain), plus the two consumers of y: the next layer (y * s_next, :877) and ToRGB
+   (sum_c rgbw[n][ch][c]*y[c], :462-474, 515-522).  The forward keeps y only as the next layer's operand
+   ya = y * ya_scale (ACT [n][c/8][planes][h][w][8]; ya_scale NULL: ya = y), so y = ya / ya_scale.
+     dy = dxs * ya_scale + sum_ch rgbw[n][ch][c] * dimg[n][ch]     dxs  F32B [n][c/8][h][w][8] (gradient w.r.t. the next
+                                                                    layer's operand; NULL: none), dimg NCHW [n][3][h][w]
+     d_conv = dy * gain * lrelu'(y) * demod[n][c]  -> out_act (ACT, operand of the data-gradient conv) and/or out_f32b
+     sums fp32 [n][c][5] = S  = sum dxs*y                   (gradient of ya_scale = the next layer's style)
+                           T0..T2 = sum dimg[ch]*y          (gradient of rgbw[n][ch][c])
+                           D  = sum d_pre*(pre - noise*ns - b), d_pre = dy*gain*lrelu', pre = the pre-activation
+                                                            (demod[n][c] * gradient of demod[n][c])
+   noise [h][w] (bstride 0) or [n][h][w]; noise_scalar = the layer's noise strength; bias [c] (already times bscale). */
+int dge_sg2_layer_bwd(const void* ya_act, const float* ya_scale, const float* dxs, const float* dimg, const float* rgbw,
+                      const float* noise, int64_t noise_bstride, float noise_scalar, const float* bias,
+                      const float* demod, float gain, float slope, void* out_act, int out_planes, float* out_f32b,
+                      float* sums, int n, int c, int h, int w, int planes, void* stream);
+/* Transpose of the x2 layer's 4x4 FIR (dge_up_fir_epilogue; :603-615) written as the space-to-depth operand of the
+   stride-2 data-gradient conv: dconv F32B [n][c/8][2h][2w][8] -> ACT [n][4c/8][planes][h+1][w+1][8] with channel block
+   (2py+px)*c/8 + g holding dt[2Y+py][2X+px], dt[u][v] = sum_{a,b<4} f[a]f[b] dconv[u-a+1][v-b+1] (f = [1,3,3,1]/4), zeros
+   beyond the (2h+1) x (2w+1) raw map.  dge_conv_forward(DGE_CONV_DOWN4X4S2, in_h = h+1, in_w = w+1) with the 3x3 kernel
+   placed in rows / columns 1..3 of the 4x4 taps then is the data gradient of the transposed conv (:879-895). */
+int dge_up_fir_bwd_s2d(const float* dconv, void* out_act, int n, int c, int h, int w, int planes, void* stream);
+/* Transpose of dge_rgb_init's x2 up-sampling of the skip image (:519-522): d_in [planes][h_in][w_in] from
+   d_out [planes][2h_in][2w_in]; per axis d_in[m] = (d[2m-1] + 3d[2m] + 3d[2m+1] + d[2m+2])/4. */
+int dge_rgb_up_bwd(const float* d_out, float* d_in, int64_t planes, int h_in, int w_in, void* stream);
 
 /* ---- optimiser (model/utils/custom_adam.py:24-76, LREQAdam.step) ------------------------------ */
 /* One multi-tensor launch:  v = beta2*v + (1-beta2)*g*g ;  p -= step[t]*g/(sqrt(v)+eps)   (beta1 == 0).

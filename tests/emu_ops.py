@@ -8,6 +8,8 @@ The product never imports this module.
 import torch
 import torch.nn.functional as F
 
+from dge_b200.ops import weight_key  # noqa: F401  (host-side cache key, no device work)
+
 CONV_3X3, CONV_1X1, CONV_UP3X3, CONV_DOWN4X4S2 = 0, 1, 2, 3
 
 
@@ -139,7 +141,7 @@ def _conv3(xa, w, planes, fn):
 def conv(x, wpk, cout, kind=CONV_3X3, *, demod=None, noise=None, noise_batched=False, noise_w=None, noise_scalar=0.0,
          bias=None, slope=1.0, gain=1.0, blend_src=None, blend_pool=False, blend_a=0.0, blend_b=1.0, preact_add=None,
          preact_up=1, out_act=False, out_planes=None, out_scale=None, out_f32b=False, out_f32b_into=None,
-         out_f32b_pool=False, out_nchw=False, rgb_w=None, rgb_out=None, checker=False, in_hw=None):
+         out_f32b_pool=False, out_nchw=False, rgb_w=None, rgb_out=None, checker=False, out_hw=None):
     assert isinstance(x, Act) and isinstance(wpk, _Packed) and preact_add is None and out_f32b_into is None
     n, h, w_ = x.n, x.h, x.w
     wt = wpk.w
@@ -153,7 +155,7 @@ def conv(x, wpk, cout, kind=CONV_3X3, *, demod=None, noise=None, noise_batched=F
         c = x.c // 4
         planes = x.planes_nchw()
         outs = None
-        hh, ww = in_hw if in_hw is not None else (h, w_)
+        hh, ww = out_hw if out_hw is not None else (h, w_)
 
         def d2s(p):
             v = p.view(n, 2, 2, c, p.shape[2], p.shape[3])                  # [n][py][px][c][h][w]
@@ -306,3 +308,117 @@ def from_rgb_bwd(d_f, f, img, slope=0.2):
     out[:, :cimg] = torch.einsum("nchw,nihw->ci", d, img.float())
     out[:, 3] = d.sum(dim=(0, 2, 3))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# StyleGAN2 synthesis: forward pieces and the backward kernels
+# ------------------------------------------------------------------------------------------------
+_F4 = torch.tensor([0.25, 0.75, 0.75, 0.25])
+
+
+def _fir_pad1(t):
+    """out[y][x] = sum_{a,b<4} f[a] f[b] t[y+a-1][x+b-1] (zero outside): (2h+1)^2 -> (2h)^2  (stencil_tma.cu)."""
+    c = t.shape[1]
+    k = (_F4[:, None] * _F4[None, :]).expand(c, 1, 4, 4).contiguous()
+    return F.conv2d(F.pad(t, (1, 1, 1, 1)), k, groups=c)
+
+
+def sg2_prep_all(S, wp32, layers, outputs):
+    styles, demods, rgb_styles, rgb_ws = [], [], [], []
+    for j, m in enumerate(layers):
+        st = m.style
+        b = None if st.bias is None else st.bias.detach() * st.bscale
+        s = F.linear(wp32[:, j], st.weight.detach() * st.wscale, b) + st.additional_bias
+        styles.append(s)
+        if m.demodulate:
+            w2 = ((m.weight.detach() * m.wscale) ** 2).sum(dim=(2, 3))
+            demods.append(torch.rsqrt((s * s) @ w2.t() + m.eps))
+        else:
+            demods.append(None)
+    for k, m in enumerate(outputs):
+        st = m.style
+        b = None if st.bias is None else st.bias.detach() * st.bscale
+        s = F.linear(wp32[:, 2 * k + 1], st.weight.detach() * st.wscale, b) + st.additional_bias
+        rgb_styles.append(s)
+        rgb_ws.append((m.weight.detach().view(m.out_c, m.in_c) * m.wscale)[None] * s[:, None, :])
+    return styles, demods, rgb_styles, rgb_ws
+
+
+def up_fir_epilogue(raw_up, n, c, h_out, w_out, *, demod=None, noise=None, noise_batched=False, noise_scalar=0.0,
+                    bias=None, slope=1.0, gain=1.0, out_scale=None, planes=2, out_act=True, out_nchw=False):
+    y = _fir_pad1(_from_blocked(raw_up))
+    if demod is not None:
+        y = y * demod.view(n, c, 1, 1)
+    if noise is not None:
+        y = y + noise.reshape(n if noise_batched else 1, 1, h_out, w_out) * noise_scalar
+    if bias is not None:
+        y = y + bias.view(1, -1, 1, 1)
+    y = torch.where(y < 0, y * slope, y) * gain
+    res = {}
+    if out_nchw:
+        res["nchw"] = y
+    if out_act:
+        res["act"] = Act.of(y if out_scale is None else y * out_scale.view(n, c, 1, 1), planes)
+    return res
+
+
+def _up2_axis(x, dim):
+    """out[2m] = (x[m-1] + 3 x[m]) / 4, out[2m+1] = (3 x[m] + x[m+1]) / 4 along `dim` (zero outside)."""
+    n = x.shape[dim]
+    pad = [0, 0] * (x.ndim - 1 - dim) + [1, 1]
+    xp = F.pad(x, pad)
+    a, b, c = xp.narrow(dim, 0, n), xp.narrow(dim, 1, n), xp.narrow(dim, 2, n)
+    even, odd = (a + 3 * b) / 4, (3 * b + c) / 4
+    return torch.stack((even, odd), dim=dim + 1).flatten(dim, dim + 1)
+
+
+def rgb_init(img_in, bias, n, nch, h_out, w_out, device):
+    out = torch.zeros((n, nch, h_out, w_out)) if bias is None else bias.view(1, nch, 1, 1).expand(n, nch, h_out, w_out).clone()
+    if img_in is not None:
+        out = out + _up2_axis(_up2_axis(img_in, 2), 3)
+    return out
+
+
+def rgb_up_bwd(d_out):
+    n, ch, ho, wo = d_out.shape
+    x = torch.zeros((n, ch, ho // 2, wo // 2), requires_grad=True)
+    with torch.enable_grad():
+        y = _up2_axis(_up2_axis(x, 2), 3)
+    return torch.autograd.grad(y, x, d_out)[0]
+
+
+def sg2_layer_bwd(ya, ya_scale, dxs, dimg, rgbw, noise, noise_batched, noise_scalar, bias, demod, gain, slope,
+                  out_kind="act", planes=2):
+    n, c, h, w = ya.n, ya.c, ya.h, ya.w
+    y = ya.to_nchw()
+    sn = torch.ones((n, c)) if ya_scale is None else ya_scale
+    isn = torch.where(sn != 0, 1.0 / sn, torch.zeros_like(sn))
+    y = y * isn.view(n, c, 1, 1)
+    dx = torch.zeros_like(y) if dxs is None else dxs.to_nchw()
+    dy = dx * sn.view(n, c, 1, 1)
+    sums = torch.zeros((n, c, 5))
+    sums[:, :, 0] = (dx * y).sum(dim=(2, 3))
+    if dimg is not None:
+        dy = dy + torch.einsum("nkc,nkhw->nchw", rgbw, dimg)
+        sums[:, :, 1:4] = torch.einsum("nkhw,nchw->nck", dimg, y)
+    pos = y > 0
+    dpre = dy * torch.where(pos, gain, gain * slope)
+    pre = y * torch.where(pos, 1.0 / gain, 1.0 / (gain * slope) if slope != 0 else 0.0)
+    nz = 0.0 if noise is None else noise.reshape(n if noise_batched else 1, 1, h, w) * noise_scalar
+    b = 0.0 if bias is None else bias.view(1, c, 1, 1)
+    sums[:, :, 4] = (dpre * (pre - nz - b)).sum(dim=(2, 3))
+    v = dpre if demod is None else dpre * demod.view(n, c, 1, 1)
+    return (Act.of(v, planes) if out_kind == "act" else F32B.of(v)), sums
+
+
+def up_fir_bwd_s2d(dconv, planes=2):
+    d = dconv.to_nchw()
+    n, c, ho, wo = d.shape
+    t = torch.zeros((n, c, ho + 1, wo + 1), requires_grad=True)
+    with torch.enable_grad():
+        y = _fir_pad1(t)
+    dt = torch.autograd.grad(y, t, d)[0]
+    dt = F.pad(dt, (0, 1, 0, 1))                                            # (2h+2) x (2w+2), zeros beyond the raw map
+    hs, ws = ho // 2 + 1, wo // 2 + 1
+    v = dt.view(n, c, hs, 2, ws, 2).permute(0, 3, 5, 1, 2, 4).reshape(n, 4 * c, hs, ws)   # channel = (2py+px)*c + ch
+    return Act.of(v, planes)

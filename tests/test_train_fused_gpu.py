@@ -137,10 +137,10 @@ def test_fused_encoder_matches_reference_gradients():
         assert rel(got[k], g) < TOL, k
 
 
-@pytest.mark.parametrize("cfg,size,bn", [((16, 512, 3), 32, 9), ((16, 64, 4), 64, 9), ((64, 64, 9), 16, 3)])
+@pytest.mark.parametrize("cfg,size,bn", [((16, 32, 3), 32, 9), ((16, 64, 4), 64, 9), ((64, 64, 9), 16, 3)])
 def test_fused_vs_unfused_graph(cfg, size, bn):
     """Fresh weights / inputs, progressive entry (`block_num`), the no-last-conv block with a 1x1 residual conv
-    ((16, 512, 3): 64 -> 128 on the last block), retain_graph + second backward, gradient w.r.t. the image.
+    (the reference itself cannot run a last block with inputs != outputs: its blend adds mismatched shapes), retain_graph + second backward, gradient w.r.t. the image.
     Both graphs run the same forward kernels up to fusion order, so an activation within rounding of zero can still
     take the other slope in one of them; the maps here are large enough that one such unit stays below the bar."""
     import model.E.E as EM
@@ -220,3 +220,148 @@ def test_inference_after_an_optimiser_step_uses_the_new_weights(which):
         c_ref, w_ref = oenc.be_forward(sd, fx["img"], fx["config"]["layer_count"])
     assert rel(w0, w_ref) > 1e-2                      # the step really moved the function ...
     assert rel(c1, c_ref) < 2e-4 and rel(w1, w_ref) < 2e-4   # ... and the cached operands followed it
+
+
+# ------------------------------------------------------------------------------------------------
+# generator (dge_b200/train_g.py)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,c,h,w,rgb,dxs,out_kind,batched", [
+    (2, 16, 8, 8, True, True, "act", False), (2, 32, 12, 20, False, True, "f32b", True),
+    (1, 64, 64, 64, True, False, "act", False), (3, 16, 5, 7, True, True, "f32b", True)])
+def test_sg2_layer_bwd_kernel(n, c, h, w, rgb, dxs, out_kind, batched):
+    from dge_b200 import ops
+    g = torch.Generator().manual_seed(c * h + w)
+    y = torch.randn(n, c, h, w, generator=g)
+    scale = torch.randn(n, c, generator=g) + 1.5 if dxs else None
+    dx = torch.randn(n, c, h, w, generator=g) if dxs else None
+    dimg = torch.randn(n, 3, h, w, generator=g) if rgb else None
+    rgbw = torch.randn(n, 3, c, generator=g) if rgb else None
+    noise = torch.randn(n if batched else 1, h, w, generator=g)
+    bias = torch.randn(c, generator=g) * 0.1
+    demod = torch.rand(n, c, generator=g) + 0.5
+    cu = lambda t: None if t is None else t.cuda()
+    ya_d = ops.nchw_to_act(y.cuda(), scale=cu(scale))
+    ya_e = emu.nchw_to_act(y, scale=scale)
+    assert torch.equal(ya_d.t.cpu(), ya_e.t)
+    got, s = ops.sg2_layer_bwd(ya_d, cu(scale), None if dx is None else _dev_f32b(dx), cu(dimg), cu(rgbw), cu(noise),
+                               batched, 0.3, cu(bias), cu(demod), 2 ** 0.5, 0.2, out_kind)
+    ref, e_s = emu.sg2_layer_bwd(ya_e, scale, None if dx is None else emu.F32B.of(dx), dimg, rgbw, noise, batched, 0.3,
+                                 bias, demod, 2 ** 0.5, 0.2, out_kind)
+    assert rel(got.to_nchw(), ref.to_nchw()) < 2e-5
+    for j in range(5):
+        sc = e_s[:, :, j].abs().max().clamp_min(1e-6)
+        assert ((s[:, :, j].cpu() - e_s[:, :, j]).abs().max() / max(sc, e_s.abs().max() * 1e-3)).item() < 1e-4, j
+
+
+@pytest.mark.parametrize("n,ci,co,h,w", [(2, 16, 16, 4, 4), (1, 64, 32, 16, 24), (2, 32, 16, 9, 5)])
+def test_up_layer_data_gradient(n, ci, co, h, w):
+    """FIR transpose (space-to-depth) + DOWN4X4S2 with out_hw == autograd of conv_transpose2d + pad + FIR."""
+    import torch.nn.functional as F
+    from dge_b200 import ops
+    g = torch.Generator().manual_seed(ci + co + h)
+    wgt = torch.randn(co, ci, 3, 3, generator=g) * 0.2
+    dconv = torch.randn(n, co, 2 * h, 2 * w, generator=g)
+    s2d_d = ops.up_fir_bwd_s2d(_dev_f32b(dconv))
+    s2d_e = emu.up_fir_bwd_s2d(emu.F32B.of(dconv))
+    assert (s2d_d.h, s2d_d.w, s2d_d.c) == (h + 1, w + 1, 4 * co)
+    assert rel(s2d_d.to_nchw(), s2d_e.to_nchw()) < 1e-5
+    w4 = torch.zeros(ci, co, 4, 4)
+    w4[:, :, 1:, 1:] = wgt.flip(2, 3).transpose(0, 1)
+    got = ops.conv(s2d_d, ops.pack_conv_weight(w4.cuda()), ci, ops.CONV_DOWN4X4S2, out_f32b=True, out_hw=(h, w))["f32b"]
+    assert (got.h, got.w) == (h, w)
+    x = torch.zeros(n, ci, h, w, requires_grad=True)
+    y = emu._fir_pad1(F.conv_transpose2d(x, wgt.flip(2, 3).transpose(0, 1), stride=2))
+    (dx,) = torch.autograd.grad(y, x, dconv)
+    assert rel(got.to_nchw(), dx) < 2e-4
+
+
+def test_rgb_up_bwd_kernel():
+    from dge_b200 import ops
+    d = torch.randn(2, 3, 16, 24, generator=torch.Generator().manual_seed(1))
+    assert rel(ops.rgb_up_bwd(d.cuda()), emu.rgb_up_bwd(d)) < 1e-6
+    img = torch.randn(2, 3, 8, 12, generator=torch.Generator().manual_seed(2))
+    assert rel(ops.rgb_init(img.cuda(), None, 2, 3, 16, 24, "cuda"), emu.rgb_init(img, None, 2, 3, 16, 24, "cpu")) < 1e-6
+
+
+def test_fused_synthesis_matches_reference_gradient():
+    import model.stylegan2_generator as SG
+    assert SG.FUSED_TRAIN
+    fx = torch.load(os.path.join(GOLD, "sg2_res32.pt"))
+    ref = torch.load(os.path.join(GOLD, "train_grads.pt"))
+    G = SG.StyleGAN2Generator(**fx["config"])
+    G.load_state_dict(fx["state_dict"], strict=True)
+    G = G.cuda()
+    wp = fx["wp"].cuda().requires_grad_(True)
+    with pytest.warns(UserWarning, match="FROZEN") if not SG._warned_frozen else _null():
+        out = G.synthesis(wp)
+    assert "SynthesisFn" in type(out["image"].grad_fn).__name__
+    assert rel(out["image"], fx["image"]) < 2e-4
+    target = torch.randn(out["image"].shape, generator=torch.Generator().manual_seed(1))
+    ((out["image"] - target.cuda()) ** 2).mean().backward()
+    assert rel(wp.grad, ref["sg2_dwp"]) < TOL
+    assert all(p.grad is None for p in G.parameters())
+    torch.manual_seed(77)
+    out_rn = G.synthesis(fx["wp"].cuda().requires_grad_(True), randomize_noise=True)
+    assert rel(out_rn["image"], fx["image_randnoise_seed77"]) < 2e-4
+
+
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def test_fused_full_iteration_vs_unfused_graph_at_256():
+    """E_align_s2.py:152-221 on StyleGAN2-256 + BE(64, 512, 7): the fused nodes against the graph of separate torch nodes
+    on the same device, both backward passes of the iteration.  (Maps this large make a single leaky-ReLU unit within
+    rounding of zero invisible at the bar.)"""
+    import model.E.E as EM
+    import model.stylegan2_generator as SG
+    import training_utils as tu
+    torch.manual_seed(0)
+    G = SG.StyleGAN2Generator(256).cuda().eval()
+    E = EM.BE(64, 512, 7, 512, 3).cuda()
+    with torch.no_grad():
+        for m in (G, E):
+            for k, p in m.named_parameters():
+                if k.endswith(("bias", "noise_strength", "noise_weight_1", "noise_weight_2", "bias_1", "bias_2")):
+                    p.copy_(torch.randn_like(p) * 0.1)
+    E.set_noise_mode("device")
+    z = torch.randn(2, 512, device="cuda")
+    lp = lambda a, b: ((a - b) ** 2).mean(dim=(1, 2, 3), keepdim=True)
+    with torch.no_grad():
+        r1 = G(z, trunc_psi=0.7, trunc_layers=8)
+    imgs1, w1 = r1["image"], r1["wp"]
+
+    def run(fused):
+        EM.FUSED_TRAIN = SG.FUSED_TRAIN = fused
+        try:
+            E.zero_grad()
+            torch.manual_seed(5)
+            const2, w2 = E(imgs1)
+            imgs2 = G.synthesis(w2)["image"]
+            l_img, _ = tu.space_loss(imgs1, imgs2, lpips_model=lp)
+            l_img.backward(retain_graph=True)
+            ga = {k: p.grad.clone() for k, p in E.named_parameters() if p.grad is not None}
+            E.zero_grad()
+            l_w, _ = tu.space_loss(w1, w2, image_space=False)
+            (0.01 * l_w).backward()
+            gb = {k: p.grad.clone() for k, p in E.named_parameters() if p.grad is not None}
+            return imgs2.detach(), ga, gb
+        finally:
+            EM.FUSED_TRAIN = SG.FUSED_TRAIN = True
+
+    img_f, fa, fb = run(True)
+    img_u, ua, ub = run(False)
+    assert rel(img_f, img_u) < 2e-4
+    for a, b in ((fa, ua), (fb, ub)):
+        assert set(a) == set(b)
+        # per-channel vectors (bias / noise-weight gradients) are sums of ~1e3-1e5 sign-alternating terms: ONE unit whose
+        # pre-activation is within rounding of zero (it may take either slope in either graph) moves them by ~1/sqrt(N);
+        # the exact 1e-3 check of every parameter is the reference-fixture test above
+        worst_w = max((rel(a[k], b[k]), k) for k in b if b[k].numel() > b[k].shape[0] * 2 or b[k].dim() == 2)
+        worst_v = max((rel(a[k], b[k]), k) for k in b)
+        assert worst_w[0] < 5e-3, worst_w
+        assert worst_v[0] < 3e-2, worst_v
