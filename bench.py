@@ -8,9 +8,19 @@ with E = BE(startf=16, maxf=512, layer_count=9) and G = StyleGAN2Generator(1024)
 weights (no checkpoints offline), fp32-equivalent split-precision bf16x3 tensor-core math.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-N > 1 is launched by the driver through torch.distributed.run (one rank per GPU); the path shards
+N > 1 is launched by the driver through torch.distributed.run (one rank per GPU); the forward path shards
 by sample with no data-path collective (forward-only => replicas), so scaling is "weak".
 Prints ONE JSON line on rank 0.
+
+Beside the headline the line carries
+  train          the whole E_align_s2.py training iteration (:140-221) through the drop-in modules at every N: one
+                 replica per GPU, encoder gradients exchanged by the bucketed NCCL all-reduce that overlaps the backward
+                 (dge_b200.dist.GradBucket, hooked into LREQAdam) -- encoder-train images/s, all-reduce and exposed-comm ms
+  reference_gpu  (N = 1) the UNMODIFIED reference on the same GPU in the same run: forward and training iteration
+                 (tools/ref_gpu_timing.py as a subprocess)
+  cpu_baseline   (N = 1) the reference's CPU path on this box's host cores (`--impl reference` as a subprocess)
+`--impl reference` times the unmodified reference modules (baseline/_ref, a git-ignored copy that travels with the
+snapshot) on the host cores at the same batch 8; without that copy it falls back to the oracle port and says so.
 """
 import argparse
 import json
@@ -142,19 +152,54 @@ def oracle_step(gsd, esd, imgs1, res=RES, layers=LAYERS):
     return osg2.synthesis(gsd, w2, res)["image"], const2, w2
 
 
-def time_cpu_oracle(steps, warmup, batch=1):
+REF_DIR = os.environ.get("DGE_REF", os.path.join(ROOT, "baseline", "_ref"))
+
+
+def reference_available():
+    return os.path.isfile(os.path.join(REF_DIR, "model", "stylegan2_generator.py"))
+
+
+def time_cpu_reference(steps, warmup, batch=BATCH):
+    """The reference's own CPU path: its unmodified modules (baseline/_ref) when the copy is there (kind "reference"), else
+    the oracle restatement (kind "port").  Must run in a process that has NOT imported the drop-in package (same module
+    names)."""
     torch.set_num_threads(os.cpu_count())
-    gsd, esd = oracle_state()
     g = torch.Generator().manual_seed(3)
     imgs1 = torch.randn(batch, 3, RES, RES, generator=g).clamp_(-1, 1)
+    if reference_available():
+        import types
+        for n in ["matplotlib", "matplotlib.pyplot", "boto3", "botocore", "botocore.exceptions", "lpips", "tensorboardX"]:
+            sys.modules.setdefault(n, types.ModuleType(n))
+        sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+        sys.modules["botocore.exceptions"].ClientError = Exception
+        sys.modules["botocore"].exceptions = sys.modules["botocore.exceptions"]
+        pkg = os.path.join(ROOT, "deep-gan-encoders_b200")
+        sys.path[:] = [REF_DIR] + [p for p in sys.path if os.path.abspath(p or ".") != pkg]
+        import model.E.E as ref_e
+        import model.stylegan2_generator as ref_g
+        assert os.path.abspath(ref_g.__file__).startswith(os.path.abspath(REF_DIR))
+        torch.manual_seed(0)
+        G = ref_g.StyleGAN2Generator(RES).eval()
+        E = ref_e.BE(STARTF, 512, LAYERS, 512, 3).eval()
+
+        def step():
+            const2, w2 = E(imgs1)
+            return G.synthesis(w2)["image"]
+        kind = "reference"
+    else:
+        gsd, esd = oracle_state()
+
+        def step():
+            return oracle_step(gsd, esd, imgs1)
+        kind = "port"
     with torch.no_grad():
         for _ in range(warmup):
-            oracle_step(gsd, esd, imgs1)
+            step()
         t0 = time.perf_counter()
         for _ in range(steps):
-            oracle_step(gsd, esd, imgs1)
+            step()
         dt = (time.perf_counter() - t0) / steps
-    return batch / dt, dt
+    return batch / dt, dt, kind
 
 
 # -------------------------------------------------------------------------------------------------
@@ -164,17 +209,19 @@ def run_reference(args):
     rank, world, _ = dist_setup(args.gpus)
     if rank != 0:
         return
-    ips, dt = time_cpu_oracle(args.steps, args.warmup, batch=1)
+    ips, dt, kind = time_cpu_reference(args.steps, args.warmup, batch=BATCH)
     cores = os.cpu_count()
-    sample = ("batch 1 of the bs=8 workload per step (CPU images/s is batch-independent: SURVEY 6 measured 0.30 "
-              "img/s at N=1 vs 0.31 at N=8); torch fp32 MKL-DNN, oracle/ restatement of the reference forward "
-              "(the Python reference cannot travel to the GPU box)")
-    line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus,
+    src = ("the UNMODIFIED reference modules (baseline/_ref: model/stylegan2_generator.py, model/E/E.py), PyTorch fp32 on the "
+           "host cores" if kind == "reference" else
+           "oracle/ torch-fp32 restatement of the reference forward (no copy of the reference under baseline/_ref)")
+    sample = f"the full step at the benchmark batch of {BATCH} ({dt:.1f} s per step), all {cores} host threads; {src}"
+    line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": 1,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "StyleGAN2-FFHQ-1024 synthesis + BE(16,9) encoder forward, CPU",
-                       "sample_batch": 1},
-            "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": "configs[2]: StyleGAN2-FFHQ-1024 synthesis + BE(startf=16, L=9) encoder forward, "
+                                   "batch 8, random-init weights, CPU", "global_batch": BATCH,
+                       "note": "one process on the host cores whatever --gpus says (rank 0 only under torchrun)"},
+            "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -333,13 +380,143 @@ def run_ours(args):
         "top_kernels": top,
         "peaks": pk,
     }
+    # ---- the training iteration (SURVEY 8f-1 / north star: encoder-train images/s at 1, 2, 4, 8 GPUs) ----------
+    if not args.no_train:
+        del graph, graph_out
+        torch.cuda.empty_cache()
+        line["train"] = train_leg(G, E, dev, rank, world, max(3, min(args.steps, 10)), 3)
     if rank == 0:
+        if world == 1 and not args.no_reference_gpu:
+            torch.cuda.empty_cache()
+            line["reference_gpu"] = run_json_subprocess(
+                [sys.executable, os.path.join(ROOT, "tools", "ref_gpu_timing.py")] + (["--no-train"] if args.no_train else []),
+                600)
         if world == 1 and not args.no_cpu_baseline:
-            cips, cdt = time_cpu_oracle(1, 1, batch=1)
-            line["cpu_baseline"] = {"value": cips, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                                    "sample": "1 warm-up + 1 timed step at batch 1 of the same 1024 workload "
-                                              f"({cdt:.1f} s), oracle/ torch-fp32 restatement, all host threads"}
+            ref = run_json_subprocess([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3",
+                                       "--warmup", "1"], 900)
+            line["cpu_baseline"] = ref.get("cpu_baseline", ref)
         print(json.dumps(line), flush=True)
+
+
+def run_json_subprocess(cmd, timeout):
+    """Run a helper in its own process (the reference's module names clash with the drop-in's) -> its last JSON line."""
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout,
+                           env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"error": (r.stderr or r.stdout)[-400:]}
+    except Exception as exc:  # noqa: BLE001
+        return {"error": repr(exc)[:400]}
+
+
+def train_leg(G, E, dev, rank, world, steps, warmup):
+    """E_align_s2.py:140-221, mtype 2, through the drop-in modules: per iteration G(z) under no_grad, E(imgs1),
+    G.synthesis(w2), the three image-space `space_loss` calls (full image, AT1 and AT2 crops) + the latent one, and the two
+    `zero_grad / backward / step` pairs.  One replica per GPU on its own slice of the seeded global z batch; LREQAdam owns
+    the gradient exchange (bucketed all-reduce overlapped with the backward)."""
+    import lpips
+    import torch.distributed as dist
+    import training_utils as tu
+    from dge_b200 import dist as ddist
+    from dge_b200 import ops
+    from model.utils.custom_adam import LREQAdam
+    E.train()
+    opt = LREQAdam([{"params": E.parameters()}], lr=0.0015, betas=(0.0, 0.99), weight_decay=0)
+    lp = lpips.LPIPS(net="vgg", pretrained=False, pnet_rand=True, verbose=False).to(dev)
+    kw = dict(trunc_psi=0.7, trunc_layers=8, randomize_noise=False)
+
+    def iteration(it):
+        z = ddist.global_latents(it % 30000, BATCH * world, 512, rank, world, device=dev)     # set_seed(iteration % 30000)
+        with torch.no_grad():
+            r = G(z, **kw)
+            imgs1, w1 = r["image"], r["wp"]
+        const2, w2 = E(imgs1)
+        imgs2 = G.synthesis(w2)["image"]
+        opt.zero_grad()
+        l0, _ = tu.space_loss(imgs1, imgs2, lpips_model=lp)
+        m = imgs1.shape[3] // 8
+        l1, _ = tu.space_loss(imgs1[:, :, :, m:-m], imgs2[:, :, :, m:-m], lpips_model=lp)
+        m2 = m + imgs1.shape[2] // 32
+        l2, _ = tu.space_loss(imgs1[:, :, m2:-m2, m2:-m2], imgs2[:, :, m2:-m2, m2:-m2], lpips_model=lp)
+        opt.zero_grad()
+        (l0 + l1 * 5 + l2 * 9).backward(retain_graph=True)
+        opt.step()
+        lw, _ = tu.space_loss(w1, w2, image_space=False)
+        opt.zero_grad()
+        (lw * 0.01).backward()
+        opt.step()
+
+    t_w = torch.randn(BATCH, 18, 512, device=dev)
+
+    def encoder_step(it, imgs):
+        const, w = E(imgs)
+        loss = ((w - t_w) ** 2).mean() + (const ** 2).mean()
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        barrier()
+        return ddist.max_over_ranks(e0.elapsed_time(e1), dev) / n
+
+    for i in range(warmup):
+        iteration(i)
+    ops.launch_count_reset()
+    iteration(warmup)
+    launches = ops.launch_count()
+    torch.cuda.reset_peak_memory_stats()
+    ms = timed(iteration, steps)
+    peak = torch.cuda.max_memory_allocated() / 2 ** 30
+    with torch.no_grad():
+        imgs = G(ddist.global_latents(7, BATCH * world, 512, rank, world, device=dev), **kw)["image"]
+    for i in range(2):
+        encoder_step(i, imgs)
+    ms_enc = timed(lambda i: encoder_step(i, imgs), steps)
+    out = {"metric": "encoder-train images/sec (E_align_s2.py iteration: StyleGAN2-FFHQ1024 + BE(16,9), bs=8/GPU)",
+           "value": BATCH * world / (ms / 1e3), "unit": UNIT, "n_gpus": world, "ms_per_iteration": ms, "steps": steps,
+           "warmup": warmup + 1, "scaling": "weak", "peak_gib": peak, "gpu_launches_per_iteration": launches,
+           "what": "G(z) no_grad + E fwd + G.synthesis fwd + 3 image-space space_loss (MSE, cosine, SSIM, LPIPS-VGG16 with "
+                   "random weights) + latent space_loss + 2 x (zero_grad, backward, gradient all-reduce, LREQAdam.step); "
+                   "fused training nodes (dge_b200/train_e.py, train_g.py), bf16x3 split-precision convs",
+           "encoder_step": {"ms": ms_enc, "images_per_s": BATCH * world / (ms_enc / 1e3),
+                            "what": "BE(16,9) forward + backward + gradient all-reduce + LREQAdam.step only"}}
+    bucket = opt._bucket
+    if world > 1 and bucket is not None:
+        # the same iterations without the exchange -> exposed communication; and the exchange alone
+        bucket.enabled = False
+        ms_nocomm = timed(iteration, steps)
+        bucket.enabled = True
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.all_reduce(bucket.flat)
+        e0.record()
+        for _ in range(5):
+            dist.all_reduce(bucket.flat)
+        e1.record()
+        barrier()
+        ar = ddist.max_over_ranks(e0.elapsed_time(e1), dev) / 5
+        out.update({"allreduce_bytes_per_iteration": 2 * bucket.bytes_per_exchange, "allreduce_ms_standalone": ar,
+                    "allreduce_busbw_gbs": 2 * (world - 1) / world * bucket.bytes_per_exchange / (ar / 1e3) / 1e9,
+                    "ms_per_iteration_without_exchange": ms_nocomm, "exposed_comm_ms_per_iteration": ms - ms_nocomm,
+                    "chunks": len(bucket.chunks), "exchange": "2 per iteration (one per backward), NCCL AVG all-reduce of "
+                    "the flat fp32 gradient bucket in 4 chunks launched from post-accumulate hooks during the backward"})
+    else:
+        out.update({"allreduce_bytes_per_iteration": 0, "exposed_comm_ms_per_iteration": 0.0})
+    E.eval()
+    return out
 
 
 def conv_flops(key, name):
@@ -428,6 +605,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-iteration leg")
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip the unmodified reference on this GPU")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -30,6 +30,22 @@ class LREQAdam(Optimizer):
         defaults = dict(lr=lr, beta_2=beta_2, eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
         self._plan_key, self._plan = None, None
+        # Data-parallel runs (one process per GPU under torchrun, torch.distributed initialised): the reference loop
+        # (E_align_s2.py:203-206, 218-221) is `zero_grad(); loss.backward(); step()` and knows nothing about ranks, so
+        # the gradient exchange lives here -- the parameters' .grad become views of one flat bucket whose all-reduce
+        # overlaps the backward (dge_b200.dist.GradBucket) and `step` waits for it before the update.
+        self._bucket = None
+        from dge_b200 import dist as _ddist
+        if _ddist.world_size() > 1:
+            ps = [p for g in self.param_groups for p in g['params']]
+            if ps and all(p.is_cuda or _ddist.dist.get_backend() == 'gloo' for p in ps):
+                self._bucket = _ddist.GradBucket(ps)
+
+    def zero_grad(self, set_to_none=True):
+        if self._bucket is not None:
+            self._bucket.zero()
+            return
+        super().zero_grad(set_to_none)
 
     def _build_plan(self, tensors, device):
         """Device-side tables for the multi-tensor launch; rebuilt only when the (p, grad, v) pointers change."""
@@ -54,6 +70,8 @@ class LREQAdam(Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        if self._bucket is not None:
+            self._bucket.finish()
         for group in self.param_groups:
             tensors, steps = [], []
             for p in group['params']:

@@ -49,6 +49,24 @@ def _worker(rank, world, port, out):
     frozen(lin2(zg)).pow(2).sum().backward()
     for p, q in zip(lin.parameters(), lin2.parameters()):
         assert torch.allclose(p.grad, q.grad, rtol=1e-5, atol=1e-6)
+    # 2b. the same exchange through the persistent bucket the optimiser owns: gradients are views of one flat buffer,
+    #     chunks are all-reduced as soon as their last gradient lands, `finish()` waits; two backward passes per
+    #     iteration (E_align_s2.py:205,220) and zero_grad keep the views
+    lin3 = torch.nn.Sequential(torch.nn.Linear(16, 8), torch.nn.Linear(8, 4))
+    lin3.load_state_dict(lin2.state_dict())
+    opt = LREQAdam(lin3.parameters(), lr=1e-3, betas=(0.0, 0.99))
+    bucket = opt._bucket
+    assert bucket is not None and len(bucket.chunks) >= 2
+    assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(bucket.params, bucket.views))
+    for it in range(2):
+        opt.zero_grad()
+        assert all(p.grad is v for p, v in zip(bucket.params, bucket.views)) and float(bucket.flat.abs().sum()) == 0.0
+        (frozen(lin3(z)).pow(2).sum() * (it + 1)).backward()
+        assert any(w is not None for w in bucket._work)            # exchange already enqueued by the hooks
+        sent = bucket.finish()
+        assert sent == bucket.flat.numel() * 4
+        for p, q in zip(lin3.parameters(), lin2.parameters()):     # average over ranks of per-rank sums = whole-batch / world
+            assert torch.allclose(p.grad, q.grad * (it + 1) / world, rtol=1e-5, atol=1e-6)
     # 3. timing reduction and buffer broadcast
     assert ddist.max_over_ranks(1.0 + rank) == float(world)
     bn = torch.nn.BatchNorm1d(4)
