@@ -203,6 +203,10 @@ def block_forward(block, x_t, pre=None):
     noise1 = block._noise(n, h, w, dev).reshape(n, h, w).contiguous()                          # E.py:60 (RNG order kept)
     noise2 = block._noise(n, h, w, dev).reshape(n, h, w).contiguous() if block.has_last_conv else None   # :73
     has_w3 = block.inputs != block.outputs
+    if has_w3 and not block.has_last_conv:
+        # E.py:84 adds the `inputs`-channel features to the `outputs`-channel residual: the reference fails here too
+        raise RuntimeError(f'BEBlock without a last conv needs inputs == outputs (got {block.inputs}, {block.outputs}): '
+                           'choose start_features so that the last block runs at maxf (16 -> 1024, 32 -> 512, 64 -> 256)')
     cfg = (block.has_last_conv, block.planes, block.instance_norm_1.eps, block.instance_norm_2.eps, noise1, noise2)
     pre_style, pre_mr = pre if pre is not None else (None, None)
     out_t, style1, style2 = _BEBlockFn.apply(

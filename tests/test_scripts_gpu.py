@@ -1,0 +1,27 @@
+"""Script tier on the B200 (north star: "E_align/embedding_img.py drop in unchanged"): the UNMODIFIED
+reference scripts' `train()` run end to end against the drop-in package -- synthetic checkpoints, two iterations, every
+forward / backward / optimiser step on dge_b200 kernels -- and write the files they are meant to write."""
+import pytest
+
+from test_scripts_cpu import run_tier
+
+pytestmark = pytest.mark.gpu
+
+
+def test_e_align_s2_trains_two_iterations_unmodified():
+    out = run_tier("E_align_s2.py", "--img-size", "64", "--iterations", "2")
+    if "skipped" in out:
+        pytest.skip(out["skipped"])
+    assert out["completed"] is True, out
+    assert out["missing_outputs"] == [], out
+    assert out["dge_launches"] > 200, out                     # the work ran on this library's kernels
+    assert out["e_checkpoint_keys"] > 50 and out["e_checkpoint_finite"], out
+
+
+def test_embedding_img_inverts_two_images_unmodified():
+    out = run_tier("embedding_img.py", "--img-size", "64", "--iterations", "2")
+    if "skipped" in out:
+        pytest.skip(out["skipped"])
+    assert out["completed"] is True, out
+    assert out["missing_outputs"] == [], out
+    assert out["dge_launches"] > 200, out
