@@ -18,6 +18,8 @@ Beside the headline the line carries
                  (dge_b200.dist.GradBucket, hooked into LREQAdam) -- encoder-train images/s, all-reduce and exposed-comm ms
   reference_gpu  (N = 1) the UNMODIFIED reference on the same GPU in the same run: forward and training iteration
                  (tools/ref_gpu_timing.py as a subprocess)
+  inversion      (N = 1) BASELINE configs[4]: the embedding_img.py inversion loop with StyleGAN2-1024 (tools/bench_invert.py),
+                 ours and the unmodified reference on this GPU, s/image and final reconstruction MSE
   cpu_baseline   (N = 1) the reference's CPU path on this box's host cores (`--impl reference` as a subprocess)
 `--impl reference` times the unmodified reference modules (baseline/_ref, a git-ignored copy that travels with the
 snapshot) on the host cores at the same batch 8; without that copy it falls back to the oracle port and says so.
@@ -391,6 +393,18 @@ def run_ours(args):
             line["reference_gpu"] = run_json_subprocess(
                 [sys.executable, os.path.join(ROOT, "tools", "ref_gpu_timing.py")] + (["--no-train"] if args.no_train else []),
                 600)
+        if world == 1 and not args.no_inversion:
+            # BASELINE configs[4]: the embedding_img.py inversion loop (batch 1), ours and the unmodified reference on this GPU
+            torch.cuda.empty_cache()
+            inv = [sys.executable, os.path.join(ROOT, "tools", "bench_invert.py"), "--images", "3", "--iterations", "6"]
+            ours_inv = run_json_subprocess(inv, 600)                                     # encoder noise drawn on the device
+            ours_same = run_json_subprocess(inv + ["--noise", "reference"], 600)          # the reference's CPU noise stream
+            ref_inv = run_json_subprocess(inv + ["--impl", "reference"], 900)
+            line["inversion"] = {"ours": ours_inv, "ours_reference_noise": ours_same, "reference_gpu": ref_inv,
+                                 "note": "timing: `ours` (device noise) vs `reference_gpu`; reconstruction MSE: "
+                                         "`ours_reference_noise` vs `reference_gpu` (identical seeds and noise stream)"}
+            if "ms_per_iteration" in ours_inv and "ms_per_iteration" in ref_inv:
+                line["inversion"]["speedup_vs_reference_gpu"] = ref_inv["ms_per_iteration"] / ours_inv["ms_per_iteration"]
         if world == 1 and not args.no_cpu_baseline:
             ref = run_json_subprocess([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3",
                                        "--warmup", "1"], 900)
@@ -607,6 +621,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-iteration leg")
     ap.add_argument("--no-reference-gpu", action="store_true", help="skip the unmodified reference on this GPU")
+    ap.add_argument("--no-inversion", action="store_true", help="skip the configs[4] inversion-loop leg")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -1227,6 +1227,78 @@ __global__ void __launch_bounds__(256) k_ssim_sum(const float* __restrict__ a, c
   block_reduce_add<1>(v, out);
 }
 
+// SSIM backward w.r.t. the second image (the training scripts back-propagate 1 - ssim(imgs1, imgs2) into imgs2,
+// training_utils.py:87-88, E_align_s2.py:184-205).  With m = blur(b), Ebb = blur(b^2), Eab = blur(a b) (gaussian, zero pad):
+//   pass 1: per pixel the partials of the SSIM map S w.r.t. those three blurred quantities -> G[0..2]
+//   pass 2: d b[q] = go/numel * ( blur(G0)[q] + 2 b[q] blur(G1)[q] + a[q] blur(G2)[q] )      (the blur is self-adjoint)
+__global__ void __launch_bounds__(256) k_ssim_grad_maps(const float* __restrict__ a, const float* __restrict__ b,
+                                                        size_t planes, int h, int w, float* __restrict__ G) {
+  const size_t total = planes * h * w;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w);
+    const int y = (int)((i / w) % h);
+    const size_t pl = i / ((size_t)w * h);
+    const float* pa = a + pl * h * w;
+    const float* pb = b + pl * h * w;
+    float m1 = 0.f, m2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
+    for (int dy = -5; dy <= 5; ++dy) {
+      const int yy = y + dy;
+      if (yy < 0 || yy >= h) continue;
+      const float gy = c_gauss11[dy + 5];
+      for (int dx = -5; dx <= 5; ++dx) {
+        const int xx = x + dx;
+        if (xx < 0 || xx >= w) continue;
+        const float g = gy * c_gauss11[dx + 5];
+        const float va = pa[(size_t)yy * w + xx], vb = pb[(size_t)yy * w + xx];
+        m1 = fmaf(g, va, m1);
+        m2 = fmaf(g, vb, m2);
+        s11 = fmaf(g, va * va, s11);
+        s22 = fmaf(g, vb * vb, s22);
+        s12 = fmaf(g, va * vb, s12);
+      }
+    }
+    const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+    const float n1 = 2.f * m1 * m2 + C1, n2 = 2.f * (s12 - m1 * m2) + C2;
+    const float d1 = m1 * m1 + m2 * m2 + C1, d2 = (s11 - m1 * m1) + (s22 - m2 * m2) + C2;
+    const float inv = 1.f / (d1 * d2), S = n1 * n2 * inv;
+    // dS/dm2: through n1 (2 m1), n2 (-2 m1), d1 (2 m2), d2 (-2 m2)
+    G[i] = 2.f * m1 * (n2 - n1) * inv - 2.f * m2 * S / d1 + 2.f * m2 * S / d2;
+    G[total + i] = -S / d2;                 // dS/dEbb
+    G[2 * total + i] = 2.f * n1 * inv;      // dS/dEab
+  }
+}
+
+__global__ void __launch_bounds__(256) k_ssim_grad_apply(const float* __restrict__ a, const float* __restrict__ b,
+                                                         const float* __restrict__ G, const float* __restrict__ go,
+                                                         size_t planes, int h, int w, float* __restrict__ db) {
+  const size_t total = planes * h * w;
+  const float scale = __ldg(go) / (float)total;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w);
+    const int y = (int)((i / w) % h);
+    const size_t pl = i / ((size_t)w * h);
+    const float* g0 = G + pl * h * w;
+    const float* g1 = g0 + total;
+    const float* g2 = g1 + total;
+    float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+    for (int dy = -5; dy <= 5; ++dy) {
+      const int yy = y + dy;
+      if (yy < 0 || yy >= h) continue;
+      const float gy = c_gauss11[dy + 5];
+      for (int dx = -5; dx <= 5; ++dx) {
+        const int xx = x + dx;
+        if (xx < 0 || xx >= w) continue;
+        const float g = gy * c_gauss11[dx + 5];
+        const size_t o = (size_t)yy * w + xx;
+        b0 = fmaf(g, g0[o], b0);
+        b1 = fmaf(g, g1[o], b1);
+        b2 = fmaf(g, g2[o], b2);
+      }
+    }
+    db[i] = scale * (b0 + 2.f * b[i] * b1 + a[i] * b2);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Grad-CAM / Grad-CAM++ maps (metric/grad_cam.py:101-194) from the hooked feature / gradient tensors (NCHW fp32).
 // The reference does this per image on the host in NumPy (float64 for the ++ variant) + cv2.resize.
@@ -1776,18 +1848,34 @@ int dge_avgpool_nchw(const float* x, float* out, int64_t planes, int h_out, int 
   DGE_REQUIRE(x && out && planes > 0 && h_out > 0 && w_out > 0 && factor >= 1, "avgpool_nchw: bad args");
   LAUNCH_1D(k_avgpool_nchw, (size_t)planes * h_out * w_out, stream, x, out, (size_t)planes, h_out, w_out, factor);
 }
-int dge_ssim_sum(const float* a, const float* b, int64_t planes, int h, int w, double* out1, void* stream) {
-  DGE_REQUIRE(a && b && out1 && planes > 0 && h > 0 && w > 0, "ssim_sum: bad args");
+// gaussian(11, 1.5) normalised, as metric/pytorch_ssim.py:8-10 (fp32 torch.Tensor arithmetic)
+static int ssim_window_init() {
   static bool init = false;
-  cudaStream_t st = (cudaStream_t)stream;
   if (!init) {
-    // gaussian(11, 1.5) normalised, as metric/pytorch_ssim.py:8-10 (fp32 torch.Tensor arithmetic)
     float g[11], sum = 0.f;
     for (int i = 0; i < 11; ++i) { g[i] = (float)exp(-(double)((i - 5) * (i - 5)) / (2.0 * 1.5 * 1.5)); sum += g[i]; }
     for (int i = 0; i < 11; ++i) g[i] /= sum;
-    if (cudaMemcpyToSymbol(c_gauss11, g, sizeof(g)) != cudaSuccess) { set_error("ssim_sum: constant upload failed"); return DGE_ERR_CUDA; }
+    if (cudaMemcpyToSymbol(c_gauss11, g, sizeof(g)) != cudaSuccess) { set_error("ssim: constant upload failed"); return DGE_ERR_CUDA; }
     init = true;
   }
+  return DGE_OK;
+}
+
+int dge_ssim_grad(const float* a, const float* b, const float* go, float* scratch3, float* db, int64_t planes, int h, int w,
+                  void* stream) {
+  DGE_REQUIRE(a && b && go && scratch3 && db && planes > 0 && h > 0 && w > 0, "ssim_grad: bad args");
+  if (int r = ssim_window_init()) return r;
+  const size_t work = (size_t)planes * h * w;
+  k_ssim_grad_maps<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>(a, b, (size_t)planes, h, w, scratch3);
+  count_launch();
+  if (int r = check_launch("k_ssim_grad_maps")) return r;
+  LAUNCH_1D(k_ssim_grad_apply, work, stream, a, b, scratch3, go, (size_t)planes, h, w, db);
+}
+
+int dge_ssim_sum(const float* a, const float* b, int64_t planes, int h, int w, double* out1, void* stream) {
+  DGE_REQUIRE(a && b && out1 && planes > 0 && h > 0 && w > 0, "ssim_sum: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int r = ssim_window_init()) return r;
   if (cudaMemsetAsync(out1, 0, sizeof(double), st) != cudaSuccess) { set_error("ssim_sum: memset failed"); return DGE_ERR_CUDA; }
   LAUNCH_1D(k_ssim_sum, (size_t)planes * h * w, stream, a, b, (size_t)planes, h, w, out1);
 }

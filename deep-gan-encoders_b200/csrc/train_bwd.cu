@@ -249,16 +249,22 @@ k_in_bwd_apply(const float* __restrict__ g, const float* __restrict__ x, const f
 //   with d_pre = d_f * lrelu'(f); img NCHW [n][cimg <= 3][h][w]
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TB_THREADS)
-k_from_rgb_bwd(const float* __restrict__ d_f, const float* __restrict__ f, const float* __restrict__ img, float slope,
-               float* __restrict__ sums, int cimg, int c, int hw) {
+k_from_rgb_bwd(const float* __restrict__ d_f, const float* __restrict__ f, const float* __restrict__ img,
+               const float* __restrict__ wgt, float slope, float* __restrict__ sums, float* __restrict__ d_img, int cimg,
+               int c, int hw) {
   __shared__ float red[TB_THREADS / 32][32];
   const int C8 = c >> 3, ng = blockIdx.y, nidx = ng / C8, grp = ng - nidx * C8;
   float acc[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+  float wk[8][3];   // this group's rows of the 1x1 weight [c][cimg] (image gradient only)
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) wk[k][ci] = (d_img && ci < cimg) ? __ldg(wgt + (size_t)(grp * 8 + k) * cimg + ci) : 0.f;
   const size_t base = (size_t)ng * hw;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)hw; i += (size_t)gridDim.x * blockDim.x) {
-    float dv[8], fv[8], px[3] = {0.f, 0.f, 0.f};
+    float dv[8], fv[8], px[3] = {0.f, 0.f, 0.f}, gi[3] = {0.f, 0.f, 0.f};
     load8_f32b(d_f, base + i, dv);
     load8_f32b(f, base + i, fv);
 #pragma unroll
@@ -271,6 +277,14 @@ k_from_rgb_bwd(const float* __restrict__ d_f, const float* __restrict__ f, const
       acc[4 * k + 1] = fmaf(d, px[1], acc[4 * k + 1]);
       acc[4 * k + 2] = fmaf(d, px[2], acc[4 * k + 2]);
       acc[4 * k + 3] += d;
+      gi[0] = fmaf(d, wk[k][0], gi[0]);
+      gi[1] = fmaf(d, wk[k][1], gi[1]);
+      gi[2] = fmaf(d, wk[k][2], gi[2]);
+    }
+    if (d_img) {   // d img[n][ci] = sum_c W[c][ci] * d_pre[c]: the channel groups of one pixel meet in an atomic add
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci)
+        if (ci < cimg) atomicAdd(d_img + ((size_t)nidx * cimg + ci) * hw + i, gi[ci]);
     }
   }
   const float t = block_sums<32>(acc, red);
@@ -469,6 +483,190 @@ __global__ void k_rgb_up_bwd(const float* __restrict__ d_out, float* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// LPIPS-VGG16 (lpips v0.1 net='vgg'; training_utils.py:93 consumes it): the pieces between the VGG convolutions.
+// The convs themselves are dge_conv_forward with bias + ReLU (slope 0) in the epilogue.
+// ---------------------------------------------------------------------------------------------
+// ScalingLayer + channel padding: NCHW [n][3][h][w] -> ACT [n][16/8][planes][h][w][8] = (x - shift) / scale, channels 3..15 = 0
+__global__ void k_lpips_input(const float* __restrict__ x, void* __restrict__ out, int n, int h, int w, int planes,
+                              float s0, float s1, float s2, float i0, float i1, float i2) {
+  const size_t hw = (size_t)h * w, total = (size_t)n * hw;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / hw, pix = i - b * hw;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    v[0] = (__ldg(x + (b * 3 + 0) * hw + pix) - s0) * i0;
+    v[1] = (__ldg(x + (b * 3 + 1) * hw + pix) - s1) * i1;
+    v[2] = (__ldg(x + (b * 3 + 2) * hw + pix) - s2) * i2;
+    store8_act_at(out, (b * 2 + 0) * planes * hw + pix, hw, planes, v);
+    store8_act_at(out, (b * 2 + 1) * planes * hw + pix, hw, planes, z);
+  }
+}
+
+// nn.MaxPool2d(2, 2) (floor mode) F32B [n][c/8][h][w][8] -> ACT [n][c/8][planes][h/2][w/2][8]
+__global__ void k_maxpool_to_act(const float* __restrict__ x, void* __restrict__ out, int n, int c, int h, int w,
+                                 int planes) {
+  const int C8 = c >> 3, ho = h >> 1, wo = w >> 1;
+  const size_t total = (size_t)n * C8 * ho * wo;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int px = (int)(i % wo);
+    size_t t = i / wo;
+    const int py = (int)(t % ho);
+    const size_t ng = t / ho;
+    float m[8];
+    load8_f32b(x, (ng * h + 2 * py) * w + 2 * px, m);
+#pragma unroll
+    for (int q = 1; q < 4; ++q) {
+      float v[8];
+      load8_f32b(x, (ng * h + 2 * py + (q >> 1)) * w + 2 * px + (q & 1), v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], v[k]);
+    }
+    store8_act_at(out, (ng * planes * ho + py) * (size_t)wo + px, (size_t)ho * wo, planes, m);
+  }
+}
+
+// Backward of [ReLU -> (tap) -> MaxPool2d(2,2)]: the gradient of a conv's pre-activation as the ACT operand of its
+// data-gradient conv.   d_pre = (y > 0) * ( g_same + (this pixel is the arg-max of its 2x2 window ? g_pool[y/2][x/2] : 0) )
+//   y: the activated conv output, F32B (y_act == NULL) or ACT (only its hi plane is read: the sign);  g_same: F32B at the
+//   same resolution (NULL: none);  g_pool: F32B at (h/2, w/2), routed to the FIRST maximum of each window in row-major order
+//   (torch's max_pool2d tie rule; ties at 0 are masked by the ReLU anyway) (NULL: none).  Thread = one 2x2 window.
+__global__ void k_relu_pool_bwd(const float* __restrict__ y_f32b, const void* __restrict__ y_act, int y_planes,
+                                const float* __restrict__ g_same, const float* __restrict__ g_pool,
+                                void* __restrict__ out, int n, int c, int h, int w, int planes) {
+  const int C8 = c >> 3, hc = (h + 1) >> 1, wc = (w + 1) >> 1, ho = h >> 1, wo = w >> 1;
+  const size_t total = (size_t)n * C8 * hc * wc, hw = (size_t)h * w;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int px = (int)(i % wc);
+    size_t t = i / wc;
+    const int py = (int)(t % hc);
+    const size_t ng = t / hc;
+    float yv[4][8];
+    bool in[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int yy = 2 * py + (q >> 1), xx = 2 * px + (q & 1);
+      in[q] = yy < h && xx < w;
+      if (in[q]) {
+        if (y_act) {
+          const uint4* yp = reinterpret_cast<const uint4*>(y_act) + ng * y_planes * hw + (size_t)yy * w + xx;
+          unpack8(__ldg(yp), yv[q]);
+          if (y_planes == 2 && g_pool) {   // the arg-max needs hi + lo; the ReLU mask alone is decided by the hi plane
+            float l[8];
+            unpack8(__ldg(yp + hw), l);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) yv[q][k] += l[k];
+          }
+        } else {
+          load8_f32b(y_f32b, ng * hw + (size_t)yy * w + xx, yv[q]);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) yv[q][k] = -1.f;
+      }
+    }
+    float gp[8];
+    const bool pooled = g_pool && py < ho && px < wo;
+    if (pooled) load8_f32b(g_pool, (ng * ho + py) * (size_t)wo + px, gp);
+    int am[8];
+    if (pooled) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        int a = 0;
+        float mv = yv[0][k];
+#pragma unroll
+        for (int q = 1; q < 4; ++q)
+          if (yv[q][k] > mv) { mv = yv[q][k]; a = q; }
+        am[k] = a;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (!in[q]) continue;
+      const size_t pix = (size_t)(2 * py + (q >> 1)) * w + 2 * px + (q & 1);
+      float g[8];
+      if (g_same) {
+        load8_f32b(g_same, ng * hw + pix, g);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] = 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (pooled && am[k] == q) g[k] += gp[k];
+        g[k] = yv[q][k] > 0.f ? g[k] : 0.f;
+      }
+      store8_act_at(out, ng * planes * hw + pix, hw, planes, g);
+    }
+  }
+}
+
+// LPIPS distance of one tap (lpips: normalize_tensor, squared difference, 1x1 `lin`, spatial mean):
+//   out[n] += (1/HW) sum_p sum_c w_c (a_c / (|a|+eps) - b_c / (|b|+eps))^2,   a = f[n], b = f[n + nb]   (f: F32B, 2*nb samples)
+// Thread = one pixel: four channel sums give everything (also for the backward):
+//   Saa = sum a^2, Sbb = sum b^2, Waa = sum w a^2, Wbb = sum w b^2, Wab = sum w a b ;  d = Waa/na^2 + Wbb/nb^2 - 2 Wab/(na nb)
+// grad_mode: 0 = forward; 1 = gradient w.r.t. b -> gb (F32B [nb]); 2 = w.r.t. a -> ga; 3 = both.  go[n] = upstream gradient.
+__global__ void __launch_bounds__(256)
+k_lpips_dist(const float* __restrict__ f, const float* __restrict__ lw, float* __restrict__ out,
+             const float* __restrict__ go, float* __restrict__ ga, float* __restrict__ gb, int grad_mode, int nb, int c,
+             int hw, float eps) {
+  __shared__ float red[8];
+  const int C8 = c >> 3, n = blockIdx.y;
+  const float inv_hw = 1.f / (float)hw;
+  float part = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)hw; i += (size_t)gridDim.x * blockDim.x) {
+    float saa = 0.f, sbb = 0.f, waa = 0.f, wbb = 0.f, wab = 0.f;
+    for (int g = 0; g < C8; ++g) {
+      float a[8], b[8];
+      load8_f32b(f, ((size_t)n * C8 + g) * hw + i, a);
+      load8_f32b(f, ((size_t)(n + nb) * C8 + g) * hw + i, b);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float w = __ldg(lw + g * 8 + k);
+        saa = fmaf(a[k], a[k], saa);
+        sbb = fmaf(b[k], b[k], sbb);
+        waa = fmaf(w * a[k], a[k], waa);
+        wbb = fmaf(w * b[k], b[k], wbb);
+        wab = fmaf(w * a[k], b[k], wab);
+      }
+    }
+    const float ra = sqrtf(saa), rb = sqrtf(sbb), na = ra + eps, nbn = rb + eps;
+    if (grad_mode == 0) {
+      part += waa / (na * na) + wbb / (nbn * nbn) - 2.f * wab / (na * nbn);
+      continue;
+    }
+    // u = a/na, v = b/nbn;  dD/dv_c = -2 w_c (u_c - v_c);  dv_c/db_k = delta_ck/nbn - b_c b_k/(nbn^2 rb)
+    //   dD/db_k = (1/nbn) [ gv_k - b_k/(nbn rb) * sum_c gv_c b_c ],  sum_c gv_c b_c = -2 (wab/na - wbb/nbn)   (a: symmetric)
+    const float scale = __ldg(go + n) * inv_hw;
+    const float sgb = -2.f * (wab / na - wbb / nbn), sga = -2.f * (wab / nbn - waa / na);
+    const float cb = rb > 0.f ? sgb / (nbn * rb) : 0.f, ca = ra > 0.f ? sga / (na * ra) : 0.f;
+    for (int g = 0; g < C8; ++g) {
+      float a[8], b[8], da[8], db[8];
+      load8_f32b(f, ((size_t)n * C8 + g) * hw + i, a);
+      load8_f32b(f, ((size_t)(n + nb) * C8 + g) * hw + i, b);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float w = __ldg(lw + g * 8 + k);
+        const float diff = a[k] / na - b[k] / nbn;
+        db[k] = scale * (-2.f * w * diff - b[k] * cb) / nbn;
+        da[k] = scale * (2.f * w * diff - a[k] * ca) / na;
+      }
+      if (grad_mode & 1) store8_f32b(gb, ((size_t)n * C8 + g) * hw + i, db);
+      if (grad_mode & 2) store8_f32b(ga, ((size_t)n * C8 + g) * hw + i, da);
+    }
+  }
+  if (grad_mode == 0) {
+#pragma unroll
+    for (int off = 16; off; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+      atomicAdd(out + n, t * inv_hw);
+    }
+  }
+}
+
 }  // namespace dge
 
 using namespace dge;
@@ -533,14 +731,16 @@ extern "C" int dge_in_bwd_apply(const float* g, const float* x, const float* mea
   return check_launch("k_in_bwd_apply");
 }
 
-extern "C" int dge_from_rgb_bwd(const float* d_f, const float* f, const float* img, float slope, float* sums, int n,
-                                int cimg, int c, int h, int w, void* stream) {
+extern "C" int dge_from_rgb_bwd(const float* d_f, const float* f, const float* img, const float* wgt, float slope,
+                                float* sums, float* d_img, int n, int cimg, int c, int h, int w, void* stream) {
   DGE_REQUIRE(d_f && f && img && sums, "from_rgb_bwd: null pointer");
+  DGE_REQUIRE(!d_img || wgt, "from_rgb_bwd: d_img needs the weight");
+  if (d_img) TB_ZERO(d_img, (size_t)n * cimg * h * w * sizeof(float));
   DGE_REQUIRE(n > 0 && cimg >= 1 && cimg <= 3 && c >= 8 && c % 8 == 0 && h > 0 && w > 0,
               "from_rgb_bwd: bad dims n=%d cimg=%d c=%d h=%d w=%d", n, cimg, c, h, w);
   TB_ZERO(sums, (size_t)4 * c * sizeof(float));
   dim3 grid(tb_splits((long long)h * w, (long long)n * (c / 8)), n * (c / 8));
-  k_from_rgb_bwd<<<grid, TB_THREADS, 0, TB_STREAM>>>(d_f, f, img, slope, sums, cimg, c, h * w);
+  k_from_rgb_bwd<<<grid, TB_THREADS, 0, TB_STREAM>>>(d_f, f, img, wgt, slope, sums, d_img, cimg, c, h * w);
   count_launch();
   return check_launch("k_from_rgb_bwd");
 }
@@ -589,4 +789,56 @@ extern "C" int dge_rgb_up_bwd(const float* d_out, float* d_in, int64_t planes, i
   k_rgb_up_bwd<<<(int)g, 256, 0, TB_STREAM>>>(d_out, d_in, (size_t)planes, h_in, w_in);
   count_launch();
   return check_launch("k_rgb_up_bwd");
+}
+
+static int tb_grid1d(size_t work, int block) {
+  size_t g = (work + block - 1) / block;
+  if (g > (size_t)tb_sms() * 32) g = (size_t)tb_sms() * 32;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+extern "C" int dge_lpips_input(const float* x, void* out_act, float shift0, float shift1, float shift2, float scale0,
+                               float scale1, float scale2, int n, int h, int w, int planes, void* stream) {
+  DGE_REQUIRE(x && out_act && n > 0 && h > 0 && w > 0 && (planes == 1 || planes == 2) && scale0 != 0.f && scale1 != 0.f &&
+                  scale2 != 0.f, "lpips_input: bad arguments");
+  k_lpips_input<<<tb_grid1d((size_t)n * h * w, 256), 256, 0, TB_STREAM>>>(x, out_act, n, h, w, planes, shift0, shift1,
+                                                                          shift2, 1.f / scale0, 1.f / scale1, 1.f / scale2);
+  count_launch();
+  return check_launch("k_lpips_input");
+}
+
+extern "C" int dge_maxpool_to_act(const float* x, void* out_act, int n, int c, int h, int w, int planes, void* stream) {
+  DGE_REQUIRE(x && out_act && n > 0 && c >= 8 && c % 8 == 0 && h >= 2 && w >= 2 && (planes == 1 || planes == 2),
+              "maxpool_to_act: bad arguments");
+  k_maxpool_to_act<<<tb_grid1d((size_t)n * (c / 8) * (h / 2) * (w / 2), 256), 256, 0, TB_STREAM>>>(x, out_act, n, c, h, w,
+                                                                                                  planes);
+  count_launch();
+  return check_launch("k_maxpool_to_act");
+}
+
+extern "C" int dge_relu_pool_bwd(const float* y_f32b, const void* y_act, int y_planes, const float* g_same,
+                                 const float* g_pool, void* out_act, int n, int c, int h, int w, int planes, void* stream) {
+  DGE_REQUIRE((y_f32b || y_act) && !(y_f32b && y_act) && out_act && (g_same || g_pool), "relu_pool_bwd: bad pointers");
+  DGE_REQUIRE(n > 0 && c >= 8 && c % 8 == 0 && h > 0 && w > 0 && (planes == 1 || planes == 2) &&
+                  (!y_act || y_planes == 1 || y_planes == 2), "relu_pool_bwd: bad dims");
+  DGE_REQUIRE(!g_pool || (h >= 2 && w >= 2), "relu_pool_bwd: pooled gradient needs h, w >= 2");
+  k_relu_pool_bwd<<<tb_grid1d((size_t)n * (c / 8) * ((h + 1) / 2) * ((w + 1) / 2), 256), 256, 0, TB_STREAM>>>(
+      y_f32b, y_act, y_planes, g_same, g_pool, out_act, n, c, h, w, planes);
+  count_launch();
+  return check_launch("k_relu_pool_bwd");
+}
+
+extern "C" int dge_lpips_dist(const float* f, const float* lin_w, float* out, const float* go, float* ga, float* gb,
+                              int nb, int c, int h, int w, float eps, void* stream) {
+  DGE_REQUIRE(f && lin_w && nb > 0 && c >= 8 && c % 8 == 0 && h > 0 && w > 0, "lpips_dist: bad arguments");
+  const int mode = (gb ? 1 : 0) | (ga ? 2 : 0);
+  DGE_REQUIRE(mode ? go != nullptr : out != nullptr, "lpips_dist: forward needs out, backward needs go");
+  long long blocks = ((long long)h * w + 255) / 256, want = ((long long)tb_sms() * 8 + nb - 1) / nb;
+  if (blocks > want) blocks = want;
+  if (blocks < 1) blocks = 1;
+  dim3 grid((unsigned)blocks, (unsigned)nb);
+  k_lpips_dist<<<grid, 256, 0, TB_STREAM>>>(f, lin_w, out, go, ga, gb, mode, nb, c, h * w, eps);
+  count_launch();
+  return check_launch("k_lpips_dist");
 }

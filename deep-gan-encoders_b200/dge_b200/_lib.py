@@ -91,6 +91,7 @@ SIGNATURES = {
     "dge_softmax_kl_sum": (c_int, [P, P, c_int64, c_int, c_int64, P, P]),
     "dge_avgpool_nchw": (c_int, [P, P, c_int64, c_int, c_int, c_int, P]),
     "dge_ssim_sum": (c_int, [P, P, c_int64, c_int, c_int, P, P]),
+    "dge_ssim_grad": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, P]),
     "dge_instance_norm_affine": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "dge_pixelnorm_to_act": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, P]),
     "dge_pixelnorm_to_rgb": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P]),
@@ -112,11 +113,15 @@ SIGNATURES = {
     "dge_in_bwd_stats": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P]),
     "dge_in_bwd_apply": (c_int, [P, P, P, P, P, P, c_int, P, c_float, c_int, P, c_float, P, P, P, c_int, c_int, c_int,
                                  c_int, c_int, P]),
-    "dge_from_rgb_bwd": (c_int, [P, P, P, c_float, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "dge_from_rgb_bwd": (c_int, [P, P, P, P, c_float, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "dge_sg2_layer_bwd": (c_int, [P, P, P, P, P, P, c_int64, c_float, P, P, c_float, c_float, P, c_int, P, P, c_int, c_int,
                                   c_int, c_int, c_int, P]),
     "dge_up_fir_bwd_s2d": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "dge_rgb_up_bwd": (c_int, [P, P, c_int64, c_int, c_int, P]),
+    "dge_lpips_input": (c_int, [P, P, c_float, c_float, c_float, c_float, c_float, c_float, c_int, c_int, c_int, c_int, P]),
+    "dge_maxpool_to_act": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "dge_relu_pool_bwd": (c_int, [P, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "dge_lpips_dist": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_float, P]),
     "dge_blend": (c_int, [P, P, P, c_float, c_float, c_int, c_int, c_int, c_int, c_int, P]),
 }
 

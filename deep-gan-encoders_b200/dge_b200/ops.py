@@ -680,15 +680,18 @@ def in_bwd_apply(g, x, mean_rstd, style, dstyle, sums, mode, res=None, rscale=0.
     return out, sums2
 
 
-def from_rgb_bwd(d_f, f, img, slope=0.2):
-    """FromRGB backward -> fp32 [c, 4] = (dW[c, 0..2], db[c])."""
+def from_rgb_bwd(d_f, f, img, slope=0.2, weight=None):
+    """FromRGB backward -> fp32 [c, 4] = (dW[c, 0..2], db[c]); with `weight` ([c, cimg, 1, 1]) also the image gradient:
+    -> (sums, d_img NCHW)."""
     assert isinstance(d_f, F32B) and isinstance(f, F32B)
     img = img.contiguous()
     sums = torch.empty((f.c, 4), dtype=torch.float32, device=f.t.device)
+    d_img = torch.empty_like(img) if weight is not None else None
+    wq = None if weight is None else weight.detach().contiguous()
     with _rec("from_rgb_bwd", (f.n, f.h, f.w, f.c)):
-        check(lib().dge_from_rgb_bwd(_p(d_f.t), _p(f.t), _f32(img), float(slope), _p(sums), f.n, img.shape[1], f.c, f.h,
-                                     f.w, _stream()))
-    return sums
+        check(lib().dge_from_rgb_bwd(_p(d_f.t), _p(f.t), _f32(img), _f32(wq), float(slope), _p(sums), _p(d_img), f.n,
+                                     img.shape[1], f.c, f.h, f.w, _stream()))
+    return sums if weight is None else (sums, d_img)
 
 
 def sg2_prep_all(S, wp32, layers, outputs):
@@ -732,6 +735,60 @@ def rgb_up_bwd(d_out):
     out = torch.empty((n, ch, ho // 2, wo // 2), dtype=torch.float32, device=d_out.device)
     check(lib().dge_rgb_up_bwd(_f32(d_out), _p(out), n * ch, ho // 2, wo // 2, _stream()))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# LPIPS-VGG16 pieces (csrc/train_bwd.cu)
+# ------------------------------------------------------------------------------------------------
+def lpips_input(x, shift, scale, planes=2):
+    """ScalingLayer + padding to 16 channels: NCHW [n, 3, h, w] -> Act [n, 16, h, w]."""
+    x = x.contiguous()
+    n, c, h, w = x.shape
+    assert c == 3, "lpips_input: RGB images"
+    out = Act(n, 16, h, w, planes, x.device)
+    check(lib().dge_lpips_input(_f32(x), _p(out.t), *[float(v) for v in shift], *[float(v) for v in scale], n, h, w, planes,
+                                _stream()))
+    return out
+
+
+def maxpool_to_act(x, planes=2):
+    assert isinstance(x, F32B)
+    out = Act(x.n, x.c, x.h // 2, x.w // 2, planes, x.t.device)
+    with _rec("maxpool_to_act", (x.n, x.h, x.w, x.c)):
+        check(lib().dge_maxpool_to_act(_p(x.t), _p(out.t), x.n, x.c, x.h, x.w, planes, _stream()))
+    return out
+
+
+def relu_pool_bwd(y, g_same=None, g_pool=None, planes=2):
+    """(y > 0) * (g_same + arg-max-routed g_pool) -> Act; y is the activated conv output (F32B or Act)."""
+    assert isinstance(y, (F32B, Act)) and (g_same is not None or g_pool is not None)
+    out = Act(y.n, y.c, y.h, y.w, planes, y.t.device)
+    is_act = isinstance(y, Act)
+    with _rec("relu_pool_bwd", (y.n, y.h, y.w, y.c)):
+        check(lib().dge_relu_pool_bwd(None if is_act else _p(y.t), _p(y.t) if is_act else None, y.planes if is_act else 0,
+                                      _p(g_same.t) if g_same is not None else None,
+                                      _p(g_pool.t) if g_pool is not None else None, _p(out.t), y.n, y.c, y.h, y.w, planes,
+                                      _stream()))
+    return out
+
+
+def lpips_dist(f, lin_w, out, eps=1e-10):
+    """Adds one tap's distance into out[nb]; f = F32B features of the 2*nb images (first half vs second half)."""
+    assert isinstance(f, F32B) and f.n % 2 == 0
+    with _rec("lpips_dist", (f.n, f.h, f.w, f.c)):
+        check(lib().dge_lpips_dist(_p(f.t), _f32(lin_w), _p(out), None, None, None, f.n // 2, f.c, f.h, f.w, float(eps),
+                                   _stream()))
+
+
+def lpips_dist_bwd(f, lin_w, go, want_a, want_b, eps=1e-10):
+    """-> (ga, gb): F32B gradients of the tap distance w.r.t. the first / second half of f (None if not wanted)."""
+    nb = f.n // 2
+    ga = F32B(nb, f.c, f.h, f.w, f.t.device) if want_a else None
+    gb = F32B(nb, f.c, f.h, f.w, f.t.device) if want_b else None
+    with _rec("lpips_dist_bwd", (f.n, f.h, f.w, f.c)):
+        check(lib().dge_lpips_dist(_p(f.t), _f32(lin_w), None, _f32(go.contiguous()), _p(ga.t) if ga is not None else None,
+                                   _p(gb.t) if gb is not None else None, nb, f.c, f.h, f.w, float(eps), _stream()))
+    return ga, gb
 
 
 def launch_count():

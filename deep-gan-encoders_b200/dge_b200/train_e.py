@@ -46,16 +46,14 @@ class _FromRGBFn(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, d_f, _ds, _dmr):
         img, f_t, weight = ctx.saved_tensors
-        sums = K.from_rgb_bwd(_f32b(d_f.contiguous()), _f32b(f_t), img, SLOPE)
+        d_img = None
+        if ctx.needs_input_grad[0]:      # embedding_img.py:88 -- E(imgs2) back-propagates into the generator
+            sums, d_img = K.from_rgb_bwd(_f32b(d_f.contiguous()), _f32b(f_t), img, SLOPE, weight=weight)
+        else:
+            sums = K.from_rgb_bwd(_f32b(d_f.contiguous()), _f32b(f_t), img, SLOPE)
         cimg = img.shape[1]
         dw = sums[:, :cimg].reshape(weight.shape)
         db = sums[:, 3].contiguous()
-        d_img = None
-        if ctx.needs_input_grad[0]:
-            # only a caller that optimises the input image itself gets here (none of the encoder scripts does):
-            # d_img = W^T (d_f * lrelu'(f)) as two small torch ops on the NCHW views
-            dpre = _f32b(d_f.contiguous()).to_nchw() * torch.where(_f32b(f_t).to_nchw() > 0, 1.0, SLOPE)
-            d_img = torch.einsum('nchw,ci->nihw', dpre, weight.view(weight.shape[0], cimg))
         return d_img, dw, db, None
 
 

@@ -40,6 +40,9 @@ import torch.nn.functional as F
 
 from dge_b200 import autograd as tc
 from dge_b200 import ops
+from dge_b200 import train_lpips
+
+FUSED = True      # False: the graph of separate torch nodes (`_distance`), kept as the cross-check
 
 
 def _find_weights():
@@ -190,6 +193,16 @@ class LPIPS(nn.Module):
     def forward(self, in0, in1, retPerLayer=False, normalize=False):
         if not (in0.is_cuda and in1.is_cuda):
             raise ops.DgeError('LPIPS: dge_b200 runs on a B200 only; there is no CPU fallback')
+        # the scripts use the metric as a fixed loss (eval mode, VGG frozen; the `lin` layers are parameters of the package
+        # but never reach an optimiser): the fused node returns no gradients for them
+        frozen = not self.pnet_tune and not self.training
+        if FUSED and frozen and not retPerLayer and in0.shape == in1.shape and in0.shape[1] == 3 \
+                and min(in0.shape[2:]) >= 32:
+            # one fused autograd node (dge_b200/train_lpips.py): convs with bias + ReLU epilogues, tap distances and the
+            # whole backward on dge_b200 kernels
+            if normalize:
+                in0, in1 = 2 * in0 - 1, 2 * in1 - 1
+            return train_lpips.distance(self, in0, in1, self.net.planes)
         return self._distance(in0, in1, retPerLayer, normalize)
 
     def _distance(self, in0, in1, retPerLayer=False, normalize=False):

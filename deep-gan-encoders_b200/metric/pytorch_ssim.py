@@ -33,10 +33,43 @@ def _ssim_mean_autograd(a, b):
     return (num / den).mean()
 
 
+class _SsimMeanFn(torch.autograd.Function):
+    """mean(SSIM map) with the fused forward kernel and the two-pass fused backward (dge_ssim_grad); SSIM is symmetric in
+    its arguments, so the gradient w.r.t. the first image is the same kernel with the roles swapped."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        n, c, h, w = a.shape
+        out = torch.empty(1, dtype=torch.float64, device=a.device)
+        ops.check(ops.lib().dge_ssim_sum(ops._p(a), ops._p(b), n * c, h, w, ops._p(out), ops._stream()))
+        ctx.save_for_backward(a, b)
+        return (out / float(a.numel())).float().view(())
+
+    @staticmethod
+    def backward(ctx, go):
+        a, b = ctx.saved_tensors
+        n, c, h, w = a.shape
+        go = go.contiguous().float().view(1)
+        scratch = torch.empty((3,) + tuple(a.shape), dtype=torch.float32, device=a.device)
+        grads = [None, None]
+        for i, (x, y) in enumerate(((b, a), (a, b))):         # gradient w.r.t. y with x as the other image
+            if ctx.needs_input_grad[i]:
+                g = torch.empty_like(y)
+                ops.check(ops.lib().dge_ssim_grad(ops._p(x), ops._p(y), ops._p(go), ops._p(scratch), ops._p(g), n * c, h, w,
+                                                  ops._stream()))
+                grads[i] = g
+        return grads[0], grads[1]
+
+
+FUSED_TRAIN = True     # False: `_ssim_mean_autograd` (separate torch nodes), the cross-check of the fused node
+
+
 def _ssim_mean(img1, img2):
     if not (img1.is_cuda and img2.is_cuda):
         raise ops.DgeError('ssim: dge_b200 runs on a B200 only; there is no CPU fallback')
     if torch.is_grad_enabled() and (img1.requires_grad or img2.requires_grad):
+        if FUSED_TRAIN:
+            return _SsimMeanFn.apply(img1.float().contiguous(), img2.float().contiguous())
         return _ssim_mean_autograd(img1.float(), img2.float())
     assert img1.shape == img2.shape and img1.ndim == 4
     a, b = img1.float().contiguous(), img2.float().contiguous()

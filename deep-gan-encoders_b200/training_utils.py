@@ -111,27 +111,90 @@ def _stats_from_sums(host, n):
     return mse1, mse2, mse3, kl, cos
 
 
+class _MseCosFn(torch.autograd.Function):
+    """(MSE, 1 - cosine) of two tensors from the six sums `dge_pair_moments` already produced for the log (:63, :74-76).
+    Backward is linear in the inputs: d/db = alpha * a + beta * b with two device scalars (no host sync)."""
+
+    @staticmethod
+    def forward(ctx, a, b, acc):
+        n = a.numel()
+        sa, sb, saa, sbb, sab, sdd = acc[0], acc[1], acc[2], acc[3], acc[4], acc[5]
+        ctx.save_for_backward(a, b, acc)
+        mse = (sdd / n).float()
+        cos = (1 - sab / (saa.sqrt() * sbb.sqrt())).float()
+        return mse, cos
+
+    @staticmethod
+    def backward(ctx, g_mse, g_cos):
+        a, b, acc = ctx.saved_tensors
+        n = a.numel()
+        saa, sbb, sab = acc[2], acc[3], acc[4]
+        na, nb = saa.sqrt(), sbb.sqrt()
+        gm, gc = g_mse.double(), g_cos.double()
+        grads = [None, None]
+        # d mse/d b = 2 (b - a) / n ;  d (1 - cos)/d b = -a / (|a||b|) + (a.b) b / (|a||b|^3)   (and symmetrically for a)
+        if ctx.needs_input_grad[1]:
+            alpha = (-2 * gm / n - gc / (na * nb)).float()
+            beta = (2 * gm / n + gc * sab / (na * nb * sbb)).float()
+            grads[1] = torch.addcmul(a * alpha, b, beta)
+        if ctx.needs_input_grad[0]:
+            alpha = (-2 * gm / n - gc / (na * nb)).float()
+            beta = (2 * gm / n + gc * sab / (na * nb * saa)).float()
+            grads[0] = torch.addcmul(b * alpha, a, beta)
+        return grads[0], grads[1], None
+
+
+class _AvgPoolFn(torch.autograd.Function):
+    """`while x.shape[2] > 256: x = F.avg_pool2d(x, 2, 2)` (:81-84) as one f x f mean; backward = broadcast / f^2."""
+
+    @staticmethod
+    def forward(ctx, x, f):
+        ctx.f = f
+        return avg_pool_to_256(x.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        f = ctx.f
+        return F.interpolate(g, scale_factor=f, mode='nearest') / float(f * f), None
+
+
+FUSED_TRAIN = True     # False: the loss terms as separate torch nodes (cross-check of the fused nodes)
+
+
 def _space_loss_autograd(a, b, image_space, lpips_model):
-    """Training form (E_align_s2.py:184-205 back-propagates through this loss): the four terms that make up the loss
-    are recorded for backward as torch CUDA ops; the statistics that are only logged (mean / std MSE, KL) still come
-    from the fused reduction kernels on the detached values."""
+    """Training form (E_align_s2.py:184-205 back-propagates through this loss).  The log statistics and the MSE / cosine
+    terms come from ONE pass of the fused moments kernel (`_MseCosFn`: their gradient is alpha*a + beta*b), the pooled SSIM
+    and LPIPS terms are fused nodes too (metric/pytorch_ssim.py, dge_b200/train_lpips.py); one host read-back per call."""
     n = a.numel()
-    host = _pair_stats(a.detach(), b.detach()).cpu().tolist()
-    mse1, mse2, mse3, kl, _ = _stats_from_sums(host, n)
-    fa, fb = a.reshape(-1), b.reshape(-1)
-    mse = (fa - fb).square().mean()                                                # :63
-    cos = 1 - fa.dot(fb) / (fa.dot(fa).sqrt() * fb.dot(fb).sqrt())                 # :74-76
+    acc = _pair_stats(a.detach(), b.detach())
+    if FUSED_TRAIN:
+        mse, cos = _MseCosFn.apply(a, b, acc)
+    else:
+        fa, fb = a.reshape(-1), b.reshape(-1)
+        mse = (fa - fb).square().mean()                                            # :63
+        cos = 1 - fa.dot(fb) / (fa.dot(fa).sqrt() * fb.dot(fb).sqrt())             # :74-76
     if image_space:
         f = 1
         while a.shape[2] // f > 256:                                               # :81-84 (2x2 means compose)
             f *= 2
-        pa, pb = (a, b) if f == 1 else (F.avg_pool2d(a, f, f), F.avg_pool2d(b, f, f))
+        if f == 1:
+            pa, pb = a, b
+        elif FUSED_TRAIN:
+            pa, pb = _AvgPoolFn.apply(a, f), _AvgPoolFn.apply(b, f)
+        else:
+            pa, pb = F.avg_pool2d(a, f, f), F.avg_pool2d(b, f, f)
         ssim_l = 1 - pytorch_ssim.ssim(pa, pb)                                     # :87-88
         lp = lpips_model(pa, pb).mean()                                            # :93
+        extra = torch.stack((cos.detach().double(), ssim_l.detach().double(), lp.detach().double()))
     else:
         ssim_l, lp = torch.tensor(0), torch.tensor(0)                              # :90, 95
+        extra = cos.detach().double().view(1)
     loss = 5 * mse + 3 * cos + ssim_l + 2 * lp                                     # :97
-    return loss, [[mse1, mse2, mse3], kl, cos.item(), ssim_l.item(), lp.item()]
+    host = torch.cat((acc, extra)).cpu().tolist()                                  # the one host read-back of this call
+    mse1, mse2, mse3, kl, _ = _stats_from_sums(host[:8], n)
+    if image_space:
+        return loss, [[mse1, mse2, mse3], kl, host[8], host[9], host[10]]
+    return loss, [[mse1, mse2, mse3], kl, host[8], 0, 0]
 
 
 def space_loss(imgs1, imgs2, image_space=True, lpips_model=None):

@@ -288,6 +288,12 @@ int dge_avgpool_nchw(const float* x, float* out, int64_t planes, int h_out, int 
 /* sum of the SSIM map (11x11 gaussian sigma 1.5, zero padding, C1=1e-4, C2=9e-4) over [planes][h][w] */
 int dge_ssim_sum(const float* a, const float* b, int64_t planes, int h, int w, double* out1, void* stream);
 
+/* Gradient of mean(SSIM map) w.r.t. the SECOND image (the one the generator produced; pytorch_ssim.py:18-38 under
+   loss.backward(), training_utils.py:87-88): db[planes][h][w] = go[0] * d mean(ssim(a, b)) / d b.  go: one device float (the
+   upstream gradient); scratch3: 3 * planes*h*w floats. */
+int dge_ssim_grad(const float* a, const float* b, const float* go, float* scratch3, float* db, int64_t planes, int h, int w,
+                  void* stream);
+
 /* ---- Grad-CAM (metric/grad_cam.py:101-194) ---------------------------------------------------- */
 /* idx_out[n] = np.argmax(logits, axis=1) (first maximum); *mode_out = np.argmax(np.bincount(idx)) (:164-165). Bit-exact. */
 int dge_argmax_mode(const float* logits, int n, int k, int64_t* idx_out, int64_t* mode_out, void* stream);
@@ -335,9 +341,11 @@ int dge_in_bwd_apply(const float* g, const float* x, const float* mean_rstd, con
                      float slope, float* out_f32b, void* out_act, float* sums2, int n, int c, int h, int w, int planes,
                      void* stream);
 /* FromRGB backward (net.py:231-240, f = lrelu(conv1x1(img, W) + b)): sums fp32 [c][4] = (dW[c][0..2], db[c]) with
-   d_pre = d_f * (f > 0 ? 1 : slope); d_f, f F32B [n][c/8][h][w][8]; img NCHW [n][cimg<=3][h][w]. */
-int dge_from_rgb_bwd(const float* d_f, const float* f, const float* img, float slope, float* sums, int n, int cimg, int c,
-                     int h, int w, void* stream);
+   d_pre = d_f * (f > 0 ? 1 : slope); d_f, f F32B [n][c/8][h][w][8]; img NCHW [n][cimg<=3][h][w].
+   d_img (optional, NCHW like img; zeroed by the call): the image gradient sum_c wgt[c][i] * d_pre[c] -- the inversion loop
+   of embedding_img.py:86-88 back-propagates through E(imgs2) into the generator; wgt = the 1x1 weight [c][cimg]. */
+int dge_from_rgb_bwd(const float* d_f, const float* f, const float* img, const float* wgt, float slope, float* sums,
+                     float* d_img, int n, int cimg, int c, int h, int w, void* stream);
 
 /* Backward of everything that follows the contraction in a StyleGAN2 synthesis layer (stylegan2_generator.py:907-921:
    y = lrelu(conv*dm + noise*ns + b)*gain), plus the two consumers of y: the next layer (y * s_next, :877) and ToRGB
@@ -364,6 +372,28 @@ int dge_up_fir_bwd_s2d(const float* dconv, void* out_act, int n, int c, int h, i
 /* Transpose of dge_rgb_init's x2 up-sampling of the skip image (:519-522): d_in [planes][h_in][w_in] from
    d_out [planes][2h_in][2w_in]; per axis d_in[m] = (d[2m-1] + 3d[2m] + 3d[2m+1] + d[2m+2])/4. */
 int dge_rgb_up_bwd(const float* d_out, float* d_in, int64_t planes, int h_in, int w_in, void* stream);
+
+/* ---- LPIPS-VGG16 perceptual distance (third-party `lpips.LPIPS(net='vgg')`, E_align_s2.py:98; consumed by
+        training_utils.py:93) -- the pieces between the VGG convolutions; the convs are dge_conv_forward with the bias and the
+        ReLU (slope 0) in the epilogue, forward and data gradient.  PARITY UNPINNED (no reference vectors offline). ---- */
+/* ScalingLayer + channel padding: NCHW [n][3][h][w] -> ACT [n][16/8][planes][h][w][8] = (x - shift[c]) / scale[c], channels
+   3..15 zero (the first VGG conv then runs on the tensor cores with a zero-padded [64][16][3][3] weight). */
+int dge_lpips_input(const float* x, void* out_act, float shift0, float shift1, float shift2, float scale0, float scale1,
+                    float scale2, int n, int h, int w, int planes, void* stream);
+/* nn.MaxPool2d(2, 2), floor mode: F32B [n][c/8][h][w][8] -> ACT [n][c/8][planes][h/2][w/2][8] (the next conv's operand). */
+int dge_maxpool_to_act(const float* x_f32b, void* out_act, int n, int c, int h, int w, int planes, void* stream);
+/* Backward of [ReLU -> MaxPool2d(2,2)] into the ACT operand of the conv's data gradient:
+     out = (y > 0) * (g_same + (pixel is the first maximum of its 2x2 window ? g_pool[y/2][x/2] : 0))
+   y = the activated conv output: F32B (y_f32b) or ACT (y_act, y_planes: hi (+ lo) planes; an ACT holds ~17 bits, so window
+   maxima closer than that may route differently from the fp32 map -- the LPIPS node keeps its pooled taps in F32B) -- exactly one;
+   g_same F32B [n][c/8][h][w][8] or NULL; g_pool F32B [n][c/8][h/2][w/2][8] or NULL (at least one). */
+int dge_relu_pool_bwd(const float* y_f32b, const void* y_act, int y_planes, const float* g_same, const float* g_pool,
+                      void* out_act, int n, int c, int h, int w, int planes, void* stream);
+/* One LPIPS tap: f F32B [2*nb][c/8][h][w][8] holds the features of the two image batches (a = f[0:nb], b = f[nb:2nb]).
+   forward  (ga == gb == NULL): out[n] += mean_p sum_c lin_w[c] * (a_c/(|a|+eps) - b_c/(|b|+eps))^2      (out: caller-zeroed)
+   backward (go = upstream gradient [nb]): gb / ga (F32B [nb][c/8][h][w][8], either may be NULL) = d out / d b, d out / d a. */
+int dge_lpips_dist(const float* f, const float* lin_w, float* out, const float* go, float* ga, float* gb, int nb, int c,
+                   int h, int w, float eps, void* stream);
 
 /* ---- optimiser (model/utils/custom_adam.py:24-76, LREQAdam.step) ------------------------------ */
 /* One multi-tensor launch:  v = beta2*v + (1-beta2)*g*g ;  p -= step[t]*g/(sqrt(v)+eps)   (beta1 == 0).

@@ -300,14 +300,16 @@ def in_bwd_apply(g, x, mean_rstd, style, dstyle, sums, mode, res=None, rscale=0.
     return Act.of(v, planes), torch.stack((v.sum(dim=(0, 2, 3)), (v * nz).sum(dim=(0, 2, 3))))
 
 
-def from_rgb_bwd(d_f, f, img, slope=0.2):
+def from_rgb_bwd(d_f, f, img, slope=0.2, weight=None):
     d = d_f.to_nchw()
     d = torch.where(f.to_nchw() > 0, d, d * slope)
     cimg = img.shape[1]
     out = torch.zeros((f.c, 4))
     out[:, :cimg] = torch.einsum("nchw,nihw->ci", d, img.float())
     out[:, 3] = d.sum(dim=(0, 2, 3))
-    return out
+    if weight is None:
+        return out
+    return out, torch.einsum("nchw,ci->nihw", d, weight.detach().view(f.c, cimg))
 
 
 # ------------------------------------------------------------------------------------------------

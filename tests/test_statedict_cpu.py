@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
 def test_conv_args_struct_matches_header():
     import ctypes
     from dge_b200._lib import ConvArgs
-    assert ctypes.sizeof(ConvArgs) == 224
+    assert ctypes.sizeof(ConvArgs) == 232
     assert ConvArgs.noise_bstride.offset == 64 and ConvArgs.out_raw_up.offset == 184
 
 
