@@ -27,6 +27,22 @@ GA, GB = 0.111, 0.889          # E.py:84
 SLOPE = 0.2                    # E.py:62,75; net.py:239
 
 
+def _packed(w, planes, dgrad=False):
+    """Packed forward / data-gradient operand of a conv weight, reused until the weight changes (ops.weight_key: an
+    optimiser step retires it).  One iteration of the inversion loop runs the encoder twice on the same weights, and
+    the two backward passes of an iteration straddle a step.  The cache lives ON the parameter object, so it dies with
+    it (a recycled device address can never alias another model's weights)."""
+    cache = w.__dict__.setdefault('_dge_packed', {})
+    slot = (planes, dgrad, K is ops)
+    key = K.weight_key(w)
+    hit = cache.get(slot)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    op = K.pack_conv_weight_dgrad(w, planes=planes) if dgrad else K.pack_conv_weight(w, planes=planes)
+    cache[slot] = (key, op)
+    return op
+
+
 def _f32b(t):
     n, c8, h, w, _ = t.shape
     return K.F32B.wrap(t, n, c8 * 8, h, w)
@@ -76,18 +92,18 @@ class _BEBlockFn(torch.autograd.Function):
             xn, rp = K.instance_norm_pool(x, mr1, planes=planes)                               # :58 and :78
         else:
             xn, _ = K.instance_norm(x, mr1, planes=planes)                                     # :58
-        y1 = K.conv(xn, K.pack_conv_weight(w1, planes=planes), c, K.CONV_3X3, noise=noise1, noise_batched=True,
+        y1 = K.conv(xn, _packed(w1, planes), c, K.CONV_3X3, noise=noise1, noise_batched=True,
                     noise_w=nw1.detach().reshape(-1), bias=b1.detach().reshape(-1), slope=SLOPE, out_f32b=True)['f32b']
         style2, mr2 = K.instance_stats(y1, eps2)                                               # :64-66
         y2 = None
         if has_last:
             y1n, _ = K.instance_norm(y1, mr2, planes=planes)                                   # :69
             # training keeps the full-resolution activated conv_2 output: its sign is the leaky-ReLU mask of the backward
-            y2 = K.conv(y1n, K.pack_conv_weight(w2, planes=planes), cout, K.CONV_3X3, noise=noise2, noise_batched=True,
+            y2 = K.conv(y1n, _packed(w2, planes), cout, K.CONV_3X3, noise=noise2, noise_batched=True,
                         noise_w=nw2.detach().reshape(-1), bias=b2.detach().reshape(-1), slope=SLOPE,
                         out_f32b=True)['f32b']                                                  # :72-75
             if w3 is not None:
-                out = K.conv(rp, K.pack_conv_weight(w3, planes=planes), cout, K.CONV_1X1, bias=b3.detach(),
+                out = K.conv(rp, _packed(w3, planes), cout, K.CONV_1X1, bias=b3.detach(),
                              blend_src=y2, blend_pool=True, blend_a=GA, blend_b=GB, out_f32b=True)['f32b']   # :76-84
             else:
                 out = K.blend(y2, x, GA, GB, pool=3)
@@ -96,7 +112,7 @@ class _BEBlockFn(torch.autograd.Function):
             _, y1n_f = K.instance_norm(y1, mr2, out_act=False, out_f32b=True)                  # :69
             if w3 is not None:
                 rp = K.f32b_to_act(x, planes)
-                out = K.conv(rp, K.pack_conv_weight(w3, planes=planes), cout, K.CONV_1X1, bias=b3.detach(),
+                out = K.conv(rp, _packed(w3, planes), cout, K.CONV_1X1, bias=b3.detach(),
                              blend_src=y1n_f, blend_pool=False, blend_a=GA, blend_b=GB, out_f32b=True)['f32b']
             else:
                 out = K.blend(y1n_f, x, GA, GB, pool=False)
@@ -135,7 +151,7 @@ class _BEBlockFn(torch.autograd.Function):
             if has_w3:
                 db3 = s[2]
             dw2 = K.conv_wgrad(dy2, K.Act.wrap(y1n_t, n, c, h, w, planes), 3)
-            g1 = K.conv(dy2, K.pack_conv_weight_dgrad(w2, planes=planes), c, K.CONV_3X3, out_f32b=True)['f32b']
+            g1 = K.conv(dy2, _packed(w2, planes, True), c, K.CONV_3X3, out_f32b=True)['f32b']
             del dy2
         else:
             g1 = K.scale_f32b(d_out, GA)                       # out = GA * IN_2(y1) + GB * residual  (E.py:69,84)
@@ -149,13 +165,13 @@ class _BEBlockFn(torch.autograd.Function):
         db1, dnw1 = s[0].view(1, -1, 1, 1), s[1].view(1, -1, 1, 1)
         del g1
         dw1 = K.conv_wgrad(dy1, xn, 3)
-        g0 = K.conv(dy1, K.pack_conv_weight_dgrad(w1, planes=planes), c, K.CONV_3X3, out_f32b=True)['f32b']
+        g0 = K.conv(dy1, _packed(w1, planes, True), c, K.CONV_3X3, out_f32b=True)['f32b']
         del dy1
         # residual branch (E.py:78-84)
         if has_w3:
             rh, rw = (h // 2, w // 2) if has_last else (h, w)
             dw3 = K.conv_wgrad(dres, K.Act.wrap(rp_t, n, c, rh, rw, planes), 1)
-            d_rp = K.conv(dres, K.pack_conv_weight_dgrad(w3, planes=planes), c, K.CONV_1X1, out_f32b=True)['f32b']
+            d_rp = K.conv(dres, _packed(w3, planes, True), c, K.CONV_1X1, out_f32b=True)['f32b']
             rscale = 0.25 if has_last else 1.0
         else:
             d_rp, rscale = d_out, GB * (0.25 if has_last else 1.0)

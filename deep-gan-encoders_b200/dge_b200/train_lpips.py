@@ -38,7 +38,8 @@ def _operands(model, planes):
         bwd.append(K.pack_conv_weight_dgrad(w, planes=planes))
         bias.append(c.bias.detach().contiguous())
     lin = [model.lins[k].model[1].weight.detach().reshape(-1).contiguous() for k in range(5)]
-    val = (fwd, bwd, bias, lin)
+    sl = model.scaling_layer
+    val = (fwd, bwd, bias, lin, (sl.shift.flatten().tolist(), sl.scale.flatten().tolist()))
     model.__dict__['_dge_vgg_ops'] = (key, val)
     return val
 
@@ -47,10 +48,9 @@ class _LpipsFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, in0, in1, model, planes):
         n = in0.shape[0]
-        fwd, bwd, bias, lin = _operands(model, planes)
+        fwd, bwd, bias, lin, (shift, scale) = _operands(model, planes)
         x = torch.cat((in0.detach().float(), in1.detach().float()), dim=0).contiguous()
-        sl = model.scaling_layer
-        act = K.lpips_input(x, sl.shift.flatten().tolist(), sl.scale.flatten().tolist(), planes)
+        act = K.lpips_input(x, shift, scale, planes)
         out = torch.zeros(n, dtype=torch.float32, device=x.device)
         saved, taps = [], []        # saved[i]: the activated output of conv i (Act, or F32B at a tap)
         i = 0
@@ -79,7 +79,7 @@ class _LpipsFn(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, go):
         n, planes = ctx.n, ctx.planes
-        fwd, bwd, bias, lin = _operands(ctx.model, planes)
+        fwd, bwd, bias, lin, _ = _operands(ctx.model, planes)
         want = (ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         go = go.reshape(n).contiguous().float()
         saved = ctx.saved

@@ -108,5 +108,5 @@ class LREQAdam(Optimizer):
                                                    float(group['eps']), ops._stream()))
         # the kernel writes the parameters through raw pointers (no torch version bump): retire every tensor derived
         # from them (packed conv weights etc.) -- see ops.weight_key
-        ops.invalidate_weight_caches()
+        ops.invalidate_weight_caches(p for g in self.param_groups for p in g['params'])
         return loss

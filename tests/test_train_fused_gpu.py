@@ -360,16 +360,17 @@ def test_fused_full_iteration_vs_unfused_graph_at_256():
     img_f, fa, fb = run(True)
     img_u, ua, ub = run(False)
     assert rel(img_f, img_u) < 2e-4
+    rel2 = lambda x, y: ((x - y).norm() / y.norm().clamp_min(1e-30)).item()
     for a, b in ((fa, ua), (fb, ub)):
         assert set(a) == set(b)
-        # per-channel vectors (bias / noise-weight gradients) are sums of ~1e3-1e5 sign-alternating terms: ONE unit whose
-        # pre-activation is within rounding of zero (it may take either slope in either graph) moves them by ~1/sqrt(N);
-        # the exact 1e-3 check of every parameter is the reference-fixture test above
-        is_vec = lambda t: t.dim() == 1 or (t.dim() == 4 and t.shape[0] == 1)      # biases, [1, C, 1, 1] noise weights
-        worst_w = max((rel(a[k], b[k]), k) for k in b if not is_vec(b[k]))
-        worst_v = max((rel(a[k], b[k]), k) for k in b)
-        assert worst_w[0] < 5e-3, worst_w
-        assert worst_v[0] < 3e-2, worst_v
+        # ONE unit whose pre-activation is within rounding of zero may take either slope in either graph (encoder,
+        # generator, LPIPS ReLUs / max-pools): it moves individual gradient entries by up to ~1e-2 of the tensor's scale but
+        # is invisible in the L2 norm.  The exact 1e-3 element-wise check of every parameter is the reference-fixture test
+        # above; here the bar is 3e-3 in L2 and a loose element-wise bound that still catches any systematic error.
+        worst2 = max((rel2(a[k], b[k]), k) for k in b)
+        worst = max((rel(a[k], b[k]), k) for k in b)
+        assert worst2[0] < 3e-3, worst2
+        assert worst[0] < 3e-2, worst
 
 
 # ------------------------------------------------------------------------------------------------

@@ -36,11 +36,16 @@ def record_masks(store):
     orig_l, orig_r, orig_p = F.leaky_relu, F.relu, F.max_pool2d
     # the pattern can only be observed on the graph of separate torch nodes: the fused training path (one node per
     # block / per synthesis pass, tests/test_train_fused_gpu.py) is switched off while recording
+    import lpips as _LP
+    import metric.pytorch_ssim as _PS
     import model.E.E as _EM
     import model.stylegan2_generator as _SG
-    fused = (_EM.FUSED_TRAIN, getattr(_SG, "FUSED_TRAIN", False))
-    _EM.FUSED_TRAIN = False
-    _SG.FUSED_TRAIN = False
+    import training_utils as _TU
+    mods = (_EM, _SG, _PS, _TU)
+    fused = [m.FUSED_TRAIN for m in mods] + [_LP.FUSED]
+    for m in mods:
+        m.FUSED_TRAIN = False
+    _LP.FUSED = False
 
     def lrelu(x, negative_slope=0.01, inplace=False):
         store.append((x.detach() > 0).cpu())
@@ -60,7 +65,9 @@ def record_masks(store):
         yield
     finally:
         F.leaky_relu, F.relu, F.max_pool2d = orig_l, orig_r, orig_p
-        _EM.FUSED_TRAIN, _SG.FUSED_TRAIN = fused
+        for m, v in zip(mods, fused):
+            m.FUSED_TRAIN = v
+        _LP.FUSED = fused[-1]
 
 
 @contextlib.contextmanager

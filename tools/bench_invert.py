@@ -132,10 +132,22 @@ def main():
     one_image(0, 2)                                       # warm-up (allocator, caches, cuDNN heuristics)
     torch.cuda.synchronize()
     torch.cuda.reset_peak_memory_stats()
+    prof = None
+    if os.environ.get("DGE_HOSTPROF"):          # where the HOST time of the loop goes (cProfile, top entries to stderr)
+        import cProfile
+        prof = cProfile.Profile()
+        prof.enable()
     t0 = time.perf_counter()
     mses = [one_image(i, a.iterations) for i in range(a.images)]
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
+    if prof is not None:
+        import io
+        import pstats
+        prof.disable()
+        buf = io.StringIO()
+        pstats.Stats(prof, stream=buf).sort_stats("tottime").print_stats(40)
+        print(buf.getvalue(), file=sys.stderr)
     ms_it = wall / (a.images * a.iterations) * 1e3
     out = {"impl": a.impl, "encoder_noise": a.noise if a.impl == "ours" else "reference", "workload": f"configs[4]: embedding_img.py:74-128 loop, StyleGAN2-{a.res} synthesis + "
                                        f"BE({startf},{layers}), batch 1, synthetic images G(z_i), seeds 30000+i",
