@@ -27,9 +27,9 @@ static int tb_sms() {
   }
   return g_tb_sms;
 }
-// blocks per (sample, channel group): enough to fill the chip ~8 blocks per SM, never more than the pixels allow
+// blocks per (sample, channel group): enough to fill the chip ~12 blocks per SM, never more than the pixels allow
 static int tb_splits(long long pixels, long long groups) {
-  long long want = ((long long)tb_sms() * 8 + groups - 1) / groups;
+  long long want = ((long long)tb_sms() * 12 + groups - 1) / groups;
   const long long cap = (pixels + TB_THREADS - 1) / TB_THREADS;
   if (want > cap) want = cap;
   if (want < 1) want = 1;
@@ -319,15 +319,19 @@ struct Sg2BwdParams {
   int c, hw, planes, out_planes;
 };
 
-__global__ void __launch_bounds__(TB_THREADS)
+// Thread = (pixel, channel HALF): 4 channels per thread keep the 5 x 4 accumulators and the per-channel constants in ~70
+// registers (three blocks per SM instead of one with 8 channels per thread: the kernel is latency-bound on its loads);
+// the two halves of a 16-byte ACT chunk / 32-byte F32B sector are read by neighbouring lanes, so accesses stay coalesced.
+__global__ void __launch_bounds__(TB_THREADS, 3)
 k_sg2_layer_bwd(const __grid_constant__ Sg2BwdParams p) {
-  __shared__ float red[TB_THREADS / 32][40];
+  __shared__ float red[TB_THREADS / 32][2][20];
   const int c = p.c, C8 = c >> 3, ng = blockIdx.y, nidx = ng / C8, grp = ng - nidx * C8;
   const size_t hw = (size_t)p.hw;
-  float sn[8], isn[8], dm[8], bs[8], rw[3][8];
+  const int half = threadIdx.x & 1;
+  float sn[4], isn[4], dm[4], bs[4], rw[3][4];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int ch = grp * 8 + k;
+  for (int k = 0; k < 4; ++k) {
+    const int ch = grp * 8 + 4 * half + k;
     sn[k] = p.ya_scale ? __ldg(p.ya_scale + (size_t)nidx * c + ch) : 1.f;
     isn[k] = sn[k] != 0.f ? 1.f / sn[k] : 0.f;
     dm[k] = p.demod ? __ldg(p.demod + (size_t)nidx * c + ch) : 1.f;
@@ -337,24 +341,29 @@ k_sg2_layer_bwd(const __grid_constant__ Sg2BwdParams p) {
   }
   const float g_pos = p.gain, g_neg = p.gain * p.slope;
   const float ig_pos = 1.f / p.gain, ig_neg = p.slope != 0.f ? 1.f / (p.gain * p.slope) : 0.f;
-  float acc[40];
+  float acc[20];
 #pragma unroll
-  for (int i = 0; i < 40; ++i) acc[i] = 0.f;
-  const uint4* ya = reinterpret_cast<const uint4*>(p.ya) + (size_t)ng * p.planes * hw;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < hw; i += (size_t)gridDim.x * blockDim.x) {
-    float y[8], dx[8], v[8];
-    unpack8(__ldg(ya + i), y);
-    if (p.planes == 2) {
-      float l[8];
-      unpack8(__ldg(ya + hw + i), l);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) y[k] += l[k];
+  for (int i = 0; i < 20; ++i) acc[i] = 0.f;
+  const uint2* ya = reinterpret_cast<const uint2*>(p.ya) + ((size_t)ng * p.planes * hw) * 2 + half;
+  const float4* dxs = p.dxs ? reinterpret_cast<const float4*>(p.dxs) + ((size_t)ng * hw) * 2 + half : nullptr;
+  const size_t stride = ((size_t)gridDim.x * blockDim.x) >> 1;
+  for (size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 1; i < hw; i += stride) {
+    float y[4], dx[4], v[4];
+    {
+      const uint2 q = __ldg(ya + 2 * i);
+      y[0] = __uint_as_float(q.x << 16); y[1] = __uint_as_float(q.x & 0xffff0000u);
+      y[2] = __uint_as_float(q.y << 16); y[3] = __uint_as_float(q.y & 0xffff0000u);
+      if (p.planes == 2) {
+        const uint2 l = __ldg(ya + 2 * (hw + i));
+        y[0] += __uint_as_float(l.x << 16); y[1] += __uint_as_float(l.x & 0xffff0000u);
+        y[2] += __uint_as_float(l.y << 16); y[3] += __uint_as_float(l.y & 0xffff0000u);
+      }
     }
-    if (p.dxs) {
-      load8_f32b(p.dxs, (size_t)ng * hw + i, dx);
+    if (dxs) {
+      const float4 t = __ldg(dxs + 2 * i);
+      dx[0] = t.x; dx[1] = t.y; dx[2] = t.z; dx[3] = t.w;
     } else {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) dx[k] = 0.f;
+      dx[0] = dx[1] = dx[2] = dx[3] = 0.f;
     }
     float di[3] = {0.f, 0.f, 0.f};
     if (p.dimg) {
@@ -363,26 +372,55 @@ k_sg2_layer_bwd(const __grid_constant__ Sg2BwdParams p) {
     }
     const float nzs = p.noise ? __ldg(p.noise + (size_t)nidx * p.noise_bstride + i) * p.noise_scalar : 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < 4; ++k) {
       const float yv = y[k] * isn[k];
       float dy = dx[k] * sn[k];
       dy = fmaf(rw[0][k], di[0], fmaf(rw[1][k], di[1], fmaf(rw[2][k], di[2], dy)));
       acc[k] = fmaf(dx[k], yv, acc[k]);
-      acc[8 + k] = fmaf(di[0], yv, acc[8 + k]);
-      acc[16 + k] = fmaf(di[1], yv, acc[16 + k]);
-      acc[24 + k] = fmaf(di[2], yv, acc[24 + k]);
+      acc[4 + k] = fmaf(di[0], yv, acc[4 + k]);
+      acc[8 + k] = fmaf(di[1], yv, acc[8 + k]);
+      acc[12 + k] = fmaf(di[2], yv, acc[12 + k]);
       const bool pos = yv > 0.f;
       const float dpre = dy * (pos ? g_pos : g_neg);
       const float pre = yv * (pos ? ig_pos : ig_neg);
-      acc[32 + k] = fmaf(dpre, pre - nzs - bs[k], acc[32 + k]);
+      acc[16 + k] = fmaf(dpre, pre - nzs - bs[k], acc[16 + k]);
       v[k] = dpre * dm[k];
     }
-    if (p.out_act) store8_act_at(p.out_act, (size_t)ng * p.out_planes * hw + i, hw, p.out_planes, v);
-    if (p.out_f32b) store8_f32b(p.out_f32b, (size_t)ng * hw + i, v);
+    if (p.out_act) {
+      uint32_t hw2[2], lw2[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const __nv_bfloat162 hb = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        hw2[j] = *reinterpret_cast<const uint32_t*>(&hb);
+        const __nv_bfloat162 lb = __floats2bfloat162_rn(v[2 * j] - __uint_as_float(hw2[j] << 16),
+                                                        v[2 * j + 1] - __uint_as_float(hw2[j] & 0xffff0000u));
+        lw2[j] = *reinterpret_cast<const uint32_t*>(&lb);
+      }
+      uint2* o = reinterpret_cast<uint2*>(p.out_act) + ((size_t)ng * p.out_planes * hw + i) * 2 + half;
+      *o = make_uint2(hw2[0], hw2[1]);
+      if (p.out_planes == 2) o[2 * hw] = make_uint2(lw2[0], lw2[1]);
+    }
+    if (p.out_f32b)
+      reinterpret_cast<float4*>(p.out_f32b)[((size_t)ng * hw + i) * 2 + half] = make_float4(v[0], v[1], v[2], v[3]);
   }
-  const float t = block_sums<40>(acc, red);
-  if (threadIdx.x < 40)
-    atomicAdd(p.sums + ((size_t)nidx * c + grp * 8 + (threadIdx.x & 7)) * 5 + (threadIdx.x >> 3), t);
+  // reduce over the lanes of the same half (xor 16, 8, 4, 2), then over the warps
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 20; ++i) {
+#pragma unroll
+    for (int off = 16; off >= 2; off >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
+  }
+  if (lane < 2) {
+#pragma unroll
+    for (int i = 0; i < 20; ++i) red[warp][lane][i] = acc[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < 40) {
+    const int hf = threadIdx.x / 20, j = threadIdx.x - hf * 20;      // j = which * 4 + k
+    float t = 0.f;
+    for (int w = 0; w < TB_THREADS / 32; ++w) t += red[w][hf][j];
+    atomicAdd(p.sums + ((size_t)nidx * c + grp * 8 + 4 * hf + (j & 3)) * 5 + (j >> 2), t);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -762,7 +800,7 @@ extern "C" int dge_sg2_layer_bwd(const void* ya_act, const float* ya_scale, cons
   p.noise_bstride = noise_bstride; p.noise_scalar = noise_scalar; p.bias = bias; p.demod = demod; p.gain = gain;
   p.slope = slope; p.out_act = out_act; p.out_f32b = out_f32b; p.sums = sums; p.c = c; p.hw = h * w; p.planes = planes;
   p.out_planes = out_planes;
-  dim3 grid(tb_splits((long long)h * w, (long long)n * (c / 8)), n * (c / 8));
+  dim3 grid(tb_splits(2ll * h * w, (long long)n * (c / 8)), n * (c / 8));   // two threads (channel halves) per pixel
   k_sg2_layer_bwd<<<grid, TB_THREADS, 0, TB_STREAM>>>(p);
   count_launch();
   return check_launch("k_sg2_layer_bwd");
