@@ -375,7 +375,7 @@ def test_lpips_vgg_distance_and_gradient_vs_oracle():
     assert rel(d, d_r) < TOL
     assert rel(a_dev.grad, a_r.grad) < TOL
     with torch.no_grad():       # identical inputs: zero up to the run-to-run rounding of the split-K atomics on the 4x4 / 8x8 maps
-        assert float(m(b.cuda(), b.cuda()).abs().max()) < 1e-9
+        assert float(m(b.cuda(), b.cuda()).abs().max()) < 1e-7      # (split-K partial sums land in any order: not bit-stable)
 
 
 def test_sg1_mapping_left_on_the_cpu_as_the_scripts_do():

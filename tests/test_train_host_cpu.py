@@ -248,3 +248,23 @@ def test_public_entry_points_still_refuse_cpu_tensors():
     from dge_b200 import autograd as tc
     with pytest.raises(ops.DgeError):
         tc.conv2d(torch.zeros(1, 16, 8, 8), torch.zeros(16, 16, 3, 3))
+
+
+def test_e_blur_margin_fixture_on_the_host_graph_and_oracle(aten_conv):
+    """The margin fixture (tests/golden/make_margin_fixtures.py) pins the oracle and the recorded graph like the others."""
+    from model.E.E_Blur import BE
+    from oracle import encoder as oenc
+    fx = torch.load(os.path.join(GOLD, "e_blur_margin.pt"))
+    assert fx["min_preactivation_over_std"] > 2e-5
+    E = BE(**fx["config"])
+    E.load_state_dict(fx["state_dict"], strict=True)
+    torch.manual_seed(fx["noise_seed"])
+    const, w = E._forward_autograd(fx["img"], 9)
+    assert rel(const, fx["const"]) < 2e-5 and rel(w, fx["w"]) < 2e-5
+    (const.sum() + (w ** 2).mean()).backward()
+    for k, g in fx["grads"].items():
+        assert rel(dict(E.named_parameters())[k].grad, g) < 3e-4, k
+    torch.manual_seed(fx["noise_seed"])
+    with torch.no_grad():
+        c_o, w_o = oenc.be_blur_forward(fx["state_dict"], fx["img"], fx["config"]["layer_count"])
+    assert rel(c_o, fx["const"]) < 2e-5 and rel(w_o, fx["w"]) < 2e-5
