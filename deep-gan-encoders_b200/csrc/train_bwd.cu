@@ -653,6 +653,7 @@ k_lpips_dist(const float* __restrict__ f, const float* __restrict__ lw, float* _
   float part = 0.f;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)hw; i += (size_t)gridDim.x * blockDim.x) {
     float saa = 0.f, sbb = 0.f, waa = 0.f, wbb = 0.f, wab = 0.f;
+#pragma unroll 4      // (up to 64 channel groups per pixel: keep several 32-byte loads in flight)
     for (int g = 0; g < C8; ++g) {
       float a[8], b[8];
       load8_f32b(f, ((size_t)n * C8 + g) * hw + i, a);
@@ -677,6 +678,7 @@ k_lpips_dist(const float* __restrict__ f, const float* __restrict__ lw, float* _
     const float scale = __ldg(go + n) * inv_hw;
     const float sgb = -2.f * (wab / na - wbb / nbn), sga = -2.f * (wab / nbn - waa / na);
     const float cb = rb > 0.f ? sgb / (nbn * rb) : 0.f, ca = ra > 0.f ? sga / (na * ra) : 0.f;
+#pragma unroll 2
     for (int g = 0; g < C8; ++g) {
       float a[8], b[8], da[8], db[8];
       load8_f32b(f, ((size_t)n * C8 + g) * hw + i, a);
