@@ -5,6 +5,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "dge_common.cuh"
 
 namespace dge {
@@ -13,7 +15,7 @@ namespace dge {
 // error / bookkeeping
 // ---------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
-static thread_local int64_t g_launches = 0;
+static std::atomic<int64_t> g_launches{0};   // process-wide: autograd runs backward nodes on its own worker thread
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -21,7 +23,7 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
-void count_launch() { ++g_launches; }
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -1507,8 +1509,8 @@ extern "C" {
 
 const char* dge_last_error(void) { return g_err; }
 int dge_version(void) { return 100; }
-int64_t dge_launch_count(void) { return g_launches; }
-void dge_launch_count_reset(void) { g_launches = 0; }
+int64_t dge_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+void dge_launch_count_reset(void) { g_launches.store(0, std::memory_order_relaxed); }
 
 int dge_device_ok(void) {
   int dev = 0;

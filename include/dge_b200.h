@@ -42,7 +42,8 @@ const char* dge_last_error(void);
 int dge_version(void);
 /* 0 if the current device is sm_100 (B200); DGE_ERR_UNSUPPORTED otherwise. */
 int dge_device_ok(void);
-/* number of kernels launched by this library on this thread since the last reset (bench.py gpu_launches) */
+/* number of kernels launched by this library in this process since the last reset (bench.py gpu_launches); process-wide:
+   torch.autograd runs the backward nodes on its own worker thread */
 int64_t dge_launch_count(void);
 void dge_launch_count_reset(void);
 
