@@ -517,7 +517,7 @@ __device__ __forceinline__ void epi_group16(const ConvKParams& p, const float* t
     }
   }
   const int H = p.H, W = p.W, C8 = p.Cout >> 3, g0 = (co0 + c) >> 3;
-  if (EPI != 3 && p.preact_add && px.valid) {
+  if (EPI != 3 && EPI != 4 && p.preact_add && px.valid) {
     float t[8];
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
@@ -535,7 +535,7 @@ __device__ __forceinline__ void epi_group16(const ConvKParams& p, const float* t
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = v[j] < 0.f ? v[j] * p.slope : v[j];
   }
-  if (EPI != 3 && p.out_pool) {
+  if (EPI == 4 || (EPI != 3 && p.out_pool)) {
     // 2x2 mean across the lanes (x ^ 1 <-> lane ^ 1, y ^ 1 <-> lane ^ 8); the even/even lane stores the pooled pixel
     const int lane = threadIdx.x & 31;
 #pragma unroll
@@ -554,7 +554,7 @@ __device__ __forceinline__ void epi_group16(const ConvKParams& p, const float* t
     return;
   }
   if (px.valid) {
-    if (EPI != 3 && p.blend_src) {
+    if (EPI != 3 && EPI != 4 && p.blend_src) {
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
         float sv[8];
@@ -612,7 +612,7 @@ __device__ __forceinline__ void epi_group16(const ConvKParams& p, const float* t
       store8_f32b(p.out_f32b, o, v);
       store8_f32b(p.out_f32b, o + HW, v + 8);
     }
-    if (EPI != 3 && p.out_nchw) {
+    if (EPI != 3 && EPI != 4 && p.out_nchw) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) p.out_nchw[((size_t)px.n * p.Cout + co0 + c + j) * HW + pix] = v[j];
     }
@@ -1724,18 +1724,24 @@ int conv_forward(const dge_conv_args* a, cudaStream_t stream) {
   // TMEM is 512 columns per SM: keep co-resident CTAs * tmem_cols <= 512 by padding the smem request.
   const size_t min_smem = (227 * 1024) / (max_occ + 1) + 1024;
   if (smem < min_smem) smem = min_smem;
-  static bool attr_set[12] = {false, false, false, false, false, false, false, false, false, false, false, false};
+  static bool attr_set[14] = {false, false, false, false, false, false, false, false, false, false, false, false, false,
+                              false};
   // EPI 2: 1x1 residual convs with a same-resolution blend (their blend loads are prefetched one unit ahead);
   // EPI 3: no residual / blend / pooled / NCHW output -- a leaner instantiation for the most common launches
   int epi = up ? 1 : ((a->kind == DGE_CONV_1X1 && a->blend_src && !a->blend_pool && !p.stack && p.ksplit == 1) ? 2 : 0);
   if (epi == 0 && p.ksplit == 1 && !a->preact_add && !a->blend_src && !a->out_nchw && !a->out_pool) epi = 3;
-  const int ei = p.ksplit > 1 ? 8 + epi + (p.pair ? 2 : 0) : epi + (p.pair ? 4 : 0);
-  const void* ktab[12] = {(const void*)conv_mma_kernel<0, false, false>, (const void*)conv_mma_kernel<1, false, false>,
-                          (const void*)conv_mma_kernel<2, false, false>, (const void*)conv_mma_kernel<3, false, false>,
-                          (const void*)conv_mma_kernel<0, true, false>,  (const void*)conv_mma_kernel<1, true, false>,
-                          (const void*)conv_mma_kernel<2, true, false>,  (const void*)conv_mma_kernel<3, true, false>,
-                          (const void*)conv_mma_kernel<0, false, true>,  (const void*)conv_mma_kernel<1, false, true>,
-                          (const void*)conv_mma_kernel<0, true, true>,   (const void*)conv_mma_kernel<1, true, true>};
+  // EPI 4: the lean epilogue + the 2x2-mean output only (the encoder's conv_2 at every resolution): the generic EPI 0
+  // instantiation spills at the 168-register limit and paced these launches, not their MMAs
+  if (epi == 0 && p.ksplit == 1 && !a->preact_add && !a->blend_src && !a->out_nchw && a->out_pool && !a->rgb_w) epi = 4;
+  // non-split: index 2*epi + pair (epi 0..4); split-K: 10 + 2*epi + pair (epi 0 / 1)
+  const int ei = p.ksplit > 1 ? 10 + 2 * epi + (p.pair ? 1 : 0) : 2 * epi + (p.pair ? 1 : 0);
+  const void* ktab[14] = {(const void*)conv_mma_kernel<0, false, false>, (const void*)conv_mma_kernel<0, true, false>,
+                          (const void*)conv_mma_kernel<1, false, false>, (const void*)conv_mma_kernel<1, true, false>,
+                          (const void*)conv_mma_kernel<2, false, false>, (const void*)conv_mma_kernel<2, true, false>,
+                          (const void*)conv_mma_kernel<3, false, false>, (const void*)conv_mma_kernel<3, true, false>,
+                          (const void*)conv_mma_kernel<4, false, false>, (const void*)conv_mma_kernel<4, true, false>,
+                          (const void*)conv_mma_kernel<0, false, true>,  (const void*)conv_mma_kernel<0, true, true>,
+                          (const void*)conv_mma_kernel<1, false, true>,  (const void*)conv_mma_kernel<1, true, true>};
   const void* kfn = ktab[ei];
   if (!attr_set[ei]) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
