@@ -56,6 +56,8 @@ def main():
     ap.add_argument("--cpu-plumbing", action="store_true")
     ap.add_argument("--img-size", type=int, default=64)
     ap.add_argument("--iterations", type=int, default=2)
+    ap.add_argument("--mtype", type=int, default=2, choices=[1, 2, 4],
+                    help="E_align_s2.py: 1 = StyleGAN1 (mapping network left on the CPU as upstream), 2 = StyleGAN2, 4 = BigGAN")
     a = ap.parse_args()
     path = find_script(a.script)
     if path is None:
@@ -94,13 +96,43 @@ def main():
     mod.writer_path = res + "/summaries"
     out = {"script": path, "iterations": a.iterations, "img_size": a.img_size}
     if a.script == "E_align_s2.py":
-        from model.stylegan2_generator import StyleGAN2Generator
-        G = StyleGAN2Generator(resolution=a.img_size)
-        perturb(G, 1)
-        ck = os.path.join(work, "stylegan2_synth.pth")
-        torch.save({"generator_smooth": G.state_dict()}, ck)
-        args = argparse.Namespace(mtype=2, checkpoint_dir_GAN=ck, config_dir=None, checkpoint_dir_E=None,
-                                  img_size=a.img_size, img_channels=3, z_dim=512, start_features=startf, batch_size=2,
+        cfg_path, z_dim = None, 512
+        if a.mtype == 2:
+            from model.stylegan2_generator import StyleGAN2Generator
+            G = StyleGAN2Generator(resolution=a.img_size)
+            perturb(G, 1)
+            ck = os.path.join(work, "stylegan2_synth.pth")
+            torch.save({"generator_smooth": G.state_dict()}, ck)
+        elif a.mtype == 1:
+            from model.stylegan1.net import Generator, Mapping
+            ck = os.path.join(work, "sg1") + "/"
+            os.makedirs(ck)
+            Gs = Generator(startf=startf, maxf=512, layer_count=layers, latent_size=512, channels=3)
+            Gm = Mapping(num_layers=2 * layers, mapping_layers=8, latent_size=512, dlatent_size=512, mapping_fmaps=512)
+            perturb(Gs, 2)
+            torch.save(Gs.state_dict(), ck + "Gs_dict.pth")
+            torch.save(Gm.state_dict(), ck + "Gm_dict.pth")
+            torch.save(torch.zeros(2 * layers, 512), ck + "center_tensor.pt")
+        else:
+            import json as _json
+            from model.biggan_generator import BigGAN
+            from model.utils.biggan_config import BigGANConfig
+            a.img_size, layers, startf, z_dim = 128, 6, 16, 128       # a 128-px BigGAN-deep: 5 up blocks from 4x4
+            cfg = {"attention_layer_position": 8, "channel_width": 64, "class_embed_dim": 128, "eps": 0.0001,
+                   "layers": [[False, 16, 16], [True, 16, 16], [False, 16, 16], [True, 16, 8], [False, 8, 8], [True, 8, 4],
+                              [False, 4, 4], [True, 4, 2], [False, 2, 2], [True, 2, 1]],
+                   "n_stats": 51, "num_classes": 1000, "output_dim": 128, "z_dim": 128}
+            cfg_path = os.path.join(work, "biggan_synth.json")
+            with open(cfg_path, "w") as f:
+                _json.dump(cfg, f)
+            G = BigGAN(BigGANConfig.from_dict(cfg))
+            with torch.no_grad():
+                G.generator.bn.weight.fill_(1.0)
+                G.generator.bn.bias.zero_()
+            ck = os.path.join(work, "biggan_synth.pt")
+            torch.save(G.state_dict(), ck)
+        args = argparse.Namespace(mtype=a.mtype, checkpoint_dir_GAN=ck, config_dir=cfg_path, checkpoint_dir_E=None,
+                                  img_size=a.img_size, img_channels=3, z_dim=z_dim, start_features=startf, batch_size=2,
                                   iterations=a.iterations, lr=0.0015, beta_1=0.0, experiment_dir=res)
         call = lambda: mod.train(tensor_writer=NullWriter(), args=args)
         expect = [res + "/models/E_model_ep0_iter0.pth", res + "/Loss.txt", res + "/imgs/ep0_iter0.jpg"]

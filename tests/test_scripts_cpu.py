@@ -18,9 +18,10 @@ def run_tier(script, *flags):
     return json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
 
 
-@pytest.mark.parametrize("script", ["E_align_s2.py", "embedding_img.py"])
-def test_unmodified_script_reaches_the_first_kernel_and_refuses_the_cpu(script):
-    out = run_tier(script, "--cpu-plumbing", "--img-size", "32")
+@pytest.mark.parametrize("script,extra", [("E_align_s2.py", ()), ("embedding_img.py", ()),
+                                          ("E_align_s2.py", ("--mtype", "1")), ("E_align_s2.py", ("--mtype", "4"))])
+def test_unmodified_script_reaches_the_first_kernel_and_refuses_the_cpu(script, extra):
+    out = run_tier(script, "--cpu-plumbing", "--img-size", "32", *extra)
     if "skipped" in out:
         pytest.skip(out["skipped"])
     assert out["completed"] is False and "no CPU fallback" in out["dge_error"]

@@ -25,3 +25,16 @@ def test_embedding_img_inverts_two_images_unmodified():
     assert out["completed"] is True, out
     assert out["missing_outputs"] == [], out
     assert out["dge_launches"] > 200, out
+
+
+@pytest.mark.parametrize("mtype", [1, 4])
+def test_e_align_s2_other_generator_families_unmodified(mtype):
+    """The same script with --mtype 1 (StyleGAN1: `Gm` stays on the CPU as upstream, E_align_s2.py:33-44,108) and --mtype 4
+    (BigGAN-deep + the class-conditional encoder E_BIG)."""
+    out = run_tier("E_align_s2.py", "--img-size", "64", "--iterations", "2", "--mtype", str(mtype))
+    if "skipped" in out:
+        pytest.skip(out["skipped"])
+    assert out["completed"] is True, out
+    assert out["missing_outputs"] == [], out
+    assert out["dge_launches"] > 200, out
+    assert out["e_checkpoint_keys"] > 50 and out["e_checkpoint_finite"], out
