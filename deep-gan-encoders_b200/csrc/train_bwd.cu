@@ -570,7 +570,7 @@ __global__ void k_maxpool_to_act(const float* __restrict__ x, void* __restrict__
 //   (torch's max_pool2d tie rule; ties at 0 are masked by the ReLU anyway) (NULL: none).  Thread = one 2x2 window.
 __global__ void k_relu_pool_bwd(const float* __restrict__ y_f32b, const void* __restrict__ y_act, int y_planes,
                                 const float* __restrict__ g_same, const float* __restrict__ g_pool,
-                                void* __restrict__ out, int n, int c, int h, int w, int planes) {
+                                void* __restrict__ out, int n, int c, int h, int w, int planes, int clamp_pos) {
   const int C8 = c >> 3, hc = (h + 1) >> 1, wc = (w + 1) >> 1, ho = h >> 1, wo = w >> 1;
   const size_t total = (size_t)n * C8 * hc * wc, hw = (size_t)h * w;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -632,6 +632,7 @@ __global__ void k_relu_pool_bwd(const float* __restrict__ y_f32b, const void* __
       for (int k = 0; k < 8; ++k) {
         if (pooled && am[k] == q) g[k] += gp[k];
         g[k] = yv[q][k] > 0.f ? g[k] : 0.f;
+        if (clamp_pos) g[k] = fmaxf(g[k], 0.f);      // guided back-propagation (grad_cam.py:209-211)
       }
       store8_act_at(out, ng * planes * hw + pix, hw, planes, g);
     }
@@ -858,13 +859,14 @@ extern "C" int dge_maxpool_to_act(const float* x, void* out_act, int n, int c, i
 }
 
 extern "C" int dge_relu_pool_bwd(const float* y_f32b, const void* y_act, int y_planes, const float* g_same,
-                                 const float* g_pool, void* out_act, int n, int c, int h, int w, int planes, void* stream) {
+                                 const float* g_pool, void* out_act, int n, int c, int h, int w, int planes, int clamp_pos,
+                                 void* stream) {
   DGE_REQUIRE((y_f32b || y_act) && !(y_f32b && y_act) && out_act && (g_same || g_pool), "relu_pool_bwd: bad pointers");
   DGE_REQUIRE(n > 0 && c >= 8 && c % 8 == 0 && h > 0 && w > 0 && (planes == 1 || planes == 2) &&
                   (!y_act || y_planes == 1 || y_planes == 2), "relu_pool_bwd: bad dims");
   DGE_REQUIRE(!g_pool || (h >= 2 && w >= 2), "relu_pool_bwd: pooled gradient needs h, w >= 2");
   k_relu_pool_bwd<<<tb_grid1d((size_t)n * (c / 8) * ((h + 1) / 2) * ((w + 1) / 2), 256), 256, 0, TB_STREAM>>>(
-      y_f32b, y_act, y_planes, g_same, g_pool, out_act, n, c, h, w, planes);
+      y_f32b, y_act, y_planes, g_same, g_pool, out_act, n, c, h, w, planes, clamp_pos);
   count_launch();
   return check_launch("k_relu_pool_bwd");
 }

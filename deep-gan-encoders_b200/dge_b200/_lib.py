@@ -120,7 +120,7 @@ SIGNATURES = {
     "dge_rgb_up_bwd": (c_int, [P, P, c_int64, c_int, c_int, P]),
     "dge_lpips_input": (c_int, [P, P, c_float, c_float, c_float, c_float, c_float, c_float, c_int, c_int, c_int, c_int, P]),
     "dge_maxpool_to_act": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
-    "dge_relu_pool_bwd": (c_int, [P, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "dge_relu_pool_bwd": (c_int, [P, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "dge_lpips_dist": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_float, P]),
     "dge_blend": (c_int, [P, P, P, c_float, c_float, c_int, c_int, c_int, c_int, c_int, P]),
 }

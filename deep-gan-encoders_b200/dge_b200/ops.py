@@ -780,8 +780,9 @@ def maxpool_to_act(x, planes=2):
     return out
 
 
-def relu_pool_bwd(y, g_same=None, g_pool=None, planes=2):
-    """(y > 0) * (g_same + arg-max-routed g_pool) -> Act; y is the activated conv output (F32B or Act)."""
+def relu_pool_bwd(y, g_same=None, g_pool=None, planes=2, clamp_pos=False):
+    """(y > 0) * (g_same + arg-max-routed g_pool) -> Act; y is the activated conv output (F32B or Act).
+    clamp_pos: additionally max(., 0) (guided back-propagation)."""
     assert isinstance(y, (F32B, Act)) and (g_same is not None or g_pool is not None)
     out = Act(y.n, y.c, y.h, y.w, planes, y.t.device)
     is_act = isinstance(y, Act)
@@ -789,7 +790,7 @@ def relu_pool_bwd(y, g_same=None, g_pool=None, planes=2):
         check(lib().dge_relu_pool_bwd(None if is_act else _p(y.t), _p(y.t) if is_act else None, y.planes if is_act else 0,
                                       _p(g_same.t) if g_same is not None else None,
                                       _p(g_pool.t) if g_pool is not None else None, _p(out.t), y.n, y.c, y.h, y.w, planes,
-                                      _stream()))
+                                      int(bool(clamp_pos)), _stream()))
     return out
 
 

@@ -1,8 +1,12 @@
 """Grad-CAM / Grad-CAM++ / guided back-propagation -- drop-in for the reference's `metric/grad_cam.py`
 (GradCAM :11-127, GradCamPlusPlus :129-194, GuidedBackPropagation :196-232, mask2cam :234-251).
 
-The classifier (`net`, a torchvision VGG16 in E_mis_align_cropping_s1.py:99-106) stays the caller's PyTorch module;
-what the reference does AFTER the backward pass on the host -- per-image NumPy loops, `cv2.resize`, `cv2.applyColorMap`,
+The classifier (`net`, a torchvision VGG16 in E_mis_align_cropping_s1.py:99-106) stays the caller's PyTorch module and the
+owner of its weights.  When it has the torchvision-VGG layout its convolutional stack runs forward and backward on this
+library's kernels (dge_b200/vgg_fused.py: convs with bias + ReLU epilogues, ReLU / max-pool backward with the guided clamp,
+tcgen05 data-gradient convs; the fully-connected head stays the caller's modules) and reports exactly what the reference's
+hooks observe; any other network runs through its own modules with the reference's hooks (`FUSED_VGG = False` forces that).
+What the reference does AFTER the backward pass on the host -- per-image NumPy loops, `cv2.resize`, `cv2.applyColorMap`,
 several device->host copies -- runs on the device: class-index argmax / bincount mode (bit-exact), channel weights,
 the CAM sum, min/max normalisation, the bilinear resize and the JET overlay.  Outputs keep the reference's dtypes:
 `__call__` -> float64 [N,1,H,W] (a CUDA tensor here; the reference returns a CPU tensor that the scripts move to the GPU).
@@ -13,6 +17,22 @@ import numpy as np
 import torch
 
 from dge_b200 import ops
+from dge_b200 import vgg_fused
+
+FUSED_VGG = True      # False: always run the caller's network through its own modules + hooks
+
+
+def _fused_runner(net, layer_name=None):
+    """The shared FusedVGG of a network (cached on the module) when the fused path applies, else None."""
+    if not FUSED_VGG or not vgg_fused.supported(net) or net.training:
+        return None
+    r = net.__dict__.get('_dge_fused_vgg')
+    if r is None:
+        r = vgg_fused.FusedVGG(net)
+        net.__dict__['_dge_fused_vgg'] = r
+    if layer_name is not None and layer_name not in r.names:
+        return None
+    return r
 
 
 def _class_index(output, index):
@@ -79,6 +99,16 @@ class GradCAM(object):
         if not inputs.is_cuda:
             raise ops.DgeError('GradCAM: dge_b200 runs on a B200 only; there is no CPU fallback')
         self.net.zero_grad()
+        fused = _fused_runner(self.net, self.layer_name)
+        if fused is not None:
+            output = fused.forward(inputs)                          # conv stack on dge_b200 kernels
+            self.feature = fused.feature(self.layer_name)           # what the forward hook saw (post in-place ReLU)
+            print("feature shape:{}".format(self.feature.size()))
+            _, index_max = _class_index(output, index)
+            output[:, index_max].mean().backward(retain_graph=True)
+            self.gradient = fused.backward(stop_at=self.layer_name)
+            print("gradient shape:{}".format(self.gradient.size()))
+            return cam_maps(self.feature, self.gradient, (inputs.size(2), inputs.size(3)), self.plus)
         output = self.net(inputs)                                   # [N, num_classes]
         _, index_max = _class_index(output, index)
         target = output[:, index_max].mean()
@@ -94,7 +124,8 @@ class GradCamPlusPlus(GradCAM):
 
 
 class GuidedBackPropagation(object):
-    """Reference :196-232 -- ReLU backward hooks on the caller's network; pure autograd, nothing to accelerate."""
+    """Reference :196-232 -- ReLU backward hooks on the caller's network (they also stay in force for every later backward
+    through it, Grad-CAM's included); a torchvision VGG runs its conv stack on the fused kernels with the same clamp."""
 
     def __init__(self, net):
         self.net = net
@@ -109,6 +140,14 @@ class GuidedBackPropagation(object):
 
     def __call__(self, inputs, index=None):
         self.net.zero_grad()
+        fused = _fused_runner(self.net) if inputs.is_cuda and inputs.requires_grad else None
+        if fused is not None:
+            output = fused.forward(inputs)
+            _, index_max = _class_index(output, index)
+            output[:, index_max].mean().backward(retain_graph=True)
+            g = fused.backward(stop_at=None).to(inputs.dtype)
+            inputs.grad = g if inputs.grad is None else inputs.grad + g
+            return inputs.grad
         output = self.net(inputs)
         _, index_max = _class_index(output, index)
         target = output[:, index_max].mean()

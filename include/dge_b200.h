@@ -387,9 +387,10 @@ int dge_maxpool_to_act(const float* x_f32b, void* out_act, int n, int c, int h, 
      out = (y > 0) * (g_same + (pixel is the first maximum of its 2x2 window ? g_pool[y/2][x/2] : 0))
    y = the activated conv output: F32B (y_f32b) or ACT (y_act, y_planes: hi (+ lo) planes; an ACT holds ~17 bits, so window
    maxima closer than that may route differently from the fp32 map -- the LPIPS node keeps its pooled taps in F32B) -- exactly one;
-   g_same F32B [n][c/8][h][w][8] or NULL; g_pool F32B [n][c/8][h/2][w/2][8] or NULL (at least one). */
+   g_same F32B [n][c/8][h][w][8] or NULL; g_pool F32B [n][c/8][h/2][w/2][8] or NULL (at least one).
+   clamp_pos != 0: out = max(out, 0) -- the ReLU backward hook of GuidedBackPropagation (metric/grad_cam.py:209-211). */
 int dge_relu_pool_bwd(const float* y_f32b, const void* y_act, int y_planes, const float* g_same, const float* g_pool,
-                      void* out_act, int n, int c, int h, int w, int planes, void* stream);
+                      void* out_act, int n, int c, int h, int w, int planes, int clamp_pos, void* stream);
 /* One LPIPS tap: f F32B [2*nb][c/8][h][w][8] holds the features of the two image batches (a = f[0:nb], b = f[nb:2nb]).
    forward  (ga == gb == NULL): out[n] += mean_p sum_c lin_w[c] * (a_c/(|a|+eps) - b_c/(|b|+eps))^2      (out: caller-zeroed)
    backward (go = upstream gradient [nb]): gb / ga (F32B [nb][c/8][h][w][8], either may be NULL) = d out / d b, d out / d a. */

@@ -71,3 +71,62 @@ def test_gradcam_classes_end_to_end(fx):
         g = gbp(x)
         assert g.shape == x.shape and torch.isfinite(g).all()
     assert "feature shape:" in buf.getvalue() and "gradient shape:" in buf.getvalue()
+
+
+def test_fused_vgg16_matches_the_hooked_network():
+    """torchvision VGG16 (random weights: the pretrained ones are not available offline): the conv stack on this library's
+    kernels (dge_b200/vgg_fused.py) against the same network run through its own modules with the reference's hooks --
+    logits, the hooked feature / gradient of `features.28`, the Grad-CAM++ mask and the guided-backprop image gradient,
+    with and without GuidedBackPropagation's ReLU hooks in force (E_mis_align_cropping_s1.py:99-106 registers both on one net).
+    Gradients in the L2 norm: a ReLU / max-pool decision within rounding of a tie may differ between the two arithmetic
+    orders and moves isolated entries only."""
+    import numpy as np
+    import metric.grad_cam as gc
+    from torchvision.models import vgg16
+    # the comparison network must compute in true fp32: cuDNN's default TF32 convs (10-bit operands) flip ReLU / max-pool
+    # decisions against an fp32-equivalent run by themselves
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    net = vgg16(weights=None).cuda().eval()
+    assert gc.vgg_fused.supported(net)
+    g = torch.Generator().manual_seed(3)
+    imgs = (torch.rand(2, 3, 64, 64, generator=g) * 2 - 1).cuda()
+    index = np.array([17, 17])
+    rel2 = lambda a, b: ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+    def run(fused, with_gbp):
+        gc.FUSED_VGG = fused
+        net.__dict__.pop('_dge_fused_vgg', None)
+        for m in net.modules():
+            m._backward_hooks.clear()
+            m._forward_hooks.clear()
+        try:
+            with contextlib.redirect_stdout(io.StringIO()) as buf:
+                cam = gc.GradCamPlusPlus(net, "features.28")
+                gbp = gc.GuidedBackPropagation(net) if with_gbp else None
+                mask = cam(imgs, index)
+                feat, grad = cam.feature.detach().clone(), cam.gradient.detach().clone()
+                gi = None
+                if gbp is not None:
+                    x = imgs.clone().requires_grad_(True)
+                    gi = gbp(x, index).detach().clone()
+                cam.remove_handlers()
+            assert "feature shape:" in buf.getvalue() and "gradient shape:" in buf.getvalue()
+            return mask, feat, grad, gi
+        finally:
+            gc.FUSED_VGG = True
+
+    with torch.no_grad():
+        fused_logits = gc.vgg_fused.FusedVGG(net).forward(imgs)
+        assert rel(fused_logits, net(imgs)) < 1e-3
+    for with_gbp in (False, True):
+        mf, ff, gf, xf = run(True, with_gbp)
+        mh, fh, gh, xh = run(False, with_gbp)
+        assert mf.dtype == torch.float64 and mf.shape == (2, 1, 64, 64)
+        assert rel(ff, fh) < 1e-3                                  # the post-ReLU map the forward hook sees
+        assert rel2(gf, gh) < 3e-3, with_gbp                       # the masked (and, with gbp, clamped) gradient
+        assert rel2(mf, mh) < 3e-3, with_gbp
+        if with_gbp:
+            assert float(gf.min()) >= 0 and float(gh.min()) >= 0   # GuidedBackPropagation's hooks clamp Grad-CAM too
+            assert xf.shape == imgs.shape and rel2(xf, xh) < 3e-3
