@@ -644,18 +644,28 @@ __global__ void k_relu_pool_bwd(const float* __restrict__ y_f32b, const void* __
 // Thread = one pixel: four channel sums give everything (also for the backward):
 //   Saa = sum a^2, Sbb = sum b^2, Waa = sum w a^2, Wbb = sum w b^2, Wab = sum w a b ;  d = Waa/na^2 + Wbb/nb^2 - 2 Wab/(na nb)
 // grad_mode: 0 = forward; 1 = gradient w.r.t. b -> gb (F32B [nb]); 2 = w.r.t. a -> ga; 3 = both.  go[n] = upstream gradient.
+// Eight lanes share a pixel, each taking every 8th channel group (the deep taps have 512 channels on 16 x 16 pixels: one
+// thread per pixel would walk 64 groups serially with a few thousand threads in flight); the five sums meet in a 3-step
+// shuffle.  A warp reads 4 pixels x 8 groups: 128-byte runs.
+constexpr int LP_CS = 8;
 __global__ void __launch_bounds__(256)
 k_lpips_dist(const float* __restrict__ f, const float* __restrict__ lw, float* __restrict__ out,
              const float* __restrict__ go, float* __restrict__ ga, float* __restrict__ gb, int grad_mode, int nb, int c,
              int hw, float eps) {
   __shared__ float red[8];
   const int C8 = c >> 3, n = blockIdx.y;
+  const int sub = threadIdx.x & (LP_CS - 1);
   const float inv_hw = 1.f / (float)hw;
   float part = 0.f;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)hw; i += (size_t)gridDim.x * blockDim.x) {
+  const size_t stride = ((size_t)gridDim.x * blockDim.x) / LP_CS;
+  // the loop bound is WARP-uniform (the shuffles below name all 32 lanes); pixels beyond the map contribute zeros
+  const size_t warp_first = (blockIdx.x * (size_t)blockDim.x + (threadIdx.x & ~31u)) / LP_CS;
+  for (size_t i0 = warp_first; i0 < (size_t)hw; i0 += stride) {
+    const size_t i = i0 + ((threadIdx.x & 31) / LP_CS);
+    const bool valid = i < (size_t)hw;
     float saa = 0.f, sbb = 0.f, waa = 0.f, wbb = 0.f, wab = 0.f;
-#pragma unroll 4      // (up to 64 channel groups per pixel: keep several 32-byte loads in flight)
-    for (int g = 0; g < C8; ++g) {
+#pragma unroll 2
+    for (int g = sub; valid && g < C8; g += LP_CS) {
       float a[8], b[8];
       load8_f32b(f, ((size_t)n * C8 + g) * hw + i, a);
       load8_f32b(f, ((size_t)(n + nb) * C8 + g) * hw + i, b);
@@ -669,18 +679,26 @@ k_lpips_dist(const float* __restrict__ f, const float* __restrict__ lw, float* _
         wab = fmaf(w * a[k], b[k], wab);
       }
     }
+#pragma unroll
+    for (int off = LP_CS / 2; off; off >>= 1) {
+      saa += __shfl_xor_sync(0xffffffffu, saa, off);
+      sbb += __shfl_xor_sync(0xffffffffu, sbb, off);
+      waa += __shfl_xor_sync(0xffffffffu, waa, off);
+      wbb += __shfl_xor_sync(0xffffffffu, wbb, off);
+      wab += __shfl_xor_sync(0xffffffffu, wab, off);
+    }
     const float ra = sqrtf(saa), rb = sqrtf(sbb), na = ra + eps, nbn = rb + eps;
     if (grad_mode == 0) {
-      part += waa / (na * na) + wbb / (nbn * nbn) - 2.f * wab / (na * nbn);
+      if (sub == 0 && valid) part += waa / (na * na) + wbb / (nbn * nbn) - 2.f * wab / (na * nbn);
       continue;
     }
+    if (!valid) continue;
     // u = a/na, v = b/nbn;  dD/dv_c = -2 w_c (u_c - v_c);  dv_c/db_k = delta_ck/nbn - b_c b_k/(nbn^2 rb)
     //   dD/db_k = (1/nbn) [ gv_k - b_k/(nbn rb) * sum_c gv_c b_c ],  sum_c gv_c b_c = -2 (wab/na - wbb/nbn)   (a: symmetric)
     const float scale = __ldg(go + n) * inv_hw;
     const float sgb = -2.f * (wab / na - wbb / nbn), sga = -2.f * (wab / nbn - waa / na);
     const float cb = rb > 0.f ? sgb / (nbn * rb) : 0.f, ca = ra > 0.f ? sga / (na * ra) : 0.f;
-#pragma unroll 2
-    for (int g = 0; g < C8; ++g) {
+    for (int g = sub; g < C8; g += LP_CS) {
       float a[8], b[8], da[8], db[8];
       load8_f32b(f, ((size_t)n * C8 + g) * hw + i, a);
       load8_f32b(f, ((size_t)(n + nb) * C8 + g) * hw + i, b);
@@ -876,7 +894,7 @@ extern "C" int dge_lpips_dist(const float* f, const float* lin_w, float* out, co
   DGE_REQUIRE(f && lin_w && nb > 0 && c >= 8 && c % 8 == 0 && h > 0 && w > 0, "lpips_dist: bad arguments");
   const int mode = (gb ? 1 : 0) | (ga ? 2 : 0);
   DGE_REQUIRE(mode ? go != nullptr : out != nullptr, "lpips_dist: forward needs out, backward needs go");
-  long long blocks = ((long long)h * w + 255) / 256, want = ((long long)tb_sms() * 8 + nb - 1) / nb;
+  long long blocks = ((long long)h * w * LP_CS + 255) / 256, want = ((long long)tb_sms() * 8 + nb - 1) / nb;
   if (blocks > want) blocks = want;
   if (blocks < 1) blocks = 1;
   dim3 grid((unsigned)blocks, (unsigned)nb);
