@@ -73,7 +73,7 @@ __device__ __forceinline__ void store8_act_at(void* base, size_t idx16_hi, size_
 //                                        dres ACT [n][co/8][planes][ho][wo][8]   = gb * d_out        (optional)
 //   sums[0][c] += sum dy2, sums[1][c] += sum dy2 * noise, sums[2][c] += sum dres     (bias_2, noise_weight_2, conv_3.bias)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TB_THREADS)
+__global__ void __launch_bounds__(TB_THREADS, 3)
 k_be_head_bwd(const float* __restrict__ d_out, const float* __restrict__ y2, const float* __restrict__ noise,
               float ga4, float gb, float slope, void* __restrict__ dy2, void* __restrict__ dres,
               float* __restrict__ sums, int co, int ho, int wo, int planes) {
@@ -173,7 +173,7 @@ k_in_bwd_stats(const float* __restrict__ g, const float* __restrict__ x, const f
 //   mode 1: dx *= lrelu'(x) (x is the activated conv output, so its sign is the pre-activation's) -> ACT, and
 //           sums2[0][c] += sum dx (bias), sums2[1][c] += sum dx * noise (noise weight)            (E.py:60-62)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TB_THREADS)
+__global__ void __launch_bounds__(TB_THREADS, 3)
 k_in_bwd_apply(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ mr,
                const float* __restrict__ style, const float* __restrict__ dstyle, const double* __restrict__ sums,
                int mode, const float* __restrict__ res, float rscale, int res_pool, const float* __restrict__ noise,
