@@ -176,14 +176,14 @@ k_in_bwd_stats(const float* __restrict__ g, const float* __restrict__ x, const f
 __global__ void __launch_bounds__(TB_THREADS, 3)
 k_in_bwd_apply(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ mr,
                const float* __restrict__ style, const float* __restrict__ dstyle, const double* __restrict__ sums,
-               int mode, const float* __restrict__ res, float rscale, int res_pool, const float* __restrict__ noise,
-               float slope, float* __restrict__ out_f32b, void* __restrict__ out_act, float* __restrict__ sums2, int c,
-               int h, int w, int planes) {
+               const float* __restrict__ gscale, int mode, const float* __restrict__ res, float rscale, int res_pool,
+               const float* __restrict__ noise, float slope, float* __restrict__ out_f32b, void* __restrict__ out_act,
+               float* __restrict__ sums2, int c, int h, int w, int planes) {
   __shared__ float red[TB_THREADS / 32][16];
   const int C8 = c >> 3, ng = blockIdx.y, nidx = ng / C8, grp = ng - nidx * C8;
   const size_t hw = (size_t)h * w;
   const float inv_hw = 1.f / (float)hw;
-  float m[8], r[8], a[8], b[8], cm[8], cs[8];
+  float m[8], r[8], a[8], b[8], cm[8], cs[8], gs[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int ch = grp * 8 + k;
@@ -192,6 +192,7 @@ k_in_bwd_apply(const float* __restrict__ g, const float* __restrict__ x, const f
     r[k] = __ldg(mr + o + 1);
     a[k] = (float)(sums[o] / (double)hw);
     b[k] = (float)(sums[o + 1] / (double)hw);
+    gs[k] = gscale ? __ldg(gscale + (size_t)nidx * c + ch) : 1.f;
     cm[k] = cs[k] = 0.f;
     if (dstyle) {
       const float sd = __ldg(style + (size_t)nidx * 2 * c + c + ch);
@@ -212,7 +213,7 @@ k_in_bwd_apply(const float* __restrict__ g, const float* __restrict__ x, const f
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float xc = xv[k] - m[k];
-      v[k] = r[k] * (gv[k] - a[k] - xc * r[k] * b[k]) + cm[k] + cs[k] * xc;
+      v[k] = r[k] * gs[k] * (gv[k] - a[k] - xc * r[k] * b[k]) + cm[k] + cs[k] * xc;
     }
     if (mode == 0) {
       if (res) {
@@ -235,7 +236,8 @@ k_in_bwd_apply(const float* __restrict__ g, const float* __restrict__ x, const f
         acc[k] += v[k];
         acc[8 + k] = fmaf(v[k], nz, acc[8 + k]);
       }
-      store8_act_at(out_act, (size_t)ng * planes * hw + i, hw, planes, v);
+      if (out_act) store8_act_at(out_act, (size_t)ng * planes * hw + i, hw, planes, v);
+      if (out_f32b) store8_f32b(out_f32b, base + i, v);
     }
   }
   if (mode == 1) {
@@ -431,11 +433,21 @@ k_sg2_layer_bwd(const __grid_constant__ Sg2BwdParams p) {
 // DGE_CONV_DOWN4X4S2 with a zero first kernel row / column then is the 3x3 stride-2 conv that inverts the transposed conv.
 // Thread = one (Y, X, channel group): a 5x5 window of dconv -> the four phases.
 // ---------------------------------------------------------------------------------------------
+// box != 0: the 2x2 box sum of the StyleGAN1 `transform_kernel` layers instead (dge_sg1_post mode 1, lreq.py:127-131):
+//   dt[u][v] = sum_{a,b<2} dconv[u-a][v-b].
 __global__ void __launch_bounds__(TB_THREADS)
-k_up_fir_bwd_s2d(const float* __restrict__ dconv, void* __restrict__ out, int n, int c, int H, int W, int planes) {
+k_up_fir_bwd_s2d(const float* __restrict__ dconv, void* __restrict__ out, int n, int c, int H, int W, int planes,
+                 int box) {
   const int C8 = c >> 3, Hs = H + 1, Ws = W + 1, Ho = 2 * H, Wo = 2 * W;
   const size_t total = (size_t)n * C8 * Hs * Ws;
-  const float wv[2][5] = {{0.25f, 0.75f, 0.75f, 0.25f, 0.f}, {0.f, 0.25f, 0.75f, 0.75f, 0.25f}};
+  // weights of window rows / columns 2Y-2 .. 2Y+2 for the even (0) and odd (1) phase
+  const float wfir[2][5] = {{0.25f, 0.75f, 0.75f, 0.25f, 0.f}, {0.f, 0.25f, 0.75f, 0.75f, 0.25f}};
+  const float wbox[2][5] = {{0.f, 1.f, 1.f, 0.f, 0.f}, {0.f, 0.f, 1.f, 1.f, 0.f}};
+  float wv[2][5];
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+#pragma unroll
+    for (int j = 0; j < 5; ++j) wv[q][j] = box ? wbox[q][j] : wfir[q][j];
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int X = (int)(i % Ws);
     size_t t = i / Ws;
@@ -768,9 +780,9 @@ extern "C" int dge_in_bwd_stats(const float* g, const float* x, const float* mea
 }
 
 extern "C" int dge_in_bwd_apply(const float* g, const float* x, const float* mean_rstd, const float* style,
-                                const float* dstyle, const double* sums, int mode, const float* res, float rscale,
-                                int res_pool, const float* noise, float slope, float* out_f32b, void* out_act,
-                                float* sums2, int n, int c, int h, int w, int planes, void* stream) {
+                                const float* dstyle, const double* sums, const float* gscale, int mode, const float* res,
+                                float rscale, int res_pool, const float* noise, float slope, float* out_f32b,
+                                void* out_act, float* sums2, int n, int c, int h, int w, int planes, void* stream) {
   DGE_REQUIRE(g && x && mean_rstd && sums, "in_bwd_apply: null pointer");
   DGE_REQUIRE(mode == 0 || mode == 1, "in_bwd_apply: mode=%d", mode);
   DGE_REQUIRE(n > 0 && c >= 8 && c % 8 == 0 && h > 0 && w > 0, "in_bwd_apply: bad dims n=%d c=%d h=%d w=%d", n, c, h, w);
@@ -779,13 +791,13 @@ extern "C" int dge_in_bwd_apply(const float* g, const float* x, const float* mea
     DGE_REQUIRE(out_f32b, "in_bwd_apply: mode 0 writes out_f32b");
     DGE_REQUIRE(!res || !res_pool || (h % 2 == 0 && w % 2 == 0), "in_bwd_apply: pooled residual needs even h, w");
   } else {
-    DGE_REQUIRE(out_act && sums2 && (planes == 1 || planes == 2) && c % 16 == 0,
-                "in_bwd_apply: mode 1 writes out_act (planes 1|2, c %% 16 == 0) and sums2");
+    DGE_REQUIRE((out_act || out_f32b) && sums2 && (!out_act || ((planes == 1 || planes == 2) && c % 16 == 0)),
+                "in_bwd_apply: mode 1 writes out_act (planes 1|2, c %% 16 == 0) and / or out_f32b, and sums2");
     TB_ZERO(sums2, (size_t)2 * c * sizeof(float));
   }
   dim3 grid(tb_splits((long long)h * w, (long long)n * (c / 8)), n * (c / 8));
-  k_in_bwd_apply<<<grid, TB_THREADS, 0, TB_STREAM>>>(g, x, mean_rstd, style, dstyle, sums, mode, res, rscale, res_pool,
-                                                      noise, slope, out_f32b, out_act, sums2, c, h, w, planes);
+  k_in_bwd_apply<<<grid, TB_THREADS, 0, TB_STREAM>>>(g, x, mean_rstd, style, dstyle, sums, gscale, mode, res, rscale,
+                                                      res_pool, noise, slope, out_f32b, out_act, sums2, c, h, w, planes);
   count_launch();
   return check_launch("k_in_bwd_apply");
 }
@@ -827,7 +839,7 @@ extern "C" int dge_sg2_layer_bwd(const void* ya_act, const float* ya_scale, cons
   return check_launch("k_sg2_layer_bwd");
 }
 
-extern "C" int dge_up_fir_bwd_s2d(const float* dconv, void* out_act, int n, int c, int h, int w, int planes,
+extern "C" int dge_up_fir_bwd_s2d(const float* dconv, void* out_act, int n, int c, int h, int w, int planes, int box,
                                   void* stream) {
   DGE_REQUIRE(dconv && out_act, "up_fir_bwd_s2d: null pointer");
   DGE_REQUIRE(n > 0 && c >= 16 && c % 16 == 0 && h > 0 && w > 0, "up_fir_bwd_s2d: bad dims n=%d c=%d h=%d w=%d", n, c, h, w);
@@ -835,7 +847,7 @@ extern "C" int dge_up_fir_bwd_s2d(const float* dconv, void* out_act, int n, int 
   const size_t work = (size_t)n * (c / 8) * (h + 1) * (w + 1);
   size_t g = (work + TB_THREADS - 1) / TB_THREADS;
   if (g > (size_t)tb_sms() * 32) g = (size_t)tb_sms() * 32;
-  k_up_fir_bwd_s2d<<<(int)g, TB_THREADS, 0, TB_STREAM>>>(dconv, out_act, n, c, h, w, planes);
+  k_up_fir_bwd_s2d<<<(int)g, TB_THREADS, 0, TB_STREAM>>>(dconv, out_act, n, c, h, w, planes, box);
   count_launch();
   return check_launch("k_up_fir_bwd_s2d");
 }

@@ -111,12 +111,12 @@ SIGNATURES = {
     "dge_mask2cam": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P]),
     "dge_be_head_bwd": (c_int, [P, P, P, c_float, c_float, c_float, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "dge_in_bwd_stats": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P]),
-    "dge_in_bwd_apply": (c_int, [P, P, P, P, P, P, c_int, P, c_float, c_int, P, c_float, P, P, P, c_int, c_int, c_int,
+    "dge_in_bwd_apply": (c_int, [P, P, P, P, P, P, P, c_int, P, c_float, c_int, P, c_float, P, P, P, c_int, c_int, c_int,
                                  c_int, c_int, P]),
     "dge_from_rgb_bwd": (c_int, [P, P, P, P, c_float, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "dge_sg2_layer_bwd": (c_int, [P, P, P, P, P, P, c_int64, c_float, P, P, c_float, c_float, P, c_int, P, P, c_int, c_int,
                                   c_int, c_int, c_int, P]),
-    "dge_up_fir_bwd_s2d": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "dge_up_fir_bwd_s2d": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "dge_rgb_up_bwd": (c_int, [P, P, c_int64, c_int, c_int, P]),
     "dge_lpips_input": (c_int, [P, P, c_float, c_float, c_float, c_float, c_float, c_float, c_int, c_int, c_int, c_int, P]),
     "dge_maxpool_to_act": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),

@@ -676,27 +676,30 @@ def in_bwd_stats(g, x, mean_rstd):
 
 
 def in_bwd_apply(g, x, mean_rstd, style, dstyle, sums, mode, res=None, rscale=0.0, res_pool=False, noise=None,
-                 slope=0.2, planes=2):
-    """Apply pass of the instance-norm backward.  mode 0 -> F32B dx (+ rscale*res); mode 1 -> (Act dx*lrelu'(x),
-    sums2 fp32 [2, c] = bias / noise-weight gradients)."""
+                 slope=0.2, planes=2, gscale=None, out_kind="act"):
+    """Apply pass of the instance-norm backward.  mode 0 -> F32B dx (+ rscale*res); mode 1 -> (dx*lrelu'(x) as Act, or as
+    F32B with out_kind="f32b"; sums2 fp32 [2, c] = bias / noise-weight gradients).  gscale [n, c]: the incoming gradient is
+    gscale * g (style modulation after the norm, StyleGAN1)."""
     assert isinstance(g, F32B) and isinstance(x, F32B) and (g.n, g.c, g.h, g.w) == (x.n, x.c, x.h, x.w)
     dev = x.t.device
     ds = None if dstyle is None else dstyle.contiguous()
+    gs = None if gscale is None else gscale.contiguous()
     if mode == 0:
         out = F32B(x.n, x.c, x.h, x.w, dev)
         if res is not None:
             assert isinstance(res, F32B) and res.c == x.c and res.n == x.n
             assert (res.h, res.w) == ((x.h // 2, x.w // 2) if res_pool else (x.h, x.w)), "in_bwd_apply: residual size"
         with _rec("in_bwd_apply0", (x.n, x.h, x.w, x.c)):
-            check(lib().dge_in_bwd_apply(_p(g.t), _p(x.t), _f32(mean_rstd), _f32(style), _f32(ds), _p(sums), 0,
+            check(lib().dge_in_bwd_apply(_p(g.t), _p(x.t), _f32(mean_rstd), _f32(style), _f32(ds), _p(sums), _f32(gs), 0,
                                          _p(res.t) if res is not None else None, float(rscale), int(bool(res_pool)), None,
                                          float(slope), _p(out.t), None, None, x.n, x.c, x.h, x.w, planes, _stream()))
         return out
-    out = Act(x.n, x.c, x.h, x.w, planes, dev)
+    out = Act(x.n, x.c, x.h, x.w, planes, dev) if out_kind == "act" else F32B(x.n, x.c, x.h, x.w, dev)
     sums2 = torch.empty((2, x.c), dtype=torch.float32, device=dev)
     with _rec("in_bwd_apply1", (x.n, x.h, x.w, x.c, planes)):
-        check(lib().dge_in_bwd_apply(_p(g.t), _p(x.t), _f32(mean_rstd), _f32(style), _f32(ds), _p(sums), 1, None, 0.0, 0,
-                                     _f32(noise), float(slope), None, _p(out.t), _p(sums2), x.n, x.c, x.h, x.w, planes,
+        check(lib().dge_in_bwd_apply(_p(g.t), _p(x.t), _f32(mean_rstd), _f32(style), _f32(ds), _p(sums), _f32(gs), 1, None,
+                                     0.0, 0, _f32(noise), float(slope), _p(out.t) if out_kind != "act" else None,
+                                     _p(out.t) if out_kind == "act" else None, _p(sums2), x.n, x.c, x.h, x.w, planes,
                                      _stream()))
     return out, sums2
 
@@ -738,14 +741,14 @@ def sg2_layer_bwd(ya, ya_scale, dxs, dimg, rgbw, noise, noise_batched, noise_sca
     return out, sums
 
 
-def up_fir_bwd_s2d(dconv, planes=2):
-    """FIR transpose of the x2 layer as the space-to-depth operand of the stride-2 data-gradient conv:
-    F32B [n, c, 2h, 2w] -> Act [n, 4c, h+1, w+1]."""
+def up_fir_bwd_s2d(dconv, planes=2, box=False):
+    """FIR transpose of the x2 layer (box=True: transpose of StyleGAN1's 2x2 box sum) as the space-to-depth operand of the
+    stride-2 data-gradient conv: F32B [n, c, 2h, 2w] -> Act [n, 4c, h+1, w+1]."""
     assert isinstance(dconv, F32B) and dconv.h % 2 == 0 and dconv.w % 2 == 0
     h, w = dconv.h // 2, dconv.w // 2
     out = Act(dconv.n, 4 * dconv.c, h + 1, w + 1, planes, dconv.t.device)
     with _rec("up_fir_bwd_s2d", (dconv.n, h, w, dconv.c)):
-        check(lib().dge_up_fir_bwd_s2d(_p(dconv.t), _p(out.t), dconv.n, dconv.c, h, w, planes, _stream()))
+        check(lib().dge_up_fir_bwd_s2d(_p(dconv.t), _p(out.t), dconv.n, dconv.c, h, w, planes, int(bool(box)), _stream()))
     return out
 
 

@@ -28,6 +28,9 @@ from torch.nn.parameter import Parameter
 import model.utils.lreq as ln
 from dge_b200 import autograd as tc
 from dge_b200 import ops
+from dge_b200 import train_g1
+
+FUSED_TRAIN = True     # False: `_decode_autograd` (separate torch nodes), the cross-check of the fused node
 
 DEFAULT_PLANES = 2
 
@@ -257,6 +260,8 @@ class Generator(nn.Module):
         if torch.is_grad_enabled() and styles.requires_grad:
             if not styles.is_cuda:
                 raise ops.DgeError('Generator.decode: dge_b200 runs on a B200 only; there is no CPU fallback')
+            if FUSED_TRAIN and all(b.conv_2.implicit_lreq for b in self.decode_block):
+                return train_g1.decode(self, styles, lod)            # one fused node (dge_b200/train_g1.py)
             return self._decode_autograd(styles, lod)
         ln._guard('Generator.decode', styles, self.const)
         x = ops.nchw_to_f32b(self.const.detach().float())

@@ -336,11 +336,14 @@ int dge_in_bwd_stats(const float* g, const float* x, const float* mean_rstd, dou
    mode 0: dx += rscale * res  (res F32B at the same resolution, or half resolution read through the 2x2-pool broadcast when
            res_pool; NULL: none) -> out_f32b                                            (block input; E.py:78-84 residual)
    mode 1: dx *= (x > 0 ? 1 : slope) -> out_act [n][c/8][planes][h][w][8]; sums2 fp32 [2][c] = sum dx, sum dx*noise
-           (x = lrelu(conv_1 + nw1*noise + b1), E.py:60-62: bias_1.grad and noise_weight_1.grad) */
+           (x = lrelu(conv_1 + nw1*noise + b1), E.py:60-62: bias_1.grad and noise_weight_1.grad)
+   gscale [n][c] (NULL = 1): the incoming gradient is gscale * g -- the `x*(s0+1)+s1` style modulation that follows the
+   instance norm in the StyleGAN1 generator (stylegan1/net.py:32-34, 154-156), sums being those of the un-scaled g; mode 1
+   may also (or instead) write the result as F32B (out_f32b). */
 int dge_in_bwd_apply(const float* g, const float* x, const float* mean_rstd, const float* style, const float* dstyle,
-                     const double* sums, int mode, const float* res, float rscale, int res_pool, const float* noise,
-                     float slope, float* out_f32b, void* out_act, float* sums2, int n, int c, int h, int w, int planes,
-                     void* stream);
+                     const double* sums, const float* gscale, int mode, const float* res, float rscale, int res_pool,
+                     const float* noise, float slope, float* out_f32b, void* out_act, float* sums2, int n, int c, int h,
+                     int w, int planes, void* stream);
 /* FromRGB backward (net.py:231-240, f = lrelu(conv1x1(img, W) + b)): sums fp32 [c][4] = (dW[c][0..2], db[c]) with
    d_pre = d_f * (f > 0 ? 1 : slope); d_f, f F32B [n][c/8][h][w][8]; img NCHW [n][cimg<=3][h][w].
    d_img (optional, NCHW like img; zeroed by the call): the image gradient sum_c wgt[c][i] * d_pre[c] -- the inversion loop
@@ -368,8 +371,10 @@ int dge_sg2_layer_bwd(const void* ya_act, const float* ya_scale, const float* dx
    stride-2 data-gradient conv: dconv F32B [n][c/8][2h][2w][8] -> ACT [n][4c/8][planes][h+1][w+1][8] with channel block
    (2py+px)*c/8 + g holding dt[2Y+py][2X+px], dt[u][v] = sum_{a,b<4} f[a]f[b] dconv[u-a+1][v-b+1] (f = [1,3,3,1]/4), zeros
    beyond the (2h+1) x (2w+1) raw map.  dge_conv_forward(DGE_CONV_DOWN4X4S2, in_h = h+1, in_w = w+1) with the 3x3 kernel
-   placed in rows / columns 1..3 of the 4x4 taps then is the data gradient of the transposed conv (:879-895). */
-int dge_up_fir_bwd_s2d(const float* dconv, void* out_act, int n, int c, int h, int w, int planes, void* stream);
+   placed in rows / columns 1..3 of the 4x4 taps then is the data gradient of the transposed conv (:879-895).
+   box != 0: the filter is the 2x2 box sum of the StyleGAN1 `transform_kernel` layers (stylegan1/lreq.py:127-131; forward:
+   dge_sg1_post mode 1) instead of the FIR: dt[u][v] = sum_{a,b<2} dconv[u-a][v-b]. */
+int dge_up_fir_bwd_s2d(const float* dconv, void* out_act, int n, int c, int h, int w, int planes, int box, void* stream);
 /* Transpose of dge_rgb_init's x2 up-sampling of the skip image (:519-522): d_in [planes][h_in][w_in] from
    d_out [planes][2h_in][2w_in]; per axis d_in[m] = (d[2m-1] + 3d[2m] + 3d[2m+1] + d[2m+2])/4. */
 int dge_rgb_up_bwd(const float* d_out, float* d_in, int64_t planes, int h_in, int w_in, void* stream);

@@ -276,7 +276,7 @@ def in_bwd_stats(g, x, mean_rstd):
 
 
 def in_bwd_apply(g, x, mean_rstd, style, dstyle, sums, mode, res=None, rscale=0.0, res_pool=False, noise=None,
-                 slope=0.2, planes=2):
+                 slope=0.2, planes=2, gscale=None, out_kind="act"):
     gv, xv = g.to_nchw(), x.to_nchw()
     n, c, h, w = xv.shape
     hw = h * w
@@ -285,6 +285,8 @@ def in_bwd_apply(g, x, mean_rstd, style, dstyle, sums, mode, res=None, rscale=0.
     b = (sums[:, :, 1] / hw).float()[:, :, None, None]
     xc = xv - m
     v = r * (gv - a - xc * r * b)
+    if gscale is not None:
+        v = v * gscale[:, :, None, None]
     if dstyle is not None:
         sd = style[:, c:, None, None]
         v = v + dstyle[:, :c, None, None] / hw + torch.where(sd > 0, dstyle[:, c:, None, None] / hw / sd, 0.0) * xc
@@ -297,7 +299,8 @@ def in_bwd_apply(g, x, mean_rstd, style, dstyle, sums, mode, res=None, rscale=0.
         return F32B.of(v)
     v = torch.where(xv > 0, v, v * slope)
     nz = noise.view(n, 1, h, w) if noise is not None else torch.zeros(())
-    return Act.of(v, planes), torch.stack((v.sum(dim=(0, 2, 3)), (v * nz).sum(dim=(0, 2, 3))))
+    return (Act.of(v, planes) if out_kind == "act" else F32B.of(v)), \
+        torch.stack((v.sum(dim=(0, 2, 3)), (v * nz).sum(dim=(0, 2, 3))))
 
 
 def from_rgb_bwd(d_f, f, img, slope=0.2, weight=None):
@@ -413,14 +416,59 @@ def sg2_layer_bwd(ya, ya_scale, dxs, dimg, rgbw, noise, noise_batched, noise_sca
     return (Act.of(v, planes) if out_kind == "act" else F32B.of(v)), sums
 
 
-def up_fir_bwd_s2d(dconv, planes=2):
+def _box2(t):
+    """out[y][x] = sum_{a,b<2} t[y+a][x+b]: (2h+1)^2 -> (2h)^2  (dge_sg1_post mode 1)."""
+    return t[:, :, :-1, :-1] + t[:, :, 1:, :-1] + t[:, :, :-1, 1:] + t[:, :, 1:, 1:]
+
+
+def up_fir_bwd_s2d(dconv, planes=2, box=False):
     d = dconv.to_nchw()
     n, c, ho, wo = d.shape
     t = torch.zeros((n, c, ho + 1, wo + 1), requires_grad=True)
     with torch.enable_grad():
-        y = _fir_pad1(t)
+        y = _box2(t) if box else _fir_pad1(t)
     dt = torch.autograd.grad(y, t, d)[0]
     dt = F.pad(dt, (0, 1, 0, 1))                                            # (2h+2) x (2w+2), zeros beyond the raw map
     hs, ws = ho // 2 + 1, wo // 2 + 1
     v = dt.view(n, c, hs, 2, ws, 2).permute(0, 3, 5, 1, 2, 4).reshape(n, 4 * c, hs, ws)   # channel = (2py+px)*c + ch
     return Act.of(v, planes)
+
+
+# ------------------------------------------------------------------------------------------------
+# StyleGAN1 pieces (csrc/elementwise.cu: k_sg1_post, k_instance_norm_style, k_to_rgb_f32b)
+# ------------------------------------------------------------------------------------------------
+def _blur3(x):
+    c = x.shape[1]
+    f = torch.tensor([0.25, 0.5, 0.25])
+    k = (f[:, None] * f[None, :]).expand(c, 1, 3, 3).contiguous()
+    return F.conv2d(x, k, padding=1, groups=c)
+
+
+def sg1_post(src, mode, n, c, h_out, w_out, noise=None, noise_w=None, bias=None, slope=0.2):
+    if mode == 1:
+        v = _blur3(_box2(_from_blocked(src)))
+    elif mode == 0:
+        v = _blur3(src.to_nchw())
+    else:
+        v = src.to_nchw()
+    if noise is not None:
+        v = v + noise.reshape(n, 1, h_out, w_out) * noise_w.view(1, -1, 1, 1)
+    if bias is not None:
+        v = v + bias.view(1, -1, 1, 1)
+    return F32B.of(torch.where(v < 0, v * slope, v))
+
+
+def instance_norm_style(x, mean_rstd, style, n, up=1, planes=2, out_act=True, out_f32b=False):
+    c = x.c
+    y = _in_apply(x, mean_rstd)
+    if y.shape[0] == 1 and n > 1:
+        y = y.expand(n, -1, -1, -1)
+    if style is not None:
+        y = y * (style[:, :c, None, None] + 1) + style[:, c:, None, None]
+    if up == 2:
+        y = y.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
+    return (Act.of(y, planes) if out_act else None), (F32B.of(y) if out_f32b else None)
+
+
+def to_rgb_f32b(x, w, bias):
+    return F.conv2d(x.to_nchw(), w.detach().float().view(w.shape[0], -1, 1, 1), None if bias is None else bias.detach().float())

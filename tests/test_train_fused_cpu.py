@@ -149,3 +149,24 @@ def test_fused_full_iteration_matches_unfused_graph(emu, emu_g):
     #  arithmetic orders may disagree on its slope: the bar here is the flip-tolerant one)
     worst = max(rel(g_f[k], g_u[k]) for k in g_u)
     assert worst < 1e-2, worst
+
+
+def test_fused_stylegan1_generator_matches_reference_gradients(monkeypatch):
+    """dge_b200/train_g1.py: d image / d styles of the fused StyleGAN1 node (emulated kernels) against the reference's own
+    backward (train_grads.pt: sg1_dstyles) for lod 5 (transposed-conv blocks), 3 (nearest-up blocks) and 0 (const block)."""
+    from dge_b200 import train_g1
+    from model.stylegan1.net import Generator
+    monkeypatch.setattr(train_g1, "K", emu_ops)
+    fx = torch.load(os.path.join(GOLD, "sg1_l6.pt"))
+    ref = torch.load(os.path.join(GOLD, "train_grads.pt"))
+    Gs = Generator(**fx["config"])
+    Gs.load_state_dict(fx["state_dict"], strict=True)
+    for lod, img in fx["images"].items():
+        styles = fx["styles"].clone().requires_grad_(True)
+        torch.manual_seed(60 + lod)
+        out = train_g1.decode(Gs, styles, lod)
+        assert rel(out, img) < 2e-4, lod
+        target = torch.randn(out.shape, generator=torch.Generator().manual_seed(2))
+        ((out - target) ** 2).mean().backward()
+        assert rel(styles.grad, ref["sg1_dstyles"][lod]) < 1e-3, lod
+    assert all(p.grad is None for p in Gs.parameters())

@@ -77,6 +77,11 @@ def test_instance_norm_backward_kernels(n, c, h, w):
         assert rel(got.to_nchw(), ref.to_nchw()) < 2e-5
         scale = ref.to_nchw().abs().sum(dim=(0, 2, 3)).max()
         assert ((s2.cpu() - e_s2).abs().max() / scale).item() < 1e-5
+    # StyleGAN1 form: per-(sample, channel) scale on the incoming gradient, fp32 output
+    gsc = torch.randn(n, c, generator=g) + 1.0
+    got, _ = ops.in_bwd_apply(gd, xd, mr_d, None, None, st, 1, slope=0.2, gscale=gsc.cuda(), out_kind="f32b")
+    ref, _ = emu.in_bwd_apply(emu.F32B.of(gr), xe, mr, None, None, e_st, 1, slope=0.2, gscale=gsc, out_kind="f32b")
+    assert isinstance(got, ops.F32B) and rel(got.to_nchw(), ref.to_nchw()) < 2e-5
 
 
 def test_instance_norm_backward_is_the_autograd_of_the_forward():
@@ -278,6 +283,28 @@ def test_up_layer_data_gradient(n, ci, co, h, w):
     assert (got.h, got.w) == (h, w)
     x = torch.zeros(n, ci, h, w, requires_grad=True)
     y = emu._fir_pad1(F.conv_transpose2d(x, wgt.flip(2, 3).transpose(0, 1), stride=2))
+    (dx,) = torch.autograd.grad(y, x, dconv)
+    assert rel(got.to_nchw(), dx) < 2e-4
+
+
+@pytest.mark.parametrize("n,c,h,w", [(2, 16, 4, 4), (1, 32, 16, 24), (2, 16, 9, 5)])
+def test_box_sum_transpose_space_to_depth(n, c, h, w):
+    """StyleGAN1 `transform_kernel` layer backwards: transpose of the 2x2 box sum written space-to-depth, then DOWN4X4S2 ==
+    autograd of conv_transpose2d(stride 2) + box sum."""
+    import torch.nn.functional as F
+    from dge_b200 import ops
+    g = torch.Generator().manual_seed(c + h)
+    ci = 32
+    wt = torch.randn(ci, c, 3, 3, generator=g) * 0.2                    # [in, out, k, k], used un-flipped
+    dconv = torch.randn(n, c, 2 * h, 2 * w, generator=g)
+    s2d_d = ops.up_fir_bwd_s2d(_dev_f32b(dconv), box=True)
+    s2d_e = emu.up_fir_bwd_s2d(emu.F32B.of(dconv), box=True)
+    assert rel(s2d_d.to_nchw(), s2d_e.to_nchw()) < 1e-5
+    w4 = torch.zeros(ci, c, 4, 4)
+    w4[:, :, 1:, 1:] = wt
+    got = ops.conv(s2d_d, ops.pack_conv_weight(w4.cuda()), ci, ops.CONV_DOWN4X4S2, out_f32b=True, out_hw=(h, w))["f32b"]
+    x = torch.zeros(n, ci, h, w, requires_grad=True)
+    y = emu._box2(F.conv_transpose2d(x, wt, stride=2))
     (dx,) = torch.autograd.grad(y, x, dconv)
     assert rel(got.to_nchw(), dx) < 2e-4
 
