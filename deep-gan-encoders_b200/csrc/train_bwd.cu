@@ -738,6 +738,76 @@ k_lpips_dist(const float* __restrict__ f, const float* __restrict__ lw, float* _
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// conditional batch norm + (leaky) ReLU, backward -- the frozen BigGAN generator under loss.backward()
+// (biggan_generator.py:138-150 + 178-190: t = relu(a[n][c] * x + b[n][c]) [-> nearest x2] -> conv).
+//   g    F32B [n][c/8][h*up][w*up][8]  gradient of the conv's input (what its data-gradient conv wrote)
+//   x    F32B [n][c/8][h][w][8]        the block-norm's input kept by the forward
+//   d    = (a*x + b > 0 ? 1 : slope) * sum_{up x up} g
+//   sums [n][c][2] += (sum d * x, sum d)                 -> gradients of a and b (the condition vector's path)
+//   dx   = a * d (+ for channels < skip_c: sum_{sup x sup} skip, the channel-drop / nearest-up identity branch :192-203)
+//        -> out_f32b and / or out_act (the operand of the next data-gradient conv)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TB_THREADS, 3)
+k_affine_relu_bwd(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ a,
+                  const float* __restrict__ b, float slope, int up, const float* __restrict__ skip, int skip_c, int sup,
+                  float* __restrict__ out_f32b, void* __restrict__ out_act, float* __restrict__ sums, int c, int h, int w,
+                  int planes) {
+  __shared__ float red[TB_THREADS / 32][16];
+  const int C8 = c >> 3, ng = blockIdx.y, nidx = ng / C8, grp = ng - nidx * C8;
+  const size_t hw = (size_t)h * w;
+  float av[8], bv[8], acc[16];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    av[k] = __ldg(a + (size_t)nidx * c + grp * 8 + k);
+    bv[k] = __ldg(b + (size_t)nidx * c + grp * 8 + k);
+    acc[k] = acc[8 + k] = 0.f;
+  }
+  const size_t base = (size_t)ng * hw, gbase = base * (size_t)(up * up);
+  const int gw = w * up;
+  const bool has_skip = skip && grp * 8 < skip_c;
+  const size_t sbase = ((size_t)nidx * (skip_c >> 3) + grp) * hw * (size_t)(sup * sup);
+  const int sw = w * sup;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < hw; i += (size_t)gridDim.x * blockDim.x) {
+    const int y = (int)(i / w), xx = (int)(i - (size_t)y * w);
+    float xv[8], gs[8], v[8];
+    load8_f32b(x, base + i, xv);
+    if (up == 1) {
+      load8_f32b(g, gbase + i, gs);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) gs[k] = 0.f;
+      for (int dy = 0; dy < up; ++dy)
+        for (int dx = 0; dx < up; ++dx) {
+          float t[8];
+          load8_f32b(g, gbase + (size_t)(y * up + dy) * gw + (xx * up + dx), t);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) gs[k] += t[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float d = fmaf(av[k], xv[k], bv[k]) > 0.f ? gs[k] : gs[k] * slope;
+      acc[2 * k] = fmaf(d, xv[k], acc[2 * k]);
+      acc[2 * k + 1] += d;
+      v[k] = av[k] * d;
+    }
+    if (has_skip) {
+      for (int dy = 0; dy < sup; ++dy)
+        for (int dx = 0; dx < sup; ++dx) {
+          float t[8];
+          load8_f32b(skip, sbase + (size_t)(y * sup + dy) * sw + (xx * sup + dx), t);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] += t[k];
+        }
+    }
+    if (out_f32b) store8_f32b(out_f32b, base + i, v);
+    if (out_act) store8_act_at(out_act, (size_t)ng * planes * hw + i, hw, planes, v);
+  }
+  const float t = block_sums<16>(acc, red);
+  if (threadIdx.x < 16) atomicAdd(sums + ((size_t)nidx * c + grp * 8) * 2 + threadIdx.x, t);
+}
+
 }  // namespace dge
 
 using namespace dge;
@@ -800,6 +870,24 @@ extern "C" int dge_in_bwd_apply(const float* g, const float* x, const float* mea
                                                       res_pool, noise, slope, out_f32b, out_act, sums2, c, h, w, planes);
   count_launch();
   return check_launch("k_in_bwd_apply");
+}
+
+extern "C" int dge_affine_relu_bwd(const float* g, const float* x, const float* a, const float* b, float slope, int up,
+                                   const float* skip, int skip_c, int skip_up, float* out_f32b, void* out_act,
+                                   float* sums, int n, int c, int h, int w, int planes, void* stream) {
+  DGE_REQUIRE(g && x && a && b && sums && (out_f32b || out_act), "affine_relu_bwd: null pointer");
+  DGE_REQUIRE(n > 0 && c >= 8 && c % 8 == 0 && h > 0 && w > 0, "affine_relu_bwd: bad dims n=%d c=%d h=%d w=%d", n, c, h, w);
+  DGE_REQUIRE(up == 1 || up == 2, "affine_relu_bwd: up=%d", up);
+  DGE_REQUIRE(!skip || (skip_c >= 8 && skip_c % 8 == 0 && skip_c <= c && (skip_up == 1 || skip_up == 2)),
+              "affine_relu_bwd: skip needs 8 <= skip_c <= c, a multiple of 8, and skip_up 1|2 (skip_c=%d skip_up=%d)",
+              skip_c, skip_up);
+  DGE_REQUIRE(!out_act || ((planes == 1 || planes == 2) && c % 16 == 0), "affine_relu_bwd: out_act needs planes 1|2, c %% 16 == 0");
+  TB_ZERO(sums, (size_t)2 * n * c * sizeof(float));
+  dim3 grid(tb_splits((long long)h * w, (long long)n * (c / 8)), n * (c / 8));
+  k_affine_relu_bwd<<<grid, TB_THREADS, 0, TB_STREAM>>>(g, x, a, b, slope, up, skip, skip_c, skip ? skip_up : 1, out_f32b,
+                                                        out_act, sums, c, h, w, planes);
+  count_launch();
+  return check_launch("k_affine_relu_bwd");
 }
 
 extern "C" int dge_from_rgb_bwd(const float* d_f, const float* f, const float* img, const float* wgt, float slope,

@@ -113,6 +113,8 @@ SIGNATURES = {
     "dge_in_bwd_stats": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P]),
     "dge_in_bwd_apply": (c_int, [P, P, P, P, P, P, P, c_int, P, c_float, c_int, P, c_float, P, P, P, c_int, c_int, c_int,
                                  c_int, c_int, P]),
+    "dge_affine_relu_bwd": (c_int, [P, P, P, P, c_float, c_int, P, c_int, c_int, P, P, P, c_int, c_int, c_int, c_int,
+                                    c_int, P]),
     "dge_from_rgb_bwd": (c_int, [P, P, P, P, c_float, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "dge_sg2_layer_bwd": (c_int, [P, P, P, P, P, P, c_int64, c_float, P, P, c_float, c_float, P, c_int, P, P, c_int, c_int,
                                   c_int, c_int, c_int, P]),

@@ -704,6 +704,27 @@ def in_bwd_apply(g, x, mean_rstd, style, dstyle, sums, mode, res=None, rscale=0.
     return out, sums2
 
 
+def affine_relu_bwd(g, x, a, b, slope=0.0, up=1, skip=None, skip_up=1, out_act=True, out_f32b=False, planes=2):
+    """Backward of t = act(a*x + b) [-> nearest x`up`] (biggan_generator.py:138-150, 178-190) -> (Act | None, F32B | None,
+    sums fp32 [n, c, 2] = (d a, d b)).  `skip` (F32B, its first channels, `skip_up` x finer): added to dx (:192-203)."""
+    assert isinstance(g, F32B) and isinstance(x, F32B)
+    assert (g.n, g.c, g.h, g.w) == (x.n, x.c, x.h * up, x.w * up), "affine_relu_bwd: geometry mismatch"
+    assert a.shape == (x.n, x.c) and b.shape == (x.n, x.c)
+    if skip is not None:
+        assert isinstance(skip, F32B) and (skip.n, skip.h, skip.w) == (x.n, x.h * skip_up, x.w * skip_up) and skip.c <= x.c
+    dev = x.t.device
+    act = Act(x.n, x.c, x.h, x.w, planes, dev) if out_act else None
+    f = F32B(x.n, x.c, x.h, x.w, dev) if out_f32b else None
+    sums = torch.empty((x.n, x.c, 2), dtype=torch.float32, device=dev)
+    with _rec("affine_relu_bwd", (x.n, x.h, x.w, x.c, up)):
+        check(lib().dge_affine_relu_bwd(_p(g.t), _p(x.t), _f32(a.contiguous()), _f32(b.contiguous()), float(slope), int(up),
+                                        _p(skip.t) if skip is not None else None, skip.c if skip is not None else 0,
+                                        int(skip_up), _p(f.t) if f is not None else None,
+                                        _p(act.t) if act is not None else None, _p(sums), x.n, x.c, x.h, x.w, planes,
+                                        _stream()))
+    return act, f, sums
+
+
 def from_rgb_bwd(d_f, f, img, slope=0.2, weight=None):
     """FromRGB backward -> fp32 [c, 4] = (dW[c, 0..2], db[c]); with `weight` ([c, cimg, 1, 1]) also the image gradient:
     -> (sums, d_img NCHW)."""

@@ -21,6 +21,7 @@ from dge_b200 import autograd as tc
 from dge_b200 import ops
 
 DEFAULT_PLANES = 2
+FUSED_TRAIN = True      # one fused autograd node per block (dge_b200/train_big.py); False: separate torch nodes
 
 
 class FromRGB(nn.Module):
@@ -154,6 +155,9 @@ class BE(nn.Module):
         return f.to_nchw()
 
     def _features_autograd(self, x, cond_vector, block_num=9):
+        if FUSED_TRAIN:
+            from dge_b200 import train_big
+            return train_big.ebig_features(self, x, cond_vector, block_num)
         cv = cond_vector.float()
         c = self.FromRGB.from_rgb
         f = F.leaky_relu(tc.lib_conv2d(x.float(), c.weight, c.bias), 0.2)                                      # :84-92

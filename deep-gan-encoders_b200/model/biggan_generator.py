@@ -30,6 +30,7 @@ from dge_b200 import ops
 from model.utils.biggan_config import BigGANConfig  # noqa: F401
 
 DEFAULT_PLANES = 2
+FUSED_TRAIN = True      # one fused autograd node per GenBlock (dge_b200/train_big.py); False: separate torch nodes
 
 
 def snconv2d(eps=1e-12, **kwargs):
@@ -202,6 +203,31 @@ class BigGANBatchNorm(nn.Module):
             return ops.cbn_coeffs(mean, var, self.eps, n, scale=s, offset=o)
         return ops.cbn_coeffs(mean, var, self.eps, n, weight=self.weight, bias=self.bias)
 
+    def coeffs_autograd(self, truncation, condition_vector, n, frozen=True):
+        """`coeffs` as differentiable torch ops -> (A, B) fp32 [n, c]: the path the gradient takes from a fused block node
+        back to the condition vector (frozen generator) or to the scale / offset layers (the BigGAN encoder)."""
+        mean, var = self.stats(truncation)
+        if self.conditional:
+            if frozen and not self.training:
+                if not hasattr(self, '_prep'):
+                    self._prep = _Prep()
+                ws, wo = self._prep.get(self, _sn_sources(self.scale) + _sn_sources(self.offset),
+                                        lambda: (sn_weight(self.scale).detach().clone(),
+                                                 sn_weight(self.offset).detach().clone()))
+            else:
+                keep = (lambda t: t.detach()) if frozen else (lambda t: t)
+                ws, wo = keep(sn_weight(self.scale)), keep(sn_weight(self.offset))
+            cv = condition_vector.float()
+            weight = 1 + F.linear(cv, ws)
+            bias = F.linear(cv, wo)
+        else:
+            keep = (lambda t: t.detach()) if frozen else (lambda t: t)
+            weight = keep(self.weight).unsqueeze(0).expand(n, -1)
+            bias = keep(self.bias).unsqueeze(0).expand(n, -1)
+        a = weight / torch.sqrt(var + self.eps)
+        b = bias - mean * a
+        return a.contiguous(), b.contiguous()
+
     def _forward_autograd(self, x, truncation, condition_vector=None, frozen=True):
         """:138-150 recorded for backward.  `frozen`: the layer's own parameters are constants (generator) or
         trainable (the BigGAN encoder re-uses this class, E_BIG.py:33-82)."""
@@ -245,10 +271,20 @@ class GenBlock(nn.Module):
         srcs = [t for c in convs for t in _sn_sources(c) + [c.bias]]
 
         def build():
-            return {'w': [ops.pack_conv_weight(sn_weight(c).detach(), planes=self.planes) for c in convs],
+            eff = [sn_weight(c).detach() for c in convs]
+            return {'w': [ops.pack_conv_weight(w, planes=self.planes) for w in eff], 'eff': eff,
                     'b': [c.bias.detach() for c in convs]}
 
         return self._prep.get(self, srcs, build)
+
+    def _prepared_k(self, kns):
+        """`_prepared` through the kernel namespace `kns` (dge_b200.ops, or the CPU tests' emulation: uncached)."""
+        if kns is ops:
+            return self._prepared()
+        convs = [self.conv_0, self.conv_1, self.conv_2, self.conv_3]
+        eff = [sn_weight(c).detach() for c in convs]
+        return {'w': [kns.pack_conv_weight(w, planes=self.planes) for w in eff], 'eff': eff,
+                'b': [c.bias.detach() for c in convs]}
 
     def run(self, x, cond_vector, truncation):
         """x: F32B -> F32B."""
@@ -314,8 +350,37 @@ class Generator(nn.Module):
         self.planes = DEFAULT_PLANES
         self._prep = _Prep()
 
+    def _frozen(self, layer):
+        """Effective (spectral-norm) weight of a frozen layer as a constant; cached in eval mode."""
+        if self.training:
+            return sn_weight(layer).detach()
+        cache = self.__dict__.setdefault('_frozen_cache', {})
+        key = ops.weight_key(*_sn_sources(layer))
+        hit = cache.get(id(layer))
+        if hit is None or hit[0] != key:
+            hit = (key, sn_weight(layer).detach().clone())
+            cache[id(layer)] = hit
+        return hit[1]
+
+    def _rgb_prepared_k(self, kns):
+        """Forward / data-gradient operands of conv_to_rgb: only channels [:3] of its output are kept (:253), so the
+        first 16 output channels are packed.  Cached in eval mode for the real kernel namespace."""
+        def build():
+            w = sn_weight(self.conv_to_rgb).detach()[:16].contiguous()
+            return {'w': kns.pack_conv_weight(w, planes=self.planes), 'wd': kns.pack_conv_weight_dgrad(w, planes=self.planes),
+                    'b': self.conv_to_rgb.bias.detach()[:16].contiguous()}
+
+        if kns is not ops:
+            return build()
+        if not hasattr(self, '_prep_rgb'):
+            self._prep_rgb = _Prep()
+        return self._prep_rgb.get(self, _sn_sources(self.conv_to_rgb) + [self.conv_to_rgb.bias], build)
+
     def _forward_autograd(self, cond_vector, truncation):
         """:232-256 recorded for backward w.r.t. the condition vector (frozen weights)."""
+        if FUSED_TRAIN:
+            from dge_b200 import train_big
+            return train_big.generator_forward(self, cond_vector, truncation)
         ch = self.config.channel_width
         x = F.linear(cond_vector, sn_weight(self.gen_z).detach(), self.gen_z.bias.detach())
         x = x.view(-1, 4, 4, 16 * ch).permute(0, 3, 1, 2).contiguous()

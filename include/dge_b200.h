@@ -344,6 +344,17 @@ int dge_in_bwd_apply(const float* g, const float* x, const float* mean_rstd, con
                      const double* sums, const float* gscale, int mode, const float* res, float rscale, int res_pool,
                      const float* noise, float slope, float* out_f32b, void* out_act, float* sums2, int n, int c, int h,
                      int w, int planes, void* stream);
+/* Conditional batch norm + (leaky) ReLU, backward: the frozen BigGAN generator under loss.backward()
+   (biggan_generator.py:138-150 with :178-190 -- t = relu(a*x + b) [-> nearest x2] -> conv; a, b fp32 [n][c] come from the
+   condition vector, so their gradients are what the encoder's z receives through every block norm).
+   g F32B [n][c/8][h*up][w*up][8]: gradient of the conv's input; x F32B [n][c/8][h][w][8]: the norm's input.
+     d = (a*x + b > 0 ? 1 : slope) * sum_{up x up} g;   sums fp32 [n][c][2] = (sum d*x, sum d) = (d a, d b)   (zeroed by the call)
+     dx = a*d, plus for channels < skip_c the sum over skip_up x skip_up of skip F32B [n][skip_c/8][h*skip_up][w*skip_up][8]
+          (GenBlock's identity branch :192-203: channel drop + nearest up-sampling; NULL: none)
+   -> out_f32b [n][c/8][h][w][8] and / or out_act [n][c/8][planes][h][w][8] (operand of the next data-gradient conv). */
+int dge_affine_relu_bwd(const float* g, const float* x, const float* a, const float* b, float slope, int up,
+                        const float* skip, int skip_c, int skip_up, float* out_f32b, void* out_act, float* sums, int n,
+                        int c, int h, int w, int planes, void* stream);
 /* FromRGB backward (net.py:231-240, f = lrelu(conv1x1(img, W) + b)): sums fp32 [c][4] = (dW[c][0..2], db[c]) with
    d_pre = d_f * (f > 0 ? 1 : slope); d_f, f F32B [n][c/8][h][w][8]; img NCHW [n][cimg<=3][h][w].
    d_img (optional, NCHW like img; zeroed by the call): the image gradient sum_c wgt[c][i] * d_pre[c] -- the inversion loop

@@ -142,7 +142,7 @@ def conv(x, wpk, cout, kind=CONV_3X3, *, demod=None, noise=None, noise_batched=F
          bias=None, slope=1.0, gain=1.0, blend_src=None, blend_pool=False, blend_a=0.0, blend_b=1.0, preact_add=None,
          preact_up=1, out_act=False, out_planes=None, out_scale=None, out_f32b=False, out_f32b_into=None,
          out_f32b_pool=False, out_nchw=False, rgb_w=None, rgb_out=None, checker=False, out_hw=None):
-    assert isinstance(x, Act) and isinstance(wpk, _Packed) and preact_add is None and out_f32b_into is None
+    assert isinstance(x, Act) and isinstance(wpk, _Packed) and out_f32b_into is None
     n, h, w_ = x.n, x.h, x.w
     wt = wpk.w
     if kind == CONV_UP3X3:
@@ -180,6 +180,11 @@ def conv(x, wpk, cout, kind=CONV_3X3, *, demod=None, noise=None, noise_batched=F
         y = y + nz * (noise_w.view(1, -1, 1, 1) if noise_w is not None else noise_scalar)
     if bias is not None:
         y = y + bias.view(1, -1, 1, 1)
+    if preact_add is not None:             # identity branch added before the activation (channel drop + nearest up)
+        sk = preact_add.to_nchw()[:, :cout]
+        if preact_up > 1:
+            sk = sk.repeat_interleave(preact_up, dim=2).repeat_interleave(preact_up, dim=3)
+        y = y + sk
     y = torch.where(y < 0, y * slope, y) * gain
     if blend_src is not None:
         s = blend_src.to_nchw()
@@ -301,6 +306,36 @@ def in_bwd_apply(g, x, mean_rstd, style, dstyle, sums, mode, res=None, rscale=0.
     nz = noise.view(n, 1, h, w) if noise is not None else torch.zeros(())
     return (Act.of(v, planes) if out_kind == "act" else F32B.of(v)), \
         torch.stack((v.sum(dim=(0, 2, 3)), (v * nz).sum(dim=(0, 2, 3))))
+
+
+def affine_act(x, a, b, relu=False, up=1, planes=2, out_act=True, out_f32b=False):
+    y = x.to_nchw() * a[:, :, None, None] + b[:, :, None, None]
+    if relu:
+        y = F.relu(y)
+    if up > 1:
+        y = y.repeat_interleave(up, dim=2).repeat_interleave(up, dim=3)
+    return (Act.of(y, planes) if out_act else None), (F32B.of(y) if out_f32b else None)
+
+
+def tanh_slice_nchw(x, nch):
+    return torch.tanh(x[:, :nch]).contiguous()
+
+
+def _sum_pool(t, k):
+    return t if k == 1 else F.avg_pool2d(t, k, k) * float(k * k)
+
+
+def affine_relu_bwd(g, x, a, b, slope=0.0, up=1, skip=None, skip_up=1, out_act=True, out_f32b=False, planes=2):
+    xv = x.to_nchw()
+    gs = _sum_pool(g.to_nchw(), up)
+    pre = xv * a[:, :, None, None] + b[:, :, None, None]
+    d = torch.where(pre > 0, gs, gs * slope)
+    sums = torch.stack(((d * xv).sum(dim=(2, 3)), d.sum(dim=(2, 3))), dim=2).contiguous()
+    v = d * a[:, :, None, None]
+    if skip is not None:
+        v = v.clone()
+        v[:, :skip.c] += _sum_pool(skip.to_nchw(), skip_up)
+    return (Act.of(v, planes) if out_act else None), (F32B.of(v) if out_f32b else None), sums
 
 
 def from_rgb_bwd(d_f, f, img, slope=0.2, weight=None):

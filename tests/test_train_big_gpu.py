@@ -1,0 +1,138 @@
+"""The fused training path of the BigGAN pair on the B200 (dge_b200/train_big.py + k_affine_relu_bwd): (1) the new backward
+kernel against tests/emu_ops.py; (2) fused nodes against the graph of separate torch nodes at working sizes (E_BIG(64, 7) at
+256^2, BigGAN-deep at channel_width 64); the reference's own gradients of both networks are held by
+tests/test_train_families_gpu.py, which runs through the fused nodes too (FUSED_TRAIN is the default).
+Criteria: L2-relative per tensor (a ReLU / leaky-ReLU unit within rounding of zero may take the other slope in the two
+arithmetic orders: tests/test_train_gpu.py header)."""
+import pytest
+import torch
+
+import emu_ops as emu
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-20)).item()
+
+
+def l2rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("n,c,h,w,up,skip_c,skip_up,slope", [
+    (2, 16, 8, 12, 1, 0, 1, 0.0), (2, 32, 9, 7, 2, 16, 2, 0.0), (1, 64, 32, 32, 1, 64, 1, 0.0),
+    (3, 48, 16, 20, 2, 0, 1, 0.2), (2, 128, 4, 4, 1, 64, 2, 0.0)])
+def test_affine_relu_bwd_kernel(n, c, h, w, up, skip_c, skip_up, slope):
+    from dge_b200 import ops
+    g = torch.Generator().manual_seed(7 * h + w + c)
+    x = torch.randn(n, c, h, w, generator=g)
+    gr = torch.randn(n, c, h * up, w * up, generator=g)
+    a = torch.randn(n, c, generator=g) * 0.5 + 1.0
+    b = torch.randn(n, c, generator=g) * 0.3
+    skip = torch.randn(n, skip_c, h * skip_up, w * skip_up, generator=g) if skip_c else None
+    act, f, sums = ops.affine_relu_bwd(ops.nchw_to_f32b(gr.cuda()), ops.nchw_to_f32b(x.cuda()), a.cuda(), b.cuda(), slope, up,
+                                       ops.nchw_to_f32b(skip.cuda()) if skip_c else None, skip_up, out_act=True,
+                                       out_f32b=True)
+    e_act, e_f, e_sums = emu.affine_relu_bwd(emu.F32B.of(gr), emu.F32B.of(x), a, b, slope, up,
+                                             emu.F32B.of(skip) if skip_c else None, skip_up, out_act=True, out_f32b=True)
+    # (fma vs mul + add in a*x + b: a unit exactly at the threshold is not in these seeds)
+    assert rel(f.to_nchw(), e_f.to_nchw()) < 1e-6
+    assert rel(act.to_nchw(), e_act.to_nchw()) < 2e-5          # hi + lo bf16 planes: ~2^-17 of each value
+    scale = e_f.to_nchw().abs().sum(dim=(2, 3)).max()
+    assert ((sums.cpu() - e_sums).abs().max() / scale).item() < 1e-5
+
+
+def _perturb(m, seed):
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.abs().max() == 0:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+
+
+def test_fused_e_big_vs_unfused_graph_at_256():
+    """E_BIG(64, 7) at 256^2 (configs[3]'s encoder), batch 2: features, heads and every parameter gradient."""
+    import model.E.E_BIG as EG
+    torch.manual_seed(0)
+    E = EG.BE(64, 512, 7, 512, 3, biggan=True)
+    _perturb(E, 3)
+    E = E.cuda()
+    E.set_noise_mode("device")
+    g = torch.Generator().manual_seed(5)
+    img = torch.randn(2, 3, 256, 256, generator=g).cuda()
+    cond = (torch.randn(2, 256, generator=g) * 0.5).cuda()
+
+    def run(fused):
+        E.zero_grad()
+        # train mode runs a spectral-norm power iteration per forward: same starting u / v for both runs
+        sd = {k: v.clone() for k, v in E.state_dict().items()}
+        torch.manual_seed(11)
+        old = EG.FUSED_TRAIN
+        EG.FUSED_TRAIN = fused
+        try:
+            c_v, z = E(img, cond)
+        finally:
+            EG.FUSED_TRAIN = old
+        ((c_v ** 2).mean() + (z ** 2).mean()).backward()
+        grads = {k: p.grad.clone() for k, p in E.named_parameters() if p.grad is not None}
+        E.load_state_dict(sd)
+        return c_v.detach(), z.detach(), grads
+
+    cu, zu, gu = run(False)
+    cf, zf, gf = run(True)
+    assert rel(cf, cu) < 1e-3 and rel(zf, zu) < 1e-3
+    assert set(gf) == set(gu) and len(gu) > 60
+    bad = {k: l2rel(gf[k], gu[k]) for k in gu if l2rel(gf[k], gu[k]) >= 3e-3}
+    assert not bad, bad
+
+
+def test_fused_biggan_vs_unfused_graph():
+    """BigGAN-deep-128-shaped generator at channel_width 64 (attention at 32^2), batch 2: image and d image / d z."""
+    import model.biggan_generator as BG
+    from model.utils.biggan_config import BigGANConfig
+    cfg = {"attention_layer_position": 4, "channel_width": 64, "class_embed_dim": 128, "eps": 0.0001,
+           "layers": [[False, 16, 16], [True, 16, 8], [False, 8, 8], [True, 8, 4], [False, 4, 4], [True, 4, 2],
+                      [False, 2, 2], [True, 2, 1]],
+           "n_stats": 51, "num_classes": 100, "output_dim": 64, "z_dim": 128}
+    torch.manual_seed(0)
+    G = BG.BigGAN(BigGANConfig.from_dict(cfg)).eval()
+    with torch.no_grad():
+        G.generator.bn.weight.fill_(1.0)
+        G.generator.bn.bias.zero_()
+        for m in G.modules():                      # converge the spectral-norm vectors (random u / v give huge weights)
+            if hasattr(m, "weight_u"):
+                for _ in range(20):
+                    m.train()
+                    BG.sn_weight(m)
+                m.eval()
+        for m in G.modules():
+            if isinstance(m, BG.SelfAttn):
+                m.gamma.fill_(0.3)
+    G = G.cuda().eval()
+    z0 = (torch.randn(2, 128, generator=torch.Generator().manual_seed(2)).clamp_(-2, 2) * 0.4).cuda()
+    label = torch.zeros(2, 100).cuda()
+    label[:, 7] = 1
+    target = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(4)).cuda()
+
+    def run(fused):
+        old = BG.FUSED_TRAIN
+        BG.FUSED_TRAIN = fused
+        try:
+            z = z0.clone().requires_grad_(True)
+            out, _ = G(z, label, 0.4)
+        finally:
+            BG.FUSED_TRAIN = old
+        ((out - target) ** 2).mean().backward()
+        return out.detach(), z.grad.clone()
+
+    ou, gu = run(False)
+    of, gf = run(True)
+    with torch.no_grad():
+        oi, _ = G(z0, label, 0.4)
+    assert rel(of, oi) < 1e-5                      # the node's forward IS the inference chain
+    assert rel(of, ou) < 1e-3
+    assert l2rel(gf, gu) < 3e-3, l2rel(gf, gu)
+    assert all(p.grad is None for p in G.parameters())

@@ -170,3 +170,90 @@ def test_fused_stylegan1_generator_matches_reference_gradients(monkeypatch):
         ((out - target) ** 2).mean().backward()
         assert rel(styles.grad, ref["sg1_dstyles"][lod]) < 1e-3, lod
     assert all(p.grad is None for p in Gs.parameters())
+
+
+@pytest.fixture()
+def emu_big(monkeypatch):
+    from dge_b200 import train_big, train_e
+    monkeypatch.setattr(train_e, "K", emu_ops)
+    monkeypatch.setattr(train_big, "K", emu_ops)
+    return emu_ops
+
+
+def test_fused_biggan_generator_matches_reference_gradient(emu_big):
+    """dge_b200/train_big.py: d image / d z of the fused GenBlock / RGB-tail nodes (emulated kernels) against the reference's
+    own backward (train_grads.pt: biggan_dz), both truncations of the fixture (0.37 interpolates the statistics)."""
+    import model.biggan_generator as BG
+    from model.utils.biggan_config import BigGANConfig
+    assert BG.FUSED_TRAIN
+    fx = torch.load(os.path.join(GOLD, "biggan_small.pt"))
+    ref = torch.load(os.path.join(GOLD, "train_grads.pt"))
+    G = BG.BigGAN(BigGANConfig.from_dict(fx["config"]))
+    G.load_state_dict(fx["state_dict"], strict=True)
+    G.eval()
+    conv = lambda x, w_, planes=2: torch.nn.functional.conv2d(x, w_, padding=w_.shape[-1] // 2)
+    orig = BG.tc.conv2d
+    BG.tc.conv2d = conv                      # the attention block between the fused nodes stays a torch graph
+    try:
+        for trunc, img in fx["images"].items():
+            z = fx["z"].clone().requires_grad_(True)
+            out, _ = G(_cuda_like(z), fx["label"], trunc)
+            assert rel(out, img) < 3e-4, trunc
+            target = torch.randn(out.shape, generator=torch.Generator().manual_seed(4))
+            ((out - target) ** 2).mean().backward()
+            assert rel(z.grad, ref["biggan_dz"][trunc]) < 1e-3, trunc
+    finally:
+        BG.tc.conv2d = orig
+    assert all(p.grad is None for p in G.parameters())
+
+
+def _cuda_like(t):
+    """BigGAN.forward refuses CPU tensors on the training path (no CPU fallback in the product); the emulated-kernel tests
+    present a CPU tensor that answers `is_cuda`."""
+    class _T(torch.Tensor):
+        @property
+        def is_cuda(self):
+            return True
+    return t.as_subclass(_T)
+
+
+def test_fused_e_big_matches_unfused_graph_and_reference(emu_big):
+    """E_BIG blocks as fused nodes (emulated kernels): features and every parameter gradient against the graph of separate
+    torch nodes with ATen convs, and against the pins of the reference's own backward (train_grads.pt: e_big)."""
+    import torch.nn.functional as F
+    import model.E.E_BIG as EG
+    from test_train_host_cpu import _check_pin
+    fx = torch.load(os.path.join(GOLD, "e_big_s16_l4.pt"))
+    ref = torch.load(os.path.join(GOLD, "train_grads.pt"))
+    E = EG.BE(**fx["config"])
+    E.load_state_dict(fx["state_dict"], strict=True)
+    E.eval()
+
+    def run(fused):
+        E.zero_grad()
+        torch.manual_seed(13)
+        old = EG.FUSED_TRAIN
+        EG.FUSED_TRAIN = fused
+        try:
+            f = E._features_autograd(fx["img"], fx["cond"])
+        finally:
+            EG.FUSED_TRAIN = old
+        (f ** 2).mean().backward()
+        return f.detach(), {k: p.grad.clone() for k, p in E.named_parameters() if p.grad is not None}
+
+    conv = lambda x, w_, planes=2: F.conv2d(x, w_, padding=w_.shape[-1] // 2)
+    lib = lambda x, w_, b=None, padding=0: F.conv2d(x, w_, b, padding=padding)
+    o1, o2 = EG.tc.conv2d, EG.tc.lib_conv2d
+    EG.tc.conv2d, EG.tc.lib_conv2d = conv, lib
+    try:
+        f_u, g_u = run(False)
+    finally:
+        EG.tc.conv2d, EG.tc.lib_conv2d = o1, o2
+    f_f, g_f = run(True)
+    assert rel(f_f, fx["features_seed13"]) < 2e-4 and rel(f_u, fx["features_seed13"]) < 2e-4
+    assert set(g_f) == set(g_u) == set(ref["e_big"])
+    worst = {k: rel(g_f[k], g_u[k]) for k in g_u}
+    bad = {k: v for k, v in worst.items() if v >= 1e-3}
+    assert not bad, bad
+    for k, pin in ref["e_big"].items():
+        _check_pin(g_f[k], pin, 1e-3, k)

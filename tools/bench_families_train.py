@@ -155,6 +155,13 @@ if only in ("both", "biggan"):
         imgs2, _ = Gb(w2, label, 0.4)
         losses_and_steps(opt, lp, imgs1, imgs2, zb, w2)
     ms = timeit(big_iter, 2, 3)
+    if os.environ.get("DGE_KPROF"):             # where the iteration's GPU time goes (kernel table to stderr)
+        with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CPU,
+                                                torch.profiler.ProfilerActivity.CUDA]) as kp:
+            big_iter()
+            torch.cuda.synchronize()
+        print(kp.key_averages().table(sort_by="self_cuda_time_total", row_limit=60, max_name_column_width=90),
+              file=sys.stderr)
     out["biggan_deep_256_bs32_train"] = {"ms_per_iteration": ms, "images_per_s": bs / (ms / 1e3),
                                          "peak_gib": torch.cuda.max_memory_allocated() / 2 ** 30}
 print(json.dumps(out))

@@ -137,10 +137,21 @@ def main():
         import cProfile
         prof = cProfile.Profile()
         prof.enable()
+    kprof = None
+    if os.environ.get("DGE_GPUTIME"):           # how much of the wall time the GPU is busy (sum of kernel times, to stderr)
+        kprof = torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA])
+        kprof.__enter__()
     t0 = time.perf_counter()
     mses = [one_image(i, a.iterations) for i in range(a.images)]
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
+    if kprof is not None:
+        kprof.__exit__(None, None, None)
+        busy = sum(e.self_device_time_total for e in kprof.key_averages()) / 1e3
+        print(f"GPU busy {busy / (a.images * a.iterations):.2f} ms / iteration of {wall / (a.images * a.iterations) * 1e3:.2f} ms wall "
+              f"(under the profiler)", file=sys.stderr)
+        print(kprof.key_averages().table(sort_by="self_cuda_time_total", row_limit=30, max_name_column_width=70),
+              file=sys.stderr)
     if prof is not None:
         import io
         import pstats

@@ -15,7 +15,7 @@ torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 planes = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-N = 8
+N = int(os.environ.get("PROBE_N", "8"))
 # (cin, cout, size, ksize): conv_1 / conv_2 of every BEBlock (model/E/E.py:27-36), 1024 -> 4
 shapes = []
 c, size = 16, 1024
