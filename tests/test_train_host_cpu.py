@@ -49,6 +49,9 @@ def aten_conv(monkeypatch):
     import model.biggan_generator as BG
     monkeypatch.setattr(EG.tc, "conv2d", conv)
     monkeypatch.setattr(BG.tc, "conv2d", conv)
+    # these tests hold the graphs of separate torch nodes (the cross-check of the fused nodes, tests/test_train_fused_cpu.py)
+    monkeypatch.setattr(EG, "FUSED_TRAIN", False)
+    monkeypatch.setattr(BG, "FUSED_TRAIN", False)
     monkeypatch.setattr(EB.tc, "conv2d", conv)
     monkeypatch.setattr(EM.tc, "conv2d", conv)
     monkeypatch.setattr(SG.tc, "conv2d", conv)
