@@ -48,6 +48,75 @@ def _f32b(t):
     return K.F32B.wrap(t, n, c8 * 8, h, w)
 
 
+# ---- case-2 encoder (model/E/E_Blur.py): the stride-2 `transform_kernel` conv in space-to-depth form -----------------
+def _k4(w):
+    """lreq.py:144-147: the 4x4 stride-2 kernel = 0.25 * (sum of the four 1-pixel shifts of the zero-padded 3x3 kernel)."""
+    k = torch.nn.functional.pad(w, (1, 1, 1, 1))
+    return (k[:, :, 1:, 1:] + k[:, :, :-1, 1:] + k[:, :, 1:, :-1] + k[:, :, :-1, :-1]) * 0.25
+
+
+_TAP_TO_S2D = ((0, 1), (1, 0), (1, 1), (2, 0))     # 4x4 tap a reads row 2Y + a - 1 = 2(Y + d) + p  ->  (d + 1, p)
+
+
+_s2d_index_cache = {}
+
+
+def _s2d_index(device):
+    """Index arrays [4, 4] (phase_y, phase_x, tap_y, tap_x) of the 16 slabs the 4x4 kernel occupies in [2][2][C][3][3]."""
+    hit = _s2d_index_cache.get(device)
+    if hit is None:
+        d = torch.tensor([t[0] for t in _TAP_TO_S2D], device=device)
+        p = torch.tensor([t[1] for t in _TAP_TO_S2D], device=device)
+        hit = tuple(t.contiguous() for t in (p[:, None].expand(4, 4), p[None, :].expand(4, 4), d[:, None].expand(4, 4),
+                                             d[None, :].expand(4, 4)))
+        _s2d_index_cache[device] = hit
+    return hit
+
+
+def _w_s2d(w):
+    """The same conv over the space-to-depth map (channel (2*py + px)*C + i holds x[2Y+py][2X+px]): a stride-1 3x3 conv
+    [Cout][4C][3][3] with 16 of its 36 (tap, phase) slabs non-zero."""
+    k4 = _k4(w)
+    co, c = k4.shape[:2]
+    ws = k4.new_zeros((co, 2, 2, c, 3, 3))
+    py, px, dy, dx = _s2d_index(w.device)
+    ws[:, py, px, :, dy, dx] = k4.permute(2, 3, 0, 1)          # (advanced indices split by a slice: result dims lead)
+    return ws.reshape(co, 4 * c, 3, 3)
+
+
+def _dw3_from_s2d(dws, c):
+    """Transpose of `_w_s2d`: gradient of the 3x3 `transform_kernel` parameter from the gradient of the 3x3 conv over the
+    space-to-depth operand (gather the 16 slabs -> d K4; each 3x3 weight feeds the four 4x4 taps it was shifted onto)."""
+    co = dws.shape[0]
+    py, px, dy, dx = _s2d_index(dws.device)
+    dk4 = dws.view(co, 2, 2, c, 3, 3)[:, py, px, :, dy, dx].permute(2, 3, 0, 1)        # [co][c][4][4]
+    return (dk4[:, :, :3, :3] + dk4[:, :, 1:, :3] + dk4[:, :, :3, 1:] + dk4[:, :, 1:, 1:]) * 0.25
+
+
+def _packed_strided(w, planes, dgrad):
+    """Forward (16-tap DOWN4X4S2) / data-gradient (3x3 over space-to-depth) operands of a `transform_kernel` conv, cached
+    on the parameter like `_packed`."""
+    cache = w.__dict__.setdefault('_dge_packed', {})
+    slot = (planes, 's2d-dgrad' if dgrad else 'down4', K is ops)
+    key = K.weight_key(w)
+    hit = cache.get(slot)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    wd = w.detach()
+    op = K.pack_conv_weight_dgrad(_w_s2d(wd).contiguous(), planes=planes) if dgrad else \
+        K.pack_conv_weight(_k4(wd).contiguous(), planes=planes)
+    cache[slot] = (key, op)
+    return op
+
+
+def _depth_to_space(g):
+    """F32B [N][4C/8][H/2][W/2][8] with channel (2*py + px)*C + i  ->  F32B [N][C/8][H][W][8]."""
+    n, c4, h2, w2 = g.n, g.c, g.h, g.w
+    c = c4 // 4
+    t = g.t.view(n, 2, 2, c // 8, h2, w2, 8).permute(0, 3, 4, 1, 5, 2, 6).reshape(n, c // 8, 2 * h2, 2 * w2, 8)
+    return K.F32B.wrap(t.contiguous(), n, c, 2 * h2, 2 * w2)
+
+
 class _FromRGBFn(torch.autograd.Function):
     """img NCHW -> (f F32B tensor, style0, mean_rstd0): net.py:231-240 + the first block's statistics (E.py:51-53)."""
 
@@ -79,7 +148,8 @@ class _BEBlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x_t, pre_style, pre_mr, w1, w2, w3, b3, nw1, b1, nw2, b2, cfg):
-        has_last, planes, eps1, eps2, noise1, noise2 = cfg
+        has_last, planes, eps1, eps2, noise1, noise2 = cfg[:6]
+        blur = cfg[6] if len(cfg) > 6 else None        # E_Blur: 'strided' (transform_kernel conv_2) / 'plain' / None (E.py)
         x = _f32b(x_t)
         n, c, h, w = x.n, x.c, x.h, x.w
         cout = w2.shape[0] if has_last else (w3.shape[0] if w3 is not None else c)
@@ -97,16 +167,25 @@ class _BEBlockFn(torch.autograd.Function):
         style2, mr2 = K.instance_stats(y1, eps2)                                               # :64-66
         y2 = None
         if has_last:
-            y1n, _ = K.instance_norm(y1, mr2, planes=planes)                                   # :69
-            # training keeps the full-resolution activated conv_2 output: its sign is the leaky-ReLU mask of the backward
-            y2 = K.conv(y1n, _packed(w2, planes), cout, K.CONV_3X3, noise=noise2, noise_batched=True,
-                        noise_w=nw2.detach().reshape(-1), bias=b2.detach().reshape(-1), slope=SLOPE,
-                        out_f32b=True)['f32b']                                                  # :72-75
+            if blur:
+                y1n = K.instance_norm_blur(y1, mr2, s2d=blur == 'strided', planes=planes)      # E_Blur.py:69-71
+            else:
+                y1n, _ = K.instance_norm(y1, mr2, planes=planes)                               # :69
+            # training keeps the activated conv_2 output before the pool / blend: its sign is the leaky-ReLU mask
+            if blur == 'strided':                                                              # E_Blur.py:72 (half size)
+                y2 = K.conv(y1n, _packed_strided(w2, planes, False), cout, K.CONV_DOWN4X4S2, noise=noise2,
+                            noise_batched=True, noise_w=nw2.detach().reshape(-1), bias=b2.detach().reshape(-1),
+                            slope=SLOPE, out_f32b=True)['f32b']
+            else:
+                y2 = K.conv(y1n, _packed(w2, planes), cout, K.CONV_3X3, noise=noise2, noise_batched=True,
+                            noise_w=nw2.detach().reshape(-1), bias=b2.detach().reshape(-1), slope=SLOPE,
+                            out_f32b=True)['f32b']                                              # :72-75
+            y2_pool = blur != 'strided'
             if w3 is not None:
                 out = K.conv(rp, _packed(w3, planes), cout, K.CONV_1X1, bias=b3.detach(),
-                             blend_src=y2, blend_pool=True, blend_a=GA, blend_b=GB, out_f32b=True)['f32b']   # :76-84
+                             blend_src=y2, blend_pool=y2_pool, blend_a=GA, blend_b=GB, out_f32b=True)['f32b']   # :76-84
             else:
-                out = K.blend(y2, x, GA, GB, pool=3)
+                out = K.blend(y2, x, GA, GB, pool=3 if y2_pool else 2)
         else:
             y1n = None
             _, y1n_f = K.instance_norm(y1, mr2, out_act=False, out_f32b=True)                  # :69
@@ -117,6 +196,7 @@ class _BEBlockFn(torch.autograd.Function):
             else:
                 out = K.blend(y1n_f, x, GA, GB, pool=False)
         ctx.cfg = (has_last, planes, (n, c, h, w), cout)
+        ctx.blur = blur
         ctx.has = (w3 is not None, y1n is not None, rp is not None, y2 is not None)
         saved = [x_t, mr1, style1, xn.t, y1.t, mr2, style2, noise1, w1]
         if has_last:
@@ -144,7 +224,26 @@ class _BEBlockFn(torch.autograd.Function):
         xn = K.Act.wrap(xn_t, n, c, h, w, planes)
         d_out = _f32b(d_out_t.contiguous())
         dw2 = dnw2 = db2 = dw3 = db3 = None
-        if has_last:
+        blur = ctx.blur
+        if has_last and blur == 'strided':
+            # conv_2 ran at stride 2: y2 and d_out share a size, so the head is a scaled leaky-ReLU mask (no pool) ...
+            y2 = _f32b(y2_t)
+            ga_tab = torch.tensor([0.0, GA], device=mr2.device).expand(n, cout, 2).contiguous()   # (mean, rstd) = (0, GA)
+            zeros = torch.zeros((n, cout, 2), dtype=torch.float64, device=mr2.device)
+            dy2, s = K.in_bwd_apply(d_out, y2, ga_tab, None, None, zeros, 1, noise=noise2, slope=SLOPE, planes=planes)
+            db2, dnw2 = s[0].view(1, -1, 1, 1), s[1].view(1, -1, 1, 1)
+            dres = None
+            if has_w3:
+                dres = K.scale_f32b(d_out, GB, to_act=True, planes=planes)
+                db3 = GB * K.f32b_channel_sums(d_out)
+            # ... and its gradients are those of a 3x3 conv over the space-to-depth operand the forward kept
+            xs = K.Act.wrap(y1n_t, n, 4 * c, h // 2, w // 2, planes)
+            dws = K.conv_wgrad(dy2, xs, 3)
+            dw2 = _dw3_from_s2d(dws, c)
+            g1 = _depth_to_space(K.conv(dy2, _packed_strided(w2, planes, True), 4 * c, K.CONV_3X3, out_f32b=True)['f32b'])
+            del dy2
+            g1 = K.sg1_post(g1, 0, n, c, h, w, slope=1.0)                                     # blur^T = blur (:71)
+        elif has_last:
             y2 = _f32b(y2_t)
             dy2, dres, s = K.be_head_bwd(d_out, y2, noise2, GA, GB, SLOPE, want_dres=has_w3, planes=planes)
             db2, dnw2 = s[0].view(1, -1, 1, 1), s[1].view(1, -1, 1, 1)
@@ -153,6 +252,8 @@ class _BEBlockFn(torch.autograd.Function):
             dw2 = K.conv_wgrad(dy2, K.Act.wrap(y1n_t, n, c, h, w, planes), 3)
             g1 = K.conv(dy2, _packed(w2, planes, True), c, K.CONV_3X3, out_f32b=True)['f32b']
             del dy2
+            if blur:
+                g1 = K.sg1_post(g1, 0, n, c, h, w, slope=1.0)                                 # blur^T = blur (E_Blur.py:71)
         else:
             g1 = K.scale_f32b(d_out, GA)                       # out = GA * IN_2(y1) + GB * residual  (E.py:69,84)
             dres = None
@@ -215,13 +316,20 @@ def block_forward(block, x_t, pre=None):
     n, _, h, w, _ = x_t.shape
     dev = x_t.device
     noise1 = block._noise(n, h, w, dev).reshape(n, h, w).contiguous()                          # E.py:60 (RNG order kept)
-    noise2 = block._noise(n, h, w, dev).reshape(n, h, w).contiguous() if block.has_last_conv else None   # :73
+    noise2 = None
     has_w3 = block.inputs != block.outputs
     if has_w3 and not block.has_last_conv:
         # E.py:84 adds the `inputs`-channel features to the `outputs`-channel residual: the reference fails here too
         raise RuntimeError(f'BEBlock without a last conv needs inputs == outputs (got {block.inputs}, {block.outputs}): '
                            'choose start_features so that the last block runs at maxf (16 -> 1024, 32 -> 512, 64 -> 256)')
-    cfg = (block.has_last_conv, block.planes, block.instance_norm_1.eps, block.instance_norm_2.eps, noise1, noise2)
+    blur = None
+    if hasattr(block, 'blur') and block.has_last_conv:                                         # model/E/E_Blur.py
+        blur = 'strided' if block.fused_scale else 'plain'
+    if blur == 'strided':                                                                      # E_Blur.py:73: half-size noise
+        noise2 = block._noise(n, h // 2, w // 2, dev).reshape(n, h // 2, w // 2).contiguous()
+    elif block.has_last_conv:
+        noise2 = block._noise(n, h, w, dev).reshape(n, h, w).contiguous()                      # :73
+    cfg = (block.has_last_conv, block.planes, block.instance_norm_1.eps, block.instance_norm_2.eps, noise1, noise2, blur)
     pre_style, pre_mr = pre if pre is not None else (None, None)
     out_t, style1, style2 = _BEBlockFn.apply(
         x_t, pre_style, pre_mr, block.conv_1.weight, block.conv_2.weight if block.has_last_conv else None,

@@ -155,7 +155,7 @@ class BE(nn.Module):
         return f.to_nchw()
 
     def _features_autograd(self, x, cond_vector, block_num=9):
-        if FUSED_TRAIN:
+        if FUSED_TRAIN and self.startf % 16 == 0:
             from dge_b200 import train_big
             return train_big.ebig_features(self, x, cond_vector, block_num)
         cv = cond_vector.float()

@@ -23,6 +23,7 @@ from dge_b200 import autograd as tc
 from dge_b200 import ops
 
 DEFAULT_PLANES = 2
+FUSED_TRAIN = True      # one fused autograd node per block (dge_b200/train_e.py); False: separate torch nodes
 
 
 class BEBlock(nn.Module):
@@ -175,6 +176,13 @@ class BE(nn.Module):
 
     def forward(self, x, block_num=9):
         if _wants_grad(self, x):
+            if FUSED_TRAIN and self.startf % 16 == 0:
+                if not x.is_cuda:
+                    raise ops.DgeError('E_Blur.BE: dge_b200 runs on a B200 only; there is no CPU fallback')
+                if not self.FromRGB.from_rgb.implicit_lreq:
+                    raise NotImplementedError('training path: explicit lreq scaling is not used by the reference')
+                from dge_b200 import train_e
+                return train_e.encoder_forward(self, x, block_num)
             return self._forward_autograd(x.float(), block_num)
         ln._guard('E_Blur.BE', x, self.FromRGB.from_rgb.weight)
         f = self.FromRGB.run(x)

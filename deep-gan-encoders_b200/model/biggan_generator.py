@@ -378,7 +378,9 @@ class Generator(nn.Module):
 
     def _forward_autograd(self, cond_vector, truncation):
         """:232-256 recorded for backward w.r.t. the condition vector (frozen weights)."""
-        if FUSED_TRAIN:
+        # (the fused nodes keep every map in the 16-channel-blocked layouts; narrower toy widths take the torch graph below)
+        if FUSED_TRAIN and all(s % 16 == 0 for l in self.layers if isinstance(l, GenBlock)
+                               for s in (l.in_size, l.out_size, l.middle_size)):
             from dge_b200 import train_big
             return train_big.generator_forward(self, cond_vector, truncation)
         ch = self.config.channel_width

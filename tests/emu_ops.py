@@ -245,6 +245,14 @@ def instance_norm_pool(x, mean_rstd, planes=2):
     return Act.of(_in_apply(x, mean_rstd), planes), Act.of(F.avg_pool2d(x.to_nchw(), 2, 2), planes)
 
 
+def instance_norm_blur(x, mean_rstd, s2d=False, planes=2):
+    y = _blur3(_in_apply(x, mean_rstd))
+    if s2d:                                # channel (2*py + px)*C + i holds y[2Y+py][2X+px]
+        n, c, h, w = y.shape
+        y = y.view(n, c, h // 2, 2, w // 2, 2).permute(0, 3, 5, 1, 2, 4).reshape(n, 4 * c, h // 2, w // 2)
+    return Act.of(y, planes)
+
+
 def from_rgb_stats_any(img, w, b, slope=0.2, eps=1e-8):
     f = F.leaky_relu(F.conv2d(img.float(), w.detach().float(), None if b is None else b.detach().float()), slope)
     fb = F32B.of(f)

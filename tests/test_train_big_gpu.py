@@ -136,3 +136,47 @@ def test_fused_biggan_vs_unfused_graph():
     assert rel(of, ou) < 1e-3
     assert l2rel(gf, gu) < 3e-3, l2rel(gf, gu)
     assert all(p.grad is None for p in G.parameters())
+
+
+@pytest.mark.parametrize("cfg,size", [((64, 512, 7), 256), ((16, 64, 5), 64)])
+def test_fused_e_blur_vs_unfused_graph(cfg, size):
+    """model/E/E_Blur.py (embedding_img.py's encoder) through the fused block nodes of dge_b200/train_e.py -- blur, stride-2
+    `transform_kernel` conv_2 on the first four blocks, plain conv + pool below -- against the graph of separate torch
+    nodes (cuDNN for the blur / strided conv), incl. retain_graph + second backward and the image gradient."""
+    import model.E.E_Blur as EB
+    startf, maxf, layers = cfg
+    torch.manual_seed(1)
+    E = EB.BE(startf, maxf, layers, 512, 3).cuda()
+    with torch.no_grad():
+        for k, p in E.named_parameters():
+            if k.endswith(("bias", "noise_weight_1", "noise_weight_2", "bias_1", "bias_2")):
+                p.copy_(torch.randn_like(p) * 0.1)
+    E.set_noise_mode("device")
+    img = torch.randn(2, 3, size, size, device="cuda")
+    res = {}
+    for fused in (True, False):
+        EB.FUSED_TRAIN = fused
+        try:
+            x = img.clone().requires_grad_(True)
+            E.zero_grad()
+            torch.manual_seed(9)
+            const, w = E(x)
+            (const ** 2).mean().backward(retain_graph=True)
+            ga = {k: p.grad.clone() for k, p in E.named_parameters() if p.grad is not None}
+            gx = x.grad.clone()
+            E.zero_grad()
+            (w ** 2).mean().backward()
+            gb = {k: p.grad.clone() for k, p in E.named_parameters() if p.grad is not None}
+            res[fused] = (const.detach(), w.detach(), ga, gx, gb)
+        finally:
+            EB.FUSED_TRAIN = True
+    f, u = res[True], res[False]
+    assert rel(f[0], u[0]) < 2e-4 and rel(f[1], u[1]) < 2e-4
+    assert l2rel(f[3], u[3]) < 3e-3
+    for a, b in ((f[2], u[2]), (f[4], u[4])):
+        assert set(a) == set(b)
+        for k in b:
+            vec = b[k].dim() == 1 or (b[k].dim() == 4 and b[k].shape[0] == 1)
+            assert vec or l2rel(a[k], b[k]) < 3e-3, k
+            # (per-channel sums of a few thousand sign-alternating terms: one flipped unit moves them by percents)
+            assert rel(a[k], b[k]) < (6e-2 if vec else 3e-2), k

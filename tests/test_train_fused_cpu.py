@@ -257,3 +257,59 @@ def test_fused_e_big_matches_unfused_graph_and_reference(emu_big):
     assert not bad, bad
     for k, pin in ref["e_big"].items():
         _check_pin(g_f[k], pin, 1e-3, k)
+
+
+def test_fused_e_blur_matches_unfused_graph_and_reference(emu):
+    """model/E/E_Blur.py (the encoder embedding_img.py uses) through the fused block nodes (emulated kernels): blur, the
+    stride-2 `transform_kernel` conv as a 3x3 conv over the space-to-depth operand, its weight gradient mapped back to the
+    3x3 parameter -- against the graph of separate torch nodes with ATen convs, the reference's pins (train_grads.pt:
+    e_blur) and, element by element at 1e-3, the margin fixture of the reference's own backward."""
+    import torch.nn.functional as F
+    import model.E.E_Blur as EB
+    from dge_b200 import train_e
+    from test_train_host_cpu import _check_pin
+    fx = torch.load(os.path.join(GOLD, "e_blur_s16_l6.pt"))
+    ref = torch.load(os.path.join(GOLD, "train_grads.pt"))
+    E = EB.BE(**fx["config"])
+    E.load_state_dict(fx["state_dict"], strict=True)
+    assert any(b.fused_scale for b in E.decode_block) and not all(b.fused_scale for b in E.decode_block)
+
+    def run(fused):
+        E.zero_grad()
+        torch.manual_seed(fx["noise_seed"])
+        const, w = train_e.encoder_forward(E, fx["img"], 9) if fused else E._forward_autograd(fx["img"], 9)
+        (const.sum() + (w ** 2).mean()).backward()
+        return const.detach(), w.detach(), {k: p.grad.clone() for k, p in E.named_parameters() if p.grad is not None}
+
+    conv = lambda x, w_, planes=2: F.conv2d(x, w_, padding=w_.shape[-1] // 2)
+    lib = lambda x, w_, b=None, stride=1, padding=0, groups=1: F.conv2d(x, w_, b, stride=stride, padding=padding, groups=groups)
+    o1, o2 = EB.tc.conv2d, EB.tc.lib_conv2d
+    EB.tc.conv2d, EB.tc.lib_conv2d = conv, lib
+    try:
+        cu, wu, gu = run(False)
+    finally:
+        EB.tc.conv2d, EB.tc.lib_conv2d = o1, o2
+    cf, wf, gf = run(True)
+    assert rel(cf, fx["const"]) < 2e-4 and rel(wf, fx["w"]) < 2e-4
+    assert set(gf) == set(gu) == set(ref["e_blur"])
+    # (this fixture was not selected for a margin around zero: a leaky-ReLU unit within the operand rounding of zero takes
+    #  the other slope in the split-precision arithmetic and moves the small per-channel sums by ~1e-2 -- the bars are
+    #  those of tests/test_train_families_gpu.py::_check_all_pins; the strict element-wise check is the margin fixture)
+    worst = {k: rel(gf[k], gu[k]) for k in gu}
+    bad = {k: v for k, v in worst.items() if v >= (2e-2 if gu[k].dim() == 1 or gu[k].shape[0] == 1 else 5e-3)}
+    assert not bad, bad
+    for k, pin in ref["e_blur"].items():
+        vec = gf[k].dim() == 1 or (gf[k].dim() == 4 and gf[k].shape[0] == 1)
+        _check_pin(gf[k], pin, 2e-2 if vec else 5e-3, k)
+    # margin fixture: every gradient element against the reference's own backward
+    mx = torch.load(os.path.join(GOLD, "e_blur_margin.pt"))
+    E2 = EB.BE(**mx["config"])
+    E2.load_state_dict(mx["state_dict"], strict=True)
+    torch.manual_seed(mx["noise_seed"])
+    const, w = train_e.encoder_forward(E2, mx["img"], 9)
+    assert rel(const, mx["const"]) < 2e-4 and rel(w, mx["w"]) < 2e-4
+    (const.sum() + (w ** 2).mean()).backward()
+    got = {k: p.grad for k, p in E2.named_parameters() if p.grad is not None}
+    assert set(got) == set(mx["grads"])
+    bad = {k: rel(got[k], g) for k, g in mx["grads"].items() if rel(got[k], g) >= 1e-3}
+    assert not bad, bad

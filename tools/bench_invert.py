@@ -32,6 +32,9 @@ def main():
     ap.add_argument("--iterations", type=int, default=10)
     ap.add_argument("--res", type=int, default=1024)
     ap.add_argument("--lr", type=float, default=0.01)
+    ap.add_argument("--encoder", default="e", choices=["e", "blur"],
+                    help="e: model/E/E.py (case 1, what E_align_s2.py trains); blur: model/E/E_Blur.py (case 2, the class "
+                         "embedding_img.py:9 imports)")
     ap.add_argument("--noise", default="device", choices=["device", "reference"],
                     help="ours: where the encoder's per-block noise is drawn.  'reference' = on the CPU generator then copied, "
                          "as upstream (E.py:60,73): the same stream as the reference arm, used for the MSE comparison; "
@@ -51,7 +54,10 @@ def main():
     else:
         sys.path.insert(0, os.path.join(ROOT, "deep-gan-encoders_b200"))
     import torch
-    import model.E.E as EM
+    if a.encoder == "blur":
+        import model.E.E_Blur as EM
+    else:
+        import model.E.E as EM
     import model.stylegan2_generator as SG
     import training_utils as tu
     from model.utils.custom_adam import LREQAdam
@@ -160,7 +166,7 @@ def main():
         pstats.Stats(prof, stream=buf).sort_stats("tottime").print_stats(40)
         print(buf.getvalue(), file=sys.stderr)
     ms_it = wall / (a.images * a.iterations) * 1e3
-    out = {"impl": a.impl, "encoder_noise": a.noise if a.impl == "ours" else "reference", "workload": f"configs[4]: embedding_img.py:74-128 loop, StyleGAN2-{a.res} synthesis + "
+    out = {"impl": a.impl, "encoder": "E_Blur.BE" if a.encoder == "blur" else "E.BE", "encoder_noise": a.noise if a.impl == "ours" else "reference", "workload": f"configs[4]: embedding_img.py:74-128 loop, StyleGAN2-{a.res} synthesis + "
                                        f"BE({startf},{layers}), batch 1, synthetic images G(z_i), seeds 30000+i",
            "images": a.images, "iterations_per_image": a.iterations, "ms_per_iteration": ms_it,
            "s_per_image_measured": wall / a.images, "s_per_image_at_1500_iterations": ms_it * 1.5,
