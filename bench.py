@@ -405,6 +405,13 @@ def run_ours(args):
                                          "`ours_reference_noise` vs `reference_gpu` (identical seeds and noise stream)"}
             if "ms_per_iteration" in ours_inv and "ms_per_iteration" in ref_inv:
                 line["inversion"]["speedup_vs_reference_gpu"] = ref_inv["ms_per_iteration"] / ours_inv["ms_per_iteration"]
+            # the same loop with the case-2 encoder, the class embedding_img.py:9 actually imports (model/E/E_Blur.py)
+            blur = [sys.executable, os.path.join(ROOT, "tools", "bench_invert.py"), "--encoder", "blur", "--images", "2",
+                    "--iterations", "5"]
+            ours_b, ref_b = run_json_subprocess(blur, 600), run_json_subprocess(blur + ["--impl", "reference"], 900)
+            line["inversion"]["e_blur"] = {"ours": ours_b, "reference_gpu": ref_b}
+            if "ms_per_iteration" in ours_b and "ms_per_iteration" in ref_b:
+                line["inversion"]["e_blur"]["speedup_vs_reference_gpu"] = ref_b["ms_per_iteration"] / ours_b["ms_per_iteration"]
         if world == 1 and not args.no_cpu_baseline:
             ref = run_json_subprocess([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3",
                                        "--warmup", "1"], 900)
