@@ -406,8 +406,8 @@ def run_ours(args):
             if "ms_per_iteration" in ours_inv and "ms_per_iteration" in ref_inv:
                 line["inversion"]["speedup_vs_reference_gpu"] = ref_inv["ms_per_iteration"] / ours_inv["ms_per_iteration"]
             # the same loop with the case-2 encoder, the class embedding_img.py:9 actually imports (model/E/E_Blur.py)
-            blur = [sys.executable, os.path.join(ROOT, "tools", "bench_invert.py"), "--encoder", "blur", "--images", "2",
-                    "--iterations", "5"]
+            blur = [sys.executable, os.path.join(ROOT, "tools", "bench_invert.py"), "--encoder", "blur", "--images", "3",
+                    "--iterations", "6"]
             ours_b, ref_b = run_json_subprocess(blur, 600), run_json_subprocess(blur + ["--impl", "reference"], 900)
             line["inversion"]["e_blur"] = {"ours": ours_b, "reference_gpu": ref_b}
             if "ms_per_iteration" in ours_b and "ms_per_iteration" in ref_b:
