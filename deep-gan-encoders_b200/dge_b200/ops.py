@@ -80,8 +80,8 @@ def _stream():
     """torch's current CUDA stream as a raw cudaStream_t (the C entry points: ~0.3 us instead of ~15 us through
     torch.cuda.current_stream(), which matters at ~600 launches per training iteration)."""
     if _raw_stream is not None and _raw_device is not None:
-        return ctypes.c_void_p(_raw_stream(_raw_device()))
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        return _raw_stream(_raw_device())              # a plain int: ctypes converts it for the `void*` parameter
+    return torch.cuda.current_stream().cuda_stream
 
 
 # ------------------------------------------------------------------------------------------------
@@ -113,14 +113,13 @@ class profile:
         return out
 
 
-class _rec:
+class _Rec:
     def __init__(self, name, key):
         self.name, self.key = name, key
 
     def __enter__(self):
-        if _prof is not None:
-            self.e0 = torch.cuda.Event(enable_timing=True)
-            self.e0.record()
+        self.e0 = torch.cuda.Event(enable_timing=True)
+        self.e0.record()
 
     def __exit__(self, *exc):
         if _prof is not None and exc[0] is None:
@@ -129,11 +128,28 @@ class _rec:
             _prof.append((self.name, self.key, self.e0, e1))
 
 
+class _NoRec:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NOREC = _NoRec()
+
+
+def _rec(name, key):
+    """Per-launch timing scope: a shared no-op object unless `ops.profile()` is active (~700 launches per training
+    iteration go through here; at batch 1 the loop is host-bound)."""
+    return _NOREC if _prof is None else _Rec(name, key)
+
+
 def _p(t):
     if t is None:
         return None
     assert t.is_cuda and t.is_contiguous(), "dge_b200 ops need contiguous CUDA tensors"
-    return ctypes.c_void_p(t.data_ptr())
+    return t.data_ptr()                                # a plain int: the bindings declare `void*` argtypes
 
 
 def _f32(t):
@@ -315,6 +331,9 @@ def pixel_norm(x, eps=1e-8):
 # ------------------------------------------------------------------------------------------------
 # conv
 # ------------------------------------------------------------------------------------------------
+_splitk_ws = {}
+
+
 def conv(x, wpk, cout, kind=CONV_3X3, *, demod=None, noise=None, noise_batched=False, noise_w=None,
          noise_scalar=0.0, bias=None, slope=1.0, gain=1.0, blend_src=None, blend_pool=False, blend_a=0.0,
          blend_b=1.0, preact_add=None, preact_up=1, out_act=False, out_planes=None, out_scale=None, out_f32b=False,
@@ -383,7 +402,10 @@ def conv(x, wpk, cout, kind=CONV_3X3, *, demod=None, noise=None, noise_batched=F
         if rgb_w is not None:
             a.rgb_w, a.rgb_out = ptr(rgb_w), ptr(rgb_out)
     if not checker:
-        wsb = int(lib().dge_conv_splitk_ws_bytes(ctypes.byref(a)))
+        wkey = (kind, a.n, a.h, a.w, a.cin, a.cout)          # what the library's split-K decision reads (conv_mma.cu)
+        wsb = _splitk_ws.get(wkey)
+        if wsb is None:
+            wsb = _splitk_ws[wkey] = int(lib().dge_conv_splitk_ws_bytes(ctypes.byref(a)))
         if wsb:                              # small maps: split-K scratch (zeroed by the call)
             ws = torch.empty((wsb // 4,), dtype=torch.float32, device=dev)
             a.splitk_ws = ptr(ws)
