@@ -296,6 +296,45 @@ extern "C" int dge_conv_wgrad(const void* dy_act, const void* x_act, float* dw, 
   p.tiles_total = (int)tiles;
   const int cin16 = (cin + 15) / 16 * 16;
   p.nblk = cin16 < 128 ? cin16 : 128;
+  // Cost model (measured, tools/probe_wgrad.py): a CTA's MMA loop (A fetch or math per MMA, whichever is longer), its
+  // epilogue -- 128 rows x taps_x*nblk columns leave as scattered 4-byte stores / atomics, ~45 us per 384 columns + ~7 us
+  // fixed, which is what small maps pay for -- and, when the contraction is split over c chunks, one more pass of fp32
+  // atomics over dW per chunk (~200 G atomics/s) plus the memset.
+  const int ksteps_tile = p.rowpair ? p.th / 2 : p.th * (p.tw / 16);
+  const double pass_us = (double)cout * cin * ksize * ksize / 200e3;
+  auto predict = [&](int nblk, int mma_n, double mmas_kstep, int blocks_y, int ncols, int* chunks_out) {
+    const double clk_mma = mma_n / 2 > 64 ? mma_n / 2 : 64;
+    const double cta_us = (double)p.tiles_total * ksteps_tile * mmas_kstep * clk_mma / 1900.0;
+    const double epi_us = 7.0 + 45.0 * ncols / 384.0;
+    int max_chunks = (2 * g_wg_sms + blocks_y - 1) / blocks_y;
+    if (max_chunks > p.tiles_total) max_chunks = p.tiles_total;
+    if (max_chunks < 1) max_chunks = 1;
+    int chunks = 1;
+    double best = (cta_us + epi_us) * ((blocks_y + g_wg_sms - 1) / g_wg_sms);
+    for (int c = 2; c <= max_chunks; ++c) {
+      const int waves = (blocks_y * c + g_wg_sms - 1) / g_wg_sms;
+      const double t = (cta_us / c + epi_us) * waves + pass_us * c + 3.0;
+      if (t < best) {
+        best = t;
+        chunks = c;
+      }
+    }
+    (void)nblk;
+    *chunks_out = chunks;
+    return best;
+  };
+  const double split_mmas = planes == 2 ? 3.0 : 1.0;
+  if (!p.stacked && p.nblk == 128) {
+    // narrower Cin blocks double the CTAs that share the epilogue: pays when the map is small (the MMA loop is short)
+    static int nblk_env = -1;
+    if (nblk_env < 0) nblk_env = getenv("DGE_WGRAD_NBLK") ? atoi(getenv("DGE_WGRAD_NBLK")) : 0;      // A/B switch
+    const int cob_n = (cout + 127) / 128;
+    int c128, c64;
+    const double t128 = predict(128, 128, split_mmas * ksize, ksize * cob_n * ((cin + 127) / 128), ksize * 128, &c128);
+    const double t64 = predict(64, 64, split_mmas * ksize, ksize * cob_n * ((cin + 63) / 64), ksize * 64, &c64);
+    if (nblk_env == 64 || nblk_env == 128) p.nblk = nblk_env;
+    else if (t64 < t128) p.nblk = 64;
+  }
   p.cin_blocks = (cin + p.nblk - 1) / p.nblk;
   if (p.stacked) {
     p.n1 = 9 * cin <= 256 ? 9 * cin : 5 * cin;
@@ -322,25 +361,9 @@ extern "C" int dge_conv_wgrad(const void* dy_act, const void* x_act, float* dw, 
   const int blocks_y = p.stacked ? p.cout_blocks : ksize * p.cout_blocks * p.cin_blocks;
   // split of the contraction: c chunks shorten every CTA's MMA loop by c but each adds one pass of fp32 atomics over dW
   // (~200 G atomics/s measured); with one chunk the CTA owns its dW block and stores it (no memset, no atomics).
-  const int ksteps_tile = p.rowpair ? p.th / 2 : p.th * (p.tw / 16);
-  const int mma_n = p.stacked ? p.n1 : p.nblk;
-  const double clk_mma = mma_n / 2 > 64 ? mma_n / 2 : 64;     // A fetch (4 KB at ~64 B/clk) or the math, whichever is longer
-  const double mmas_kstep = (planes == 2 ? 3.0 : 1.0) * (p.stacked ? (p.n2 ? 2 : 1) : p.taps_x);
-  const double cta_us = (double)p.tiles_total * ksteps_tile * mmas_kstep * clk_mma / 1900.0;
-  const double pass_us = (double)cout * cin * ksize * ksize / 200e3;
-  int max_chunks = (2 * g_wg_sms + blocks_y - 1) / blocks_y;
-  if (max_chunks > p.tiles_total) max_chunks = p.tiles_total;
-  if (max_chunks < 1) max_chunks = 1;
   int chunks = 1;
-  double best = cta_us * ((blocks_y + g_wg_sms - 1) / g_wg_sms);
-  for (int c = 2; c <= max_chunks; ++c) {
-    const int waves = (blocks_y * c + g_wg_sms - 1) / g_wg_sms;
-    const double t = cta_us / c * waves + pass_us * c + 3.0;   // + memset and the atomics' tail
-    if (t < best) {
-      best = t;
-      chunks = c;
-    }
-  }
+  predict(p.nblk, p.stacked ? p.n1 : p.nblk, split_mmas * (p.stacked ? (p.n2 ? 2 : 1) : p.taps_x), blocks_y,
+          (p.stacked ? 9 : p.taps_x) * p.nblk, &chunks);
   p.chunks = chunks;
   p.atomic = chunks > 1;
   p.accumulate = accumulate;
