@@ -40,11 +40,12 @@ def record_masks(store):
     import metric.pytorch_ssim as _PS
     import model.E.E as _EM
     import model.E.E_BIG as _EG
+    import model.E.E_Blur as _EB
     import model.biggan_generator as _BG
     import model.stylegan1.net as _S1
     import model.stylegan2_generator as _SG
     import training_utils as _TU
-    mods = (_EM, _SG, _PS, _TU, _S1, _EG, _BG)
+    mods = (_EM, _SG, _PS, _TU, _S1, _EG, _BG, _EB)
     fused = [m.FUSED_TRAIN for m in mods] + [_LP.FUSED]
     for m in mods:
         m.FUSED_TRAIN = False
