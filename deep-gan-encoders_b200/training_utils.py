@@ -226,6 +226,11 @@ def space_loss(imgs1, imgs2, image_space=True, lpips_model=None):
     else:
         ssim_l, lp_v = 0, 0
     loss = 5 * mse1 + 3 * cos + ssim_l + 2 * lp_v
-    loss_t = torch.tensor(loss, dtype=torch.float32, device=dev)
+    if image_space and lp.requires_grad:
+        # neither image carries a gradient but the caller's LPIPS module does (its `lin` weights): the reference's loss then
+        # still has a grad_fn, and E_mis_align_cropping_s1.py:187-193 calls backward() on exactly such losses
+        loss_t = torch.tensor(5 * mse1 + 3 * cos + ssim_l, dtype=torch.float32, device=dev) + 2 * lp
+    else:
+        loss_t = torch.tensor(loss, dtype=torch.float32, device=dev)
     loss_info = [[mse1, mse2, mse3], kl, cos, ssim_l, lp_v]
     return loss_t, loss_info

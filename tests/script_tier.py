@@ -52,7 +52,7 @@ def perturb(module, seed):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("script", choices=["E_align_s2.py", "embedding_img.py"])
+    ap.add_argument("script", choices=["E_align_s2.py", "embedding_img.py", "E_mis_align_cropping_s1.py"])
     ap.add_argument("--cpu-plumbing", action="store_true")
     ap.add_argument("--img-size", type=int, default=64)
     ap.add_argument("--iterations", type=int, default=2)
@@ -82,7 +82,7 @@ def main():
     work = tempfile.mkdtemp(prefix="dge_script_")
     os.chdir(work)
     res = os.path.join(work, "result")
-    for d in (res, res + "/imgs", res + "/models", res + "/summaries"):
+    for d in (res, res + "/imgs", res + "/models", res + "/summaries", res + "/grad_cam"):
         os.makedirs(d)
     layers = int(__import__("math").log2(a.img_size)) - 1
     # start_features must reach maxf = 512 by the last block (the reference's last block blends `inputs`-channel features
@@ -94,8 +94,31 @@ def main():
     mod.device = torch.device("cpu" if a.cpu_plumbing else "cuda")
     mod.resultPath, mod.resultPath1_1, mod.resultPath1_2 = res, res + "/imgs", res + "/models"
     mod.writer_path = res + "/summaries"
+    mod.resultPath_grad_cam = res + "/grad_cam"
     out = {"script": path, "iterations": a.iterations, "img_size": a.img_size}
-    if a.script == "E_align_s2.py":
+    if a.script == "E_mis_align_cropping_s1.py":
+        # the Grad-CAM variant (:99-106, 158-171): torchvision's VGG16 classifier (its published weights are not available
+        # offline: `pretrained=True` is answered with seeded random weights), Grad-CAM++ masks, guided back-propagation and
+        # mask2cam on both images of every iteration, StyleGAN2 generator
+        import torchvision
+        _vgg16 = torchvision.models.vgg16
+
+        def vgg16_offline(*_a, **_k):
+            torch.manual_seed(7)
+            return _vgg16(weights=None)
+        torchvision.models.vgg16 = vgg16_offline
+        from model.stylegan2_generator import StyleGAN2Generator
+        G = StyleGAN2Generator(resolution=a.img_size)
+        perturb(G, 1)
+        ck = os.path.join(work, "stylegan2_synth.pth")
+        torch.save({"generator_smooth": G.state_dict()}, ck)
+        args = argparse.Namespace(mtype=2, checkpoint_dir_GAN=ck, config_dir=None, checkpoint_dir_E=None,
+                                  img_size=a.img_size, img_channels=3, z_dim=512, start_features=startf, batch_size=2,
+                                  iterations=a.iterations, lr=0.0015, beta_1=0.0, experiment_dir=res)
+        call = lambda: mod.train(tensor_writer=NullWriter(), args=args)
+        expect = [res + "/models/E_model_ep0_iter0.pth", res + "/Loss.txt", res + "/imgs/ep0_iter0.png",
+                  res + "/grad_cam/heatmap_0.png", res + "/grad_cam/cam_0.png", res + "/grad_cam/gb_0.png"]
+    elif a.script == "E_align_s2.py":
         cfg_path, z_dim = None, 512
         if a.mtype == 2:
             from model.stylegan2_generator import StyleGAN2Generator

@@ -101,3 +101,26 @@ def test_lreq_adam_on_encoder_parameters():
         ooptim.lreq_adam_step(ref_p, grads, ref_v, [step] * len(ref_p), coefs, 0.0015, 0.99)
     for p, q in zip(params, ref_p):
         assert ((p.detach().cpu() - q).abs().max() / q.abs().max().clamp_min(1e-20)).item() < 1e-6
+
+
+def test_space_loss_of_detached_images_still_reaches_the_lpips_module():
+    """E_mis_align_cropping_s1.py:171-193 calls `backward()` on losses whose images are all `.detach().clone()`: upstream
+    that works only because the LPIPS module's `lin` weights require grad.  The drop-in keeps that graph: the loss has a
+    grad_fn, backward() fills the `lin` gradients, and the value is the one the no-grad evaluation returns."""
+    import os
+    os.environ["DGE_LPIPS_ALLOW_RANDOM"] = "1"
+    import lpips
+    import training_utils as tu
+    lp = lpips.LPIPS(net="vgg", pretrained=False, pnet_rand=True, verbose=False).cuda()
+    g = torch.Generator().manual_seed(3)
+    a = torch.rand(2, 3, 64, 64, generator=g).cuda() * 2 - 1
+    b = torch.rand(2, 3, 64, 64, generator=g).cuda() * 2 - 1
+    loss, info = tu.space_loss(a.detach().clone(), b.detach().clone(), lpips_model=lp)
+    assert loss.requires_grad
+    loss.backward()
+    grads = [p.grad for p in lp.lins.parameters()]
+    assert all(gr is not None and torch.isfinite(gr).all() for gr in grads) and any(gr.abs().max() > 0 for gr in grads)
+    with torch.no_grad():
+        loss0, info0 = tu.space_loss(a, b, lpips_model=lp)
+    assert not loss0.requires_grad
+    assert abs(float(loss) - float(loss0)) <= 1e-5 * abs(float(loss0)) and abs(info[4] - info0[4]) <= 1e-5 * abs(info0[4]) + 1e-9

@@ -19,7 +19,8 @@ def run_tier(script, *flags):
 
 
 @pytest.mark.parametrize("script,extra", [("E_align_s2.py", ()), ("embedding_img.py", ()),
-                                          ("E_align_s2.py", ("--mtype", "1")), ("E_align_s2.py", ("--mtype", "4"))])
+                                          ("E_align_s2.py", ("--mtype", "1")), ("E_align_s2.py", ("--mtype", "4")),
+                                          ("E_mis_align_cropping_s1.py", ())])
 def test_unmodified_script_reaches_the_first_kernel_and_refuses_the_cpu(script, extra):
     out = run_tier(script, "--cpu-plumbing", "--img-size", "32", *extra)
     if "skipped" in out:

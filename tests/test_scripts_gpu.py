@@ -38,3 +38,15 @@ def test_e_align_s2_other_generator_families_unmodified(mtype):
     assert out["missing_outputs"] == [], out
     assert out["dge_launches"] > 200, out
     assert out["e_checkpoint_keys"] > 50 and out["e_checkpoint_finite"], out
+
+
+def test_e_mis_align_cropping_trains_two_iterations_unmodified():
+    """The Grad-CAM variant of the training script (E_mis_align_cropping_s1.py: Grad-CAM++ masks, guided back-propagation and
+    mask2cam on a torchvision VGG16 every iteration) -- unmodified, on the drop-in package."""
+    out = run_tier("E_mis_align_cropping_s1.py", "--img-size", "64", "--iterations", "2")
+    if "skipped" in out:
+        pytest.skip(out["skipped"])
+    assert out["completed"] is True, out
+    assert out["missing_outputs"] == [], out
+    assert out["dge_launches"] > 300, out
+    assert out["e_checkpoint_keys"] > 50 and out["e_checkpoint_finite"], out
