@@ -52,7 +52,7 @@ def perturb(module, seed):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("script", choices=["E_align_s2.py", "embedding_img.py", "E_mis_align_cropping_s1.py"])
+    ap.add_argument("script", choices=["E_align_s2.py", "embedding_img.py", "E_mis_align_cropping_s1.py", "E_align_cropping_s1.py"])
     ap.add_argument("--cpu-plumbing", action="store_true")
     ap.add_argument("--img-size", type=int, default=64)
     ap.add_argument("--iterations", type=int, default=2)
@@ -118,7 +118,7 @@ def main():
         call = lambda: mod.train(tensor_writer=NullWriter(), args=args)
         expect = [res + "/models/E_model_ep0_iter0.pth", res + "/Loss.txt", res + "/imgs/ep0_iter0.png",
                   res + "/grad_cam/heatmap_0.png", res + "/grad_cam/cam_0.png", res + "/grad_cam/gb_0.png"]
-    elif a.script == "E_align_s2.py":
+    elif a.script in ("E_align_s2.py", "E_align_cropping_s1.py"):       # (the cropping variant: same loop, detached losses)
         cfg_path, z_dim = None, 512
         if a.mtype == 2:
             from model.stylegan2_generator import StyleGAN2Generator

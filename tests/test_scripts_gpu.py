@@ -50,3 +50,14 @@ def test_e_mis_align_cropping_trains_two_iterations_unmodified():
     assert out["missing_outputs"] == [], out
     assert out["dge_launches"] > 300, out
     assert out["e_checkpoint_keys"] > 50 and out["e_checkpoint_finite"], out
+
+
+def test_e_align_cropping_s1_trains_two_iterations_unmodified():
+    """E_align_cropping_s1.py: the E_align loop whose three image losses are all computed on detached clones."""
+    out = run_tier("E_align_cropping_s1.py", "--img-size", "64", "--iterations", "2")
+    if "skipped" in out:
+        pytest.skip(out["skipped"])
+    assert out["completed"] is True, out
+    assert out["missing_outputs"] == [], out
+    assert out["dge_launches"] > 200, out
+    assert out["e_checkpoint_keys"] > 50 and out["e_checkpoint_finite"], out
