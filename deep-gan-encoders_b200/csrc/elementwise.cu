@@ -1490,6 +1490,35 @@ __global__ void k_lreq_adam(float* const* __restrict__ params, const float* cons
   const float* g = grads[t];
   float* v = vs[t];
   const float st = step[t], omb = 1.f - beta2;
+  // 128-bit path when the three streams of this block are 16-byte aligned (gradients may be views into the flat
+  // all-reduce bucket at any 4-byte offset): 5 streams of 4 B per element, HBM-bound
+  if ((((uintptr_t)(p + off) | (uintptr_t)(g + off) | (uintptr_t)(v + off)) & 15) == 0) {
+    const long long n4 = (end - off) >> 2;
+    float4* p4 = reinterpret_cast<float4*>(p + off);
+    const float4* g4 = reinterpret_cast<const float4*>(g + off);
+    float4* v4 = reinterpret_cast<float4*>(v + off);
+    for (long long i = threadIdx.x; i < n4; i += blockDim.x) {
+      const float4 gq = g4[i];
+      float4 vq = v4[i], pq = p4[i];
+      vq.x = vq.x * beta2 + omb * gq.x * gq.x;
+      vq.y = vq.y * beta2 + omb * gq.y * gq.y;
+      vq.z = vq.z * beta2 + omb * gq.z * gq.z;
+      vq.w = vq.w * beta2 + omb * gq.w * gq.w;
+      pq.x = pq.x - st * (gq.x / (sqrtf(vq.x) + eps));
+      pq.y = pq.y - st * (gq.y / (sqrtf(vq.y) + eps));
+      pq.z = pq.z - st * (gq.z / (sqrtf(vq.z) + eps));
+      pq.w = pq.w - st * (gq.w / (sqrtf(vq.w) + eps));
+      v4[i] = vq;
+      p4[i] = pq;
+    }
+    for (long long i = off + (n4 << 2) + threadIdx.x; i < end; i += blockDim.x) {
+      const float gi = g[i];
+      const float vi = v[i] * beta2 + omb * gi * gi;
+      v[i] = vi;
+      p[i] = p[i] - st * (gi / (sqrtf(vi) + eps));
+    }
+    return;
+  }
   for (long long i = off + threadIdx.x; i < end; i += blockDim.x) {
     const float gi = g[i];
     const float vi = v[i] * beta2 + omb * gi * gi;
