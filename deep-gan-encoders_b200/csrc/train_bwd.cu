@@ -324,13 +324,23 @@ struct Sg2BwdParams {
 // Thread = (pixel, channel HALF): 4 channels per thread keep the 5 x 4 accumulators and the per-channel constants in ~70
 // registers (three blocks per SM instead of one with 8 channels per thread: the kernel is latency-bound on its loads);
 // the two halves of a 16-byte ACT chunk / 32-byte F32B sector are read by neighbouring lanes, so accesses stay coalesced.
-__global__ void __launch_bounds__(TB_THREADS, 3)
+// RGB: the layer feeds a ToRGB (d_image term + the three T sums); without it 12 accumulators and 12 constants fewer.
+// DXS: a next layer exists (its data gradient dxs and the S sum); the last layer of the network has none.
+template <bool RGB, bool DXS>
+__global__ void __launch_bounds__(TB_THREADS, RGB ? 3 : 4)
 k_sg2_layer_bwd(const __grid_constant__ Sg2BwdParams p) {
   __shared__ float red[TB_THREADS / 32][2][20];
   const int c = p.c, C8 = c >> 3, ng = blockIdx.y, nidx = ng / C8, grp = ng - nidx * C8;
   const size_t hw = (size_t)p.hw;
   const int half = threadIdx.x & 1;
-  float sn[4], isn[4], dm[4], bs[4], rw[3][4];
+  // the 3 x 8 ToRGB weights of this (sample, channel group) live in shared memory (12 registers the loop cannot spare)
+  __shared__ __align__(16) float srw[2][3][4];
+  if (RGB && threadIdx.x < 24) {
+    const int hf = threadIdx.x / 12, q = (threadIdx.x % 12) >> 2, k = threadIdx.x & 3;
+    srw[hf][q][k] = __ldg(p.rgbw + ((size_t)nidx * 3 + q) * c + grp * 8 + 4 * hf + k);
+  }
+  if (RGB) __syncthreads();
+  float sn[4], isn[4], dm[4], bs[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int ch = grp * 8 + 4 * half + k;
@@ -338,57 +348,74 @@ k_sg2_layer_bwd(const __grid_constant__ Sg2BwdParams p) {
     isn[k] = sn[k] != 0.f ? 1.f / sn[k] : 0.f;
     dm[k] = p.demod ? __ldg(p.demod + (size_t)nidx * c + ch) : 1.f;
     bs[k] = p.bias ? __ldg(p.bias + ch) : 0.f;
-#pragma unroll
-    for (int q = 0; q < 3; ++q) rw[q][k] = p.rgbw ? __ldg(p.rgbw + ((size_t)nidx * 3 + q) * c + ch) : 0.f;
   }
   const float g_pos = p.gain, g_neg = p.gain * p.slope;
   const float ig_pos = 1.f / p.gain, ig_neg = p.slope != 0.f ? 1.f / (p.gain * p.slope) : 0.f;
   float acc[20];
 #pragma unroll
   for (int i = 0; i < 20; ++i) acc[i] = 0.f;
+  // every base pointer of the loop is formed once (the 64-bit index products were ~20 % of the instructions issued)
   const uint2* ya = reinterpret_cast<const uint2*>(p.ya) + ((size_t)ng * p.planes * hw) * 2 + half;
-  const float4* dxs = p.dxs ? reinterpret_cast<const float4*>(p.dxs) + ((size_t)ng * hw) * 2 + half : nullptr;
-  const size_t stride = ((size_t)gridDim.x * blockDim.x) >> 1;
-  for (size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 1; i < hw; i += stride) {
+  const float4* dxs = DXS ? reinterpret_cast<const float4*>(p.dxs) + ((size_t)ng * hw) * 2 + half : nullptr;
+  const float* di0 = RGB ? p.dimg + (size_t)nidx * 3 * hw : nullptr;
+  const float* nzp = p.noise ? p.noise + (size_t)nidx * p.noise_bstride : nullptr;
+  uint2* oact = p.out_act ? reinterpret_cast<uint2*>(p.out_act) + ((size_t)ng * p.out_planes * hw) * 2 + half : nullptr;
+  const unsigned uhw = (unsigned)hw;
+  float4* of32 = p.out_f32b ? reinterpret_cast<float4*>(p.out_f32b) + ((size_t)ng * hw) * 2 + half : nullptr;
+  const bool two_in = p.planes == 2, two_out = p.out_planes == 2;
+  const float nsc = p.noise_scalar;
+  const unsigned stride = (gridDim.x * blockDim.x) >> 1;
+  for (unsigned i = (blockIdx.x * blockDim.x + threadIdx.x) >> 1; i < (unsigned)hw; i += stride) {
     float y[4], dx[4], v[4];
     {
       const uint2 q = __ldg(ya + 2 * i);
       y[0] = __uint_as_float(q.x << 16); y[1] = __uint_as_float(q.x & 0xffff0000u);
       y[2] = __uint_as_float(q.y << 16); y[3] = __uint_as_float(q.y & 0xffff0000u);
-      if (p.planes == 2) {
-        const uint2 l = __ldg(ya + 2 * (hw + i));
+      if (two_in) {
+        const uint2 l = __ldg(ya + 2 * (size_t)(i + uhw));
         y[0] += __uint_as_float(l.x << 16); y[1] += __uint_as_float(l.x & 0xffff0000u);
         y[2] += __uint_as_float(l.y << 16); y[3] += __uint_as_float(l.y & 0xffff0000u);
       }
     }
-    if (dxs) {
+    if (DXS) {
       const float4 t = __ldg(dxs + 2 * i);
       dx[0] = t.x; dx[1] = t.y; dx[2] = t.z; dx[3] = t.w;
     } else {
       dx[0] = dx[1] = dx[2] = dx[3] = 0.f;
     }
     float di[3] = {0.f, 0.f, 0.f};
-    if (p.dimg) {
-#pragma unroll
-      for (int q = 0; q < 3; ++q) di[q] = __ldg(p.dimg + ((size_t)nidx * 3 + q) * hw + i);
+    if (RGB) {
+      di[0] = __ldg(di0 + i);
+      di[1] = __ldg(di0 + (i + uhw));
+      di[2] = __ldg(di0 + (size_t)i + 2 * (size_t)uhw);
     }
-    const float nzs = p.noise ? __ldg(p.noise + (size_t)nidx * p.noise_bstride + i) * p.noise_scalar : 0.f;
+    const float nzs = nzp ? __ldg(nzp + i) * nsc : 0.f;
+    float rw[3][4];
+    if (RGB) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const float4 t = *reinterpret_cast<const float4*>(srw[half][q]);
+        rw[q][0] = t.x; rw[q][1] = t.y; rw[q][2] = t.z; rw[q][3] = t.w;
+      }
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float yv = y[k] * isn[k];
-      float dy = dx[k] * sn[k];
-      dy = fmaf(rw[0][k], di[0], fmaf(rw[1][k], di[1], fmaf(rw[2][k], di[2], dy)));
-      acc[k] = fmaf(dx[k], yv, acc[k]);
-      acc[4 + k] = fmaf(di[0], yv, acc[4 + k]);
-      acc[8 + k] = fmaf(di[1], yv, acc[8 + k]);
-      acc[12 + k] = fmaf(di[2], yv, acc[12 + k]);
+      float dy = DXS ? dx[k] * sn[k] : 0.f;
+      if (DXS) acc[k] = fmaf(dx[k], yv, acc[k]);
+      if (RGB) {
+        dy = fmaf(rw[0][k], di[0], fmaf(rw[1][k], di[1], fmaf(rw[2][k], di[2], dy)));
+        acc[4 + k] = fmaf(di[0], yv, acc[4 + k]);
+        acc[8 + k] = fmaf(di[1], yv, acc[8 + k]);
+        acc[12 + k] = fmaf(di[2], yv, acc[12 + k]);
+      }
       const bool pos = yv > 0.f;
       const float dpre = dy * (pos ? g_pos : g_neg);
       const float pre = yv * (pos ? ig_pos : ig_neg);
       acc[16 + k] = fmaf(dpre, pre - nzs - bs[k], acc[16 + k]);
       v[k] = dpre * dm[k];
     }
-    if (p.out_act) {
+    if (oact) {
       uint32_t hw2[2], lw2[2];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
@@ -398,12 +425,10 @@ k_sg2_layer_bwd(const __grid_constant__ Sg2BwdParams p) {
                                                         v[2 * j + 1] - __uint_as_float(hw2[j] & 0xffff0000u));
         lw2[j] = *reinterpret_cast<const uint32_t*>(&lb);
       }
-      uint2* o = reinterpret_cast<uint2*>(p.out_act) + ((size_t)ng * p.out_planes * hw + i) * 2 + half;
-      *o = make_uint2(hw2[0], hw2[1]);
-      if (p.out_planes == 2) o[2 * hw] = make_uint2(lw2[0], lw2[1]);
+      oact[2 * i] = make_uint2(hw2[0], hw2[1]);
+      if (two_out) oact[2 * (size_t)(i + uhw)] = make_uint2(lw2[0], lw2[1]);
     }
-    if (p.out_f32b)
-      reinterpret_cast<float4*>(p.out_f32b)[((size_t)ng * hw + i) * 2 + half] = make_float4(v[0], v[1], v[2], v[3]);
+    if (of32) of32[2 * i] = make_float4(v[0], v[1], v[2], v[3]);
   }
   // reduce over the lanes of the same half (xor 16, 8, 4, 2), then over the warps
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -922,7 +947,10 @@ extern "C" int dge_sg2_layer_bwd(const void* ya_act, const float* ya_scale, cons
   p.slope = slope; p.out_act = out_act; p.out_f32b = out_f32b; p.sums = sums; p.c = c; p.hw = h * w; p.planes = planes;
   p.out_planes = out_planes;
   dim3 grid(tb_splits(2ll * h * w, (long long)n * (c / 8)), n * (c / 8));   // two threads (channel halves) per pixel
-  k_sg2_layer_bwd<<<grid, TB_THREADS, 0, TB_STREAM>>>(p);
+  if (p.dimg && p.dxs) k_sg2_layer_bwd<true, true><<<grid, TB_THREADS, 0, TB_STREAM>>>(p);
+  else if (p.dimg) k_sg2_layer_bwd<true, false><<<grid, TB_THREADS, 0, TB_STREAM>>>(p);
+  else if (p.dxs) k_sg2_layer_bwd<false, true><<<grid, TB_THREADS, 0, TB_STREAM>>>(p);
+  else k_sg2_layer_bwd<false, false><<<grid, TB_THREADS, 0, TB_STREAM>>>(p);
   count_launch();
   return check_launch("k_sg2_layer_bwd");
 }
