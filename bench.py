@@ -514,6 +514,15 @@ def train_leg(G, E, dev, rank, world, steps, warmup):
                    "fused training nodes (dge_b200/train_e.py, train_g.py), bf16x3 split-precision convs",
            "encoder_step": {"ms": ms_enc, "images_per_s": BATCH * world / (ms_enc / 1e3),
                             "what": "BE(16,9) forward + backward + gradient all-reduce + LREQAdam.step only"}}
+    # data-parallel correctness, not just speed: every rank started from the same weights, saw different images and applied the
+    # averaged gradients -> after all those steps the replicas must still be bit-identical (and finite)
+    chk = torch.stack([p.detach().double().sum() for p in E.parameters()])
+    out["train_state"] = {"parameters_finite": bool(torch.isfinite(chk).all())}
+    if world > 1:
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        out["train_state"]["replicas_bit_identical"] = bool((hi == lo).all())
     bucket = opt._bucket
     if world > 1 and bucket is not None:
         # the same iterations without the exchange -> exposed communication; and the exchange alone

@@ -30,6 +30,13 @@ from model.utils.custom_adam import LREQAdam
 
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
+# under torchrun (BASELINE configs[3] names 4 x B200): one process per GPU, each with its own batch; LREQAdam then owns the
+# bucketed NCCL all-reduce of the encoder gradients (dge_b200/dist.py), nothing else changes in the loop
+WORLD, RANK = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+if WORLD > 1:
+    import torch.distributed as dist
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    dist.init_process_group("nccl")
 dev = torch.device("cuda")
 BIGGAN_CFG = {"attention_layer_position": 8, "channel_width": 128, "class_embed_dim": 128, "eps": 0.0001,
               "layers": [[False, 16, 16], [True, 16, 16], [False, 16, 16], [True, 16, 8], [False, 8, 8], [True, 8, 8],
@@ -68,6 +75,8 @@ def timeit(fn, warm, it):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
+    if WORLD > 1:
+        dist.barrier()
     torch.cuda.reset_peak_memory_stats()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -75,7 +84,12 @@ def timeit(fn, warm, it):
         fn()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / it
+    ms = e0.elapsed_time(e1) / it
+    if WORLD > 1:                      # device time, max over ranks
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
 
 
 def losses_and_steps(opt, lp, imgs1, imgs2, w1, w2):
@@ -113,7 +127,7 @@ if only in ("both", "sg1"):
     coefs = torch.ones(1, 14, 1, device=dev)
     coefs[:, :7] = 0.7
     opt = LREQAdam([{"params": E1.parameters()}], lr=0.0015, betas=(0.0, 0.99), weight_decay=0)
-    z = torch.randn(16, 512, device=dev)
+    z = torch.randn(16, 512, device=dev, generator=torch.Generator(device=dev).manual_seed(100 + RANK))
 
     def sg1_iter():
         with torch.no_grad():
@@ -123,10 +137,11 @@ if only in ("both", "sg1"):
         imgs2 = Gs.forward(w2, 6)
         losses_and_steps(opt, lp, imgs1, imgs2, w1, w2)
     ms = timeit(sg1_iter, 2, 5)
-    out["stylegan1_256_bs16_train"] = {"ms_per_iteration": ms, "images_per_s": 16 / (ms / 1e3),
+    out["stylegan1_256_bs16_train"] = {"ms_per_iteration": ms, "images_per_s": 16 * WORLD / (ms / 1e3),
                                        "peak_gib": torch.cuda.max_memory_allocated() / 2 ** 30}
-    del Gs, Gm, E1, opt
-    torch.cuda.empty_cache()
+    if only == "both":
+        del Gs, Gm, E1, opt
+        torch.cuda.empty_cache()
 if only in ("both", "biggan"):
     from model.biggan_generator import BigGAN
     from model.E.E_BIG import BE as BE_BIG
@@ -136,6 +151,14 @@ if only in ("both", "biggan"):
     with torch.no_grad():
         Gb.generator.bn.weight.fill_(1.0)
         Gb.generator.bn.bias.zero_()
+        # random spectral-norm vectors give huge effective weights (and NaN images): converge them as a trained checkpoint's are
+        for m in Gb.modules():
+            if hasattr(m, "weight_u"):
+                m.train()
+                for _ in range(20):
+                    for hook in m._forward_pre_hooks.values():
+                        hook(m, None)
+        Gb.eval()
     Gb = Gb.to(dev)
     Eb = BE_BIG(64, 512, 7, 512, 3, biggan=True)
     perturb(Eb, 3)
@@ -144,7 +167,7 @@ if only in ("both", "biggan"):
         Eb.set_noise_mode("device")
     opt = LREQAdam([{"params": Eb.parameters()}], lr=0.0015, betas=(0.0, 0.99), weight_decay=0)
     bs = 32
-    zb = torch.randn(bs, 128, device=dev).clamp_(-2, 2) * 0.4
+    zb = torch.randn(bs, 128, device=dev, generator=torch.Generator(device=dev).manual_seed(200 + RANK)).clamp_(-2, 2) * 0.4
     label = torch.zeros(bs, 1000, device=dev)
     label[:, 30] = 1
 
@@ -154,6 +177,22 @@ if only in ("both", "biggan"):
         const2, w2 = Eb(imgs1, const1)
         imgs2, _ = Gb(w2, label, 0.4)
         losses_and_steps(opt, lp, imgs1, imgs2, zb, w2)
+    if os.environ.get("DGE_SYNCDBG") and WORLD > 1:
+        def rep(tag):
+            nm = [k for k, _ in Eb.named_parameters()]
+            for what, ts in (("param", [p.detach() for p in Eb.parameters()]),
+                             ("grad", [p.grad.detach() if p.grad is not None else torch.zeros(1, device=dev) for p in Eb.parameters()])):
+                t = torch.stack([x.double().sum() for x in ts])
+                lo, hi = t.clone(), t.clone()
+                dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+                dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+                bad = [nm[i] for i in torch.nonzero(hi != lo).flatten().tolist()]
+                if RANK == 0:
+                    print(tag, what, "differ", len(bad), bad[:3], file=sys.stderr, flush=True)
+        rep("init")
+        for it in range(3):
+            big_iter()
+            rep(f"after iteration {it}")
     ms = timeit(big_iter, 2, 3)
     if os.environ.get("DGE_KPROF"):             # where the iteration's GPU time goes (kernel table to stderr)
         with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CPU,
@@ -162,6 +201,23 @@ if only in ("both", "biggan"):
             torch.cuda.synchronize()
         print(kp.key_averages().table(sort_by="self_cuda_time_total", row_limit=60, max_name_column_width=90),
               file=sys.stderr)
-    out["biggan_deep_256_bs32_train"] = {"ms_per_iteration": ms, "images_per_s": bs / (ms / 1e3),
+    out["biggan_deep_256_bs32_train"] = {"ms_per_iteration": ms, "images_per_s": bs * WORLD / (ms / 1e3),
                                          "peak_gib": torch.cuda.max_memory_allocated() / 2 ** 30}
-print(json.dumps(out))
+out["n_gpus"] = WORLD
+if WORLD > 1:
+    # the replicas must hold identical weights after their steps (same initial weights, averaged gradients)
+    enc = Eb if only in ("both", "biggan") else E1
+    names = [k for k, _ in enc.named_parameters()]
+    chk = torch.stack([p.detach().double().sum() for p in enc.parameters()])
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    differ = [names[i] for i in torch.nonzero(hi != lo).flatten().tolist()]
+    out["parameters_finite"] = bool(torch.isfinite(chk).all())
+    out["replicas_in_sync"] = not differ
+    out["parameters_out_of_sync"] = differ[:12]
+    dist.barrier()
+if RANK == 0:
+    print(json.dumps(out))
+if WORLD > 1:
+    dist.destroy_process_group()
