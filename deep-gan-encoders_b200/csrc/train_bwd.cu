@@ -84,32 +84,39 @@ k_be_head_bwd(const float* __restrict__ d_out, const float* __restrict__ y2, con
   float acc[24];
 #pragma unroll
   for (int i = 0; i < 24; ++i) acc[i] = 0.f;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < hwp; i += (size_t)gridDim.x * blockDim.x) {
-    const int py = (int)(i / wo), px = (int)(i - (size_t)py * wo);
+  // (32-bit pixel indices and per-block base pointers: the 64-bit index arithmetic was a fifth of the issued instructions
+  //  in these latency-bound loops -- ncu source page of k_sg2_layer_bwd)
+  const float* d_out_b = d_out + (size_t)ng * hwp * 8;
+  const float* y2_b = y2 + (size_t)ng * hw * 8;
+  const float* noise_b = noise ? noise + (size_t)nidx * hw : nullptr;
+  const size_t dres_b = (size_t)ng * planes * hwp, dy2_b = (size_t)ng * planes * hw;
+  const unsigned uwo = (unsigned)wo, stride = gridDim.x * blockDim.x;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)hwp; i += stride) {
+    const unsigned py = i / uwo, px = i - py * uwo;
     float d[8], r[8];
-    load8_f32b(d_out, (size_t)ng * hwp + i, d);
+    load8_f32b(d_out_b, i, d);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       r[k] = gb * d[k];
       acc[16 + k] += r[k];
       d[k] *= ga4;
     }
-    if (dres) store8_act_at(dres, (size_t)ng * planes * hwp + i, hwp, planes, r);
+    if (dres) store8_act_at(dres, dres_b + i, hwp, planes, r);
 #pragma unroll
     for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
       for (int dx = 0; dx < 2; ++dx) {
-        const size_t pix = (size_t)(2 * py + dy) * W + (2 * px + dx);
+        const unsigned pix = (2 * py + dy) * (unsigned)W + (2 * px + dx);
         float y[8], v[8];
-        load8_f32b(y2, (size_t)ng * hw + pix, y);
-        const float nz = noise ? __ldg(noise + (size_t)nidx * hw + pix) : 0.f;
+        load8_f32b(y2_b, pix, y);
+        const float nz = noise_b ? __ldg(noise_b + pix) : 0.f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           v[k] = y[k] > 0.f ? d[k] : d[k] * slope;
           acc[k] += v[k];
           acc[8 + k] = fmaf(v[k], nz, acc[8 + k]);
         }
-        store8_act_at(dy2, (size_t)ng * planes * hw + pix, hw, planes, v);
+        store8_act_at(dy2, dy2_b + pix, hw, planes, v);
       }
   }
   const float t = block_sums<24>(acc, red);
@@ -132,11 +139,13 @@ k_in_bwd_stats(const float* __restrict__ g, const float* __restrict__ x, const f
     r[k] = __ldg(mr + o + 1);
     s1[k] = s2[k] = 0.f;
   }
-  const size_t base = (size_t)ng * hw;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)hw; i += (size_t)gridDim.x * blockDim.x) {
+  const float* g_b = g + (size_t)ng * hw * 8;
+  const float* x_b = x + (size_t)ng * hw * 8;
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)hw; i += stride) {
     float gv[8], xv[8];
-    load8_f32b(g, base + i, gv);
-    load8_f32b(x, base + i, xv);
+    load8_f32b(g_b, i, gv);
+    load8_f32b(x_b, i, xv);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       s1[k] += gv[k];
@@ -204,40 +213,46 @@ k_in_bwd_apply(const float* __restrict__ g, const float* __restrict__ x, const f
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
   const size_t base = (size_t)ng * hw;
-  const int wr = res_pool ? (w >> 1) : w;
-  const size_t rbase = (size_t)ng * (res_pool ? (hw >> 2) : hw);
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < hw; i += (size_t)gridDim.x * blockDim.x) {
+  const unsigned wr = res_pool ? (unsigned)(w >> 1) : (unsigned)w, uw = (unsigned)w;
+  const float* g_b = g + base * 8;
+  const float* x_b = x + base * 8;
+  const float* res_b = res ? res + (size_t)ng * (res_pool ? (hw >> 2) : hw) * 8 : nullptr;
+  const float* noise_b = noise ? noise + (size_t)nidx * hw : nullptr;
+  float* of_b = out_f32b ? out_f32b + base * 8 : nullptr;
+  const size_t act_b = (size_t)ng * planes * hw;
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)hw; i += stride) {
     float gv[8], xv[8], v[8];
-    load8_f32b(g, base + i, gv);
-    load8_f32b(x, base + i, xv);
+    load8_f32b(g_b, i, gv);
+    load8_f32b(x_b, i, xv);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float xc = xv[k] - m[k];
       v[k] = r[k] * gs[k] * (gv[k] - a[k] - xc * r[k] * b[k]) + cm[k] + cs[k] * xc;
     }
     if (mode == 0) {
-      if (res) {
-        size_t ri = i;
+      if (res_b) {
+        unsigned ri = i;
         if (res_pool) {
-          const int y = (int)(i / w), xx = (int)(i - (size_t)y * w);
-          ri = (size_t)(y >> 1) * wr + (xx >> 1);
+          const unsigned y = i / uw, xx = i - y * uw;
+          ri = (y >> 1) * wr + (xx >> 1);
         }
         float rv[8];
-        load8_f32b(res, rbase + ri, rv);
+        load8_f32b(res_b, ri, rv);
 #pragma unroll
         for (int k = 0; k < 8; ++k) v[k] = fmaf(rscale, rv[k], v[k]);
       }
-      store8_f32b(out_f32b, base + i, v);
+      store8_f32b(of_b, i, v);
     } else {
-      const float nz = noise ? __ldg(noise + (size_t)nidx * hw + i) : 0.f;
+      const float nz = noise_b ? __ldg(noise_b + i) : 0.f;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         v[k] = xv[k] > 0.f ? v[k] : v[k] * slope;
         acc[k] += v[k];
         acc[8 + k] = fmaf(v[k], nz, acc[8 + k]);
       }
-      if (out_act) store8_act_at(out_act, (size_t)ng * planes * hw + i, hw, planes, v);
-      if (out_f32b) store8_f32b(out_f32b, base + i, v);
+      if (out_act) store8_act_at(out_act, act_b + i, hw, planes, v);
+      if (of_b) store8_f32b(of_b, i, v);
     }
   }
   if (mode == 1) {
