@@ -475,31 +475,34 @@ k_sg2_layer_bwd(const __grid_constant__ Sg2BwdParams p) {
 // ---------------------------------------------------------------------------------------------
 // box != 0: the 2x2 box sum of the StyleGAN1 `transform_kernel` layers instead (dge_sg1_post mode 1, lreq.py:127-131):
 //   dt[u][v] = sum_{a,b<2} dconv[u-a][v-b].
+// weights of window rows / columns 2Y-2 .. 2Y+2 for the even (0) and odd (1) phase: compile-time constants, so the taps
+// with a zero weight cost nothing (BOX: 2 of 5 per phase, FIR: 4 of 5)
+template <bool BOX>
+__device__ __forceinline__ constexpr float s2d_w(int q, int j) {
+  return BOX ? ((j == 1 + q || j == 2 + q) ? 1.f : 0.f)
+             : ((j == 0 + q || j == 3 + q) ? 0.25f : ((j == 1 + q || j == 2 + q) ? 0.75f : 0.f));
+}
+
+template <bool BOX>
 __global__ void __launch_bounds__(TB_THREADS)
-k_up_fir_bwd_s2d(const float* __restrict__ dconv, void* __restrict__ out, int n, int c, int H, int W, int planes,
-                 int box) {
+k_up_fir_bwd_s2d(const float* __restrict__ dconv, void* __restrict__ out, int n, int c, int H, int W, int planes) {
   const int C8 = c >> 3, Hs = H + 1, Ws = W + 1, Ho = 2 * H, Wo = 2 * W;
   const size_t total = (size_t)n * C8 * Hs * Ws;
-  // weights of window rows / columns 2Y-2 .. 2Y+2 for the even (0) and odd (1) phase
-  const float wfir[2][5] = {{0.25f, 0.75f, 0.75f, 0.25f, 0.f}, {0.f, 0.25f, 0.75f, 0.75f, 0.25f}};
-  const float wbox[2][5] = {{0.f, 1.f, 1.f, 0.f, 0.f}, {0.f, 0.f, 1.f, 1.f, 0.f}};
-  float wv[2][5];
-#pragma unroll
-  for (int q = 0; q < 2; ++q)
-#pragma unroll
-    for (int j = 0; j < 5; ++j) wv[q][j] = box ? wbox[q][j] : wfir[q][j];
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int X = (int)(i % Ws);
-    size_t t = i / Ws;
-    const int Y = (int)(t % Hs);
-    t /= Hs;
-    const int g = (int)(t % C8), nidx = (int)(t / C8);
+  // (32-bit index arithmetic: the host checks total < 2^31; three 64-bit divisions per thread cost more than the filter)
+  const unsigned uWs = (unsigned)Ws, uHs = (unsigned)Hs, uC8 = (unsigned)C8, stride = gridDim.x * blockDim.x;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)total; i += stride) {
+    unsigned t = i / uWs;
+    const int X = (int)(i - t * uWs);
+    const unsigned t2 = t / uHs;
+    const int Y = (int)(t - t2 * uHs);
+    const unsigned nq = t2 / uC8;
+    const int g = (int)(t2 - nq * uC8), nidx = (int)nq;
     float o[4][8];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
 #pragma unroll
       for (int k = 0; k < 8; ++k) o[q][k] = 0.f;
-    const size_t base = ((size_t)nidx * C8 + g) * Ho * (size_t)Wo;
+    const float* src = dconv + ((size_t)nidx * C8 + g) * Ho * (size_t)Wo * 8;
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
       const int r = 2 * Y - 2 + j;
@@ -512,19 +515,23 @@ k_up_fir_bwd_s2d(const float* __restrict__ dconv, void* __restrict__ out, int n,
         const int cc = 2 * X - 2 + b;
         if (cc < 0 || cc >= Wo) continue;
         float v[8];
-        load8_f32b(dconv, base + (size_t)r * Wo + cc, v);
+        load8_f32b(src, (unsigned)(r * Wo + cc), v);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          h0[k] = fmaf(wv[0][b], v[k], h0[k]);
-          h1[k] = fmaf(wv[1][b], v[k], h1[k]);
+          if (s2d_w<BOX>(0, b) != 0.f) h0[k] = fmaf(s2d_w<BOX>(0, b), v[k], h0[k]);
+          if (s2d_w<BOX>(1, b) != 0.f) h1[k] = fmaf(s2d_w<BOX>(1, b), v[k], h1[k]);
         }
       }
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        o[0][k] = fmaf(wv[0][j], h0[k], o[0][k]);
-        o[1][k] = fmaf(wv[0][j], h1[k], o[1][k]);
-        o[2][k] = fmaf(wv[1][j], h0[k], o[2][k]);
-        o[3][k] = fmaf(wv[1][j], h1[k], o[3][k]);
+        if (s2d_w<BOX>(0, j) != 0.f) {
+          o[0][k] = fmaf(s2d_w<BOX>(0, j), h0[k], o[0][k]);
+          o[1][k] = fmaf(s2d_w<BOX>(0, j), h1[k], o[1][k]);
+        }
+        if (s2d_w<BOX>(1, j) != 0.f) {
+          o[2][k] = fmaf(s2d_w<BOX>(1, j), h0[k], o[2][k]);
+          o[3][k] = fmaf(s2d_w<BOX>(1, j), h1[k], o[3][k]);
+        }
       }
     }
     const size_t hws = (size_t)Hs * Ws, pix = (size_t)Y * Ws + X;
@@ -976,9 +983,12 @@ extern "C" int dge_up_fir_bwd_s2d(const float* dconv, void* out_act, int n, int 
   DGE_REQUIRE(n > 0 && c >= 16 && c % 16 == 0 && h > 0 && w > 0, "up_fir_bwd_s2d: bad dims n=%d c=%d h=%d w=%d", n, c, h, w);
   DGE_REQUIRE(planes == 1 || planes == 2, "up_fir_bwd_s2d: planes=%d", planes);
   const size_t work = (size_t)n * (c / 8) * (h + 1) * (w + 1);
+  DGE_REQUIRE(work < (1ull << 31) && (size_t)4 * h * w < (1ull << 31),
+              "up_fir_bwd_s2d: map too large for 32-bit indexing (n=%d c=%d h=%d w=%d)", n, c, h, w);
   size_t g = (work + TB_THREADS - 1) / TB_THREADS;
   if (g > (size_t)tb_sms() * 32) g = (size_t)tb_sms() * 32;
-  k_up_fir_bwd_s2d<<<(int)g, TB_THREADS, 0, TB_STREAM>>>(dconv, out_act, n, c, h, w, planes, box);
+  if (box) k_up_fir_bwd_s2d<true><<<(int)g, TB_THREADS, 0, TB_STREAM>>>(dconv, out_act, n, c, h, w, planes);
+  else k_up_fir_bwd_s2d<false><<<(int)g, TB_THREADS, 0, TB_STREAM>>>(dconv, out_act, n, c, h, w, planes);
   count_launch();
   return check_launch("k_up_fir_bwd_s2d");
 }
