@@ -44,35 +44,41 @@ def _operands(model, planes):
     return val
 
 
+def _forward_chain(model, in0, in1, planes, keep_all=True):
+    """The fused forward: -> (distance [N], saved activations (every conv's output; only the five taps if not keep_all))."""
+    n = in0.shape[0]
+    fwd, bwd, bias, lin, (shift, scale) = _operands(model, planes)
+    x = torch.cat((in0.detach().float(), in1.detach().float()), dim=0).contiguous()
+    act = K.lpips_input(x, shift, scale, planes)
+    out = torch.zeros(n, dtype=torch.float32, device=x.device)
+    saved = []                      # saved[i]: the activated output of conv i (Act, or F32B at a tap)
+    i = 0
+    for k, idxs in enumerate(_VGG):
+        for j in range(len(idxs)):
+            last = j == len(idxs) - 1
+            cout = bias[i].numel()
+            r = K.conv(act, fwd[i], cout, K.CONV_3X3, bias=bias[i], slope=0.0, out_act=not last, out_f32b=last)
+            if last:
+                f = r['f32b']
+                saved.append(f)
+                K.lpips_dist(f, lin[k], out)
+                if k < 4:
+                    act = K.maxpool_to_act(f, planes)
+            else:
+                act = r['act']
+                if keep_all:
+                    saved.append(act)
+            i += 1
+    return out, saved
+
+
 class _LpipsFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, in0, in1, model, planes):
         n = in0.shape[0]
-        fwd, bwd, bias, lin, (shift, scale) = _operands(model, planes)
-        x = torch.cat((in0.detach().float(), in1.detach().float()), dim=0).contiguous()
-        act = K.lpips_input(x, shift, scale, planes)
-        out = torch.zeros(n, dtype=torch.float32, device=x.device)
-        saved, taps = [], []        # saved[i]: the activated output of conv i (Act, or F32B at a tap)
-        i = 0
-        for k, idxs in enumerate(_VGG):
-            for j in range(len(idxs)):
-                last = j == len(idxs) - 1
-                cout = bias[i].numel()
-                r = K.conv(act, fwd[i], cout, K.CONV_3X3, bias=bias[i], slope=0.0, out_act=not last, out_f32b=last)
-                if last:
-                    f = r['f32b']
-                    saved.append(f)
-                    taps.append(f)
-                    K.lpips_dist(f, lin[k], out)
-                    if k < 4:
-                        act = K.maxpool_to_act(f, planes)
-                else:
-                    act = r['act']
-                    saved.append(act)
-                i += 1
+        out, saved = _forward_chain(model, in0, in1, planes)
         ctx.model, ctx.planes, ctx.n = model, planes, n
         ctx.saved = saved
-        ctx.img_hw = x.shape[2:]
         return out.view(n, 1, 1, 1)
 
     @staticmethod
@@ -112,6 +118,44 @@ class _LpipsFn(torch.autograd.Function):
             g = g_in.to_nchw()[:, :3] / sl.scale.to(g_in.t.device)                      # ScalingLayer: (x - shift) / scale
             grads[half] = g.contiguous()
         return grads[0], grads[1], None, None
+
+
+class _LpipsLinOnlyFn(torch.autograd.Function):
+    """The distance of two images that carry NO gradient, as a function of the module's five `lin` weights only.  The
+    package's result requires grad through those weights even then, and some of the scripts call backward() on exactly
+    such losses (E_mis_align_cropping_s1.py:171-193, E_align_cropping_s1.py:185-206, embedding_img.py:96-112).  Forward = the
+    fused chain; backward = d out[n] / d w_k[c] = mean_p (a_c/|a| - b_c/|b|)^2 from the five saved taps (torch reductions:
+    nobody's optimiser holds these weights, the path only has to exist and be right)."""
+
+    @staticmethod
+    def forward(ctx, model, in0, in1, planes, *lin_w):
+        n = in0.shape[0]
+        out, taps = _forward_chain(model, in0, in1, planes, keep_all=False)
+        ctx.n, ctx.taps, ctx.shapes = n, taps, [w.shape for w in lin_w]
+        return out.view(n, 1, 1, 1)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, go):
+        n = ctx.n
+        go = go.reshape(n, 1).float()
+        grads = []
+        for tap, shape, need in zip(ctx.taps, ctx.shapes, ctx.needs_input_grad[4:]):
+            if not need:
+                grads.append(None)
+                continue
+            f = tap.to_nchw()
+            a, b = f[:n], f[n:]
+            na = a.pow(2).sum(dim=1, keepdim=True).sqrt() + 1e-10         # lpips.normalize_tensor
+            nb = b.pow(2).sum(dim=1, keepdim=True).sqrt() + 1e-10
+            s = (a / na - b / nb).pow(2).mean(dim=(2, 3))                 # [n, C]
+            grads.append((go * s).sum(dim=0).reshape(shape))
+        return (None, None, None, None, *grads)
+
+
+def distance_lin_only(model, in0, in1, planes=2):
+    """[N, 1, 1, 1] distance of gradient-free images, differentiable w.r.t. the module's `lin` weights."""
+    return _LpipsLinOnlyFn.apply(model, in0, in1, planes, *[model.lins[k].model[1].weight for k in range(5)])
 
 
 def distance(model, in0, in1, planes=2):

@@ -198,15 +198,17 @@ class LPIPS(nn.Module):
         frozen = not self.pnet_tune and not self.training
         # ... but when NEITHER image carries a gradient the package's result still requires grad through its `lin` weights,
         # and E_mis_align_cropping_s1.py:187-193 relies on exactly that (it calls backward() on losses of detached clones):
-        # that case takes the torch-node graph, which records the `lin` layers
+        # that case is a second node with the same fused forward whose backward returns the `lin` gradients
         lin_only = torch.is_grad_enabled() and not (in0.requires_grad or in1.requires_grad) and \
             any(p.requires_grad for p in self.lins.parameters())
-        if FUSED and frozen and not lin_only and not retPerLayer and in0.shape == in1.shape and in0.shape[1] == 3 \
+        if FUSED and frozen and not retPerLayer and in0.shape == in1.shape and in0.shape[1] == 3 \
                 and min(in0.shape[2:]) >= 32:
             # one fused autograd node (dge_b200/train_lpips.py): convs with bias + ReLU epilogues, tap distances and the
             # whole backward on dge_b200 kernels
             if normalize:
                 in0, in1 = 2 * in0 - 1, 2 * in1 - 1
+            if lin_only:
+                return train_lpips.distance_lin_only(self, in0, in1, self.net.planes)
             return train_lpips.distance(self, in0, in1, self.net.planes)
         return self._distance(in0, in1, retPerLayer, normalize)
 

@@ -124,3 +124,17 @@ def test_space_loss_of_detached_images_still_reaches_the_lpips_module():
         loss0, info0 = tu.space_loss(a, b, lpips_model=lp)
     assert not loss0.requires_grad
     assert abs(float(loss) - float(loss0)) <= 1e-5 * abs(float(loss0)) and abs(info[4] - info0[4]) <= 1e-5 * abs(info0[4]) + 1e-9
+    # the `lin` gradients of the fused node (dge_b200/train_lpips.py::_LpipsLinOnlyFn) = those of the graph of torch nodes
+    fused = [gr.clone() for gr in grads]
+    for p in lp.lins.parameters():
+        p.grad = None
+    lpips.FUSED = False
+    try:
+        loss_u, _ = tu.space_loss(a.detach().clone(), b.detach().clone(), lpips_model=lp)
+        loss_u.backward()
+    finally:
+        lpips.FUSED = True
+    for gf, p in zip(fused, lp.lins.parameters()):
+        # (mean of squared DIFFERENCES of unit-normalised features of two random-VGG maps: the two evaluation orders differ
+        #  by ~2e-3 of these 1e-9-sized values)
+        assert ((gf - p.grad).abs().max() / p.grad.abs().max().clamp_min(1e-20)).item() < 1e-2
