@@ -896,26 +896,54 @@ __global__ void k_cbn_coeffs(const float* __restrict__ scale, const float* __res
   }
 }
 
-__global__ void k_affine_act(const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b,
-                             int relu, int up, void* __restrict__ out_act, float* __restrict__ out_f32b, int n, int c,
-                             int h, int w, int planes) {
-  const int C8 = c >> 3;
-  const size_t total = (size_t)n * C8 * h * w;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const Idx4 q = decode4(i, C8, h, w);
+// grid = (splits, n * C/8): a block owns one (sample, 8-channel group), keeps its 16 coefficients in registers and walks its
+// pixels with 32-bit indices (the flat form spent most of its instructions on three 64-bit divisions, 16 coefficient loads
+// and the output index products per element and stayed at 74 % of the copy bandwidth).
+__global__ void __launch_bounds__(256)
+k_affine_act(const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b, int relu, int up,
+             void* __restrict__ out_act, float* __restrict__ out_f32b, int c, int h, int w, int planes) {
+  const int C8 = c >> 3, ng = blockIdx.y, nidx = ng / C8, grp = ng - nidx * C8;
+  float av[8], bv[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    av[k] = __ldg(a + (size_t)nidx * c + grp * 8 + k);
+    bv[k] = __ldg(b + (size_t)nidx * c + grp * 8 + k);
+  }
+  const unsigned hw = (unsigned)(h * w), uw = (unsigned)w, ow = (unsigned)(w * up), ohw = hw * (unsigned)(up * up);
+  const float* xb = x + (size_t)ng * hw * 8;
+  float* fb = out_f32b ? out_f32b + (size_t)ng * ohw * 8 : nullptr;
+  uint4* ab = out_act ? reinterpret_cast<uint4*>(out_act) + (size_t)ng * planes * ohw : nullptr;
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += stride) {
     float v[8];
-    load8_f32b(x, i, v);
+    load8_f32b(xb, i, v);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const size_t s = (size_t)q.n * c + q.g * 8 + k;
-      float t = fmaf(v[k], __ldg(a + s), __ldg(b + s));
+      const float t = fmaf(v[k], av[k], bv[k]);
       v[k] = (relu && t < 0.f) ? 0.f : t;
     }
-    for (int dy = 0; dy < up; ++dy)
-      for (int dx = 0; dx < up; ++dx) {
-        if (out_f32b) store8_f32b(out_f32b, f32b_idx32(q.n, q.g, q.y * up + dy, q.x * up + dx, C8, h * up, w * up), v);
-        if (out_act) store8_act(out_act, q.n, q.g, q.y * up + dy, q.x * up + dx, C8, planes, h * up, w * up, v);
+    if (up == 1) {
+      if (fb) store8_f32b(fb, i, v);
+      if (ab) {
+        uint4 hi, lo;
+        split8(v, hi, lo);
+        ab[i] = hi;
+        if (planes == 2) ab[i + ohw] = lo;
       }
+    } else {
+      const unsigned y = i / uw, xx = i - y * uw;
+      uint4 hi, lo;
+      if (ab) split8(v, hi, lo);
+      for (int dy = 0; dy < up; ++dy)
+        for (int dx = 0; dx < up; ++dx) {
+          const unsigned o = (y * up + dy) * ow + xx * up + dx;
+          if (fb) store8_f32b(fb, o, v);
+          if (ab) {
+            ab[o] = hi;
+            if (planes == 2) ab[o + ohw] = lo;
+          }
+        }
+    }
   }
 }
 
@@ -1801,7 +1829,19 @@ int dge_affine_act(const float* x, const float* a, const float* b, int relu, int
   DGE_REQUIRE(x && a && b && (out_act || out_f32b), "affine_act: null pointer");
   REQ_NCHW("affine_act");
   DGE_REQUIRE((up == 1 || up == 2) && (!out_act || planes == 1 || planes == 2), "affine_act: up=%d planes=%d", up, planes);
-  LAUNCH_1D(k_affine_act, (size_t)n * (c / 8) * h * w, stream, x, a, b, relu, up, out_act, out_f32b, n, c, h, w, planes);
+  DGE_REQUIRE((long long)h * w * up * up < (1ll << 31), "affine_act: map too large for 32-bit indexing (h=%d w=%d)", h, w);
+  {
+    const long long groups = (long long)n * (c / 8), pixels = (long long)h * w;
+    long long splits = (148ll * 12 + groups - 1) / groups, cap = (pixels + 255) / 256;
+    if (splits > cap) splits = cap;
+    if (splits < 1) splits = 1;
+    if (splits > 65535) splits = 65535;
+    DGE_REQUIRE(groups <= 65535, "affine_act: n * c / 8 = %lld exceeds the grid limit", groups);
+    dim3 grid((unsigned)splits, (unsigned)groups);
+    k_affine_act<<<grid, 256, 0, (cudaStream_t)stream>>>(x, a, b, relu, up, out_act, out_f32b, c, h, w, planes);
+    count_launch();
+    return check_launch("k_affine_act");
+  }
 }
 int dge_maxpool2_f32b(const float* x, float* out, int n, int c, int h_out, int w_out, void* stream) {
   DGE_REQUIRE(x && out && n > 0 && c > 0 && c % 8 == 0 && h_out > 0 && w_out > 0, "maxpool2_f32b: bad args");
