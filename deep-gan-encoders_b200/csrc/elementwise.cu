@@ -914,8 +914,10 @@ __global__ void k_cbn_coeffs(const float* __restrict__ scale, const float* __res
 // and the output index products per element and stayed at 74 % of the copy bandwidth).
 __global__ void __launch_bounds__(256)
 k_affine_act(const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b, int relu, int up,
-             void* __restrict__ out_act, float* __restrict__ out_f32b, int c, int h, int w, int planes) {
-  const int C8 = c >> 3, ng = blockIdx.y, nidx = ng / C8, grp = ng - nidx * C8;
+             void* __restrict__ out_act, float* __restrict__ out_f32b, int groups, int c, int h, int w, int planes) {
+  const int C8 = c >> 3;
+  for (int ng = blockIdx.y; ng < groups; ng += gridDim.y) {      // (grid.y is capped at 65535)
+  const int nidx = ng / C8, grp = ng - nidx * C8;
   float av[8], bv[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -957,6 +959,7 @@ k_affine_act(const float* __restrict__ x, const float* __restrict__ a, const flo
           }
         }
     }
+  }
   }
 }
 
@@ -1849,9 +1852,9 @@ int dge_affine_act(const float* x, const float* a, const float* b, int relu, int
     if (splits > cap) splits = cap;
     if (splits < 1) splits = 1;
     if (splits > 65535) splits = 65535;
-    DGE_REQUIRE(groups <= 65535, "affine_act: n * c / 8 = %lld exceeds the grid limit", groups);
-    dim3 grid((unsigned)splits, (unsigned)groups);
-    k_affine_act<<<grid, 256, 0, (cudaStream_t)stream>>>(x, a, b, relu, up, out_act, out_f32b, c, h, w, planes);
+    DGE_REQUIRE(groups < (1ll << 31), "affine_act: too many (sample, channel group) pairs (%lld)", groups);
+    dim3 grid((unsigned)splits, (unsigned)(groups < 65535 ? groups : 65535));
+    k_affine_act<<<grid, 256, 0, (cudaStream_t)stream>>>(x, a, b, relu, up, out_act, out_f32b, (int)groups, c, h, w, planes);
     count_launch();
     return check_launch("k_affine_act");
   }
