@@ -302,7 +302,7 @@ extern "C" int dge_conv_wgrad(const void* dy_act, const void* x_act, float* dw, 
   // atomics over dW per chunk (~200 G atomics/s) plus the memset.
   const int ksteps_tile = p.rowpair ? p.th / 2 : p.th * (p.tw / 16);
   const double pass_us = (double)cout * cin * ksize * ksize / 200e3;
-  auto predict = [&](int nblk, int mma_n, double mmas_kstep, int blocks_y, int ncols, int* chunks_out) {
+  auto predict = [&](int mma_n, double mmas_kstep, int blocks_y, int ncols, int* chunks_out) {
     const double clk_mma = mma_n / 2 > 64 ? mma_n / 2 : 64;
     const double cta_us = (double)p.tiles_total * ksteps_tile * mmas_kstep * clk_mma / 1900.0;
     const double epi_us = 7.0 + 45.0 * ncols / 384.0;
@@ -319,7 +319,6 @@ extern "C" int dge_conv_wgrad(const void* dy_act, const void* x_act, float* dw, 
         chunks = c;
       }
     }
-    (void)nblk;
     *chunks_out = chunks;
     return best;
   };
@@ -330,8 +329,8 @@ extern "C" int dge_conv_wgrad(const void* dy_act, const void* x_act, float* dw, 
     if (nblk_env < 0) nblk_env = getenv("DGE_WGRAD_NBLK") ? atoi(getenv("DGE_WGRAD_NBLK")) : 0;      // A/B switch
     const int cob_n = (cout + 127) / 128;
     int c128, c64;
-    const double t128 = predict(128, 128, split_mmas * ksize, ksize * cob_n * ((cin + 127) / 128), ksize * 128, &c128);
-    const double t64 = predict(64, 64, split_mmas * ksize, ksize * cob_n * ((cin + 63) / 64), ksize * 64, &c64);
+    const double t128 = predict(128, split_mmas * ksize, ksize * cob_n * ((cin + 127) / 128), ksize * 128, &c128);
+    const double t64 = predict(64, split_mmas * ksize, ksize * cob_n * ((cin + 63) / 64), ksize * 64, &c64);
     if (nblk_env == 64 || nblk_env == 128) p.nblk = nblk_env;
     else if (t64 < t128) p.nblk = 64;
   }
@@ -362,7 +361,7 @@ extern "C" int dge_conv_wgrad(const void* dy_act, const void* x_act, float* dw, 
   // split of the contraction: c chunks shorten every CTA's MMA loop by c but each adds one pass of fp32 atomics over dW
   // (~200 G atomics/s measured); with one chunk the CTA owns its dW block and stores it (no memset, no atomics).
   int chunks = 1;
-  predict(p.nblk, p.stacked ? p.n1 : p.nblk, split_mmas * (p.stacked ? (p.n2 ? 2 : 1) : p.taps_x), blocks_y,
+  predict(p.stacked ? p.n1 : p.nblk, split_mmas * (p.stacked ? (p.n2 ? 2 : 1) : p.taps_x), blocks_y,
           (p.stacked ? 9 : p.taps_x) * p.nblk, &chunks);
   p.chunks = chunks;
   p.atomic = chunks > 1;
