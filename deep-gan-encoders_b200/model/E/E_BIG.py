@@ -6,9 +6,10 @@ Block (reference order kept): CBN1 (no activation; running stats ar
 -> conv_1 -> noise, bias, lrelu -> CBN2 -> conv_2 -> noise, bias, lrelu [-> lrelu AGAIN when channels change, :163]
 -> + residual (conv_3(CBN3(x)) when channels change) -> 2x2 avg-pool.  `truncation` is hard-wired to 0.4 (:222).
 
-Training: as in `model/E/E.py` -- a call that must be recorded for backward builds a differentiable graph whose 3x3 /
-1x1 convs run forward / data-gradient / weight-gradient on the tcgen05 kernels; the conditional-BN affines (whose
-spectral-norm `scale` / `offset` layers are trainable here) and the point-wise steps are torch CUDA ops in this build.
+Training: as in `model/E/E.py` -- a call that must be recorded for backward runs ONE fused autograd node per block
+(`dge_b200/train_big.py`, `FUSED_TRAIN`): the conditional-BN affines enter the node as [N, C] coefficient tensors, so the
+trainable spectral-norm `scale` / `offset` layers (and their power iteration) stay small torch graphs around it.
+`_forward_autograd` -- separate torch nodes with the convs on the tcgen05 kernels -- is kept as the cross-check.
 """
 import torch
 import torch.nn as nn

@@ -7,9 +7,10 @@ Kernels: the instance-norm apply, the blur and (for the strided blocks) a space-
 (`dge_instance_norm_blur`); the strided conv runs on the tensor cores as a 16-tap conv over the 4 input phases
 (`DGE_CONV_DOWN4X4S2`), exact at the borders (the blurred intermediate is zero-padded).
 
-Training: as in `model/E/E.py`, a call that must be recorded for backward builds a differentiable graph whose stride-1
-3x3 / 1x1 convs run forward / data-gradient / weight-gradient on the tcgen05 kernels; the stride-2 `transform_kernel`
-conv of the first four blocks, the blur and the point-wise steps are torch CUDA ops in this build.
+Training: as in `model/E/E.py`, a call that must be recorded for backward runs ONE fused autograd node per block
+(`dge_b200/train_e.py`, `FUSED_TRAIN`): the blur is its own transpose, and both gradients of the stride-2 `transform_kernel`
+conv are a stride-1 3x3 conv over the space-to-depth operand the forward already wrote.  `_forward_autograd` -- the graph of
+separate torch nodes (cuDNN for the blur and the strided conv) -- is kept as the cross-check (`FUSED_TRAIN = False`).
 """
 import torch
 import torch.nn as nn

@@ -14,10 +14,11 @@ dge_b200 kernel:
 `truncation` follows the reference's Python arithmetic (`math.modf(truncation / step)`), tensors included.
 
 Training (E_align_s2.py:162, mtype 4: `generator(w2, conditions, truncation)` with w2 from the encoder under autograd):
-when `z` requires grad, `BigGAN.forward` records a differentiable graph w.r.t. `z` (`_forward_autograd`); the generator
-is frozen (its effective spectral-norm weights enter as constants), the 1x1 / 3x3 convs whose channel counts are
-multiples of 16 run forward and backward on the tcgen05 kernels (dge_b200.autograd.conv2d), the conditional-BN
-affines, the attention products and the remaining point-wise steps are torch CUDA ops in this build.
+when `z` requires grad, `BigGAN.forward` records a differentiable graph w.r.t. `z`; the generator is frozen (its effective
+spectral-norm weights enter as constants).  `FUSED_TRAIN`: one autograd node per GenBlock and one for the RGB tail
+(`dge_b200/train_big.py`): forward = the inference kernel chain, backward = 4 x [data-gradient conv -> `dge_affine_relu_bwd`];
+the [N, C] conditional-BN coefficients and the attention block stay torch graphs.  Channel counts that are not multiples
+of 16 (toy widths) and `FUSED_TRAIN = False` take the graph of separate torch nodes with tcgen05 convs (`_forward_autograd`).
 """
 import math
 
