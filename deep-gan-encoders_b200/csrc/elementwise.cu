@@ -205,6 +205,56 @@ k_sg2_prep(const dge_sg2_prep_item* __restrict__ items, const float* __restrict_
   }
 }
 
+// Transpose of k_sg2_prep (training: the frozen generator's gradient w.r.t. wp).  Block = (item, sample).
+//   layer item : ds[c] = S[c] - style[c] * sum_o (D[o] * demod[o]^2) * w2[o][c]      (S = d style, D = demod * d demod)
+//   ToRGB item : ds[c] = sum_j T[c][j] * rgb_w[j][c] * rgb_scale                       (T = d of the modulated ToRGB weights)
+//   d_wp[n][wp_index][k] += st_wscale * sum_c ds[c] * st_w[c][k]
+// gsrc[item] = (s_off, s_stride, d_off, t_off): float offsets into `sums` (-1 = absent)
+__global__ void __launch_bounds__(256)
+k_sg2_prep_bwd(const dge_sg2_prep_item* __restrict__ items, const float* __restrict__ arena,
+               const long long* __restrict__ gsrc, const float* __restrict__ sums, float* __restrict__ d_wp,
+               int num_layers, int wdim) {
+  __shared__ float s_q[2048];
+  __shared__ float s_ds[2048];
+  const dge_sg2_prep_item it = items[blockIdx.x];
+  const int n = blockIdx.y;
+  const long long s_off = gsrc[4 * blockIdx.x], s_stride = gsrc[4 * blockIdx.x + 1], d_off = gsrc[4 * blockIdx.x + 2],
+                  t_off = gsrc[4 * blockIdx.x + 3];
+  if (t_off >= 0) {
+    for (int c = threadIdx.x; c < it.cin; c += blockDim.x) {
+      float ds = 0.f;
+      for (int j = 0; j < it.nch; ++j)
+        ds = fmaf(__ldg(sums + t_off + ((size_t)n * it.cin + c) * 5 + j), __ldg(it.rgb_w + (size_t)j * it.cin + c), ds);
+      s_ds[c] = ds * it.rgb_scale;
+    }
+  } else {
+    const bool dem = it.w2 && d_off >= 0 && it.demod_off >= 0;
+    if (dem) {
+      for (int o = threadIdx.x; o < it.cout; o += blockDim.x) {
+        const float dm = arena[it.demod_off + (size_t)n * it.cout + o];
+        s_q[o] = __ldg(sums + d_off + ((size_t)n * it.cout + o) * 5) * dm * dm;
+      }
+      __syncthreads();
+    }
+    for (int c = threadIdx.x; c < it.cin; c += blockDim.x) {
+      float ds = s_off >= 0 ? __ldg(sums + s_off + ((size_t)n * it.cin + c) * s_stride) : 0.f;
+      if (dem) {
+        float r = 0.f;
+        for (int o = 0; o < it.cout; ++o) r = fmaf(s_q[o], __ldg(it.w2 + (size_t)o * it.cin + c), r);
+        ds -= arena[it.style_off + (size_t)n * it.cin + c] * r;
+      }
+      s_ds[c] = ds;
+    }
+  }
+  __syncthreads();
+  float* dst = d_wp + ((size_t)n * num_layers + it.wp_index) * wdim;
+  for (int k = threadIdx.x; k < wdim; k += blockDim.x) {
+    float acc = 0.f;
+    for (int c = 0; c < it.cin; ++c) acc = fmaf(s_ds[c], __ldg(it.st_w + (size_t)c * wdim + k), acc);
+    atomicAdd(dst + k, acc * it.st_wscale);      // a layer and the ToRGB that shares its wp row both land here
+  }
+}
+
 __global__ void k_pixel_norm(const float* __restrict__ x, float* __restrict__ y, int n, int k, float eps) {
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
@@ -1657,6 +1707,21 @@ int dge_sg2_prep(const dge_sg2_prep_item* items, int n_items, const float* wp, f
   k_sg2_prep<<<grid, 256, 0, (cudaStream_t)stream>>>(items, wp, arena, num_layers, wdim);
   count_launch();
   return check_launch("k_sg2_prep");
+}
+
+int dge_sg2_prep_bwd(const dge_sg2_prep_item* items, int n_items, const float* arena, const int64_t* gsrc,
+                     const float* sums, float* d_wp, int n, int num_layers, int wdim, void* stream) {
+  DGE_REQUIRE(items && arena && gsrc && sums && d_wp && n_items > 0 && n > 0 && num_layers > 0 && wdim > 0,
+              "sg2_prep_bwd: bad args");
+  cudaError_t e = cudaMemsetAsync(d_wp, 0, (size_t)n * num_layers * wdim * sizeof(float), (cudaStream_t)stream);
+  if (e != cudaSuccess) {
+    set_error("sg2_prep_bwd: cudaMemsetAsync failed: %s", cudaGetErrorString(e));
+    return DGE_ERR_CUDA;
+  }
+  dim3 grid(n_items, n);
+  k_sg2_prep_bwd<<<grid, 256, 0, (cudaStream_t)stream>>>(items, arena, (const long long*)gsrc, sums, d_wp, num_layers, wdim);
+  count_launch();
+  return check_launch("k_sg2_prep_bwd");
 }
 
 int dge_pixel_norm(const float* x, float* y, int n, int k, float eps, void* stream) {

@@ -69,6 +69,7 @@ SIGNATURES = {
     "dge_demod": (c_int, [P, P, P, c_int, c_int, c_int, c_float, P]),
     "dge_rgb_weights": (c_int, [P, P, P, c_int, c_int, c_int, c_float, P]),
     "dge_sg2_prep": (c_int, [P, c_int, P, P, c_int, c_int, c_int, P]),
+    "dge_sg2_prep_bwd": (c_int, [P, c_int, P, P, P, P, c_int, c_int, c_int, P]),
     "dge_dense": (c_int, [P, P, P, P, c_int, c_int, c_int, c_float, c_float, c_float, c_float, c_float, P]),
     "dge_pixel_norm": (c_int, [P, P, c_int, c_int, c_float, P]),
     "dge_nchw_to_act": (c_int, [P, c_int64, P, P, c_int, c_int, c_int, c_int, c_int, P]),

@@ -762,18 +762,45 @@ def from_rgb_bwd(d_f, f, img, slope=0.2, weight=None):
 
 
 def sg2_prep_all(S, wp32, layers, outputs):
-    """(styles, demods, rgb_styles, rgb_weights) of one synthesis pass: one launch (SynthesisModule._prep)."""
-    return S._prep(wp32, layers, outputs)
+    """(styles, demods, rgb_styles, rgb_weights, handle) of one synthesis pass: one launch (SynthesisModule._prep);
+    `handle` is what `sg2_prep_bwd` needs to run the transpose."""
+    return S._prep(wp32, layers, outputs, with_handle=True)
+
+
+def sg2_prep_bwd(S, handle, layers, outputs, sums, layer_offs, const_off, n):
+    """Transpose of `sg2_prep_all` in one launch (dge_sg2_prep_bwd): the reductions of the synthesis backward -> d wp
+    [n, num_layers, w_space_dim].  `sums`: one fp32 arena holding, at float offset layer_offs[i], layer i's
+    `sg2_layer_bwd` sums [n, out_c, 5] and, at const_off, the style gradient of layer 0 [n, in_c]."""
+    c = handle['cache']
+    key = (tuple(layer_offs), const_off)
+    g = c.get('gsrc')
+    if g is None or g[0] != key:
+        nl = len(layers)
+        rows = []
+        for i in range(nl):
+            s_off, s_stride = (const_off, 1) if i == 0 else (layer_offs[i - 1], 5)
+            rows.append((s_off, s_stride, layer_offs[i] + 4 if layers[i].demodulate else -1, -1))
+        for k in range(len(outputs)):
+            rows.append((-1, 0, -1, layer_offs[2 * k] + 1))
+        g = c['gsrc'] = (key, torch.tensor(rows, dtype=torch.int64).to(sums.device))
+    d_wp = torch.empty((n, S.num_layers, S.w_space_dim), dtype=torch.float32, device=sums.device)
+    with _rec("sg2_prep_bwd", (n, c['n_items'])):
+        check(lib().dge_sg2_prep_bwd(_p(c['items']), c['n_items'], _p(handle['arena']), _p(g[1]), _p(sums), _p(d_wp), n,
+                                     S.num_layers, S.w_space_dim, _stream()))
+    return d_wp
 
 
 def sg2_layer_bwd(ya, ya_scale, dxs, dimg, rgbw, noise, noise_batched, noise_scalar, bias, demod, gain, slope,
-                  out_kind="act", planes=2):
-    """Backward of a synthesis layer's epilogue + its consumers -> (d_conv as Act | F32B, sums fp32 [n, c, 5])."""
+                  out_kind="act", planes=2, sums=None):
+    """Backward of a synthesis layer's epilogue + its consumers -> (d_conv as Act | F32B, sums fp32 [n, c, 5]);
+    `sums`: a contiguous [n, c, 5] fp32 destination (a slice of the arena `sg2_prep_bwd` reads), else allocated."""
     assert isinstance(ya, Act) and (dxs is None or (isinstance(dxs, F32B) and (dxs.n, dxs.c, dxs.h, dxs.w) ==
                                                     (ya.n, ya.c, ya.h, ya.w)))
     dev = ya.t.device
     out = Act(ya.n, ya.c, ya.h, ya.w, planes, dev) if out_kind == "act" else F32B(ya.n, ya.c, ya.h, ya.w, dev)
-    sums = torch.empty((ya.n, ya.c, 5), dtype=torch.float32, device=dev)
+    if sums is None:
+        sums = torch.empty((ya.n, ya.c, 5), dtype=torch.float32, device=dev)
+    assert sums.shape == (ya.n, ya.c, 5) and sums.is_contiguous() and sums.dtype == torch.float32
     di = None if dimg is None else dimg.contiguous()
     with _rec("sg2_layer_bwd", (ya.n, ya.h, ya.w, ya.c, out_kind)):
         check(lib().dge_sg2_layer_bwd(

@@ -14,8 +14,9 @@ the last layer's output.  Backward, per layer from the top (csrc/train_bwd.cu):
                      3x3 conv that inverts the transposed conv, as 9 of 16 taps over the space-to-depth map
     rgb_up_bwd       transpose of the skip image's x2 up-sampling
 
-and finally a handful of [N, C] x [C, 512] products that turn the per-layer sums into d wp (style affine :872-877,
-demodulation :867-870, ToRGB modulation :462-474).  `K` is the kernel namespace (see train_e.py).
+and finally ONE launch (sg2_prep_bwd, the transpose of the forward's sg2_prep) that turns the per-layer sums into d wp
+(style affine :872-877, demodulation :867-870, ToRGB modulation :462-474): every layer's sums land in one arena whose
+offsets the kernel's item table knows.  `K` is the kernel namespace (see train_e.py).
 """
 import torch
 from torch.autograd.function import once_differentiable
@@ -71,7 +72,7 @@ class _SynthesisFn(torch.autograd.Function):
         nl = S.num_layers
         layers = [getattr(S, f'layer{i}') for i in range(nl - 1)]
         outputs = [getattr(S, f'output{k}') for k in range(nl // 2)]
-        styles, demods, rgb_styles, rgb_ws = K.sg2_prep_all(S, wp32.contiguous(), layers, outputs)
+        styles, demods, rgb_styles, rgb_ws, prep = K.sg2_prep_all(S, wp32.contiguous(), layers, outputs)
         planes = layers[0].planes
         const = S.early_layer.const.detach().float()
         xa = K.nchw_to_act(const, scale=styles[0], planes=planes, batch=n)                        # :630-632
@@ -102,7 +103,7 @@ class _SynthesisFn(torch.autograd.Function):
         ctx.S, ctx.geom = S, (n, nl, planes)
         ctx.noises = noises
         ctx.acts = xas + [y_last]
-        ctx.tabs = (styles, demods, rgb_styles, rgb_ws)
+        ctx.tabs = (styles, demods, rgb_styles, rgb_ws, prep)
         ctx.mark_non_differentiable(*styles, *rgb_styles)
         return (image,) + tuple(styles) + tuple(rgb_styles)
 
@@ -111,7 +112,7 @@ class _SynthesisFn(torch.autograd.Function):
     def backward(ctx, d_image, *_unused):
         S = ctx.S
         n, nl, planes = ctx.geom
-        styles, demods, rgb_styles, rgb_ws = ctx.tabs
+        styles, demods, rgb_styles, rgb_ws, prep = ctx.tabs
         layers = [getattr(S, f'layer{i}') for i in range(nl - 1)]
         outputs = [getattr(S, f'output{k}') for k in range(nl // 2)]
         acts = ctx.acts
@@ -120,9 +121,14 @@ class _SynthesisFn(torch.autograd.Function):
         d_imgs[nk - 1] = d_image.contiguous().float()
         for k in range(nk - 1, 0, -1):                                                            # :519-522 transposed
             d_imgs[k - 1] = K.rgb_up_bwd(d_imgs[k])
-        d_style = [None] * (nl - 1)      # S: gradient of each layer's style through the modulation x * s
-        d_dm = [None] * (nl - 1)         # D: demod * gradient of demod
-        d_rgbw = [None] * nk             # T: gradient of the ToRGB weights
+        # one arena for every reduction the style gradient needs: [n, C0] (layer 0's style through x_0 = const * s_0),
+        # then per layer the [n, out_c, 5] sums of sg2_layer_bwd: 0 = d style of the NEXT layer (through x * s),
+        # 1..3 = d of the ToRGB weights, 4 = demod * d demod
+        const_off, offs, total = 0, [], n * layers[0].in_c
+        for layer in layers:
+            offs.append(total)
+            total += n * layer.out_c * 5
+        arena = torch.empty(total, dtype=torch.float32, device=d_image.device)
         dxs = None
         for i in range(nl - 2, -1, -1):
             layer = layers[i]
@@ -131,15 +137,11 @@ class _SynthesisFn(torch.autograd.Function):
             k = i // 2 if i % 2 == 0 else None
             noise, batched = ctx.noises[i]
             up = layer.use_conv2d_transpose
-            dconv, sums = K.sg2_layer_bwd(
+            dconv, _ = K.sg2_layer_bwd(
                 acts[i + 1], None if last else styles[i + 1], dxs, None if k is None else d_imgs[k],
                 None if k is None else rgb_ws[k], noise, batched, p['strength'], p['bias'], demods[i],
-                layer.activate_scale, layer.slope, out_kind='f32b' if up else 'act', planes=planes)
-            if not last:
-                d_style[i + 1] = sums[:, :, 0]
-            if k is not None:
-                d_rgbw[k] = sums[:, :, 1:4]
-            d_dm[i] = sums[:, :, 4]
+                layer.activate_scale, layer.slope, out_kind='f32b' if up else 'act', planes=planes,
+                sums=arena[offs[i]:offs[i] + n * layer.out_c * 5].view(n, layer.out_c, 5))
             if up:
                 s2d = K.up_fir_bwd_s2d(dconv, planes)
                 dxs = K.conv(s2d, _dgrad_operands(layer, planes), layer.in_c, K.CONV_DOWN4X4S2, out_f32b=True,
@@ -148,20 +150,8 @@ class _SynthesisFn(torch.autograd.Function):
                 dxs = K.conv(dconv, _dgrad_operands(layer, planes), layer.in_c, K.CONV_3X3, out_f32b=True)['f32b']
             del dconv
         const = S.early_layer.const.detach().float()
-        d_style[0] = (dxs.to_nchw() * const).sum(dim=(2, 3))                                      # x_0 = const * s_0
-        # per-layer sums -> d wp: [N, C] x [C, 512] products (style affine :872-877, 990-996)
-        d_wp = torch.zeros((n, nl, S.w_space_dim), dtype=torch.float32, device=d_image.device)
-        for i, layer in enumerate(layers):
-            ds = d_style[i]
-            if layer.demodulate:     # dm = rsqrt(sum_i W2[o][i] s_i^2 + eps): d s_i = -s_i * sum_o D[o] dm[o]^2 W2[o][i]
-                ds = ds - styles[i] * ((d_dm[i] * demods[i] * demods[i]) @ _consts(layer, planes)['w2'])
-            st = layer.style
-            d_wp[:, i] += ds @ (st.weight.detach() * st.wscale)
-        for k, out_l in enumerate(outputs):
-            w = out_l.weight.detach().view(out_l.out_c, out_l.in_c) * out_l.wscale               # [3, C]
-            ds = (d_rgbw[k] * w.t().unsqueeze(0)).sum(dim=2)                                      # [N, C]
-            st = out_l.style
-            d_wp[:, 2 * k + 1] += ds @ (st.weight.detach() * st.wscale)
+        torch.sum(dxs.to_nchw() * const, dim=(2, 3), out=arena[:n * layers[0].in_c].view(n, layers[0].in_c))
+        d_wp = K.sg2_prep_bwd(S, prep, layers, outputs, arena, offs, const_off, n)
         return d_wp, None, None
 
 

@@ -530,10 +530,11 @@ class SynthesisModule(nn.Module):
     def get_nf(self, res):
         return min(self.fmaps_base // res, self.fmaps_max)
 
-    def _prep(self, wp32, layers, outputs):
+    def _prep(self, wp32, layers, outputs, with_handle=False):
         """-> (styles, demods, rgb_styles, rgb_weights), all views into one arena filled by `dge_sg2_prep`.
         The item table (device array of `dge_sg2_prep_item`) is rebuilt only when a parameter or the batch size
-        changes."""
+        changes.  with_handle: a fifth element {'cache': the cached item table, 'arena': this pass's arena} for
+        `dge_sg2_prep_bwd` (training, dge_b200/train_g.py)."""
         import ctypes
         from dge_b200._lib import Sg2PrepItem
         n, dev = wp32.shape[0], wp32.device
@@ -597,6 +598,8 @@ class SynthesisModule(nn.Module):
         demods = [view(c['views'][i]['demod']) if 'demod' in c['views'][i] else None for i in range(nl)]
         rgb_styles = [view(c['views'][nl + k]['style']) for k in range(len(outputs))]
         rgb_ws = [view(c['views'][nl + k]['rgbw']) for k in range(len(outputs))]
+        if with_handle:
+            return styles, demods, rgb_styles, rgb_ws, {'cache': c, 'arena': arena}
         return styles, demods, rgb_styles, rgb_ws
 
     def _forward_autograd(self, wp, randomize_noise=False):

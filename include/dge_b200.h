@@ -168,6 +168,17 @@ typedef struct dge_sg2_prep_item {
 int dge_sg2_prep(const dge_sg2_prep_item* items, int n_items, const float* wp, float* arena, int n, int num_layers,
                  int wdim, void* stream);
 
+/* Transpose of dge_sg2_prep for the training step (the frozen generator's gradient w.r.t. wp, E_align_s2.py:160-205): the
+   per-layer reductions dge_sg2_layer_bwd left in `sums` -> d_wp [n][num_layers][wdim] (zeroed by the call), one launch.
+   `items`, `arena`: what dge_sg2_prep was given / filled (styles, demods).  gsrc: DEVICE array [n_items][4] of float offsets
+   into `sums`, (s_off, s_stride, d_off, t_off), -1 = absent:
+     layer item : S[c] = sums[s_off + (n*cin + c)*s_stride]          (d style),  D[o] = sums[d_off + (n*cout + o)*5] (demod * d demod)
+                  ds[c] = S[c] - style[n][c] * sum_o D[o] * demod[n][o]^2 * w2[o][c]           (:867-877)
+     ToRGB item : T[c][j] = sums[t_off + (n*cin + c)*5 + j],  ds[c] = rgb_scale * sum_j T[c][j] * rgb_w[j][c]   (:462-474)
+     d_wp[n][wp_index][k] += st_wscale * sum_c ds[c] * st_w[c][k]                                   (:990-996 transposed) */
+int dge_sg2_prep_bwd(const dge_sg2_prep_item* items, int n_items, const float* arena, const int64_t* gsrc,
+                     const float* sums, float* d_wp, int n, int num_layers, int wdim, void* stream);
+
 /* ---- dense (DenseBlock.forward stylegan2_generator.py:990-996; ln.Linear lreq.py:68-75) ------ */
 /* y[n][m] = act((sum_k x[n][k]*w[m][k])*wscale + b[m]*bscale + add_bias) * gain ; act = lrelu(slope) */
 int dge_dense(const float* x, const float* w, const float* b, float* y, int n, int k, int m, float wscale,

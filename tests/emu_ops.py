@@ -389,7 +389,29 @@ def sg2_prep_all(S, wp32, layers, outputs):
         s = F.linear(wp32[:, 2 * k + 1], st.weight.detach() * st.wscale, b) + st.additional_bias
         rgb_styles.append(s)
         rgb_ws.append((m.weight.detach().view(m.out_c, m.in_c) * m.wscale)[None] * s[:, None, :])
-    return styles, demods, rgb_styles, rgb_ws
+    return styles, demods, rgb_styles, rgb_ws, {'styles': styles, 'demods': demods}
+
+
+def sg2_prep_bwd(S, handle, layers, outputs, sums, layer_offs, const_off, n):
+    """dge_sg2_prep_bwd restated with torch ops on the same arena (include/dge_b200.h)."""
+    styles, demods = handle['styles'], handle['demods']
+    d_wp = torch.zeros((n, S.num_layers, S.w_space_dim))
+
+    def lsum(i):
+        c = layers[i].out_c
+        return sums[layer_offs[i]:layer_offs[i] + n * c * 5].view(n, c, 5)
+
+    for i, m in enumerate(layers):
+        ds = sums[const_off:const_off + n * m.in_c].view(n, m.in_c) if i == 0 else lsum(i - 1)[:, :, 0]
+        if m.demodulate:
+            w2 = ((m.weight.detach() * m.wscale) ** 2).sum(dim=(2, 3))
+            ds = ds - styles[i] * ((lsum(i)[:, :, 4] * demods[i] * demods[i]) @ w2)
+        d_wp[:, i] += ds @ (m.style.weight.detach() * m.style.wscale)
+    for k, m in enumerate(outputs):
+        w = m.weight.detach().view(m.out_c, m.in_c) * m.wscale
+        ds = (lsum(2 * k)[:, :, 1:4] * w.t().unsqueeze(0)).sum(dim=2)
+        d_wp[:, 2 * k + 1] += ds @ (m.style.weight.detach() * m.style.wscale)
+    return d_wp
 
 
 def up_fir_epilogue(raw_up, n, c, h_out, w_out, *, demod=None, noise=None, noise_batched=False, noise_scalar=0.0,
@@ -436,8 +458,9 @@ def rgb_up_bwd(d_out):
 
 
 def sg2_layer_bwd(ya, ya_scale, dxs, dimg, rgbw, noise, noise_batched, noise_scalar, bias, demod, gain, slope,
-                  out_kind="act", planes=2):
+                  out_kind="act", planes=2, sums=None):
     n, c, h, w = ya.n, ya.c, ya.h, ya.w
+    sums_out = sums
     y = ya.to_nchw()
     sn = torch.ones((n, c)) if ya_scale is None else ya_scale
     isn = torch.where(sn != 0, 1.0 / sn, torch.zeros_like(sn))
@@ -456,6 +479,9 @@ def sg2_layer_bwd(ya, ya_scale, dxs, dimg, rgbw, noise, noise_batched, noise_sca
     b = 0.0 if bias is None else bias.view(1, c, 1, 1)
     sums[:, :, 4] = (dpre * (pre - nz - b)).sum(dim=(2, 3))
     v = dpre if demod is None else dpre * demod.view(n, c, 1, 1)
+    if sums_out is not None:
+        sums_out.copy_(sums)
+        sums = sums_out
     return (Act.of(v, planes) if out_kind == "act" else F32B.of(v)), sums
 
 

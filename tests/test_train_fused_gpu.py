@@ -317,6 +317,38 @@ def test_rgb_up_bwd_kernel():
     assert rel(ops.rgb_init(img.cuda(), None, 2, 3, 16, 24, "cuda"), emu.rgb_init(img, None, 2, 3, 16, 24, "cpu")) < 1e-6
 
 
+def test_sg2_prep_bwd_kernel():
+    """dge_sg2_prep_bwd (one launch: every layer's style / demodulation / ToRGB transposes -> d wp) against its torch
+    statement, on a random arena of sums and the styles / demods the forward's dge_sg2_prep produced."""
+    import model.stylegan2_generator as SG
+    from dge_b200 import ops
+    fx = torch.load(os.path.join(GOLD, "sg2_res32.pt"))
+    G = SG.StyleGAN2Generator(**fx["config"])
+    G.load_state_dict(fx["state_dict"], strict=True)
+    S, Sd = G.synthesis, None
+    n, nl = 3, G.synthesis.num_layers
+    wp = torch.randn(n, nl, S.w_space_dim, generator=torch.Generator().manual_seed(5))
+    layers = [getattr(S, f"layer{i}") for i in range(nl - 1)]
+    outputs = [getattr(S, f"output{k}") for k in range(nl // 2)]
+    *_, h_e = emu.sg2_prep_all(S, wp, layers, outputs)
+    offs, total = [], n * layers[0].in_c
+    for l in layers:
+        offs.append(total)
+        total += n * l.out_c * 5
+    sums = torch.randn(total, generator=torch.Generator().manual_seed(6))
+    want = emu.sg2_prep_bwd(S, h_e, layers, outputs, sums, offs, 0, n)
+    import copy
+    Sd = copy.deepcopy(S).cuda()
+    layers_d = [getattr(Sd, f"layer{i}") for i in range(nl - 1)]
+    outputs_d = [getattr(Sd, f"output{k}") for k in range(nl // 2)]
+    styles, demods, _, _, h_d = ops.sg2_prep_all(Sd, wp.cuda(), layers_d, outputs_d)
+    assert rel(styles[3], h_e["styles"][3]) < 1e-5 and rel(demods[3], h_e["demods"][3]) < 1e-5
+    got = ops.sg2_prep_bwd(Sd, h_d, layers_d, outputs_d, sums.cuda(), offs, 0, n)
+    assert rel(got, want) < 1e-5
+    again = ops.sg2_prep_bwd(Sd, h_d, layers_d, outputs_d, sums.cuda(), offs, 0, n)
+    assert torch.equal(got, again)                                  # two-term atomic sums: order-independent
+
+
 def test_fused_synthesis_matches_reference_gradient():
     import model.stylegan2_generator as SG
     assert SG.FUSED_TRAIN
