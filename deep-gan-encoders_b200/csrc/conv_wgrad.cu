@@ -16,6 +16,14 @@
 //            all 4 warps = final epilogue (one TMEM lane = one output channel per thread).
 //   TMEM   : taps_x accumulators of [128 x nblk] fp32 side by side (<= 384 columns), live for the whole CTA.
 //   planes == 2 => split precision as in the forward kernel: dy = dh+dl, x = xh+xl, acc += dh*xh + dh*xl + dl*xh.
+//
+// Thin layers (Cin <= 32: the 1024^2 / 512^2 blocks of the encoder), "cross-stacked" mode: an MMA costs its 4 KB A fetch
+// (~64 clk) however few of its 128 rows and N columns carry data, so both MMA dimensions are filled with filter taps:
+//     dW[o][i][ky][kx] = sum_q dy[o][q - (0, kx-1)] * x[i][q + (ky-1, 0)]
+//   A rows    = (kx, o):  three copies of the dy tile shifted by one column each (TMA zero-fills outside the map),
+//   B columns = (ky, i-group, hi | lo): three copies of the x tile shifted by one row each, the lo plane next to the hi plane,
+// and a K step of 16 pixels is TWO MMAs (dh x [xh | xl] -> D1, dl x xh -> D2) instead of six: ~160 clk per 16 pixels per
+// SM, which at 148 SMs consumes the operands at HBM speed.  The epilogue adds the three partial products.
 #include <stdlib.h>
 #include <string.h>
 
@@ -40,6 +48,9 @@ struct WgradParams {
   int stacked;                     // all 9 taps side by side in N (Cin <= 32): x is staged as 9 shifted tiles
   int n1, n2;                      // stacked: N of the first / second MMA of a K step (n2 = 0: one MMA)
   uint32_t slot_bytes;             // stacked: bytes of one tap's x tile set
+  int xstack;                      // cross-stacked mode (see the header): rows = (kx, o), columns = (ky, i, plane)
+  int R;                           // xstack: output channels per CTA (3 * R <= 128 rows)
+  uint32_t a_slot_bytes;           // xstack: bytes of one shifted dy tile set
   int rowpair;                     // maps <= 8 pixels wide: a K step is 8 pixels of row r + 8 pixels of row r+1
   int atomic, accumulate;          // chunks > 1: partial sums merge with atomics; else plain store / add
   float* dw;
@@ -124,8 +135,15 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
         const int y0 = ty * p.th, x0 = tx * p.tw;
         uint8_t* st = smem + (size_t)s * p.stage_bytes;
-        uint8_t* sx = st + (size_t)16 * p.planes * p.dy_tile_bytes;
-        if (p.stacked) {
+        uint8_t* sx = st + (p.xstack ? (size_t)3 * p.a_slot_bytes : (size_t)16 * p.planes * p.dy_tile_bytes);
+        if (p.xstack) {
+          mbar_arrive_expect_tx(&full_bar[s], 3u * p.dy_bytes + 3u * p.x_bytes);
+#pragma unroll 1
+          for (int k = 0; k < 3; ++k) {
+            tma_load_4d(st + (size_t)k * p.a_slot_bytes, &tm_dy, &full_bar[s], 2 * (x0 + 1 - k), y0, cob * p.a_groups, n);
+            tma_load_4d(sx + (size_t)k * p.slot_bytes, &tm_x, &full_bar[s], 2 * x0, y0 + k - 1, 0, n);
+          }
+        } else if (p.stacked) {
           mbar_arrive_expect_tx(&full_bar[s], p.dy_bytes + 9u * p.x_bytes);
           tma_load_4d(st, &tm_dy, &full_bar[s], 2 * x0, y0, cob * 16 * p.planes, n);
 #pragma unroll 1
@@ -148,6 +166,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
       // the two 8-pixel K groups of a K step: neighbours in a row (128 B apart), or the same 8 columns of two rows
       const uint32_t a_lbo = p.rowpair ? (uint32_t)p.tw * 16u : 128u, b_lbo = p.rowpair ? (uint32_t)p.pw * 16u : 128u;
       const uint64_t a_desc0 = wg_desc(0, a_lbo, a_sbo), b_desc0 = wg_desc(0, b_lbo, b_sbo);
+      const uint64_t bx_desc0 = wg_desc(0, b_lbo, p.x_tile_bytes);   // xstack: (hi, lo) planes as neighbouring N groups
       const uint32_t a_lo = p.dy_tile_bytes >> 4, b_lo = p.x_tile_bytes >> 4;   // plane 1 (lo) offsets, 16-byte units
       const int segs = p.rowpair ? 1 : p.tw / 16, rstep = p.rowpair ? 2 : 1;
       for (int t = t0, it = 0; t < t1; ++t, ++it) {
@@ -156,12 +175,18 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
         mbar_wait(&full_bar[s], ph);
         wg_fence_after();
         const uint32_t a_base = smem_u32(smem + (size_t)s * p.stage_bytes);
-        const uint32_t b_base = a_base + 16u * p.planes * p.dy_tile_bytes;
+        const uint32_t b_base = a_base + (p.xstack ? 3u * p.a_slot_bytes : 16u * p.planes * p.dy_tile_bytes);
         for (int r = 0; r < p.th; r += rstep) {
           for (int sg = 0; sg < segs; ++sg) {
             const uint64_t da = a_desc0 + (uint64_t)(((a_base >> 4) + (uint32_t)(r * p.tw + sg * 16)) & 0x3fff);
             const uint32_t acc0 = (it == 0 && r == 0 && sg == 0) ? 0u : 1u;
-            if (p.stacked) {
+            if (p.xstack) {
+              // D1 += dh(kx-stacked) x [xh | xl](ky-stacked): consecutive B groups alternate hi / lo (stride = one tile);
+              // D2 += dl x xh: every other group (stride = planes tiles)
+              const uint32_t boff = ((b_base >> 4) + (uint32_t)(r * p.tw + sg * 16)) & 0x3fff;
+              wg_mma(tmem, da, bx_desc0 + (uint64_t)boff, idesc1, acc0);
+              if (p.planes == 2) wg_mma(tmem + (uint32_t)p.n1, da + a_lo, b_desc0 + (uint64_t)boff, idesc2, acc0);
+            } else if (p.stacked) {
               // one (or two) wide MMAs cover all 9 taps: N group g = tap * (Cin/8) + channel group, uniform stride
               const uint64_t db = b_desc0 + (uint64_t)(((b_base >> 4) + (uint32_t)(r * p.tw + sg * 16)) & 0x3fff);
               wg_mma(tmem, da, db, idesc1, acc0);
@@ -202,8 +227,51 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
   // =================================== epilogue (all warps) ================================
   mbar_wait_relaxed(&done_bar, 0);
   wg_fence_after();
+  if (p.xstack) {
+    // lane = kx * R + o; D1 columns ((ky * G + g) * planes + plane) * 8 + c, D2 columns (ky * G + g) * 8 + c  (G = Cin / 8)
+    if (warp * 32 < 3 * p.R && t1 > t0) {
+      const int row = warp * 32 + lane;
+      const int kx = row / p.R, co = cob * p.R + (row - kx * p.R);
+      const int G = p.Cin / 8;
+      for (int kg = 0; kg < 3 * G; ++kg) {
+        uint32_t r1[16], r2[8];
+        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+        if (p.planes == 2) {
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+              "%15}, [%16];"
+              : "=r"(r1[0]), "=r"(r1[1]), "=r"(r1[2]), "=r"(r1[3]), "=r"(r1[4]), "=r"(r1[5]), "=r"(r1[6]), "=r"(r1[7]),
+                "=r"(r1[8]), "=r"(r1[9]), "=r"(r1[10]), "=r"(r1[11]), "=r"(r1[12]), "=r"(r1[13]), "=r"(r1[14]),
+                "=r"(r1[15])
+              : "r"(lane_base + (uint32_t)(kg * 16)));
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=r"(r2[0]), "=r"(r2[1]), "=r"(r2[2]), "=r"(r2[3]), "=r"(r2[4]), "=r"(r2[5]), "=r"(r2[6]),
+                         "=r"(r2[7])
+                       : "r"(lane_base + (uint32_t)(p.n1 + kg * 8)));
+        } else {
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=r"(r1[0]), "=r"(r1[1]), "=r"(r1[2]), "=r"(r1[3]), "=r"(r1[4]), "=r"(r1[5]), "=r"(r1[6]),
+                         "=r"(r1[7])
+                       : "r"(lane_base + (uint32_t)(kg * 8)));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) r1[8 + i] = r2[i] = 0u;
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int ky = kg / G, ci0 = (kg - ky * G) * 8;
+        if (row < 3 * p.R) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float* q = p.dw + ((size_t)co * p.Cin + ci0 + i) * 9 + ky * 3 + kx;
+            const float v = __uint_as_float(r1[i]) + __uint_as_float(r1[8 + i]) + __uint_as_float(r2[i]);
+            if (p.atomic) atomicAdd(q, v);
+            else *q = p.accumulate ? *q + v : v;
+          }
+        }
+      }
+    }
+  }
   const int co = cob * 128 + warp * 32 + lane;
-  if (cob * 128 + warp * 32 < p.Cout && t1 > t0) {
+  if (!p.xstack && cob * 128 + warp * 32 < p.Cout && t1 > t0) {
     const int ncols = (p.stacked ? 9 : p.taps_x) * p.nblk;
     const int tap_base = p.stacked ? 0 : ky * p.ksize;
     const int kk = p.ksize * p.ksize;
@@ -288,7 +356,18 @@ extern "C" int dge_conv_wgrad(const void* dy_act, const void* x_act, float* dw, 
   static int no_stack = -1;
   if (no_stack < 0) no_stack = getenv("DGE_WGRAD_NO_STACK") ? 1 : 0;
   p.stacked = (ksize == 3 && cin % 16 == 0 && cin <= 32 && !no_stack) ? 1 : 0;
-  p.pw = p.stacked ? p.tw : p.tw + 2 * p.pad;
+  // cross-stacked mode (header): R output channels per CTA, the largest of 40 / 32 / 24 / 16 / 8 that divides Cout
+  static int no_xstack = -1;
+  if (no_xstack < 0) no_xstack = getenv("DGE_WGRAD_NO_XSTACK") ? 1 : 0;
+  if (p.stacked && !no_xstack) {
+    for (int r = 40; r >= 8 && !p.xstack; r -= 8)
+      if (cout % r == 0) {
+        p.xstack = 1;
+        p.R = r;
+      }
+    if (p.xstack) p.stacked = 0;
+  }
+  p.pw = (p.stacked || p.xstack) ? p.tw : p.tw + 2 * p.pad;
   p.tiles_x = (w + p.tw - 1) / p.tw;
   p.tiles_y = (h + p.th - 1) / p.th;
   const long long tiles = (long long)n * p.tiles_x * p.tiles_y;
@@ -339,9 +418,14 @@ extern "C" int dge_conv_wgrad(const void* dy_act, const void* x_act, float* dw, 
     p.n1 = 9 * cin <= 256 ? 9 * cin : 5 * cin;
     p.n2 = 9 * cin - p.n1;
   }
-  p.cout_blocks = (cout + 127) / 128;
+  if (p.xstack) {
+    p.n1 = 3 * cin * planes;     // D1: (ky, channel group, plane)
+    p.n2 = 3 * cin;              // D2: (ky, channel group), planes == 2 only
+  }
+  p.cout_blocks = p.xstack ? cout / p.R : (cout + 127) / 128;
   const int a_groups_total = (cout / 8) * planes, b_groups_total = (cin / 8) * planes;
   p.a_groups = 16 * planes < a_groups_total ? 16 * planes : a_groups_total;
+  if (p.xstack) p.a_groups = (p.R / 8) * planes;
   p.b_groups = (p.nblk / 8) * planes < b_groups_total ? (p.nblk / 8) * planes : b_groups_total;
   p.dy_tile_bytes = (uint32_t)(p.th * p.tw * 16);
   p.x_tile_bytes = (uint32_t)(p.th * p.pw * 16);
@@ -349,20 +433,31 @@ extern "C" int dge_conv_wgrad(const void* dy_act, const void* x_act, float* dw, 
   p.x_bytes = p.x_tile_bytes * p.b_groups;
   // smem image per stage keeps room for the full 16 / nblk/8 groups so the descriptor strides do not depend on clamping
   p.slot_bytes = p.x_tile_bytes * (uint32_t)((p.nblk / 8) * planes);
-  const uint32_t x_region = p.slot_bytes * (p.stacked ? 9u : 1u);
-  p.stage_bytes = (16u * planes * p.dy_tile_bytes + x_region + 127u) & ~127u;
-  p.stages = (int)((216u * 1024u) / p.stage_bytes);
+  const uint32_t x_region = p.slot_bytes * (p.stacked ? 9u : (p.xstack ? 3u : 1u));
+  p.a_slot_bytes = p.dy_bytes;
+  // xstack: the M = 128 descriptor spans 16 row groups whatever 3 * R is (rows past 3 * R land in accumulator lanes nobody
+  // reads); the span of the last stage stays inside the allocation through `tail` bytes of slack
+  const uint32_t a_region = p.xstack ? 3u * p.a_slot_bytes : 16u * planes * p.dy_tile_bytes;
+  const uint32_t tail = p.xstack ? 16u * planes * p.dy_tile_bytes : 0u;
+  p.stage_bytes = (a_region + x_region + 127u) & ~127u;
+  p.stages = (int)(((p.xstack ? 224u : 216u) * 1024u - tail) / p.stage_bytes);
   if (p.stages > WG_MAX_STAGES) p.stages = WG_MAX_STAGES;
   DGE_REQUIRE(p.stages >= 2, "conv_wgrad: stage of %u bytes does not fit twice in shared memory", p.stage_bytes);
   int cols = 32;
-  while (cols < (p.stacked ? 9 : p.taps_x) * p.nblk) cols *= 2;
+  while (cols < (p.xstack ? p.n1 + (planes == 2 ? p.n2 : 0) : (p.stacked ? 9 : p.taps_x) * p.nblk)) cols *= 2;
   p.tmem_cols = cols;
-  const int blocks_y = p.stacked ? p.cout_blocks : ksize * p.cout_blocks * p.cin_blocks;
+  const int blocks_y = (p.stacked || p.xstack) ? p.cout_blocks : ksize * p.cout_blocks * p.cin_blocks;
   // split of the contraction: c chunks shorten every CTA's MMA loop by c but each adds one pass of fp32 atomics over dW
   // (~200 G atomics/s measured); with one chunk the CTA owns its dW block and stores it (no memset, no atomics).
   int chunks = 1;
-  predict(p.stacked ? p.n1 : p.nblk, split_mmas * (p.stacked ? (p.n2 ? 2 : 1) : p.taps_x), blocks_y,
-          (p.stacked ? 9 : p.taps_x) * p.nblk, &chunks);
+  if (p.xstack) {
+    // one K step = MMA(N = n1) + MMA(N = n2): pass the summed clocks as one MMA of twice that many columns
+    const int clk = (p.n1 / 2 > 64 ? p.n1 / 2 : 64) + (planes == 2 ? (p.n2 / 2 > 64 ? p.n2 / 2 : 64) : 0);
+    predict(2 * clk, 1.0, blocks_y, 3 * cin, &chunks);
+  } else {
+    predict(p.stacked ? p.n1 : p.nblk, split_mmas * (p.stacked ? (p.n2 ? 2 : 1) : p.taps_x), blocks_y,
+            (p.stacked ? 9 : p.taps_x) * p.nblk, &chunks);
+  }
   p.chunks = chunks;
   p.atomic = chunks > 1;
   p.accumulate = accumulate;
@@ -386,7 +481,7 @@ extern "C" int dge_conv_wgrad(const void* dy_act, const void* x_act, float* dw, 
     if (r) return r;
   }
 
-  const size_t smem = (size_t)p.stages * p.stage_bytes + 256;
+  const size_t smem = (size_t)p.stages * p.stage_bytes + tail + 256;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -205,7 +205,12 @@ def test_conv_data_gradient(case):
 @pytest.mark.parametrize("case", [(2, 16, 32, 24, 16, 3), (2, 128, 128, 16, 16, 3), (1, 64, 128, 9, 17, 1),
                                   (2, 512, 512, 4, 4, 3), (1, 144, 192, 20, 40, 3), (2, 32, 32, 64, 80, 3),
                                   (3, 256, 64, 33, 31, 1), (2, 64, 64, 7, 8, 3), (3, 32, 48, 11, 5, 3),
-                                  (8, 512, 512, 8, 8, 3)],
+                                  (8, 512, 512, 8, 8, 3),
+                                  # thin layers: the cross-stacked mode (rows = (kx, o), columns = (ky, i, plane)) with
+                                  # R = 16 / 32 x 2 blocks / 24 / 40 output channels per CTA, ragged and <= 8-wide maps
+                                  (2, 16, 16, 40, 40, 3), (1, 32, 64, 33, 47, 3), (2, 16, 48, 21, 70, 3),
+                                  (1, 32, 80, 64, 64, 3), (4, 16, 32, 128, 128, 3), (2, 32, 32, 8, 8, 3),
+                                  (2, 16, 16, 4, 6, 3), (1, 32, 32, 256, 256, 3)],
                          ids=lambda c: "n%d_ci%d_co%d_%dx%d_k%d" % c)
 def test_conv_weight_gradient(case):
     """dL/dW of y = conv2d(x, W) (dge_conv_wgrad: pixels are the contraction index, both operands MN-major tiles of the
@@ -235,6 +240,14 @@ def test_conv_weight_gradient_plain_bf16_is_close():
     x = torch.randn(2, 64, 32, 32, device="cuda", generator=g)
     dy = torch.randn(2, 64, 32, 32, device="cuda", generator=g)
     wt = torch.zeros(64, 64, 3, 3, device="cuda", requires_grad=True)
+    (dw_ref,) = torch.autograd.grad(F.conv2d(x, wt, padding=1), wt, dy)
+    dw = ops.conv_wgrad(ops.nchw_to_act(dy, planes=1), ops.nchw_to_act(x, planes=1), 3)
+    torch.cuda.synchronize()
+    assert _rel(dw, dw_ref) < 2e-2
+    # thin layer (cross-stacked mode, one MMA per K step)
+    x = torch.randn(2, 32, 40, 56, device="cuda", generator=g)
+    dy = torch.randn(2, 64, 40, 56, device="cuda", generator=g)
+    wt = torch.zeros(64, 32, 3, 3, device="cuda", requires_grad=True)
     (dw_ref,) = torch.autograd.grad(F.conv2d(x, wt, padding=1), wt, dy)
     dw = ops.conv_wgrad(ops.nchw_to_act(dy, planes=1), ops.nchw_to_act(x, planes=1), 3)
     torch.cuda.synchronize()
