@@ -245,7 +245,10 @@ def run_ours(args):
         z = ddist.global_latents(100, BATCH * world, 512, rank, world, device=dev)
         imgs1 = G(z, trunc_psi=0.7, trunc_layers=8, randomize_noise=False)["image"].contiguous()
         imgs1_host = imgs1.cpu().pin_memory()
-        out_host = torch.empty((BATCH, 18 + 16, 512), dtype=torch.float32).pin_memory()  # w2 [8,18,512] + const2 [8,512,4,4]
+        # w2 [8,18,512] and const2 [8,512,4,4]: two CONTIGUOUS pinned buffers (a strided slice of one pinned tensor makes
+        # copy_ stage through pageable memory, i.e. a blocking D2H that serialises the host with every step)
+        w2_host = torch.empty((BATCH, 18, 512), dtype=torch.float32).pin_memory()
+        const2_host = torch.empty((BATCH, 512, 4, 4), dtype=torch.float32).pin_memory()
 
         def step(x):
             const2, w2 = E(x)
@@ -334,8 +337,8 @@ def run_ours(args):
             static_in.copy_(staging[slot], non_blocking=True)
             consumed[slot].record(main)
             img2, const2, w2 = run_step()
-            out_host[:, :18].copy_(w2, non_blocking=True)
-            out_host[:, 18:].copy_(const2.view(BATCH, 16, 512), non_blocking=True)
+            w2_host.copy_(w2, non_blocking=True)
+            const2_host.copy_(const2, non_blocking=True)
             # reconstruction MSE: one pass of the fused moments kernel (dge_pair_moments), 6 doubles back to the host
             ops.check(ops.lib().dge_pair_moments(ops._p(img2), ops._p(static_in), img2.numel(), ops._p(mom),
                                                  ops._stream()))
@@ -349,7 +352,7 @@ def run_ours(args):
         ms_e2e = timed(e2e_step, args.steps)
         copy_stream.synchronize()
         h2d = imgs1_host.numel() * 4
-        d2h = out_host.numel() * 4 + mom_host.numel() * 8
+        d2h = (w2_host.numel() + const2_host.numel()) * 4 + mom_host.numel() * 8
 
         # ---- per-kernel roofline: CUDA events around every launch of one more step ------------------
         with ops.profile() as rec:
