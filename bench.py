@@ -408,6 +408,11 @@ def run_ours(args):
                                          "`ours_reference_noise` vs `reference_gpu` (identical seeds and noise stream)"}
             if "ms_per_iteration" in ours_inv and "ms_per_iteration" in ref_inv:
                 line["inversion"]["speedup_vs_reference_gpu"] = ref_inv["ms_per_iteration"] / ours_inv["ms_per_iteration"]
+            # opt-in switch DGE_TRAIN_GRAPHS=1: the synthesis node replays CUDA graphs (dge_b200/train_g.py)
+            ours_g = run_json_subprocess(inv + ["--graphs"], 600)
+            line["inversion"]["ours_graphs"] = ours_g
+            if "ms_per_iteration" in ours_g and "ms_per_iteration" in ref_inv:
+                line["inversion"]["speedup_vs_reference_gpu_graphs"] = ref_inv["ms_per_iteration"] / ours_g["ms_per_iteration"]
             # the same loop with the case-2 encoder, the class embedding_img.py:9 actually imports (model/E/E_Blur.py)
             blur = [sys.executable, os.path.join(ROOT, "tools", "bench_invert.py"), "--encoder", "blur", "--images", "3",
                     "--iterations", "6"]

@@ -18,6 +18,9 @@ and finally ONE launch (sg2_prep_bwd, the transpose of the forward's sg2_prep) t
 (style affine :872-877, demodulation :867-870, ToRGB modulation :462-474): every layer's sums land in one arena whose
 offsets the kernel's item table knows.  `K` is the kernel namespace (see train_e.py).
 """
+import os
+import warnings
+
 import torch
 from torch.autograd.function import once_differentiable
 
@@ -65,94 +68,199 @@ def _dgrad_operands(layer, planes):
     return op
 
 
+def _run_forward(S, wp32, randomize_noise):
+    """The forward kernel chain -> (outputs: (image, *styles, *rgb_styles), saved: what the backward reads)."""
+    n, dev = wp32.shape[0], wp32.device
+    nl = S.num_layers
+    layers = [getattr(S, f'layer{i}') for i in range(nl - 1)]
+    outputs = [getattr(S, f'output{k}') for k in range(nl // 2)]
+    styles, demods, rgb_styles, rgb_ws, prep = K.sg2_prep_all(S, wp32.contiguous(), layers, outputs)
+    planes = layers[0].planes
+    const = S.early_layer.const.detach().float()
+    xa = K.nchw_to_act(const, scale=styles[0], planes=planes, batch=n)                        # :630-632
+    xas, noises = [], []
+    image = None
+    y_last = None
+    for i, layer in enumerate(layers):
+        p = _consts(layer, planes)
+        nxt = styles[i + 1] if i + 1 < nl - 1 else None
+        noise, batched = layer._noise(n, randomize_noise, dev)
+        xas.append(xa)
+        noises.append((noise, batched))
+        if layer.use_conv2d_transpose:                                                        # :879-896
+            raw = K.conv(xa, p['wpk'], layer.out_c, K.CONV_UP3X3)['raw_up']
+            xa = K.up_fir_epilogue(raw, n, layer.out_c, 2 * xa.h, 2 * xa.w, demod=demods[i], noise=noise,
+                                   noise_batched=batched, noise_scalar=p['strength'], bias=p['bias'],
+                                   slope=layer.slope, gain=layer.activate_scale, out_scale=nxt,
+                                   planes=planes)['act']
+            continue
+        k = i // 2
+        image = K.rgb_init(image, _consts(outputs[k], planes)['bias'], n, S.image_channels, layer.res, layer.res, dev)
+        r = K.conv(xa, p['wpk'], layer.out_c, K.CONV_3X3, demod=demods[i], noise=noise, noise_batched=batched,
+                   noise_scalar=p['strength'], bias=p['bias'], slope=layer.slope, gain=layer.activate_scale,
+                   out_act=True, out_scale=nxt, rgb_w=rgb_ws[k], rgb_out=image)             # :897-921, 515-522
+        xa = r['act']
+        if nxt is None:
+            y_last = xa
+    saved = {'geom': (n, nl, planes), 'noises': noises, 'acts': xas + [y_last],
+             'tabs': (styles, demods, rgb_styles, rgb_ws, prep)}
+    return (image,) + tuple(styles) + tuple(rgb_styles), saved
+
+
+def _run_backward(S, saved, d_image):
+    """d image -> d wp [n, num_layers, w_space_dim] from what `_run_forward` saved."""
+    n, nl, planes = saved['geom']
+    styles, demods, rgb_styles, rgb_ws, prep = saved['tabs']
+    layers = [getattr(S, f'layer{i}') for i in range(nl - 1)]
+    outputs = [getattr(S, f'output{k}') for k in range(nl // 2)]
+    acts = saved['acts']
+    nk = nl // 2
+    d_imgs = [None] * nk
+    d_imgs[nk - 1] = d_image.contiguous().float()
+    for k in range(nk - 1, 0, -1):                                                            # :519-522 transposed
+        d_imgs[k - 1] = K.rgb_up_bwd(d_imgs[k])
+    # one arena for every reduction the style gradient needs: [n, C0] (layer 0's style through x_0 = const * s_0),
+    # then per layer the [n, out_c, 5] sums of sg2_layer_bwd: 0 = d style of the NEXT layer (through x * s),
+    # 1..3 = d of the ToRGB weights, 4 = demod * d demod
+    const_off, offs, total = 0, [], n * layers[0].in_c
+    for layer in layers:
+        offs.append(total)
+        total += n * layer.out_c * 5
+    arena = torch.empty(total, dtype=torch.float32, device=d_image.device)
+    dxs = None
+    for i in range(nl - 2, -1, -1):
+        layer = layers[i]
+        last = i == nl - 2
+        p = _consts(layer, planes)
+        k = i // 2 if i % 2 == 0 else None
+        noise, batched = saved['noises'][i]
+        up = layer.use_conv2d_transpose
+        dconv, _ = K.sg2_layer_bwd(
+            acts[i + 1], None if last else styles[i + 1], dxs, None if k is None else d_imgs[k],
+            None if k is None else rgb_ws[k], noise, batched, p['strength'], p['bias'], demods[i],
+            layer.activate_scale, layer.slope, out_kind='f32b' if up else 'act', planes=planes,
+            sums=arena[offs[i]:offs[i] + n * layer.out_c * 5].view(n, layer.out_c, 5))
+        if up:
+            s2d = K.up_fir_bwd_s2d(dconv, planes)
+            dxs = K.conv(s2d, _dgrad_operands(layer, planes), layer.in_c, K.CONV_DOWN4X4S2, out_f32b=True,
+                         out_hw=(acts[i].h, acts[i].w))['f32b']
+        else:
+            dxs = K.conv(dconv, _dgrad_operands(layer, planes), layer.in_c, K.CONV_3X3, out_f32b=True)['f32b']
+        del dconv
+    const = S.early_layer.const.detach().float()
+    torch.sum(dxs.to_nchw() * const, dim=(2, 3), out=arena[:n * layers[0].in_c].view(n, layers[0].in_c))
+    return K.sg2_prep_bwd(S, prep, layers, outputs, arena, offs, const_off, n)
+
+
+# ------------------------------------------------------------------------------------------------
+# CUDA-graph replay of the node (SURVEY 8f-3: at batch 1 the inversion loop is bound by the host's ~70 + ~75 launch calls
+# per pass, not by the GPU).  Opt-in: `DGE_TRAIN_GRAPHS=1` in the environment, or `train_g.GRAPHS = True`.
+#
+# After `_GRAPH_WARMUP` eager passes of one configuration (module, batch, planes, weights epoch) the forward chain is
+# captured into a CUDA graph over a private memory pool, and the first backward after that into a second graph over the
+# same pool; later passes copy `wp` / `d image` into the graphs' static inputs, replay, and hand out CLONES of the static
+# outputs, so nothing the caller holds aliases graph memory.  The saved activations live in the pool and are overwritten
+# by the next forward replay: a backward through an OLDER pass than the latest one (two synthesis passes alive, backward
+# through the first) cannot be served and raises -- that pattern needs GRAPHS = False.  `retain_graph=True` + a second
+# backward of the latest pass (E_align_s2.py:205,220; embedding_img.py:100-128) replays the same backward graph.
+# `randomize_noise=True` (a CPU draw per layer, :912-913) and parameters that changed since the capture fall back to /
+# re-capture the eager chain.  Any failure while capturing disables the graphs for that module with a warning: the eager
+# chain is always the fallback, never a different result.
+# ------------------------------------------------------------------------------------------------
+GRAPHS = os.environ.get('DGE_TRAIN_GRAPHS', '0') == '1'
+_GRAPH_WARMUP = 2
+
+
+class _GraphState:
+    def __init__(self, key):
+        self.key, self.calls, self.gen = key, 0, 0
+        self.failed = False
+        self.fwd = self.bwd = None
+        self.wp_in = self.outs = self.saved = self.d_image_in = self.d_wp = None
+
+
+def _graph_key(S, wp32):
+    srcs = S.__dict__.get('_train_graph_srcs')
+    if srcs is None:
+        srcs = S.__dict__['_train_graph_srcs'] = list(S.parameters()) + list(S.buffers())
+    return (tuple(wp32.shape), wp32.device.index, S.layer0.planes, K.weight_key(*srcs))
+
+
+def _graph_state(S, wp32):
+    key = _graph_key(S, wp32)
+    st = S.__dict__.get('_train_graph')
+    if st is None or st.key != key:
+        st = S.__dict__['_train_graph'] = _GraphState(key)     # new shapes / weights: start over (drops the old pool)
+    return st
+
+
 class _SynthesisFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, wp32, S, randomize_noise):
-        n, dev = wp32.shape[0], wp32.device
-        nl = S.num_layers
-        layers = [getattr(S, f'layer{i}') for i in range(nl - 1)]
-        outputs = [getattr(S, f'output{k}') for k in range(nl // 2)]
-        styles, demods, rgb_styles, rgb_ws, prep = K.sg2_prep_all(S, wp32.contiguous(), layers, outputs)
-        planes = layers[0].planes
-        const = S.early_layer.const.detach().float()
-        xa = K.nchw_to_act(const, scale=styles[0], planes=planes, batch=n)                        # :630-632
-        xas, noises = [], []
-        image = None
-        y_last = None
-        for i, layer in enumerate(layers):
-            p = _consts(layer, planes)
-            nxt = styles[i + 1] if i + 1 < nl - 1 else None
-            noise, batched = layer._noise(n, randomize_noise, dev)
-            xas.append(xa)
-            noises.append((noise, batched))
-            if layer.use_conv2d_transpose:                                                        # :879-896
-                raw = K.conv(xa, p['wpk'], layer.out_c, K.CONV_UP3X3)['raw_up']
-                xa = K.up_fir_epilogue(raw, n, layer.out_c, 2 * xa.h, 2 * xa.w, demod=demods[i], noise=noise,
-                                       noise_batched=batched, noise_scalar=p['strength'], bias=p['bias'],
-                                       slope=layer.slope, gain=layer.activate_scale, out_scale=nxt,
-                                       planes=planes)['act']
-                continue
-            k = i // 2
-            image = K.rgb_init(image, _consts(outputs[k], planes)['bias'], n, S.image_channels, layer.res, layer.res, dev)
-            r = K.conv(xa, p['wpk'], layer.out_c, K.CONV_3X3, demod=demods[i], noise=noise, noise_batched=batched,
-                       noise_scalar=p['strength'], bias=p['bias'], slope=layer.slope, gain=layer.activate_scale,
-                       out_act=True, out_scale=nxt, rgb_w=rgb_ws[k], rgb_out=image)             # :897-921, 515-522
-            xa = r['act']
-            if nxt is None:
-                y_last = xa
-        ctx.S, ctx.geom = S, (n, nl, planes)
-        ctx.noises = noises
-        ctx.acts = xas + [y_last]
-        ctx.tabs = (styles, demods, rgb_styles, rgb_ws, prep)
-        ctx.mark_non_differentiable(*styles, *rgb_styles)
-        return (image,) + tuple(styles) + tuple(rgb_styles)
+        ctx.S = S
+        st = None
+        if GRAPHS and K is ops and wp32.is_cuda and not randomize_noise:
+            st = _graph_state(S, wp32)
+            if st.failed:
+                st = None
+        if st is not None and st.fwd is None and st.calls >= _GRAPH_WARMUP:
+            try:
+                torch.cuda.synchronize()
+                st.wp_in = wp32.detach().clone()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    st.outs, st.saved = _run_forward(S, st.wp_in, False)
+                st.fwd = g
+            except Exception as exc:  # noqa: BLE001 -- the eager chain is the fallback
+                warnings.warn(f'dge_b200 train_g: CUDA-graph capture of the synthesis forward failed ({exc!r}); '
+                              'running eagerly')
+                st.failed, st.fwd = True, None
+                torch.cuda.synchronize()
+                st = None
+        if st is not None and st.fwd is not None:
+            st.wp_in.copy_(wp32)
+            st.fwd.replay()
+            st.gen += 1
+            ctx.graph, ctx.gen = st, st.gen
+            outs = tuple(o.clone() for o in st.outs)
+        else:
+            if st is not None:
+                st.calls += 1
+            ctx.graph = None
+            outs, ctx.saved = _run_forward(S, wp32, randomize_noise)
+        ctx.mark_non_differentiable(*outs[1:])
+        return outs
 
     @staticmethod
     @once_differentiable
     def backward(ctx, d_image, *_unused):
-        S = ctx.S
-        n, nl, planes = ctx.geom
-        styles, demods, rgb_styles, rgb_ws, prep = ctx.tabs
-        layers = [getattr(S, f'layer{i}') for i in range(nl - 1)]
-        outputs = [getattr(S, f'output{k}') for k in range(nl // 2)]
-        acts = ctx.acts
-        nk = nl // 2
-        d_imgs = [None] * nk
-        d_imgs[nk - 1] = d_image.contiguous().float()
-        for k in range(nk - 1, 0, -1):                                                            # :519-522 transposed
-            d_imgs[k - 1] = K.rgb_up_bwd(d_imgs[k])
-        # one arena for every reduction the style gradient needs: [n, C0] (layer 0's style through x_0 = const * s_0),
-        # then per layer the [n, out_c, 5] sums of sg2_layer_bwd: 0 = d style of the NEXT layer (through x * s),
-        # 1..3 = d of the ToRGB weights, 4 = demod * d demod
-        const_off, offs, total = 0, [], n * layers[0].in_c
-        for layer in layers:
-            offs.append(total)
-            total += n * layer.out_c * 5
-        arena = torch.empty(total, dtype=torch.float32, device=d_image.device)
-        dxs = None
-        for i in range(nl - 2, -1, -1):
-            layer = layers[i]
-            last = i == nl - 2
-            p = _consts(layer, planes)
-            k = i // 2 if i % 2 == 0 else None
-            noise, batched = ctx.noises[i]
-            up = layer.use_conv2d_transpose
-            dconv, _ = K.sg2_layer_bwd(
-                acts[i + 1], None if last else styles[i + 1], dxs, None if k is None else d_imgs[k],
-                None if k is None else rgb_ws[k], noise, batched, p['strength'], p['bias'], demods[i],
-                layer.activate_scale, layer.slope, out_kind='f32b' if up else 'act', planes=planes,
-                sums=arena[offs[i]:offs[i] + n * layer.out_c * 5].view(n, layer.out_c, 5))
-            if up:
-                s2d = K.up_fir_bwd_s2d(dconv, planes)
-                dxs = K.conv(s2d, _dgrad_operands(layer, planes), layer.in_c, K.CONV_DOWN4X4S2, out_f32b=True,
-                             out_hw=(acts[i].h, acts[i].w))['f32b']
-            else:
-                dxs = K.conv(dconv, _dgrad_operands(layer, planes), layer.in_c, K.CONV_3X3, out_f32b=True)['f32b']
-            del dconv
-        const = S.early_layer.const.detach().float()
-        torch.sum(dxs.to_nchw() * const, dim=(2, 3), out=arena[:n * layers[0].in_c].view(n, layers[0].in_c))
-        d_wp = K.sg2_prep_bwd(S, prep, layers, outputs, arena, offs, const_off, n)
-        return d_wp, None, None
+        S, st = ctx.S, ctx.graph
+        if st is None:
+            return _run_backward(S, ctx.saved, d_image), None, None
+        if ctx.gen != st.gen:
+            raise RuntimeError(
+                'dge_b200 train_g: backward through a synthesis pass whose saved activations were overwritten by a later '
+                'pass (CUDA-graph mode keeps ONE pass alive); set dge_b200.train_g.GRAPHS = False / unset '
+                'DGE_TRAIN_GRAPHS for this pattern')
+        if st.failed:
+            return _run_backward(S, st.saved, d_image), None, None
+        if st.bwd is None:
+            try:
+                st.d_image_in = d_image.detach().contiguous().float().clone()
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=st.fwd.pool()):
+                    st.d_wp = _run_backward(S, st.saved, st.d_image_in)
+                st.bwd = g
+            except Exception as exc:  # noqa: BLE001 -- this pass's activations are intact: finish it eagerly
+                warnings.warn(f'dge_b200 train_g: CUDA-graph capture of the synthesis backward failed ({exc!r}); '
+                              'running eagerly')
+                st.failed = True
+                torch.cuda.synchronize()
+                return _run_backward(S, st.saved, d_image), None, None
+        st.d_image_in.copy_(d_image)
+        st.bwd.replay()
+        return st.d_wp.clone(), None, None
 
 
 def synthesis_forward(S, wp, randomize_noise=False):

@@ -349,6 +349,74 @@ def test_sg2_prep_bwd_kernel():
     assert torch.equal(got, again)                                  # two-term atomic sums: order-independent
 
 
+def test_synthesis_node_cuda_graph_replay_matches_eager():
+    """`train_g.GRAPHS` (opt-in, DGE_TRAIN_GRAPHS=1): after two eager passes the synthesis node replays CUDA graphs over static
+    buffers.  Same kernels in the same order: images and d wp equal up to the order of the fp32 atomics of the ToRGB / style
+    reductions; `retain_graph` + a second backward replays; a backward through an overwritten pass raises; changed weights
+    re-capture."""
+    import copy
+    import model.stylegan2_generator as SG
+    from dge_b200 import train_g
+    fx = torch.load(os.path.join(GOLD, "sg2_res32.pt"))
+    G = SG.StyleGAN2Generator(**fx["config"])
+    G.load_state_dict(fx["state_dict"], strict=True)
+    G = G.cuda()
+    G2 = copy.deepcopy(G)
+    gen = torch.Generator().manual_seed(11)
+    shape = fx["wp"].shape
+
+    def one(Gm, wp_cpu, tgt_cpu, twice=False):
+        wp = wp_cpu.cuda().requires_grad_(True)
+        img = Gm.synthesis(wp)["image"]
+        loss = ((img - tgt_cpu.cuda()) ** 2).mean()
+        loss.backward(retain_graph=twice)
+        g1 = wp.grad.clone()
+        if twice:
+            wp.grad = None
+            (loss * 2).backward()
+            return img.detach(), g1, wp.grad.clone()
+        return img.detach(), g1, None
+
+    assert not train_g.GRAPHS
+    try:
+        for it in range(6):
+            wp_cpu = fx["wp"] + 0.3 * torch.randn(shape, generator=gen)
+            tgt = torch.randn(fx["image"].shape, generator=gen)
+            train_g.GRAPHS = False
+            img_e, g_e, g2_e = one(G2, wp_cpu, tgt, twice=it == 4)
+            train_g.GRAPHS = True
+            img_g, g_g, g2_g = one(G, wp_cpu, tgt, twice=it == 4)
+            st = G.synthesis.__dict__["_train_graph"]
+            assert (st.fwd is not None) == (it >= 2) and not st.failed
+            assert rel(img_g, img_e) < 1e-6
+            assert rel(g_g, g_e) < 1e-5
+            if g2_e is not None:
+                assert rel(g2_g, g2_e) < 1e-5 and rel(g2_g, 2 * g_e) < 1e-5
+        assert st.bwd is not None
+        # two passes alive, backward through the older one: refused, not wrong
+        wp_a = fx["wp"].cuda().requires_grad_(True)
+        img_a = G.synthesis(wp_a)["image"]
+        img_b = G.synthesis(fx["wp"].cuda().requires_grad_(True))["image"]
+        with pytest.raises(RuntimeError, match="overwritten by a later"):
+            img_a.sum().backward()
+        img_b.sum().backward()
+        # new weights: the graphs are dropped and re-captured from the live parameters
+        with torch.no_grad():
+            for Gm in (G, G2):
+                Gm.synthesis.layer1.bias.add_(0.25)
+        for it in range(4):
+            wp_cpu = fx["wp"] + 0.3 * torch.randn(shape, generator=gen)
+            tgt = torch.randn(fx["image"].shape, generator=gen)
+            train_g.GRAPHS = False
+            img_e, g_e, _ = one(G2, wp_cpu, tgt)
+            train_g.GRAPHS = True
+            img_g, g_g, _ = one(G, wp_cpu, tgt)
+            assert rel(img_g, img_e) < 1e-6 and rel(g_g, g_e) < 1e-5
+        assert G.synthesis.__dict__["_train_graph"].fwd is not None
+    finally:
+        train_g.GRAPHS = False
+
+
 def test_fused_synthesis_matches_reference_gradient():
     import model.stylegan2_generator as SG
     assert SG.FUSED_TRAIN

@@ -39,6 +39,8 @@ def main():
                     help="ours: where the encoder's per-block noise is drawn.  'reference' = on the CPU generator then copied, "
                          "as upstream (E.py:60,73): the same stream as the reference arm, used for the MSE comparison; "
                          "'device' = on the GPU (no 11 MB of CPU randn + H2D per encoder pass), used for the timing")
+    ap.add_argument("--graphs", action="store_true",
+                    help="ours: CUDA-graph replay of the synthesis node (dge_b200.train_g.GRAPHS, the DGE_TRAIN_GRAPHS=1 switch)")
     a = ap.parse_args()
     sys.path.insert(0, ROOT)
     if a.impl == "reference":
@@ -78,6 +80,9 @@ def main():
     G, E = G.to(dev), E.to(dev)
     if a.impl == "ours":
         E.set_noise_mode(a.noise)
+        if a.graphs:
+            from dge_b200 import train_g
+            train_g.GRAPHS = True
     e_state = {k: v.detach().clone() for k, v in E.state_dict().items()}
     if a.impl == "ours":
         import lpips
@@ -135,7 +140,7 @@ def main():
             mse = info[0][0]
         return mse
 
-    one_image(0, 2)                                       # warm-up (allocator, caches, cuDNN heuristics)
+    one_image(0, 5 if a.graphs else 2)                    # warm-up (allocator, caches, cuDNN heuristics, graph capture)
     torch.cuda.synchronize()
     torch.cuda.reset_peak_memory_stats()
     prof = None
@@ -166,7 +171,7 @@ def main():
         pstats.Stats(prof, stream=buf).sort_stats("tottime").print_stats(40)
         print(buf.getvalue(), file=sys.stderr)
     ms_it = wall / (a.images * a.iterations) * 1e3
-    out = {"impl": a.impl, "encoder": "E_Blur.BE" if a.encoder == "blur" else "E.BE", "encoder_noise": a.noise if a.impl == "ours" else "reference", "workload": f"configs[4]: embedding_img.py:74-128 loop, StyleGAN2-{a.res} synthesis + "
+    out = {"impl": a.impl, "encoder": "E_Blur.BE" if a.encoder == "blur" else "E.BE", "encoder_noise": a.noise if a.impl == "ours" else "reference", "graphs": bool(a.graphs and a.impl == "ours"), "workload": f"configs[4]: embedding_img.py:74-128 loop, StyleGAN2-{a.res} synthesis + "
                                        f"BE({startf},{layers}), batch 1, synthetic images G(z_i), seeds 30000+i",
            "images": a.images, "iterations_per_image": a.iterations, "ms_per_iteration": ms_it,
            "s_per_image_measured": wall / a.images, "s_per_image_at_1500_iterations": ms_it * 1.5,
