@@ -18,12 +18,10 @@ and finally ONE launch (sg2_prep_bwd, the transpose of the forward's sg2_prep) t
 (style affine :872-877, demodulation :867-870, ToRGB modulation :462-474): every layer's sums land in one arena whose
 offsets the kernel's item table knows.  `K` is the kernel namespace (see train_e.py).
 """
-import os
-import warnings
-
 import torch
 from torch.autograd.function import once_differentiable
 
+from . import graphs
 from . import ops
 
 K = ops
@@ -152,33 +150,7 @@ def _run_backward(S, saved, d_image):
     return K.sg2_prep_bwd(S, prep, layers, outputs, arena, offs, const_off, n)
 
 
-# ------------------------------------------------------------------------------------------------
-# CUDA-graph replay of the node (at batch 1 the inversion loop is bound by the host's ~70 + ~75 launch calls
-# per pass, not by the GPU).  Opt-in: `DGE_TRAIN_GRAPHS=1` in the environment, or `train_g.GRAPHS = True`.
-#
-# After `_GRAPH_WARMUP` eager passes of one configuration (module, batch, planes, weights epoch) the forward chain is
-# captured into a CUDA graph over a private memory pool, and the first backward after that into a second graph over the
-# same pool; later passes copy `wp` / `d image` into the graphs' static inputs, replay, and hand out CLONES of the static
-# outputs, so nothing the caller holds aliases graph memory.  The saved activations live in the pool and are overwritten
-# by the next forward replay: a backward through an OLDER pass than the latest one (two synthesis passes alive, backward
-# through the first) cannot be served and raises -- that pattern needs GRAPHS = False.  `retain_graph=True` + a second
-# backward of the latest pass (E_align_s2.py:205,220; embedding_img.py:100-128) replays the same backward graph.
-# `randomize_noise=True` (a CPU draw per layer, :912-913) and parameters that changed since the capture fall back to /
-# re-capture the eager chain.  Any failure while capturing disables the graphs for that module with a warning: the eager
-# chain is always the fallback, never a different result.
-# ------------------------------------------------------------------------------------------------
-GRAPHS = os.environ.get('DGE_TRAIN_GRAPHS', '0') == '1'
-_GRAPH_WARMUP = 2
-
-
-class _GraphState:
-    def __init__(self, key):
-        self.key, self.calls, self.gen = key, 0, 0
-        self.failed = False
-        self.fwd = self.bwd = None
-        self.wp_in = self.outs = self.saved = self.d_image_in = self.d_wp = None
-
-
+# CUDA-graph replay of the node: dge_b200/graphs.py (opt-in).  slot = 'synthesis'; key = wp shape, planes, weights epoch.
 def _graph_key(S, wp32):
     srcs = S.__dict__.get('_train_graph_srcs')
     if srcs is None:
@@ -186,81 +158,23 @@ def _graph_key(S, wp32):
     return (tuple(wp32.shape), wp32.device.index, S.layer0.planes, K.weight_key(*srcs))
 
 
-def _graph_state(S, wp32):
-    key = _graph_key(S, wp32)
-    st = S.__dict__.get('_train_graph')
-    if st is None or st.key != key:
-        st = S.__dict__['_train_graph'] = _GraphState(key)     # new shapes / weights: start over (drops the old pool)
-    return st
-
-
 class _SynthesisFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, wp32, S, randomize_noise):
         ctx.S = S
-        st = None
-        if GRAPHS and K is ops and wp32.is_cuda and not randomize_noise:
-            st = _graph_state(S, wp32)
-            if st.failed:
-                st = None
-        if st is not None and st.fwd is None and st.calls >= _GRAPH_WARMUP:
-            try:
-                torch.cuda.synchronize()
-                st.wp_in = wp32.detach().clone()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    st.outs, st.saved = _run_forward(S, st.wp_in, False)
-                st.fwd = g
-            except Exception as exc:  # noqa: BLE001 -- the eager chain is the fallback
-                warnings.warn(f'dge_b200 train_g: CUDA-graph capture of the synthesis forward failed ({exc!r}); '
-                              'running eagerly')
-                st.failed, st.fwd = True, None
-                torch.cuda.synchronize()
-                st = None
-        if st is not None and st.fwd is not None:
-            st.wp_in.copy_(wp32)
-            st.fwd.replay()
-            st.gen += 1
-            ctx.graph, ctx.gen = st, st.gen
-            outs = tuple(o.clone() for o in st.outs)
-        else:
-            if st is not None:
-                st.calls += 1
-            ctx.graph = None
-            outs, ctx.saved = _run_forward(S, wp32, randomize_noise)
+        # CPU noise draws (randomize_noise, :912-913) cannot be captured
+        outs, ctx.handle = graphs.forward(S, 'synthesis', _graph_key(S, wp32) if graphs.GRAPHS else None, (wp32,),
+                                          lambda wp: _run_forward(S, wp, randomize_noise), 'train_g (synthesis)',
+                                          enabled=K is ops and wp32.is_cuda and not randomize_noise)
         ctx.mark_non_differentiable(*outs[1:])
         return outs
 
     @staticmethod
     @once_differentiable
     def backward(ctx, d_image, *_unused):
-        S, st = ctx.S, ctx.graph
-        if st is None:
-            return _run_backward(S, ctx.saved, d_image), None, None
-        if ctx.gen != st.gen:
-            raise RuntimeError(
-                'dge_b200 train_g: backward through a synthesis pass whose saved activations were overwritten by a later '
-                'pass (CUDA-graph mode keeps ONE pass alive); set dge_b200.train_g.GRAPHS = False / unset '
-                'DGE_TRAIN_GRAPHS for this pattern')
-        if st.failed:
-            return _run_backward(S, st.saved, d_image), None, None
-        if st.bwd is None:
-            try:
-                st.d_image_in = d_image.detach().contiguous().float().clone()
-                torch.cuda.synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=st.fwd.pool()):
-                    st.d_wp = _run_backward(S, st.saved, st.d_image_in)
-                st.bwd = g
-            except Exception as exc:  # noqa: BLE001 -- this pass's activations are intact: finish it eagerly
-                warnings.warn(f'dge_b200 train_g: CUDA-graph capture of the synthesis backward failed ({exc!r}); '
-                              'running eagerly')
-                st.failed = True
-                torch.cuda.synchronize()
-                return _run_backward(S, st.saved, d_image), None, None
-        st.d_image_in.copy_(d_image)
-        st.bwd.replay()
-        return st.d_wp.clone(), None, None
+        S = ctx.S
+        d_wp = graphs.backward(ctx.handle, (d_image,), lambda saved, g: _run_backward(S, saved, g), 'train_g (synthesis)')
+        return d_wp, None, None
 
 
 def synthesis_forward(S, wp, randomize_noise=False):

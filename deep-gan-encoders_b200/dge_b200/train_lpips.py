@@ -14,6 +14,7 @@ oracle/lpips.py.
 import torch
 from torch.autograd.function import once_differentiable
 
+from . import graphs
 from . import ops
 
 K = ops
@@ -72,52 +73,74 @@ def _forward_chain(model, in0, in1, planes, keep_all=True):
     return out, saved
 
 
+def _backward_chain(model, planes, n, saved, go, want):
+    """d distance [n] -> (d in0 | None, d in1 | None) from the saved conv outputs."""
+    fwd, bwd, bias, lin, _ = _operands(model, planes)
+    go = go.reshape(n).contiguous().float()
+    sl = model.scaling_layer
+    grads = [None, None]
+    # tap gradients for both halves in one launch per tap
+    tap_idx = [sum(len(v) for v in _VGG[:k + 1]) - 1 for k in range(5)]
+    tap_g = [K.lpips_dist_bwd(saved[ti], lin[k], go, want[0], want[1]) for k, ti in enumerate(tap_idx)]
+    for half in (0, 1):
+        if not want[half]:
+            continue
+
+        def view(t):                 # this half of a saved [2n, ...] tensor (batch-major layouts: a contiguous slice)
+            if isinstance(t, K.F32B):
+                return K.F32B.wrap(t.t[half * n:(half + 1) * n], n, t.c, t.h, t.w)
+            return K.Act.wrap(t.t[half * n:(half + 1) * n], n, t.c, t.h, t.w, t.planes)
+
+        g_in = None                  # gradient w.r.t. the INPUT of the conv above (F32B), flowing down
+        i = len(saved) - 1
+        for k in range(4, -1, -1):
+            for j in range(len(_VGG[k]) - 1, -1, -1):
+                y = view(saved[i])
+                if j == len(_VGG[k]) - 1:       # tap: its own distance gradient + what came back through the pool
+                    d = K.relu_pool_bwd(y, g_same=tap_g[k][half], g_pool=g_in, planes=planes)
+                else:
+                    d = K.relu_pool_bwd(y, g_same=g_in, planes=planes)
+                cin = 16 if i == 0 else (saved[i - 1].c)
+                g_in = K.conv(d, bwd[i], cin, K.CONV_3X3, out_f32b=True)['f32b']
+                i -= 1
+        g = g_in.to_nchw()[:, :3] / sl.scale.to(g_in.t.device)                      # ScalingLayer: (x - shift) / scale
+        grads[half] = g.contiguous()
+    return grads[0], grads[1]
+
+
+def _graph_key(model):
+    srcs = model.__dict__.get('_dge_graph_srcs')
+    if srcs is None:
+        srcs = model.__dict__['_dge_graph_srcs'] = list(model.parameters()) + list(model.buffers())
+    return K.weight_key(*srcs)
+
+
 class _LpipsFn(torch.autograd.Function):
+    """CUDA-graph replay (dge_b200/graphs.py, opt-in): one slot per (input shapes, which image needs a gradient) -- the three
+    `space_loss` calls of an iteration pool to 256x256, 256x192 and 176x176 (training_utils.py:81-84), so each has its own."""
+
     @staticmethod
     def forward(ctx, in0, in1, model, planes):
         n = in0.shape[0]
-        out, saved = _forward_chain(model, in0, in1, planes)
-        ctx.model, ctx.planes, ctx.n = model, planes, n
-        ctx.saved = saved
+        want = (ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        ctx.model, ctx.planes, ctx.n, ctx.want = model, planes, n, want
+        slot = ('lpips', tuple(in0.shape), tuple(in1.shape), in0.dtype, in1.dtype, in0.device.index, planes, want)
+
+        def fwd(a, b):
+            out, saved = _forward_chain(model, a, b, planes)
+            return (out,), saved
+
+        (out,), ctx.handle = graphs.forward(model, slot, _graph_key(model) if graphs.GRAPHS else None, (in0, in1), fwd,
+                                            'train_lpips', enabled=K is ops and in0.is_cuda)
         return out.view(n, 1, 1, 1)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, go):
-        n, planes = ctx.n, ctx.planes
-        fwd, bwd, bias, lin, _ = _operands(ctx.model, planes)
-        want = (ctx.needs_input_grad[0], ctx.needs_input_grad[1])
-        go = go.reshape(n).contiguous().float()
-        saved = ctx.saved
-        sl = ctx.model.scaling_layer
-        grads = [None, None]
-        # tap gradients for both halves in one launch per tap
-        tap_idx = [sum(len(v) for v in _VGG[:k + 1]) - 1 for k in range(5)]
-        tap_g = [K.lpips_dist_bwd(saved[ti], lin[k], go, want[0], want[1]) for k, ti in enumerate(tap_idx)]
-        for half in (0, 1):
-            if not want[half]:
-                continue
-
-            def view(t):                 # this half of a saved [2n, ...] tensor (batch-major layouts: a contiguous slice)
-                if isinstance(t, K.F32B):
-                    return K.F32B.wrap(t.t[half * n:(half + 1) * n], n, t.c, t.h, t.w)
-                return K.Act.wrap(t.t[half * n:(half + 1) * n], n, t.c, t.h, t.w, t.planes)
-
-            g_in = None                  # gradient w.r.t. the INPUT of the conv above (F32B), flowing down
-            i = len(saved) - 1
-            for k in range(4, -1, -1):
-                for j in range(len(_VGG[k]) - 1, -1, -1):
-                    y = view(saved[i])
-                    if j == len(_VGG[k]) - 1:       # tap: its own distance gradient + what came back through the pool
-                        d = K.relu_pool_bwd(y, g_same=tap_g[k][half], g_pool=g_in, planes=planes)
-                    else:
-                        d = K.relu_pool_bwd(y, g_same=g_in, planes=planes)
-                    cin = 16 if i == 0 else (saved[i - 1].c)
-                    g_in = K.conv(d, bwd[i], cin, K.CONV_3X3, out_f32b=True)['f32b']
-                    i -= 1
-            g = g_in.to_nchw()[:, :3] / sl.scale.to(g_in.t.device)                      # ScalingLayer: (x - shift) / scale
-            grads[half] = g.contiguous()
-        return grads[0], grads[1], None, None
+        model, planes, n, want = ctx.model, ctx.planes, ctx.n, ctx.want
+        g0, g1 = graphs.backward(ctx.handle, (go,), lambda saved, g: _backward_chain(model, planes, n, saved, g, want),
+                                 'train_lpips')
+        return g0, g1, None, None
 
 
 class _LpipsLinOnlyFn(torch.autograd.Function):
@@ -130,26 +153,39 @@ class _LpipsLinOnlyFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, in0, in1, planes, *lin_w):
         n = in0.shape[0]
-        out, taps = _forward_chain(model, in0, in1, planes, keep_all=False)
-        ctx.n, ctx.taps, ctx.shapes = n, taps, [w.shape for w in lin_w]
+        need = tuple(ctx.needs_input_grad[4:])
+        ctx.n, ctx.shapes, ctx.need = n, [w.shape for w in lin_w], need
+        slot = ('lpips-lin', tuple(in0.shape), tuple(in1.shape), in0.dtype, in1.dtype, in0.device.index, planes, need)
+
+        def fwd(a, b):
+            out, taps = _forward_chain(model, a, b, planes, keep_all=False)
+            return (out,), taps
+
+        (out,), ctx.handle = graphs.forward(model, slot, _graph_key(model) if graphs.GRAPHS else None, (in0, in1), fwd,
+                                            'train_lpips (lin only)', enabled=K is ops and in0.is_cuda)
         return out.view(n, 1, 1, 1)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, go):
-        n = ctx.n
-        go = go.reshape(n, 1).float()
-        grads = []
-        for tap, shape, need in zip(ctx.taps, ctx.shapes, ctx.needs_input_grad[4:]):
-            if not need:
-                grads.append(None)
-                continue
-            f = tap.to_nchw()
-            a, b = f[:n], f[n:]
-            na = a.pow(2).sum(dim=1, keepdim=True).sqrt() + 1e-10         # lpips.normalize_tensor
-            nb = b.pow(2).sum(dim=1, keepdim=True).sqrt() + 1e-10
-            s = (a / na - b / nb).pow(2).mean(dim=(2, 3))                 # [n, C]
-            grads.append((go * s).sum(dim=0).reshape(shape))
+        n, shapes, need = ctx.n, ctx.shapes, ctx.need
+
+        def bwd(taps, go):
+            go = go.reshape(n, 1).float()
+            grads = []
+            for tap, shape, nd in zip(taps, shapes, need):
+                if not nd:
+                    grads.append(None)
+                    continue
+                f = tap.to_nchw()
+                a, b = f[:n], f[n:]
+                na = a.pow(2).sum(dim=1, keepdim=True).sqrt() + 1e-10         # lpips.normalize_tensor
+                nb = b.pow(2).sum(dim=1, keepdim=True).sqrt() + 1e-10
+                s = (a / na - b / nb).pow(2).mean(dim=(2, 3))                 # [n, C]
+                grads.append((go * s).sum(dim=0).reshape(shape))
+            return tuple(grads)
+
+        grads = graphs.backward(ctx.handle, (go,), bwd, 'train_lpips (lin only)')
         return (None, None, None, None, *grads)
 
 

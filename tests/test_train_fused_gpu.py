@@ -350,13 +350,13 @@ def test_sg2_prep_bwd_kernel():
 
 
 def test_synthesis_node_cuda_graph_replay_matches_eager():
-    """`train_g.GRAPHS` (opt-in, DGE_TRAIN_GRAPHS=1): after two eager passes the synthesis node replays CUDA graphs over static
+    """`dge_b200.graphs.GRAPHS` (opt-in, DGE_TRAIN_GRAPHS=1): after two eager passes the synthesis node replays CUDA graphs over static
     buffers.  Same kernels in the same order: images and d wp equal up to the order of the fp32 atomics of the ToRGB / style
     reductions; `retain_graph` + a second backward replays; a backward through an overwritten pass raises; changed weights
     re-capture."""
     import copy
     import model.stylegan2_generator as SG
-    from dge_b200 import train_g
+    from dge_b200 import graphs
     fx = torch.load(os.path.join(GOLD, "sg2_res32.pt"))
     G = SG.StyleGAN2Generator(**fx["config"])
     G.load_state_dict(fx["state_dict"], strict=True)
@@ -377,16 +377,16 @@ def test_synthesis_node_cuda_graph_replay_matches_eager():
             return img.detach(), g1, wp.grad.clone()
         return img.detach(), g1, None
 
-    assert not train_g.GRAPHS
+    assert not graphs.GRAPHS
     try:
         for it in range(6):
             wp_cpu = fx["wp"] + 0.3 * torch.randn(shape, generator=gen)
             tgt = torch.randn(fx["image"].shape, generator=gen)
-            train_g.GRAPHS = False
+            graphs.GRAPHS = False
             img_e, g_e, g2_e = one(G2, wp_cpu, tgt, twice=it == 4)
-            train_g.GRAPHS = True
+            graphs.GRAPHS = True
             img_g, g_g, g2_g = one(G, wp_cpu, tgt, twice=it == 4)
-            st = G.synthesis.__dict__["_train_graph"]
+            st = G.synthesis.__dict__["_dge_graphs"]["synthesis"]
             assert (st.fwd is not None) == (it >= 2) and not st.failed
             assert rel(img_g, img_e) < 1e-6
             assert rel(g_g, g_e) < 1e-5
@@ -407,14 +407,56 @@ def test_synthesis_node_cuda_graph_replay_matches_eager():
         for it in range(4):
             wp_cpu = fx["wp"] + 0.3 * torch.randn(shape, generator=gen)
             tgt = torch.randn(fx["image"].shape, generator=gen)
-            train_g.GRAPHS = False
+            graphs.GRAPHS = False
             img_e, g_e, _ = one(G2, wp_cpu, tgt)
-            train_g.GRAPHS = True
+            graphs.GRAPHS = True
             img_g, g_g, _ = one(G, wp_cpu, tgt)
             assert rel(img_g, img_e) < 1e-6 and rel(g_g, g_e) < 1e-5
-        assert G.synthesis.__dict__["_train_graph"].fwd is not None
+        assert G.synthesis.__dict__["_dge_graphs"]["synthesis"].fwd is not None
     finally:
-        train_g.GRAPHS = False
+        graphs.GRAPHS = False
+
+
+def test_lpips_nodes_cuda_graph_replay_matches_eager():
+    """The fused LPIPS node and its lin-weights-only sibling under `dge_b200.graphs.GRAPHS`: one replay slot per input
+    shape (the three space_loss calls of an iteration pool to different sizes), results and gradients as the eager node."""
+    import lpips
+    from dge_b200 import graphs
+    lp = lpips.LPIPS(net="vgg", pretrained=False, pnet_rand=True, verbose=False).cuda()
+    gen = torch.Generator().manual_seed(3)
+    shapes = [(2, 3, 64, 64), (2, 3, 64, 48)]
+
+    def one(shape, detach):
+        a = torch.rand(shape, generator=gen) * 2 - 1
+        b = torch.rand(shape, generator=gen) * 2 - 1
+        res = []
+        for on in (False, True):
+            graphs.GRAPHS = on
+            bb = b.cuda().requires_grad_(not detach)
+            for p_ in lp.parameters():
+                p_.grad = None
+            d = lp(a.cuda(), bb)
+            (d.sum() * 3).backward()
+            lin_g = [p_.grad.clone() for p_ in lp.parameters() if p_.grad is not None]
+            res.append((d.detach().clone(), None if detach else bb.grad.clone(), lin_g))
+        (d_e, g_e, l_e), (d_g, g_g, l_g) = res
+        assert rel(d_g, d_e) < 1e-6
+        if not detach:
+            assert rel(g_g, g_e) < 1e-5
+        assert len(l_e) == len(l_g)
+        for x, y in zip(l_g, l_e):      # mean (a/|a| - b/|b|)^2 of near-equal random-VGG features: cancellation amplifies
+            assert rel(x, y) < TOL      # the run-to-run order of the convs' fp32 split-K atomics (observed 4e-5)
+
+    assert not graphs.GRAPHS
+    try:
+        for it in range(5):
+            for shape in shapes:
+                one(shape, detach=False)
+                one(shape, detach=True)
+        table = lp.__dict__["_dge_graphs"]
+        assert len(table) == 4 and all(st.fwd is not None and st.bwd is not None and not st.failed for st in table.values())
+    finally:
+        graphs.GRAPHS = False
 
 
 def test_fused_synthesis_matches_reference_gradient():

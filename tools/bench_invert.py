@@ -40,7 +40,7 @@ def main():
                          "as upstream (E.py:60,73): the same stream as the reference arm, used for the MSE comparison; "
                          "'device' = on the GPU (no 11 MB of CPU randn + H2D per encoder pass), used for the timing")
     ap.add_argument("--graphs", action="store_true",
-                    help="ours: CUDA-graph replay of the synthesis node (dge_b200.train_g.GRAPHS, the DGE_TRAIN_GRAPHS=1 switch)")
+                    help="ours: CUDA-graph replay of the frozen nodes: synthesis pass + LPIPS (dge_b200.graphs.GRAPHS, the DGE_TRAIN_GRAPHS=1 switch)")
     a = ap.parse_args()
     sys.path.insert(0, ROOT)
     if a.impl == "reference":
@@ -81,8 +81,8 @@ def main():
     if a.impl == "ours":
         E.set_noise_mode(a.noise)
         if a.graphs:
-            from dge_b200 import train_g
-            train_g.GRAPHS = True
+            from dge_b200 import graphs
+            graphs.GRAPHS = True
     e_state = {k: v.detach().clone() for k, v in E.state_dict().items()}
     if a.impl == "ours":
         import lpips
