@@ -19,6 +19,7 @@ tests swap it for a torch emulation of the same C-ABI functions to check the cha
 import torch
 from torch.autograd.function import once_differentiable
 
+from . import graphs
 from . import ops
 
 K = ops          # kernel namespace (tests/emu_ops.py replaces it on the CPU)
@@ -27,11 +28,17 @@ GA, GB = 0.111, 0.889          # E.py:84
 SLOPE = 0.2                    # E.py:62,75; net.py:239
 
 
+def _capturing():
+    return K is ops and torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+
+
 def _packed(w, planes, dgrad=False):
     """Packed forward / data-gradient operand of a conv weight, reused until the weight changes (ops.weight_key: an
     optimiser step retires it).  One iteration of the inversion loop runs the encoder twice on the same weights, and
     the two backward passes of an iteration straddle a step.  The cache lives ON the parameter object, so it dies with
     it (a recycled device address can never alias another model's weights)."""
+    if _capturing():                 # a replayed chain packs from the LIVE parameter on every replay (graphs.py)
+        return K.pack_conv_weight_dgrad(w, planes=planes) if dgrad else K.pack_conv_weight(w, planes=planes)
     cache = w.__dict__.setdefault('_dge_packed', {})
     slot = (planes, dgrad, K is ops)
     key = K.weight_key(w)
@@ -96,13 +103,16 @@ def _dw3_from_s2d(dws, c):
 def _packed_strided(w, planes, dgrad):
     """Forward (16-tap DOWN4X4S2) / data-gradient (3x3 over space-to-depth) operands of a `transform_kernel` conv, cached
     on the parameter like `_packed`."""
+    wd = w.detach()
+    if _capturing():
+        return K.pack_conv_weight_dgrad(_w_s2d(wd).contiguous(), planes=planes) if dgrad else \
+            K.pack_conv_weight(_k4(wd).contiguous(), planes=planes)
     cache = w.__dict__.setdefault('_dge_packed', {})
     slot = (planes, 's2d-dgrad' if dgrad else 'down4', K is ops)
     key = K.weight_key(w)
     hit = cache.get(slot)
     if hit is not None and hit[0] == key:
         return hit[1]
-    wd = w.detach()
     op = K.pack_conv_weight_dgrad(_w_s2d(wd).contiguous(), planes=planes) if dgrad else \
         K.pack_conv_weight(_k4(wd).contiguous(), planes=planes)
     cache[slot] = (key, op)
@@ -142,143 +152,186 @@ class _FromRGBFn(torch.autograd.Function):
         return d_img, dw, db, None
 
 
+def _be_fwd(x_t, pre_style, pre_mr, w1, w2, w3, b3, nw1, b1, nw2, b2, cfg):
+    """Forward kernel chain of one BEBlock -> ((out F32B tensor, style1, style2), saved tensors, meta)."""
+    has_last, planes, eps1, eps2, noise1, noise2 = cfg[:6]
+    blur = cfg[6] if len(cfg) > 6 else None        # E_Blur: 'strided' (transform_kernel conv_2) / 'plain' / None (E.py)
+    x = _f32b(x_t)
+    n, c, h, w = x.n, x.c, x.h, x.w
+    cout = w2.shape[0] if has_last else (w3.shape[0] if w3 is not None else c)
+    if pre_style is not None:
+        style1, mr1 = pre_style, pre_mr
+    else:
+        style1, mr1 = K.instance_stats(x, eps1)                                            # E.py:51-53 + IN stats
+    rp = None
+    if has_last and w3 is not None:
+        xn, rp = K.instance_norm_pool(x, mr1, planes=planes)                               # :58 and :78
+    else:
+        xn, _ = K.instance_norm(x, mr1, planes=planes)                                     # :58
+    y1 = K.conv(xn, _packed(w1, planes), c, K.CONV_3X3, noise=noise1, noise_batched=True,
+                noise_w=nw1.detach().reshape(-1), bias=b1.detach().reshape(-1), slope=SLOPE, out_f32b=True)['f32b']
+    style2, mr2 = K.instance_stats(y1, eps2)                                               # :64-66
+    y2 = None
+    if has_last:
+        if blur:
+            y1n = K.instance_norm_blur(y1, mr2, s2d=blur == 'strided', planes=planes)      # E_Blur.py:69-71
+        else:
+            y1n, _ = K.instance_norm(y1, mr2, planes=planes)                               # :69
+        # training keeps the activated conv_2 output before the pool / blend: its sign is the leaky-ReLU mask
+        if blur == 'strided':                                                              # E_Blur.py:72 (half size)
+            y2 = K.conv(y1n, _packed_strided(w2, planes, False), cout, K.CONV_DOWN4X4S2, noise=noise2,
+                        noise_batched=True, noise_w=nw2.detach().reshape(-1), bias=b2.detach().reshape(-1),
+                        slope=SLOPE, out_f32b=True)['f32b']
+        else:
+            y2 = K.conv(y1n, _packed(w2, planes), cout, K.CONV_3X3, noise=noise2, noise_batched=True,
+                        noise_w=nw2.detach().reshape(-1), bias=b2.detach().reshape(-1), slope=SLOPE,
+                        out_f32b=True)['f32b']                                              # :72-75
+        y2_pool = blur != 'strided'
+        if w3 is not None:
+            out = K.conv(rp, _packed(w3, planes), cout, K.CONV_1X1, bias=b3.detach(),
+                         blend_src=y2, blend_pool=y2_pool, blend_a=GA, blend_b=GB, out_f32b=True)['f32b']   # :76-84
+        else:
+            out = K.blend(y2, x, GA, GB, pool=3 if y2_pool else 2)
+    else:
+        y1n = None
+        _, y1n_f = K.instance_norm(y1, mr2, out_act=False, out_f32b=True)                  # :69
+        if w3 is not None:
+            rp = K.f32b_to_act(x, planes)
+            out = K.conv(rp, _packed(w3, planes), cout, K.CONV_1X1, bias=b3.detach(),
+                         blend_src=y1n_f, blend_pool=False, blend_a=GA, blend_b=GB, out_f32b=True)['f32b']
+        else:
+            out = K.blend(y1n_f, x, GA, GB, pool=False)
+    meta = {'cfg': (has_last, planes, (n, c, h, w), cout), 'blur': blur,
+            'has': (w3 is not None, y1n is not None, rp is not None, y2 is not None)}
+    saved = [x_t, mr1, style1, xn.t, y1.t, mr2, style2, noise1, w1]
+    if has_last:
+        saved += [y1n.t, y2.t, noise2, w2]
+    if w3 is not None:
+        saved += [rp.t, w3]
+    s1 = style1.clone() if pre_style is not None else style1
+    return (out.t, s1, style2), saved, meta
+
+
+def _be_bwd(meta, sv, d_out_t, d_style1, d_style2):
+    """Backward kernel chain of one BEBlock -> (d x, d conv_1.w, d conv_2.w, d conv_3.w, d conv_3.b, d noise_weight_1,
+    d bias_1, d noise_weight_2, d bias_2); entries of absent parameters are None."""
+    has_last, planes, (n, c, h, w), cout = meta['cfg']
+    has_w3 = meta['has'][0]
+    sv = list(sv)
+    x_t, mr1, style1, xn_t, y1_t, mr2, style2, noise1, w1 = sv[:9]
+    p = 9
+    if has_last:
+        y1n_t, y2_t, noise2, w2 = sv[p:p + 4]
+        p += 4
+    if has_w3:
+        rp_t, w3 = sv[p:p + 2]
+    x, y1 = _f32b(x_t), _f32b(y1_t)
+    xn = K.Act.wrap(xn_t, n, c, h, w, planes)
+    d_out = _f32b(d_out_t.contiguous())
+    dw2 = dnw2 = db2 = dw3 = db3 = None
+    blur = meta['blur']
+    if has_last and blur == 'strided':
+        # conv_2 ran at stride 2: y2 and d_out share a size, so the head is a scaled leaky-ReLU mask (no pool) ...
+        y2 = _f32b(y2_t)
+        ga_tab = torch.zeros((n, cout, 2), dtype=torch.float32, device=mr2.device)             # (mean, rstd) = (0, GA)
+        ga_tab[:, :, 1] = GA
+        zeros = torch.zeros((n, cout, 2), dtype=torch.float64, device=mr2.device)
+        dy2, s = K.in_bwd_apply(d_out, y2, ga_tab, None, None, zeros, 1, noise=noise2, slope=SLOPE, planes=planes)
+        db2, dnw2 = s[0].view(1, -1, 1, 1), s[1].view(1, -1, 1, 1)
+        dres = None
+        if has_w3:
+            dres = K.scale_f32b(d_out, GB, to_act=True, planes=planes)
+            db3 = GB * K.f32b_channel_sums(d_out)
+        # ... and its gradients are those of a 3x3 conv over the space-to-depth operand the forward kept
+        xs = K.Act.wrap(y1n_t, n, 4 * c, h // 2, w // 2, planes)
+        dws = K.conv_wgrad(dy2, xs, 3)
+        dw2 = _dw3_from_s2d(dws, c)
+        g1 = _depth_to_space(K.conv(dy2, _packed_strided(w2, planes, True), 4 * c, K.CONV_3X3, out_f32b=True)['f32b'])
+        del dy2
+        g1 = K.sg1_post(g1, 0, n, c, h, w, slope=1.0)                                     # blur^T = blur (:71)
+    elif has_last:
+        y2 = _f32b(y2_t)
+        dy2, dres, s = K.be_head_bwd(d_out, y2, noise2, GA, GB, SLOPE, want_dres=has_w3, planes=planes)
+        db2, dnw2 = s[0].view(1, -1, 1, 1), s[1].view(1, -1, 1, 1)
+        if has_w3:
+            db3 = s[2]
+        dw2 = K.conv_wgrad(dy2, K.Act.wrap(y1n_t, n, c, h, w, planes), 3)
+        g1 = K.conv(dy2, _packed(w2, planes, True), c, K.CONV_3X3, out_f32b=True)['f32b']
+        del dy2
+        if blur:
+            g1 = K.sg1_post(g1, 0, n, c, h, w, slope=1.0)                                 # blur^T = blur (E_Blur.py:71)
+    else:
+        g1 = K.scale_f32b(d_out, GA)                       # out = GA * IN_2(y1) + GB * residual  (E.py:69,84)
+        dres = None
+        if has_w3:
+            dres = K.scale_f32b(d_out, GB, to_act=True, planes=planes)
+            db3 = GB * K.f32b_channel_sums(d_out)
+    # IN_2 + the style (mean, std) of y1 + lrelu' of conv_1's activation  ->  operand of conv_1's gradients
+    st2 = K.in_bwd_stats(g1, y1, mr2)
+    dy1, s = K.in_bwd_apply(g1, y1, mr2, style2, d_style2, st2, 1, noise=noise1, slope=SLOPE, planes=planes)
+    db1, dnw1 = s[0].view(1, -1, 1, 1), s[1].view(1, -1, 1, 1)
+    del g1
+    dw1 = K.conv_wgrad(dy1, xn, 3)
+    g0 = K.conv(dy1, _packed(w1, planes, True), c, K.CONV_3X3, out_f32b=True)['f32b']
+    del dy1
+    # residual branch (E.py:78-84)
+    if has_w3:
+        rh, rw = (h // 2, w // 2) if has_last else (h, w)
+        dw3 = K.conv_wgrad(dres, K.Act.wrap(rp_t, n, c, rh, rw, planes), 1)
+        d_rp = K.conv(dres, _packed(w3, planes, True), c, K.CONV_1X1, out_f32b=True)['f32b']
+        rscale = 0.25 if has_last else 1.0
+    else:
+        d_rp, rscale = d_out, GB * (0.25 if has_last else 1.0)
+    st1 = K.in_bwd_stats(g0, x, mr1)
+    d_x = K.in_bwd_apply(g0, x, mr1, style1, d_style1, st1, 0, res=d_rp, rscale=rscale, res_pool=has_last)
+    return d_x.t, dw1, dw2, dw3, db3, dnw1, db1, dnw2, db2
+
+
 class _BEBlockFn(torch.autograd.Function):
     """One BEBlock (E.py:50-85).  Inputs: x (F32B tensor), optional precomputed (style1, mean_rstd1), the block's
-    parameters.  Outputs: (out F32B tensor, style1 [N, 2C], style2 [N, 2C])."""
+    parameters.  Outputs: (out F32B tensor, style1 [N, 2C], style2 [N, 2C]).
+
+    CUDA-graph replay (dge_b200/graphs.py, opt-in): unlike the frozen nodes this one's parameters change between replays
+    (LREQAdam steps twice per iteration, and the two backward passes of an iteration straddle a step), so the captured
+    chains pack their conv operands from the LIVE parameters on every replay (`_packed` under capture) and the slot key is
+    the parameters' storage, not their values.  An iteration of the inversion loop keeps TWO encoder passes alive
+    (`E(imgs1)`, `E(imgs2)`: embedding_img.py:86,88), so every block alternates between two slots; a third pass alive at
+    once is refused at its backward like any overwritten pass."""
 
     @staticmethod
-    def forward(ctx, x_t, pre_style, pre_mr, w1, w2, w3, b3, nw1, b1, nw2, b2, cfg):
-        has_last, planes, eps1, eps2, noise1, noise2 = cfg[:6]
-        blur = cfg[6] if len(cfg) > 6 else None        # E_Blur: 'strided' (transform_kernel conv_2) / 'plain' / None (E.py)
-        x = _f32b(x_t)
-        n, c, h, w = x.n, x.c, x.h, x.w
-        cout = w2.shape[0] if has_last else (w3.shape[0] if w3 is not None else c)
-        if pre_style is not None:
-            style1, mr1 = pre_style, pre_mr
-        else:
-            style1, mr1 = K.instance_stats(x, eps1)                                            # E.py:51-53 + IN stats
-        rp = None
-        if has_last and w3 is not None:
-            xn, rp = K.instance_norm_pool(x, mr1, planes=planes)                               # :58 and :78
-        else:
-            xn, _ = K.instance_norm(x, mr1, planes=planes)                                     # :58
-        y1 = K.conv(xn, _packed(w1, planes), c, K.CONV_3X3, noise=noise1, noise_batched=True,
-                    noise_w=nw1.detach().reshape(-1), bias=b1.detach().reshape(-1), slope=SLOPE, out_f32b=True)['f32b']
-        style2, mr2 = K.instance_stats(y1, eps2)                                               # :64-66
-        y2 = None
-        if has_last:
-            if blur:
-                y1n = K.instance_norm_blur(y1, mr2, s2d=blur == 'strided', planes=planes)      # E_Blur.py:69-71
-            else:
-                y1n, _ = K.instance_norm(y1, mr2, planes=planes)                               # :69
-            # training keeps the activated conv_2 output before the pool / blend: its sign is the leaky-ReLU mask
-            if blur == 'strided':                                                              # E_Blur.py:72 (half size)
-                y2 = K.conv(y1n, _packed_strided(w2, planes, False), cout, K.CONV_DOWN4X4S2, noise=noise2,
-                            noise_batched=True, noise_w=nw2.detach().reshape(-1), bias=b2.detach().reshape(-1),
-                            slope=SLOPE, out_f32b=True)['f32b']
-            else:
-                y2 = K.conv(y1n, _packed(w2, planes), cout, K.CONV_3X3, noise=noise2, noise_batched=True,
-                            noise_w=nw2.detach().reshape(-1), bias=b2.detach().reshape(-1), slope=SLOPE,
-                            out_f32b=True)['f32b']                                              # :72-75
-            y2_pool = blur != 'strided'
-            if w3 is not None:
-                out = K.conv(rp, _packed(w3, planes), cout, K.CONV_1X1, bias=b3.detach(),
-                             blend_src=y2, blend_pool=y2_pool, blend_a=GA, blend_b=GB, out_f32b=True)['f32b']   # :76-84
-            else:
-                out = K.blend(y2, x, GA, GB, pool=3 if y2_pool else 2)
-        else:
-            y1n = None
-            _, y1n_f = K.instance_norm(y1, mr2, out_act=False, out_f32b=True)                  # :69
-            if w3 is not None:
-                rp = K.f32b_to_act(x, planes)
-                out = K.conv(rp, _packed(w3, planes), cout, K.CONV_1X1, bias=b3.detach(),
-                             blend_src=y1n_f, blend_pool=False, blend_a=GA, blend_b=GB, out_f32b=True)['f32b']
-            else:
-                out = K.blend(y1n_f, x, GA, GB, pool=False)
-        ctx.cfg = (has_last, planes, (n, c, h, w), cout)
-        ctx.blur = blur
-        ctx.has = (w3 is not None, y1n is not None, rp is not None, y2 is not None)
-        saved = [x_t, mr1, style1, xn.t, y1.t, mr2, style2, noise1, w1]
-        if has_last:
-            saved += [y1n.t, y2.t, noise2, w2]
-        if w3 is not None:
-            saved += [rp.t, w3]
+    def forward(ctx, x_t, pre_style, pre_mr, w1, w2, w3, b3, nw1, b1, nw2, b2, cfg, owner=None):
+        params = (w1, w2, w3, b3, nw1, b1, nw2, b2)
+        if graphs.GRAPHS and owner is not None and K is ops and x_t.is_cuda:
+            noise1, noise2 = cfg[4], cfg[5]
+            has_n2, has_pre = noise2 is not None, pre_style is not None
+            dyn = [x_t, noise1] + ([noise2] if has_n2 else []) + ([pre_style, pre_mr] if has_pre else [])
+
+            def fwd(*d):
+                i = 2 + has_n2
+                cfg2 = tuple(cfg[:4]) + (d[1], d[2] if has_n2 else None) + tuple(cfg[6:])
+                outs, saved, meta = _be_fwd(d[0], d[i] if has_pre else None, d[i + 1] if has_pre else None, *params, cfg2)
+                return outs, (saved, meta)
+
+            rr = owner.__dict__.get('_dge_rr', 0)
+            owner.__dict__['_dge_rr'] = rr + 1
+            slot = ('be', tuple(x_t.shape), has_pre, has_n2, tuple(cfg[:4]), tuple(cfg[6:]), rr % 2)
+            key = tuple(None if p is None else (p.data_ptr(), tuple(p.shape)) for p in params)
+            outs, ctx.handle = graphs.forward(owner, slot, key, dyn, fwd, 'train_e (encoder block)')
+            return outs
+        ctx.handle = None
+        outs, saved, ctx.meta = _be_fwd(x_t, pre_style, pre_mr, *params, cfg)
         ctx.save_for_backward(*saved)
-        s1 = style1.clone() if pre_style is not None else style1
-        return out.t, s1, style2
+        return outs
 
     @staticmethod
     @once_differentiable
     def backward(ctx, d_out_t, d_style1, d_style2):
-        has_last, planes, (n, c, h, w), cout = ctx.cfg
-        has_w3 = ctx.has[0]
-        sv = list(ctx.saved_tensors)
-        x_t, mr1, style1, xn_t, y1_t, mr2, style2, noise1, w1 = sv[:9]
-        p = 9
-        if has_last:
-            y1n_t, y2_t, noise2, w2 = sv[p:p + 4]
-            p += 4
-        if has_w3:
-            rp_t, w3 = sv[p:p + 2]
-        x, y1 = _f32b(x_t), _f32b(y1_t)
-        xn = K.Act.wrap(xn_t, n, c, h, w, planes)
-        d_out = _f32b(d_out_t.contiguous())
-        dw2 = dnw2 = db2 = dw3 = db3 = None
-        blur = ctx.blur
-        if has_last and blur == 'strided':
-            # conv_2 ran at stride 2: y2 and d_out share a size, so the head is a scaled leaky-ReLU mask (no pool) ...
-            y2 = _f32b(y2_t)
-            ga_tab = torch.tensor([0.0, GA], device=mr2.device).expand(n, cout, 2).contiguous()   # (mean, rstd) = (0, GA)
-            zeros = torch.zeros((n, cout, 2), dtype=torch.float64, device=mr2.device)
-            dy2, s = K.in_bwd_apply(d_out, y2, ga_tab, None, None, zeros, 1, noise=noise2, slope=SLOPE, planes=planes)
-            db2, dnw2 = s[0].view(1, -1, 1, 1), s[1].view(1, -1, 1, 1)
-            dres = None
-            if has_w3:
-                dres = K.scale_f32b(d_out, GB, to_act=True, planes=planes)
-                db3 = GB * K.f32b_channel_sums(d_out)
-            # ... and its gradients are those of a 3x3 conv over the space-to-depth operand the forward kept
-            xs = K.Act.wrap(y1n_t, n, 4 * c, h // 2, w // 2, planes)
-            dws = K.conv_wgrad(dy2, xs, 3)
-            dw2 = _dw3_from_s2d(dws, c)
-            g1 = _depth_to_space(K.conv(dy2, _packed_strided(w2, planes, True), 4 * c, K.CONV_3X3, out_f32b=True)['f32b'])
-            del dy2
-            g1 = K.sg1_post(g1, 0, n, c, h, w, slope=1.0)                                     # blur^T = blur (:71)
-        elif has_last:
-            y2 = _f32b(y2_t)
-            dy2, dres, s = K.be_head_bwd(d_out, y2, noise2, GA, GB, SLOPE, want_dres=has_w3, planes=planes)
-            db2, dnw2 = s[0].view(1, -1, 1, 1), s[1].view(1, -1, 1, 1)
-            if has_w3:
-                db3 = s[2]
-            dw2 = K.conv_wgrad(dy2, K.Act.wrap(y1n_t, n, c, h, w, planes), 3)
-            g1 = K.conv(dy2, _packed(w2, planes, True), c, K.CONV_3X3, out_f32b=True)['f32b']
-            del dy2
-            if blur:
-                g1 = K.sg1_post(g1, 0, n, c, h, w, slope=1.0)                                 # blur^T = blur (E_Blur.py:71)
+        if ctx.handle is not None:
+            g = graphs.backward(ctx.handle, (d_out_t, d_style1, d_style2),
+                                lambda sm, a, b, c: _be_bwd(sm[1], sm[0], a, b, c), 'train_e (encoder block)')
         else:
-            g1 = K.scale_f32b(d_out, GA)                       # out = GA * IN_2(y1) + GB * residual  (E.py:69,84)
-            dres = None
-            if has_w3:
-                dres = K.scale_f32b(d_out, GB, to_act=True, planes=planes)
-                db3 = GB * K.f32b_channel_sums(d_out)
-        # IN_2 + the style (mean, std) of y1 + lrelu' of conv_1's activation  ->  operand of conv_1's gradients
-        st2 = K.in_bwd_stats(g1, y1, mr2)
-        dy1, s = K.in_bwd_apply(g1, y1, mr2, style2, d_style2, st2, 1, noise=noise1, slope=SLOPE, planes=planes)
-        db1, dnw1 = s[0].view(1, -1, 1, 1), s[1].view(1, -1, 1, 1)
-        del g1
-        dw1 = K.conv_wgrad(dy1, xn, 3)
-        g0 = K.conv(dy1, _packed(w1, planes, True), c, K.CONV_3X3, out_f32b=True)['f32b']
-        del dy1
-        # residual branch (E.py:78-84)
-        if has_w3:
-            rh, rw = (h // 2, w // 2) if has_last else (h, w)
-            dw3 = K.conv_wgrad(dres, K.Act.wrap(rp_t, n, c, rh, rw, planes), 1)
-            d_rp = K.conv(dres, _packed(w3, planes, True), c, K.CONV_1X1, out_f32b=True)['f32b']
-            rscale = 0.25 if has_last else 1.0
-        else:
-            d_rp, rscale = d_out, GB * (0.25 if has_last else 1.0)
-        st1 = K.in_bwd_stats(g0, x, mr1)
-        d_x = K.in_bwd_apply(g0, x, mr1, style1, d_style1, st1, 0, res=d_rp, rscale=rscale, res_pool=has_last)
-        return d_x.t, None, None, dw1, dw2, dw3, db3, dnw1, db1, dnw2, db2, None
+            g = _be_bwd(ctx.meta, ctx.saved_tensors, d_out_t, d_style1, d_style2)
+        return (g[0], None, None) + tuple(g[1:]) + (None, None)
 
 
 class _F32BToNCHW(torch.autograd.Function):
@@ -334,7 +387,7 @@ def block_forward(block, x_t, pre=None):
     out_t, style1, style2 = _BEBlockFn.apply(
         x_t, pre_style, pre_mr, block.conv_1.weight, block.conv_2.weight if block.has_last_conv else None,
         block.conv_3.weight if has_w3 else None, block.conv_3.bias if has_w3 else None, block.noise_weight_1,
-        block.bias_1, block.noise_weight_2, block.bias_2, cfg)
+        block.bias_1, block.noise_weight_2, block.bias_2, cfg, block)
     lin = torch.nn.functional.linear
     w1 = lin(style1, block.inver_mod1.weight, block.inver_mod1.bias)                           # :54
     w2 = lin(style2, block.inver_mod2.weight, block.inver_mod2.bias)                           # :67

@@ -234,6 +234,86 @@ def test_inference_after_an_optimiser_step_uses_the_new_weights(which):
     assert rel(c1, c_ref) < 2e-4 and rel(w1, w_ref) < 2e-4   # ... and the cached operands followed it
 
 
+@pytest.mark.parametrize("enc", ["E", "E_Blur"])
+def test_encoder_nodes_cuda_graph_replay_follow_the_live_weights(enc):
+    """`dge_b200.graphs.GRAPHS` on the encoder block nodes: two encoder passes alive per iteration (two slots per block),
+    two backward / step pairs per iteration as embedding_img.py:100-128 has them.  The replayed chains must pack their
+    operands from the parameters as they are NOW: after every iteration both models hold the same (updated) weights, and
+    every gradient of the graph-replay model must match the eager model's."""
+    from dge_b200 import graphs
+    from model.utils.custom_adam import LREQAdam
+    if enc == "E":
+        import model.E.E as EM
+    else:
+        import model.E.E_Blur as EM
+    torch.manual_seed(1)
+    E_e = EM.BE(16, 64, 4, 512, 3).cuda()
+    with torch.no_grad():
+        for k, p in E_e.named_parameters():
+            if k.endswith(("bias", "noise_weight_1", "noise_weight_2", "bias_1", "bias_2")):
+                p.copy_(torch.randn_like(p) * 0.1)
+    # (not copy.deepcopy: Parameter.__deepcopy__ drops the `lr_equalization_coef` attribute LREQAdam scales its step with)
+    E_g = EM.BE(16, 64, 4, 512, 3).cuda()
+    E_g.load_state_dict(E_e.state_dict())
+    for m in (E_e, E_g):
+        m.set_noise_mode("device")
+    opts = {id(E_e): LREQAdam(E_e.parameters(), lr=0.02, betas=(0.0, 0.99)),
+            id(E_g): LREQAdam(E_g.parameters(), lr=0.02, betas=(0.0, 0.99))}
+    img = torch.randn(2, 3, 64, 64, device="cuda")
+    # generic upstream gradients (fixed random projections): sums like (w ** 2).mean() send gradients that the instance-norm
+    # Jacobians almost annihilate, and what is left of them is run-to-run rounding of the split-K atomics, not signal
+    r_w, r_c, r_i = None, None, torch.randn(2, 3, 64, 64, device="cuda")
+
+    def iteration(E, it):
+        nonlocal r_w, r_c
+        opt = opts[id(E)]
+        torch.manual_seed(100 + it)
+        const1, w1 = E(img)
+        if r_w is None:
+            r_w, r_c = torch.randn_like(w1), torch.randn_like(const1)
+            torch.manual_seed(100 + it)
+            const1, w1 = E(img)
+        img2 = img + 0.05 * torch.tanh((w1 * r_w).mean(dim=(1, 2))).view(-1, 1, 1, 1) * r_i   # depends on w1
+        const2, w2 = E(img2)
+        opt.zero_grad()
+        ((w1 * r_w).mean() + (const1 * r_c).mean()).backward(retain_graph=True)
+        ga = {k: p.grad.clone() for k, p in E.named_parameters() if p.grad is not None}
+        opt.step()
+        opt.zero_grad()
+        (((w1 - w2) * r_w).mean() + ((const1 - const2) * r_c).mean() + (w2 * r_w.flip(0)).mean()).backward()
+        gb = {k: p.grad.clone() for k, p in E.named_parameters() if p.grad is not None}
+        opt.step()
+        return w1.detach().clone(), w2.detach().clone(), ga, gb
+
+    assert not graphs.GRAPHS
+    try:
+        for it in range(7):
+            graphs.GRAPHS = False
+            r_e = iteration(E_e, it)
+            graphs.GRAPHS = True
+            r_g = iteration(E_g, it)
+            assert rel(r_g[0], r_e[0]) < 1e-4 and rel(r_g[1], r_e[1]) < 1e-4, it
+            for a, b in ((r_g[2], r_e[2]), (r_g[3], r_e[3])):
+                assert set(a) == set(b)
+                for k in b:
+                    assert rel(a[k], b[k]) < TOL, (it, k, rel(a[k], b[k]))
+            with torch.no_grad():                      # same weights again (the two optimisers' states drift by rounding)
+                for pg, pe in zip(E_g.parameters(), E_e.parameters()):
+                    pg.copy_(pe)
+        states = [st for blk in E_g.decode_block for st in blk.__dict__.get("_dge_graphs", {}).values()]
+        assert len(states) == 2 * len(E_g.decode_block)
+        assert all(st.fwd is not None and st.bwd is not None and not st.failed for st in states)
+        # a third pass of the same shape alive at once: its slot is overwritten, its backward refused
+        graphs.GRAPHS = True
+        c_a, w_a = E_g(img)
+        E_g(img)
+        E_g(img)
+        with pytest.raises(RuntimeError, match="overwritten by a later"):
+            (w_a ** 2).mean().backward()
+    finally:
+        graphs.GRAPHS = False
+
+
 # ------------------------------------------------------------------------------------------------
 # generator (dge_b200/train_g.py)
 # ------------------------------------------------------------------------------------------------
@@ -444,8 +524,8 @@ def test_lpips_nodes_cuda_graph_replay_matches_eager():
         if not detach:
             assert rel(g_g, g_e) < 1e-5
         assert len(l_e) == len(l_g)
-        for x, y in zip(l_g, l_e):      # mean (a/|a| - b/|b|)^2 of near-equal random-VGG features: cancellation amplifies
-            assert rel(x, y) < TOL      # the run-to-run order of the convs' fp32 split-K atomics (observed 4e-5)
+        for x, y in zip(l_g, l_e):      # mean (a/|a| - b/|b|)^2 of near-equal random-VGG features (values ~5e-9): cancellation
+            assert rel(x, y) < 2e-2     # amplifies the run-to-run order of the convs' fp32 split-K atomics (seen 4e-5 .. 1.1e-3)
 
     assert not graphs.GRAPHS
     try:
