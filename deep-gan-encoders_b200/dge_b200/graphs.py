@@ -14,6 +14,7 @@ off.  `retain_graph=True` + a second backward of the latest pass (E_align_s2.py:
 the same backward graph.  Any failure while capturing disables the graphs of that slot with a warning: the eager chain is
 always the fallback, never a different result.
 """
+import collections
 import os
 import warnings
 
@@ -21,6 +22,8 @@ import torch
 
 GRAPHS = os.environ.get('DGE_TRAIN_GRAPHS', '0') == '1'
 WARMUP = 2
+MAX_SLOTS = 8       # replay states kept per owner module, least recently used first out: scripts that crop to a new random
+                    # size every iteration (E_align_cropping_s1.py:150-170) would otherwise collect a memory pool per size
 
 
 class State:
@@ -34,10 +37,13 @@ class State:
 
 def state_for(owner, slot, key):
     """The replay state of (owner module, slot); a changed key (new weights) starts over and drops the old pool."""
-    table = owner.__dict__.setdefault('_dge_graphs', {})
+    table = owner.__dict__.setdefault('_dge_graphs', collections.OrderedDict())
     st = table.get(slot)
     if st is None or st.key != key:
         st = table[slot] = State(key)
+    table.move_to_end(slot)
+    while len(table) > MAX_SLOTS:            # a dropped state lives on while a pass that used it still holds its handle
+        table.popitem(last=False)
     return st
 
 
