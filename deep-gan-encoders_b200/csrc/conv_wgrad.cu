@@ -360,8 +360,10 @@ extern "C" int dge_conv_wgrad(const void* dy_act, const void* x_act, float* dw, 
   static int no_xstack = -1;
   if (no_xstack < 0) no_xstack = getenv("DGE_WGRAD_NO_XSTACK") ? 1 : 0;
   if (p.stacked && !no_xstack) {
+    // ... as long as that is at most two CTAs' worth: every Cout block repeats the MMAs over the same x tiles, and from three
+    // blocks on round 1's layout (128 output channels per CTA, taps on N only) issues fewer of them
     for (int r = 40; r >= 8 && !p.xstack; r -= 8)
-      if (cout % r == 0) {
+      if (cout % r == 0 && cout / r <= 2) {
         p.xstack = 1;
         p.R = r;
       }
